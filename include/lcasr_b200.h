@@ -1,0 +1,226 @@
+/*
+ * lcasr_b200 — C ABI of the B200-native (sm_100a) encoder + CTC hot path of
+ * robflynnyh/long-context-asr.
+ *
+ * The reference has no FFI / plugin registry: its boundary is the Python class contract
+ * (SURVEY.md §8b).  This header is what a native binding for that contract binds to.  Every entry
+ * point cites the reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch / C++ types;
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void*; no entry point synchronises the device or the
+ *     stream (exceptions are documented per function), so calls are CUDA-graph capturable;
+ *   - return value: 0 = ok; <0 = LCASR_E_* ; the message is available from lcasr_last_error()
+ *     (thread-local);  nothing is ever thrown across the boundary and there is NO CPU fallback;
+ *   - matrices are row-major; "W[N,K]" weights use the torch.nn.Linear layout (out, in);
+ *   - dtype codes: LCASR_F32 / LCASR_BF16.
+ */
+#ifndef LCASR_B200_H_
+#define LCASR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCASR_ABI_VERSION 1
+
+enum { LCASR_F32 = 0, LCASR_BF16 = 1 };
+enum { LCASR_OK = 0, LCASR_E_BADARG = -1, LCASR_E_UNSUPPORTED = -2, LCASR_E_CUDA = -3, LCASR_E_NOMEM = -4 };
+enum { LCASR_ACT_NONE = 0, LCASR_ACT_GELU_TANH = 1, LCASR_ACT_SILU = 2 };
+enum { LCASR_NORM_LAYERNORM = 0, LCASR_NORM_RMSNORM = 1 };
+enum { LCASR_GEMM_AUTO = 0, LCASR_GEMM_SIMT = 1, LCASR_GEMM_TCGEN05 = 2 };
+enum { LCASR_ATTN_AUTO = 0, LCASR_ATTN_SIMT = 1, LCASR_ATTN_TCGEN05 = 2 };
+
+int lcasr_abi_version(void);
+const char* lcasr_last_error(void);
+/* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
+int64_t lcasr_launch_count(void);
+void lcasr_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Unit operators (one per reference op on the path; used by the parity tests and by ncu)
+ * ---------------------------------------------------------------------------------------- */
+
+/* torch.nn.LayerNorm(d, eps=1e-5) / lcasr RMSNorm (lcasr/components/normalisation.py:30-47,
+ * eps added OUTSIDE the sqrt) over the last dim of x[M,d] (fp32).  Writes any of: out_f32[M,d],
+ * out_lo[M,d] in `lo_dtype` (the GEMM-operand copy).  Replaces PreNorm.norm
+ * (lcasr/components/wrappers.py:14-15), ConformerLayer.norm_out (sconformer_xl.py:371) and
+ * decoder.norm (decoder.py:23). `bias` may be NULL (RMSNorm). In-place (out_f32 == x) is allowed. */
+int lcasr_layernorm(const float* x, const float* weight, const float* bias, int64_t M, int d,
+                    float eps, int kind, float* out_f32, void* out_lo, int lo_dtype, void* stream);
+
+/* ConvSubsampling.conv[0] + SiLU: Conv2d(1->C, 3x3, stride 2, pad 1) on the [B,1,T,F] image
+ * (lcasr/components/subsampling.py:277-290, run at :418).  spec is the model input [B,F,T] fp32
+ * (sconformer_xl.py:185 transposes it); w [C,9] (= weight[C,1,3,3], taps (time,freq) row-major),
+ * out is channels-last [B,T1,F1,C] with T1=(T-1)/2+1, F1=(F-1)/2+1. */
+int lcasr_subsample_conv0(const float* spec, const float* w, const float* b, int B, int F, int64_t T,
+                          int C, void* out, int out_dtype, void* stream);
+
+/* ConvSubsampling depthwise Conv2d(C,C,3x3,stride 2,pad 1,groups=C) (subsampling.py:296-312), no
+ * activation; channels-last in [B,Tin,Fin,C] -> out [B,Tout,Fout,C], same dtype. */
+int lcasr_subsample_dwconv(const void* in, int dtype, const float* w, const float* b, int B,
+                           int64_t Tin, int Fin, int C, void* out, void* stream);
+
+/* out = epilogue(A[M,K] . W[N,K]^T): every dense contraction of the path — nn.Linear / 1x1 Conv
+ * (attention.py:483,487; fused_dense.py:464-470; convolution.py:62-86 pointwise; decoder.py:18-19;
+ * subsampling.py:314-323,374).  A and W share `ab_dtype`; fp32 accumulation.
+ *   y = acc + bias (bias[N] fp32 or NULL);  y = act(y);
+ *   if resid != NULL: out(fp32) = resid[M,N] + alpha * y   (resid may alias out)
+ *   else            : out = y in `out_dtype`.
+ * impl: LCASR_GEMM_TCGEN05 needs ab_dtype == BF16, K % 8 == 0 and 16-byte aligned A/W;
+ *       LCASR_GEMM_AUTO picks tcgen05 for bf16 operands and the SIMT fp32 kernel otherwise. */
+int lcasr_gemm(const void* A, const void* W, int ab_dtype, int64_t M, int N, int K,
+               const float* bias, int act, const float* resid, float alpha, void* out,
+               int out_dtype, int impl, void* stream);
+
+/* fp32 -> compute-dtype copy of n elements (the implicit autocast cast in front of a Linear when
+ * decoder_norm=False, decoder.py:23-24). */
+int lcasr_cast_f32(const float* in, int64_t n, void* out, int out_dtype, void* stream);
+
+/* torch.nn.functional.glu(x, dim=channels) (convolution.py:107): in [M,2d] -> out [M,d],
+ * out[:,j] = in[:,j] * sigmoid(in[:,d+j]). */
+int lcasr_glu(const void* in, int dtype, int64_t M, int d, void* out, void* stream);
+
+/* RotaryPositionalEmbedding.forward (rotary_emb.py:44-57): cos/sin [N, Dh/2] fp32 of
+ * angle = fp32(pos_offset + n) / interp * inv_freq[j]. */
+int lcasr_rope_table(const float* inv_freq, float interp, int64_t pos_offset, int64_t N, int half,
+                     float* cos_out, float* sin_out, void* stream);
+
+/* The qkv split + rotary of Attention.forward (attention.py:485 "b n (h d qkv)", :499-506,
+ * rotary_emb.py:61-73).  qkv [B*N, 3*H*Dh] holds the projection computed with DE-INTERLEAVED
+ * weight rows, i.e. columns are [q(h,dh) | k(h,dh) | v(h,dh)].  Writes q,k [B,N,H,Dh] (rotated;
+ * cos/sin may be NULL = no rotary) and v either [B,N,H,Dh] (v_transposed=0) or [B,H,Dh,Npad]
+ * (v_transposed=1, row pitch Npad >= N, the K-major layout the tcgen05 PV product wants). */
+int lcasr_rope_split(const void* qkv, int dtype, int B, int64_t N, int H, int Dh, const float* cos_t,
+                     const float* sin_t, void* q, void* k, void* v, int v_transposed, int64_t Npad,
+                     void* stream);
+
+/* softmax(q k^T / sqrt(Dh)) v, non-causal, no mask (attention.py:532 flash path / :541 SDPA).
+ * q,k [B,N,H,Dh]; v [B,N,H,Dh] (v_transposed=0) or [B,H,Dh,Npad]; out [B,N,H*Dh]. */
+int lcasr_attention(const void* q, const void* k, const void* v, int dtype, int B, int64_t N, int H,
+                    int Dh, int v_transposed, int64_t Npad, void* out, int impl, void* stream);
+
+/* depthwise Conv1d(k, pad (k-1)/2, groups=d) + bias -> BatchRenorm1d eval affine
+ * ((y-mean)/std*weight+bias, no eps; batchrenorm.py:86-91) -> SiLU  (convolution.py:112-121).
+ * in/out channels-last [B,N,d]; w [d,ksize] fp32. */
+int lcasr_dwconv_brn_silu(const void* in, int dtype, int B, int64_t N, int d, int ksize, const float* w,
+                          const float* b, const float* brn_mean, const float* brn_std,
+                          const float* brn_w, const float* brn_b, void* out, int out_dtype, void* stream);
+
+/* row softmax over V classes (sconformer_xl.py:242): in [M,V] -> out [M,V]. */
+int lcasr_softmax(const void* in, int in_dtype, int64_t M, int V, void* out, int out_dtype, void* stream);
+
+/* F.log_softmax(logits, -1) (decoder.py:25), in place on fp32 logits [M,V], fused with the
+ * per-frame argmax of GreedyCTCDecoder (decoding/greedy.py:19); argmax (int32[M]) may be NULL. */
+int lcasr_log_softmax_argmax(float* logits, int64_t M, int V, int32_t* argmax, void* stream);
+
+/* torch.argmax(emission, dim=-1) (decoding/greedy.py:19) on an fp32 [M,V] tensor; first max wins. */
+int lcasr_argmax_rows(const float* x, int64_t M, int V, int32_t* argmax, void* stream);
+
+/* GreedyCTCDecoder.forward (decoding/greedy.py:19-21): unique_consecutive + drop blank on
+ * per-frame argmax ids [B,N]; lengths[B] (int32, NULL = N). tokens [B,N] int32 (compacted prefix),
+ * n_tokens [B] int32. */
+int lcasr_greedy_collapse(const int32_t* argmax, int B, int64_t N, const int32_t* lengths, int blank,
+                          int32_t* tokens, int32_t* n_tokens, void* stream);
+
+/* torch.nn.CTCLoss(blank, reduction='none') forward (exp/train.py:104,249).  log_probs is
+ * BATCH-major [B,N,V] fp32 (the tensor the model returns; the reference passes its transpose
+ * view).  targets [B,S_max] int64 (padded), input_lengths int32[B], target_lengths int64[B].
+ * nll [B] fp32.  alpha_ws: NULL, or fp32 [B,N,2*S_max+1] to keep alpha for the backward. */
+int lcasr_ctc_loss_fwd(const float* log_probs, int B, int64_t N, int V, const int64_t* targets,
+                       int64_t S_max, const int32_t* input_lengths, const int64_t* target_lengths,
+                       int blank, float* nll, float* alpha_ws, void* stream);
+
+/* gradient of sum_b grad_nll[b]*nll[b] w.r.t. log_probs [B,N,V] (ATen ctc_loss_backward semantics;
+ * frames >= input_length get 0).  alpha_ws from the forward; beta_ws fp32 [B,N,2*S_max+1] scratch. */
+int lcasr_ctc_loss_bwd(const float* log_probs, int B, int64_t N, int V, const int64_t* targets,
+                       int64_t S_max, const int32_t* input_lengths, const int64_t* target_lengths,
+                       int blank, const float* nll, const float* grad_nll, const float* alpha_ws,
+                       float* beta_ws, float* grad, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The model: SCConformerXL.forward (lcasr/models/sconformer_xl.py:162-252), equal-length path
+ * ---------------------------------------------------------------------------------------- */
+
+typedef struct lcasr_config {
+  int32_t abi_version;        /* LCASR_ABI_VERSION */
+  int32_t n_layers, d_model, n_heads, head_dim;
+  int32_t feat_in;            /* 80 */
+  int32_t conv_channels;      /* subsampling_conv_channels */
+  int32_t conv_kernel_size;   /* 9 */
+  int32_t num_classes;        /* vocab_size + 1 */
+  int32_t norm_kind;          /* LCASR_NORM_* (default_norm) */
+  int32_t decoder_norm;       /* decoder_norm kwarg */
+  int32_t use_rotary, self_conditioning, legasee_double_norm, bias_in_ff;
+  int32_t compute_dtype;      /* LCASR_BF16 (tcgen05 path) or LCASR_F32 (SIMT fp32 parity mode) */
+  float   rotary_interp;      /* rotary_interpolation_factor */
+  float   norm_eps;           /* 1e-5 (LayerNorm) / 1e-8 (RMSNorm) */
+} lcasr_config;
+
+/* Matrices ("*_w" of rank 2) are in `compute_dtype`; every vector and every depthwise filter is
+ * fp32.  qkv_w rows are de-interleaved to [q | k | v]; sub_out_w columns are permuted from the
+ * reference's (c*F3+f) to channels-last (f*C+c).  Unused pointers (e.g. biases when bias_in_ff=0,
+ * norm biases for RMSNorm) are NULL. */
+typedef struct lcasr_layer_weights {
+  const float *ff1_norm_w, *ff1_norm_b; const void *ff1_fc1_w; const float *ff1_fc1_b; const void *ff1_fc2_w; const float *ff1_fc2_b;
+  const float *attn_norm_w, *attn_norm_b; const void *qkv_w; const void *out_w;
+  const float *conv_norm_w, *conv_norm_b; const void *pw1_w; const float *pw1_b;
+  const float *dw_w, *dw_b, *brn_mean, *brn_std, *brn_w, *brn_b; const void *pw2_w; const float *pw2_b;
+  const float *ff2_norm_w, *ff2_norm_b; const void *ff2_fc1_w; const float *ff2_fc1_b; const void *ff2_fc2_w; const float *ff2_fc2_b;
+  const float *norm_out_w, *norm_out_b;
+} lcasr_layer_weights;
+
+typedef struct lcasr_weights {
+  const float *conv0_w, *conv0_b;                          /* [C,9], [C] */
+  const float *dw1_w, *dw1_b; const void *pw1_w; const float *pw1_b;   /* conv.2 / conv.3 */
+  const float *dw2_w, *dw2_b; const void *pw2_w; const float *pw2_b;   /* conv.5 / conv.6 */
+  const void *sub_out_w;                                   /* [d, F3*C] permuted */
+  const float *inv_freq;                                   /* [Dh/2] or NULL */
+  const float *dec_norm_w, *dec_norm_b; const void *dec_ff_w; const float *dec_ff_b;
+  const void *dec_rep_w; const float *dec_rep_b;
+  const lcasr_layer_weights* layers_host;                  /* HOST array [n_layers] of device ptrs */
+} lcasr_weights;
+
+typedef struct lcasr_model lcasr_model;
+
+/* Builds a model handle.  Weights are BORROWED (the caller — PyTorch — owns them and must keep
+ * them alive and unchanged; call again after load_state_dict).  Replaces SCConformerXL.__init__ +
+ * load_state_dict (sconformer_xl.py:32-160, lcasr/utils/general.py:57-59). */
+int lcasr_model_create(const lcasr_config* cfg, const lcasr_weights* w, lcasr_model** out);
+void lcasr_model_destroy(lcasr_model* m);
+
+/* test / profiling hook: force the GEMM (LCASR_GEMM_*) and attention (LCASR_ATTN_*) kernels */
+int lcasr_model_set_impl(lcasr_model* m, int gemm_impl, int attn_impl);
+
+/* tokens after 8x subsampling: calc_length (subsampling.py:557-567) applied three times */
+int64_t lcasr_out_length(int64_t T);
+
+/* bytes of device workspace lcasr_model_forward needs for a [B,feat_in,T] input */
+int64_t lcasr_model_workspace_bytes(const lcasr_model* m, int B, int64_t T);
+
+/* SCConformerXL.forward(audio_signal[B,feat_in,T]) with all lengths == T
+ * (sconformer_xl.py:162-252).  Writes out[B,N,num_classes] fp32: log-probs, or logits when
+ * return_logits != 0.  argmax (int32 [B,N], may be NULL) is the fused per-frame argmax that
+ * GreedyCTCDecoder (decoding/greedy.py:19) would compute.  workspace: device scratch of at least
+ * lcasr_model_workspace_bytes().  Asynchronous on `stream`. */
+int lcasr_model_forward(lcasr_model* m, const float* spec, int B, int64_t T, float* out,
+                        int32_t* argmax, int return_logits, void* workspace, int64_t workspace_bytes,
+                        void* stream);
+
+/* End-to-end convenience used by bench.py's e2e leg and by a non-PyTorch host: pinned-host
+ * spectrogram in, token ids out (H2D copy, forward, greedy collapse, D2H copy of tokens, stream
+ * synchronise).  tokens_host [B,N] int32, n_tokens_host [B] int32. */
+int lcasr_model_transcribe_host(lcasr_model* m, const float* spec_host, int B, int64_t T,
+                                int32_t* tokens_host, int32_t* n_tokens_host, float* logp_dev_or_null,
+                                void* workspace, int64_t workspace_bytes, void* stream);
+
+/* workspace bytes lcasr_model_transcribe_host needs (forward workspace + input/token staging) */
+int64_t lcasr_model_transcribe_workspace_bytes(const lcasr_model* m, int B, int64_t T);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCASR_B200_H_ */

@@ -1,0 +1,139 @@
+"""ctypes binding of liblcasr_b200.so (the C ABI declared in include/lcasr_b200.h).
+
+There is deliberately no fallback: if the shared library is missing the import raises, and every
+wrapper raises ``RuntimeError`` with ``lcasr_last_error()`` when a call returns non-zero.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblcasr_b200.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_GELU_TANH, ACT_SILU = 0, 1, 2
+NORM_LAYERNORM, NORM_RMSNORM = 0, 1
+GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
+ATTN_AUTO, ATTN_SIMT, ATTN_TCGEN05 = 0, 1, 2
+ABI_VERSION = 1
+
+vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class LcasrConfig(C.Structure):
+    _fields_ = [(n, i32) for n in (
+        "abi_version", "n_layers", "d_model", "n_heads", "head_dim", "feat_in", "conv_channels",
+        "conv_kernel_size", "num_classes", "norm_kind", "decoder_norm", "use_rotary", "self_conditioning",
+        "legasee_double_norm", "bias_in_ff", "compute_dtype")] + [("rotary_interp", f32), ("norm_eps", f32)]
+
+
+LAYER_FIELDS = (
+    "ff1_norm_w", "ff1_norm_b", "ff1_fc1_w", "ff1_fc1_b", "ff1_fc2_w", "ff1_fc2_b",
+    "attn_norm_w", "attn_norm_b", "qkv_w", "out_w",
+    "conv_norm_w", "conv_norm_b", "pw1_w", "pw1_b",
+    "dw_w", "dw_b", "brn_mean", "brn_std", "brn_w", "brn_b", "pw2_w", "pw2_b",
+    "ff2_norm_w", "ff2_norm_b", "ff2_fc1_w", "ff2_fc1_b", "ff2_fc2_w", "ff2_fc2_b",
+    "norm_out_w", "norm_out_b")
+
+
+class LcasrLayerWeights(C.Structure):
+    _fields_ = [(n, vp) for n in LAYER_FIELDS]
+
+
+MODEL_FIELDS = (
+    "conv0_w", "conv0_b", "dw1_w", "dw1_b", "pw1_w", "pw1_b", "dw2_w", "dw2_b", "pw2_w", "pw2_b",
+    "sub_out_w", "inv_freq", "dec_norm_w", "dec_norm_b", "dec_ff_w", "dec_ff_b", "dec_rep_w", "dec_rep_b")
+
+
+class LcasrWeights(C.Structure):
+    _fields_ = [(n, vp) for n in MODEL_FIELDS] + [("layers_host", C.POINTER(LcasrLayerWeights))]
+
+
+# name -> argtypes; every function returns int status unless listed in _OTHER_RESTYPE
+_SIGNATURES = {
+    "lcasr_layernorm": [vp, vp, vp, i64, i32, f32, i32, vp, vp, i32, vp],
+    "lcasr_subsample_conv0": [vp, vp, vp, i32, i32, i64, i32, vp, i32, vp],
+    "lcasr_subsample_dwconv": [vp, i32, vp, vp, i32, i64, i32, i32, vp, vp],
+    "lcasr_gemm": [vp, vp, i32, i64, i32, i32, vp, i32, vp, f32, vp, i32, i32, vp],
+    "lcasr_cast_f32": [vp, i64, vp, i32, vp],
+    "lcasr_glu": [vp, i32, i64, i32, vp, vp],
+    "lcasr_rope_table": [vp, f32, i64, i64, i32, vp, vp, vp],
+    "lcasr_rope_split": [vp, i32, i32, i64, i32, i32, vp, vp, vp, vp, vp, i32, i64, vp],
+    "lcasr_attention": [vp, vp, vp, i32, i32, i64, i32, i32, i32, i64, vp, i32, vp],
+    "lcasr_dwconv_brn_silu": [vp, i32, i32, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp],
+    "lcasr_softmax": [vp, i32, i64, i32, vp, i32, vp],
+    "lcasr_log_softmax_argmax": [vp, i64, i32, vp, vp],
+    "lcasr_argmax_rows": [vp, i64, i32, vp, vp],
+    "lcasr_greedy_collapse": [vp, i32, i64, vp, i32, vp, vp, vp],
+    "lcasr_ctc_loss_fwd": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp],
+    "lcasr_ctc_loss_bwd": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp],
+    "lcasr_model_create": [C.POINTER(LcasrConfig), C.POINTER(LcasrWeights), C.POINTER(vp)],
+    "lcasr_model_set_impl": [vp, i32, i32],
+    "lcasr_model_forward": [vp, vp, i32, i64, vp, vp, i32, vp, i64, vp],
+    "lcasr_model_transcribe_host": [vp, vp, i32, i64, vp, vp, vp, vp, i64, vp],
+}
+_OTHER = {
+    "lcasr_abi_version": ([], i32),
+    "lcasr_last_error": ([], C.c_char_p),
+    "lcasr_launch_count": ([], i64),
+    "lcasr_reset_launch_count": ([], None),
+    "lcasr_out_length": ([i64], i64),
+    "lcasr_model_destroy": ([vp], None),
+    "lcasr_model_workspace_bytes": ([vp, i32, i64], i64),
+    "lcasr_model_transcribe_workspace_bytes": ([vp, i32, i64], i64),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES) + tuple(_OTHER)
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C long-context-asr_b200/csrc`). lcasr_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, args in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = args, i32
+    for name, (args, res) in _OTHER.items():
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = args, res
+    if lib.lcasr_abi_version() != ABI_VERSION:
+        raise ImportError(f"liblcasr_b200.so ABI {lib.lcasr_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
+    return lib
+
+
+lib = _load()
+
+
+class LcasrError(RuntimeError):
+    pass
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = lib.lcasr_last_error().decode(errors="replace")
+        raise LcasrError(f"lcasr_b200 {what} failed (status {status}): {msg}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(lib, name)(*args), name)
+
+
+def ptr(t):
+    """device/host pointer of a torch tensor (or None)."""
+    return None if t is None else t.data_ptr()
+
+
+def dtype_code(torch_dtype) -> int:
+    import torch
+    if torch_dtype == torch.float32:
+        return F32
+    if torch_dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"lcasr_b200 supports float32 / bfloat16 tensors, got {torch_dtype}")
+
+
+def current_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,79 @@
+// C-ABI plumbing: error reporting, launch counter, GEMM / attention dispatch.
+#include "common.cuh"
+#include <cstring>
+
+namespace lcasr {
+
+std::atomic<int64_t> g_launch_count{0};
+
+char* last_error_buf() {
+  static thread_local char buf[1024] = {0};
+  return buf;
+}
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 1024, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int gemm_simt_launch(const void* A, const void* W, int ab_dtype, int64_t M, int N, int K, const float* bias, int act,
+                     const float* resid, float alpha, void* out, int out_dtype, cudaStream_t st);
+int gemm_tc_launch(const void* A, const void* W, int64_t M, int N, int K, const float* bias, int act, const float* resid,
+                   float alpha, void* out, int out_dtype, cudaStream_t st);
+int attn_simt_launch(const void* q, const void* k, const void* v, int dtype, int B, int64_t N, int H, int Dh,
+                     int v_transposed, int64_t Npad, void* out, cudaStream_t st);
+int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N, int H, int Dh, int v_transposed,
+                   int64_t Npad, void* out, cudaStream_t st);
+
+}  // namespace lcasr
+
+using namespace lcasr;
+
+extern "C" int lcasr_abi_version(void) { return LCASR_ABI_VERSION; }
+extern "C" const char* lcasr_last_error(void) { return last_error_buf(); }
+extern "C" int64_t lcasr_launch_count(void) { return g_launch_count.load(); }
+extern "C" void lcasr_reset_launch_count(void) { g_launch_count.store(0); }
+
+extern "C" int64_t lcasr_out_length(int64_t T) {
+  // calc_length (subsampling.py:557-567): floor((L + 2 - 3) / 2 + 1) three times == (L-1)/2 + 1 for L >= 1
+  for (int i = 0; i < 3; ++i) T = T >= 1 ? (T - 1) / 2 + 1 : 0;
+  return T;
+}
+
+extern "C" int lcasr_gemm(const void* A, const void* W, int ab_dtype, int64_t M, int N, int K, const float* bias,
+                          int act, const float* resid, float alpha, void* out, int out_dtype, int impl, void* stream) {
+  LCASR_CHECK_ARG(A && W && out, "gemm: NULL operand");
+  LCASR_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
+  LCASR_CHECK_ARG(ab_dtype == LCASR_F32 || ab_dtype == LCASR_BF16, "gemm: bad operand dtype %d", ab_dtype);
+  LCASR_CHECK_ARG(out_dtype == LCASR_F32 || out_dtype == LCASR_BF16, "gemm: bad output dtype %d", out_dtype);
+  LCASR_CHECK_ARG(act >= LCASR_ACT_NONE && act <= LCASR_ACT_SILU, "gemm: bad activation %d", act);
+  LCASR_CHECK_ARG(!resid || out_dtype == LCASR_F32, "gemm: a residual epilogue writes fp32");
+  if (M == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (impl == LCASR_GEMM_AUTO) impl = ab_dtype == LCASR_BF16 ? LCASR_GEMM_TCGEN05 : LCASR_GEMM_SIMT;
+  if (impl == LCASR_GEMM_TCGEN05) {
+    LCASR_CHECK_ARG(ab_dtype == LCASR_BF16, "gemm: the tcgen05 kernel takes bf16 operands");
+    return gemm_tc_launch(A, W, M, N, K, bias, act, resid, alpha, out, out_dtype, st);
+  }
+  LCASR_CHECK_ARG(impl == LCASR_GEMM_SIMT, "gemm: bad impl %d", impl);
+  return gemm_simt_launch(A, W, ab_dtype, M, N, K, bias, act, resid, alpha, out, out_dtype, st);
+}
+
+extern "C" int lcasr_attention(const void* q, const void* k, const void* v, int dtype, int B, int64_t N, int H, int Dh,
+                               int v_transposed, int64_t Npad, void* out, int impl, void* stream) {
+  LCASR_CHECK_ARG(q && k && v && out, "attention: NULL operand");
+  LCASR_CHECK_ARG(B > 0 && N > 0 && H > 0 && Dh > 0, "attention: bad shape");
+  LCASR_CHECK_ARG(dtype == LCASR_F32 || dtype == LCASR_BF16, "attention: bad dtype %d", dtype);
+  LCASR_CHECK_ARG(!v_transposed || Npad >= N, "attention: Npad < N");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (impl == LCASR_ATTN_AUTO) impl = dtype == LCASR_BF16 ? LCASR_ATTN_TCGEN05 : LCASR_ATTN_SIMT;
+  if (impl == LCASR_ATTN_TCGEN05) {
+    LCASR_CHECK_ARG(dtype == LCASR_BF16, "attention: the tcgen05 kernel takes bf16 operands");
+    return attn_tc_launch(q, k, v, B, N, H, Dh, v_transposed, Npad, out, st);
+  }
+  LCASR_CHECK_ARG(impl == LCASR_ATTN_SIMT, "attention: bad impl %d", impl);
+  return attn_simt_launch(q, k, v, dtype, B, N, H, Dh, v_transposed, Npad, out, st);
+}

@@ -1,0 +1,263 @@
+// CTC loss: torch.nn.CTCLoss(blank=V, reduction=...) as exp/train.py:104,249 calls it
+// (ATen LossCTC: Graves et al. alpha/beta recursion in the log domain).
+//
+// Forward (alpha): one CTA per sample; the 2S+1 extended-label states are strided over the
+// threads, alpha(t-1)/alpha(t) are double-buffered in shared memory (2*(2S+1)*4 bytes: 27001 states
+// of a 1-hour recording = 216 KB, inside the 227 KB a CTA may own), one __syncthreads per frame;
+// the log-prob gathers of frame t+1 are prefetched into registers while frame t is computed.
+// Latency-bound (serial in time); algorithmic HBM bytes = N*V*4 only if every class were read —
+// in fact it touches (S+1) values per frame.
+// Backward: beta recursion run the same way backwards in time writing log(alpha*beta) in place,
+// then a collect kernel (one CTA per frame) scatters into the class axis.
+#include "common.cuh"
+
+namespace lcasr {
+
+constexpr int kCtcMaxSPT = 32;
+
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+  float m = fmaxf(fmaxf(a, b), c);
+  if (m == -INFINITY) return -INFINITY;
+  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+}
+
+// direction = +1: alpha (forward in time, labels as given); direction = -1: beta (time and label
+// order reversed — the recursion is symmetric). `store` (may be NULL) receives the per-frame state
+// vector in ORIGINAL (t, s) coordinates; for beta it is ADDED to what is there (alpha+beta).
+template <int SPT>
+__global__ void __launch_bounds__(1024) ctc_recursion_kernel(const float* __restrict__ log_probs, int64_t N, int V,
+                                                             const int64_t* __restrict__ targets, int64_t S_max,
+                                                             const int32_t* __restrict__ input_lengths,
+                                                             const int64_t* __restrict__ target_lengths, int blank,
+                                                             int direction, float* __restrict__ nll,
+                                                             float* __restrict__ store) {
+  extern __shared__ float sm_alpha[];  // [2][Lp_pad]
+  const int b = blockIdx.x;
+  const int NT = blockDim.x;
+  const int tid = threadIdx.x;
+  const int64_t T = input_lengths ? min((int64_t)input_lengths[b], N) : N;
+  const int64_t S = target_lengths[b];
+  const int Lp = (int)(2 * S + 1);
+  const int Lp_max = (int)(2 * S_max + 1);
+  const int Lp_pad = SPT * NT;
+  float* cur = sm_alpha;
+  float* nxt = sm_alpha + Lp_pad;
+  const float* lp = log_probs + (int64_t)b * N * V;
+  const int64_t* tgt = targets + (int64_t)b * S_max;
+  float* st = store ? store + (int64_t)b * N * Lp_max : nullptr;
+
+  if (T <= 0 || (T < S)) {  // ATen: impossible alignment -> inf loss
+    if (tid == 0 && nll) nll[b] = INFINITY;
+    return;
+  }
+
+  // label of state s in the (possibly reversed) extended sequence, and the "skip" permission
+  int lab[SPT];
+  bool skip[SPT];
+#pragma unroll
+  for (int j = 0; j < SPT; ++j) {
+    int s = tid + j * NT;
+    lab[j] = blank;
+    skip[j] = false;
+    if (s < Lp && (s & 1)) {
+      int64_t li = (s - 1) >> 1;                       // index in the (reversed) label sequence
+      int64_t oi = direction > 0 ? li : (S - 1 - li);  // index in the original targets
+      lab[j] = (int)tgt[oi];
+      if (li >= 1) {
+        int64_t po = direction > 0 ? oi - 1 : oi + 1;
+        skip[j] = tgt[po] != tgt[oi];
+      }
+    }
+  }
+  auto frame = [&](int64_t step) -> int64_t { return direction > 0 ? step : (T - 1 - step); };
+
+  float lpv[SPT], lpn[SPT];
+  {
+    const float* row = lp + frame(0) * V;
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) {
+      int s = tid + j * NT;
+      float a = -INFINITY;
+      if (s == 0) a = row[blank];
+      else if (s == 1 && Lp > 1) a = row[lab[j]];
+      cur[s] = a;
+      if (st && s < Lp) {
+        int so = direction > 0 ? s : (Lp - 1 - s);
+        float* p = st + frame(0) * Lp_max + so;
+        *p = direction > 0 ? a : (*p + a);
+      }
+    }
+    if (T > 1) {
+      const float* row1 = lp + frame(1) * V;
+#pragma unroll
+      for (int j = 0; j < SPT; ++j) lpv[j] = row1[lab[j]];
+    }
+  }
+  __syncthreads();
+  for (int64_t step = 1; step < T; ++step) {
+    if (step + 1 < T) {
+      const float* rown = lp + frame(step + 1) * V;
+#pragma unroll
+      for (int j = 0; j < SPT; ++j) lpn[j] = rown[lab[j]];
+    }
+    float* strow = st ? st + frame(step) * Lp_max : nullptr;
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) {
+      int s = tid + j * NT;
+      if (s < Lp) {
+        float a0 = cur[s];
+        float a1 = s >= 1 ? cur[s - 1] : -INFINITY;
+        float a2 = skip[j] ? cur[s - 2] : -INFINITY;
+        float a = lse3(a0, a1, a2) + lpv[j];
+        nxt[s] = a;
+        if (strow) {
+          int so = direction > 0 ? s : (Lp - 1 - s);
+          strow[so] = direction > 0 ? a : (strow[so] + a);
+        }
+      }
+    }
+    __syncthreads();
+    float* tmp = cur; cur = nxt; nxt = tmp;
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) lpv[j] = lpn[j];
+  }
+  if (tid == 0 && nll) {
+    float l1 = cur[Lp - 1];
+    float l2 = Lp > 1 ? cur[Lp - 2] : -INFINITY;
+    float m = fmaxf(l1, l2);
+    nll[b] = m == -INFINITY ? INFINITY : -(m + logf(expf(l1 - m) + expf(l2 - m)));
+  }
+}
+
+// grad[b,t,c] = exp(lp) - exp(log(sum_{s:ext[s]=c} exp(ab[t,s])) + nll - lp)     (t < input_length)
+// ab = alpha+beta (log), both including lp[t,ext[s]] (ATen convention).  One CTA per (t, b).
+__global__ void __launch_bounds__(256) ctc_grad_collect_kernel(const float* __restrict__ log_probs, int64_t N, int V,
+                                                               const int64_t* __restrict__ targets, int64_t S_max,
+                                                               const int32_t* __restrict__ input_lengths,
+                                                               const int64_t* __restrict__ target_lengths, int blank,
+                                                               const float* __restrict__ nll,
+                                                               const float* __restrict__ grad_nll,
+                                                               const float* __restrict__ ab, float* __restrict__ grad) {
+  extern __shared__ float acc[];  // [V] linear-domain sums relative to the frame max
+  __shared__ float red[8];
+  const int64_t t = blockIdx.x;
+  const int b = blockIdx.y;
+  const int64_t T = input_lengths ? min((int64_t)input_lengths[b], N) : N;
+  float* g = grad + ((int64_t)b * N + t) * V;
+  const int64_t S = target_lengths[b];
+  if (t >= T || T < S) {
+    for (int c = threadIdx.x; c < V; c += blockDim.x) g[c] = 0.f;
+    return;
+  }
+  const int Lp = (int)(2 * S + 1), Lp_max = (int)(2 * S_max + 1);
+  const float* abr = ab + ((int64_t)b * N + t) * Lp_max;
+  const int64_t* tgt = targets + (int64_t)b * S_max;
+  const float* lp = log_probs + ((int64_t)b * N + t) * V;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) acc[c] = 0.f;
+  float mx = -INFINITY;
+  for (int s = threadIdx.x; s < Lp; s += blockDim.x) mx = fmaxf(mx, abr[s]);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  if (mx != -INFINITY) {
+    float blank_sum = 0.f;  // the S+1 blank states would serialise on one shared-memory atomic
+    for (int s = threadIdx.x; s < Lp; s += blockDim.x) {
+      float v = abr[s];
+      if (v == -INFINITY) continue;
+      float e = expf(v - mx);
+      if (s & 1) atomicAdd(&acc[(int)tgt[(s - 1) >> 1]], e);
+      else blank_sum += e;
+    }
+    blank_sum = warp_sum(blank_sum);
+    if ((threadIdx.x & 31) == 0 && blank_sum != 0.f) atomicAdd(&acc[blank], blank_sum);
+  }
+  __syncthreads();
+  const float nl = nll[b], gn = grad_nll ? grad_nll[b] : 1.f;
+  const bool bad = isinf(nl);  // zero_infinity=False: grads of an inf loss are NaN in ATen; we emit 0*gn
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    float l = lp[c];
+    float occ = acc[c] > 0.f ? expf(logf(acc[c]) + mx + nl - l) : 0.f;
+    g[c] = bad ? 0.f : (expf(l) - occ) * gn;
+  }
+}
+
+template <int SPT>
+static int launch_rec(const float* lp, int B, int64_t N, int V, const int64_t* tg, int64_t S_max, const int32_t* il,
+                      const int64_t* tl, int blank, int dir, float* nll, float* store, int nt, cudaStream_t st) {
+  size_t smem = (size_t)2 * SPT * nt * sizeof(float);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    LCASR_CUDA(cudaFuncSetAttribute(ctc_recursion_kernel<SPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  ctc_recursion_kernel<SPT><<<B, nt, smem, st>>>(lp, N, V, tg, S_max, il, tl, blank, dir, nll, store);
+  LCASR_LAUNCH_CHECK();
+  return 0;
+}
+
+static int ctc_recursion(const float* lp, int B, int64_t N, int V, const int64_t* tg, int64_t S_max, const int32_t* il,
+                         const int64_t* tl, int blank, int dir, float* nll, float* store, cudaStream_t st) {
+  const int64_t Lp = 2 * S_max + 1;
+  LCASR_CHECK_ARG(Lp <= (int64_t)kCtcMaxSPT * 1024 && Lp * 8 <= 227 * 1024 - 64,
+                  "ctc_loss: %lld extended states do not fit one CTA's shared memory (max 29048)", (long long)Lp);
+  int spt = 1;
+  while ((int64_t)spt * 1024 < Lp) spt *= 2;
+  if (Lp <= 512) spt = 1;
+  int nt = (int)round_up(ceil_div(Lp, spt), 32);
+  if (nt > 1024) nt = 1024;
+  // shrink padding for the big cases so 2*SPT*nt*4 stays within 227 KB
+  while ((size_t)2 * spt * nt * 4 > 227 * 1024 && nt > 32) nt -= 32;
+  LCASR_CHECK_ARG((int64_t)spt * nt >= Lp, "ctc_loss: internal sizing error");
+  switch (spt) {
+    case 1: return launch_rec<1>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st);
+    case 2: return launch_rec<2>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st);
+    case 4: return launch_rec<4>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st);
+    case 8: return launch_rec<8>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st);
+    case 16: return launch_rec<16>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st);
+    default: return launch_rec<32>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st);
+  }
+}
+
+}  // namespace lcasr
+
+using namespace lcasr;
+
+extern "C" int lcasr_ctc_loss_fwd(const float* log_probs, int B, int64_t N, int V, const int64_t* targets,
+                                  int64_t S_max, const int32_t* input_lengths, const int64_t* target_lengths,
+                                  int blank, float* nll, float* alpha_ws, void* stream) {
+  LCASR_CHECK_ARG(log_probs && targets && target_lengths && nll, "ctc_loss_fwd: NULL argument");
+  LCASR_CHECK_ARG(B > 0 && N > 0 && V > 1 && S_max >= 0 && blank >= 0 && blank < V, "ctc_loss_fwd: bad shape");
+  return ctc_recursion(log_probs, B, N, V, targets, S_max, input_lengths, target_lengths, blank, +1, nll, alpha_ws,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int lcasr_ctc_loss_bwd(const float* log_probs, int B, int64_t N, int V, const int64_t* targets,
+                                  int64_t S_max, const int32_t* input_lengths, const int64_t* target_lengths,
+                                  int blank, const float* nll, const float* grad_nll, const float* alpha_ws,
+                                  float* beta_ws, float* grad, void* stream) {
+  LCASR_CHECK_ARG(log_probs && targets && target_lengths && nll && alpha_ws && beta_ws && grad,
+                  "ctc_loss_bwd: NULL argument");
+  LCASR_CHECK_ARG(B > 0 && N > 0 && V > 1 && S_max >= 0 && blank >= 0 && blank < V, "ctc_loss_bwd: bad shape");
+  LCASR_CHECK_ARG((size_t)V * 4 <= 200 * 1024, "ctc_loss_bwd: V=%d too large", V);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t Lp_max = 2 * S_max + 1;
+  // beta_ws <- alpha, then the reversed recursion adds beta - lp[t, ext[s]] ... we store alpha+beta
+  LCASR_CUDA(cudaMemcpyAsync(beta_ws, alpha_ws, (size_t)B * N * Lp_max * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  LCASR_TRY(ctc_recursion(log_probs, B, N, V, targets, S_max, input_lengths, target_lengths, blank, -1, nullptr,
+                          beta_ws, st));
+  size_t smem = (size_t)V * sizeof(float);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    LCASR_CUDA(cudaFuncSetAttribute(ctc_grad_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  LCASR_CHECK_ARG(B <= 65535, "ctc_loss_bwd: batch too large");
+  dim3 grid((unsigned)N, (unsigned)B);
+  ctc_grad_collect_kernel<<<grid, 256, smem, st>>>(log_probs, N, V, targets, S_max, input_lengths, target_lengths, blank,
+                                                   nll, grad_nll, beta_ws, grad);
+  LCASR_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,271 @@
+// tcgen05 GEMM  out = epi(A[M,K] . W[N,K]^T), bf16 operands, fp32 accumulation in tensor memory.
+//
+// Persistent, warp-specialised (one CTA per SM, 192 threads):
+//   warp 0   TMA producer   : cp.async.bulk.tensor 128x64 (A) and BNx64 (W) bf16 boxes, 128B swizzle,
+//                             into a STAGES-deep shared-memory ring (mbarrier full/empty pairs)
+//   warp 1   MMA issuer     : one elected thread issues tcgen05.mma.cta_group::1.kind::f16
+//                             (M=128, N=BN, K=16) x4 per stage into one of two TMEM accumulators,
+//                             tcgen05.commit releases the smem slot / publishes the accumulator
+//   warps 2-5 epilogue      : tcgen05.ld 32 lanes x 32 columns -> bias/activation/residual -> global;
+//                             overlaps the next tile's main loop through the 2nd TMEM accumulator
+// Both operands are K-major (activations [M,K] and nn.Linear weights [N,K] are K-contiguous), so no
+// transposes are needed anywhere on the path.  Out-of-range rows / K tail are zero-filled by TMA.
+// Tensor-bound: algorithmic FLOPs = 2*M*N*K.
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace lcasr {
+
+using namespace ptx;
+
+constexpr int TG_BM = 128, TG_BK = 64, TG_THREADS = 192;
+
+template <int BN> struct TgCfg {
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int A_BYTES = TG_BM * TG_BK * 2;
+  static constexpr int B_BYTES = BN * TG_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;  // double-buffered fp32 accumulator (power of two: 256 / 512)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/;
+};
+
+struct TgEpilogue {
+  const float* bias;   // [N] or null
+  const float* resid;  // [M,N] fp32 or null
+  float alpha;
+  int act;
+};
+
+template <typename TOut>
+__device__ __forceinline__ void tg_store_chunk(const uint32_t (&r)[32], int64_t row, int col0, int64_t M, int N,
+                                               const TgEpilogue& ep, TOut* __restrict__ out) {
+  if (row >= M) return;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {  // 8 columns at a time (N % 8 == 0 so a group is all-in or all-out)
+    const int col = col0 + g * 8;
+    if (col >= N) break;
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(r[g * 8 + i]);
+    if (ep.bias) {
+      float4 b0 = *reinterpret_cast<const float4*>(ep.bias + col), b1 = *reinterpret_cast<const float4*>(ep.bias + col + 4);
+      y[0] += b0.x; y[1] += b0.y; y[2] += b0.z; y[3] += b0.w; y[4] += b1.x; y[5] += b1.y; y[6] += b1.z; y[7] += b1.w;
+    }
+    if (ep.act == LCASR_ACT_GELU_TANH) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float x = y[i];
+        float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+        y[i] = 0.5f * x * (1.0f + tanh_approx(u));
+      }
+    } else if (ep.act == LCASR_ACT_SILU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = __fdividef(y[i], 1.0f + __expf(-y[i]));
+    }
+    if (ep.resid) {
+      float rr[8];
+      Vec8<float>::load(ep.resid + row * N + col, rr);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = fmaf(ep.alpha, y[i], rr[i]);
+    }
+    Vec8<TOut>::store(out + row * N + col, y);
+  }
+}
+
+template <int BN, typename TOut>
+__global__ void __launch_bounds__(TG_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int64_t M, int N, int K,
+               TgEpilogue ep, TOut* __restrict__ out) {
+  using Cfg = TgCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * Cfg::STAGES + 4];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle atoms need 1024B alignment
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = (K + TG_BK - 1) / TG_BK;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int64_t tiles_m = (M + TG_BM - 1) / TG_BM;
+  const int64_t total_tiles = tiles_m * tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer ----------------
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_idx = (int)(tile / tiles_n) * TG_BM, n_idx = (int)(tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          tma_load_2d(sa, &tmA, full_bar(stage), kb * TG_BK, m_idx);
+          tma_load_2d(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * TG_BK, n_idx);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc = make_idesc_bf16(TG_BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc_kmajor(sa, 1024, kLayoutSW128);
+          const uint64_t bdesc = make_smem_desc_kmajor(sa + Cfg::A_BYTES, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < TG_BK / 16; ++k)  // +32 bytes (= 2 in >>4 units) per K=16 step inside the swizzle row
+            umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(empty_bar(stage));
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {  // ---------------- epilogue warps 2..5 ----------------
+    const int lane_base = (warp & 3) * 32;  // TMEM lanes this warp may touch
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int64_t m_idx = (tile / tiles_n) * TG_BM;
+      const int n_idx = (int)(tile % tiles_n) * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int64_t row = m_idx + lane_base + lane;
+      const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (n_idx + c * 32 >= N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_addr + c * 32, r);
+        tmem_wait_ld();
+        tg_store_chunk<TOut>(r, row, n_idx + c * 32, M, N, ep, out);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiled)p;
+  }
+  return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes,
+                      uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swizzle) {
+  PFN_tmapEncodeTiled fn = get_encode_fn();
+  if (!fn) return set_error(LCASR_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_pitch_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(LCASR_E_CUDA, "cuTensorMapEncodeTiled failed (%d): base=%p rows=%llu cols=%llu pitch=%llu box=%ux%u",
+                     (int)r, base, (unsigned long long)rows, (unsigned long long)cols,
+                     (unsigned long long)row_pitch_bytes, box_rows, box_cols);
+  return 0;
+}
+
+int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_bytes,
+                      uint64_t pitch2_bytes, uint32_t box0, uint32_t box1, uint32_t box2, CUtensorMapSwizzle swizzle) {
+  PFN_tmapEncodeTiled fn = get_encode_fn();
+  if (!fn) return set_error(LCASR_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {pitch1_bytes, pitch2_bytes};
+  cuuint32_t box[3] = {box0, box1, box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(LCASR_E_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d): base=%p dims=%llu,%llu,%llu", (int)r, base,
+                     (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2);
+  return 0;
+}
+
+template <int BN, typename TOut>
+static int launch_tc(const void* A, const void* W, int64_t M, int N, int K, const TgEpilogue& ep, void* out,
+                     cudaStream_t st) {
+  using Cfg = TgCfg<BN>;
+  CUtensorMap tmA, tmB;
+  LCASR_TRY(make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)K * 2, TG_BM, TG_BK, CU_TENSOR_MAP_SWIZZLE_128B));
+  LCASR_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, BN, TG_BK, CU_TENSOR_MAP_SWIZZLE_128B));
+  static bool attr_set = false;
+  if (!attr_set) {
+    LCASR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int64_t tiles = ceil_div(M, TG_BM) * ceil_div(N, BN);
+  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+  gemm_tc_kernel<BN, TOut><<<grid, TG_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, ep, (TOut*)out);
+  LCASR_LAUNCH_CHECK();
+  return 0;
+}
+
+int gemm_tc_launch(const void* A, const void* W, int64_t M, int N, int K, const float* bias, int act, const float* resid,
+                   float alpha, void* out, int out_dtype, cudaStream_t st) {
+  LCASR_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "gemm(tcgen05): K=%d and N=%d must be multiples of 8", K, N);
+  LCASR_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0,
+                  "gemm(tcgen05): A, W and out must be 16-byte aligned");
+  LCASR_CHECK_ARG(M < (int64_t)1 << 31, "gemm(tcgen05): M too large");
+  LCASR_CHECK_ARG(((uintptr_t)bias & 15) == 0 && ((uintptr_t)resid & 15) == 0, "gemm(tcgen05): bias/resid must be 16-byte aligned");
+  LCASR_CHECK_ARG(!resid || out_dtype == LCASR_F32, "gemm: a residual epilogue writes fp32");
+  TgEpilogue ep{bias, resid, alpha, act};
+  const bool wide = (N % 256 == 0) || N > 512;
+  if (out_dtype == LCASR_BF16)
+    return wide ? launch_tc<256, bf16>(A, W, M, N, K, ep, out, st) : launch_tc<128, bf16>(A, W, M, N, K, ep, out, st);
+  return wide ? launch_tc<256, float>(A, W, M, N, K, ep, out, st) : launch_tc<128, float>(A, W, M, N, K, ep, out, st);
+}
+
+}  // namespace lcasr

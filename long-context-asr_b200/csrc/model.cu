@@ -1,0 +1,239 @@
+// Host-side orchestration of SCConformerXL.forward (lcasr/models/sconformer_xl.py:162-252,
+// ConformerLayer.forward :346-372) as a fixed sequence of kernel launches on one stream.
+// No host synchronisation, no allocation: every intermediate lives in the caller's workspace.
+//
+// HBM layout (all row-major, "M" = B*N tokens, e = bytes of the compute dtype):
+//   x      [M, d]            fp32   residual stream (kept fp32 in both precisions, >= the reference)
+//   a      [M, d]            e      normalised GEMM operand / attention output
+//   wide   [M, max(4d,V1)]   e      FFN hidden | qkv | pw1 pre-GLU | self-conditioning logits/probs
+//   q,k,v  [M, d]            e      (g / c of the conv module alias q / k)
+//   subsampling scratch (dead once x is produced) aliases a..v:
+//     s1 [B,T1,F1,C]  s2 [B,T2,F2,C] x2   s3 [B,N,F3,C] x2     channels-last
+#include "common.cuh"
+#include <vector>
+#include <new>
+
+namespace lcasr {
+int attn_tc_available();
+}
+
+using namespace lcasr;
+
+struct lcasr_model {
+  lcasr_config cfg;
+  lcasr_weights w;
+  std::vector<lcasr_layer_weights> layers;
+  int attn_impl = LCASR_ATTN_AUTO;
+  int gemm_impl = LCASR_GEMM_AUTO;
+};
+
+namespace {
+
+struct Plan {
+  int B; int64_t T, T1, T2, N, M; int F1, F2, F3;
+  size_t off_x, off_cos, off_sin, off_a, off_wide, off_q, off_k, off_v;
+  size_t off_s1, off_s2a, off_s2b, off_s3a, off_s3b;
+  size_t total;
+  int64_t Npad;
+};
+
+inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+Plan make_plan(const lcasr_config& c, int B, int64_t T) {
+  Plan p{};
+  p.B = B; p.T = T;
+  p.T1 = (T - 1) / 2 + 1; p.T2 = (p.T1 - 1) / 2 + 1; p.N = (p.T2 - 1) / 2 + 1;
+  p.F1 = (c.feat_in - 1) / 2 + 1; p.F2 = (p.F1 - 1) / 2 + 1; p.F3 = (p.F2 - 1) / 2 + 1;
+  p.M = (int64_t)B * p.N;
+  p.Npad = round_up(p.N, 128);
+  const size_t e = dtype_size(c.compute_dtype);
+  const int d = c.d_model, C = c.conv_channels, V1 = c.num_classes;
+  size_t o = 0;
+  p.off_x = o; o += al((size_t)p.M * d * 4);
+  p.off_cos = o; o += al((size_t)p.N * (c.head_dim / 2) * 4);
+  p.off_sin = o; o += al((size_t)p.N * (c.head_dim / 2) * 4);
+  const size_t scratch0 = o;
+  // layer scratch
+  p.off_a = o; o += al((size_t)p.M * d * e);
+  size_t wide_cols = (size_t)4 * d;
+  if ((size_t)V1 > wide_cols) wide_cols = V1;
+  p.off_wide = o; o += al((size_t)p.M * wide_cols * e);
+  p.off_q = o; o += al((size_t)p.M * d * e);
+  p.off_k = o; o += al((size_t)p.M * d * e);
+  p.off_v = o; o += al((size_t)B * c.n_heads * c.head_dim * p.Npad * e);  // >= M*d: also holds the transposed layout
+  const size_t layer_end = o;
+  // subsampling scratch aliases the layer scratch
+  o = scratch0;
+  p.off_s1 = o; o += al((size_t)B * p.T1 * p.F1 * C * e);
+  p.off_s2a = o; o += al((size_t)B * p.T2 * p.F2 * C * e);
+  p.off_s2b = o; o += al((size_t)B * p.T2 * p.F2 * C * e);
+  p.off_s3a = o; o += al((size_t)B * p.N * p.F3 * C * e);
+  p.off_s3b = o; o += al((size_t)B * p.N * p.F3 * C * e);
+  p.total = o > layer_end ? o : layer_end;
+  return p;
+}
+
+}  // namespace
+
+extern "C" int lcasr_model_create(const lcasr_config* cfg, const lcasr_weights* w, lcasr_model** out) {
+  LCASR_CHECK_ARG(cfg && w && out, "model_create: NULL argument");
+  LCASR_CHECK_ARG(cfg->abi_version == LCASR_ABI_VERSION, "model_create: ABI version %d != %d", cfg->abi_version,
+                  LCASR_ABI_VERSION);
+  LCASR_CHECK_ARG(cfg->n_layers > 0 && cfg->d_model > 0 && cfg->n_heads > 0 && cfg->head_dim > 0, "model_create: bad dims");
+  LCASR_CHECK_ARG(cfg->n_heads * cfg->head_dim == cfg->d_model,
+                  "model_create: n_heads*head_dim (%d) != d_model (%d) is not supported", cfg->n_heads * cfg->head_dim,
+                  cfg->d_model);
+  LCASR_CHECK_ARG(cfg->d_model % 8 == 0 && cfg->conv_channels % 8 == 0 && cfg->num_classes % 8 == 0,
+                  "model_create: d_model, conv_channels and num_classes must be multiples of 8");
+  LCASR_CHECK_ARG(cfg->head_dim == 32 || cfg->head_dim == 64 || cfg->head_dim == 128,
+                  "model_create: head_dim=%d not in {32,64,128}", cfg->head_dim);
+  LCASR_CHECK_ARG(cfg->compute_dtype == LCASR_F32 || cfg->compute_dtype == LCASR_BF16, "model_create: bad compute dtype");
+  LCASR_CHECK_ARG(w->layers_host, "model_create: layers_host is NULL");
+  LCASR_CHECK_ARG(!cfg->use_rotary || w->inv_freq, "model_create: use_rotary without inv_freq");
+  lcasr_model* m = new (std::nothrow) lcasr_model();
+  if (!m) return set_error(LCASR_E_NOMEM, "model_create: out of host memory");
+  m->cfg = *cfg;
+  m->w = *w;
+  m->layers.assign(w->layers_host, w->layers_host + cfg->n_layers);
+  m->w.layers_host = m->layers.data();
+  *out = m;
+  return 0;
+}
+
+extern "C" void lcasr_model_destroy(lcasr_model* m) { delete m; }
+
+extern "C" int lcasr_model_set_impl(lcasr_model* m, int gemm_impl, int attn_impl) {
+  LCASR_CHECK_ARG(m, "model_set_impl: NULL model");
+  m->gemm_impl = gemm_impl;
+  m->attn_impl = attn_impl;
+  return 0;
+}
+
+extern "C" int64_t lcasr_model_workspace_bytes(const lcasr_model* m, int B, int64_t T) {
+  if (!m || B <= 0 || T <= 0) return -1;
+  return (int64_t)make_plan(m->cfg, B, T).total;
+}
+
+extern "C" int lcasr_model_forward(lcasr_model* m, const float* spec, int B, int64_t T, float* out, int32_t* argmax,
+                                   int return_logits, void* workspace, int64_t workspace_bytes, void* stream) {
+  LCASR_CHECK_ARG(m && spec && out && workspace, "model_forward: NULL argument");
+  LCASR_CHECK_ARG(B > 0 && T > 0, "model_forward: bad shape B=%d T=%lld", B, (long long)T);
+  const lcasr_config& c = m->cfg;
+  const lcasr_weights& w = m->w;
+  const Plan p = make_plan(c, B, T);
+  LCASR_CHECK_ARG(p.N > 0, "model_forward: input too short");
+  LCASR_CHECK_ARG((size_t)workspace_bytes >= p.total, "model_forward: workspace %lld < required %lld bytes",
+                  (long long)workspace_bytes, (long long)p.total);
+  LCASR_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "model_forward: workspace must be 256-byte aligned");
+  char* ws = (char*)workspace;
+  const int cd = c.compute_dtype;
+  const int d = c.d_model, C = c.conv_channels, V1 = c.num_classes, H = c.n_heads, Dh = c.head_dim;
+  const int64_t M = p.M, N = p.N;
+  float* x = (float*)(ws + p.off_x);
+  float* cos_t = (float*)(ws + p.off_cos);
+  float* sin_t = (float*)(ws + p.off_sin);
+  void* a = ws + p.off_a; void* wide = ws + p.off_wide;
+  void* q = ws + p.off_q; void* k = ws + p.off_k; void* v = ws + p.off_v;
+  const int gi = m->gemm_impl;
+  int ai = m->attn_impl;
+  if (ai == LCASR_ATTN_AUTO) ai = (cd == LCASR_BF16 && attn_tc_available()) ? LCASR_ATTN_TCGEN05 : LCASR_ATTN_SIMT;
+  const int vt = ai == LCASR_ATTN_TCGEN05 ? 1 : 0;
+
+  auto gemm = [&](const void* A, const void* W, int64_t rows, int n, int kk, const float* bias, int act,
+                  const float* resid, float alpha, void* o, int odt) {
+    return lcasr_gemm(A, W, cd, rows, n, kk, bias, act, resid, alpha, o, odt, gi, stream);
+  };
+  auto norm = [&](const float* nw, const float* nb, float* o32, void* olo) {
+    return lcasr_layernorm(x, nw, nb, M, d, c.norm_eps, c.norm_kind, o32, olo, cd, stream);
+  };
+
+  // ---- subsampling (subsampling.py:384-428) ----
+  {
+    void* s1 = ws + p.off_s1; void* s2a = ws + p.off_s2a; void* s2b = ws + p.off_s2b;
+    void* s3a = ws + p.off_s3a; void* s3b = ws + p.off_s3b;
+    LCASR_TRY(lcasr_subsample_conv0(spec, w.conv0_w, w.conv0_b, B, c.feat_in, T, C, s1, cd, stream));
+    LCASR_TRY(lcasr_subsample_dwconv(s1, cd, w.dw1_w, w.dw1_b, B, p.T1, p.F1, C, s2a, stream));
+    LCASR_TRY(gemm(s2a, w.pw1_w, (int64_t)B * p.T2 * p.F2, C, C, w.pw1_b, LCASR_ACT_SILU, nullptr, 0.f, s2b, cd));
+    LCASR_TRY(lcasr_subsample_dwconv(s2b, cd, w.dw2_w, w.dw2_b, B, p.T2, p.F2, C, s3a, stream));
+    LCASR_TRY(gemm(s3a, w.pw2_w, (int64_t)B * N * p.F3, C, C, w.pw2_b, LCASR_ACT_SILU, nullptr, 0.f, s3b, cd));
+    LCASR_TRY(gemm(s3b, w.sub_out_w, M, d, p.F3 * C, nullptr, LCASR_ACT_NONE, nullptr, 0.f, x, LCASR_F32));
+  }
+  if (c.use_rotary)
+    LCASR_TRY(lcasr_rope_table(w.inv_freq, c.rotary_interp, 0, N, Dh / 2, cos_t, sin_t, stream));
+
+  auto ffn = [&](const float* nw, const float* nb, const void* fc1, const float* b1, const void* fc2, const float* b2) {
+    LCASR_TRY(norm(nw, nb, nullptr, a));
+    LCASR_TRY(gemm(a, fc1, M, 4 * d, d, b1, LCASR_ACT_GELU_TANH, nullptr, 0.f, wide, cd));
+    LCASR_TRY(gemm(wide, fc2, M, d, 4 * d, b2, LCASR_ACT_NONE, x, 0.5f, x, LCASR_F32));  // x += 0.5*ffn
+    return 0;
+  };
+
+  for (int l = 0; l < c.n_layers; ++l) {
+    const lcasr_layer_weights& L = m->layers[l];
+    LCASR_TRY(ffn(L.ff1_norm_w, L.ff1_norm_b, L.ff1_fc1_w, L.ff1_fc1_b, L.ff1_fc2_w, L.ff1_fc2_b));
+    // attention (attention.py:509-551)
+    LCASR_TRY(norm(L.attn_norm_w, L.attn_norm_b, nullptr, a));
+    LCASR_TRY(gemm(a, L.qkv_w, M, 3 * d, d, nullptr, LCASR_ACT_NONE, nullptr, 0.f, wide, cd));
+    LCASR_TRY(lcasr_rope_split(wide, cd, B, N, H, Dh, c.use_rotary ? cos_t : nullptr, c.use_rotary ? sin_t : nullptr, q, k,
+                               v, vt, p.Npad, stream));
+    LCASR_TRY(lcasr_attention(q, k, v, cd, B, N, H, Dh, vt, p.Npad, a, ai, stream));
+    LCASR_TRY(gemm(a, L.out_w, M, d, d, nullptr, LCASR_ACT_NONE, x, 1.0f, x, LCASR_F32));
+    // convolution module (convolution.py:103-124)
+    LCASR_TRY(norm(L.conv_norm_w, L.conv_norm_b, nullptr, a));
+    LCASR_TRY(gemm(a, L.pw1_w, M, 2 * d, d, L.pw1_b, LCASR_ACT_NONE, nullptr, 0.f, wide, cd));
+    LCASR_TRY(lcasr_glu(wide, cd, M, d, q, stream));
+    LCASR_TRY(lcasr_dwconv_brn_silu(q, cd, B, N, d, c.conv_kernel_size, L.dw_w, L.dw_b, L.brn_mean, L.brn_std, L.brn_w,
+                                    L.brn_b, k, cd, stream));
+    LCASR_TRY(gemm(k, L.pw2_w, M, d, d, L.pw2_b, LCASR_ACT_NONE, x, 1.0f, x, LCASR_F32));
+    LCASR_TRY(ffn(L.ff2_norm_w, L.ff2_norm_b, L.ff2_fc1_w, L.ff2_fc1_b, L.ff2_fc2_w, L.ff2_fc2_b));
+    LCASR_TRY(norm(L.norm_out_w, L.norm_out_b, x, nullptr));
+    if (l != c.n_layers - 1 && c.self_conditioning) {  // sconformer_xl.py:241-243
+      if (c.decoder_norm) LCASR_TRY(norm(w.dec_norm_w, w.dec_norm_b, nullptr, a));
+      else LCASR_TRY(lcasr_cast_f32(x, M * d, a, cd, stream));
+      LCASR_TRY(gemm(a, w.dec_ff_w, M, V1, d, w.dec_ff_b, LCASR_ACT_NONE, nullptr, 0.f, wide, cd));
+      LCASR_TRY(lcasr_softmax(wide, cd, M, V1, wide, cd, stream));
+      LCASR_TRY(gemm(wide, w.dec_rep_w, M, d, V1, w.dec_rep_b, LCASR_ACT_NONE, x, 1.0f, x, LCASR_F32));
+    }
+  }
+  if (c.legasee_double_norm && c.decoder_norm) LCASR_TRY(norm(w.dec_norm_w, w.dec_norm_b, x, nullptr));
+  if (c.decoder_norm) LCASR_TRY(norm(w.dec_norm_w, w.dec_norm_b, nullptr, a));
+  else LCASR_TRY(lcasr_cast_f32(x, M * d, a, cd, stream));
+  LCASR_TRY(gemm(a, w.dec_ff_w, M, V1, d, w.dec_ff_b, LCASR_ACT_NONE, nullptr, 0.f, out, LCASR_F32));
+  if (!return_logits) LCASR_TRY(lcasr_log_softmax_argmax(out, M, V1, argmax, stream));
+  return 0;
+}
+
+extern "C" int lcasr_model_transcribe_host(lcasr_model* m, const float* spec_host, int B, int64_t T,
+                                           int32_t* tokens_host, int32_t* n_tokens_host, float* logp_dev,
+                                           void* workspace, int64_t workspace_bytes, void* stream) {
+  LCASR_CHECK_ARG(m && spec_host && tokens_host && n_tokens_host && logp_dev && workspace,
+                  "transcribe_host: NULL argument (logp_dev must hold B*N*num_classes floats + staging, see docs)");
+  const lcasr_config& c = m->cfg;
+  const int64_t N = lcasr_out_length(T);
+  cudaStream_t st = (cudaStream_t)stream;
+  // staging carved from the END of the caller's workspace: spec [B,F,T] fp32, argmax/tokens [B,N] i32, counts [B]
+  const size_t need_fwd = (size_t)lcasr_model_workspace_bytes(m, B, T);
+  const size_t spec_bytes = al((size_t)B * c.feat_in * T * 4), tok_bytes = al((size_t)B * N * 4), cnt_bytes = al((size_t)B * 4);
+  LCASR_CHECK_ARG((size_t)workspace_bytes >= need_fwd + spec_bytes + 2 * tok_bytes + cnt_bytes,
+                  "transcribe_host: workspace %lld < %lld bytes", (long long)workspace_bytes,
+                  (long long)(need_fwd + spec_bytes + 2 * tok_bytes + cnt_bytes));
+  char* ws = (char*)workspace;
+  float* spec_dev = (float*)(ws + need_fwd);
+  int32_t* am = (int32_t*)(ws + need_fwd + spec_bytes);
+  int32_t* tok = (int32_t*)(ws + need_fwd + spec_bytes + tok_bytes);
+  int32_t* cnt = (int32_t*)(ws + need_fwd + spec_bytes + 2 * tok_bytes);
+  LCASR_CUDA(cudaMemcpyAsync(spec_dev, spec_host, (size_t)B * c.feat_in * T * 4, cudaMemcpyHostToDevice, st));
+  LCASR_TRY(lcasr_model_forward(m, spec_dev, B, T, logp_dev, am, 0, workspace, (int64_t)need_fwd, stream));
+  LCASR_TRY(lcasr_greedy_collapse(am, B, N, nullptr, c.num_classes - 1, tok, cnt, stream));
+  LCASR_CUDA(cudaMemcpyAsync(tokens_host, tok, (size_t)B * N * 4, cudaMemcpyDeviceToHost, st));
+  LCASR_CUDA(cudaMemcpyAsync(n_tokens_host, cnt, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  LCASR_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int64_t lcasr_model_transcribe_workspace_bytes(const lcasr_model* m, int B, int64_t T) {
+  if (!m || B <= 0 || T <= 0) return -1;
+  const int64_t N = lcasr_out_length(T);
+  return lcasr_model_workspace_bytes(m, B, T) + (int64_t)al((size_t)B * m->cfg.feat_in * T * 4) +
+         2 * (int64_t)al((size_t)B * N * 4) + (int64_t)al((size_t)B * 4);
+}

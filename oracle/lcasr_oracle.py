@@ -383,8 +383,11 @@ def _ctc_alpha(lp: np.ndarray, tgt: np.ndarray, blank: int) -> np.ndarray:
         alpha[0, 1] = lp[0, ext[1]]
     for t in range(1, T):
         a = alpha[t - 1]
-        a1 = np.concatenate(([-np.inf], a[:-1]))
-        a2 = np.where(skip, np.concatenate(([-np.inf, -np.inf], a[:-2])), -np.inf)
+        a1 = np.full(Lp, -np.inf)
+        a1[1:] = a[:-1]
+        a2 = np.full(Lp, -np.inf)
+        a2[2:] = a[:-2]
+        a2 = np.where(skip, a2, -np.inf)
         alpha[t] = _logaddexp3(a, a1, a2) + lp[t, ext]
     return alpha
 

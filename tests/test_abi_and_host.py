@@ -1,0 +1,92 @@
+"""CPU: the C-ABI library loads and exports every symbol include/lcasr_b200.h declares; host-side
+logic of the drop-in classes (constructor kwargs, state_dict layout, error behaviour).  No kernels
+are launched here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, GOLDEN_CASES, load_golden
+from oracle import lcasr_oracle as O
+
+
+def test_library_exports_every_declared_symbol():
+    import lcasr_b200
+    header = open(os.path.join(ROOT, "include", "lcasr_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(lcasr_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(lcasr_b200._lib.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    assert set(lcasr_b200._lib.EXPORTED_SYMBOLS) <= declared
+    assert lib.lcasr_abi_version() == 1
+
+
+def test_out_length_host_function():
+    import lcasr_b200
+    for T in (1, 2, 7, 8, 9, 264, 1000, 1024, 16384, 131072, 360000):
+        assert lcasr_b200.ops.out_length(T) == O.calc_length(T)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_state_dict_layout_matches_reference(name):
+    import lcasr_b200
+    g = load_golden(name)
+    cfg = O.make_config(**g["config"])
+    model = lcasr_b200.SCConformerXL(**cfg)
+    mine = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert mine == g["state_dict_shapes"]
+    sd = O.synth_state_dict(cfg, seed=g["weight_seed"], peak=g["peak"])
+    model.load_state_dict(sd, strict=True)  # bin/load_pretrained.py:58 loads strict
+
+
+def test_constructor_accepts_reference_kwargs_and_rejects_off_path_ones():
+    import lcasr_b200
+    # kwargs found in the released configs that the reference swallows through **kwargs
+    m = lcasr_b200.SCConformerXL(vocab_size=127, n_layers=1, d_model=64, n_heads=2, head_dim=32, subsampling_conv_channels=32,
+                                 qk_rms_norm=False, shift_kvs=False, gated_sc=False, encoder_mode="conformer",
+                                 self_condition_subsampling=False, ff_checkpoint_lvl=2, rotary_base_freq=1500000,
+                                 flash_attn=True, checkpoint_every_n_layers=1, use_rotary=True, decoder_norm=True)
+    assert m.decoder.num_classes == 128 and m.subsampling.subsampling_factor == 8
+    assert float(m.rotary_pos_emb.rotary_interpolation_factor) == 1.0
+    assert m.layers[0].attend.fn.n_heads == 2
+    with pytest.raises(AssertionError):
+        lcasr_b200.SCConformerXL(default_norm="batch_norm")
+    with pytest.raises(NotImplementedError):
+        lcasr_b200.SCConformerXL(subsampling="stacking")
+    with pytest.raises(NotImplementedError):
+        lcasr_b200.SCConformerXL(attention_window_size=128)
+
+
+def test_no_cpu_fallback():
+    import lcasr_b200
+    m = lcasr_b200.SCConformerXL(vocab_size=127, n_layers=1, d_model=64, n_heads=2, head_dim=32, subsampling_conv_channels=32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(1, 80, 64))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        lcasr_b200.GreedyCTCDecoder(None, 127)(torch.randn(5, 128))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        lcasr_b200.CTCLoss(blank=127)(torch.randn(5, 1, 128), torch.zeros(1, 2, dtype=torch.long), torch.tensor([5]), torch.tensor([2]))
+
+
+def test_param_groups_follow_reference_rule():
+    import lcasr_b200
+    m = lcasr_b200.SCConformerXL(vocab_size=127, n_layers=1, d_model=64, n_heads=2, head_dim=32, subsampling_conv_channels=32,
+                                 decoder_norm=True, use_rotary=True)
+    groups = m.get_param_groups({"weight_decay": 0.1})
+    n_all = sum(1 for _ in m.parameters())
+    assert len(groups) == 2 and len(groups[0]["params"]) + len(groups[1]["params"]) == n_all
+    assert groups[1]["weight_decay"] == 0.0
+    assert not isinstance(m.get_param_groups({"weight_decay": 0.0}), list)
+
+
+def test_bad_arguments_return_errors_not_crashes():
+    import lcasr_b200
+    L = lcasr_b200._lib
+    assert L.lib.lcasr_gemm(None, None, 0, 4, 4, 4, None, 0, None, 1.0, None, 0, 0, None) == -1
+    assert b"NULL" in L.lib.lcasr_last_error()
+    assert L.lib.lcasr_layernorm(None, None, None, 1, 8, 1e-5, 0, None, None, 0, None) == -1
+    assert L.lib.lcasr_model_workspace_bytes(None, 1, 100) == -1

@@ -1,0 +1,214 @@
+"""GPU parity of every unit operator of the C ABI against the oracle / torch fp32 on the same
+seeded inputs.  fp32 kernels: ~1e-5 relative; bf16 kernels: <= ~1 bf16 ulp of the output scale."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import report
+from oracle import lcasr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+@pytest.mark.parametrize("d", [64, 256, 768, 2048, 200])
+@pytest.mark.parametrize("kind", ["layer_norm", "rms_norm"])
+def test_layernorm(cuda_device, d, kind):
+    from lcasr_b200 import ops
+    M = 333
+    x = _rand(M, d, seed=1, scale=3.0) + 0.7
+    w, b = 1 + 0.1 * _rand(d, seed=2), 0.1 * _rand(d, seed=3)
+    if kind == "layer_norm":
+        ref = F.layer_norm(x, (d,), w, b, 1e-5)
+        eps = 1e-5
+    else:
+        ref = w * (x / (x.norm(2, dim=-1, keepdim=True) * d ** -0.5 + 1e-8))
+        b, eps = None, 1e-8
+    xc = x.to(cuda_device)
+    o32, obf = ops.layernorm(xc, w.to(cuda_device), None if b is None else b.to(cuda_device), eps, kind, out_f32=True,
+                             lo_dtype=torch.bfloat16)
+    assert (o32.cpu() - ref).abs().max() < 2e-5
+    assert (obf.float().cpu() - ref).abs().max() < 2 ** -8 * ref.abs().max()
+    # in place
+    ops_out = xc.clone()
+    from lcasr_b200 import _lib as L
+    L.call("lcasr_layernorm", ops_out.data_ptr(), w.to(cuda_device).data_ptr(), None if b is None else b.to(cuda_device).data_ptr(),
+           M, d, eps, 1 if kind == "rms_norm" else 0, ops_out.data_ptr(), None, 0, L.current_stream())
+    assert (ops_out.cpu() - ref).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("C,T,B", [(32, 264, 2), (256, 1024, 1), (512, 77, 1)])
+def test_subsampling_stencils(cuda_device, C, T, B):
+    from lcasr_b200 import ops
+    Fq = 80
+    spec = _rand(B, Fq, T, seed=4)
+    w0, b0 = _rand(C, 1, 3, 3, seed=5), 0.1 * _rand(C, seed=6)
+    ref0 = F.silu(F.conv2d(spec.transpose(1, 2).unsqueeze(1), w0, b0, stride=2, padding=1))  # [B,C,T1,F1]
+    for dt, tol in ((torch.float32, 1e-5), (torch.bfloat16, 2 ** -8)):
+        got = ops.subsample_conv0(spec.to(cuda_device), w0.reshape(C, 9).contiguous().to(cuda_device), b0.to(cuda_device), dt)
+        got = got.float().cpu().permute(0, 3, 1, 2)
+        assert got.shape == ref0.shape
+        assert (got - ref0).abs().max() < tol * max(1.0, ref0.abs().max())
+    w1, b1 = _rand(C, 1, 3, 3, seed=7), 0.1 * _rand(C, seed=8)
+    ref1 = F.conv2d(ref0, w1, b1, stride=2, padding=1, groups=C)
+    x_cl = ref0.permute(0, 2, 3, 1).contiguous()
+    for dt, tol in ((torch.float32, 1e-5), (torch.bfloat16, 2 ** -7)):
+        got = ops.subsample_dwconv(x_cl.to(cuda_device, dt), w1.reshape(C, 9).contiguous().to(cuda_device), b1.to(cuda_device))
+        got = got.float().cpu().permute(0, 3, 1, 2)
+        assert got.shape == ref1.shape
+        assert (got - ref1).abs().max() < tol * max(1.0, ref1.abs().max())
+
+
+@pytest.mark.parametrize("M,N,K", [(66, 192, 64), (333, 128, 320), (1000, 4096, 256), (128, 256, 4096), (257, 72, 36)])
+def test_gemm_simt_fp32(cuda_device, M, N, K):
+    from lcasr_b200 import ops, _lib as L
+    a, w = _rand(M, K, seed=9), _rand(N, K, seed=10) / math.sqrt(K)
+    bias, resid = _rand(N, seed=11), _rand(M, N, seed=12)
+    ref = a.double() @ w.double().T
+    ac, wc = a.to(cuda_device), w.to(cuda_device)
+    got = ops.gemm(ac, wc, impl=L.GEMM_SIMT)
+    assert (got.cpu().double() - ref).abs().max() < 1e-5 * max(1.0, ref.abs().max())
+    got = ops.gemm(ac, wc, bias=bias.to(cuda_device), act=L.ACT_GELU_TANH, impl=L.GEMM_SIMT)
+    assert (got.cpu() - F.gelu((ref + bias).float(), approximate="tanh")).abs().max() < 2e-5
+    got = ops.gemm(ac, wc, bias=bias.to(cuda_device), act=L.ACT_SILU, impl=L.GEMM_SIMT)
+    assert (got.cpu() - F.silu((ref + bias).float())).abs().max() < 2e-5
+    r = resid.to(cuda_device)
+    got = ops.gemm(ac, wc, bias=bias.to(cuda_device), resid=r, alpha=0.5, impl=L.GEMM_SIMT, out=r)  # in place
+    assert (got.cpu() - (resid + 0.5 * (ref + bias).float())).abs().max() < 2e-5
+
+
+def test_glu_and_cast(cuda_device):
+    from lcasr_b200 import ops
+    x = _rand(77, 2 * 256, seed=13)
+    ref = F.glu(x, dim=-1)
+    assert (ops.glu(x.to(cuda_device)).cpu() - ref).abs().max() < 1e-6
+    assert (ops.glu(x.to(cuda_device, torch.bfloat16)).float().cpu() - F.glu(x.bfloat16().float(), -1)).abs().max() < 2 ** -8 * 4
+
+
+@pytest.mark.parametrize("Dh,base", [(32, 1500000), (128, 1500000), (64, 10000)])
+def test_rope_table_and_split(cuda_device, Dh, base):
+    from lcasr_b200 import ops
+    N, B, H = 300, 2, 3
+    inv_freq = 1.0 / (base ** (torch.arange(0, Dh, 2).float() / Dh))
+    sd = {"rotary_pos_emb.inv_freq": inv_freq, "rotary_pos_emb.rotary_interpolation_factor": torch.tensor(1.0)}
+    for off in (0, 44000):
+        cos_ref, sin_ref = O.rotary_tables(sd, N, offset=off)
+        cos, sin = ops.rope_table(inv_freq.to(cuda_device), 1.0, N, offset=off)
+        assert (cos.cpu() - cos_ref[:, : Dh // 2]).abs().max() < 2e-6  # same fp32 angle; libm vs CUDA sincos
+        assert (sin.cpu() - sin_ref[:, : Dh // 2]).abs().max() < 2e-6
+    cos_ref, sin_ref = O.rotary_tables(sd, N)
+    cos, sin = ops.rope_table(inv_freq.to(cuda_device), 1.0, N)
+    d = H * Dh
+    qkv = _rand(B * N, 3 * d, seed=14)
+    q_ref, k_ref, v_ref = [t.reshape(B, N, H, Dh) for t in qkv.split(d, dim=-1)]
+    c, s = cos_ref[None, :, None, :], sin_ref[None, :, None, :]
+    q_rot = q_ref * c + O.rotate_half(q_ref) * s
+    k_rot = k_ref * c + O.rotate_half(k_ref) * s
+    q, k, v = ops.rope_split(qkv.to(cuda_device), B, N, H, Dh, cos, sin)
+    assert (q.cpu() - q_rot).abs().max() < 1e-5 and (k.cpu() - k_rot).abs().max() < 1e-5
+    assert torch.equal(v.cpu(), v_ref)
+    q, k, vt = ops.rope_split(qkv.to(cuda_device), B, N, H, Dh, cos, sin, v_transposed=True)
+    assert torch.equal(vt.cpu()[..., :N], v_ref.permute(0, 2, 3, 1))
+    q, k, v = ops.rope_split(qkv.to(cuda_device), B, N, H, Dh, None, None)
+    assert torch.equal(q.cpu(), q_ref) and torch.equal(k.cpu(), k_ref)
+
+
+@pytest.mark.parametrize("Dh,N,H,B", [(32, 33, 2, 2), (128, 125, 1, 1), (32, 300, 3, 1), (64, 64, 2, 1), (128, 257, 2, 2)])
+def test_attention_simt(cuda_device, Dh, N, H, B):
+    from lcasr_b200 import ops, _lib as L
+    q, k, v = (_rand(B, N, H, Dh, seed=s) for s in (15, 16, 17))
+    ref = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)).transpose(1, 2).reshape(B, N, H * Dh)
+    got = ops.attention(q.to(cuda_device), k.to(cuda_device), v.to(cuda_device), impl=L.ATTN_SIMT)
+    assert (got.cpu() - ref).abs().max() < 2e-5
+    gb = ops.attention(q.to(cuda_device, torch.bfloat16), k.to(cuda_device, torch.bfloat16), v.to(cuda_device, torch.bfloat16),
+                       impl=L.ATTN_SIMT)
+    assert (gb.float().cpu() - ref).abs().max() < 3e-2
+
+
+@pytest.mark.parametrize("d,N,B", [(64, 50, 2), (256, 128, 1), (768, 333, 1)])
+def test_dwconv_brn_silu(cuda_device, d, N, B):
+    from lcasr_b200 import ops
+    x = _rand(B, N, d, seed=18)
+    w, b = _rand(d, 1, 9, seed=19) / 3, 0.1 * _rand(d, seed=20)
+    rm, rs = 0.1 * _rand(d, seed=21), 0.75 + 0.5 * torch.rand(d, generator=torch.Generator().manual_seed(22))
+    bw, bb = 1 + 0.1 * _rand(d, seed=23), 0.1 * _rand(d, seed=24)
+    y = F.conv1d(x.transpose(1, 2), w, b, padding=4, groups=d)
+    y = (y - rm[None, :, None]) / rs[None, :, None] * bw[None, :, None] + bb[None, :, None]
+    ref = F.silu(y).transpose(1, 2)
+    args = [t.to(cuda_device) for t in (w.reshape(d, 9).contiguous(), b, rm, rs, bw, bb)]
+    got = ops.dwconv_brn_silu(x.to(cuda_device), *args)
+    assert (got.cpu() - ref).abs().max() < 1e-5
+    gb = ops.dwconv_brn_silu(x.to(cuda_device, torch.bfloat16), *args)
+    assert (gb.float().cpu() - ref).abs().max() < 2 ** -7 * max(1.0, ref.abs().max())
+
+
+@pytest.mark.parametrize("V", [128, 256, 4096])
+def test_softmax_logsoftmax_argmax(cuda_device, V):
+    from lcasr_b200 import ops
+    x = _rand(77, V, seed=25, scale=3.0)
+    x[5, 17] = x[5].max() + 1.0
+    x[5, 90] = x[5, 17]  # tie: first index must win (torch.argmax semantics)
+    assert (ops.softmax(x.to(cuda_device)).cpu() - x.softmax(-1)).abs().max() < 1e-6
+    sb = ops.softmax(x.to(cuda_device, torch.bfloat16)).float().cpu()
+    assert (sb - x.bfloat16().float().softmax(-1)).abs().max() < 2 ** -8
+    lg = x.to(cuda_device).clone()
+    am = ops.log_softmax_argmax_(lg)
+    assert (lg.cpu() - x.log_softmax(-1)).abs().max() < 2e-6
+    assert torch.equal(am.cpu().long(), x.argmax(-1))
+    assert int(am[5]) == 17
+    assert torch.equal(ops.argmax_rows(x.to(cuda_device)).cpu().long(), x.argmax(-1))
+
+
+def test_greedy_collapse(cuda_device):
+    from lcasr_b200 import ops
+    blank = 9
+    g = torch.Generator().manual_seed(26)
+    for N in (1, 5, 1024, 1025, 5000):
+        ids = torch.randint(7, 10, (3, N), generator=g).int()
+        ids[1] = blank  # all blank
+        tokens, n = ops.greedy_collapse(ids.to(cuda_device), blank)
+        for b in range(3):
+            ref = [i for i in torch.unique_consecutive(ids[b]).tolist() if i != blank]
+            assert tokens[b, : int(n[b])].tolist() == ref
+    ids = torch.randint(0, 4, (2, 100), generator=g).int()
+    lens = torch.tensor([100, 37], dtype=torch.int32)
+    tokens, n = ops.greedy_collapse(ids.to(cuda_device), 3, lens.to(cuda_device))
+    ref = [i for i in torch.unique_consecutive(ids[1, :37]).tolist() if i != 3]
+    assert tokens[1, : int(n[1])].tolist() == ref
+
+
+@pytest.mark.parametrize("B,N,V,S", [(2, 33, 128, 9), (1, 128, 4096, 38), (3, 50, 16, 0), (2, 700, 256, 300), (1, 40, 8, 20)])
+def test_ctc_loss_forward_backward(cuda_device, B, N, V, S):
+    import lcasr_b200
+    from lcasr_b200 import ops
+    blank = V - 1
+    g = torch.Generator().manual_seed(27)
+    lp = torch.randn(B, N, V, generator=g).log_softmax(-1)
+    Sm = max(S, 1)
+    tgt = torch.randint(0, V - 1, (B, Sm), generator=g)
+    if S >= 4:
+        tgt[:, 2] = tgt[:, 1]  # repeated labels
+    tl = torch.tensor([S if b == 0 else max(S - b, 0) for b in range(B)], dtype=torch.long)
+    il = torch.tensor([N if b == 0 else N - 3 * b for b in range(B)], dtype=torch.int32)
+    ref = O.ctc_loss(lp.numpy(), tgt.numpy(), il.numpy(), tl.numpy(), blank)
+    nll, alpha = ops.ctc_loss_fwd(lp.to(cuda_device), tgt.to(cuda_device), il.to(cuda_device), tl.to(cuda_device), blank,
+                                  keep_alpha=True)
+    np.testing.assert_allclose(nll.cpu().numpy(), ref, rtol=1e-4)  # north_star: CTC loss within 1e-3 relative
+    tref = F.ctc_loss(lp.transpose(0, 1), tgt, il.long(), tl, blank=blank, reduction="none")
+    np.testing.assert_allclose(nll.cpu().numpy(), tref.numpy(), rtol=1e-4)
+    # backward through the drop-in module, reduction='sum' as exp/train.py:104
+    lpc = lp.to(cuda_device).requires_grad_(True)
+    loss = lcasr_b200.CTCLoss(blank=blank, reduction="sum")(lpc.transpose(0, 1), tgt, il, tl)
+    loss.backward()
+    gref = O.ctc_grad(lp.numpy(), tgt.numpy(), il.numpy(), tl.numpy(), blank)
+    assert abs(loss.item() - ref.sum()) < 1e-4 * abs(ref.sum())
+    np.testing.assert_allclose(lpc.grad.cpu().numpy(), gref, rtol=1e-3, atol=2e-4)
+    report(test="ctc", B=B, N=N, V=V, S=S, nll_rel=float(np.abs(nll.cpu().numpy() - ref).max() / np.abs(ref).max()),
+           grad_abs=float(np.abs(lpc.grad.cpu().numpy() - gref).max()))
