@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py — audio-seconds/second of the encoder + CTC hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, sm_100a)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+
+A step = one pass of the hot path over one batch of synthetic recordings:
+SCConformerXL.forward (8x conv subsampling, L conformer layers, self-conditioned CTC head, log-softmax
++ per-frame argmax) followed by the greedy CTC collapse.  Default workload = the configuration the
+metric is quoted on, BASELINE.json configs[2]: 6L-768D-24H (head dim 32) at 20-min context
+(131072 frames), one recording per GPU; it fits one GPU.  N > 1: one process per GPU (torchrun), each
+rank transcribes its own recording — recordings are independent, no data-path collective ("weak").
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (model key in oracle.BASELINE_MODELS, frames T, recordings per GPU)
+    "cfg1": ("cfg1_6L256D8H", 1024, 1),
+    "cfg2": ("cfg2_9L768D6H", 16384, 16),
+    "cfg3": ("cfg3_6L768D24H", 131072, 1),
+    "cfg4": ("cfg4_3L2048D16H", 360000, 1),
+}
+CATS = ["subsample", "norm", "gemm", "attention", "rope", "convmod", "softmax"]
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def flops_forward(cfg, T, N):
+    """Algorithmic forward FLOPs per recording (SURVEY §8d formulas; 2*m*n*k, full N x N attention)."""
+    d, C, L, V1 = cfg["d_model"], cfg["subsampling_conv_channels"], cfg["n_layers"], cfg["vocab_size"] + 1
+    sub = 2 * 9 * C * (T // 2) * 40 + 2 * 9 * C * (T // 4) * 20 + 2 * C * C * (T // 4) * 20 + 2 * 9 * C * N * 10 + 2 * C * C * N * 10 + 2 * 10 * C * d * N
+    layer = N * (46 * d * d + 18 * d) + 4 * N * N * d
+    sc = (L - 1) * N * 4 * d * V1 if cfg["self_conditioning"] else 0
+    return sub + L * layer + sc + N * 2 * d * V1
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def cpu_reference_run(cfg, B, T, steps, warmup, budget_s):
+    """The reference's CPU path (eval/run_eval_cpu.sh-style: fp32, eval, no autocast, one forward over the
+    whole context + GreedyCTCDecoder) via the oracle port, on all host cores.  Returns (audio_s_per_s,
+    seconds per step, steps actually timed, cores)."""
+    import torch
+    from oracle import lcasr_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.synth_state_dict(cfg, seed=12345)
+    x = O.synth_input(B, T, cfg["feat_in"], seed=1234)
+    V = cfg["vocab_size"]
+
+    def step():
+        with torch.no_grad():
+            lp, _ = O.encoder_forward(sd, cfg, x)
+            return [O.greedy_decode(lp[b], V) for b in range(B)]
+
+    t_start = time.perf_counter()
+    did_warm = 0
+    for _ in range(warmup):
+        if did_warm >= 1 and time.perf_counter() - t_start > 0.2 * budget_s:
+            break
+        step(); did_warm += 1
+    times = []
+    for _ in range(max(1, steps)):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    per_step = sum(times) / len(times)
+    return B * T / 100.0 / per_step, per_step, len(times), cores, did_warm
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="recordings per GPU (0 = workload default)")
+    ap.add_argument("--frames", type=int, default=0, help="override context length in 10 ms frames")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    args = ap.parse_args()
+
+    from oracle import lcasr_oracle as O  # cpu_baseline leg / --impl reference only (never the product path)
+    rank, world, local = dist_env()
+    mkey, T, B = WORKLOADS[args.workload]
+    T = args.frames or T
+    B = args.batch or B
+    cfg = O.make_config(**O.BASELINE_MODELS[mkey])
+    N = O.calc_length(T)
+    audio_s = B * T / 100.0
+    config = {"workload": f"{args.workload}: lcasr {mkey} random-init, {T} frames ({T / 6000:.1f} min) context, "
+                          f"{B} recording(s)/GPU, forward + CTC log-softmax + greedy decode",
+              "frames": T, "tokens": N, "recordings_per_gpu": B, "parallelism": f"batch-parallel x{args.gpus} (independent recordings)",
+              "l2": "working set (>1 GB of activations per step) exceeds the 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        v, per_step, done, cores, warm = cpu_reference_run(cfg, B, T, args.steps, args.warmup, 2.0 * args.cpu_budget_s)
+        line = {"impl": "reference", "metric": "audio-sec/sec encoder+CTC", "value": v, "unit": "audio-s/s", "n_gpus": args.gpus,
+                "steps": done, "warmup": warm, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                 "sample": f"{done} of {args.steps} requested steps timed, each one full {T}-frame forward + greedy "
+                                           f"decode of {B} recording(s) through the oracle port (fp32, torch CPU ops)"},
+                "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import lcasr_b200
+    from lcasr_b200 import _lib as L
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sd = O.synth_state_dict(cfg, seed=12345)          # deterministic random-init weights (no checkpoints offline)
+    model = lcasr_b200.SCConformerXL(**cfg, compute_dtype=args.dtype)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+    x_host = O.synth_input(B, T, cfg["feat_in"], seed=1234 + rank).pin_memory()
+    x = x_host.to(dev)
+    dec = lcasr_b200.GreedyCTCDecoder(None, blank_id=cfg["vocab_size"])
+
+    def step_device():
+        model(x)
+        return lcasr_b200.ops.greedy_collapse(model.last_argmax, cfg["vocab_size"])
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    # ---- device-resident timing: exactly K steps between barriers, CUDA events, max over ranks ----
+    L.call("lcasr_model_set_timing", model._handle, 1)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    L.lib.lcasr_reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    launches = int(L.lib.lcasr_launch_count())
+    clocks = sampler.stop() if sampler else None
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms = (ctypes.c_float * len(CATS))()
+    cnt = (ctypes.c_int32 * len(CATS))()
+    L.call("lcasr_model_get_timing", model._handle, ms, cnt, len(CATS))
+    L.call("lcasr_model_set_timing", model._handle, 0)
+    ms_per_step = ms_total / args.steps
+    value = world * audio_s / (ms_per_step / 1e3)
+
+    # ---- end to end through the public API with HOST buffers (H2D + forward + collapse + D2H tokens) ----
+    for _ in range(2):
+        model.transcribe_host(x_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        toks = model.transcribe_host(x_host)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+    e2e_value = world * audio_s / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = load_peaks()
+    d, H, Dh = cfg["d_model"], cfg["n_heads"], cfg["head_dim"]
+    kern = {}
+    for name, m_, c_ in zip(CATS, ms, cnt):
+        kern[name] = {"ms_per_step": m_ / args.steps, "launches_per_step": c_ / args.steps}
+    attn_launch_s = (ms[3] / max(1, cnt[3])) / 1e3
+    attn_flops = 4.0 * B * N * N * d                       # per launch (one layer): QK^T + PV, full N x N
+    gemm_flops = flops_forward(cfg, T, N) * B - cfg["n_layers"] * attn_flops
+    achieved = attn_flops / attn_launch_s / 1e12 if attn_launch_s > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload)
+        except (ValueError, OSError):
+            traffic = None
+    roofline = {"kernel": "attention (flash, non-causal, fused softmax)", "bound": "tensor", "achieved": achieved,
+                "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sust"], "traffic": traffic,
+                "peak_source": peaks["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+                "launch_ms": attn_launch_s * 1e3, "algorithmic_flops_per_launch": attn_flops,
+                "share_of_step": (ms[3] / args.steps) / ms_per_step,
+                "gemm_tflops": gemm_flops / ((ms[2] / args.steps) / 1e3) / 1e12 if ms[2] > 0 else None,
+                "model_tflops_per_step": flops_forward(cfg, T, N) * B / 1e12}
+
+    line = {"metric": "audio-sec/sec encoder+CTC", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
+                    "d2h_bytes_per_step": int(B * N * 4 + B * 4), "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": launches, "roofline": roofline, "kernels": kern}
+
+    if not args.no_cpu_baseline and world == 1:
+        v, per_step, done, cores, _ = cpu_reference_run(cfg, B, T, 1, 0, args.cpu_budget_s)
+        line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                "sample": f"one full {T}-frame forward + greedy decode of {B} recording(s) through the oracle "
+                                          f"port (fp32 torch CPU ops, {cores} threads), {per_step:.1f} s"}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -195,6 +195,14 @@ void lcasr_model_destroy(lcasr_model* m);
 /* test / profiling hook: force the GEMM (LCASR_GEMM_*) and attention (LCASR_ATTN_*) kernels */
 int lcasr_model_set_impl(lcasr_model* m, int gemm_impl, int attn_impl);
 
+/* In-step kernel timing for the roofline report: when enabled, lcasr_model_forward brackets every
+ * kernel launch with CUDA events on the launch stream; lcasr_model_get_timing synchronises, returns
+ * the summed milliseconds / launch counts per category and clears the recorder.
+ * Categories: 0 subsampling stencils, 1 norms/casts, 2 GEMMs, 3 attention, 4 rotary, 5 conv module
+ * (GLU, dwconv+BRN+SiLU), 6 softmax / log-softmax+argmax.  ncat >= 7. */
+int lcasr_model_set_timing(lcasr_model* m, int enable);
+int lcasr_model_get_timing(lcasr_model* m, float* ms_by_cat, int32_t* launches_by_cat, int ncat);
+
 /* tokens after 8x subsampling: calc_length (subsampling.py:557-567) applied three times */
 int64_t lcasr_out_length(int64_t T);
 

@@ -70,6 +70,8 @@ _SIGNATURES = {
     "lcasr_ctc_loss_bwd": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp],
     "lcasr_model_create": [C.POINTER(LcasrConfig), C.POINTER(LcasrWeights), C.POINTER(vp)],
     "lcasr_model_set_impl": [vp, i32, i32],
+    "lcasr_model_set_timing": [vp, i32],
+    "lcasr_model_get_timing": [vp, vp, vp, i32],
     "lcasr_model_forward": [vp, vp, i32, i64, vp, vp, i32, vp, i64, vp],
     "lcasr_model_transcribe_host": [vp, vp, i32, i64, vp, vp, vp, vp, i64, vp],
 }

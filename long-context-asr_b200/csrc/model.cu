@@ -19,12 +19,32 @@ int attn_tc_available();
 
 using namespace lcasr;
 
+// kernel categories for the in-step CUDA-event timing (bench.py's roofline numbers)
+enum { CAT_SUBSAMPLE = 0, CAT_NORM, CAT_GEMM, CAT_ATTN, CAT_ROPE, CAT_CONVMOD, CAT_SOFTMAX, CAT_COUNT };
+
 struct lcasr_model {
   lcasr_config cfg;
   lcasr_weights w;
   std::vector<lcasr_layer_weights> layers;
   int attn_impl = LCASR_ATTN_AUTO;
   int gemm_impl = LCASR_GEMM_AUTO;
+  // optional per-op timing: (start,end) event pairs recorded on the launch stream
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool;
+  struct Span { int cat; size_t e0, e1; };
+  std::vector<Span> spans;
+  size_t ev_used = 0;
+  cudaEvent_t next_event() {
+    if (ev_used == ev_pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev_pool.push_back(e);
+    }
+    return ev_pool[ev_used++];
+  }
+  ~lcasr_model() {
+    for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+  }
 };
 
 namespace {
@@ -139,27 +159,52 @@ extern "C" int lcasr_model_forward(lcasr_model* m, const float* spec, int B, int
   if (ai == LCASR_ATTN_AUTO) ai = (cd == LCASR_BF16 && attn_tc_available()) ? LCASR_ATTN_TCGEN05 : LCASR_ATTN_SIMT;
   const int vt = ai == LCASR_ATTN_TCGEN05 ? 1 : 0;
 
+  cudaStream_t cst = (cudaStream_t)stream;
+  auto timed = [&](int cat, int status) {  // closes the span opened by begin()
+    if (m->timing && !m->spans.empty() && m->spans.back().e1 == (size_t)-1) {
+      m->spans.back().e1 = m->ev_used;
+      cudaEventRecord(m->next_event(), cst);
+    }
+    (void)cat;
+    return status;
+  };
+  auto begin = [&](int cat) {
+    if (m->timing) {
+      m->spans.push_back({cat, m->ev_used, (size_t)-1});
+      cudaEventRecord(m->next_event(), cst);
+    }
+    return cat;
+  };
+#define OP(cat, expr)            \
+  do {                           \
+    begin(cat);                  \
+    int _st = (expr);            \
+    timed(cat, _st);             \
+    if (_st != 0) return _st;    \
+  } while (0)
   auto gemm = [&](const void* A, const void* W, int64_t rows, int n, int kk, const float* bias, int act,
                   const float* resid, float alpha, void* o, int odt) {
-    return lcasr_gemm(A, W, cd, rows, n, kk, bias, act, resid, alpha, o, odt, gi, stream);
+    begin(CAT_GEMM);
+    return timed(CAT_GEMM, lcasr_gemm(A, W, cd, rows, n, kk, bias, act, resid, alpha, o, odt, gi, stream));
   };
   auto norm = [&](const float* nw, const float* nb, float* o32, void* olo) {
-    return lcasr_layernorm(x, nw, nb, M, d, c.norm_eps, c.norm_kind, o32, olo, cd, stream);
+    begin(CAT_NORM);
+    return timed(CAT_NORM, lcasr_layernorm(x, nw, nb, M, d, c.norm_eps, c.norm_kind, o32, olo, cd, stream));
   };
 
   // ---- subsampling (subsampling.py:384-428) ----
   {
     void* s1 = ws + p.off_s1; void* s2a = ws + p.off_s2a; void* s2b = ws + p.off_s2b;
     void* s3a = ws + p.off_s3a; void* s3b = ws + p.off_s3b;
-    LCASR_TRY(lcasr_subsample_conv0(spec, w.conv0_w, w.conv0_b, B, c.feat_in, T, C, s1, cd, stream));
-    LCASR_TRY(lcasr_subsample_dwconv(s1, cd, w.dw1_w, w.dw1_b, B, p.T1, p.F1, C, s2a, stream));
+    OP(CAT_SUBSAMPLE, lcasr_subsample_conv0(spec, w.conv0_w, w.conv0_b, B, c.feat_in, T, C, s1, cd, stream));
+    OP(CAT_SUBSAMPLE, lcasr_subsample_dwconv(s1, cd, w.dw1_w, w.dw1_b, B, p.T1, p.F1, C, s2a, stream));
     LCASR_TRY(gemm(s2a, w.pw1_w, (int64_t)B * p.T2 * p.F2, C, C, w.pw1_b, LCASR_ACT_SILU, nullptr, 0.f, s2b, cd));
-    LCASR_TRY(lcasr_subsample_dwconv(s2b, cd, w.dw2_w, w.dw2_b, B, p.T2, p.F2, C, s3a, stream));
+    OP(CAT_SUBSAMPLE, lcasr_subsample_dwconv(s2b, cd, w.dw2_w, w.dw2_b, B, p.T2, p.F2, C, s3a, stream));
     LCASR_TRY(gemm(s3a, w.pw2_w, (int64_t)B * N * p.F3, C, C, w.pw2_b, LCASR_ACT_SILU, nullptr, 0.f, s3b, cd));
     LCASR_TRY(gemm(s3b, w.sub_out_w, M, d, p.F3 * C, nullptr, LCASR_ACT_NONE, nullptr, 0.f, x, LCASR_F32));
   }
   if (c.use_rotary)
-    LCASR_TRY(lcasr_rope_table(w.inv_freq, c.rotary_interp, 0, N, Dh / 2, cos_t, sin_t, stream));
+    OP(CAT_ROPE, lcasr_rope_table(w.inv_freq, c.rotary_interp, 0, N, Dh / 2, cos_t, sin_t, stream));
 
   auto ffn = [&](const float* nw, const float* nb, const void* fc1, const float* b1, const void* fc2, const float* b2) {
     LCASR_TRY(norm(nw, nb, nullptr, a));
@@ -168,38 +213,67 @@ extern "C" int lcasr_model_forward(lcasr_model* m, const float* spec, int B, int
     return 0;
   };
 
+  // transposed-V layout: the key padding columns [N, Npad) are read by TMA (times P == 0): keep them finite
+  if (vt) LCASR_CUDA(cudaMemsetAsync(v, 0, (size_t)B * H * Dh * p.Npad * dtype_size(cd), cst));
+
   for (int l = 0; l < c.n_layers; ++l) {
     const lcasr_layer_weights& L = m->layers[l];
     LCASR_TRY(ffn(L.ff1_norm_w, L.ff1_norm_b, L.ff1_fc1_w, L.ff1_fc1_b, L.ff1_fc2_w, L.ff1_fc2_b));
     // attention (attention.py:509-551)
     LCASR_TRY(norm(L.attn_norm_w, L.attn_norm_b, nullptr, a));
     LCASR_TRY(gemm(a, L.qkv_w, M, 3 * d, d, nullptr, LCASR_ACT_NONE, nullptr, 0.f, wide, cd));
-    LCASR_TRY(lcasr_rope_split(wide, cd, B, N, H, Dh, c.use_rotary ? cos_t : nullptr, c.use_rotary ? sin_t : nullptr, q, k,
+    OP(CAT_ROPE, lcasr_rope_split(wide, cd, B, N, H, Dh, c.use_rotary ? cos_t : nullptr, c.use_rotary ? sin_t : nullptr, q, k,
                                v, vt, p.Npad, stream));
-    LCASR_TRY(lcasr_attention(q, k, v, cd, B, N, H, Dh, vt, p.Npad, a, ai, stream));
+    OP(CAT_ATTN, lcasr_attention(q, k, v, cd, B, N, H, Dh, vt, p.Npad, a, ai, stream));
     LCASR_TRY(gemm(a, L.out_w, M, d, d, nullptr, LCASR_ACT_NONE, x, 1.0f, x, LCASR_F32));
     // convolution module (convolution.py:103-124)
     LCASR_TRY(norm(L.conv_norm_w, L.conv_norm_b, nullptr, a));
     LCASR_TRY(gemm(a, L.pw1_w, M, 2 * d, d, L.pw1_b, LCASR_ACT_NONE, nullptr, 0.f, wide, cd));
-    LCASR_TRY(lcasr_glu(wide, cd, M, d, q, stream));
-    LCASR_TRY(lcasr_dwconv_brn_silu(q, cd, B, N, d, c.conv_kernel_size, L.dw_w, L.dw_b, L.brn_mean, L.brn_std, L.brn_w,
+    OP(CAT_CONVMOD, lcasr_glu(wide, cd, M, d, q, stream));
+    OP(CAT_CONVMOD, lcasr_dwconv_brn_silu(q, cd, B, N, d, c.conv_kernel_size, L.dw_w, L.dw_b, L.brn_mean, L.brn_std, L.brn_w,
                                     L.brn_b, k, cd, stream));
     LCASR_TRY(gemm(k, L.pw2_w, M, d, d, L.pw2_b, LCASR_ACT_NONE, x, 1.0f, x, LCASR_F32));
     LCASR_TRY(ffn(L.ff2_norm_w, L.ff2_norm_b, L.ff2_fc1_w, L.ff2_fc1_b, L.ff2_fc2_w, L.ff2_fc2_b));
     LCASR_TRY(norm(L.norm_out_w, L.norm_out_b, x, nullptr));
     if (l != c.n_layers - 1 && c.self_conditioning) {  // sconformer_xl.py:241-243
       if (c.decoder_norm) LCASR_TRY(norm(w.dec_norm_w, w.dec_norm_b, nullptr, a));
-      else LCASR_TRY(lcasr_cast_f32(x, M * d, a, cd, stream));
+      else OP(CAT_NORM, lcasr_cast_f32(x, M * d, a, cd, stream));
       LCASR_TRY(gemm(a, w.dec_ff_w, M, V1, d, w.dec_ff_b, LCASR_ACT_NONE, nullptr, 0.f, wide, cd));
-      LCASR_TRY(lcasr_softmax(wide, cd, M, V1, wide, cd, stream));
+      OP(CAT_SOFTMAX, lcasr_softmax(wide, cd, M, V1, wide, cd, stream));
       LCASR_TRY(gemm(wide, w.dec_rep_w, M, d, V1, w.dec_rep_b, LCASR_ACT_NONE, x, 1.0f, x, LCASR_F32));
     }
   }
   if (c.legasee_double_norm && c.decoder_norm) LCASR_TRY(norm(w.dec_norm_w, w.dec_norm_b, x, nullptr));
   if (c.decoder_norm) LCASR_TRY(norm(w.dec_norm_w, w.dec_norm_b, nullptr, a));
-  else LCASR_TRY(lcasr_cast_f32(x, M * d, a, cd, stream));
+  else OP(CAT_NORM, lcasr_cast_f32(x, M * d, a, cd, stream));
   LCASR_TRY(gemm(a, w.dec_ff_w, M, V1, d, w.dec_ff_b, LCASR_ACT_NONE, nullptr, 0.f, out, LCASR_F32));
-  if (!return_logits) LCASR_TRY(lcasr_log_softmax_argmax(out, M, V1, argmax, stream));
+  if (!return_logits) OP(CAT_SOFTMAX, lcasr_log_softmax_argmax(out, M, V1, argmax, stream));
+#undef OP
+  return 0;
+}
+
+extern "C" int lcasr_model_set_timing(lcasr_model* m, int enable) {
+  LCASR_CHECK_ARG(m, "model_set_timing: NULL model");
+  m->timing = enable != 0;
+  m->spans.clear();
+  m->ev_used = 0;
+  return 0;
+}
+
+// Synchronises the device, sums the recorded spans per category and resets the recorder.
+extern "C" int lcasr_model_get_timing(lcasr_model* m, float* ms_by_cat, int32_t* launches_by_cat, int ncat) {
+  LCASR_CHECK_ARG(m && ms_by_cat && launches_by_cat && ncat >= CAT_COUNT, "model_get_timing: bad arguments");
+  LCASR_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < ncat; ++i) { ms_by_cat[i] = 0.f; launches_by_cat[i] = 0; }
+  for (const auto& sp : m->spans) {
+    if (sp.e1 == (size_t)-1) continue;
+    float ms = 0.f;
+    LCASR_CUDA(cudaEventElapsedTime(&ms, m->ev_pool[sp.e0], m->ev_pool[sp.e1]));
+    ms_by_cat[sp.cat] += ms;
+    launches_by_cat[sp.cat] += 1;
+  }
+  m->spans.clear();
+  m->ev_used = 0;
   return 0;
 }
 

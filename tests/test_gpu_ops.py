@@ -98,11 +98,17 @@ def test_rope_table_and_split(cuda_device, Dh, base):
     N, B, H = 300, 2, 3
     inv_freq = 1.0 / (base ** (torch.arange(0, Dh, 2).float() / Dh))
     sd = {"rotary_pos_emb.inv_freq": inv_freq, "rotary_pos_emb.rotary_interpolation_factor": torch.tensor(1.0)}
-    for off in (0, 44000):
-        cos_ref, sin_ref = O.rotary_tables(sd, N, offset=off)
+    for off in (0, 44000):  # positions reach 45000 at 1-hour context
         cos, sin = ops.rope_table(inv_freq.to(cuda_device), 1.0, N, offset=off)
-        assert (cos.cpu() - cos_ref[:, : Dh // 2]).abs().max() < 2e-6  # same fp32 angle; libm vs CUDA sincos
-        assert (sin.cpu() - sin_ref[:, : Dh // 2]).abs().max() < 2e-6
+        # the fp32 angle the reference forms (rotary_emb.py:52-53), then cos/sin evaluated in float64:
+        # torch's vectorised CPU cosf itself is only ~1e-4 accurate at |angle| ~ 4e4
+        ang = (torch.arange(off, off + N).float()[:, None] * inv_freq[None, :]).double()
+        assert (cos.cpu().double() - ang.cos()).abs().max() < 5e-7
+        assert (sin.cpu().double() - ang.sin()).abs().max() < 5e-7
+    cos_ref, sin_ref = O.rotary_tables(sd, N)
+    cos, sin = ops.rope_table(inv_freq.to(cuda_device), 1.0, N)
+    assert (cos.cpu() - cos_ref[:, : Dh // 2]).abs().max() < 2e-6
+    assert (sin.cpu() - sin_ref[:, : Dh // 2]).abs().max() < 2e-6
     cos_ref, sin_ref = O.rotary_tables(sd, N)
     cos, sin = ops.rope_table(inv_freq.to(cuda_device), 1.0, N)
     d = H * Dh
