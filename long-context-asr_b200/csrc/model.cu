@@ -157,7 +157,7 @@ extern "C" int lcasr_model_forward(lcasr_model* m, const float* spec, int B, int
   const int gi = m->gemm_impl;
   int ai = m->attn_impl;
   if (ai == LCASR_ATTN_AUTO) ai = (cd == LCASR_BF16 && attn_tc_available()) ? LCASR_ATTN_TCGEN05 : LCASR_ATTN_SIMT;
-  const int vt = ai == LCASR_ATTN_TCGEN05 ? 1 : 0;
+  const int vt = 0;  // natural [B,N,H,Dh] V: the tcgen05 kernel consumes it as an MN-major B operand (no transpose pass)
 
   cudaStream_t cst = (cudaStream_t)stream;
   auto timed = [&](int cat, int status) {  // closes the span opened by begin()
