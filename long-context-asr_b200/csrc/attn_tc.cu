@@ -13,6 +13,7 @@
 // Algorithmic FLOPs per launch = 4 * B * H * N^2 * Dh.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include <cstdlib>
 
 namespace lcasr {
 
@@ -265,6 +266,384 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
+
+// ================================================================================================
+// Version 2 (default for the natural V layout): TWO query tiles per CTA, FA4-style ping-pong.
+//   warps 0-3  softmax for query tile A (rows q0 .. q0+127)      warp 8  TMA producer
+//   warps 4-7  softmax for query tile B (rows q0+128 .. q0+255)  warp 9  MMA issuer   (10,11 idle)
+// TMEM: S_A [0,128) | S_B [128,256) | O_A [256,256+Dh) | O_B [256+Dh,256+2Dh).  P_t aliases S_t.
+// The tensor pipe executes one thread's MMAs in issue order, so the issuer simply emits
+//   PV_t(j) ; QK_t(j+1)      for t = A, B
+// after P_t(j) is published: QK_t(j+1) may overwrite S_t/P_t because PV_t(j) precedes it in the pipe,
+// and when s_full[t] fires for tile j+1, PV_t(j) has retired, so the softmax warps may rescale O_t
+// without any extra barrier.  While tile A waits for its MMAs, tile B's softmax keeps the MUFU/FMA
+// pipes busy (two softmax warps per SM sub-partition), and K/V smem traffic per FLOP is halved.
+// ================================================================================================
+constexpr int FA2_THREADS = 384;
+
+template <int DH> struct Fa2Cfg {
+  static constexpr int STAGES = DH == 128 ? 2 : (DH == 64 ? 3 : 4);
+  static constexpr int ROW_BYTES = DH >= 64 ? 128 : 64;
+  static constexpr int SUB = DH >= 64 ? DH / 64 : 1;
+  static constexpr int SUB_COLS = DH >= 64 ? 64 : DH;
+  static constexpr uint32_t LAYOUT = DH >= 64 ? kLayoutSW128 : kLayoutSW64;
+  static constexpr int Q_SUB_BYTES = 2 * FA_BQ * ROW_BYTES;   // one 64-col sub-tile of BOTH query tiles
+  static constexpr int Q_BYTES = SUB * Q_SUB_BYTES;
+  static constexpr int KV_SUB_BYTES = FA_BK * ROW_BYTES;
+  static constexpr int K_BYTES = SUB * KV_SUB_BYTES;
+  static constexpr int STAGE_BYTES = 2 * K_BYTES;
+  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * STAGE_BYTES + 1024;
+  // Dh <= 64: P gets its own TMEM columns, so QK(j+1) can be issued as soon as the softmax warps
+  // have pulled S(j) into registers (the tensor-pipe round trip leaves the softmax critical path).
+  // Dh = 128: no TMEM left for that (2x128 S + 2x128 O = 512): P(j) aliases S(j).
+  static constexpr bool SEP_P = DH <= 64;
+  static constexpr int P_COL = SEP_P ? 256 : 0;     // + t*64 (SEP_P) / + t*128 (aliased)
+  static constexpr int P_STRIDE = SEP_P ? 64 : FA_BK;
+  static constexpr int O_COL = SEP_P ? 384 : 256;   // + t*DH
+};
+
+template <int DH, int POLY>
+__global__ void __launch_bounds__(FA2_THREADS, 1)
+attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, int64_t N, int H, float scale_log2, bf16* __restrict__ out) {
+  using Cfg = Fa2Cfg<DH>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[1 + 2 * Cfg::STAGES + 9];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = smem_base;
+  auto k_smem = [&](int s) { return smem_base + Cfg::Q_BYTES + s * Cfg::STAGE_BYTES; };
+  auto v_smem = [&](int s) { return smem_base + Cfg::Q_BYTES + s * Cfg::STAGE_BYTES + Cfg::K_BYTES; };
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t q_full = bar0;
+  auto kv_full = [&](int s) { return bar0 + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bar0 + 8u * (1 + Cfg::STAGES + s); };
+  auto s_full = [&](int t) { return bar0 + 8u * (1 + 2 * Cfg::STAGES + t); };       // QK(j) retired
+  auto p_full = [&](int t) { return bar0 + 8u * (1 + 2 * Cfg::STAGES + 2 + t); };   // P(j) published
+  auto pv_done = [&](int t) { return bar0 + 8u * (1 + 2 * Cfg::STAGES + 4 + t); };  // PV(j) retired
+  const uint32_t stagger = bar0 + 8u * (1 + 2 * Cfg::STAGES + 6);  // tile A half-way through its first tile
+  auto s_free = [&](int t) { return bar0 + 8u * (1 + 2 * Cfg::STAGES + 7 + t); };   // S(j) is in registers
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y;
+  const int64_t b = blockIdx.z;
+  const int64_t q0 = (int64_t)blockIdx.x * (2 * FA_BQ);
+  const int n_tiles = (int)((N + FA_BK - 1) / FA_BK);
+
+  if (warp == 8 && lane == 0) {
+    prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(s_full(t), 1); mbar_init(p_full(t), 4); mbar_init(pv_done(t), 1); mbar_init(s_free(t), 4);
+    }
+    mbar_init(stagger, 4);
+    fence_barrier_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(smem_u32(&tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+
+
+  if (warp >= 8) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+   if (warp == 8) {
+    if (lane == 0) {  // ------------------------- TMA producer -------------------------
+      const int row_q = (int)(b * N + q0);
+      mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+      for (int i = 0; i < Cfg::SUB; ++i)  // 256-row box: tile A rows then tile B rows
+        tma_load_2d(q_smem + i * Cfg::Q_SUB_BYTES, &tmQ, q_full, h * DH + i * Cfg::SUB_COLS, row_q);
+      int stage = 0; uint32_t phase = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(kv_empty(stage), phase ^ 1);
+        mbar_arrive_expect_tx(kv_full(stage), Cfg::STAGE_BYTES);
+        const int row_k = (int)(b * N + (int64_t)j * FA_BK);
+#pragma unroll
+        for (int i = 0; i < Cfg::SUB; ++i) {
+          tma_load_2d(k_smem(stage) + i * Cfg::KV_SUB_BYTES, &tmK, kv_full(stage), h * DH + i * Cfg::SUB_COLS, row_k);
+          tma_load_2d(v_smem(stage) + i * Cfg::KV_SUB_BYTES, &tmV, kv_full(stage), h * DH + i * Cfg::SUB_COLS, row_k);
+        }
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------- MMA issuer -------------------------
+    // The whole warp runs this loop converged (barrier polls are warp-uniform); one elected lane
+    // issues the tcgen05 instructions.  Descriptors are a per-stage base + compile-time increments so
+    // that each MMA costs one uniform add, not a descriptor rebuild (the issue latency of this thread
+    // is on the critical path of every softmax iteration).
+    constexpr uint32_t idesc_qk = make_idesc_bf16(FA_BQ, FA_BK, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(FA_BQ, DH, 1);  // B (= V) is MN-major
+    constexpr uint32_t SBO = 8 * Cfg::ROW_BYTES;
+    constexpr uint32_t DESC_HI = ((SBO >> 4) & 0x3FFF) | (1u << 14) | (Cfg::LAYOUT << 29);  // SBO | version 1 | swizzle
+    constexpr uint32_t LBO_K = 1u << 16;                                                   // unused for K-major
+    constexpr uint32_t LBO_V = ((Cfg::KV_SUB_BYTES >> 4) & 0x3FFF) << 16;                  // next 64-dh sub-tile
+    auto mk = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; };
+    const uint32_t q_lo0 = (q_smem >> 4) | LBO_K;
+    const uint32_t k_lo0 = (k_smem(0) >> 4) | LBO_K;
+    const uint32_t v_lo0 = (v_smem(0) >> 4) | LBO_V;
+    auto issue_qk = [&](int stage, int t) {
+      const uint32_t d_tmem = tmem_base + t * FA_BK;
+      const uint32_t a_lo = q_lo0 + t * ((FA_BQ * Cfg::ROW_BYTES) >> 4);
+      const uint32_t b_lo = k_lo0 + stage * (Cfg::STAGE_BYTES >> 4);
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        const int sub = (kk * 16) / Cfg::SUB_COLS, within = (kk * 16) % Cfg::SUB_COLS;
+        umma_f16_ss(d_tmem, mk(a_lo + ((sub * Cfg::Q_SUB_BYTES + within * 2) >> 4)),
+                    mk(b_lo + ((sub * Cfg::KV_SUB_BYTES + within * 2) >> 4)), idesc_qk, kk != 0);
+      }
+    };
+    auto issue_pv = [&](int stage, int t, bool accumulate) {
+      const uint32_t d_tmem = tmem_base + Cfg::O_COL + t * DH;
+      const uint32_t a_tmem = tmem_base + Cfg::P_COL + t * Cfg::P_STRIDE;
+      const uint32_t b_lo = v_lo0 + stage * (Cfg::STAGE_BYTES >> 4);
+#pragma unroll
+      for (int kk = 0; kk < FA_BK / 16; ++kk)  // 16 key rows per step
+        umma_f16_ts(d_tmem, a_tmem + kk * 8, mk(b_lo + ((kk * 16 * Cfg::ROW_BYTES) >> 4)), idesc_pv,
+                    (accumulate || kk != 0) ? 1u : 0u);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(kv_full(0), 0);
+    tc_fence_after();
+    if (elect_one()) {
+      issue_qk(0, 0); umma_commit(s_full(0));
+      issue_qk(0, 1); umma_commit(s_full(1));
+    }
+    __syncwarp();
+    // Event-driven service of the two query tiles (they stay out of phase: one computes exponentials
+    // while the other waits for the tensor pipe).  Tiles may drift apart by up to STAGES-1 K/V tiles.
+    //   SEP_P : QK_t(j+1) is issued when S_t(j) has been read (s_free), PV_t(j) when P_t(j) is published
+    //   else  : PV_t(j) ; QK_t(j+1) are issued together when P_t(j) is published (P aliases S; the
+    //           in-order tensor pipe makes the overwrite safe)
+    int qk_n[2] = {1, 1};  // QK tiles issued so far
+    int jt[2] = {0, 0};    // PV tiles issued so far
+    int full_upto = 0;     // highest K/V tile whose kv_full has been observed
+    uint32_t idle = 0;
+    uint64_t idle_t0 = 0;
+    auto kv_landed = [&](int jj) {  // warp-uniform; jj <= full_upto + 1 always holds
+      if (jj <= full_upto) return true;
+      if (!mbar_test_wait(kv_full(jj % Cfg::STAGES), (jj / Cfg::STAGES) & 1)) return false;
+      full_upto = jj;
+      return true;
+    };
+    while (jt[0] < n_tiles || jt[1] < n_tiles) {
+      bool progressed = false;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if constexpr (Cfg::SEP_P) {
+          const int jq = qk_n[t];
+          if (jq < n_tiles && mbar_test_wait(s_free(t), (jq - 1) & 1) && kv_landed(jq)) {
+            tc_fence_after();
+            if (elect_one()) {
+              issue_qk(jq % Cfg::STAGES, t);
+              umma_commit(s_full(t));
+            }
+            __syncwarp();
+            qk_n[t] = jq + 1;
+            progressed = true;
+          }
+          const int j = jt[t];
+          if (j < n_tiles && mbar_test_wait(p_full(t), j & 1)) {
+            tc_fence_after();
+            const int stage = j % Cfg::STAGES;
+            const bool release = jt[t ^ 1] > j;  // the other tile already consumed K/V(j)
+            if (elect_one()) {
+              issue_pv(stage, t, j > 0);
+              if (release) umma_commit(kv_empty(stage));
+              umma_commit(pv_done(t));
+            }
+            __syncwarp();
+            jt[t] = j + 1;
+            progressed = true;
+          }
+        } else {
+          const int j = jt[t];
+          if (j >= n_tiles || !mbar_test_wait(p_full(t), j & 1)) continue;
+          const bool more = j + 1 < n_tiles;
+          if (more && !kv_landed(j + 1)) continue;  // K(j+1) not landed yet
+          tc_fence_after();
+          const int stage = j % Cfg::STAGES;
+          const bool release = jt[t ^ 1] > j;
+          if (elect_one()) {
+            issue_pv(stage, t, j > 0);
+            if (release) umma_commit(kv_empty(stage));
+            umma_commit(pv_done(t));
+            if (more) {
+              issue_qk((j + 1) % Cfg::STAGES, t);
+              umma_commit(s_full(t));
+            }
+          }
+          __syncwarp();
+          jt[t] = j + 1;
+          progressed = true;
+        }
+      }
+      if (progressed) {
+        idle = 0; idle_t0 = 0;
+      } else if ((++idle & 0xFFFF) == 0) {  // deadlock guard: trap instead of hanging the GPU
+        uint64_t now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (idle_t0 == 0) idle_t0 = now;
+        else if (now - idle_t0 > 4000000000ull) {
+          if (lane == 0)
+            printf("lcasr_b200: attention MMA issuer stalled (block %d,%d,%d tiles %d/%d of %d)\n", blockIdx.x, blockIdx.y,
+                   blockIdx.z, jt[0], jt[1], n_tiles);
+          asm volatile("trap;");
+        }
+      }
+    }
+   }
+  } else {  // ------------------------- softmax warps -------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int t = warp >> 2;                 // query tile of this warp group
+    const int lane_base = (warp & 3) * 32;   // TMEM lane quarter == warp_id % 4
+    const int row = lane_base + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)lane_base << 16);
+    const uint32_t s_addr = t_lane + t * FA_BK;
+    const uint32_t p_addr = t_lane + Cfg::P_COL + t * Cfg::P_STRIDE;
+    const uint32_t o_addr = t_lane + Cfg::O_COL + t * DH;
+    float m_run = -INFINITY, l_run = 0.f;
+    // de-synchronise the two query tiles: B starts when A is half-way through its first exp phase, so
+    // that afterwards one tile's MUFU phase overlaps the other's MMA round trip / load / max phases
+    if (t == 1) mbar_wait(stagger, 0);
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(s_full(t), j & 1);
+      tc_fence_after();
+      uint32_t s[FA_BK];
+#pragma unroll
+      for (int c = 0; c < FA_BK / 32; ++c) tmem_ld_32x32b_x32(s_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+      tmem_wait_ld();
+      if constexpr (Cfg::SEP_P) {  // S_t is in registers: the issuer may overwrite it with QK_t(j+1) now
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free(t));
+      }
+      const int64_t valid = N - (int64_t)j * FA_BK;
+      if (valid < FA_BK) {
+#pragma unroll
+        for (int i = 0; i < FA_BK; ++i)
+          if (i >= valid) s[i] = 0xff800000u;  // -inf: key does not exist
+      }
+      float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < FA_BK; i += 8) {  // FMNMX3: two values per instruction, four independent chains
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          asm("max.f32 %0, %0, %1, %2;" : "+f"(mxa[u]) : "f"(__uint_as_float(s[i + 2 * u])), "f"(__uint_as_float(s[i + 2 * u + 1])));
+      }
+      const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])) * scale_log2;
+      if (j == 0) {
+        m_run = mx;
+      } else {
+        const bool grow = mx > m_run + 8.0f;
+        if (__any_sync(0xffffffffu, grow)) {
+          // O_t must be quiescent.  Aliased P: PV_t(j-1) precedes QK_t(j) in the tensor pipe, so it has
+          // retired when s_full fired.  Separate P: wait for its commit.
+          if constexpr (Cfg::SEP_P) { mbar_wait(pv_done(t), (j - 1) & 1); tc_fence_after(); }
+          const float m_new = grow ? mx : m_run;
+          const float alpha = ex2_approx(m_run - m_new);
+          l_run *= alpha;
+          m_run = m_new;
+#pragma unroll
+          for (int c = 0; c < DH / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(o_addr + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x32(o_addr + c * 32, o);
+          }
+          tmem_wait_st();
+        }
+      }
+      float sums[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // independent chains: no serial FADD latency
+      const float neg_m = -m_run;
+      // separate P buffer: PV_t(j-1) must have consumed P_t(j-1) before it is overwritten (long done in
+      // steady state — the wait is a formality, but it is what makes the reuse legal)
+      if constexpr (Cfg::SEP_P) { if (j > 0) { mbar_wait(pv_done(t), (j - 1) & 1); tc_fence_after(); } }
+#pragma unroll
+      for (int c = 0; c < FA_BK / 64; ++c) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x0 = fmaf(__uint_as_float(s[c * 64 + 2 * i]), scale_log2, neg_m);
+          const float x1 = fmaf(__uint_as_float(s[c * 64 + 2 * i + 1]), scale_log2, neg_m);
+          // POLY == 9 / 8: timing experiments only (no exponentials at all / all on the FMA pipes)
+          const float p0 = POLY == 9 ? x0 : (POLY == 8 ? ex2_poly(x0) : ex2_approx(x0));
+          const float p1 = POLY == 9 ? x1 : (POLY == 8 ? ex2_poly(x1)
+                           : ((POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == 0) ? ex2_poly(x1) : ex2_approx(x1)));
+          sums[(2 * i) & 7] += p0; sums[(2 * i + 1) & 7] += p1;
+          __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
+          pk[i] = *reinterpret_cast<uint32_t*>(&pp);
+        }
+        tmem_st_32x32b_x32(p_addr + c * 32, pk);
+        if (c == 0 && j == 0 && t == 0) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(stagger);
+        }
+      }
+      l_run += ((sums[0] + sums[1]) + (sums[2] + sums[3])) + ((sums[4] + sums[5]) + (sums[6] + sums[7]));
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(t));
+    }
+    mbar_wait(pv_done(t), (n_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int64_t n = q0 + t * FA_BQ + row;
+    bf16* orow = out + ((b * N + n) * H + h) * DH;
+#pragma unroll
+    for (int c = 0; c < DH / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(o_addr + c * 32, o);
+      tmem_wait_ld();
+      if (n < N) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(o[g * 8 + i]) * inv_l;
+          Vec8<bf16>::store(orow + c * 32 + g * 8, y);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int DH, int POLY>
+static int launch_attn_tc2(const void* q, const void* k, const void* v, int B, int64_t N, int H, void* out, cudaStream_t st) {
+  using Cfg = Fa2Cfg<DH>;
+  const uint64_t d = (uint64_t)H * DH;
+  const CUtensorMapSwizzle sw = DH >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMap tmQ, tmK, tmV;
+  LCASR_TRY(make_tmap_2d_bf16(&tmQ, q, (uint64_t)B * N, d, d * 2, 2 * FA_BQ, Cfg::SUB_COLS, sw));
+  LCASR_TRY(make_tmap_2d_bf16(&tmK, k, (uint64_t)B * N, d, d * 2, FA_BK, Cfg::SUB_COLS, sw));
+  LCASR_TRY(make_tmap_2d_bf16(&tmV, v, (uint64_t)B * N, d, d * 2, FA_BK, Cfg::SUB_COLS, sw));
+  static bool attr_set = false;
+  if (!attr_set) {
+    LCASR_CUDA(cudaFuncSetAttribute(attn_tc2_kernel<DH, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)ceil_div(N, 2 * FA_BQ), (unsigned)H, (unsigned)B);
+  const float scale_log2 = 1.4426950408889634f / sqrtf((float)DH);
+  attn_tc2_kernel<DH, POLY><<<grid, FA2_THREADS, Cfg::SMEM_BYTES, st>>>(tmQ, tmK, tmV, N, H, scale_log2, (bf16*)out);
+  LCASR_LAUNCH_CHECK();
+  return 0;
+}
+
 int attn_tc_available() { return 1; }
 
 template <int DH, bool VT>
@@ -297,10 +676,21 @@ int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N
   LCASR_CHECK_ARG((int64_t)B * N < ((int64_t)1 << 31), "attention(tcgen05): B*N too large");
   LCASR_CHECK_ARG(!v_transposed || Npad % 8 == 0, "attention(tcgen05): Npad must be a multiple of 8");
   LCASR_CHECK_ARG(H <= 65535 && B <= 65535, "attention(tcgen05): too many heads / batch entries");
+  static const bool force_v1 = getenv("LCASR_ATTN_V1") != nullptr;  // debugging aid: one query tile per CTA
+  // fraction of exponentials evaluated on the FMA pipes: POLY=p -> every p-th odd key, i.e. 1/(2p) of all
+  static const int poly = getenv("LCASR_ATTN_POLY") ? atoi(getenv("LCASR_ATTN_POLY")) : 0;  // measured: the Dh=32 kernel is latency- not MUFU-bound, offload does not pay yet
 #define LCASR_FA(DHV)                                                                                             \
   case DHV:                                                                                                       \
-    return v_transposed ? launch_attn_tc<DHV, true>(q, k, v, B, N, H, Npad, out, st)                              \
-                        : launch_attn_tc<DHV, false>(q, k, v, B, N, H, Npad, out, st);
+    if (v_transposed) return launch_attn_tc<DHV, true>(q, k, v, B, N, H, Npad, out, st);                          \
+    if (force_v1) return launch_attn_tc<DHV, false>(q, k, v, B, N, H, Npad, out, st);                             \
+    switch (poly) {                                                                                               \
+      case 0: return launch_attn_tc2<DHV, 0>(q, k, v, B, N, H, out, st);                                          \
+      case 1: return launch_attn_tc2<DHV, 1>(q, k, v, B, N, H, out, st);                                          \
+      case 2: return launch_attn_tc2<DHV, 2>(q, k, v, B, N, H, out, st);                                          \
+      case 8: return launch_attn_tc2<DHV, 8>(q, k, v, B, N, H, out, st);                                          \
+      case 9: return launch_attn_tc2<DHV, 9>(q, k, v, B, N, H, out, st);                                          \
+      default: return launch_attn_tc2<DHV, 4>(q, k, v, B, N, H, out, st);                                         \
+    }
   switch (Dh) {
     LCASR_FA(32) LCASR_FA(64) LCASR_FA(128)
     default:

@@ -34,20 +34,30 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
-      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware instead of spinning
+      : "memory");
+  return ok;
+}
+// non-blocking probe (no hardware suspend): for polling several barriers from one thread
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
   return ok;
 }
-// Spins until the phase with the given parity has completed.  A deadlock (a protocol bug) would
-// hang the GPU; after ~4 s of spinning we trap instead so the process dies with a CUDA error.
+// Waits until the phase with the given parity has completed.  A deadlock (a protocol bug) would
+// hang the GPU; after ~4 s of waiting we trap instead so the process dies with a CUDA error.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint64_t t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xFFFF) == 0) {
+    if ((++spins & 0x3FF) == 0) {
       uint64_t now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       if (t0 == 0) t0 = now;
@@ -196,6 +206,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = i + f, f in [-0.5, 0.5], degree-3
+// minimax polynomial for 2^f (max relative error 1.6e-4 — far below the bf16 rounding of P) and an
+// integer add into the exponent field.  Used for a fraction of the softmax exponentials so the
+// MUFU pipe (16 ex2/clk/SM) is not the only unit doing them (FA-4's trick).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;  // 1.5 * 2^23: the low mantissa bits of t now hold round(x)
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(0.05360212177038193f, f, 0.24237291514873505f);
+  p = fmaf(p, f, 0.6935023665428162f);
+  p = fmaf(p, f, 0.9999481439590454f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
 }
 
 }  // namespace ptx
