@@ -281,6 +281,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // ================================================================================================
 constexpr int FA2_THREADS = 384;
 
+// Optional phase trace of CTA (0,0,0) (tools/trace_attn.py): clock64 stamps of the softmax warps
+// (quarter 0 of each query tile) and of the MMA issuer.  Enabled by lcasr_debug_attn_trace(1).
+constexpr int kTraceIters = 32;
+__device__ long long g_attn_trace[2 * kTraceIters * 8 + 4 * kTraceIters * 4];
+__device__ int g_attn_trace_on = 0;
+#ifdef LCASR_ATTN_TRACE
+#define TRACE_M0 const long long tm0 = clock64()
+#define TRACE_M1(t, j) do { if (g_attn_trace_on && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (j) < kTraceIters) { \
+    long long* tp = g_attn_trace + 2 * kTraceIters * 8 + ((t) * kTraceIters + (j)) * 4; tp[0] = tm0; tp[1] = clock64(); } } while (0)
+#else
+#define TRACE_M0 do { } while (0)
+#define TRACE_M1(t, j) do { } while (0)
+#endif
+
 template <int DH> struct Fa2Cfg {
   static constexpr int STAGES = DH == 128 ? 2 : (DH == 64 ? 3 : 4);
   static constexpr int ROW_BYTES = DH >= 64 ? 128 : 64;
@@ -299,7 +313,16 @@ template <int DH> struct Fa2Cfg {
   static constexpr bool SEP_P = DH <= 64;
   static constexpr int P_COL = SEP_P ? 256 : 0;     // + t*64 (SEP_P) / + t*128 (aliased)
   static constexpr int P_STRIDE = SEP_P ? 64 : FA_BK;
-  static constexpr int O_COL = SEP_P ? 384 : 256;   // + t*DH
+  static constexpr int O_COL = SEP_P ? 384 : 256;   // + t*O_STRIDE
+  // Dh = 32: the softmax row sums come out of the tensor core for free.  V gets 16 extra "columns" of
+  // ones (a constant all-ones MN-atom in shared memory reached through the descriptor's LBO), so PV
+  // produces O[:, 32..47] = sum_k P[:, k] — with the bf16-rounded P that the numerator uses — and the
+  // softmax warps drop 128 FADDs per row tile (22% of their instructions; they are issue/latency bound).
+  static constexpr bool MMA_SUM = false;  // implemented and parity-tested for DH == 32, but measured 4% slower: off
+  static constexpr int PV_N = MMA_SUM ? DH + 16 : DH;
+  static constexpr int O_STRIDE = MMA_SUM ? 64 : DH;
+  static constexpr int ONES_BYTES = MMA_SUM ? FA_BK * ROW_BYTES : 0;
+  static constexpr int SMEM_TOTAL = SMEM_BYTES + ONES_BYTES;
 };
 
 template <int DH, int POLY>
@@ -323,6 +346,12 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   auto pv_done = [&](int t) { return bar0 + 8u * (1 + 2 * Cfg::STAGES + 4 + t); };  // PV(j) retired
   const uint32_t stagger = bar0 + 8u * (1 + 2 * Cfg::STAGES + 6);  // tile A half-way through its first tile
   auto s_free = [&](int t) { return bar0 + 8u * (1 + 2 * Cfg::STAGES + 7 + t); };   // S(j) is in registers
+  const uint32_t ones_smem = smem_base + Cfg::Q_BYTES + Cfg::STAGES * Cfg::STAGE_BYTES;
+  if constexpr (Cfg::MMA_SUM) {  // all-ones bf16 tile (swizzle-invariant), visible to the async proxy before any MMA
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem_raw + (ones_smem - smem_u32(smem_raw)));
+    for (int i = threadIdx.x; i < Cfg::ONES_BYTES / 4; i += FA2_THREADS) ones[i] = 0x3F803F80u;
+    fence_proxy_async();
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y;
@@ -379,7 +408,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // that each MMA costs one uniform add, not a descriptor rebuild (the issue latency of this thread
     // is on the critical path of every softmax iteration).
     constexpr uint32_t idesc_qk = make_idesc_bf16(FA_BQ, FA_BK, 0);
-    constexpr uint32_t idesc_pv = make_idesc_bf16(FA_BQ, DH, 1);  // B (= V) is MN-major
+    constexpr uint32_t idesc_pv = make_idesc_bf16(FA_BQ, Cfg::PV_N, 1);  // B (= V) is MN-major
     constexpr uint32_t SBO = 8 * Cfg::ROW_BYTES;
     constexpr uint32_t DESC_HI = ((SBO >> 4) & 0x3FFF) | (1u << 14) | (Cfg::LAYOUT << 29);  // SBO | version 1 | swizzle
     constexpr uint32_t LBO_K = 1u << 16;                                                   // unused for K-major
@@ -387,7 +416,11 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     auto mk = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; };
     const uint32_t q_lo0 = (q_smem >> 4) | LBO_K;
     const uint32_t k_lo0 = (k_smem(0) >> 4) | LBO_K;
-    const uint32_t v_lo0 = (v_smem(0) >> 4) | LBO_V;
+    // MMA_SUM: the second MN-atom of the B operand is the shared all-ones tile: LBO = ones - V(stage)
+    const uint32_t v_lo0 = Cfg::MMA_SUM ? (v_smem(0) >> 4) | ((((ones_smem - v_smem(0)) >> 4) & 0x3FFF) << 16)
+                                        : (v_smem(0) >> 4) | LBO_V;
+    constexpr uint32_t V_STAGE_STEP = Cfg::MMA_SUM ? (Cfg::STAGE_BYTES >> 4) - ((Cfg::STAGE_BYTES >> 4) << 16)
+                                                   : (Cfg::STAGE_BYTES >> 4);  // address up, LBO down
     auto issue_qk = [&](int stage, int t) {
       const uint32_t d_tmem = tmem_base + t * FA_BK;
       const uint32_t a_lo = q_lo0 + t * ((FA_BQ * Cfg::ROW_BYTES) >> 4);
@@ -400,9 +433,9 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     };
     auto issue_pv = [&](int stage, int t, bool accumulate) {
-      const uint32_t d_tmem = tmem_base + Cfg::O_COL + t * DH;
+      const uint32_t d_tmem = tmem_base + Cfg::O_COL + t * Cfg::O_STRIDE;
       const uint32_t a_tmem = tmem_base + Cfg::P_COL + t * Cfg::P_STRIDE;
-      const uint32_t b_lo = v_lo0 + stage * (Cfg::STAGE_BYTES >> 4);
+      const uint32_t b_lo = v_lo0 + stage * V_STAGE_STEP;
 #pragma unroll
       for (int kk = 0; kk < FA_BK / 16; ++kk)  // 16 key rows per step
         umma_f16_ts(d_tmem, a_tmem + kk * 8, mk(b_lo + ((kk * 16 * Cfg::ROW_BYTES) >> 4)), idesc_pv,
@@ -453,12 +486,14 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tc_fence_after();
             const int stage = j % Cfg::STAGES;
             const bool release = jt[t ^ 1] > j;  // the other tile already consumed K/V(j)
+            TRACE_M0;
             if (elect_one()) {
               issue_pv(stage, t, j > 0);
               if (release) umma_commit(kv_empty(stage));
               umma_commit(pv_done(t));
             }
             __syncwarp();
+            TRACE_M1(t, j);
             jt[t] = j + 1;
             progressed = true;
           }
@@ -470,6 +505,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tc_fence_after();
           const int stage = j % Cfg::STAGES;
           const bool release = jt[t ^ 1] > j;
+          TRACE_M0;
           if (elect_one()) {
             issue_pv(stage, t, j > 0);
             if (release) umma_commit(kv_empty(stage));
@@ -480,6 +516,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
           }
           __syncwarp();
+          TRACE_M1(t, j);
           jt[t] = j + 1;
           progressed = true;
         }
@@ -507,18 +544,33 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t t_lane = tmem_base + ((uint32_t)lane_base << 16);
     const uint32_t s_addr = t_lane + t * FA_BK;
     const uint32_t p_addr = t_lane + Cfg::P_COL + t * Cfg::P_STRIDE;
-    const uint32_t o_addr = t_lane + Cfg::O_COL + t * DH;
+    const uint32_t o_addr = t_lane + Cfg::O_COL + t * Cfg::O_STRIDE;
     float m_run = -INFINITY, l_run = 0.f;
     // de-synchronise the two query tiles: B starts when A is half-way through its first exp phase, so
     // that afterwards one tile's MUFU phase overlaps the other's MMA round trip / load / max phases
+    // (An explicit MUFU ping-pong between the two warps of a sub-partition — named barriers, FA-3 style —
+    //  was tried and measured neutral: one warp alone reaches only 9.5 cycles/exp, two overlapping 8.1.)
     if (t == 1) mbar_wait(stagger, 0);
+    uint32_t s_ready = 0;
+#ifdef LCASR_ATTN_TRACE  // compile with -DLCASR_ATTN_TRACE for tools/trace_attn.py (costs ~5% otherwise)
+    const bool tr = g_attn_trace_on && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (warp & 3) == 0 && lane == 0;
+#define TRACE_S(k) do { if (tr && j < kTraceIters) g_attn_trace[(t * kTraceIters + j) * 8 + (k)] = clock64(); } while (0)
+#else
+#define TRACE_S(k) do { } while (0)
+#endif
     for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(s_full(t), j & 1);
+      TRACE_S(0);
+      if (!s_ready) mbar_wait(s_full(t), j & 1);  // usually already observed during the previous iteration
+      TRACE_S(1);
       tc_fence_after();
+      // non-blocking probe now, consumed later: the barrier latency hides behind the TMEM load
+      uint32_t pv_ok = 1;
+      if constexpr (Cfg::SEP_P) { if (j > 0) pv_ok = mbar_test_wait(pv_done(t), (j - 1) & 1); }
       uint32_t s[FA_BK];
 #pragma unroll
       for (int c = 0; c < FA_BK / 32; ++c) tmem_ld_32x32b_x32(s_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
       tmem_wait_ld();
+      TRACE_S(2);
       if constexpr (Cfg::SEP_P) {  // S_t is in registers: the issuer may overwrite it with QK_t(j+1) now
         tc_fence_before();
         __syncwarp();
@@ -545,7 +597,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (__any_sync(0xffffffffu, grow)) {
           // O_t must be quiescent.  Aliased P: PV_t(j-1) precedes QK_t(j) in the tensor pipe, so it has
           // retired when s_full fired.  Separate P: wait for its commit.
-          if constexpr (Cfg::SEP_P) { mbar_wait(pv_done(t), (j - 1) & 1); tc_fence_after(); }
+          if constexpr (Cfg::SEP_P) { if (!pv_ok) { mbar_wait(pv_done(t), (j - 1) & 1); pv_ok = 1; } tc_fence_after(); }
           const float m_new = grow ? mx : m_run;
           const float alpha = ex2_approx(m_run - m_new);
           l_run *= alpha;
@@ -559,14 +611,26 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
             tmem_st_32x32b_x32(o_addr + c * 32, o);
           }
+          if constexpr (Cfg::MMA_SUM) {  // the row-sum columns live in O as well
+            uint32_t o2[16];
+            tmem_ld_32x32b_x16(o_addr + DH, o2);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o2[i] = __float_as_uint(__uint_as_float(o2[i]) * alpha);
+            tmem_st_32x32b_x16(o_addr + DH, o2);
+          }
           tmem_wait_st();
         }
       }
+      TRACE_S(3);
       float sums[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // independent chains: no serial FADD latency
       const float neg_m = -m_run;
-      // separate P buffer: PV_t(j-1) must have consumed P_t(j-1) before it is overwritten (long done in
-      // steady state — the wait is a formality, but it is what makes the reuse legal)
-      if constexpr (Cfg::SEP_P) { if (j > 0) { mbar_wait(pv_done(t), (j - 1) & 1); tc_fence_after(); } }
+      // separate P buffer: PV_t(j-1) must have consumed P_t(j-1) before it is overwritten (long retired
+      // in steady state — the wait is a formality, but it is what makes the reuse legal)
+      if constexpr (Cfg::SEP_P) {
+        if (!pv_ok) mbar_wait(pv_done(t), (j - 1) & 1);
+        tc_fence_after();
+      }
 #pragma unroll
       for (int c = 0; c < FA_BK / 64; ++c) {
         uint32_t pk[32];
@@ -578,7 +642,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const float p0 = POLY == 9 ? x0 : (POLY == 8 ? ex2_poly(x0) : ex2_approx(x0));
           const float p1 = POLY == 9 ? x1 : (POLY == 8 ? ex2_poly(x1)
                            : ((POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == 0) ? ex2_poly(x1) : ex2_approx(x1)));
-          sums[(2 * i) & 7] += p0; sums[(2 * i + 1) & 7] += p1;
+          if constexpr (!Cfg::MMA_SUM) { sums[(2 * i) & 7] += p0; sums[(2 * i + 1) & 7] += p1; }
           __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
           pk[i] = *reinterpret_cast<uint32_t*>(&pp);
         }
@@ -588,14 +652,25 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (lane == 0) mbar_arrive(stagger);
         }
       }
+      if constexpr (Cfg::SEP_P)
+        s_ready = (j + 1 < n_tiles) ? mbar_test_wait(s_full(t), (j + 1) & 1) : 0;  // probe next S early
       l_run += ((sums[0] + sums[1]) + (sums[2] + sums[3])) + ((sums[4] + sums[5]) + (sums[6] + sums[7]));
+      TRACE_S(4);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(t));
+      TRACE_S(5);
     }
+#undef TRACE_S
     mbar_wait(pv_done(t), (n_tiles - 1) & 1);
     tc_fence_after();
+    if constexpr (Cfg::MMA_SUM) {
+      uint32_t o2[16];
+      tmem_ld_32x32b_x16(o_addr + DH, o2);
+      tmem_wait_ld();
+      l_run = __uint_as_float(o2[0]);
+    }
     const float inv_l = 1.0f / l_run;
     const int64_t n = q0 + t * FA_BQ + row;
     bf16* orow = out + ((b * N + n) * H + h) * DH;
@@ -634,17 +709,320 @@ static int launch_attn_tc2(const void* q, const void* k, const void* v, int B, i
   LCASR_TRY(make_tmap_2d_bf16(&tmV, v, (uint64_t)B * N, d, d * 2, FA_BK, Cfg::SUB_COLS, sw));
   static bool attr_set = false;
   if (!attr_set) {
-    LCASR_CUDA(cudaFuncSetAttribute(attn_tc2_kernel<DH, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    LCASR_CUDA(cudaFuncSetAttribute(attn_tc2_kernel<DH, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div(N, 2 * FA_BQ), (unsigned)H, (unsigned)B);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)DH);
-  attn_tc2_kernel<DH, POLY><<<grid, FA2_THREADS, Cfg::SMEM_BYTES, st>>>(tmQ, tmK, tmV, N, H, scale_log2, (bf16*)out);
+  attn_tc2_kernel<DH, POLY><<<grid, FA2_THREADS, Cfg::SMEM_TOTAL, st>>>(tmQ, tmK, tmV, N, H, scale_log2, (bf16*)out);
+  LCASR_LAUNCH_CHECK();
+  return 0;
+}
+
+
+// ================================================================================================
+// Version 3 (head_dim 32): FOUR query tiles per CTA (512 query rows), 64-key K/V tiles.
+// With Dh = 32 the tensor work per score is tiny (128 MMA flops vs one exponential): the kernel is
+// bound by the softmax warps' latency chain (TMEM load -> row max -> exp -> pack -> TMEM store ->
+// barrier), not by any single pipe (measured: removing every ex2 only takes it from 2.1 to 1.5 ms).
+// So the design maximises the number of independent softmax chains per SM: 16 softmax warps (4 per
+// SM sub-partition) instead of 8, each working on a 32-row x 64-key block, which still fits tensor
+// memory exactly:   S_t 4x64 | P_t 4x32 | O_t 4x32  = 512 columns.
+//   warps 0-15  softmax, tile t = warp/4, TMEM lane quarter = warp%4
+//   warp 16     TMA producer (Q once, K/V 64-key tiles, 8-stage ring)
+//   warp 17     MMA issuer (converged warp, elected lane, polls the 4 tiles' barriers)
+// Protocol per tile t (P has its own columns, so nothing aliases):
+//   s_full[t]  QK_t(j) retired            -> softmax may read S_t
+//   s_free[t]  softmax finished reading S_t(j)  -> issuer may run QK_t(j+1)
+//   p_full[t]  P_t(j) stored (O_t rescaled)     -> issuer runs PV_t(j)
+//   pv_done[t] PV_t(j) retired            -> P_t / O_t may be touched again
+//   kv_empty[s] counts 4 commits (one per tile's PV) -> producer refills the stage
+// ================================================================================================
+constexpr int FA3_NT = 4, FA3_BK = 64, FA3_STAGES = 8, FA3_THREADS = 640;
+
+template <int POLY>
+__global__ void __launch_bounds__(FA3_THREADS, 1)
+attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, int64_t N, int H, float scale_log2, bf16* __restrict__ out) {
+  constexpr int DH = 32, NT = FA3_NT, BK = FA3_BK, STAGES = FA3_STAGES;
+  constexpr int ROW_BYTES = 64;                       // 32 bf16: SWIZZLE_64B rows
+  constexpr int Q_BYTES = NT * FA_BQ * ROW_BYTES;     // 32 KB
+  constexpr int K_BYTES = BK * ROW_BYTES;             // 4 KB
+  constexpr int STAGE_BYTES = 2 * K_BYTES;
+  constexpr int P_COL = NT * BK, O_COL = NT * BK + NT * (BK / 2);
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[1 + 2 * STAGES + 4 * NT];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = smem_base;
+  auto k_smem = [&](int st) { return smem_base + Q_BYTES + st * STAGE_BYTES; };
+  auto v_smem = [&](int st) { return smem_base + Q_BYTES + st * STAGE_BYTES + K_BYTES; };
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t q_full = bar0;
+  auto kv_full = [&](int st) { return bar0 + 8u * (1 + st); };
+  auto kv_empty = [&](int st) { return bar0 + 8u * (1 + STAGES + st); };
+  auto s_full = [&](int t) { return bar0 + 8u * (1 + 2 * STAGES + t); };
+  auto s_free = [&](int t) { return bar0 + 8u * (1 + 2 * STAGES + NT + t); };
+  auto p_full = [&](int t) { return bar0 + 8u * (1 + 2 * STAGES + 2 * NT + t); };
+  auto pv_done = [&](int t) { return bar0 + 8u * (1 + 2 * STAGES + 3 * NT + t); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y;
+  const int64_t b = blockIdx.z;
+  const int64_t q0 = (int64_t)blockIdx.x * (NT * FA_BQ);
+  const int n_tiles = (int)((N + BK - 1) / BK);
+
+  if (warp == 16 && lane == 0) {
+    prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
+    mbar_init(q_full, 1);
+    for (int st = 0; st < STAGES; ++st) { mbar_init(kv_full(st), 1); mbar_init(kv_empty(st), NT); }
+    for (int t = 0; t < NT; ++t) {
+      mbar_init(s_full(t), 1); mbar_init(s_free(t), 4); mbar_init(p_full(t), 4); mbar_init(pv_done(t), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 17) {
+    tmem_alloc(smem_u32(&tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+
+  if (warp >= 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 16) {
+      if (lane == 0) {  // ------------------------- TMA producer -------------------------
+        const int row_q = (int)(b * N + q0);
+        mbar_arrive_expect_tx(q_full, Q_BYTES);
+        tma_load_2d(q_smem, &tmQ, q_full, h * DH, row_q);                                   // tiles 0,1 (256-row box)
+        tma_load_2d(q_smem + 2 * FA_BQ * ROW_BYTES, &tmQ, q_full, h * DH, row_q + 2 * FA_BQ);  // tiles 2,3
+        int stage = 0; uint32_t phase = 0;
+        for (int j = 0; j < n_tiles; ++j) {
+          mbar_wait(kv_empty(stage), phase ^ 1);
+          mbar_arrive_expect_tx(kv_full(stage), STAGE_BYTES);
+          const int row_k = (int)(b * N + (int64_t)j * BK);
+          tma_load_2d(k_smem(stage), &tmK, kv_full(stage), h * DH, row_k);
+          tma_load_2d(v_smem(stage), &tmV, kv_full(stage), h * DH, row_k);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 17) {
+      // ------------------------- MMA issuer -------------------------
+      constexpr uint32_t idesc_qk = make_idesc_bf16(FA_BQ, BK, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(FA_BQ, DH, 1);  // V is MN-major
+      constexpr uint32_t DESC_HI = (((8 * ROW_BYTES) >> 4) & 0x3FFF) | (1u << 14) | (kLayoutSW64 << 29);
+      auto mk = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; };
+      const uint32_t q_lo0 = (q_smem >> 4) | (1u << 16);
+      const uint32_t k_lo0 = (k_smem(0) >> 4) | (1u << 16);
+      const uint32_t v_lo0 = (v_smem(0) >> 4) | (1u << 16);  // LBO unused: N = 32 is a single MN atom
+      auto issue_qk = [&](int stage, int t) {
+        const uint32_t a_lo = q_lo0 + t * ((FA_BQ * ROW_BYTES) >> 4);
+        const uint32_t b_lo = k_lo0 + stage * (STAGE_BYTES >> 4);
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk)
+          umma_f16_ss(tmem_base + t * BK, mk(a_lo + ((kk * 32) >> 4)), mk(b_lo + ((kk * 32) >> 4)), idesc_qk, kk != 0);
+      };
+      auto issue_pv = [&](int stage, int t, bool accumulate) {
+        const uint32_t b_lo = v_lo0 + stage * (STAGE_BYTES >> 4);
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk)
+          umma_f16_ts(tmem_base + O_COL + t * DH, tmem_base + P_COL + t * (BK / 2) + kk * 8,
+                      mk(b_lo + ((kk * 16 * ROW_BYTES) >> 4)), idesc_pv, (accumulate || kk != 0) ? 1u : 0u);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(kv_full(0), 0);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { issue_qk(0, t); umma_commit(s_full(t)); }
+      }
+      __syncwarp();
+      int qk_n[NT], pv_n[NT];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) { qk_n[t] = 1; pv_n[t] = 0; }
+      int full_upto = 0, remaining = NT;
+      uint32_t idle = 0;
+      uint64_t idle_t0 = 0;
+      while (remaining > 0) {
+        bool progressed = false;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const int jq = qk_n[t];
+          if (jq < n_tiles && mbar_test_wait(s_free(t), (jq - 1) & 1)) {
+            bool landed = jq <= full_upto;
+            if (!landed && mbar_test_wait(kv_full(jq % STAGES), (jq / STAGES) & 1)) { full_upto = jq; landed = true; }
+            if (landed) {
+              tc_fence_after();
+              if (elect_one()) { issue_qk(jq % STAGES, t); umma_commit(s_full(t)); }
+              __syncwarp();
+              qk_n[t] = jq + 1;
+              progressed = true;
+            }
+          }
+          const int j = pv_n[t];
+          if (j < n_tiles && mbar_test_wait(p_full(t), j & 1)) {
+            tc_fence_after();
+            if (elect_one()) {
+              issue_pv(j % STAGES, t, j > 0);
+              umma_commit(kv_empty(j % STAGES));  // the 4th tile's commit releases the stage
+              umma_commit(pv_done(t));
+            }
+            __syncwarp();
+            pv_n[t] = j + 1;
+            if (j + 1 == n_tiles) --remaining;
+            progressed = true;
+          }
+        }
+        if (progressed) {
+          idle = 0; idle_t0 = 0;
+        } else if ((++idle & 0xFFFF) == 0) {  // deadlock guard: trap instead of hanging the GPU
+          uint64_t now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (idle_t0 == 0) idle_t0 = now;
+          else if (now - idle_t0 > 4000000000ull) {
+            if (lane == 0) printf("lcasr_b200: attention(v3) MMA issuer stalled (block %d,%d,%d)\n", blockIdx.x, blockIdx.y, blockIdx.z);
+            asm volatile("trap;");
+          }
+        }
+      }
+    }
+  } else {  // ------------------------- softmax warps -------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int t = warp >> 2;
+    const int lane_base = (warp & 3) * 32;
+    const int row = lane_base + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)lane_base << 16);
+    const uint32_t s_addr = t_lane + t * BK;
+    const uint32_t p_addr = t_lane + P_COL + t * (BK / 2);
+    const uint32_t o_addr = t_lane + O_COL + t * DH;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(s_full(t), j & 1);
+      tc_fence_after();
+      uint32_t s[BK];
+      tmem_ld_32x32b_x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+      tmem_ld_32x32b_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free(t));  // S_t(j) is in registers: QK_t(j+1) may overwrite it
+      const int64_t valid = N - (int64_t)j * BK;
+      if (valid < BK) {
+#pragma unroll
+        for (int i = 0; i < BK; ++i)
+          if (i >= valid) s[i] = 0xff800000u;
+      }
+      float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < BK; i += 8) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          asm("max.f32 %0, %0, %1, %2;" : "+f"(mxa[u]) : "f"(__uint_as_float(s[i + 2 * u])), "f"(__uint_as_float(s[i + 2 * u + 1])));
+      }
+      const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])) * scale_log2;
+      if (j == 0) {
+        m_run = mx;
+      } else {
+        mbar_wait(pv_done(t), (j - 1) & 1);  // P_t / O_t are free again (long retired in steady state)
+        tc_fence_after();
+        const bool grow = mx > m_run + 8.0f;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float m_new = grow ? mx : m_run;
+          const float alpha = ex2_approx(m_run - m_new);
+          l_run *= alpha;
+          m_run = m_new;
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(o_addr, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x32b_x32(o_addr, o);
+          tmem_wait_st();
+        }
+      }
+      float sums[4] = {0.f, 0.f, 0.f, 0.f};
+      const float neg_m = -m_run;
+      uint32_t pk[BK / 2];
+#pragma unroll
+      for (int i = 0; i < BK / 2; ++i) {
+        const float x0 = fmaf(__uint_as_float(s[2 * i]), scale_log2, neg_m);
+        const float x1 = fmaf(__uint_as_float(s[2 * i + 1]), scale_log2, neg_m);
+        const float p0 = ex2_approx(x0);
+        const float p1 = (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == 0) ? ex2_poly(x1) : ex2_approx(x1);
+        sums[(2 * i) & 3] += p0; sums[(2 * i + 1) & 3] += p1;
+        __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
+        pk[i] = *reinterpret_cast<uint32_t*>(&pp);
+      }
+      l_run += (sums[0] + sums[1]) + (sums[2] + sums[3]);
+      tmem_st_32x32b_x32(p_addr, pk);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(t));
+    }
+    mbar_wait(pv_done(t), (n_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int64_t n = q0 + t * FA_BQ + row;
+    uint32_t o[32];
+    tmem_ld_32x32b_x32(o_addr, o);
+    tmem_wait_ld();
+    if (n < N) {
+      bf16* orow = out + ((b * N + n) * H + h) * DH;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(o[g * 8 + i]) * inv_l;
+        Vec8<bf16>::store(orow + g * 8, y);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int POLY>
+static int launch_attn_tc3(const void* q, const void* k, const void* v, int B, int64_t N, int H, void* out, cudaStream_t st) {
+  constexpr int DH = 32;
+  constexpr int SMEM = FA3_NT * FA_BQ * 64 + FA3_STAGES * 2 * FA3_BK * 64 + 1024;
+  const uint64_t d = (uint64_t)H * DH;
+  CUtensorMap tmQ, tmK, tmV;
+  LCASR_TRY(make_tmap_2d_bf16(&tmQ, q, (uint64_t)B * N, d, d * 2, 2 * FA_BQ, DH, CU_TENSOR_MAP_SWIZZLE_64B));
+  LCASR_TRY(make_tmap_2d_bf16(&tmK, k, (uint64_t)B * N, d, d * 2, FA3_BK, DH, CU_TENSOR_MAP_SWIZZLE_64B));
+  LCASR_TRY(make_tmap_2d_bf16(&tmV, v, (uint64_t)B * N, d, d * 2, FA3_BK, DH, CU_TENSOR_MAP_SWIZZLE_64B));
+  static bool attr_set = false;
+  if (!attr_set) {
+    LCASR_CUDA(cudaFuncSetAttribute(attn_tc3_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)ceil_div(N, FA3_NT * FA_BQ), (unsigned)H, (unsigned)B);
+  const float scale_log2 = 1.4426950408889634f / sqrtf((float)DH);
+  attn_tc3_kernel<POLY><<<grid, FA3_THREADS, SMEM, st>>>(tmQ, tmK, tmV, N, H, scale_log2, (bf16*)out);
   LCASR_LAUNCH_CHECK();
   return 0;
 }
 
 int attn_tc_available() { return 1; }
+
+}  // namespace lcasr
+// debug hooks (not part of the public header): phase trace of the v2 attention kernel
+extern "C" int lcasr_debug_attn_trace(int enable) {
+  int v = enable;
+  return cudaMemcpyToSymbol(lcasr::g_attn_trace_on, &v, sizeof(int)) == cudaSuccess ? 0 : -3;
+}
+extern "C" int lcasr_debug_attn_trace_read(long long* host, int n) {
+  const int total = (int)(sizeof(lcasr::g_attn_trace) / sizeof(long long));
+  if (n > total) n = total;
+  return cudaMemcpyFromSymbol(host, lcasr::g_attn_trace, (size_t)n * sizeof(long long)) == cudaSuccess ? n : -3;
+}
+namespace lcasr {
 
 template <int DH, bool VT>
 static int launch_attn_tc(const void* q, const void* k, const void* v, int B, int64_t N, int H, int64_t Npad, void* out,
@@ -677,12 +1055,16 @@ int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N
   LCASR_CHECK_ARG(!v_transposed || Npad % 8 == 0, "attention(tcgen05): Npad must be a multiple of 8");
   LCASR_CHECK_ARG(H <= 65535 && B <= 65535, "attention(tcgen05): too many heads / batch entries");
   static const bool force_v1 = getenv("LCASR_ATTN_V1") != nullptr;  // debugging aid: one query tile per CTA
+  static const bool force_v3 = getenv("LCASR_ATTN_V3") != nullptr;  // experiment: four query tiles / 64-key tiles for Dh=32 (measured slower)
   // fraction of exponentials evaluated on the FMA pipes: POLY=p -> every p-th odd key, i.e. 1/(2p) of all
   static const int poly = getenv("LCASR_ATTN_POLY") ? atoi(getenv("LCASR_ATTN_POLY")) : 0;  // measured: the Dh=32 kernel is latency- not MUFU-bound, offload does not pay yet
 #define LCASR_FA(DHV)                                                                                             \
   case DHV:                                                                                                       \
     if (v_transposed) return launch_attn_tc<DHV, true>(q, k, v, B, N, H, Npad, out, st);                          \
     if (force_v1) return launch_attn_tc<DHV, false>(q, k, v, B, N, H, Npad, out, st);                             \
+    if (DHV == 32 && force_v3) return poly == 2 ? launch_attn_tc3<2>(q, k, v, B, N, H, out, st)                  \
+                                     : (poly == 4 ? launch_attn_tc3<4>(q, k, v, B, N, H, out, st)                \
+                                                  : launch_attn_tc3<0>(q, k, v, B, N, H, out, st));               \
     switch (poly) {                                                                                               \
       case 0: return launch_attn_tc2<DHV, 0>(q, k, v, B, N, H, out, st);                                          \
       case 1: return launch_attn_tc2<DHV, 1>(q, k, v, B, N, H, out, st);                                          \
