@@ -103,6 +103,12 @@ int lcasr_rope_split(const void* qkv, int dtype, int B, int64_t N, int H, int Dh
 int lcasr_attention(const void* q, const void* k, const void* v, int dtype, int B, int64_t N, int H,
                     int Dh, int v_transposed, int64_t Npad, void* out, int impl, void* stream);
 
+/* Same attention with Nq query rows against Nk keys/values per batch entry (q [B,Nq,H,Dh]; k,v
+ * [B,Nk,H,Dh], natural layout): the sequence-parallel form of Attention.forward, where a rank owns
+ * a block of Nq query tokens and attends to the all-gathered K/V of the whole recording. */
+int lcasr_attention_cross(const void* q, const void* k, const void* v, int dtype, int B, int64_t Nq,
+                          int64_t Nk, int H, int Dh, void* out, int impl, void* stream);
+
 /* depthwise Conv1d(k, pad (k-1)/2, groups=d) + bias -> BatchRenorm1d eval affine
  * ((y-mean)/std*weight+bias, no eps; batchrenorm.py:86-91) -> SiLU  (convolution.py:112-121).
  * in/out channels-last [B,N,d]; w [d,ksize] fp32. */

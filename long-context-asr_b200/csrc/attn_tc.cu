@@ -328,7 +328,8 @@ template <int DH> struct Fa2Cfg {
 template <int DH, int POLY>
 __global__ void __launch_bounds__(FA2_THREADS, 1)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, int64_t N, int H, float scale_log2, bf16* __restrict__ out) {
+                const __grid_constant__ CUtensorMap tmV, int64_t N, int64_t Nk, int H, float scale_log2,
+                bf16* __restrict__ out) {  // N = query rows per batch entry, Nk = keys per batch entry
   using Cfg = Fa2Cfg<DH>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[1 + 2 * Cfg::STAGES + 9];
@@ -357,7 +358,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int h = blockIdx.y;
   const int64_t b = blockIdx.z;
   const int64_t q0 = (int64_t)blockIdx.x * (2 * FA_BQ);
-  const int n_tiles = (int)((N + FA_BK - 1) / FA_BK);
+  const int n_tiles = (int)((Nk + FA_BK - 1) / FA_BK);
 
   if (warp == 8 && lane == 0) {
     prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
@@ -392,7 +393,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int j = 0; j < n_tiles; ++j) {
         mbar_wait(kv_empty(stage), phase ^ 1);
         mbar_arrive_expect_tx(kv_full(stage), Cfg::STAGE_BYTES);
-        const int row_k = (int)(b * N + (int64_t)j * FA_BK);
+        const int row_k = (int)(b * Nk + (int64_t)j * FA_BK);
 #pragma unroll
         for (int i = 0; i < Cfg::SUB; ++i) {
           tma_load_2d(k_smem(stage) + i * Cfg::KV_SUB_BYTES, &tmK, kv_full(stage), h * DH + i * Cfg::SUB_COLS, row_k);
@@ -576,7 +577,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(s_free(t));
       }
-      const int64_t valid = N - (int64_t)j * FA_BK;
+      const int64_t valid = Nk - (int64_t)j * FA_BK;
       if (valid < FA_BK) {
 #pragma unroll
         for (int i = 0; i < FA_BK; ++i)
@@ -699,14 +700,15 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 template <int DH, int POLY>
-static int launch_attn_tc2(const void* q, const void* k, const void* v, int B, int64_t N, int H, void* out, cudaStream_t st) {
+static int launch_attn_tc2(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, int H, void* out,
+                           cudaStream_t st) {
   using Cfg = Fa2Cfg<DH>;
   const uint64_t d = (uint64_t)H * DH;
   const CUtensorMapSwizzle sw = DH >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap tmQ, tmK, tmV;
   LCASR_TRY(make_tmap_2d_bf16(&tmQ, q, (uint64_t)B * N, d, d * 2, 2 * FA_BQ, Cfg::SUB_COLS, sw));
-  LCASR_TRY(make_tmap_2d_bf16(&tmK, k, (uint64_t)B * N, d, d * 2, FA_BK, Cfg::SUB_COLS, sw));
-  LCASR_TRY(make_tmap_2d_bf16(&tmV, v, (uint64_t)B * N, d, d * 2, FA_BK, Cfg::SUB_COLS, sw));
+  LCASR_TRY(make_tmap_2d_bf16(&tmK, k, (uint64_t)B * Nk, d, d * 2, FA_BK, Cfg::SUB_COLS, sw));
+  LCASR_TRY(make_tmap_2d_bf16(&tmV, v, (uint64_t)B * Nk, d, d * 2, FA_BK, Cfg::SUB_COLS, sw));
   static bool attr_set = false;
   if (!attr_set) {
     LCASR_CUDA(cudaFuncSetAttribute(attn_tc2_kernel<DH, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
@@ -714,7 +716,7 @@ static int launch_attn_tc2(const void* q, const void* k, const void* v, int B, i
   }
   dim3 grid((unsigned)ceil_div(N, 2 * FA_BQ), (unsigned)H, (unsigned)B);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)DH);
-  attn_tc2_kernel<DH, POLY><<<grid, FA2_THREADS, Cfg::SMEM_TOTAL, st>>>(tmQ, tmK, tmV, N, H, scale_log2, (bf16*)out);
+  attn_tc2_kernel<DH, POLY><<<grid, FA2_THREADS, Cfg::SMEM_TOTAL, st>>>(tmQ, tmK, tmV, N, Nk, H, scale_log2, (bf16*)out);
   LCASR_LAUNCH_CHECK();
   return 0;
 }
@@ -1047,11 +1049,12 @@ static int launch_attn_tc(const void* q, const void* k, const void* v, int B, in
   return 0;
 }
 
-int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N, int H, int Dh, int v_transposed,
-                   int64_t Npad, void* out, cudaStream_t st) {
+int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, int H, int Dh,
+                   int v_transposed, int64_t Npad, void* out, cudaStream_t st) {
+  LCASR_CHECK_ARG(Nk == N || !v_transposed, "attention(tcgen05): Nq != Nk needs the natural V layout");
   LCASR_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0 && ((uintptr_t)v & 15) == 0 && ((uintptr_t)out & 15) == 0,
                   "attention(tcgen05): q, k, v, out must be 16-byte aligned");
-  LCASR_CHECK_ARG((int64_t)B * N < ((int64_t)1 << 31), "attention(tcgen05): B*N too large");
+  LCASR_CHECK_ARG((int64_t)B * N < ((int64_t)1 << 31) && (int64_t)B * Nk < ((int64_t)1 << 31), "attention(tcgen05): B*N too large");
   LCASR_CHECK_ARG(!v_transposed || Npad % 8 == 0, "attention(tcgen05): Npad must be a multiple of 8");
   LCASR_CHECK_ARG(H <= 65535 && B <= 65535, "attention(tcgen05): too many heads / batch entries");
   static const bool force_v1 = getenv("LCASR_ATTN_V1") != nullptr;  // debugging aid: one query tile per CTA
@@ -1061,17 +1064,17 @@ int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N
 #define LCASR_FA(DHV)                                                                                             \
   case DHV:                                                                                                       \
     if (v_transposed) return launch_attn_tc<DHV, true>(q, k, v, B, N, H, Npad, out, st);                          \
-    if (force_v1) return launch_attn_tc<DHV, false>(q, k, v, B, N, H, Npad, out, st);                             \
-    if (DHV == 32 && force_v3) return poly == 2 ? launch_attn_tc3<2>(q, k, v, B, N, H, out, st)                  \
+    if (force_v1 && Nk == N) return launch_attn_tc<DHV, false>(q, k, v, B, N, H, Npad, out, st);                  \
+    if (DHV == 32 && force_v3 && Nk == N) return poly == 2 ? launch_attn_tc3<2>(q, k, v, B, N, H, out, st)                  \
                                      : (poly == 4 ? launch_attn_tc3<4>(q, k, v, B, N, H, out, st)                \
                                                   : launch_attn_tc3<0>(q, k, v, B, N, H, out, st));               \
     switch (poly) {                                                                                               \
-      case 0: return launch_attn_tc2<DHV, 0>(q, k, v, B, N, H, out, st);                                          \
-      case 1: return launch_attn_tc2<DHV, 1>(q, k, v, B, N, H, out, st);                                          \
-      case 2: return launch_attn_tc2<DHV, 2>(q, k, v, B, N, H, out, st);                                          \
-      case 8: return launch_attn_tc2<DHV, 8>(q, k, v, B, N, H, out, st);                                          \
-      case 9: return launch_attn_tc2<DHV, 9>(q, k, v, B, N, H, out, st);                                          \
-      default: return launch_attn_tc2<DHV, 4>(q, k, v, B, N, H, out, st);                                         \
+      case 0: return launch_attn_tc2<DHV, 0>(q, k, v, B, N, Nk, H, out, st);                                          \
+      case 1: return launch_attn_tc2<DHV, 1>(q, k, v, B, N, Nk, H, out, st);                                          \
+      case 2: return launch_attn_tc2<DHV, 2>(q, k, v, B, N, Nk, H, out, st);                                          \
+      case 8: return launch_attn_tc2<DHV, 8>(q, k, v, B, N, Nk, H, out, st);                                          \
+      case 9: return launch_attn_tc2<DHV, 9>(q, k, v, B, N, Nk, H, out, st);                                          \
+      default: return launch_attn_tc2<DHV, 4>(q, k, v, B, N, Nk, H, out, st);                                         \
     }
   switch (Dh) {
     LCASR_FA(32) LCASR_FA(64) LCASR_FA(128)

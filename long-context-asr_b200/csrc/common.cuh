@@ -78,6 +78,23 @@ __device__ __forceinline__ float warp_max(float v) {
 // x * sigmoid(x); expf keeps fp32-mode parity at the 1e-6 level
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// bf16-output variants: one MUFU (tanh.approx, rel. error 2^-11 — below bf16's 2^-9) instead of ex2 + rcp
+__device__ __forceinline__ float tanh_approx_f(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float silu_fast(float x) {  // x*sigmoid(x) = h + h*tanh(h), h = x/2
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx_f(h), h);
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx_f(0.5f * x), 0.5f); }
+template <typename TOut> __device__ __forceinline__ float silu_for(float x) {
+  if constexpr (sizeof(TOut) == 2) return silu_fast(x); else return silu_f(x);
+}
+template <typename TOut> __device__ __forceinline__ float sigmoid_for(float x) {
+  if constexpr (sizeof(TOut) == 2) return sigmoid_fast(x); else return sigmoid_f(x);
+}
 // F.gelu(x, approximate='tanh')  (fused_dense.py:466)
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(128) dwconv_brn_silu_kernel(const TIn* __restr
       float a = 0.f;
 #pragma unroll
       for (int k = 0; k < KS; ++k) a = fmaf(wr[c][k], win[k][c], a);
-      y[c] = silu_f(fmaf(a, scale[c], shift[c]));
+      y[c] = silu_for<TOut>(fmaf(a, scale[c], shift[c]));
     }
     Vec8<TOut>::store(out + (batch * N + n) * d + c0, y);
   }

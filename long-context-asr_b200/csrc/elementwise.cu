@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(256) glu_kernel(const T* __restrict__ in, int6
     Vec8<T>::load(in + m * 2 * d + j, a);
     Vec8<T>::load(in + m * 2 * d + d + j, g);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = a[i] * sigmoid_f(g[i]);
+    for (int i = 0; i < 8; ++i) y[i] = a[i] * sigmoid_for<T>(g[i]);
     Vec8<T>::store(out + m * d + j, y);
   }
 }

@@ -65,7 +65,7 @@ __device__ __forceinline__ void tg_store_chunk_direct(const uint32_t (&r)[32], i
     }
   } else if (ep.act == LCASR_ACT_SILU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) y[i] = __fdividef(y[i], 1.0f + __expf(-y[i]));
+    for (int i = 0; i < 32; ++i) y[i] = silu_fast(y[i]);
   }
   bf16* op = out + row * N + col0;
 #pragma unroll

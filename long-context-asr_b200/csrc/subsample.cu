@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) subsample_conv0_kernel(const float* __res
       float a = br[c];
 #pragma unroll
       for (int k = 0; k < 9; ++k) a = fmaf(wr[c][k], in[k], a);
-      y[c] = silu_f(a);
+      y[c] = silu_for<TOut>(a);
     }
     TOut* o = out + (((int64_t)b * T1 + t1) * F1 + f1) * C + cg * 8;
     Vec8<TOut>::store(o, y);

@@ -325,11 +325,16 @@ class SCConformerXL(nn.Module):
             return (vec(prefix + ".scale"), None) if rms else (vec(prefix + ".weight"), vec(prefix + ".bias"))
 
         w = L.LcasrWeights()
+        layers = (L.LcasrLayerWeights * self.n_layers)()
         keep = []
+        packed: Dict[str, Optional[torch.Tensor]] = {}  # the same tensors by name (sequence-parallel driver, tests)
+
+        cur_prefix = [""]  # "" for model-level tensors, "layers.<l>." inside the layer loop
 
         def put(struct, field, t):
             if t is not None:
                 keep.append(t)
+            packed[cur_prefix[0] + field] = t
             setattr(struct, field, L.ptr(t))
 
         put(w, "conv0_w", vec("subsampling.conv.0.weight").reshape(Cc, 9).contiguous())
@@ -349,9 +354,9 @@ class SCConformerXL(nn.Module):
         put(w, "dec_ff_w", mat(sd["decoder.ff.weight"])); put(w, "dec_ff_b", vec("decoder.ff.bias"))
         put(w, "dec_rep_w", mat(sd["decoder.reprojection.weight"])); put(w, "dec_rep_b", vec("decoder.reprojection.bias"))
 
-        layers = (L.LcasrLayerWeights * self.n_layers)()
         for l in range(self.n_layers):
             p, lw = f"layers.{l}.", layers[l]
+            cur_prefix[0] = p
             for ff in ("ff1", "ff2"):
                 nw, nb = norm_wb(p + ff + ".fn.norm")
                 put(lw, ff + "_norm_w", nw); put(lw, ff + "_norm_b", nb)
@@ -387,6 +392,7 @@ class SCConformerXL(nn.Module):
         L.call("lcasr_model_create", C.byref(cfg), C.byref(w), C.byref(handle))
         self._handle = handle.value
         self._keepalive = (keep, layers, w)
+        self._packed = packed
         L.call("lcasr_model_set_impl", self._handle, *self._impl)
 
     def _ensure_built(self, device):

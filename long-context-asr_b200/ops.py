@@ -111,6 +111,16 @@ def attention(q, k, v, v_transposed=False, impl=L.ATTN_AUTO):
     return out
 
 
+def attention_cross(q, k, v, impl=L.ATTN_AUTO):
+    """q [B,Nq,H,Dh] against k,v [B,Nk,H,Dh] (sequence-parallel attention: local queries, gathered K/V)."""
+    _cuda(q, k, v)
+    B, Nq, H, Dh = q.shape
+    Nk = k.shape[1]
+    out = torch.empty(B, Nq, H * Dh, dtype=q.dtype, device=q.device)
+    L.call("lcasr_attention_cross", L.ptr(q), L.ptr(k), L.ptr(v), L.dtype_code(q.dtype), B, Nq, Nk, H, Dh, L.ptr(out), impl, _s())
+    return out
+
+
 def dwconv_brn_silu(x, w, b, mean, std, bw, bb):
     _cuda(x, w, b, mean, std, bw, bb)
     B, N, d = x.shape
