@@ -10,6 +10,8 @@
 // Backward: beta recursion run the same way backwards in time writing log(alpha*beta) in place,
 // then a collect kernel (one CTA per frame) scatters into the class axis.
 #include "common.cuh"
+#include <cooperative_groups.h>
+#include <cstdlib>
 
 namespace lcasr {
 
@@ -129,6 +131,151 @@ __global__ void __launch_bounds__(1024) ctc_recursion_kernel(const float* __rest
   }
 }
 
+// ---- long sequences: one thread-block CLUSTER per sample -------------------------------------
+// A 1-hour recording has 45000 frames x 27001 states; on one SM that is ~26 us per frame (1.16 s,
+// the same as ATen's kernel).  Here the states are split over the CTAs of a cluster (<= 8 SMs, 1024
+// threads each, SPT <= 4 contiguous states per thread); alpha(t-1)/alpha(t) stay double-buffered in
+// each CTA's shared memory, the two boundary states come from the left neighbour through distributed
+// shared memory, and one cluster barrier per frame replaces __syncthreads.
+namespace cg = cooperative_groups;
+
+template <int SPT>
+__global__ void __launch_bounds__(1024) ctc_cluster_kernel(const float* __restrict__ log_probs, int64_t N, int V,
+                                                           const int64_t* __restrict__ targets, int64_t S_max,
+                                                           const int32_t* __restrict__ input_lengths,
+                                                           const int64_t* __restrict__ target_lengths, int blank,
+                                                           int direction, float* __restrict__ nll,
+                                                           float* __restrict__ store) {
+  extern __shared__ float sm_alpha[];  // [2][CH]
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+  const int b = blockIdx.x / csize;
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int CH = NT * SPT;
+  const int64_t T = input_lengths ? min((int64_t)input_lengths[b], N) : N;
+  const int64_t S = target_lengths[b];
+  const int Lp = (int)(2 * S + 1), Lp_max = (int)(2 * S_max + 1);
+  float* cur = sm_alpha;
+  float* nxt = sm_alpha + CH;
+  const float* lp = log_probs + (int64_t)b * N * V;
+  const int64_t* tgt = targets + (int64_t)b * S_max;
+  float* st = store ? store + (int64_t)b * N * Lp_max : nullptr;
+  if (T <= 0 || T < S) {  // uniform over the cluster
+    if (crank == 0 && tid == 0 && nll) nll[b] = INFINITY;
+    return;
+  }
+  const int loc0 = tid * SPT, s0 = crank * CH + loc0;
+  int lab[SPT];
+  bool skip[SPT];
+#pragma unroll
+  for (int j = 0; j < SPT; ++j) {
+    const int s = s0 + j;
+    lab[j] = blank;
+    skip[j] = false;
+    if (s < Lp && (s & 1)) {
+      const int64_t li = (s - 1) >> 1;
+      const int64_t oi = direction > 0 ? li : (S - 1 - li);
+      lab[j] = (int)tgt[oi];
+      if (li >= 1) skip[j] = tgt[direction > 0 ? oi - 1 : oi + 1] != tgt[oi];
+    }
+  }
+  auto frame = [&](int64_t step) -> int64_t { return direction > 0 ? step : (T - 1 - step); };
+  float lpv[SPT], lpn[SPT];
+  {
+    const float* row = lp + frame(0) * V;
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) {
+      const int s = s0 + j;
+      float a = -INFINITY;
+      if (s == 0) a = row[blank];
+      else if (s == 1 && Lp > 1) a = row[lab[j]];
+      cur[loc0 + j] = a;
+      if (st && s < Lp) {
+        float* p = st + frame(0) * Lp_max + (direction > 0 ? s : (Lp - 1 - s));
+        *p = direction > 0 ? a : (*p + a);
+      }
+    }
+    if (T > 1) {
+      const float* row1 = lp + frame(1) * V;
+#pragma unroll
+      for (int j = 0; j < SPT; ++j) lpv[j] = row1[lab[j]];
+    }
+  }
+  // the left neighbour's two buffers (distributed shared memory)
+  const float* left_cur = crank > 0 ? cluster.map_shared_rank(cur, crank - 1) : nullptr;
+  const float* left_nxt = crank > 0 ? cluster.map_shared_rank(nxt, crank - 1) : nullptr;
+  cluster.sync();
+  for (int64_t step = 1; step < T; ++step) {
+    if (step + 1 < T) {
+      const float* rown = lp + frame(step + 1) * V;
+#pragma unroll
+      for (int j = 0; j < SPT; ++j) lpn[j] = rown[lab[j]];
+    }
+    float* strow = st ? st + frame(step) * Lp_max : nullptr;
+    float prev1, prev2;  // alpha(t-1) of states s0-1, s0-2
+    if (loc0 >= 2) { prev1 = cur[loc0 - 1]; prev2 = cur[loc0 - 2]; }
+    else if (crank > 0) { prev1 = left_cur[CH - 1]; prev2 = left_cur[CH - 2]; }  // only thread 0 of a CTA (SPT >= 2) ...
+    else { prev1 = -INFINITY; prev2 = -INFINITY; }
+    if (SPT == 1 && loc0 == 1) { prev1 = cur[0]; prev2 = crank > 0 ? left_cur[CH - 1] : -INFINITY; }  // ... or threads 0,1 (SPT == 1)
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) {
+      const int s = s0 + j;
+      const float a0 = cur[loc0 + j];
+      if (s < Lp) {
+        const float a2 = skip[j] ? prev2 : -INFINITY;
+        const float m = fmaxf(fmaxf(a0, prev1), a2);
+        float a = -INFINITY;
+        if (m != -INFINITY) a = m + __logf(__expf(a0 - m) + __expf(prev1 - m) + __expf(a2 - m)) + lpv[j];
+        nxt[loc0 + j] = a;
+        if (strow) {
+          const int so = direction > 0 ? s : (Lp - 1 - s);
+          strow[so] = direction > 0 ? a : (strow[so] + a);
+        }
+      }
+      prev2 = prev1;
+      prev1 = a0;
+    }
+    cluster.sync();
+    { float* tmp = cur; cur = nxt; nxt = tmp; }
+    { const float* tmp = left_cur; left_cur = left_nxt; left_nxt = tmp; }
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) lpv[j] = lpn[j];
+  }
+  if (nll) {  // the thread that owns state Lp-1 finishes the sample
+    const int sl = Lp - 1;
+    if (sl >= s0 && sl < s0 + SPT) {
+      const int loc = sl - crank * CH;
+      const float l1 = cur[loc];
+      float l2 = -INFINITY;
+      if (Lp > 1) l2 = loc >= 1 ? cur[loc - 1] : left_cur[CH - 1];
+      const float m = fmaxf(l1, l2);
+      nll[b] = m == -INFINITY ? INFINITY : -(m + logf(expf(l1 - m) + expf(l2 - m)));
+    }
+  }
+  cluster.sync();  // nobody exits while a neighbour may still read its shared memory
+}
+
+template <int SPT>
+static int launch_cluster(const float* lp, int B, int64_t N, int V, const int64_t* tg, int64_t S_max, const int32_t* il,
+                          const int64_t* tl, int blank, int dir, float* nll, float* store, int nt, int csize,
+                          cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(B * csize));
+  cfg.blockDim = dim3((unsigned)nt);
+  cfg.dynamicSmemBytes = (size_t)2 * SPT * nt * sizeof(float);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LCASR_CUDA(cudaLaunchKernelEx(&cfg, ctc_cluster_kernel<SPT>, lp, N, V, tg, S_max, il, tl, blank, dir, nll, store));
+  count_launch();
+  return 0;
+}
+
 // grad[b,t,c] = exp(lp) - exp(log(sum_{s:ext[s]=c} exp(ab[t,s])) + nll - lp)     (t < input_length)
 // ab = alpha+beta (log), both including lp[t,ext[s]] (ATen convention).  One CTA per (t, b).
 __global__ void __launch_bounds__(256) ctc_grad_collect_kernel(const float* __restrict__ log_probs, int64_t N, int V,
@@ -201,6 +348,20 @@ static int launch_rec(const float* lp, int B, int64_t N, int V, const int64_t* t
 static int ctc_recursion(const float* lp, int B, int64_t N, int V, const int64_t* tg, int64_t S_max, const int32_t* il,
                          const int64_t* tl, int blank, int dir, float* nll, float* store, cudaStream_t st) {
   const int64_t Lp = 2 * S_max + 1;
+  static const bool no_cluster = getenv("LCASR_CTC_NO_CLUSTER") != nullptr;  // A/B switch for profiling
+  if (Lp > 4096 && !no_cluster) {  // spread the states over a cluster of up to 8 SMs (below that the cluster
+                                    // barrier costs more than it saves: measured 2.7 vs 1.45 ms at 1229 states)
+    LCASR_CHECK_ARG(Lp <= 8 * 1024 * 4, "ctc_loss: %lld extended states exceed one cluster (max 32768)", (long long)Lp);
+    int spt = 1;
+    while ((int64_t)8 * 1024 * spt < Lp) spt *= 2;          // fewest states per thread that still fits 8 CTAs
+    const int csize = (int)ceil_div(Lp, (int64_t)1024 * spt);
+    const int nt = 1024;
+    switch (spt) {
+      case 1: return launch_cluster<1>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, csize, st);
+      case 2: return launch_cluster<2>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, csize, st);
+      default: return launch_cluster<4>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, csize, st);
+    }
+  }
   LCASR_CHECK_ARG(Lp <= (int64_t)kCtcMaxSPT * 1024 && Lp * 8 <= 227 * 1024 - 64,
                   "ctc_loss: %lld extended states do not fit one CTA's shared memory (max 29048)", (long long)Lp);
   int spt = 1;

@@ -220,3 +220,35 @@ def test_ctc_loss_forward_backward(cuda_device, B, N, V, S):
     np.testing.assert_allclose(lpc.grad.cpu().numpy(), gref, rtol=5e-3, atol=2e-4 * max(1.0, N / 64))
     report(test="ctc", B=B, N=N, V=V, S=S, nll_rel=float(np.abs(nll.cpu().numpy() - ref).max() / np.abs(ref).max()),
            grad_abs=float(np.abs(lpc.grad.cpu().numpy() - gref).max()))
+
+
+@pytest.mark.parametrize("B,N,V,S", [(2, 2500, 64, 700), (1, 7000, 128, 3000), (1, 20000, 4096, 9000)])
+def test_ctc_loss_cluster_kernel_long_sequences(cuda_device, B, N, V, S):
+    """> 1024 extended states: the thread-block-cluster kernel (DSMEM boundary exchange) against torch's
+    CPU ctc_loss (ATen) for the loss and its gradient."""
+    import lcasr_b200
+    blank = V - 1
+    g = torch.Generator().manual_seed(31)
+    lp = torch.randn(B, N, V, generator=g).log_softmax(-1)
+    tgt = torch.randint(0, V - 1, (B, S), generator=g)
+    tgt[:, 5] = tgt[:, 4]
+    tl = torch.tensor([S - 7 * b for b in range(B)], dtype=torch.long)
+    il = torch.tensor([N - 11 * b for b in range(B)], dtype=torch.int32)
+    def torch_ctc(x):
+        x = x.clone().requires_grad_(True)
+        loss = F.ctc_loss(x.transpose(0, 1), tgt, il.long(), tl, blank=blank, reduction="none")
+        loss.sum().backward()
+        return loss.detach(), x.grad
+    ref64, g64 = torch_ctc(lp.double())   # ground truth
+    ref32, g32 = torch_ctc(lp)            # what the reference computes (ATen, fp32 log-domain recursion)
+    lpc = lp.to(cuda_device).requires_grad_(True)
+    nll = lcasr_b200.CTCLoss(blank=blank, reduction="none")(lpc.transpose(0, 1), tgt, il, tl)
+    nll.sum().backward()
+    rel = ((nll.detach().cpu().double() - ref64).abs() / ref64.abs()).max().item()
+    gerr = (lpc.grad.cpu().double() - g64).abs().max().item()
+    gerr_torch32 = (g32.double() - g64).abs().max().item()
+    report(test="ctc_cluster", B=B, N=N, V=V, S=S, nll_rel=rel, grad_abs_vs_fp64=gerr, torch_fp32_grad_abs_vs_fp64=gerr_torch32)
+    assert rel < 1e-5  # north_star: CTC loss within 1e-3 relative
+    # |alpha+beta| grows ~ 8*N, so an fp32 recursion cannot resolve the exponent better than its ulp: the
+    # bar is "no worse than the reference's own fp32 implementation" (x2 margin)
+    assert gerr < 2.0 * gerr_torch32 + 1e-3
