@@ -281,6 +281,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // ================================================================================================
 constexpr int FA2_THREADS = 384;
 
+// The MMA issuer polls several mbarriers.  A hot polling loop competes for issue slots with the two or
+// three softmax warps on its SM sub-partition (and every tile waits for its slowest quarter), so the
+// loop backs off for a few dozen cycles whenever a sweep found nothing to do.
+#ifndef LCASR_POLL_SLEEP_NS
+#define LCASR_POLL_SLEEP_NS 0
+#endif
+#define LCASR_POLL_BACKOFF() ((LCASR_POLL_SLEEP_NS) > 0 ? __nanosleep(LCASR_POLL_SLEEP_NS) : (void)0)
+
 // Optional phase trace of CTA (0,0,0) (tools/trace_attn.py): clock64 stamps of the softmax warps
 // (quarter 0 of each query tile) and of the MMA issuer.  Enabled by lcasr_debug_attn_trace(1).
 constexpr int kTraceIters = 32;
@@ -524,7 +532,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       if (progressed) {
         idle = 0; idle_t0 = 0;
-      } else if ((++idle & 0xFFFF) == 0) {  // deadlock guard: trap instead of hanging the GPU
+      } else if (LCASR_POLL_BACKOFF(), (++idle & 0xFFFF) == 0) {  // deadlock guard: trap instead of hanging the GPU
         uint64_t now;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
         if (idle_t0 == 0) idle_t0 = now;
@@ -722,295 +730,6 @@ static int launch_attn_tc2(const void* q, const void* k, const void* v, int B, i
 }
 
 
-// ================================================================================================
-// Version 3 (head_dim 32): FOUR query tiles per CTA (512 query rows), 64-key K/V tiles.
-// With Dh = 32 the tensor work per score is tiny (128 MMA flops vs one exponential): the kernel is
-// bound by the softmax warps' latency chain (TMEM load -> row max -> exp -> pack -> TMEM store ->
-// barrier), not by any single pipe (measured: removing every ex2 only takes it from 2.1 to 1.5 ms).
-// So the design maximises the number of independent softmax chains per SM: 16 softmax warps (4 per
-// SM sub-partition) instead of 8, each working on a 32-row x 64-key block, which still fits tensor
-// memory exactly:   S_t 4x64 | P_t 4x32 | O_t 4x32  = 512 columns.
-//   warps 0-15  softmax, tile t = warp/4, TMEM lane quarter = warp%4
-//   warp 16     TMA producer (Q once, K/V 64-key tiles, 8-stage ring)
-//   warp 17     MMA issuer (converged warp, elected lane, polls the 4 tiles' barriers)
-// Protocol per tile t (P has its own columns, so nothing aliases):
-//   s_full[t]  QK_t(j) retired            -> softmax may read S_t
-//   s_free[t]  softmax finished reading S_t(j)  -> issuer may run QK_t(j+1)
-//   p_full[t]  P_t(j) stored (O_t rescaled)     -> issuer runs PV_t(j)
-//   pv_done[t] PV_t(j) retired            -> P_t / O_t may be touched again
-//   kv_empty[s] counts 4 commits (one per tile's PV) -> producer refills the stage
-// ================================================================================================
-constexpr int FA3_NT = 4, FA3_BK = 64, FA3_STAGES = 8, FA3_THREADS = 640;
-
-template <int POLY>
-__global__ void __launch_bounds__(FA3_THREADS, 1)
-attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, int64_t N, int H, float scale_log2, bf16* __restrict__ out) {
-  constexpr int DH = 32, NT = FA3_NT, BK = FA3_BK, STAGES = FA3_STAGES;
-  constexpr int ROW_BYTES = 64;                       // 32 bf16: SWIZZLE_64B rows
-  constexpr int Q_BYTES = NT * FA_BQ * ROW_BYTES;     // 32 KB
-  constexpr int K_BYTES = BK * ROW_BYTES;             // 4 KB
-  constexpr int STAGE_BYTES = 2 * K_BYTES;
-  constexpr int P_COL = NT * BK, O_COL = NT * BK + NT * (BK / 2);
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[1 + 2 * STAGES + 4 * NT];
-  __shared__ uint32_t tmem_slot;
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t q_smem = smem_base;
-  auto k_smem = [&](int st) { return smem_base + Q_BYTES + st * STAGE_BYTES; };
-  auto v_smem = [&](int st) { return smem_base + Q_BYTES + st * STAGE_BYTES + K_BYTES; };
-  const uint32_t bar0 = smem_u32(bars);
-  const uint32_t q_full = bar0;
-  auto kv_full = [&](int st) { return bar0 + 8u * (1 + st); };
-  auto kv_empty = [&](int st) { return bar0 + 8u * (1 + STAGES + st); };
-  auto s_full = [&](int t) { return bar0 + 8u * (1 + 2 * STAGES + t); };
-  auto s_free = [&](int t) { return bar0 + 8u * (1 + 2 * STAGES + NT + t); };
-  auto p_full = [&](int t) { return bar0 + 8u * (1 + 2 * STAGES + 2 * NT + t); };
-  auto pv_done = [&](int t) { return bar0 + 8u * (1 + 2 * STAGES + 3 * NT + t); };
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.y;
-  const int64_t b = blockIdx.z;
-  const int64_t q0 = (int64_t)blockIdx.x * (NT * FA_BQ);
-  const int n_tiles = (int)((N + BK - 1) / BK);
-
-  if (warp == 16 && lane == 0) {
-    prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
-    mbar_init(q_full, 1);
-    for (int st = 0; st < STAGES; ++st) { mbar_init(kv_full(st), 1); mbar_init(kv_empty(st), NT); }
-    for (int t = 0; t < NT; ++t) {
-      mbar_init(s_full(t), 1); mbar_init(s_free(t), 4); mbar_init(p_full(t), 4); mbar_init(pv_done(t), 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 17) {
-    tmem_alloc(smem_u32(&tmem_slot), 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
-
-  if (warp >= 16) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 16) {
-      if (lane == 0) {  // ------------------------- TMA producer -------------------------
-        const int row_q = (int)(b * N + q0);
-        mbar_arrive_expect_tx(q_full, Q_BYTES);
-        tma_load_2d(q_smem, &tmQ, q_full, h * DH, row_q);                                   // tiles 0,1 (256-row box)
-        tma_load_2d(q_smem + 2 * FA_BQ * ROW_BYTES, &tmQ, q_full, h * DH, row_q + 2 * FA_BQ);  // tiles 2,3
-        int stage = 0; uint32_t phase = 0;
-        for (int j = 0; j < n_tiles; ++j) {
-          mbar_wait(kv_empty(stage), phase ^ 1);
-          mbar_arrive_expect_tx(kv_full(stage), STAGE_BYTES);
-          const int row_k = (int)(b * N + (int64_t)j * BK);
-          tma_load_2d(k_smem(stage), &tmK, kv_full(stage), h * DH, row_k);
-          tma_load_2d(v_smem(stage), &tmV, kv_full(stage), h * DH, row_k);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    } else if (warp == 17) {
-      // ------------------------- MMA issuer -------------------------
-      constexpr uint32_t idesc_qk = make_idesc_bf16(FA_BQ, BK, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(FA_BQ, DH, 1);  // V is MN-major
-      constexpr uint32_t DESC_HI = (((8 * ROW_BYTES) >> 4) & 0x3FFF) | (1u << 14) | (kLayoutSW64 << 29);
-      auto mk = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; };
-      const uint32_t q_lo0 = (q_smem >> 4) | (1u << 16);
-      const uint32_t k_lo0 = (k_smem(0) >> 4) | (1u << 16);
-      const uint32_t v_lo0 = (v_smem(0) >> 4) | (1u << 16);  // LBO unused: N = 32 is a single MN atom
-      auto issue_qk = [&](int stage, int t) {
-        const uint32_t a_lo = q_lo0 + t * ((FA_BQ * ROW_BYTES) >> 4);
-        const uint32_t b_lo = k_lo0 + stage * (STAGE_BYTES >> 4);
-#pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk)
-          umma_f16_ss(tmem_base + t * BK, mk(a_lo + ((kk * 32) >> 4)), mk(b_lo + ((kk * 32) >> 4)), idesc_qk, kk != 0);
-      };
-      auto issue_pv = [&](int stage, int t, bool accumulate) {
-        const uint32_t b_lo = v_lo0 + stage * (STAGE_BYTES >> 4);
-#pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk)
-          umma_f16_ts(tmem_base + O_COL + t * DH, tmem_base + P_COL + t * (BK / 2) + kk * 8,
-                      mk(b_lo + ((kk * 16 * ROW_BYTES) >> 4)), idesc_pv, (accumulate || kk != 0) ? 1u : 0u);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(kv_full(0), 0);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int t = 0; t < NT; ++t) { issue_qk(0, t); umma_commit(s_full(t)); }
-      }
-      __syncwarp();
-      int qk_n[NT], pv_n[NT];
-#pragma unroll
-      for (int t = 0; t < NT; ++t) { qk_n[t] = 1; pv_n[t] = 0; }
-      int full_upto = 0, remaining = NT;
-      uint32_t idle = 0;
-      uint64_t idle_t0 = 0;
-      while (remaining > 0) {
-        bool progressed = false;
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-          const int jq = qk_n[t];
-          if (jq < n_tiles && mbar_test_wait(s_free(t), (jq - 1) & 1)) {
-            bool landed = jq <= full_upto;
-            if (!landed && mbar_test_wait(kv_full(jq % STAGES), (jq / STAGES) & 1)) { full_upto = jq; landed = true; }
-            if (landed) {
-              tc_fence_after();
-              if (elect_one()) { issue_qk(jq % STAGES, t); umma_commit(s_full(t)); }
-              __syncwarp();
-              qk_n[t] = jq + 1;
-              progressed = true;
-            }
-          }
-          const int j = pv_n[t];
-          if (j < n_tiles && mbar_test_wait(p_full(t), j & 1)) {
-            tc_fence_after();
-            if (elect_one()) {
-              issue_pv(j % STAGES, t, j > 0);
-              umma_commit(kv_empty(j % STAGES));  // the 4th tile's commit releases the stage
-              umma_commit(pv_done(t));
-            }
-            __syncwarp();
-            pv_n[t] = j + 1;
-            if (j + 1 == n_tiles) --remaining;
-            progressed = true;
-          }
-        }
-        if (progressed) {
-          idle = 0; idle_t0 = 0;
-        } else if ((++idle & 0xFFFF) == 0) {  // deadlock guard: trap instead of hanging the GPU
-          uint64_t now;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-          if (idle_t0 == 0) idle_t0 = now;
-          else if (now - idle_t0 > 4000000000ull) {
-            if (lane == 0) printf("lcasr_b200: attention(v3) MMA issuer stalled (block %d,%d,%d)\n", blockIdx.x, blockIdx.y, blockIdx.z);
-            asm volatile("trap;");
-          }
-        }
-      }
-    }
-  } else {  // ------------------------- softmax warps -------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    const int t = warp >> 2;
-    const int lane_base = (warp & 3) * 32;
-    const int row = lane_base + lane;
-    const uint32_t t_lane = tmem_base + ((uint32_t)lane_base << 16);
-    const uint32_t s_addr = t_lane + t * BK;
-    const uint32_t p_addr = t_lane + P_COL + t * (BK / 2);
-    const uint32_t o_addr = t_lane + O_COL + t * DH;
-    float m_run = -INFINITY, l_run = 0.f;
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(s_full(t), j & 1);
-      tc_fence_after();
-      uint32_t s[BK];
-      tmem_ld_32x32b_x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-      tmem_ld_32x32b_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_free(t));  // S_t(j) is in registers: QK_t(j+1) may overwrite it
-      const int64_t valid = N - (int64_t)j * BK;
-      if (valid < BK) {
-#pragma unroll
-        for (int i = 0; i < BK; ++i)
-          if (i >= valid) s[i] = 0xff800000u;
-      }
-      float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int i = 0; i < BK; i += 8) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          asm("max.f32 %0, %0, %1, %2;" : "+f"(mxa[u]) : "f"(__uint_as_float(s[i + 2 * u])), "f"(__uint_as_float(s[i + 2 * u + 1])));
-      }
-      const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])) * scale_log2;
-      if (j == 0) {
-        m_run = mx;
-      } else {
-        mbar_wait(pv_done(t), (j - 1) & 1);  // P_t / O_t are free again (long retired in steady state)
-        tc_fence_after();
-        const bool grow = mx > m_run + 8.0f;
-        if (__any_sync(0xffffffffu, grow)) {
-          const float m_new = grow ? mx : m_run;
-          const float alpha = ex2_approx(m_run - m_new);
-          l_run *= alpha;
-          m_run = m_new;
-          uint32_t o[32];
-          tmem_ld_32x32b_x32(o_addr, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_32x32b_x32(o_addr, o);
-          tmem_wait_st();
-        }
-      }
-      float sums[4] = {0.f, 0.f, 0.f, 0.f};
-      const float neg_m = -m_run;
-      uint32_t pk[BK / 2];
-#pragma unroll
-      for (int i = 0; i < BK / 2; ++i) {
-        const float x0 = fmaf(__uint_as_float(s[2 * i]), scale_log2, neg_m);
-        const float x1 = fmaf(__uint_as_float(s[2 * i + 1]), scale_log2, neg_m);
-        const float p0 = ex2_approx(x0);
-        const float p1 = (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == 0) ? ex2_poly(x1) : ex2_approx(x1);
-        sums[(2 * i) & 3] += p0; sums[(2 * i + 1) & 3] += p1;
-        __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
-        pk[i] = *reinterpret_cast<uint32_t*>(&pp);
-      }
-      l_run += (sums[0] + sums[1]) + (sums[2] + sums[3]);
-      tmem_st_32x32b_x32(p_addr, pk);
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full(t));
-    }
-    mbar_wait(pv_done(t), (n_tiles - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.0f / l_run;
-    const int64_t n = q0 + t * FA_BQ + row;
-    uint32_t o[32];
-    tmem_ld_32x32b_x32(o_addr, o);
-    tmem_wait_ld();
-    if (n < N) {
-      bf16* orow = out + ((b * N + n) * H + h) * DH;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float y[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(o[g * 8 + i]) * inv_l;
-        Vec8<bf16>::store(orow + g * 8, y);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 17) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-template <int POLY>
-static int launch_attn_tc3(const void* q, const void* k, const void* v, int B, int64_t N, int H, void* out, cudaStream_t st) {
-  constexpr int DH = 32;
-  constexpr int SMEM = FA3_NT * FA_BQ * 64 + FA3_STAGES * 2 * FA3_BK * 64 + 1024;
-  const uint64_t d = (uint64_t)H * DH;
-  CUtensorMap tmQ, tmK, tmV;
-  LCASR_TRY(make_tmap_2d_bf16(&tmQ, q, (uint64_t)B * N, d, d * 2, 2 * FA_BQ, DH, CU_TENSOR_MAP_SWIZZLE_64B));
-  LCASR_TRY(make_tmap_2d_bf16(&tmK, k, (uint64_t)B * N, d, d * 2, FA3_BK, DH, CU_TENSOR_MAP_SWIZZLE_64B));
-  LCASR_TRY(make_tmap_2d_bf16(&tmV, v, (uint64_t)B * N, d, d * 2, FA3_BK, DH, CU_TENSOR_MAP_SWIZZLE_64B));
-  static bool attr_set = false;
-  if (!attr_set) {
-    LCASR_CUDA(cudaFuncSetAttribute(attn_tc3_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
-  }
-  dim3 grid((unsigned)ceil_div(N, FA3_NT * FA_BQ), (unsigned)H, (unsigned)B);
-  const float scale_log2 = 1.4426950408889634f / sqrtf((float)DH);
-  attn_tc3_kernel<POLY><<<grid, FA3_THREADS, SMEM, st>>>(tmQ, tmK, tmV, N, H, scale_log2, (bf16*)out);
-  LCASR_LAUNCH_CHECK();
-  return 0;
-}
-
 int attn_tc_available() { return 1; }
 
 }  // namespace lcasr
@@ -1058,16 +777,12 @@ int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N
   LCASR_CHECK_ARG(!v_transposed || Npad % 8 == 0, "attention(tcgen05): Npad must be a multiple of 8");
   LCASR_CHECK_ARG(H <= 65535 && B <= 65535, "attention(tcgen05): too many heads / batch entries");
   static const bool force_v1 = getenv("LCASR_ATTN_V1") != nullptr;  // debugging aid: one query tile per CTA
-  static const bool force_v3 = getenv("LCASR_ATTN_V3") != nullptr;  // experiment: four query tiles / 64-key tiles for Dh=32 (measured slower)
   // fraction of exponentials evaluated on the FMA pipes: POLY=p -> every p-th odd key, i.e. 1/(2p) of all
   static const int poly = getenv("LCASR_ATTN_POLY") ? atoi(getenv("LCASR_ATTN_POLY")) : 0;  // measured: the Dh=32 kernel is latency- not MUFU-bound, offload does not pay yet
 #define LCASR_FA(DHV)                                                                                             \
   case DHV:                                                                                                       \
     if (v_transposed) return launch_attn_tc<DHV, true>(q, k, v, B, N, H, Npad, out, st);                          \
     if (force_v1 && Nk == N) return launch_attn_tc<DHV, false>(q, k, v, B, N, H, Npad, out, st);                  \
-    if (DHV == 32 && force_v3 && Nk == N) return poly == 2 ? launch_attn_tc3<2>(q, k, v, B, N, H, out, st)                  \
-                                     : (poly == 4 ? launch_attn_tc3<4>(q, k, v, B, N, H, out, st)                \
-                                                  : launch_attn_tc3<0>(q, k, v, B, N, H, out, st));               \
     switch (poly) {                                                                                               \
       case 0: return launch_attn_tc2<DHV, 0>(q, k, v, B, N, Nk, H, out, st);                                          \
       case 1: return launch_attn_tc2<DHV, 1>(q, k, v, B, N, Nk, H, out, st);                                          \
