@@ -64,6 +64,11 @@ int lcasr_subsample_conv0(const float* spec, const float* w, const float* b, int
 int lcasr_subsample_dwconv(const void* in, int dtype, const float* w, const float* b, int B,
                            int64_t Tin, int Fin, int C, void* out, void* stream);
 
+/* conv[0] + SiLU + conv[2] (the first depthwise level) in one kernel, bf16 output [B,T2,F2,C]: the
+ * 160x-expanded conv0 activation never leaves shared memory.  C must be a multiple of 64. */
+int lcasr_subsample_conv0_dw(const float* spec, const float* w0, const float* b0, const float* w1,
+                             const float* b1, int B, int F, int64_t T, int C, void* out, void* stream);
+
 /* out = epilogue(A[M,K] . W[N,K]^T): every dense contraction of the path — nn.Linear / 1x1 Conv
  * (attention.py:483,487; fused_dense.py:464-470; convolution.py:62-86 pointwise; decoder.py:18-19;
  * subsampling.py:314-323,374).  A and W share `ab_dtype`; fp32 accumulation.

@@ -55,6 +55,7 @@ _SIGNATURES = {
     "lcasr_layernorm": [vp, vp, vp, i64, i32, f32, i32, vp, vp, i32, vp],
     "lcasr_subsample_conv0": [vp, vp, vp, i32, i32, i64, i32, vp, i32, vp],
     "lcasr_subsample_dwconv": [vp, i32, vp, vp, i32, i64, i32, i32, vp, vp],
+    "lcasr_subsample_conv0_dw": [vp, vp, vp, vp, vp, i32, i32, i64, i32, vp, vp],
     "lcasr_gemm": [vp, vp, i32, i64, i32, i32, vp, i32, vp, f32, vp, i32, i32, vp],
     "lcasr_cast_f32": [vp, i64, vp, i32, vp],
     "lcasr_glu": [vp, i32, i64, i32, vp, vp],

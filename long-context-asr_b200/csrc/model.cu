@@ -196,8 +196,12 @@ extern "C" int lcasr_model_forward(lcasr_model* m, const float* spec, int B, int
   {
     void* s1 = ws + p.off_s1; void* s2a = ws + p.off_s2a; void* s2b = ws + p.off_s2b;
     void* s3a = ws + p.off_s3a; void* s3b = ws + p.off_s3b;
-    OP(CAT_SUBSAMPLE, lcasr_subsample_conv0(spec, w.conv0_w, w.conv0_b, B, c.feat_in, T, C, s1, cd, stream));
-    OP(CAT_SUBSAMPLE, lcasr_subsample_dwconv(s1, cd, w.dw1_w, w.dw1_b, B, p.T1, p.F1, C, s2a, stream));
+    if (cd == LCASR_BF16 && C % 64 == 0) {  // conv0 + SiLU + depthwise level 1 fused: the 160x activation stays on chip
+      OP(CAT_SUBSAMPLE, lcasr_subsample_conv0_dw(spec, w.conv0_w, w.conv0_b, w.dw1_w, w.dw1_b, B, c.feat_in, T, C, s2a, stream));
+    } else {
+      OP(CAT_SUBSAMPLE, lcasr_subsample_conv0(spec, w.conv0_w, w.conv0_b, B, c.feat_in, T, C, s1, cd, stream));
+      OP(CAT_SUBSAMPLE, lcasr_subsample_dwconv(s1, cd, w.dw1_w, w.dw1_b, B, p.T1, p.F1, C, s2a, stream));
+    }
     LCASR_TRY(gemm(s2a, w.pw1_w, (int64_t)B * p.T2 * p.F2, C, C, w.pw1_b, LCASR_ACT_SILU, nullptr, 0.f, s2b, cd));
     OP(CAT_SUBSAMPLE, lcasr_subsample_dwconv(s2b, cd, w.dw2_w, w.dw2_b, B, p.T2, p.F2, C, s3a, stream));
     LCASR_TRY(gemm(s3a, w.pw2_w, (int64_t)B * N * p.F3, C, C, w.pw2_b, LCASR_ACT_SILU, nullptr, 0.f, s3b, cd));

@@ -4,6 +4,7 @@
 //   conv0 : reads B*F*T*4 bytes, writes B*T1*F1*C*e bytes  (the activation is 160x the input)
 //   dwconv: reads B*Tin*Fin*C*e, writes B*Tout*Fout*C*e
 #include "common.cuh"
+#include <cstdlib>
 
 namespace lcasr {
 
@@ -110,6 +111,101 @@ __global__ void __launch_bounds__(256) subsample_dwconv_kernel(const T* __restri
   }
 }
 
+// ---- fused conv0 + SiLU + first depthwise level (bf16 path) -------------------------------------
+// The 1->C conv0 activation is 160x the input (1.3 GB in bf16 for a 20-minute recording): writing it
+// and reading it back 2.25x for the stride-2 depthwise conv is what made the two separate kernels
+// HBM-bound.  Here a CTA owns (batch, 8 output rows of the depthwise level, 64 channels): it stages the
+// 35 x (F+2) spectrogram patch, computes the 17 x (F1+2) x 64 conv0+SiLU tile into shared memory as bf16
+// (zeros where the depthwise conv pads), and reduces it to the 8 x F2 x 64 depthwise outputs.
+// HBM traffic drops to: input (re-read by the 4-8 channel groups, L2-resident) + the depthwise output.
+constexpr int kFuCG = 64;
+
+template <int kFuTT2, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) subsample_conv0_dw_fused_kernel(
+    const float* __restrict__ spec, const float* __restrict__ w0, const float* __restrict__ b0,
+    const float* __restrict__ w1, const float* __restrict__ b1, int F, int64_t T, int C, int64_t T1, int F1,
+    int64_t T2, int F2, bf16* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t fsm[];
+  constexpr int A0R = 2 * kFuTT2 + 1;           // conv0 rows needed: 17
+  constexpr int INR = 2 * A0R + 1;              // input frames needed: 35
+  const int FW = F + 2, A0W = F1 + 2;
+  float* s_in = reinterpret_cast<float*>(fsm);                                   // [INR][FW], col 0 = freq -1
+  __nv_bfloat162* s_a0 = reinterpret_cast<__nv_bfloat162*>(fsm + ((INR * FW * 4 + 15) & ~15));  // [A0R][A0W][32]
+  const int cgi = blockIdx.y, b = blockIdx.z;
+  const int64_t t2_0 = (int64_t)blockIdx.x * kFuTT2;
+  const int64_t a0_row0 = 2 * t2_0 - 1;         // global conv0 row of tile row 0
+  const int64_t t_in0 = 2 * a0_row0 - 1;        // global input frame of patch row 0
+  for (int idx = threadIdx.x; idx < INR * FW; idx += blockDim.x) {
+    const int f = idx / INR - 1, r = idx % INR;
+    const int64_t t = t_in0 + r;
+    float v = 0.f;
+    if (f >= 0 && f < F && t >= 0 && t < T) v = spec[((int64_t)b * F + f) * T + t];
+    s_in[r * FW + (f + 1)] = v;
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;   // lane -> channel pair, warp -> positions
+  const int c0 = cgi * kFuCG + 2 * lane;
+  float wa[2][9], ba[2], wd[2][9], bd[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    ba[c] = b0[c0 + c]; bd[c] = b1[c0 + c];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { wa[c][k] = w0[(c0 + c) * 9 + k]; wd[c][k] = w1[(c0 + c) * 9 + k]; }
+  }
+  __syncthreads();
+  // phase 1: conv0 + SiLU tile (bf16x2 per lane), zero where the depthwise conv sees padding.
+  // Warp w walks tile positions w, w+8, ... with (row, col) advanced incrementally (no div/mod, 32-bit math).
+  {
+    const int r_lo = (int)max((int64_t)0, -a0_row0);                       // tile rows below are conv0 row < 0
+    const int r_hi = (int)min((int64_t)A0R, T1 - a0_row0);                 // tile rows from here on are >= T1
+    int r = 0, c = wid;                                                    // A0W > 8, so one wrap per step at most
+#pragma unroll 2
+    for (int p = wid; p < A0R * A0W; p += 8) {
+      float y0 = 0.f, y1 = 0.f;
+      if (r >= r_lo && r < r_hi && c >= 1 && c <= F1) {
+        const float* in0 = s_in + (2 * r) * FW + 2 * (c - 1);
+        float a = ba[0], bq = ba[1];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float v = in0[i * FW + j];
+            a = fmaf(wa[0][i * 3 + j], v, a);
+            bq = fmaf(wa[1][i * 3 + j], v, bq);
+          }
+        y0 = silu_fast(a); y1 = silu_fast(bq);
+      }
+      s_a0[p * 32 + lane] = __floats2bfloat162_rn(y0, y1);
+      c += 8;
+      if (c >= A0W) { c -= A0W; ++r; }
+    }
+  }
+  __syncthreads();
+  // phase 2: depthwise 3x3 stride 2 over the tile
+  {
+    const int tl_hi = (int)min((int64_t)kFuTT2, T2 - t2_0);
+    int tl = 0, f2 = wid;
+    while (f2 >= F2) { f2 -= F2; ++tl; }                                    // F2 may be < 8
+    bf16* obase = out + (((int64_t)b * T2 + t2_0) * F2) * C + c0;
+#pragma unroll 2
+    for (int q = wid; q < kFuTT2 * F2; q += 8) {
+      if (tl >= tl_hi) break;
+      const __nv_bfloat162* a0p = s_a0 + ((2 * tl) * A0W + 2 * f2) * 32 + lane;
+      float a = bd[0], bq = bd[1];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float2 v = __bfloat1622float2(a0p[(i * A0W + j) * 32]);
+          a = fmaf(wd[0][i * 3 + j], v.x, a);
+          bq = fmaf(wd[1][i * 3 + j], v.y, bq);
+        }
+      *reinterpret_cast<__nv_bfloat162*>(obase + (size_t)q * C) = __floats2bfloat162_rn(a, bq);
+      f2 += 8;
+      while (f2 >= F2) { f2 -= F2; ++tl; }
+    }
+  }
+}
+
 }  // namespace lcasr
 
 using namespace lcasr;
@@ -151,4 +247,32 @@ extern "C" int lcasr_subsample_dwconv(const void* in, int dtype, const float* w,
                                                                       total_vec, (float*)out);
   LCASR_LAUNCH_CHECK();
   return 0;
+}
+
+template <int TT2, int MINB>
+static int launch_fused(const float* spec, const float* w0, const float* b0, const float* w1, const float* b1, int B, int F,
+                        int64_t T, int C, void* out, cudaStream_t st) {
+  const int64_t T1 = (T - 1) / 2 + 1, T2 = (T1 - 1) / 2 + 1;
+  const int F1 = (F - 1) / 2 + 1, F2 = (F1 - 1) / 2 + 1;
+  const size_t smem = (((size_t)(2 * (2 * TT2 + 1) + 1) * (F + 2) * 4 + 15) & ~(size_t)15) + (size_t)(2 * TT2 + 1) * (F1 + 2) * 32 * 4;
+  LCASR_CHECK_ARG(smem <= 110 * 1024, "subsample_conv0_dw: feat_in=%d too large for the fused tile", F);
+  LCASR_CHECK_ARG(ceil_div(T2, TT2) <= 0x7fffffff && B <= 65535, "subsample_conv0_dw: grid too large");
+  static bool attr_set = false;
+  if (!attr_set) {
+    LCASR_CUDA(cudaFuncSetAttribute(subsample_conv0_dw_fused_kernel<TT2, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)ceil_div(T2, TT2), (unsigned)(C / kFuCG), (unsigned)B);
+  subsample_conv0_dw_fused_kernel<TT2, MINB><<<grid, 256, smem, st>>>(spec, w0, b0, w1, b1, F, T, C, T1, F1, T2, F2, (bf16*)out);
+  LCASR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lcasr_subsample_conv0_dw(const float* spec, const float* w0, const float* b0, const float* w1,
+                                        const float* b1, int B, int F, int64_t T, int C, void* out, void* stream) {
+  LCASR_CHECK_ARG(spec && w0 && b0 && w1 && b1 && out && B > 0 && F > 0 && T > 0, "subsample_conv0_dw: bad arguments");
+  LCASR_CHECK_ARG(C % kFuCG == 0, "subsample_conv0_dw: conv_channels=%d must be a multiple of %d (use the unfused kernels)", C, kFuCG);
+  static const int tt2 = getenv("LCASR_SUB_TT2") ? atoi(getenv("LCASR_SUB_TT2")) : 4;  // tuning knob: depthwise rows per CTA (4: 1.48 ms, 8: 1.63 ms at cfg3)
+  if (tt2 == 4) return launch_fused<4, 4>(spec, w0, b0, w1, b1, B, F, T, C, out, (cudaStream_t)stream);
+  return launch_fused<8, 2>(spec, w0, b0, w1, b1, B, F, T, C, out, (cudaStream_t)stream);
 }

@@ -56,6 +56,17 @@ def subsample_dwconv(x, w, b):
     return out
 
 
+def subsample_conv0_dw(spec, w0, b0, w1, b1):
+    """fused conv0 + SiLU + first depthwise level, bf16 output [B,T2,F2,C]."""
+    _cuda(spec, w0, b0, w1, b1)
+    B, F, T = spec.shape
+    C = w0.shape[0]
+    T1, F1 = (T - 1) // 2 + 1, (F - 1) // 2 + 1
+    out = torch.empty(B, (T1 - 1) // 2 + 1, (F1 - 1) // 2 + 1, C, dtype=torch.bfloat16, device=spec.device)
+    L.call("lcasr_subsample_conv0_dw", L.ptr(spec), L.ptr(w0), L.ptr(b0), L.ptr(w1), L.ptr(b1), B, F, T, C, L.ptr(out), _s())
+    return out
+
+
 def gemm(a, w, bias=None, act=L.ACT_NONE, resid=None, alpha=1.0, out_dtype=None, impl=L.GEMM_AUTO, out=None):
     """epilogue(a[M,K] @ w[N,K]^T)."""
     _cuda(a, w, bias, resid)

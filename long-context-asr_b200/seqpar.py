@@ -135,8 +135,11 @@ def forward_sequence_parallel(model, spec: torch.Tensor, comm, return_logits: bo
         s_tok, e_tok = blocks[r]
         f0, f1, drop = frame_slice(s_tok, e_tok)
         sl = spec[:, :, f0:f1].contiguous()
-        a = ops.subsample_conv0(sl, P["conv0_w"], P["conv0_b"], cdt)
-        a = ops.subsample_dwconv(a, P["dw1_w"], P["dw1_b"])
+        if cdt == torch.bfloat16 and Cc % 64 == 0:
+            a = ops.subsample_conv0_dw(sl, P["conv0_w"], P["conv0_b"], P["dw1_w"], P["dw1_b"])
+        else:
+            a = ops.subsample_conv0(sl, P["conv0_w"], P["conv0_b"], cdt)
+            a = ops.subsample_dwconv(a, P["dw1_w"], P["dw1_b"])
         B_, T2, F2, _ = a.shape
         a = ops.gemm(a.view(-1, Cc), P["pw1_w"], bias=P["pw1_b"], act=L.ACT_SILU, impl=gi).view(B_, T2, F2, Cc)
         a = ops.subsample_dwconv(a, P["dw2_w"], P["dw2_b"])

@@ -252,3 +252,22 @@ def test_ctc_loss_cluster_kernel_long_sequences(cuda_device, B, N, V, S):
     # |alpha+beta| grows ~ 8*N, so an fp32 recursion cannot resolve the exponent better than its ulp: the
     # bar is "no worse than the reference's own fp32 implementation" (x2 margin)
     assert gerr < 2.0 * gerr_torch32 + 1e-3
+
+
+@pytest.mark.parametrize("C,T,B", [(64, 264, 2), (256, 1027, 1), (512, 77, 1), (128, 8, 1)])
+def test_subsampling_fused_conv0_dw(cuda_device, C, T, B):
+    """conv0 + SiLU + first depthwise level in one kernel against torch fp32 and against the two
+    separate kernels (same bf16 rounding point: the conv0 activation)."""
+    from lcasr_b200 import ops
+    Fq = 80
+    spec = _rand(B, Fq, T, seed=40)
+    w0, b0 = _rand(C, 1, 3, 3, seed=41), 0.1 * _rand(C, seed=42)
+    w1, b1 = _rand(C, 1, 3, 3, seed=43) / 3, 0.1 * _rand(C, seed=44)
+    a0 = F.silu(F.conv2d(spec.transpose(1, 2).unsqueeze(1), w0, b0, stride=2, padding=1))
+    ref = F.conv2d(a0, w1, b1, stride=2, padding=1, groups=C).permute(0, 2, 3, 1)  # [B,T2,F2,C]
+    args = [t.to(cuda_device) for t in (spec, w0.reshape(C, 9).contiguous(), b0, w1.reshape(C, 9).contiguous(), b1)]
+    got = ops.subsample_conv0_dw(*args)
+    assert got.shape == ref.shape
+    assert (got.float().cpu() - ref).abs().max() < 2 ** -6 * max(1.0, ref.abs().max())
+    two = ops.subsample_dwconv(ops.subsample_conv0(args[0], args[1], args[2], torch.bfloat16), args[3], args[4])
+    assert (got.float() - two.float()).abs().max().item() <= 2 ** -7 * max(1.0, ref.abs().max().item())
