@@ -40,18 +40,19 @@ struct TgEpilogue {
 // Measured faster than the transposed variant below for 2-byte outputs (923 vs 654 TFLOP/s on the
 // 768->3072 GELU GEMM): the extra shared-memory round trip costs more than the partially filled lines.
 __device__ __forceinline__ void tg_store_chunk_direct(const uint32_t (&r)[32], int64_t row, int col0, int64_t M, int N,
-                                                      const TgEpilogue& ep, bf16* __restrict__ out) {
+                                                      const TgEpilogue& ep, const float* __restrict__ bias_chunk,
+                                                      bf16* __restrict__ out) {
   if (row >= M) return;
   const int ngroups = min(4, (N - col0) >> 3);  // 8 columns per group; N % 8 == 0
   float y[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(r[i]);
   if (ep.bias) {
-    const float4* bp = reinterpret_cast<const float4*>(ep.bias + col0);
+    const float4* bp = reinterpret_cast<const float4*>(bias_chunk);  // shared memory (broadcast reads)
 #pragma unroll
     for (int g = 0; g < 4; ++g)
       if (g < ngroups) {
-        const float4 b0 = __ldg(bp + 2 * g), b1 = __ldg(bp + 2 * g + 1);
+        const float4 b0 = bp[2 * g], b1 = bp[2 * g + 1];
         y[8 * g + 0] += b0.x; y[8 * g + 1] += b0.y; y[8 * g + 2] += b0.z; y[8 * g + 3] += b0.w;
         y[8 * g + 4] += b1.x; y[8 * g + 5] += b1.y; y[8 * g + 6] += b1.z; y[8 * g + 7] += b1.w;
       }
@@ -80,10 +81,22 @@ __device__ __forceinline__ void tg_store_chunk_direct(const uint32_t (&r)[32], i
 // 8 consecutive lanes cover one row's 128 contiguous bytes: every global load / store instruction of the
 // warp then covers 4 full lines.  All loads of the chunk (residual) are issued before any store
 // (`out` may alias `resid`: in-place residual update).
+// residual values of one chunk for this lane's 8 (row, 4-column) slots; issued one chunk AHEAD of their use so
+// the L2/HBM latency overlaps the previous chunk's work (4 epilogue warps cannot hide it by occupancy)
+__device__ __forceinline__ void tg_load_resid(float4 (&res)[8], int lane, int64_t row0, int col0, int64_t M, int N,
+                                              const float* resid) {
+  const int col = col0 + 4 * (lane & 7), rsub = lane >> 3;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int64_t row = row0 + it * 4 + rsub;
+    if (row < M && col < N) res[it] = *reinterpret_cast<const float4*>(resid + row * N + col);
+  }
+}
+
 template <typename TOut>
-__device__ __forceinline__ void tg_store_chunk(const uint32_t (&r)[32], float4* __restrict__ stage, int lane,
-                                               int64_t row0, int col0, int64_t M, int N, const TgEpilogue& ep,
-                                               TOut* out) {
+__device__ __forceinline__ void tg_store_chunk(const uint32_t (&r)[32], const float4 (&res)[8], float4* __restrict__ stage,
+                                               int lane, int64_t row0, int col0, int64_t M, int N, const TgEpilogue& ep,
+                                               const float* __restrict__ bias_chunk, TOut* out) {
   // 1) lane == row: write 8 float4 (columns 4q..4q+3) at swizzled slot q ^ (row & 7)
 #pragma unroll
   for (int q = 0; q < 8; ++q)
@@ -95,15 +108,7 @@ __device__ __forceinline__ void tg_store_chunk(const uint32_t (&r)[32], float4* 
   const int col = col0 + 4 * qq;
   const bool col_ok = col < N;
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ep.bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-  float4 res[8];
-  if (ep.resid) {
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int64_t row = row0 + it * 4 + rsub;
-      if (row < M && col_ok) res[it] = *reinterpret_cast<const float4*>(ep.resid + row * N + col);
-    }
-  }
+  if (ep.bias) bias4 = *reinterpret_cast<const float4*>(bias_chunk + 4 * qq);  // shared memory
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int rr = it * 4 + rsub;
@@ -151,6 +156,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t bars[2 * Cfg::STAGES + 4];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float4 epi_stage[4][32 * 8];  // per epilogue warp: 32 rows x 32 fp32, swizzled
+  __shared__ __align__(16) float bias_s[2][BN];          // the tile's bias slice, staged while the main loop still runs
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle atoms need 1024B alignment
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -226,18 +232,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int64_t m_idx = (tile / tiles_n) * TG_BM;
       const int n_idx = (int)(tile % tiles_n) * BN;
+      if (ep.bias) {  // stage this tile's bias slice now: its latency hides behind the wait for the accumulator
+        const int e = (warp & 3) * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < BN / 128; ++i) {
+          const int col = n_idx + i * 128 + e;
+          bias_s[acc][i * 128 + e] = col < N ? __ldg(ep.bias + col) : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      }
+      const int64_t row0 = m_idx + lane_base;
+      float4 res_nxt[8];
+      if constexpr (sizeof(TOut) == 4) {
+        if (ep.resid) tg_load_resid(res_nxt, lane, row0, n_idx, M, N, ep.resid);  // chunk 0, in flight during the wait
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int64_t row0 = m_idx + lane_base;
       const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + acc * BN;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         if (n_idx + c * 32 >= N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_addr + c * 32, r);
-        tmem_wait_ld();
-        if constexpr (sizeof(TOut) == 2) tg_store_chunk_direct(r, row0 + lane, n_idx + c * 32, M, N, ep, out);
-        else tg_store_chunk<TOut>(r, epi_stage[warp & 3], lane, row0, n_idx + c * 32, M, N, ep, out);
+        if constexpr (sizeof(TOut) == 2) {
+          tmem_wait_ld();
+          tg_store_chunk_direct(r, row0 + lane, n_idx + c * 32, M, N, ep, &bias_s[acc][c * 32], out);
+        } else {
+          float4 res_cur[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) res_cur[i] = res_nxt[i];
+          if (ep.resid && c + 1 < BN / 32 && n_idx + (c + 1) * 32 < N)
+            tg_load_resid(res_nxt, lane, row0, n_idx + (c + 1) * 32, M, N, ep.resid);  // in flight during this chunk
+          tmem_wait_ld();
+          tg_store_chunk<TOut>(r, res_cur, epi_stage[warp & 3], lane, row0, n_idx + c * 32, M, N, ep, &bias_s[acc][c * 32], out);
+        }
       }
       tc_fence_before();
       __syncwarp();
