@@ -114,6 +114,17 @@ int lcasr_attention(const void* q, const void* k, const void* v, int dtype, int 
 int lcasr_attention_cross(const void* q, const void* k, const void* v, int dtype, int B, int64_t Nq,
                           int64_t Nk, int H, int Dh, void* out, int impl, void* stream);
 
+/* Attention with a key-padding mask: kv_len[b] (device int32[B]) keys of batch entry b are valid, the rest
+ * are masked (the ragged-batch path of Attention.forward, attention.py:511,541,547 with the att_mask built at
+ * sconformer_xl.py:207-213).  Rows of padded queries are unspecified (the reference zeroes them). */
+int lcasr_attention_masked(const void* q, const void* k, const void* v, int dtype, int B, int64_t Nq,
+                           int64_t Nk, const int32_t* kv_len, int H, int Dh, void* out, int impl,
+                           void* stream);
+
+/* GLU that writes zeros for tokens n >= lengths[b] (convolution.py:107-110: glu then masked_fill). */
+int lcasr_glu_masked(const void* in, int dtype, int B, int64_t N, int d, const int32_t* lengths, void* out,
+                     void* stream);
+
 /* depthwise Conv1d(k, pad (k-1)/2, groups=d) + bias -> BatchRenorm1d eval affine
  * ((y-mean)/std*weight+bias, no eps; batchrenorm.py:86-91) -> SiLU  (convolution.py:112-121).
  * in/out channels-last [B,N,d]; w [d,ksize] fp32. */
@@ -228,6 +239,12 @@ int64_t lcasr_model_workspace_bytes(const lcasr_model* m, int B, int64_t T);
 int lcasr_model_forward(lcasr_model* m, const float* spec, int B, int64_t T, float* out,
                         int32_t* argmax, int return_logits, void* workspace, int64_t workspace_bytes,
                         void* stream);
+
+/* Same with a ragged batch: tok_len (device int32[B]) = valid tokens per recording after subsampling
+ * (lcasr_out_length of each item's frame count).  NULL = all equal (identical to lcasr_model_forward). */
+int lcasr_model_forward_lengths(lcasr_model* m, const float* spec, int B, int64_t T, const int32_t* tok_len,
+                                float* out, int32_t* argmax, int return_logits, void* workspace,
+                                int64_t workspace_bytes, void* stream);
 
 /* End-to-end convenience used by bench.py's e2e leg and by a non-PyTorch host: pinned-host
  * spectrogram in, token ids out (H2D copy, forward, greedy collapse, D2H copy of tokens, stream

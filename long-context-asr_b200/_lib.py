@@ -63,6 +63,8 @@ _SIGNATURES = {
     "lcasr_rope_split": [vp, i32, i32, i64, i32, i32, vp, vp, vp, vp, vp, i32, i64, vp],
     "lcasr_attention": [vp, vp, vp, i32, i32, i64, i32, i32, i32, i64, vp, i32, vp],
     "lcasr_attention_cross": [vp, vp, vp, i32, i32, i64, i64, i32, i32, vp, i32, vp],
+    "lcasr_attention_masked": [vp, vp, vp, i32, i32, i64, i64, vp, i32, i32, vp, i32, vp],
+    "lcasr_glu_masked": [vp, i32, i32, i64, i32, vp, vp, vp],
     "lcasr_dwconv_brn_silu": [vp, i32, i32, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp],
     "lcasr_softmax": [vp, i32, i64, i32, vp, i32, vp],
     "lcasr_log_softmax_argmax": [vp, i64, i32, vp, vp],
@@ -75,6 +77,7 @@ _SIGNATURES = {
     "lcasr_model_set_timing": [vp, i32],
     "lcasr_model_get_timing": [vp, vp, vp, i32],
     "lcasr_model_forward": [vp, vp, i32, i64, vp, vp, i32, vp, i64, vp],
+    "lcasr_model_forward_lengths": [vp, vp, i32, i64, vp, vp, vp, i32, vp, i64, vp],
     "lcasr_model_transcribe_host": [vp, vp, i32, i64, vp, vp, vp, vp, i64, vp],
 }
 _OTHER = {

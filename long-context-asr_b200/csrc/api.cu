@@ -23,10 +23,10 @@ int gemm_simt_launch(const void* A, const void* W, int ab_dtype, int64_t M, int 
                      const float* resid, float alpha, void* out, int out_dtype, cudaStream_t st);
 int gemm_tc_launch(const void* A, const void* W, int64_t M, int N, int K, const float* bias, int act, const float* resid,
                    float alpha, void* out, int out_dtype, cudaStream_t st);
-int attn_simt_launch(const void* q, const void* k, const void* v, int dtype, int B, int64_t N, int64_t Nk, int H, int Dh,
-                     int v_transposed, int64_t Npad, void* out, cudaStream_t st);
-int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, int H, int Dh,
-                   int v_transposed, int64_t Npad, void* out, cudaStream_t st);
+int attn_simt_launch(const void* q, const void* k, const void* v, int dtype, int B, int64_t N, int64_t Nk, const int32_t* kv_len,
+                     int H, int Dh, int v_transposed, int64_t Npad, void* out, cudaStream_t st);
+int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len, int H,
+                   int Dh, int v_transposed, int64_t Npad, void* out, cudaStream_t st);
 
 }  // namespace lcasr
 
@@ -62,8 +62,9 @@ extern "C" int lcasr_gemm(const void* A, const void* W, int ab_dtype, int64_t M,
   return gemm_simt_launch(A, W, ab_dtype, M, N, K, bias, act, resid, alpha, out, out_dtype, st);
 }
 
-static int attention_dispatch(const void* q, const void* k, const void* v, int dtype, int B, int64_t N, int64_t Nk, int H,
-                              int Dh, int v_transposed, int64_t Npad, void* out, int impl, void* stream) {
+static int attention_dispatch(const void* q, const void* k, const void* v, int dtype, int B, int64_t N, int64_t Nk,
+                              const int32_t* kv_len, int H, int Dh, int v_transposed, int64_t Npad, void* out, int impl,
+                              void* stream) {
   LCASR_CHECK_ARG(q && k && v && out, "attention: NULL operand");
   LCASR_CHECK_ARG(B > 0 && N > 0 && Nk > 0 && H > 0 && Dh > 0, "attention: bad shape");
   LCASR_CHECK_ARG(dtype == LCASR_F32 || dtype == LCASR_BF16, "attention: bad dtype %d", dtype);
@@ -72,18 +73,23 @@ static int attention_dispatch(const void* q, const void* k, const void* v, int d
   if (impl == LCASR_ATTN_AUTO) impl = dtype == LCASR_BF16 ? LCASR_ATTN_TCGEN05 : LCASR_ATTN_SIMT;
   if (impl == LCASR_ATTN_TCGEN05) {
     LCASR_CHECK_ARG(dtype == LCASR_BF16, "attention: the tcgen05 kernel takes bf16 operands");
-    return attn_tc_launch(q, k, v, B, N, Nk, H, Dh, v_transposed, Npad, out, st);
+    return attn_tc_launch(q, k, v, B, N, Nk, kv_len, H, Dh, v_transposed, Npad, out, st);
   }
   LCASR_CHECK_ARG(impl == LCASR_ATTN_SIMT, "attention: bad impl %d", impl);
-  return attn_simt_launch(q, k, v, dtype, B, N, Nk, H, Dh, v_transposed, Npad, out, st);
+  return attn_simt_launch(q, k, v, dtype, B, N, Nk, kv_len, H, Dh, v_transposed, Npad, out, st);
 }
 
 extern "C" int lcasr_attention(const void* q, const void* k, const void* v, int dtype, int B, int64_t N, int H, int Dh,
                                int v_transposed, int64_t Npad, void* out, int impl, void* stream) {
-  return attention_dispatch(q, k, v, dtype, B, N, N, H, Dh, v_transposed, Npad, out, impl, stream);
+  return attention_dispatch(q, k, v, dtype, B, N, N, nullptr, H, Dh, v_transposed, Npad, out, impl, stream);
 }
 
 extern "C" int lcasr_attention_cross(const void* q, const void* k, const void* v, int dtype, int B, int64_t Nq, int64_t Nk,
                                      int H, int Dh, void* out, int impl, void* stream) {
-  return attention_dispatch(q, k, v, dtype, B, Nq, Nk, H, Dh, 0, 0, out, impl, stream);
+  return attention_dispatch(q, k, v, dtype, B, Nq, Nk, nullptr, H, Dh, 0, 0, out, impl, stream);
+}
+
+extern "C" int lcasr_attention_masked(const void* q, const void* k, const void* v, int dtype, int B, int64_t Nq, int64_t Nk,
+                                      const int32_t* kv_len, int H, int Dh, void* out, int impl, void* stream) {
+  return attention_dispatch(q, k, v, dtype, B, Nq, Nk, kv_len, H, Dh, 0, 0, out, impl, stream);
 }

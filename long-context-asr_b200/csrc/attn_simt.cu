@@ -10,7 +10,8 @@ constexpr int SA_BQ = 64, SA_BK = 64, SA_THREADS = 256;
 
 template <typename T, int DH>
 __global__ void __launch_bounds__(SA_THREADS) attn_simt_kernel(const T* __restrict__ q, const T* __restrict__ k,
-                                                               const T* __restrict__ v, int64_t N, int64_t Nk, int H,
+                                                               const T* __restrict__ v, int64_t N, int64_t Nk,
+                                                               const int32_t* __restrict__ kv_len, int H,
                                                                int v_transposed, int64_t Npad, float scale,
                                                                T* __restrict__ out) {  // N query rows, Nk keys per batch entry
   extern __shared__ float smem[];
@@ -30,6 +31,7 @@ __global__ void __launch_bounds__(SA_THREADS) attn_simt_kernel(const T* __restri
   const int d = H * DH;
   const T* qb = q + (b * N) * d + h * DH;
   const T* kb = k + (b * Nk) * d + h * DH;
+  const int64_t Nkv = kv_len ? min((int64_t)kv_len[b], Nk) : Nk;  // valid keys (key-padding mask of ragged batches)
 
   for (int idx = tid; idx < SA_BQ * DH; idx += SA_THREADS) {
     int r = idx / DH, c = idx % DH;
@@ -46,13 +48,13 @@ __global__ void __launch_bounds__(SA_THREADS) attn_simt_kernel(const T* __restri
 #pragma unroll
     for (int j = 0; j < OC; ++j) o_acc[i][j] = 0.f;
 
-  for (int64_t k0 = 0; k0 < Nk; k0 += SA_BK) {
+  for (int64_t k0 = 0; k0 < Nkv; k0 += SA_BK) {
     __syncthreads();
     for (int idx = tid; idx < SA_BK * DH; idx += SA_THREADS) {
       int r = idx / DH, c = idx % DH;
       int64_t n = k0 + r;
       float kv = 0.f, vv = 0.f;
-      if (n < Nk) {
+      if (n < Nkv) {
         kv = to_f32<T>(kb[n * d + c]);
         vv = v_transposed ? to_f32<T>(v[((b * H + h) * DH + c) * Npad + n]) : to_f32<T>(v[(b * Nk + n) * d + h * DH + c]);
       }
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(SA_THREADS) attn_simt_kernel(const T* __restri
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         int64_t n = k0 + tx * 4 + j;
-        Ss[(ty * 4 + i) * (SA_BK + 1) + tx * 4 + j] = n < Nk ? s[i][j] : -INFINITY;
+        Ss[(ty * 4 + i) * (SA_BK + 1) + tx * 4 + j] = n < Nkv ? s[i][j] : -INFINITY;
       }
     __syncthreads();
     // online softmax: 4 threads per row, 16 columns each
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(SA_THREADS) attn_simt_kernel(const T* __restri
 }
 
 template <typename T, int DH>
-static int launch_attn_simt(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, int H, int vt, int64_t Npad,
+static int launch_attn_simt(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len, int H, int vt, int64_t Npad,
                             void* out, cudaStream_t st) {
   size_t smem = sizeof(float) * (2 * SA_BQ * (DH + 1) + SA_BK * DH + SA_BQ * (SA_BK + 1) + 3 * SA_BQ);
   static bool attr_set = false;
@@ -157,18 +159,18 @@ static int launch_attn_simt(const void* q, const void* k, const void* v, int B, 
   }
   dim3 grid((unsigned)ceil_div(N, SA_BQ), H, B);
   float scale = 1.0f / sqrtf((float)DH);
-  attn_simt_kernel<T, DH><<<grid, SA_THREADS, smem, st>>>((const T*)q, (const T*)k, (const T*)v, N, Nk, H, vt, Npad, scale,
+  attn_simt_kernel<T, DH><<<grid, SA_THREADS, smem, st>>>((const T*)q, (const T*)k, (const T*)v, N, Nk, kv_len, H, vt, Npad, scale,
                                                           (T*)out);
   LCASR_LAUNCH_CHECK();
   return 0;
 }
 
-int attn_simt_launch(const void* q, const void* k, const void* v, int dtype, int B, int64_t N, int64_t Nk, int H, int Dh,
+int attn_simt_launch(const void* q, const void* k, const void* v, int dtype, int B, int64_t N, int64_t Nk, const int32_t* kv_len, int H, int Dh,
                      int v_transposed, int64_t Npad, void* out, cudaStream_t st) {
 #define LCASR_SA(DHV)                                                                                     \
   case DHV:                                                                                               \
-    return dtype == LCASR_BF16 ? launch_attn_simt<bf16, DHV>(q, k, v, B, N, Nk, H, v_transposed, Npad, out, st) \
-                               : launch_attn_simt<float, DHV>(q, k, v, B, N, Nk, H, v_transposed, Npad, out, st);
+    return dtype == LCASR_BF16 ? launch_attn_simt<bf16, DHV>(q, k, v, B, N, Nk, kv_len, H, v_transposed, Npad, out, st) \
+                               : launch_attn_simt<float, DHV>(q, k, v, B, N, Nk, kv_len, H, v_transposed, Npad, out, st);
   switch (Dh) {
     LCASR_SA(32) LCASR_SA(64) LCASR_SA(128)
     default:

@@ -336,8 +336,10 @@ template <int DH> struct Fa2Cfg {
 template <int DH, int POLY>
 __global__ void __launch_bounds__(FA2_THREADS, 1)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, int64_t N, int64_t Nk, int H, float scale_log2,
-                bf16* __restrict__ out) {  // N = query rows per batch entry, Nk = keys per batch entry
+                const __grid_constant__ CUtensorMap tmV, int64_t N, int64_t Nk, const int32_t* __restrict__ kv_len, int H,
+                float scale_log2, bf16* __restrict__ out) {
+  // N = query rows per batch entry, Nk = keys per batch entry (row pitch of k/v); kv_len (may be NULL): the
+  // number of VALID keys of each batch entry — the key-padding mask of ragged batches (attention.py:511-547)
   using Cfg = Fa2Cfg<DH>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[1 + 2 * Cfg::STAGES + 9];
@@ -366,7 +368,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int h = blockIdx.y;
   const int64_t b = blockIdx.z;
   const int64_t q0 = (int64_t)blockIdx.x * (2 * FA_BQ);
-  const int n_tiles = (int)((Nk + FA_BK - 1) / FA_BK);
+  const int64_t Nkv = kv_len ? min((int64_t)kv_len[blockIdx.z], Nk) : Nk;  // valid keys of this batch entry
+  const int n_tiles = (int)((Nkv + FA_BK - 1) / FA_BK);
 
   if (warp == 8 && lane == 0) {
     prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
@@ -585,7 +588,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(s_free(t));
       }
-      const int64_t valid = Nk - (int64_t)j * FA_BK;
+      const int64_t valid = Nkv - (int64_t)j * FA_BK;
       if (valid < FA_BK) {
 #pragma unroll
         for (int i = 0; i < FA_BK; ++i)
@@ -708,8 +711,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 template <int DH, int POLY>
-static int launch_attn_tc2(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, int H, void* out,
-                           cudaStream_t st) {
+static int launch_attn_tc2(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len,
+                           int H, void* out, cudaStream_t st) {
   using Cfg = Fa2Cfg<DH>;
   const uint64_t d = (uint64_t)H * DH;
   const CUtensorMapSwizzle sw = DH >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -724,7 +727,7 @@ static int launch_attn_tc2(const void* q, const void* k, const void* v, int B, i
   }
   dim3 grid((unsigned)ceil_div(N, 2 * FA_BQ), (unsigned)H, (unsigned)B);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)DH);
-  attn_tc2_kernel<DH, POLY><<<grid, FA2_THREADS, Cfg::SMEM_TOTAL, st>>>(tmQ, tmK, tmV, N, Nk, H, scale_log2, (bf16*)out);
+  attn_tc2_kernel<DH, POLY><<<grid, FA2_THREADS, Cfg::SMEM_TOTAL, st>>>(tmQ, tmK, tmV, N, Nk, kv_len, H, scale_log2, (bf16*)out);
   LCASR_LAUNCH_CHECK();
   return 0;
 }
@@ -768,8 +771,9 @@ static int launch_attn_tc(const void* q, const void* k, const void* v, int B, in
   return 0;
 }
 
-int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, int H, int Dh,
-                   int v_transposed, int64_t Npad, void* out, cudaStream_t st) {
+int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len, int H,
+                   int Dh, int v_transposed, int64_t Npad, void* out, cudaStream_t st) {
+  LCASR_CHECK_ARG(!kv_len || !v_transposed, "attention(tcgen05): key lengths need the natural V layout");
   LCASR_CHECK_ARG(Nk == N || !v_transposed, "attention(tcgen05): Nq != Nk needs the natural V layout");
   LCASR_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0 && ((uintptr_t)v & 15) == 0 && ((uintptr_t)out & 15) == 0,
                   "attention(tcgen05): q, k, v, out must be 16-byte aligned");
@@ -782,14 +786,14 @@ int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N
 #define LCASR_FA(DHV)                                                                                             \
   case DHV:                                                                                                       \
     if (v_transposed) return launch_attn_tc<DHV, true>(q, k, v, B, N, H, Npad, out, st);                          \
-    if (force_v1 && Nk == N) return launch_attn_tc<DHV, false>(q, k, v, B, N, H, Npad, out, st);                  \
+    if (force_v1 && Nk == N && !kv_len) return launch_attn_tc<DHV, false>(q, k, v, B, N, H, Npad, out, st);                  \
     switch (poly) {                                                                                               \
-      case 0: return launch_attn_tc2<DHV, 0>(q, k, v, B, N, Nk, H, out, st);                                          \
-      case 1: return launch_attn_tc2<DHV, 1>(q, k, v, B, N, Nk, H, out, st);                                          \
-      case 2: return launch_attn_tc2<DHV, 2>(q, k, v, B, N, Nk, H, out, st);                                          \
-      case 8: return launch_attn_tc2<DHV, 8>(q, k, v, B, N, Nk, H, out, st);                                          \
-      case 9: return launch_attn_tc2<DHV, 9>(q, k, v, B, N, Nk, H, out, st);                                          \
-      default: return launch_attn_tc2<DHV, 4>(q, k, v, B, N, Nk, H, out, st);                                         \
+      case 0: return launch_attn_tc2<DHV, 0>(q, k, v, B, N, Nk, kv_len, H, out, st);                                          \
+      case 1: return launch_attn_tc2<DHV, 1>(q, k, v, B, N, Nk, kv_len, H, out, st);                                          \
+      case 2: return launch_attn_tc2<DHV, 2>(q, k, v, B, N, Nk, kv_len, H, out, st);                                          \
+      case 8: return launch_attn_tc2<DHV, 8>(q, k, v, B, N, Nk, kv_len, H, out, st);                                          \
+      case 9: return launch_attn_tc2<DHV, 9>(q, k, v, B, N, Nk, kv_len, H, out, st);                                          \
+      default: return launch_attn_tc2<DHV, 4>(q, k, v, B, N, Nk, kv_len, H, out, st);                                         \
     }
   switch (Dh) {
     LCASR_FA(32) LCASR_FA(64) LCASR_FA(128)

@@ -4,8 +4,11 @@
 namespace lcasr {
 
 // ---- GLU over channels (convolution.py:107): out[m,j] = in[m,j] * sigmoid(in[m,d+j]) ----------
+// `lengths` (may be NULL): valid tokens per batch entry of N tokens; rows at or beyond it are written as
+// zeros — the reference's `x.masked_fill(pad_mask, 0)` in front of the depthwise conv (convolution.py:109-110)
 template <typename T>
-__global__ void __launch_bounds__(256) glu_kernel(const T* __restrict__ in, int64_t M, int d, T* __restrict__ out) {
+__global__ void __launch_bounds__(256) glu_kernel(const T* __restrict__ in, int64_t M, int d, T* __restrict__ out,
+                                                  const int32_t* __restrict__ lengths, int64_t N) {
   const int vec_per_row = d / 8;
   const int64_t total = M * vec_per_row;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -15,8 +18,9 @@ __global__ void __launch_bounds__(256) glu_kernel(const T* __restrict__ in, int6
     float a[8], g[8], y[8];
     Vec8<T>::load(in + m * 2 * d + j, a);
     Vec8<T>::load(in + m * 2 * d + d + j, g);
+    const bool pad = lengths && (m % N) >= lengths[m / N];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = a[i] * sigmoid_for<T>(g[i]);
+    for (int i = 0; i < 8; ++i) y[i] = pad ? 0.f : a[i] * sigmoid_for<T>(g[i]);
     Vec8<T>::store(out + m * d + j, y);
   }
 }
@@ -116,17 +120,27 @@ static inline unsigned grid_for(int64_t total, int block) {
 
 using namespace lcasr;
 
-extern "C" int lcasr_glu(const void* in, int dtype, int64_t M, int d, void* out, void* stream) {
+static int glu_launch(const void* in, int dtype, int64_t M, int d, void* out, const int32_t* lengths, int64_t N, void* stream) {
   LCASR_CHECK_ARG(in && out && M >= 0 && d > 0 && d % 8 == 0, "glu: bad arguments (d=%d must be a multiple of 8)", d);
   if (M == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   int64_t total = M * (d / 8);
   if (dtype == LCASR_BF16)
-    glu_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)in, M, d, (bf16*)out);
+    glu_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)in, M, d, (bf16*)out, lengths, N);
   else
-    glu_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)in, M, d, (float*)out);
+    glu_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)in, M, d, (float*)out, lengths, N);
   LCASR_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int lcasr_glu(const void* in, int dtype, int64_t M, int d, void* out, void* stream) {
+  return glu_launch(in, dtype, M, d, out, nullptr, 1, stream);
+}
+
+extern "C" int lcasr_glu_masked(const void* in, int dtype, int B, int64_t N, int d, const int32_t* lengths, void* out,
+                                void* stream) {
+  LCASR_CHECK_ARG(B > 0 && N > 0, "glu_masked: bad shape");
+  return glu_launch(in, dtype, (int64_t)B * N, d, out, lengths, N, stream);
 }
 
 extern "C" int lcasr_rope_table(const float* inv_freq, float interp, int64_t pos_offset, int64_t N, int half,

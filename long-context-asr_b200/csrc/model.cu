@@ -134,8 +134,21 @@ extern "C" int64_t lcasr_model_workspace_bytes(const lcasr_model* m, int B, int6
   return (int64_t)make_plan(m->cfg, B, T).total;
 }
 
+extern "C" int lcasr_model_forward_lengths(lcasr_model* m, const float* spec, int B, int64_t T, const int32_t* tok_len,
+                                           float* out, int32_t* argmax, int return_logits, void* workspace,
+                                           int64_t workspace_bytes, void* stream);
+
 extern "C" int lcasr_model_forward(lcasr_model* m, const float* spec, int B, int64_t T, float* out, int32_t* argmax,
                                    int return_logits, void* workspace, int64_t workspace_bytes, void* stream) {
+  return lcasr_model_forward_lengths(m, spec, B, T, nullptr, out, argmax, return_logits, workspace, workspace_bytes, stream);
+}
+
+// tok_len (device int32[B], may be NULL): valid TOKENS per recording after subsampling (ragged batch,
+// sconformer_xl.py:204-213).  Keys beyond it are masked in attention (attention.py:511-547) and the conv
+// module's input is zeroed there (convolution.py:109-110); outputs of padded frames are unspecified.
+extern "C" int lcasr_model_forward_lengths(lcasr_model* m, const float* spec, int B, int64_t T, const int32_t* tok_len,
+                                           float* out, int32_t* argmax, int return_logits, void* workspace,
+                                           int64_t workspace_bytes, void* stream) {
   LCASR_CHECK_ARG(m && spec && out && workspace, "model_forward: NULL argument");
   LCASR_CHECK_ARG(B > 0 && T > 0, "model_forward: bad shape B=%d T=%lld", B, (long long)T);
   const lcasr_config& c = m->cfg;
@@ -228,12 +241,14 @@ extern "C" int lcasr_model_forward(lcasr_model* m, const float* spec, int B, int
     LCASR_TRY(gemm(a, L.qkv_w, M, 3 * d, d, nullptr, LCASR_ACT_NONE, nullptr, 0.f, wide, cd));
     OP(CAT_ROPE, lcasr_rope_split(wide, cd, B, N, H, Dh, c.use_rotary ? cos_t : nullptr, c.use_rotary ? sin_t : nullptr, q, k,
                                v, vt, p.Npad, stream));
-    OP(CAT_ATTN, lcasr_attention(q, k, v, cd, B, N, H, Dh, vt, p.Npad, a, ai, stream));
+    if (tok_len) OP(CAT_ATTN, lcasr_attention_masked(q, k, v, cd, B, N, N, tok_len, H, Dh, a, ai, stream));
+    else OP(CAT_ATTN, lcasr_attention(q, k, v, cd, B, N, H, Dh, vt, p.Npad, a, ai, stream));
     LCASR_TRY(gemm(a, L.out_w, M, d, d, nullptr, LCASR_ACT_NONE, x, 1.0f, x, LCASR_F32));
     // convolution module (convolution.py:103-124)
     LCASR_TRY(norm(L.conv_norm_w, L.conv_norm_b, nullptr, a));
     LCASR_TRY(gemm(a, L.pw1_w, M, 2 * d, d, L.pw1_b, LCASR_ACT_NONE, nullptr, 0.f, wide, cd));
-    OP(CAT_CONVMOD, lcasr_glu(wide, cd, M, d, q, stream));
+    if (tok_len) OP(CAT_CONVMOD, lcasr_glu_masked(wide, cd, B, N, d, tok_len, q, stream));
+    else OP(CAT_CONVMOD, lcasr_glu(wide, cd, M, d, q, stream));
     OP(CAT_CONVMOD, lcasr_dwconv_brn_silu(q, cd, B, N, d, c.conv_kernel_size, L.dw_w, L.dw_b, L.brn_mean, L.brn_std, L.brn_w,
                                     L.brn_b, k, cd, stream));
     LCASR_TRY(gemm(k, L.pw2_w, M, d, d, L.pw2_b, LCASR_ACT_NONE, x, 1.0f, x, LCASR_F32));

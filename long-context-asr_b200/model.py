@@ -409,8 +409,9 @@ class SCConformerXL(nn.Module):
     # ---- forward ------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, audio_signal, length=None, cached_kvs=None, cached_kv_lengths=None, return_logits=False):
-        """audio_signal [B, feat_in, T] fp32 CUDA; length [B] or None (=T).  Equal lengths only
-        (the path every BASELINE config exercises, sconformer_xl.py:204-205)."""
+        """audio_signal [B, feat_in, T] fp32 CUDA; length [B] frames per recording, or None (= T).
+        Ragged batches take the key-padding-mask path (sconformer_xl.py:204-215): rows of padded tokens
+        in `final_posteriors` are unspecified, exactly `length[b]` rows of recording b are meaningful."""
         if cached_kvs is not None or cached_kv_lengths is not None:
             raise NotImplementedError("cached_kvs is dead code in the reference (SURVEY §3.2) and not supported")
         if not audio_signal.is_cuda:
@@ -418,24 +419,35 @@ class SCConformerXL(nn.Module):
         if audio_signal.dim() != 3 or audio_signal.shape[1] != self.feat_in:
             raise ValueError(f"audio_signal must be [B, {self.feat_in}, T], got {tuple(audio_signal.shape)}")
         B, _, T = audio_signal.shape
+        device = audio_signal.device
+        N = int(L.lib.lcasr_out_length(T))
+        tok_len = None  # None = every recording fills the batch (sconformer_xl.py:204-205)
         if length is not None:
             lens = [int(v) for v in (length.tolist() if torch.is_tensor(length) else length)]
-            if any(v != T for v in lens):
-                raise NotImplementedError("ragged batches (length != T) are a 'next' row (SURVEY §8 f4); pad-free equal-length batches only")
-        device = audio_signal.device
+            if len(lens) != B or any(v < 1 or v > T for v in lens):
+                raise ValueError(f"length must hold {B} frame counts in [1, {T}], got {lens}")
+            toks = [int(L.lib.lcasr_out_length(v)) for v in lens]  # subsampling.py:557-567 per recording
+            if max(toks) != N:
+                # the reference sizes its rotary tables and masks by length.max() (:188,198); a batch whose
+                # longest recording is shorter than the padded tensor is a caller error there too (shape clash)
+                raise ValueError("the longest recording must span the padded batch (length.max() == T up to the 8x rounding)")
+            if min(toks) != max(toks):
+                tok_len = torch.tensor(toks, dtype=torch.int32, device=device)
+            length_out = torch.tensor(toks, dtype=torch.int32, device=device)
+        else:
+            length_out = torch.full((B,), N, dtype=torch.int32, device=device)
         x = audio_signal.to(torch.float32).contiguous()
         self._ensure_built(device)
-        N = int(L.lib.lcasr_out_length(T))
         V1 = self.decoder.num_classes
         out = torch.empty(B, N, V1, dtype=torch.float32, device=device)
         argmax = torch.empty(B, N, dtype=torch.int32, device=device)
         nbytes = int(L.lib.lcasr_model_workspace_bytes(self._handle, B, T))
         ws = self._ws(nbytes, device)
         with torch.cuda.device(device):
-            L.call("lcasr_model_forward", self._handle, L.ptr(x), B, T, L.ptr(out), L.ptr(argmax), int(return_logits),
-                   L.ptr(ws), ws.numel(), L.current_stream())
+            L.call("lcasr_model_forward_lengths", self._handle, L.ptr(x), B, T, L.ptr(tok_len), L.ptr(out), L.ptr(argmax),
+                   int(return_logits), L.ptr(ws), ws.numel(), L.current_stream())
         self.last_argmax = None if return_logits else argmax
-        return {"final_posteriors": out, "length": torch.full((B,), N, dtype=torch.int32, device=device)}
+        return {"final_posteriors": out, "length": length_out}
 
     @torch.no_grad()
     def transcribe_host(self, spec_host: torch.Tensor):

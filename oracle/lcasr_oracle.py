@@ -241,10 +241,19 @@ def rotate_half(x: Tensor) -> Tensor:  # rotary_emb.py:61-66
     return torch.cat((-x[..., h:], x[..., :h]), dim=-1)
 
 
-def attention_forward(sd, cfg: dict, p: str, a: Tensor, cos, sin, collect=None) -> Tensor:
-    """attention.py:483-487 (qkv split, qkv index fastest), :499-551; a = LN(x) [B,N,d]."""
+def attention_forward(sd, cfg: dict, p: str, a: Tensor, cos, sin, collect=None, pad_mask=None) -> Tensor:
+    """attention.py:483-487 (qkv split, qkv index fastest), :499-551; a = LN(x) [B,N,d].
+    pad_mask [B,N] bool (True = padded token) for ragged batches: input rows zeroed (:511), additive
+    -finfo.max mask on every (query, key) pair with a padded member (sconformer_xl.py:211-213), output rows
+    zeroed (:547)."""
     B, N, _ = a.shape
     H, Dh = cfg["n_heads"], cfg["head_dim"]
+    attn_mask = None
+    if pad_mask is not None:
+        a = a.masked_fill(pad_mask.unsqueeze(-1), 0)
+        valid = ~pad_mask
+        attn_mask = ~(valid[:, None, :, None] * valid[:, None, None, :])
+        attn_mask = attn_mask.to(a.dtype) * -torch.finfo(a.dtype).max
     qkv = (a @ sd[p + "attend.fn.qkv_proj.weight"].T).view(B, N, H, Dh, 3)
     q, k, v = qkv[..., 0], qkv[..., 1], qkv[..., 2]
     if cos is not None:
@@ -253,19 +262,25 @@ def attention_forward(sd, cfg: dict, p: str, a: Tensor, cos, sin, collect=None) 
         k = k * c + rotate_half(k) * s
     if collect is not None:
         collect[p + "q"], collect[p + "k"], collect[p + "v"] = q, k, v
-    o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2))  # attention.py:541
+    o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+                                       attn_mask=attn_mask)  # attention.py:541
     o = o.transpose(1, 2).reshape(B, N, H * Dh)
+    if pad_mask is not None:
+        o = o.masked_fill(pad_mask.unsqueeze(-1), 0)
     if collect is not None:
         collect[p + "attn_o"] = o
     return o @ sd[p + "attend.fn.out_proj.weight"].T
 
 
-def conv_module_forward(sd, cfg: dict, p: str, a: Tensor, collect=None) -> Tensor:
-    """convolution.py:103-124 with BatchRenorm eval (batchrenorm.py:86-91); a = LN(x) [B,N,d]."""
+def conv_module_forward(sd, cfg: dict, p: str, a: Tensor, collect=None, pad_mask=None) -> Tensor:
+    """convolution.py:103-124 with BatchRenorm eval (batchrenorm.py:86-91); a = LN(x) [B,N,d].
+    pad_mask [B,N] (True = padded): the GLU output is zeroed there before the depthwise conv (:109-110)."""
     d, ks = cfg["d_model"], cfg["conv_kernel_size"]
     y = a.transpose(1, 2)
     y = F.conv1d(y, sd[p + "conv.fn.pointwise_conv1.weight"], sd[p + "conv.fn.pointwise_conv1.bias"])
     y = F.glu(y, dim=1)  # first half * sigmoid(second half)
+    if pad_mask is not None:
+        y = y.float().masked_fill(pad_mask.unsqueeze(1), 0.0)
     if collect is not None:
         collect[p + "glu"] = y.transpose(1, 2)
     y = F.conv1d(y, sd[p + "conv.fn.depthwise_conv.weight"], sd[p + "conv.fn.depthwise_conv.bias"],
@@ -296,9 +311,11 @@ def decoder_logits(sd, cfg: dict, x: Tensor) -> Tensor:
 
 
 def encoder_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, return_logits: bool = False,
-                    collect: Optional[dict] = None) -> Tuple[Tensor, Tensor]:
-    """SCConformerXL.forward, equal-length path (sconformer_xl.py:162-252, 346-372).
-    x [B, feat_in, T] fp32 -> (final_posteriors [B,N,V+1], length int32[B])."""
+                    collect: Optional[dict] = None, lengths=None) -> Tuple[Tensor, Tensor]:
+    """SCConformerXL.forward (sconformer_xl.py:162-252, 346-372).
+    x [B, feat_in, T] fp32 -> (final_posteriors [B,N,V+1], length int32[B]).  `lengths` (frames per
+    recording, None = all T): a ragged batch takes the pad-mask path of :188,204-215 (the non-flash
+    branch, which is the one that runs on CPU)."""
     assert cfg["subsampling"] == "dw_striding" and not cfg["transformer"] and not cfg["sandwich_norm"]
     sd = {k: (v.float() if v.is_floating_point() else v) for k, v in sd.items()}
     B, _, T = x.shape
@@ -308,18 +325,24 @@ def encoder_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, return_logits: 
     assert N == calc_length(T)
     if collect is not None:
         collect["sub.out"] = h
+    tok_len = torch.full((B,), N, dtype=torch.int32)
+    pad_mask = None
+    if lengths is not None:
+        tok_len = torch.tensor([calc_length(int(v)) for v in lengths], dtype=torch.int32)
+        if int(tok_len.max()) != int(tok_len.min()):  # sconformer_xl.py:204
+            pad_mask = torch.arange(N)[None, :] >= tok_len[:, None]
     cos = sin = None
     if cfg["use_rotary"]:
-        cos, sin = rotary_tables(sd, N)
+        cos, sin = rotary_tables(sd, int(tok_len.max()))  # :198-200 (== N whenever one recording is unpadded)
     for l in range(L):
         p = f"layers.{l}."
         h = 0.5 * ffn_forward(sd, cfg, p + "ff1.fn.fn", _norm(h, sd, p + "ff1.fn.norm", cfg)) + h
         if collect is not None:
             collect[p + "after_ff1"] = h
-        h = attention_forward(sd, cfg, p, _norm(h, sd, p + "attend.norm", cfg), cos, sin, collect) + h
+        h = attention_forward(sd, cfg, p, _norm(h, sd, p + "attend.norm", cfg), cos, sin, collect, pad_mask) + h
         if collect is not None:
             collect[p + "after_attn"] = h
-        h = conv_module_forward(sd, cfg, p, _norm(h, sd, p + "conv.norm", cfg), collect) + h
+        h = conv_module_forward(sd, cfg, p, _norm(h, sd, p + "conv.norm", cfg), collect, pad_mask) + h
         if collect is not None:
             collect[p + "after_conv"] = h
         h = 0.5 * ffn_forward(sd, cfg, p + "ff2.fn.fn", _norm(h, sd, p + "ff2.fn.norm", cfg)) + h
@@ -335,8 +358,7 @@ def encoder_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, return_logits: 
         h = _norm(h, sd, "decoder.norm", cfg)  # sconformer_xl.py:246
     logits = decoder_logits(sd, cfg, h)  # :247 (norm applied a second time inside)
     out = logits if return_logits else F.log_softmax(logits, dim=-1)
-    length = torch.full((B,), N, dtype=torch.int32)
-    return out, length
+    return out, tok_len
 
 
 # --------------------------------------------------------------------------------------------

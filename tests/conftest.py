@@ -10,6 +10,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+RAGGED_CASES = ["tiny_lengths", "tiny_lengths_dh128"]  # batches with per-recording lengths (key-padding mask path)
 GOLDEN_CASES = ["tiny_dh32_ragged", "tiny_dh128", "tiny_rms_nosc", "tiny_norotary", "cfg1_6L256D8H", "cfg1_peaky"]
 
 
@@ -26,6 +27,7 @@ def load_golden(name):
     for k in ("batch", "frames", "weight_seed", "input_seed", "target_seed"):
         g[k] = int(g[k])
     g["peak"] = float(g["peak"])
+    g["frame_lengths"] = g["frame_lengths"].tolist() if "frame_lengths" in g else [g["frames"]] * g["batch"]
     return g
 
 

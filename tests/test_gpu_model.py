@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_CASES, load_golden
+from conftest import GOLDEN_CASES, RAGGED_CASES, load_golden
 from gpu_util import build_model, margin_mask, report
 from oracle import lcasr_oracle as O
 
@@ -80,8 +80,41 @@ def test_return_logits_and_repack_after_load_state_dict(cuda_device):
     lp2 = model(x)["final_posteriors"].cpu()
     ref2, _ = O.encoder_forward(sd2, cfg, x.cpu())
     assert (lp2 - ref2).abs().max().item() < 1e-4
-    with pytest.raises(NotImplementedError):
-        model(x, length=torch.tensor([g["frames"], g["frames"] - 8]))
+    with pytest.raises(ValueError):
+        model(x, length=torch.tensor([g["frames"] - 64, g["frames"] - 64]))  # longest recording must span the batch
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", RAGGED_CASES)
+def test_ragged_batch_matches_reference_golden(cuda_device, name, mode):
+    """forward(audio_signal, length) with unequal lengths: key-padding mask in attention, zeroed pads in
+    front of the depthwise conv (sconformer_xl.py:204-215, attention.py:511-547, convolution.py:109-110).
+    Valid rows only are compared (padded rows carry no meaning for any caller)."""
+    import lcasr_b200
+    g = load_golden(name)
+    model, cfg, sd = build_model(g, cuda_device, mode)
+    x = O.synth_input(g["batch"], g["frames"], cfg["feat_in"], seed=g["input_seed"]).to(cuda_device)
+    out = model(x, length=torch.tensor(g["frame_lengths"], device=cuda_device))
+    assert out["length"].dtype == torch.int32 and out["length"].cpu().tolist() == g["length"].tolist()
+    lp, ref = out["final_posteriors"].cpu(), torch.from_numpy(g["final_posteriors"])
+    scale = max(1.0, ref.abs().max().item() / 8)
+    tol = 1e-4 * scale if mode == "fp32" else 2e-2 * scale * 2.5
+    dec = lcasr_b200.GreedyCTCDecoder(None, blank_id=cfg["vocab_size"])
+    worst = 0.0
+    for b, n in enumerate(g["length"].tolist()):
+        worst = max(worst, (lp[b, :n] - ref[b, :n]).abs().max().item())
+        if mode == "fp32":
+            assert dec(out["final_posteriors"][b, :n]) == g["greedy"][b]
+        else:
+            safe = margin_mask(ref[b, :n], 4e-2 * scale)
+            assert bool((lp[b, :n].argmax(-1) == ref[b, :n].argmax(-1))[safe].all())
+    report(test="model_ragged_" + mode, case=name, max_abs=worst, ref_scale=ref.abs().max().item())
+    assert worst < tol, f"ragged batch ({mode}) off by {worst}"
+    V = cfg["vocab_size"]
+    tgt, tl = O.synth_targets(g["batch"], int(g["length"].min()), vocab=V, frac=0.3, seed=g["target_seed"])
+    loss = lcasr_b200.CTCLoss(blank=V, reduction="sum")(out["final_posteriors"].transpose(0, 1), tgt, out["length"], tl)
+    rel = abs(loss.item() - float(g["ctc_loss_sum"])) / abs(float(g["ctc_loss_sum"]))
+    assert rel < (1e-3 if mode == "fp32" else 5e-3)
 
 
 def test_transcribe_host_end_to_end(cuda_device):
