@@ -164,6 +164,108 @@ int lcasr_ctc_loss_bwd(const float* log_probs, int B, int64_t N, int V, const in
                        float* beta_ws, float* grad, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Training step (cfg 5): the operators behind loss.backward() of exp/train.py:249-262.  The
+ * reference gets these from torch.autograd over the modules of SURVEY §8 a3-a11; here each is
+ * a hand-written kernel.  Activations bf16 (the reference trains under bf16 autocast,
+ * exp/train.py:225), residual stream / its gradient / parameter gradients fp32.
+ * fp32 gradient outputs ACCUMULATE (+=): the caller zeroes them (or passes an existing .grad).
+ * ---------------------------------------------------------------------------------------- */
+
+enum { LCASR_EPI_SCALE = 0, LCASR_EPI_EXP2 = 1, LCASR_EPI_DS = 2, LCASR_EPI_GELU_BWD = 3, LCASR_EPI_SILU_BWD = 4 };
+
+/* General tcgen05 GEMM of the backward pass: for every batch entry (b1 < nb1, b2 < nb2)
+ *     acc[M,N] = sum_k A(m,k) * B(n,k)
+ * A is stored [M,K] row-major (a_mn=0, pitch lda) or [K,M] row-major (a_mn=1, "MN-major"); B is
+ * stored [N,K] (b_mn=0) or [K,N] (b_mn=1); batch entry (b1,b2) of a tensor starts s?1*b1 + s?2*b2
+ * elements after its base.  bf16 operands, fp32 accumulation.  Epilogue `epi`:
+ *   SCALE     out = alpha*acc
+ *   EXP2      out = exp2(alpha*acc - rowvec[row])                (attention backward: P from the saved lse)
+ *   DS        out = aux * (acc - rowvec[row]) * alpha            (attention backward: dS = P o (dP - D) * scale)
+ *   GELU_BWD  out = alpha*acc * gelu_tanh'(aux)                  (fused_dense.py:466 backward)
+ *   SILU_BWD  out = alpha*acc * silu'(aux)
+ * out_dtype BF16: stored; F32: out += alpha*acc with fp32 atomics (SCALE only), which is what split-K
+ * (ksplit > 1, or 0 = choose) and gradient accumulation need.  N, pitches and strides are multiples of 8.
+ * Replaces the cuBLAS calls autograd issues for nn.Linear / 1x1 Conv backward and the flash-attn
+ * backward (attention.py:532) of the reference. */
+typedef struct lcasr_gemm_ex_args {
+  const void* A; const void* B; void* out; const void* aux; const float* rowvec;
+  int64_t M; int32_t N, K;
+  int32_t a_mn, b_mn;
+  int64_t lda, ldb, ldo, ldaux;
+  int32_t nb1, nb2;
+  int64_t sa1, sa2, sb1, sb2, so1, so2, sx1, sx2, sr1, sr2;
+  float alpha; int32_t epi; int32_t out_dtype; int32_t ksplit;
+} lcasr_gemm_ex_args;
+int lcasr_gemm_ex(const lcasr_gemm_ex_args* args, void* stream);
+
+/* Attention forward that also returns lse [B,H,N] fp32 = log2-domain log-sum-exp of the scaled scores
+ * (bf16, natural-layout V, tcgen05 kernel). */
+int lcasr_attention_train(const void* q, const void* k, const void* v, int B, int64_t N, int H, int Dh,
+                          void* out, float* lse, void* stream);
+
+/* out(bf16) = scale * in(fp32), n % 8 == 0 */
+int lcasr_scale_cast(const float* in, int64_t n, float scale, void* out, void* stream);
+/* out = gelu_tanh(in) / silu(in), bf16 (the pre-activation is kept for the backward) */
+int lcasr_act_fwd(const void* in, int64_t n, int act, void* out, void* stream);
+/* out = dy * act'(pre), bf16 (pre = the saved pre-activation) */
+int lcasr_act_bwd(const void* pre, const void* dy, int64_t n, int act, void* out, void* stream);
+/* x(fp32) += a(bf16) */
+int lcasr_add_bf16(float* x, const void* a, int64_t n, void* stream);
+/* GLU backward: u [M,2d] (the GLU input), dg [M,d] -> du [M,2d] */
+int lcasr_glu_bwd(const void* u, const void* dg, int64_t M, int d, void* du, void* stream);
+/* rotary backward (rotation by -theta of dq, dk) + merge with dv into dqkv [B*N, 3*H*Dh] = [dq|dk|dv] */
+int lcasr_rope_bwd_merge(const void* dq, const void* dk, const void* dv, int B, int64_t N, int H, int Dh,
+                         const float* cos_t, const float* sin_t, void* dqkv, void* stream);
+/* out[b,h,n] = sum_dh a[b,n,h,dh]*b[b,n,h,dh] (the D term of the attention backward) */
+int lcasr_rowdot(const void* a, const void* b, int B, int64_t N, int H, int Dh, float* out, void* stream);
+/* dl = scale * p o (dp - sum(p o dp)), rows of V (self-conditioning softmax, sconformer_xl.py:242) */
+int lcasr_softmax_bwd(const void* p, const void* dp, int64_t M, int V, float scale, void* dl, void* stream);
+/* dl(bf16) = scale * (dlp - exp(lp) * sum(dlp)) (decoder.py:29 log_softmax; lp, dlp fp32) */
+int lcasr_log_softmax_bwd(const float* lp, const float* dlp, int64_t M, int V, float scale, void* dl,
+                          void* stream);
+/* out[d] += scale * column sums of in [M,d] (bias gradients) */
+int lcasr_colsum(const void* in, int dtype, int64_t M, int d, float scale, float* out, void* stream);
+/* LayerNorm / lcasr-RMSNorm backward from the saved input x (statistics recomputed): dx = or += (accumulate),
+ * dweight += , dbias += (LayerNorm only). dy in dy_dtype. */
+int lcasr_layernorm_bwd(const float* x, const void* dy, int dy_dtype, const float* weight, int64_t M, int d,
+                        float eps, int kind, int accumulate, float* dx, float* dweight, float* dbias,
+                        void* stream);
+/* depthwise Conv1d(k, pad (k-1)/2, groups=d)+bias, channels-last bf16 [B,N,d] (convolution.py:112), with
+ * optional per-channel sum / sum-of-squares of the output (BatchRenorm batch statistics); its data gradient
+ * and its weight / bias gradients (dw [d,k], db [d], +=). */
+int lcasr_dwconv1d_fwd(const void* in, int B, int64_t N, int d, int ksize, const float* w, const float* b,
+                       void* out, float* sum, float* sumsq, void* stream);
+int lcasr_dwconv1d_bwd_data(const void* dout, int B, int64_t N, int d, int ksize, const float* w, void* din,
+                            void* stream);
+int lcasr_dwconv1d_bwd_weight(const void* x, const void* dout, int B, int64_t N, int d, int ksize, float* dw,
+                              float* db, void* stream);
+/* BatchRenorm1d training forward (batchrenorm.py:52-84) from the channel sums over `count` tokens:
+ * writes the affine z = c*A + Bc, saves stats [5,d] = (mu, sigma, r, d, std) and updates running_mean /
+ * running_std in place with `momentum`.  rmax, dmax: the module's current clamps (:41-50). */
+int lcasr_brn_train_stats(const float* sum, const float* sumsq, int64_t count, int d, float* running_mean,
+                          float* running_std, float eps, float rmax, float dmax, float momentum,
+                          const float* weight, const float* bias, float* A, float* Bc, float* stats,
+                          void* stream);
+/* y = silu(c*A + Bc) */
+int lcasr_affine_silu(const void* c, int64_t M, int d, const float* A, const float* Bc, void* out, void* stream);
+/* dz = dy * silu'(c*A+Bc) (bf16) and S1 += sum dz, S2 += sum dz*xhat per channel */
+int lcasr_affine_silu_bwd(const void* c, const void* dy, int64_t M, int d, const float* A, const float* Bc,
+                          const float* stats, void* dz, float* S1, float* S2, void* stream);
+/* BatchRenorm backward, per channel: dweight +=, dbias +=, and coef [3,d] of dc = k1*dz + k2*c + k3 */
+int lcasr_brn_bwd_finalize(const float* S1, const float* S2, int64_t count, int d, const float* weight,
+                           const float* stats, float* dweight, float* dbias, float* coef, void* stream);
+/* out = coef[0]*a + coef[1]*b + coef[2] per channel, bf16 [M,d] */
+int lcasr_affine3(const void* a, const void* b, int64_t M, int d, const float* coef, void* out, void* stream);
+/* backward of the subsampling stencils (subsampling.py:277-312): depthwise 3x3 s2 data / weight gradients
+ * (channels-last bf16) and the conv0 (+SiLU) weight gradient (pre-activation recomputed from the spectrogram) */
+int lcasr_subsample_dwconv_bwd_data(const void* dout, const float* w, int B, int64_t Tin, int Fin, int C,
+                                    void* din, void* stream);
+int lcasr_subsample_dwconv_bwd_weight(const void* in, const void* dout, int B, int64_t Tin, int Fin, int C,
+                                      float* dw, float* db, void* stream);
+int lcasr_subsample_conv0_bwd(const float* spec, const float* w, const float* b, const void* ds1, int B, int F,
+                              int64_t T, int C, float* dw, float* db, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * The model: SCConformerXL.forward (lcasr/models/sconformer_xl.py:162-252), equal-length path
  * ---------------------------------------------------------------------------------------- */
 

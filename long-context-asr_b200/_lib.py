@@ -50,6 +50,18 @@ class LcasrWeights(C.Structure):
     _fields_ = [(n, vp) for n in MODEL_FIELDS] + [("layers_host", C.POINTER(LcasrLayerWeights))]
 
 
+EPI_SCALE, EPI_EXP2, EPI_DS, EPI_GELU_BWD, EPI_SILU_BWD = 0, 1, 2, 3, 4
+
+
+class LcasrGemmExArgs(C.Structure):
+    """mirror of lcasr_gemm_ex_args (include/lcasr_b200.h)"""
+    _fields_ = ([(n, vp) for n in ("A", "B", "out", "aux", "rowvec")] + [("M", i64), ("N", i32), ("K", i32),
+                ("a_mn", i32), ("b_mn", i32)] + [(n, i64) for n in ("lda", "ldb", "ldo", "ldaux")] +
+                [("nb1", i32), ("nb2", i32)] +
+                [(n, i64) for n in ("sa1", "sa2", "sb1", "sb2", "so1", "so2", "sx1", "sx2", "sr1", "sr2")] +
+                [("alpha", f32), ("epi", i32), ("out_dtype", i32), ("ksplit", i32)])
+
+
 # name -> argtypes; every function returns int status unless listed in _OTHER_RESTYPE
 _SIGNATURES = {
     "lcasr_layernorm": [vp, vp, vp, i64, i32, f32, i32, vp, vp, i32, vp],
@@ -72,6 +84,30 @@ _SIGNATURES = {
     "lcasr_greedy_collapse": [vp, i32, i64, vp, i32, vp, vp, vp],
     "lcasr_ctc_loss_fwd": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp],
     "lcasr_ctc_loss_bwd": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp],
+    "lcasr_gemm_ex": [C.POINTER(LcasrGemmExArgs), vp],
+    "lcasr_attention_train": [vp, vp, vp, i32, i64, i32, i32, vp, vp, vp],
+    "lcasr_scale_cast": [vp, i64, f32, vp, vp],
+    "lcasr_act_fwd": [vp, i64, i32, vp, vp],
+    "lcasr_act_bwd": [vp, vp, i64, i32, vp, vp],
+    "lcasr_add_bf16": [vp, vp, i64, vp],
+    "lcasr_glu_bwd": [vp, vp, i64, i32, vp, vp],
+    "lcasr_rope_bwd_merge": [vp, vp, vp, i32, i64, i32, i32, vp, vp, vp, vp],
+    "lcasr_rowdot": [vp, vp, i32, i64, i32, i32, vp, vp],
+    "lcasr_softmax_bwd": [vp, vp, i64, i32, f32, vp, vp],
+    "lcasr_log_softmax_bwd": [vp, vp, i64, i32, f32, vp, vp],
+    "lcasr_colsum": [vp, i32, i64, i32, f32, vp, vp],
+    "lcasr_layernorm_bwd": [vp, vp, i32, vp, i64, i32, f32, i32, i32, vp, vp, vp, vp],
+    "lcasr_dwconv1d_fwd": [vp, i32, i64, i32, i32, vp, vp, vp, vp, vp, vp],
+    "lcasr_dwconv1d_bwd_data": [vp, i32, i64, i32, i32, vp, vp, vp],
+    "lcasr_dwconv1d_bwd_weight": [vp, vp, i32, i64, i32, i32, vp, vp, vp],
+    "lcasr_brn_train_stats": [vp, vp, i64, i32, vp, vp, f32, f32, f32, f32, vp, vp, vp, vp, vp, vp],
+    "lcasr_affine_silu": [vp, i64, i32, vp, vp, vp, vp],
+    "lcasr_affine_silu_bwd": [vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp],
+    "lcasr_brn_bwd_finalize": [vp, vp, i64, i32, vp, vp, vp, vp, vp, vp],
+    "lcasr_affine3": [vp, vp, i64, i32, vp, vp, vp],
+    "lcasr_subsample_dwconv_bwd_data": [vp, vp, i32, i64, i32, i32, vp, vp],
+    "lcasr_subsample_dwconv_bwd_weight": [vp, vp, i32, i64, i32, i32, vp, vp, vp],
+    "lcasr_subsample_conv0_bwd": [vp, vp, vp, vp, i32, i32, i64, i32, vp, vp, vp],
     "lcasr_model_create": [C.POINTER(LcasrConfig), C.POINTER(LcasrWeights), C.POINTER(vp)],
     "lcasr_model_set_impl": [vp, i32, i32],
     "lcasr_model_set_timing": [vp, i32],

@@ -26,7 +26,7 @@ int gemm_tc_launch(const void* A, const void* W, int64_t M, int N, int K, const 
 int attn_simt_launch(const void* q, const void* k, const void* v, int dtype, int B, int64_t N, int64_t Nk, const int32_t* kv_len,
                      int H, int Dh, int v_transposed, int64_t Npad, void* out, cudaStream_t st);
 int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len, int H,
-                   int Dh, int v_transposed, int64_t Npad, void* out, cudaStream_t st);
+                   int Dh, int v_transposed, int64_t Npad, void* out, float* lse, cudaStream_t st);
 
 }  // namespace lcasr
 
@@ -73,7 +73,7 @@ static int attention_dispatch(const void* q, const void* k, const void* v, int d
   if (impl == LCASR_ATTN_AUTO) impl = dtype == LCASR_BF16 ? LCASR_ATTN_TCGEN05 : LCASR_ATTN_SIMT;
   if (impl == LCASR_ATTN_TCGEN05) {
     LCASR_CHECK_ARG(dtype == LCASR_BF16, "attention: the tcgen05 kernel takes bf16 operands");
-    return attn_tc_launch(q, k, v, B, N, Nk, kv_len, H, Dh, v_transposed, Npad, out, st);
+    return attn_tc_launch(q, k, v, B, N, Nk, kv_len, H, Dh, v_transposed, Npad, out, nullptr, st);
   }
   LCASR_CHECK_ARG(impl == LCASR_ATTN_SIMT, "attention: bad impl %d", impl);
   return attn_simt_launch(q, k, v, dtype, B, N, Nk, kv_len, H, Dh, v_transposed, Npad, out, st);
@@ -92,4 +92,12 @@ extern "C" int lcasr_attention_cross(const void* q, const void* k, const void* v
 extern "C" int lcasr_attention_masked(const void* q, const void* k, const void* v, int dtype, int B, int64_t Nq, int64_t Nk,
                                       const int32_t* kv_len, int H, int Dh, void* out, int impl, void* stream) {
   return attention_dispatch(q, k, v, dtype, B, Nq, Nk, kv_len, H, Dh, 0, 0, out, impl, stream);
+}
+
+// training forward: bf16 tcgen05 attention that also returns the per-row log-sum-exp the backward needs
+extern "C" int lcasr_attention_train(const void* q, const void* k, const void* v, int B, int64_t N, int H, int Dh, void* out,
+                                     float* lse, void* stream) {
+  LCASR_CHECK_ARG(q && k && v && out && lse, "attention_train: NULL operand");
+  LCASR_CHECK_ARG(B > 0 && N > 0 && H > 0 && Dh > 0, "attention_train: bad shape");
+  return attn_tc_launch(q, k, v, B, N, N, nullptr, H, Dh, 0, 0, out, lse, (cudaStream_t)stream);
 }

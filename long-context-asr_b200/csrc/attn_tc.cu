@@ -337,7 +337,9 @@ template <int DH, int POLY>
 __global__ void __launch_bounds__(FA2_THREADS, 1)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, int64_t N, int64_t Nk, const int32_t* __restrict__ kv_len, int H,
-                float scale_log2, bf16* __restrict__ out) {
+                float scale_log2, bf16* __restrict__ out, float* __restrict__ lse) {
+  // lse (may be NULL; training): [B,H,N] fp32, log2-domain log-sum-exp of the SCALED scores of every query row
+  // (lse2 = max*scale*log2e + log2(sum)), so that the backward recomputes P = exp2(s*scale*log2e - lse2)
   // N = query rows per batch entry, Nk = keys per batch entry (row pitch of k/v); kv_len (may be NULL): the
   // number of VALID keys of each batch entry — the key-padding mask of ragged batches (attention.py:511-547)
   using Cfg = Fa2Cfg<DH>;
@@ -686,6 +688,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float inv_l = 1.0f / l_run;
     const int64_t n = q0 + t * FA_BQ + row;
     bf16* orow = out + ((b * N + n) * H + h) * DH;
+    if (lse && n < N) lse[(b * H + h) * N + n] = m_run + log2f(l_run);
 #pragma unroll
     for (int c = 0; c < DH / 32; ++c) {
       uint32_t o[32];
@@ -712,7 +715,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 template <int DH, int POLY>
 static int launch_attn_tc2(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len,
-                           int H, void* out, cudaStream_t st) {
+                           int H, void* out, float* lse, cudaStream_t st) {
   using Cfg = Fa2Cfg<DH>;
   const uint64_t d = (uint64_t)H * DH;
   const CUtensorMapSwizzle sw = DH >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -727,7 +730,7 @@ static int launch_attn_tc2(const void* q, const void* k, const void* v, int B, i
   }
   dim3 grid((unsigned)ceil_div(N, 2 * FA_BQ), (unsigned)H, (unsigned)B);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)DH);
-  attn_tc2_kernel<DH, POLY><<<grid, FA2_THREADS, Cfg::SMEM_TOTAL, st>>>(tmQ, tmK, tmV, N, Nk, kv_len, H, scale_log2, (bf16*)out);
+  attn_tc2_kernel<DH, POLY><<<grid, FA2_THREADS, Cfg::SMEM_TOTAL, st>>>(tmQ, tmK, tmV, N, Nk, kv_len, H, scale_log2, (bf16*)out, lse);
   LCASR_LAUNCH_CHECK();
   return 0;
 }
@@ -772,7 +775,8 @@ static int launch_attn_tc(const void* q, const void* k, const void* v, int B, in
 }
 
 int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len, int H,
-                   int Dh, int v_transposed, int64_t Npad, void* out, cudaStream_t st) {
+                   int Dh, int v_transposed, int64_t Npad, void* out, float* lse, cudaStream_t st) {
+  LCASR_CHECK_ARG(!lse || !v_transposed, "attention(tcgen05): the log-sum-exp output needs the natural V layout");
   LCASR_CHECK_ARG(!kv_len || !v_transposed, "attention(tcgen05): key lengths need the natural V layout");
   LCASR_CHECK_ARG(Nk == N || !v_transposed, "attention(tcgen05): Nq != Nk needs the natural V layout");
   LCASR_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0 && ((uintptr_t)v & 15) == 0 && ((uintptr_t)out & 15) == 0,
@@ -786,14 +790,14 @@ int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N
 #define LCASR_FA(DHV)                                                                                             \
   case DHV:                                                                                                       \
     if (v_transposed) return launch_attn_tc<DHV, true>(q, k, v, B, N, H, Npad, out, st);                          \
-    if (force_v1 && Nk == N && !kv_len) return launch_attn_tc<DHV, false>(q, k, v, B, N, H, Npad, out, st);                  \
+    if (force_v1 && Nk == N && !kv_len && !lse) return launch_attn_tc<DHV, false>(q, k, v, B, N, H, Npad, out, st);                  \
     switch (poly) {                                                                                               \
-      case 0: return launch_attn_tc2<DHV, 0>(q, k, v, B, N, Nk, kv_len, H, out, st);                                          \
-      case 1: return launch_attn_tc2<DHV, 1>(q, k, v, B, N, Nk, kv_len, H, out, st);                                          \
-      case 2: return launch_attn_tc2<DHV, 2>(q, k, v, B, N, Nk, kv_len, H, out, st);                                          \
-      case 8: return launch_attn_tc2<DHV, 8>(q, k, v, B, N, Nk, kv_len, H, out, st);                                          \
-      case 9: return launch_attn_tc2<DHV, 9>(q, k, v, B, N, Nk, kv_len, H, out, st);                                          \
-      default: return launch_attn_tc2<DHV, 4>(q, k, v, B, N, Nk, kv_len, H, out, st);                                         \
+      case 0: return launch_attn_tc2<DHV, 0>(q, k, v, B, N, Nk, kv_len, H, out, lse, st);                                          \
+      case 1: return launch_attn_tc2<DHV, 1>(q, k, v, B, N, Nk, kv_len, H, out, lse, st);                                          \
+      case 2: return launch_attn_tc2<DHV, 2>(q, k, v, B, N, Nk, kv_len, H, out, lse, st);                                          \
+      case 8: return launch_attn_tc2<DHV, 8>(q, k, v, B, N, Nk, kv_len, H, out, lse, st);                                          \
+      case 9: return launch_attn_tc2<DHV, 9>(q, k, v, B, N, Nk, kv_len, H, out, lse, st);                                          \
+      default: return launch_attn_tc2<DHV, 4>(q, k, v, B, N, Nk, kv_len, H, out, lse, st);                                         \
     }
   switch (Dh) {
     LCASR_FA(32) LCASR_FA(64) LCASR_FA(128)

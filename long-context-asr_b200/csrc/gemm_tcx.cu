@@ -1,0 +1,396 @@
+// tcgen05 GEMM for the TRAINING path: the same persistent warp-specialised pipeline as gemm_tc.cu
+// (TMA producer warp, single-thread tcgen05.mma issuer, 4 epilogue warps, double-buffered TMEM
+// accumulator), generalised in the three ways the backward pass needs:
+//
+//   * either operand may be MN-major: the stored matrix is [K, M] (resp. [K, N]) row-major.  This is what
+//     data-gradient (dX = dY . W, W stored [out,in] = [K,N]) and weight-gradient (dW = dY^T . X, both
+//     operands stored token-major = [K,M] / [K,N]) GEMMs look like; the UMMA descriptors read such tiles
+//     directly (a_major / b_major bits of the instruction descriptor), so no transposed copies exist.
+//   * up to two batch dimensions with independent strides per tensor (4-D tensor maps): the five GEMMs of
+//     the attention backward run over (head, recording) pairs in one launch, straight on the
+//     [B,N,H,Dh] layout.
+//   * split-K with fp32 atomic accumulation (weight gradients have K = all tokens of the batch and few
+//     output tiles) and the backward epilogues: P = exp2(s*a - lse), dS = P o (dP - D) * a,
+//     dH = dY o gelu'(h), plain scale.
+//
+// Tensor-bound: algorithmic FLOPs = 2*M*N*K per batch entry.
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace lcasr {
+
+using namespace ptx;
+
+constexpr int TX_BM = 128, TX_BK = 64, TX_THREADS = 192;
+
+template <int BN> struct TxCfg {
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int A_BYTES = TX_BM * TX_BK * 2;
+  static constexpr int B_BYTES = BN * TX_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+};
+
+struct TxParams {
+  int64_t M;
+  int N, K;
+  int nb1, nb2;                 // batch = b2 * nb1 + b1
+  int ksplit, kper;             // K blocks per split
+  int64_t ldo, so1, so2;        // output row pitch / batch strides (elements)
+  const bf16* aux;              // bf16, indexed like the output (own pitch / strides)
+  int64_t ldx, sx1, sx2;
+  const float* rowvec;          // fp32 per output row: rowvec[b2*sr2 + b1*sr1 + row]
+  int64_t sr1, sr2;
+  float alpha;
+  int epi;
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// kind::f16 instruction descriptor with both majorness bits ([15] a_major, [16] b_major; 1 = MN-major)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// MN-major operand tile in shared memory: [64 K rows][64 MN elements = 128 swizzled bytes] per 64-element
+// MN sub-tile, sub-tiles 8192 B apart (LBO); 8 K rows = 1024 B (SBO); one K=16 step = 2048 B.
+__device__ __forceinline__ uint64_t make_smem_desc_mnmajor(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((8192u >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)kLayoutSW128 << 61;
+  return d;
+}
+
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float u = k0 * (x + k1 * x * x * x);
+  const float t = tanh_approx(u);
+  const float du = k0 * (1.0f + 3.0f * k1 * x * x);
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
+}
+__device__ __forceinline__ float silu_grad(float x) {
+  const float s = sigmoid_fast(x);
+  return s * (1.0f + x * (1.0f - s));
+}
+
+// one 32-column chunk of one accumulator row (lane == row)
+template <typename TOut>
+__device__ __forceinline__ void tx_store_chunk(const uint32_t (&r)[32], int64_t row, int col0, const TxParams& p, int b1,
+                                               int b2, TOut* __restrict__ out) {
+  if (row >= p.M) return;
+  const int ngroups = min(4, (p.N - col0) >> 3);  // N % 8 == 0
+  float y[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(r[i]);
+  const float a = p.alpha;
+  if (p.epi == LCASR_EPI_SCALE) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) y[i] *= a;
+  } else if (p.epi == LCASR_EPI_EXP2) {
+    const float rv = p.rowvec[b2 * p.sr2 + b1 * p.sr1 + row];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) y[i] = ex2_approx(fmaf(y[i], a, -rv));
+  } else {
+    const bf16* xp = p.aux + b2 * p.sx2 + b1 * p.sx1 + row * p.ldx + col0;
+    float rv = 0.f;
+    if (p.epi == LCASR_EPI_DS) rv = p.rowvec[b2 * p.sr2 + b1 * p.sr1 + row];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < ngroups) {
+        float x[8];
+        Vec8<bf16>::load(xp + 8 * g, x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float& v = y[8 * g + i];
+          if (p.epi == LCASR_EPI_DS) v = x[i] * (v - rv) * a;
+          else if (p.epi == LCASR_EPI_GELU_BWD) v = a * v * gelu_tanh_grad(x[i]);
+          else v = a * v * silu_grad(x[i]);  // LCASR_EPI_SILU_BWD
+        }
+      }
+  }
+  TOut* op = out + b2 * p.so2 + b1 * p.so1 + row * p.ldo + col0;
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    if (g < ngroups) {
+      if constexpr (sizeof(TOut) == 2) {
+        Vec8<bf16>::store(op + 8 * g, *reinterpret_cast<const float(*)[8]>(&y[8 * g]));
+      } else {  // fp32 outputs ACCUMULATE (split-K partials, gradient accumulation into an existing buffer)
+        atomicAdd(reinterpret_cast<float4*>(op + 8 * g), make_float4(y[8 * g], y[8 * g + 1], y[8 * g + 2], y[8 * g + 3]));
+        atomicAdd(reinterpret_cast<float4*>(op + 8 * g + 4),
+                  make_float4(y[8 * g + 4], y[8 * g + 5], y[8 * g + 6], y[8 * g + 7]));
+      }
+    }
+}
+
+struct TxTile {
+  int m_idx, n_idx, b1, b2, kb0, kb1;
+};
+
+template <int BN>
+__device__ __forceinline__ TxTile tx_decode(int64_t tile, const TxParams& p, int tiles_n, int64_t tiles_m, int num_k) {
+  TxTile t;
+  const int ks = (int)(tile % p.ksplit);
+  tile /= p.ksplit;
+  t.n_idx = (int)(tile % tiles_n) * BN;
+  tile /= tiles_n;
+  t.m_idx = (int)(tile % tiles_m) * TX_BM;
+  tile /= tiles_m;
+  t.b1 = (int)(tile % p.nb1);
+  t.b2 = (int)(tile / p.nb1);
+  t.kb0 = ks * p.kper;
+  t.kb1 = min(num_k, t.kb0 + p.kper);
+  return t;
+}
+
+template <int BN, int A_MN, int B_MN, typename TOut>
+__global__ void __launch_bounds__(TX_THREADS, 1)
+gemm_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TxParams p, TOut* out) {
+  using Cfg = TxCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * Cfg::STAGES + 4];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = (p.K + TX_BK - 1) / TX_BK;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int64_t tiles_m = (p.M + TX_BM - 1) / TX_BM;
+  const int64_t total_tiles = tiles_m * tiles_n * p.ksplit * p.nb1 * p.nb2;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer ----------------
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TxTile t = tx_decode<BN>(tile, p, tiles_n, tiles_m, num_k);
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+          if constexpr (A_MN) {
+#pragma unroll
+            for (int i = 0; i < TX_BM / 64; ++i)
+              tma_load_4d(sa + i * 8192, &tmA, full_bar(stage), t.m_idx + i * 64, kb * TX_BK, t.b1, t.b2);
+          } else {
+            tma_load_4d(sa, &tmA, full_bar(stage), kb * TX_BK, t.m_idx, t.b1, t.b2);
+          }
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_4d(sb + i * 8192, &tmB, full_bar(stage), t.n_idx + i * 64, kb * TX_BK, t.b1, t.b2);
+          } else {
+            tma_load_4d(sb, &tmB, full_bar(stage), kb * TX_BK, t.n_idx, t.b1, t.b2);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc = make_idesc_bf16_mn(TX_BM, BN, A_MN, B_MN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TxTile t = tx_decode<BN>(tile, p, tiles_n, tiles_m, num_k);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+          const uint64_t adesc = A_MN ? make_smem_desc_mnmajor(sa) : make_smem_desc_kmajor(sa, 1024, kLayoutSW128);
+          const uint64_t bdesc = B_MN ? make_smem_desc_mnmajor(sb) : make_smem_desc_kmajor(sb, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < TX_BK / 16; ++k)  // K-major: +32 B per K=16 step; MN-major: +16 rows * 128 B
+            umma_f16_ss(d_tmem, adesc + (A_MN ? 128 : 2) * k, bdesc + (B_MN ? 128 : 2) * k, idesc,
+                        (kb != t.kb0 || k != 0) ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {  // ---------------- epilogue warps 2..5 ----------------
+    const int lane_base = (warp & 3) * 32;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TxTile t = tx_decode<BN>(tile, p, tiles_n, tiles_m, num_k);
+      const int64_t row = (int64_t)t.m_idx + lane_base + lane;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (t.n_idx + c * 32 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_addr + c * 32, r);
+        tmem_wait_ld();
+        tx_store_chunk<TOut>(r, row, t.n_idx + c * 32, p, t.b1, t.b2, out);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+
+typedef CUresult (*PFN_tmapEncodeTiledX)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiledX get_encode_fn_x() {
+  static PFN_tmapEncodeTiledX fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiledX)ptr;
+  }
+  return fn;
+}
+
+// 4-D bf16 tensor map over a stored row-major matrix [rows, cols] (pitch elements) with two batch dims.
+static int make_tmap_4d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, int64_t pitch, int nb1, int64_t s1,
+                        int nb2, int64_t s2, uint32_t box_rows, uint32_t box_cols) {
+  PFN_tmapEncodeTiledX fn = get_encode_fn_x();
+  if (!fn) return set_error(LCASR_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  // strides of size-1 dims are never used for addressing but must still be valid (multiple of 16 B, > 0)
+  const uint64_t st1 = nb1 > 1 ? (uint64_t)s1 * 2 : (uint64_t)pitch * 2;
+  const uint64_t st2 = nb2 > 1 ? (uint64_t)s2 * 2 : (uint64_t)pitch * 2;
+  cuuint64_t dims[4] = {cols, rows, (cuuint64_t)nb1, (cuuint64_t)nb2};
+  cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, st1, st2};
+  cuuint32_t box[4] = {box_cols, box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(LCASR_E_CUDA,
+                     "cuTensorMapEncodeTiled(4d) failed (%d): base=%p rows=%llu cols=%llu pitch=%lld nb=%d,%d s=%lld,%lld box=%ux%u",
+                     (int)r, base, (unsigned long long)rows, (unsigned long long)cols, (long long)pitch, nb1, nb2,
+                     (long long)s1, (long long)s2, box_rows, box_cols);
+  return 0;
+}
+
+template <int BN, int A_MN, int B_MN, typename TOut>
+static int launch_tcx(const lcasr_gemm_ex_args& g, const TxParams& p, cudaStream_t st) {
+  using Cfg = TxCfg<BN>;
+  CUtensorMap tmA, tmB;
+  // stored matrices: K-major operand = [M or N rows, K cols]; MN-major operand = [K rows, M or N cols]
+  if (A_MN) LCASR_TRY(make_tmap_4d(&tmA, g.A, (uint64_t)g.K, (uint64_t)g.M, g.lda, g.nb1, g.sa1, g.nb2, g.sa2, TX_BK, 64));
+  else LCASR_TRY(make_tmap_4d(&tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, g.lda, g.nb1, g.sa1, g.nb2, g.sa2, TX_BM, TX_BK));
+  if (B_MN) LCASR_TRY(make_tmap_4d(&tmB, g.B, (uint64_t)g.K, (uint64_t)g.N, g.ldb, g.nb1, g.sb1, g.nb2, g.sb2, TX_BK, 64));
+  else LCASR_TRY(make_tmap_4d(&tmB, g.B, (uint64_t)g.N, (uint64_t)g.K, g.ldb, g.nb1, g.sb1, g.nb2, g.sb2, BN, TX_BK));
+  static bool attr_set = false;
+  if (!attr_set) {
+    LCASR_CUDA(cudaFuncSetAttribute(gemm_tcx_kernel<BN, A_MN, B_MN, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int64_t tiles = ceil_div(g.M, TX_BM) * ceil_div(g.N, BN) * p.ksplit * g.nb1 * g.nb2;
+  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+  gemm_tcx_kernel<BN, A_MN, B_MN, TOut><<<grid, TX_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p, (TOut*)g.out);
+  LCASR_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN, typename TOut>
+static int dispatch_major(const lcasr_gemm_ex_args& g, const TxParams& p, cudaStream_t st) {
+  if (g.a_mn) return g.b_mn ? launch_tcx<BN, 1, 1, TOut>(g, p, st) : launch_tcx<BN, 1, 0, TOut>(g, p, st);
+  return g.b_mn ? launch_tcx<BN, 0, 1, TOut>(g, p, st) : launch_tcx<BN, 0, 0, TOut>(g, p, st);
+}
+
+}  // namespace lcasr
+
+using namespace lcasr;
+
+extern "C" int lcasr_gemm_ex(const lcasr_gemm_ex_args* gp, void* stream) {
+  LCASR_CHECK_ARG(gp, "gemm_ex: NULL args");
+  const lcasr_gemm_ex_args& g = *gp;
+  LCASR_CHECK_ARG(g.A && g.B && g.out, "gemm_ex: NULL operand");
+  LCASR_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0 && g.nb1 > 0 && g.nb2 > 0, "gemm_ex: bad shape");
+  LCASR_CHECK_ARG(g.M < ((int64_t)1 << 31), "gemm_ex: M too large");
+  LCASR_CHECK_ARG(g.N % 8 == 0, "gemm_ex: N=%d must be a multiple of 8", g.N);
+  LCASR_CHECK_ARG(g.lda % 8 == 0 && g.ldb % 8 == 0 && g.sa1 % 8 == 0 && g.sa2 % 8 == 0 && g.sb1 % 8 == 0 && g.sb2 % 8 == 0,
+                  "gemm_ex: operand pitches / batch strides must be multiples of 8 elements (TMA: 16 bytes)");
+  LCASR_CHECK_ARG(((uintptr_t)g.A & 15) == 0 && ((uintptr_t)g.B & 15) == 0 && ((uintptr_t)g.out & 15) == 0 &&
+                      ((uintptr_t)g.aux & 15) == 0,
+                  "gemm_ex: A, B, out, aux must be 16-byte aligned");
+  LCASR_CHECK_ARG(g.out_dtype == LCASR_BF16 || g.out_dtype == LCASR_F32, "gemm_ex: bad out dtype");
+  LCASR_CHECK_ARG(g.ldo % (g.out_dtype == LCASR_BF16 ? 8 : 4) == 0 && g.so1 % 8 == 0 && g.so2 % 8 == 0,
+                  "gemm_ex: output pitch / strides must keep 16-byte alignment");
+  LCASR_CHECK_ARG(g.epi >= LCASR_EPI_SCALE && g.epi <= LCASR_EPI_SILU_BWD, "gemm_ex: bad epilogue %d", g.epi);
+  const bool needs_aux = g.epi == LCASR_EPI_DS || g.epi == LCASR_EPI_GELU_BWD || g.epi == LCASR_EPI_SILU_BWD;
+  const bool needs_rv = g.epi == LCASR_EPI_EXP2 || g.epi == LCASR_EPI_DS;
+  LCASR_CHECK_ARG(!needs_aux || (g.aux && g.ldaux % 8 == 0 && g.sx1 % 8 == 0 && g.sx2 % 8 == 0), "gemm_ex: epilogue %d needs aux", g.epi);
+  LCASR_CHECK_ARG(!needs_rv || g.rowvec, "gemm_ex: epilogue %d needs rowvec", g.epi);
+  LCASR_CHECK_ARG(g.out_dtype == LCASR_F32 || g.ksplit <= 1, "gemm_ex: split-K needs an fp32 (accumulating) output");
+  LCASR_CHECK_ARG(g.out_dtype == LCASR_BF16 || g.epi == LCASR_EPI_SCALE, "gemm_ex: fp32 outputs accumulate alpha*acc only");
+  const int num_k = (int)ceil_div(g.K, TX_BK);
+  const bool wide = (g.N % 256 == 0) || g.N > 512;
+  const int BN = wide ? 256 : 128;
+  int ksplit = g.ksplit;
+  if (ksplit <= 0) {  // auto: fill the machine ~2x when the output has few tiles (weight gradients)
+    ksplit = 1;
+    if (g.out_dtype == LCASR_F32) {
+      const int64_t tiles = ceil_div(g.M, TX_BM) * ceil_div(g.N, BN) * g.nb1 * g.nb2;
+      if (tiles < 2 * kNumSMs) ksplit = (int)ceil_div(2 * kNumSMs, tiles);
+      if (ksplit > num_k / 4) ksplit = num_k / 4 > 0 ? num_k / 4 : 1;  // >= 4 K blocks (256 deep) per split
+    }
+  }
+  if (ksplit > num_k) ksplit = num_k;
+  const int kper = (int)ceil_div(num_k, ksplit);
+  ksplit = (int)ceil_div(num_k, kper);  // no empty splits
+  TxParams p;
+  p.M = g.M; p.N = g.N; p.K = g.K; p.nb1 = g.nb1; p.nb2 = g.nb2; p.ksplit = ksplit; p.kper = kper;
+  p.ldo = g.ldo; p.so1 = g.so1; p.so2 = g.so2;
+  p.aux = (const bf16*)g.aux; p.ldx = g.ldaux; p.sx1 = g.sx1; p.sx2 = g.sx2;
+  p.rowvec = g.rowvec; p.sr1 = g.sr1; p.sr2 = g.sr2;
+  p.alpha = g.alpha; p.epi = g.epi;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g.out_dtype == LCASR_BF16)
+    return wide ? dispatch_major<256, bf16>(g, p, st) : dispatch_major<128, bf16>(g, p, st);
+  return wide ? dispatch_major<256, float>(g, p, st) : dispatch_major<128, float>(g, p, st);
+}

@@ -1,0 +1,257 @@
+"""Tensor-level wrappers over the TRAINING entry points of the C ABI (include/lcasr_b200.h, "Training step").
+
+PyTorch owns memory and the stream; every arithmetic operation of the backward pass is one of the
+hand-written kernels in csrc/{gemm_tcx,train,subsample_bwd}.cu.  bf16 activations, fp32 gradients of
+parameters and of the residual stream.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from .ops import _cuda, _s
+
+BF = torch.bfloat16
+
+
+def gemm_ex(A, B, out, M, N, K, *, a_mn=False, b_mn=False, lda, ldb, ldo, nb=(1, 1), sa=(0, 0), sb=(0, 0), so=(0, 0),
+            aux=None, ldaux=0, sx=(0, 0), rowvec=None, sr=(0, 0), alpha=1.0, epi=L.EPI_SCALE, ksplit=0):
+    """acc[M,N] = sum_k A(m,k) B(n,k) per batch entry; see lcasr_gemm_ex in the header for the layouts."""
+    args = L.LcasrGemmExArgs(
+        A=L.ptr(A), B=L.ptr(B), out=L.ptr(out), aux=L.ptr(aux), rowvec=L.ptr(rowvec), M=M, N=N, K=K, a_mn=int(a_mn),
+        b_mn=int(b_mn), lda=lda, ldb=ldb, ldo=ldo, ldaux=ldaux, nb1=nb[0], nb2=nb[1], sa1=sa[0], sa2=sa[1], sb1=sb[0],
+        sb2=sb[1], so1=so[0], so2=so[1], sx1=sx[0], sx2=sx[1], sr1=sr[0], sr2=sr[1], alpha=float(alpha), epi=epi,
+        out_dtype=L.dtype_code(out.dtype), ksplit=ksplit)
+    L.call("lcasr_gemm_ex", C.byref(args), _s())
+    return out
+
+
+def dgrad(dy, w, out=None, aux=None, epi=L.EPI_SCALE, alpha=1.0):
+    """dx[M,in] = alpha * dy[M,out] @ w[out,in]  (bf16 out, or fp32 `out` that is accumulated into)."""
+    _cuda(dy, w, aux)
+    M, No = dy.shape
+    Ni = w.shape[1]
+    assert w.shape[0] == No
+    if out is None:
+        out = torch.empty(M, Ni, dtype=BF, device=dy.device)
+    return gemm_ex(dy, w, out, M, Ni, No, b_mn=True, lda=No, ldb=Ni, ldo=Ni, aux=aux, ldaux=Ni, epi=epi, alpha=alpha)
+
+
+def wgrad(dy, x, dw, alpha=1.0):
+    """dw[out,in] (fp32) += alpha * dy[M,out]^T @ x[M,in]; split-K over the tokens."""
+    _cuda(dy, x, dw)
+    M, No = dy.shape
+    Ni = x.shape[1]
+    assert x.shape[0] == M and tuple(dw.shape) == (No, Ni) and dw.dtype == torch.float32
+    return gemm_ex(dy, x, dw, No, Ni, M, a_mn=True, b_mn=True, lda=No, ldb=Ni, ldo=Ni, alpha=alpha)
+
+
+def attention_train(q, k, v):
+    """q,k,v bf16 [B,N,H,Dh] -> (out [B,N,H*Dh] bf16, lse2 [B,H,N] fp32 in the log2 domain)."""
+    _cuda(q, k, v)
+    B, N, H, Dh = q.shape
+    out = torch.empty(B, N, H * Dh, dtype=BF, device=q.device)
+    lse = torch.empty(B, H, N, dtype=torch.float32, device=q.device)
+    L.call("lcasr_attention_train", L.ptr(q), L.ptr(k), L.ptr(v), B, N, H, Dh, L.ptr(out), L.ptr(lse), _s())
+    return out, lse
+
+
+def attention_bwd(q, k, v, o, do, lse, chunk_b: int = 0):
+    """Backward of softmax(q k^T / sqrt(Dh)) v from the saved output and log-sum-exp.
+    q,k,v,o,do bf16 [B,N,H,Dh]; returns dq, dk, dv (same layout).  P and dS are materialised per group of
+    recordings ([b,H,N,N] bf16 each, sized to stay L2-resident) and every product is one batched tcgen05 GEMM."""
+    _cuda(q, k, v, o, do, lse)
+    B, N, H, Dh = q.shape
+    d = H * Dh
+    dev = q.device
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    Dvec = torch.empty(B, H, N, dtype=torch.float32, device=dev)
+    L.call("lcasr_rowdot", L.ptr(do), L.ptr(o), B, N, H, Dh, L.ptr(Dvec), _s())
+    if chunk_b <= 0:  # P + dS of one chunk ~ 96 MB
+        chunk_b = max(1, min(B, (48 << 20) // (H * N * N * 2)))
+    Np = (N + 7) // 8 * 8  # row pitch of the score matrices
+    P = torch.empty(chunk_b, H, N, Np, dtype=BF, device=dev)
+    dS = torch.empty_like(P)
+    scale = 1.0 / (Dh ** 0.5)
+    sNN = N * Np
+    for b0 in range(0, B, chunk_b):
+        nb = min(chunk_b, B - b0)
+        qs, ks, vs, dos = q[b0:], k[b0:], v[b0:], do[b0:]
+        bat = dict(nb=(H, nb))
+        x4 = (Dh, N * d)  # (head, recording) strides of a [B,N,H,Dh] tensor
+        s4 = (sNN, H * sNN)
+        r4 = (N, H * N)
+        # P = exp2(scale*log2e * q k^T - lse2)
+        gemm_ex(qs, ks, P, N, N, Dh, lda=d, ldb=d, ldo=Np, sa=x4, sb=x4, so=s4, rowvec=lse[b0:], sr=r4,
+                alpha=scale * 1.4426950408889634, epi=L.EPI_EXP2, **bat)
+        # dS = P o (do v^T - D) * scale
+        gemm_ex(dos, vs, dS, N, N, Dh, lda=d, ldb=d, ldo=Np, sa=x4, sb=x4, so=s4, aux=P, ldaux=Np, sx=s4,
+                rowvec=Dvec[b0:], sr=r4, alpha=scale, epi=L.EPI_DS, **bat)
+        # dq = dS k       (B operand k stored [keys, Dh] = [K, N]: MN-major)
+        gemm_ex(dS, ks, dq[b0:], N, Dh, N, b_mn=True, lda=Np, ldb=d, ldo=d, sa=s4, sb=x4, so=x4, **bat)
+        # dk = dS^T q     (A stored [q, keys] = [K, M]: MN-major)
+        gemm_ex(dS, qs, dk[b0:], N, Dh, N, a_mn=True, b_mn=True, lda=Np, ldb=d, ldo=d, sa=s4, sb=x4, so=x4, **bat)
+        # dv = P^T do
+        gemm_ex(P, dos, dv[b0:], N, Dh, N, a_mn=True, b_mn=True, lda=Np, ldb=d, ldo=d, sa=s4, sb=x4, so=x4, **bat)
+    return dq, dk, dv
+
+
+def scale_cast(x, scale=1.0):
+    _cuda(x)
+    out = torch.empty(x.shape, dtype=BF, device=x.device)
+    L.call("lcasr_scale_cast", L.ptr(x), x.numel(), float(scale), L.ptr(out), _s())
+    return out
+
+
+def act_fwd(x, act):
+    _cuda(x)
+    out = torch.empty_like(x)
+    L.call("lcasr_act_fwd", L.ptr(x), x.numel(), act, L.ptr(out), _s())
+    return out
+
+
+def act_bwd(pre, dy, act):
+    _cuda(pre, dy)
+    out = torch.empty_like(pre)
+    L.call("lcasr_act_bwd", L.ptr(pre), L.ptr(dy), pre.numel(), act, L.ptr(out), _s())
+    return out
+
+
+def add_bf16_(x, a):
+    _cuda(x, a)
+    assert x.dtype == torch.float32 and a.dtype == BF and x.numel() == a.numel()
+    L.call("lcasr_add_bf16", L.ptr(x), L.ptr(a), x.numel(), _s())
+    return x
+
+
+def glu_bwd(u, dg):
+    _cuda(u, dg)
+    M, d = dg.shape
+    du = torch.empty_like(u)
+    L.call("lcasr_glu_bwd", L.ptr(u), L.ptr(dg), M, d, L.ptr(du), _s())
+    return du
+
+
+def rope_bwd_merge(dq, dk, dv, cos=None, sin=None):
+    _cuda(dq, dk, dv, cos, sin)
+    B, N, H, Dh = dq.shape
+    out = torch.empty(B * N, 3 * H * Dh, dtype=BF, device=dq.device)
+    L.call("lcasr_rope_bwd_merge", L.ptr(dq), L.ptr(dk), L.ptr(dv), B, N, H, Dh, L.ptr(cos), L.ptr(sin), L.ptr(out), _s())
+    return out
+
+
+def softmax_bwd(p, dp, scale=1.0, out=None):
+    _cuda(p, dp)
+    M, V = p.shape
+    out = torch.empty_like(p) if out is None else out
+    L.call("lcasr_softmax_bwd", L.ptr(p), L.ptr(dp), M, V, float(scale), L.ptr(out), _s())
+    return out
+
+
+def log_softmax_bwd(lp, dlp, scale=1.0):
+    _cuda(lp, dlp)
+    M, V = lp.shape
+    out = torch.empty(M, V, dtype=BF, device=lp.device)
+    L.call("lcasr_log_softmax_bwd", L.ptr(lp), L.ptr(dlp), M, V, float(scale), L.ptr(out), _s())
+    return out
+
+
+def colsum_(out, x, scale=1.0):
+    """out[d] (fp32) += scale * x.sum(0)"""
+    _cuda(out, x)
+    M, d = x.shape
+    L.call("lcasr_colsum", L.ptr(x), L.dtype_code(x.dtype), M, d, float(scale), L.ptr(out), _s())
+    return out
+
+
+def layernorm_bwd(x, dy, weight, dx, dweight, dbias=None, eps=1e-5, kind="layer_norm", accumulate=True):
+    _cuda(x, dy, weight, dx, dweight, dbias)
+    M, d = x.shape
+    L.call("lcasr_layernorm_bwd", L.ptr(x), L.ptr(dy), L.dtype_code(dy.dtype), L.ptr(weight), M, d, float(eps),
+           L.NORM_RMSNORM if kind == "rms_norm" else L.NORM_LAYERNORM, int(accumulate), L.ptr(dx), L.ptr(dweight),
+           L.ptr(dbias), _s())
+    return dx
+
+
+def dwconv1d_fwd(x, w, b, stats=False):
+    _cuda(x, w, b)
+    B, N, d = x.shape
+    out = torch.empty_like(x)
+    s = torch.zeros(2, d, dtype=torch.float32, device=x.device) if stats else None
+    L.call("lcasr_dwconv1d_fwd", L.ptr(x), B, N, d, w.shape[-1], L.ptr(w), L.ptr(b), L.ptr(out),
+           L.ptr(s[0]) if stats else None, L.ptr(s[1]) if stats else None, _s())
+    return out, s
+
+
+def dwconv1d_bwd_data(dout, w):
+    _cuda(dout, w)
+    B, N, d = dout.shape
+    din = torch.empty_like(dout)
+    L.call("lcasr_dwconv1d_bwd_data", L.ptr(dout), B, N, d, w.shape[-1], L.ptr(w), L.ptr(din), _s())
+    return din
+
+
+def dwconv1d_bwd_weight_(x, dout, dw, db):
+    _cuda(x, dout, dw, db)
+    B, N, d = x.shape
+    L.call("lcasr_dwconv1d_bwd_weight", L.ptr(x), L.ptr(dout), B, N, d, dw.shape[-1], L.ptr(dw), L.ptr(db), _s())
+
+
+def brn_train_stats(sums, count, running_mean, running_std, eps, rmax, dmax, momentum, weight, bias):
+    """returns (A, Bc, stats[5,d]); updates running_mean / running_std in place."""
+    d = weight.numel()
+    dev = weight.device
+    A = torch.empty(d, dtype=torch.float32, device=dev)
+    Bc = torch.empty_like(A)
+    stats = torch.empty(5, d, dtype=torch.float32, device=dev)
+    L.call("lcasr_brn_train_stats", L.ptr(sums[0]), L.ptr(sums[1]), int(count), d, L.ptr(running_mean), L.ptr(running_std),
+           float(eps), float(rmax), float(dmax), float(momentum), L.ptr(weight), L.ptr(bias), L.ptr(A), L.ptr(Bc),
+           L.ptr(stats), _s())
+    return A, Bc, stats
+
+
+def affine_silu(c, A, Bc):
+    _cuda(c, A, Bc)
+    out = torch.empty_like(c)
+    L.call("lcasr_affine_silu", L.ptr(c), c.numel() // c.shape[-1], c.shape[-1], L.ptr(A), L.ptr(Bc), L.ptr(out), _s())
+    return out
+
+
+def brn_silu_bwd(c, dy, A, Bc, stats, weight, dweight, dbias):
+    """backward of y = silu(BatchRenorm_train(c)): returns dc (bf16); dweight, dbias (fp32) accumulate."""
+    _cuda(c, dy, A, Bc, stats, weight, dweight, dbias)
+    d = c.shape[-1]
+    M = c.numel() // d
+    dz = torch.empty_like(c)
+    S = torch.zeros(2, d, dtype=torch.float32, device=c.device)
+    L.call("lcasr_affine_silu_bwd", L.ptr(c), L.ptr(dy), M, d, L.ptr(A), L.ptr(Bc), L.ptr(stats), L.ptr(dz), L.ptr(S[0]),
+           L.ptr(S[1]), _s())
+    coef = torch.empty(3, d, dtype=torch.float32, device=c.device)
+    L.call("lcasr_brn_bwd_finalize", L.ptr(S[0]), L.ptr(S[1]), M, d, L.ptr(weight), L.ptr(stats), L.ptr(dweight),
+           L.ptr(dbias), L.ptr(coef), _s())
+    dc = torch.empty_like(c)
+    L.call("lcasr_affine3", L.ptr(dz), L.ptr(c), M, d, L.ptr(coef), L.ptr(dc), _s())
+    return dc
+
+
+def subsample_dwconv_bwd_data(dout, w, Tin, Fin):
+    _cuda(dout, w)
+    B, C_ = dout.shape[0], dout.shape[-1]
+    din = torch.empty(B, Tin, Fin, C_, dtype=BF, device=dout.device)
+    L.call("lcasr_subsample_dwconv_bwd_data", L.ptr(dout), L.ptr(w), B, Tin, Fin, C_, L.ptr(din), _s())
+    return din
+
+
+def subsample_dwconv_bwd_weight_(x, dout, dw, db):
+    _cuda(x, dout, dw, db)
+    B, Tin, Fin, C_ = x.shape
+    L.call("lcasr_subsample_dwconv_bwd_weight", L.ptr(x), L.ptr(dout), B, Tin, Fin, C_, L.ptr(dw), L.ptr(db), _s())
+
+
+def subsample_conv0_bwd_(spec, w, b, ds1, dw, db):
+    _cuda(spec, w, b, ds1, dw, db)
+    B, F, T = spec.shape
+    L.call("lcasr_subsample_conv0_bwd", L.ptr(spec), L.ptr(w), L.ptr(b), L.ptr(ds1), B, F, T, w.shape[0], L.ptr(dw),
+           L.ptr(db), _s())
