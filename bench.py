@@ -33,6 +33,8 @@ WORKLOADS = {
     "cfg2": ("cfg2_9L768D6H", 16384, 16),
     "cfg3": ("cfg3_6L768D24H", 131072, 1),
     "cfg4": ("cfg4_3L2048D16H", 360000, 1),
+    # training step: forward (train mode) + CTC loss + backward (+ gradient all-reduce when N > 1), batch 8 per GPU
+    "cfg5": ("cfg5_6L768D6H", 16384, 8),
 }
 CATS = ["subsample", "norm", "gemm", "attention", "rope", "convmod", "softmax"]
 
@@ -143,6 +145,161 @@ def cpu_reference_run(cfg, B, T, steps, warmup, budget_s):
     return B * T / 100.0 / per_step, per_step, len(times), cores, did_warm
 
 
+def flops_train_step(cfg, T, N):
+    """forward + backward: every GEMM-shaped forward FLOP costs 2 more in the backward (data + weight gradient;
+    attention: dQ, dK, dV, dP and the recomputed P = 2.5x the forward)."""
+    d, L = cfg["d_model"], cfg["n_layers"]
+    fwd = flops_forward(cfg, T, N)
+    attn = L * 4 * N * N * d
+    return fwd + 2 * (fwd - attn) + 2.5 * attn
+
+
+def cpu_reference_train(cfg, B, T, budget_s):
+    """The reference's training step on the host cores through the oracle port: train-mode forward, CTC loss,
+    autograd backward (fp32).  A bounded sample: `Bs` recordings of the batch."""
+    import torch
+    from oracle import lcasr_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.synth_state_dict(cfg, seed=12345)
+    Bs = 1
+    x = O.synth_input(Bs, T, cfg["feat_in"], seed=1234)
+    N = O.calc_length(T)
+    tgt, tl = O.synth_targets(Bs, N, vocab=cfg["vocab_size"], frac=0.3, seed=99)
+    t0 = time.perf_counter()
+    O.training_step(sd, cfg, x, tgt, tl)
+    per = time.perf_counter() - t0
+    return Bs * T / 100.0 / per, per, Bs, cores
+
+
+def train_bench(args, cfg, mkey, T, B, rank, world, local):
+    """cfg 5: the training step through the drop-in classes exactly as exp/train.py:236-262 drives them."""
+    import torch
+    import lcasr_b200
+    from lcasr_b200 import _lib as L
+    from oracle import lcasr_oracle as O
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    N = O.calc_length(T)
+    V = cfg["vocab_size"]
+    sd = O.synth_state_dict(cfg, seed=12345)
+    model = lcasr_b200.SCConformerXL(**cfg, compute_dtype="bf16")
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).train()
+    from lcasr_b200.training import TrainEngine
+    model._train_engine = TrainEngine(model)
+    if world > 1:
+        model._train_engine.dp_group = dist.group.WORLD  # gradients all-reduced (averaged) inside backward
+    ctc = lcasr_b200.CTCLoss(blank=V, reduction="sum")
+    x_host = O.synth_input(B, T, cfg["feat_in"], seed=1234 + rank).pin_memory()
+    tgt_host, tl_host = O.synth_targets(B, N, vocab=V, frac=0.3, seed=99 + rank)
+    tgt_host, tl_host = tgt_host.pin_memory(), tl_host.pin_memory()
+    x, tgt, tl = x_host.to(dev), tgt_host.to(dev), tl_host.to(dev)
+
+    def step(xd, tg, tln):
+        out = model(audio_signal=xd, length=None)
+        loss = ctc(out["final_posteriors"].transpose(0, 1), tg, out["length"], tln).sum()
+        for p in model.parameters():
+            p.grad = None
+        loss.backward()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step(x, tgt, tl)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    L.lib.lcasr_reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(x, tgt, tl)
+    e1.record()
+    barrier()
+    launches = int(L.lib.lcasr_launch_count())
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    audio_s = B * T / 100.0
+    value = world * audio_s / (ms_per_step / 1e3)
+
+    # end to end: pinned host batch -> H2D -> step -> loss value back on the host
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss = step(x_host.to(dev, non_blocking=True), tgt_host.to(dev, non_blocking=True), tl_host.to(dev, non_blocking=True))
+        loss_host = loss.item()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+
+    # kernel breakdown: two instrumented steps (CUDA events around every C-ABI call on the launch stream)
+    L.TIMING = {}
+    for _ in range(2):
+        step(x, tgt, tl)
+    torch.cuda.synchronize()
+    rec, L.TIMING = L.timing_summary(L.TIMING), None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    peaks = load_peaks()
+    kern = {k: {"ms_per_step": v[0] / 2, "launches_per_step": v[1] / 2} for k, v in sorted(rec.items(), key=lambda kv: -kv[1][0])}
+    gemm_ms = (rec.get("lcasr_gemm", (0, 0))[0] + rec.get("lcasr_gemm_ex", (0, 0))[0]) / 2
+    attn_fwd_ms = rec.get("lcasr_attention_train", (0, 0))[0] / 2
+    total_flops = flops_train_step(cfg, T, N) * B
+    attn_fwd_flops = cfg["n_layers"] * 4.0 * N * N * cfg["d_model"] * B
+    gemm_flops = total_flops - attn_fwd_flops  # everything GEMM-shaped except the fused forward attention kernel
+    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {"kernel": "tcgen05 GEMMs of the step (gemm_tc_kernel forward, gemm_tcx_kernel backward incl. the 5 batched "
+                          "attention-backward products)", "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sust"],
+                "unit": "TFLOP/s", "frac": achieved / peaks["tf_sust"], "traffic": None,
+                "peak_source": peaks["source"] + ", sustained bf16 figure (kernels timed inside a long step)",
+                "launch_ms": gemm_ms, "algorithmic_flops_per_launch": gemm_flops, "share_of_step": gemm_ms / ms_per_step,
+                "attention_fwd_tflops": attn_fwd_flops / (attn_fwd_ms / 1e3) / 1e12 if attn_fwd_ms > 0 else None,
+                "model_tflops_per_step": total_flops / 1e12,
+                "note": "achieved = (algorithmic FLOPs of all GEMM launches of one step) / (their summed CUDA-event time)"}
+    config = {"workload": f"cfg5: lcasr {mkey} random-init, training step (train-mode forward + CTC loss + backward"
+                          f"{' + gradient all-reduce' if world > 1 else ''}), {T} frames ({T / 6000:.1f} min) chunks, batch {B} per GPU",
+              "frames": T, "tokens": N, "recordings_per_gpu": B, "parallelism": f"data-parallel x{world}" if world > 1 else "single GPU",
+              "l2": "working set (>8 GB of saved activations per step) exceeds the 126 MB L2; no explicit flush"}
+    line = {"metric": "audio-sec/sec training step (fwd+bwd+CTC)", "value": value, "unit": "audio-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": world * audio_s / e2e_s, "unit": "audio-s/s",
+                    "h2d_bytes_per_step": int(x_host.numel() * 4 + tgt_host.numel() * 8 + tl_host.numel() * 8),
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3, "loss": loss_host},
+            "gpu_launches": launches, "roofline": roofline, "kernels": kern}
+    if not args.no_cpu_baseline and world == 1:
+        v, per, Bs, cores = cpu_reference_train(cfg, B, T, args.cpu_budget_s)
+        line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                "sample": f"one training step (train-mode forward + CTC + autograd backward, fp32) of {Bs} of the {B} "
+                                          f"recordings through the oracle port ({cores} threads), {per:.1f} s"}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -169,6 +326,21 @@ def main():
                           f"{B} recording(s)/GPU, forward + CTC log-softmax + greedy decode",
               "frames": T, "tokens": N, "recordings_per_gpu": B, "parallelism": f"batch-parallel x{args.gpus} (independent recordings)",
               "l2": "working set (>1 GB of activations per step) exceeds the 126 MB L2; no explicit flush"}
+
+    if args.workload == "cfg5":
+        if args.impl == "reference":
+            if rank != 0:
+                return 0
+            v, per, Bs, cores = cpu_reference_train(cfg, B, T, args.cpu_budget_s)
+            print(json.dumps({"impl": "reference", "metric": "audio-sec/sec training step (fwd+bwd+CTC)", "value": v,
+                              "unit": "audio-s/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": per * 1e3,
+                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                              "config": config, "gpu_launches": 0,
+                              "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                               "sample": f"one training step of {Bs} recording(s) through the oracle port"},
+                              "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            return 0
+        return train_bench(args, cfg, mkey, T, B, rank, world, local)
 
     if args.impl == "reference":
         if rank != 0:

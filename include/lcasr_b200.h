@@ -184,7 +184,8 @@ enum { LCASR_EPI_SCALE = 0, LCASR_EPI_EXP2 = 1, LCASR_EPI_DS = 2, LCASR_EPI_GELU
  *   GELU_BWD  out = alpha*acc * gelu_tanh'(aux)                  (fused_dense.py:466 backward)
  *   SILU_BWD  out = alpha*acc * silu'(aux)
  * out_dtype BF16: stored; F32: out += alpha*acc with fp32 atomics (SCALE only), which is what split-K
- * (ksplit > 1, or 0 = choose) and gradient accumulation need.  N, pitches and strides are multiples of 8.
+ * (ksplit > 1, or 0 = choose) and gradient accumulation need.  Pitches and strides are multiples of 8; so is
+ * N, except for bf16 outputs whose pitch leaves room for N rounded up to 8 (padding columns are unspecified).
  * Replaces the cuBLAS calls autograd issues for nn.Linear / 1x1 Conv backward and the flash-attn
  * backward (attention.py:532) of the reference. */
 typedef struct lcasr_gemm_ex_args {

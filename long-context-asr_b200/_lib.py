@@ -159,8 +159,26 @@ def check(status: int, what: str = "") -> None:
         raise LcasrError(f"lcasr_b200 {what} failed (status {status}): {msg}")
 
 
+# Optional per-entry-point device timing (bench.py's kernel breakdown of the Python-orchestrated training step):
+# set TIMING = {} to collect {name: [(start_event, end_event), ...]} on the current stream; None = off.
+TIMING = None
+
+
 def call(name: str, *args) -> None:
+    if TIMING is None:
+        check(getattr(lib, name)(*args), name)
+        return
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(getattr(lib, name)(*args), name)
+    e1.record()
+    TIMING.setdefault(name, []).append((e0, e1))
+
+
+def timing_summary(rec) -> dict:
+    """{name: (total ms, calls)} from a TIMING record (call after a synchronize)."""
+    return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in rec.items()}
 
 
 def ptr(t):

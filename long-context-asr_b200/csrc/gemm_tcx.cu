@@ -35,6 +35,7 @@ template <int BN> struct TxCfg {
 struct TxParams {
   int64_t M;
   int N, K;
+  int Nst;                      // columns stored per row: N rounded up to 8 (padding columns hold garbage)
   int nb1, nb2;                 // batch = b2 * nb1 + b1
   int ksplit, kper;             // K blocks per split
   int64_t ldo, so1, so2;        // output row pitch / batch strides (elements)
@@ -88,7 +89,7 @@ template <typename TOut>
 __device__ __forceinline__ void tx_store_chunk(const uint32_t (&r)[32], int64_t row, int col0, const TxParams& p, int b1,
                                                int b2, TOut* __restrict__ out) {
   if (row >= p.M) return;
-  const int ngroups = min(4, (p.N - col0) >> 3);  // N % 8 == 0
+  const int ngroups = min(4, (p.Nst - col0) >> 3);  // 8 columns per group
   float y[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(r[i]);
@@ -352,7 +353,11 @@ extern "C" int lcasr_gemm_ex(const lcasr_gemm_ex_args* gp, void* stream) {
   LCASR_CHECK_ARG(g.A && g.B && g.out, "gemm_ex: NULL operand");
   LCASR_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0 && g.nb1 > 0 && g.nb2 > 0, "gemm_ex: bad shape");
   LCASR_CHECK_ARG(g.M < ((int64_t)1 << 31), "gemm_ex: M too large");
-  LCASR_CHECK_ARG(g.N % 8 == 0, "gemm_ex: N=%d must be a multiple of 8", g.N);
+  // bf16 outputs may have any N when the row pitch leaves room for the 8-column store granularity: the
+  // padding columns then receive unspecified values (consumers bound their K / M extent by the true size)
+  const int Nst = (g.N + 7) / 8 * 8;
+  LCASR_CHECK_ARG(g.N % 8 == 0 || (g.out_dtype == LCASR_BF16 && g.ldo >= Nst && (!g.aux || g.ldaux >= Nst)),
+                  "gemm_ex: N=%d must be a multiple of 8 (or a bf16 output with pitch >= N rounded up to 8)", g.N);
   LCASR_CHECK_ARG(g.lda % 8 == 0 && g.ldb % 8 == 0 && g.sa1 % 8 == 0 && g.sa2 % 8 == 0 && g.sb1 % 8 == 0 && g.sb2 % 8 == 0,
                   "gemm_ex: operand pitches / batch strides must be multiples of 8 elements (TMA: 16 bytes)");
   LCASR_CHECK_ARG(((uintptr_t)g.A & 15) == 0 && ((uintptr_t)g.B & 15) == 0 && ((uintptr_t)g.out & 15) == 0 &&
@@ -384,7 +389,7 @@ extern "C" int lcasr_gemm_ex(const lcasr_gemm_ex_args* gp, void* stream) {
   const int kper = (int)ceil_div(num_k, ksplit);
   ksplit = (int)ceil_div(num_k, kper);  // no empty splits
   TxParams p;
-  p.M = g.M; p.N = g.N; p.K = g.K; p.nb1 = g.nb1; p.nb2 = g.nb2; p.ksplit = ksplit; p.kper = kper;
+  p.M = g.M; p.N = g.N; p.Nst = Nst; p.K = g.K; p.nb1 = g.nb1; p.nb2 = g.nb2; p.ksplit = ksplit; p.kper = kper;
   p.ldo = g.ldo; p.so1 = g.so1; p.so2 = g.so2;
   p.aux = (const bf16*)g.aux; p.ldx = g.ldaux; p.sx1 = g.sx1; p.sx2 = g.sx2;
   p.rowvec = g.rowvec; p.sr1 = g.sr1; p.sr2 = g.sr2;

@@ -407,8 +407,39 @@ class SCConformerXL(nn.Module):
         return self._workspace
 
     # ---- forward ------------------------------------------------------------------------------
-    @torch.no_grad()
     def forward(self, audio_signal, length=None, cached_kvs=None, cached_kv_lengths=None, return_logits=False):
+        """Same signature and result as the reference (sconformer_xl.py:162-252).  ``model.eval()``: one fused
+        inference call (no autograd graph).  ``model.train()``: the training path (training.py) — BatchRenorm uses
+        batch statistics and updates its running buffers, and ``final_posteriors`` carries a grad_fn whose
+        backward is the hand-written backward pass, so ``loss.backward()`` fills ``.grad`` of every parameter."""
+        if self.training:
+            return self._forward_train(audio_signal, length, cached_kvs, cached_kv_lengths, return_logits)
+        return self._forward_eval(audio_signal, length, cached_kvs, cached_kv_lengths, return_logits)
+
+    def _forward_train(self, audio_signal, length, cached_kvs, cached_kv_lengths, return_logits):
+        from .training import train_forward
+        if cached_kvs is not None or cached_kv_lengths is not None:
+            raise NotImplementedError("cached_kvs is dead code in the reference (SURVEY §3.2) and not supported")
+        if not audio_signal.is_cuda:
+            raise RuntimeError("lcasr_b200.SCConformerXL runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if audio_signal.dim() != 3 or audio_signal.shape[1] != self.feat_in:
+            raise ValueError(f"audio_signal must be [B, {self.feat_in}, T], got {tuple(audio_signal.shape)}")
+        if self.compute_dtype != torch.bfloat16:
+            raise NotImplementedError("the training path computes in bf16 (the reference trains under bf16 autocast)")
+        if return_logits:
+            raise NotImplementedError("return_logits=True is an inference option (decoder.py:26-27)")
+        B, _, T = audio_signal.shape
+        if length is not None:
+            lens = [int(v) for v in (length.tolist() if torch.is_tensor(length) else length)]
+            if any(v != T for v in lens):
+                raise NotImplementedError("training on padded batches is a 'next' row (SURVEY §8 f4); equal-length chunks only "
+                                          "(what exp/train.py feeds: fixed max_seq_len chunks)")
+        lp = train_forward(self, audio_signal.detach().to(torch.float32).contiguous())
+        N = lp.shape[1]
+        return {"final_posteriors": lp, "length": torch.full((B,), N, dtype=torch.int32, device=audio_signal.device)}
+
+    @torch.no_grad()
+    def _forward_eval(self, audio_signal, length=None, cached_kvs=None, cached_kv_lengths=None, return_logits=False):
         """audio_signal [B, feat_in, T] fp32 CUDA; length [B] frames per recording, or None (= T).
         Ragged batches take the key-padding-mask path (sconformer_xl.py:204-215): rows of padded tokens
         in `final_posteriors` are unspecified, exactly `length[b]` rows of recording b are meaningful."""

@@ -272,7 +272,14 @@ def attention_forward(sd, cfg: dict, p: str, a: Tensor, cos, sin, collect=None, 
     return o @ sd[p + "attend.fn.out_proj.weight"].T
 
 
-def conv_module_forward(sd, cfg: dict, p: str, a: Tensor, collect=None, pad_mask=None) -> Tensor:
+def brn_clamps(num_batches_tracked: int) -> Tuple[float, float]:
+    """batchrenorm.py:41-50: rmax = clamp(2/35000*n + 25/35, 1, 3), dmax = clamp(5/20000*n - 25/20, 0, 5)."""
+    n = float(num_batches_tracked)
+    return min(max(2.0 / 35000.0 * n + 25.0 / 35.0, 1.0), 3.0), min(max(5.0 / 20000.0 * n - 25.0 / 20.0, 0.0), 5.0)
+
+
+def conv_module_forward(sd, cfg: dict, p: str, a: Tensor, collect=None, pad_mask=None, train: bool = False,
+                        new_stats: Optional[dict] = None) -> Tensor:
     """convolution.py:103-124 with BatchRenorm eval (batchrenorm.py:86-91); a = LN(x) [B,N,d].
     pad_mask [B,N] (True = padded): the GLU output is zeroed there before the depthwise conv (:109-110)."""
     d, ks = cfg["d_model"], cfg["conv_kernel_size"]
@@ -287,7 +294,20 @@ def conv_module_forward(sd, cfg: dict, p: str, a: Tensor, collect=None, pad_mask
                  padding=(ks - 1) // 2, groups=d)
     rm, rs = sd[p + "conv.fn.batch_norm.running_mean"], sd[p + "conv.fn.batch_norm.running_std"]
     bw, bb = sd[p + "conv.fn.batch_norm.weight"], sd[p + "conv.fn.batch_norm.bias"]
-    y = (y - rm[None, :, None]) / rs[None, :, None]  # eval: no eps
+    if train:  # batchrenorm.py:62-84: batch statistics over (B, N); r and d are constants for autograd
+        eps, momentum = 1e-3, 0.01
+        rmax, dmax = brn_clamps(int(sd[p + "conv.fn.batch_norm.num_batches_tracked"]))
+        yt = y.transpose(1, 2)  # [B,N,d]
+        mu = yt.mean((0, 1))
+        sigma = yt.std((0, 1), unbiased=False) + eps
+        r = (sigma.detach() / rs).clamp(1.0 / rmax, rmax)
+        dd = ((mu.detach() - rm) / rs).clamp(-dmax, dmax)
+        y = ((yt - mu) / sigma * r + dd).transpose(1, 2)
+        if new_stats is not None:
+            new_stats[p + "conv.fn.batch_norm.running_mean"] = (rm + momentum * (mu.detach() - rm)).detach()
+            new_stats[p + "conv.fn.batch_norm.running_std"] = (rs + momentum * (sigma.detach() - rs)).detach()
+    else:
+        y = (y - rm[None, :, None]) / rs[None, :, None]  # eval: no eps
     y = bw[None, :, None] * y + bb[None, :, None]
     y = F.silu(y)
     if collect is not None:
@@ -311,11 +331,14 @@ def decoder_logits(sd, cfg: dict, x: Tensor) -> Tensor:
 
 
 def encoder_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, return_logits: bool = False,
-                    collect: Optional[dict] = None, lengths=None) -> Tuple[Tensor, Tensor]:
+                    collect: Optional[dict] = None, lengths=None, train: bool = False,
+                    new_stats: Optional[dict] = None) -> Tuple[Tensor, Tensor]:
     """SCConformerXL.forward (sconformer_xl.py:162-252, 346-372).
     x [B, feat_in, T] fp32 -> (final_posteriors [B,N,V+1], length int32[B]).  `lengths` (frames per
     recording, None = all T): a ragged batch takes the pad-mask path of :188,204-215 (the non-flash
-    branch, which is the one that runs on CPU)."""
+    branch, which is the one that runs on CPU).  train=True: module.train() semantics (BatchRenorm uses batch
+    statistics; dropout is 0 in every released config); differentiable w.r.t. the tensors of `sd`, new running
+    statistics are returned through `new_stats`."""
     assert cfg["subsampling"] == "dw_striding" and not cfg["transformer"] and not cfg["sandwich_norm"]
     sd = {k: (v.float() if v.is_floating_point() else v) for k, v in sd.items()}
     B, _, T = x.shape
@@ -342,7 +365,7 @@ def encoder_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, return_logits: 
         h = attention_forward(sd, cfg, p, _norm(h, sd, p + "attend.norm", cfg), cos, sin, collect, pad_mask) + h
         if collect is not None:
             collect[p + "after_attn"] = h
-        h = conv_module_forward(sd, cfg, p, _norm(h, sd, p + "conv.norm", cfg), collect, pad_mask) + h
+        h = conv_module_forward(sd, cfg, p, _norm(h, sd, p + "conv.norm", cfg), collect, pad_mask, train, new_stats) + h
         if collect is not None:
             collect[p + "after_conv"] = h
         h = 0.5 * ffn_forward(sd, cfg, p + "ff2.fn.fn", _norm(h, sd, p + "ff2.fn.norm", cfg)) + h
@@ -454,3 +477,21 @@ def ctc_grad(log_probs, targets, input_lengths, target_lengths, blank: int) -> n
             res[:, ext[s]] = np.logaddexp(res[:, ext[s]], ab[:, s])
         grad[b, :T] = np.exp(lp) - np.exp(res + nll - lp)
     return grad
+
+
+# --------------------------------------------------------------------------------------------
+# training step (exp/train.py:236-262): forward in train mode, CTC loss (sum), backward
+# --------------------------------------------------------------------------------------------
+
+def training_step(sd: Dict[str, Tensor], cfg: dict, x: Tensor, targets: Tensor, target_lengths: Tensor):
+    """loss = CTCLoss(blank=V, reduction='sum')(log_probs.transpose(0,1), targets, length, target_lengths)
+    (exp/train.py:104,249) of the train-mode forward, and d loss / d parameter for every floating-point
+    parameter of `sd` (buffers excluded).  Returns (loss float, {name: grad}, {buffer name: new running stat})."""
+    buffers = ("running_mean", "running_std", "num_batches_tracked", "inv_freq", "rotary_interpolation_factor")
+    leaves = {k: (v.detach().clone().float().requires_grad_(True) if not k.endswith(buffers) else v) for k, v in sd.items()}
+    new_stats: Dict[str, Tensor] = {}
+    lp, length = encoder_forward(leaves, cfg, x, train=True, new_stats=new_stats)
+    loss = F.ctc_loss(lp.transpose(0, 1), targets, length.long(), target_lengths, blank=cfg["vocab_size"], reduction="sum")
+    loss.backward()
+    grads = {k: v.grad for k, v in leaves.items() if isinstance(v, Tensor) and v.requires_grad and v.grad is not None}
+    return float(loss.detach()), grads, new_stats, lp.detach()

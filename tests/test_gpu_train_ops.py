@@ -76,7 +76,8 @@ def test_gemm_ex_activation_backward_epilogues(cuda_device, epi):
     _close(got, p32.grad, 2 ** -6, f"dgrad+{epi}'")
 
 
-@pytest.mark.parametrize("B,N,H,Dh", [(2, 256, 2, 128), (3, 200, 4, 32), (1, 1000, 2, 64), (8, 2048, 6, 128)])
+@pytest.mark.parametrize("B,N,H,Dh", [(2, 256, 2, 128), (3, 200, 4, 32), (1, 1000, 2, 64), (8, 2048, 6, 128), (2, 33, 2, 32),
+                                        (2, 65, 1, 128)])
 def test_attention_train_and_backward(cuda_device, B, N, H, Dh):
     from lcasr_b200 import train_ops as T
     q = _rand(B, N, H, Dh, seed=11).to(BF).to(cuda_device)
