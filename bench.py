@@ -184,6 +184,8 @@ def train_bench(args, cfg, mkey, T, B, rank, world, local):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # rank 0 prints ONE JSON line on stdout: NCCL's version banner / warnings go to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
@@ -365,6 +367,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
+        # rank 0 prints ONE JSON line on stdout: NCCL's version banner / warnings go to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)

@@ -199,11 +199,21 @@ typedef struct lcasr_gemm_ex_args {
 } lcasr_gemm_ex_args;
 int lcasr_gemm_ex(const lcasr_gemm_ex_args* args, void* stream);
 
+/* First half of the attention backward in ONE pass per (recording, head): S = q k^T and dP = dO v^T as two
+ * accumulators of the same tile, P = exp2(S*scale*log2e - lse2) and dS = P o (dP - dvec) * scale written as
+ * bf16 [nb,H,N,Np] (Np = N rounded up to 8).  q,k,v,d_out bf16 [nb,N,H,Dh]; lse2, dvec fp32 [nb,H,N]. */
+int lcasr_attention_bwd_pds(const void* q, const void* k, const void* v, const void* d_out, const float* lse2,
+                            const float* dvec, int nb, int64_t N, int H, int Dh, void* P, void* dS, void* stream);
+
 /* Attention forward that also returns lse [B,H,N] fp32 = log2-domain log-sum-exp of the scaled scores
  * (bf16, natural-layout V, tcgen05 kernel). */
 int lcasr_attention_train(const void* q, const void* k, const void* v, int B, int64_t N, int H, int Dh,
                           void* out, float* lse, void* stream);
 
+/* Training forward of Linear + activation: pre = A.W^T + bias and out = act(pre), both bf16 [M,N] (tcgen05 GEMM
+ * with a two-output epilogue; replaces lcasr_gemm + lcasr_act_fwd). */
+int lcasr_gemm_act_pre(const void* A, const void* W, int64_t M, int N, int K, const float* bias, int act,
+                       void* out, void* pre_out, void* stream);
 /* out(bf16) = scale * in(fp32), n % 8 == 0 */
 int lcasr_scale_cast(const float* in, int64_t n, float scale, void* out, void* stream);
 /* out = gelu_tanh(in) / silu(in), bf16 (the pre-activation is kept for the backward) */
@@ -265,6 +275,17 @@ int lcasr_subsample_dwconv_bwd_weight(const void* in, const void* dout, int B, i
                                       float* dw, float* db, void* stream);
 int lcasr_subsample_conv0_bwd(const float* spec, const float* w, const float* b, const void* ds1, int B, int F,
                               int64_t T, int C, float* dw, float* db, void* stream);
+
+/* Training form of the CTC loss (up to 4096 extended states): the alpha and beta recursions are independent, so
+ * one launch runs both concurrently (2*B CTAs) into alpha_ws / beta_ws [B,N,2*S_max+1]; the backward is then
+ * only lcasr_ctc_loss_grad (the class scatter).  Same results as lcasr_ctc_loss_fwd + lcasr_ctc_loss_bwd. */
+int lcasr_ctc_loss_fwd_ab(const float* log_probs, int B, int64_t N, int V, const int64_t* targets,
+                          int64_t S_max, const int32_t* input_lengths, const int64_t* target_lengths,
+                          int blank, float* nll, float* alpha_ws, float* beta_ws, void* stream);
+int lcasr_ctc_loss_grad(const float* log_probs, int B, int64_t N, int V, const int64_t* targets,
+                        int64_t S_max, const int32_t* input_lengths, const int64_t* target_lengths,
+                        int blank, const float* nll, const float* grad_nll, const float* alpha_ws,
+                        const float* beta_ws, float* grad, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * The model: SCConformerXL.forward (lcasr/models/sconformer_xl.py:162-252), equal-length path

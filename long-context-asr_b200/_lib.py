@@ -84,8 +84,12 @@ _SIGNATURES = {
     "lcasr_greedy_collapse": [vp, i32, i64, vp, i32, vp, vp, vp],
     "lcasr_ctc_loss_fwd": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp],
     "lcasr_ctc_loss_bwd": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp],
+    "lcasr_ctc_loss_fwd_ab": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp, vp],
+    "lcasr_ctc_loss_grad": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp],
     "lcasr_gemm_ex": [C.POINTER(LcasrGemmExArgs), vp],
+    "lcasr_attention_bwd_pds": [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, vp, vp, vp],
     "lcasr_attention_train": [vp, vp, vp, i32, i64, i32, i32, vp, vp, vp],
+    "lcasr_gemm_act_pre": [vp, vp, i64, i32, i32, vp, i32, vp, vp, vp],
     "lcasr_scale_cast": [vp, i64, f32, vp, vp],
     "lcasr_act_fwd": [vp, i64, i32, vp, vp],
     "lcasr_act_bwd": [vp, vp, i64, i32, vp, vp],
@@ -162,9 +166,10 @@ def check(status: int, what: str = "") -> None:
 # Optional per-entry-point device timing (bench.py's kernel breakdown of the Python-orchestrated training step):
 # set TIMING = {} to collect {name: [(start_event, end_event), ...]} on the current stream; None = off.
 TIMING = None
+TIMING_TAGS = False  # True: split entries by the shape tag some wrappers pass (per-shape GEMM table)
 
 
-def call(name: str, *args) -> None:
+def call(name: str, *args, tag: str = "") -> None:
     if TIMING is None:
         check(getattr(lib, name)(*args), name)
         return
@@ -173,7 +178,7 @@ def call(name: str, *args) -> None:
     e0.record()
     check(getattr(lib, name)(*args), name)
     e1.record()
-    TIMING.setdefault(name, []).append((e0, e1))
+    TIMING.setdefault(name + tag if TIMING_TAGS else name, []).append((e0, e1))
 
 
 def timing_summary(rec) -> dict:

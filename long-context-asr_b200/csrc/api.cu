@@ -22,7 +22,7 @@ int set_error(int code, const char* fmt, ...) {
 int gemm_simt_launch(const void* A, const void* W, int ab_dtype, int64_t M, int N, int K, const float* bias, int act,
                      const float* resid, float alpha, void* out, int out_dtype, cudaStream_t st);
 int gemm_tc_launch(const void* A, const void* W, int64_t M, int N, int K, const float* bias, int act, const float* resid,
-                   float alpha, void* out, int out_dtype, cudaStream_t st);
+                   float alpha, void* out, int out_dtype, cudaStream_t st, void* pre_out = nullptr);
 int attn_simt_launch(const void* q, const void* k, const void* v, int dtype, int B, int64_t N, int64_t Nk, const int32_t* kv_len,
                      int H, int Dh, int v_transposed, int64_t Npad, void* out, cudaStream_t st);
 int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len, int H,
@@ -100,4 +100,13 @@ extern "C" int lcasr_attention_train(const void* q, const void* k, const void* v
   LCASR_CHECK_ARG(q && k && v && out && lse, "attention_train: NULL operand");
   LCASR_CHECK_ARG(B > 0 && N > 0 && H > 0 && Dh > 0, "attention_train: bad shape");
   return attn_tc_launch(q, k, v, B, N, N, nullptr, H, Dh, 0, 0, out, lse, (cudaStream_t)stream);
+}
+
+// training forward: out = act(pre), pre = A.W^T + bias, both stored as bf16 (the backward needs the pre-activation)
+extern "C" int lcasr_gemm_act_pre(const void* A, const void* W, int64_t M, int N, int K, const float* bias, int act, void* out,
+                                  void* pre_out, void* stream) {
+  LCASR_CHECK_ARG(A && W && out && pre_out, "gemm_act_pre: NULL operand");
+  LCASR_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_act_pre: bad shape");
+  LCASR_CHECK_ARG(act == LCASR_ACT_GELU_TANH || act == LCASR_ACT_SILU, "gemm_act_pre: bad activation %d", act);
+  return gemm_tc_launch(A, W, M, N, K, bias, act, nullptr, 0.f, out, LCASR_BF16, (cudaStream_t)stream, pre_out);
 }

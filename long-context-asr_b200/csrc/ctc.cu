@@ -32,9 +32,18 @@ __global__ void __launch_bounds__(1024) ctc_recursion_kernel(const float* __rest
                                                              const int32_t* __restrict__ input_lengths,
                                                              const int64_t* __restrict__ target_lengths, int blank,
                                                              int direction, float* __restrict__ nll,
-                                                             float* __restrict__ store) {
+                                                             float* __restrict__ store, float* __restrict__ store_beta,
+                                                             int batch) {
+  // direction == 0: BOTH recursions in one launch (grid = 2*batch CTAs): CTA b < batch runs alpha into `store`,
+  // CTA batch+b runs beta into `store_beta` (plain stores: the two are independent and run concurrently)
   extern __shared__ float sm_alpha[];  // [2][Lp_pad]
-  const int b = blockIdx.x;
+  const bool both = direction == 0;
+  if (both) {
+    direction = (int)blockIdx.x < batch ? +1 : -1;
+    if (direction < 0) { store = store_beta; nll = nullptr; }
+  }
+  const bool beta_adds = !both;  // legacy two-launch form: beta is added onto the alpha already in `store`
+  const int b = both ? (int)blockIdx.x % batch : (int)blockIdx.x;
   const int NT = blockDim.x;
   const int tid = threadIdx.x;
   const int64_t T = input_lengths ? min((int64_t)input_lengths[b], N) : N;
@@ -86,7 +95,7 @@ __global__ void __launch_bounds__(1024) ctc_recursion_kernel(const float* __rest
       if (st && s < Lp) {
         int so = direction > 0 ? s : (Lp - 1 - s);
         float* p = st + frame(0) * Lp_max + so;
-        *p = direction > 0 ? a : (*p + a);
+        *p = (direction > 0 || !beta_adds) ? a : (*p + a);
       }
     }
     if (T > 1) {
@@ -114,7 +123,7 @@ __global__ void __launch_bounds__(1024) ctc_recursion_kernel(const float* __rest
         nxt[s] = a;
         if (strow) {
           int so = direction > 0 ? s : (Lp - 1 - s);
-          strow[so] = direction > 0 ? a : (strow[so] + a);
+          strow[so] = (direction > 0 || !beta_adds) ? a : (strow[so] + a);
         }
       }
     }
@@ -284,7 +293,9 @@ __global__ void __launch_bounds__(256) ctc_grad_collect_kernel(const float* __re
                                                                const int64_t* __restrict__ target_lengths, int blank,
                                                                const float* __restrict__ nll,
                                                                const float* __restrict__ grad_nll,
-                                                               const float* __restrict__ ab, float* __restrict__ grad) {
+                                                               const float* __restrict__ ab, const float* __restrict__ ab2,
+                                                               float* __restrict__ grad) {
+  // ab2 == NULL: `ab` holds alpha+beta; else ab = alpha, ab2 = beta (kept apart by the concurrent recursion)
   extern __shared__ float acc[];  // [V] linear-domain sums relative to the frame max
   __shared__ float red[8];
   const int64_t t = blockIdx.x;
@@ -298,11 +309,12 @@ __global__ void __launch_bounds__(256) ctc_grad_collect_kernel(const float* __re
   }
   const int Lp = (int)(2 * S + 1), Lp_max = (int)(2 * S_max + 1);
   const float* abr = ab + ((int64_t)b * N + t) * Lp_max;
+  const float* abr2 = ab2 ? ab2 + ((int64_t)b * N + t) * Lp_max : nullptr;
   const int64_t* tgt = targets + (int64_t)b * S_max;
   const float* lp = log_probs + ((int64_t)b * N + t) * V;
   for (int c = threadIdx.x; c < V; c += blockDim.x) acc[c] = 0.f;
   float mx = -INFINITY;
-  for (int s = threadIdx.x; s < Lp; s += blockDim.x) mx = fmaxf(mx, abr[s]);
+  for (int s = threadIdx.x; s < Lp; s += blockDim.x) mx = fmaxf(mx, abr2 ? abr[s] + abr2[s] : abr[s]);
   mx = warp_max(mx);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
   __syncthreads();
@@ -312,7 +324,7 @@ __global__ void __launch_bounds__(256) ctc_grad_collect_kernel(const float* __re
   if (mx != -INFINITY) {
     float blank_sum = 0.f;  // the S+1 blank states would serialise on one shared-memory atomic
     for (int s = threadIdx.x; s < Lp; s += blockDim.x) {
-      float v = abr[s];
+      float v = abr2 ? abr[s] + abr2[s] : abr[s];
       if (v == -INFINITY) continue;
       float e = expf(v - mx);
       if (s & 1) atomicAdd(&acc[(int)tgt[(s - 1) >> 1]], e);
@@ -333,21 +345,25 @@ __global__ void __launch_bounds__(256) ctc_grad_collect_kernel(const float* __re
 
 template <int SPT>
 static int launch_rec(const float* lp, int B, int64_t N, int V, const int64_t* tg, int64_t S_max, const int32_t* il,
-                      const int64_t* tl, int blank, int dir, float* nll, float* store, int nt, cudaStream_t st) {
+                      const int64_t* tl, int blank, int dir, float* nll, float* store, int nt, cudaStream_t st,
+                      float* store_beta = nullptr) {
   size_t smem = (size_t)2 * SPT * nt * sizeof(float);
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
     LCASR_CUDA(cudaFuncSetAttribute(ctc_recursion_kernel<SPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  ctc_recursion_kernel<SPT><<<B, nt, smem, st>>>(lp, N, V, tg, S_max, il, tl, blank, dir, nll, store);
+  ctc_recursion_kernel<SPT><<<dir == 0 ? 2 * B : B, nt, smem, st>>>(lp, N, V, tg, S_max, il, tl, blank, dir, nll, store,
+                                                                    store_beta, B);
   LCASR_LAUNCH_CHECK();
   return 0;
 }
 
 static int ctc_recursion(const float* lp, int B, int64_t N, int V, const int64_t* tg, int64_t S_max, const int32_t* il,
-                         const int64_t* tl, int blank, int dir, float* nll, float* store, cudaStream_t st) {
+                         const int64_t* tl, int blank, int dir, float* nll, float* store, cudaStream_t st,
+                         float* store_beta = nullptr) {
   const int64_t Lp = 2 * S_max + 1;
+  LCASR_CHECK_ARG(dir != 0 || Lp <= 4096, "ctc_loss: the concurrent alpha/beta form covers up to 4096 extended states");
   static const bool no_cluster = getenv("LCASR_CTC_NO_CLUSTER") != nullptr;  // A/B switch for profiling
   if (Lp > 4096 && !no_cluster) {  // spread the states over a cluster of up to 8 SMs (below that the cluster
                                     // barrier costs more than it saves: measured 2.7 vs 1.45 ms at 1229 states)
@@ -373,12 +389,12 @@ static int ctc_recursion(const float* lp, int B, int64_t N, int V, const int64_t
   while ((size_t)2 * spt * nt * 4 > 227 * 1024 && nt > 32) nt -= 32;
   LCASR_CHECK_ARG((int64_t)spt * nt >= Lp, "ctc_loss: internal sizing error");
   switch (spt) {
-    case 1: return launch_rec<1>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st);
-    case 2: return launch_rec<2>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st);
-    case 4: return launch_rec<4>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st);
-    case 8: return launch_rec<8>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st);
-    case 16: return launch_rec<16>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st);
-    default: return launch_rec<32>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st);
+    case 1: return launch_rec<1>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st, store_beta);
+    case 2: return launch_rec<2>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st, store_beta);
+    case 4: return launch_rec<4>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st, store_beta);
+    case 8: return launch_rec<8>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st, store_beta);
+    case 16: return launch_rec<16>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st, store_beta);
+    default: return launch_rec<32>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st, store_beta);
   }
 }
 
@@ -418,7 +434,39 @@ extern "C" int lcasr_ctc_loss_bwd(const float* log_probs, int B, int64_t N, int 
   LCASR_CHECK_ARG(B <= 65535, "ctc_loss_bwd: batch too large");
   dim3 grid((unsigned)N, (unsigned)B);
   ctc_grad_collect_kernel<<<grid, 256, smem, st>>>(log_probs, N, V, targets, S_max, input_lengths, target_lengths, blank,
-                                                   nll, grad_nll, beta_ws, grad);
+                                                   nll, grad_nll, beta_ws, nullptr, grad);
+  LCASR_LAUNCH_CHECK();
+  return 0;
+}
+
+// Training form: alpha and beta recursions in ONE launch (2*B CTAs, independent, concurrent) ...
+extern "C" int lcasr_ctc_loss_fwd_ab(const float* log_probs, int B, int64_t N, int V, const int64_t* targets,
+                                     int64_t S_max, const int32_t* input_lengths, const int64_t* target_lengths,
+                                     int blank, float* nll, float* alpha_ws, float* beta_ws, void* stream) {
+  LCASR_CHECK_ARG(log_probs && targets && target_lengths && nll && alpha_ws && beta_ws, "ctc_loss_fwd_ab: NULL argument");
+  LCASR_CHECK_ARG(B > 0 && N > 0 && V > 1 && S_max >= 0 && blank >= 0 && blank < V, "ctc_loss_fwd_ab: bad shape");
+  return ctc_recursion(log_probs, B, N, V, targets, S_max, input_lengths, target_lengths, blank, 0, nll, alpha_ws,
+                       (cudaStream_t)stream, beta_ws);
+}
+
+// ... and the gradient from the two state lattices (no recursion left in the backward).
+extern "C" int lcasr_ctc_loss_grad(const float* log_probs, int B, int64_t N, int V, const int64_t* targets,
+                                   int64_t S_max, const int32_t* input_lengths, const int64_t* target_lengths,
+                                   int blank, const float* nll, const float* grad_nll, const float* alpha_ws,
+                                   const float* beta_ws, float* grad, void* stream) {
+  LCASR_CHECK_ARG(log_probs && targets && target_lengths && nll && alpha_ws && beta_ws && grad, "ctc_loss_grad: NULL argument");
+  LCASR_CHECK_ARG(B > 0 && B <= 65535 && N > 0 && V > 1 && S_max >= 0 && blank >= 0 && blank < V, "ctc_loss_grad: bad shape");
+  LCASR_CHECK_ARG((size_t)V * 4 <= 200 * 1024, "ctc_loss_grad: V=%d too large", V);
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t smem = (size_t)V * sizeof(float);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    LCASR_CUDA(cudaFuncSetAttribute(ctc_grad_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  dim3 grid((unsigned)N, (unsigned)B);
+  ctc_grad_collect_kernel<<<grid, 256, smem, st>>>(log_probs, N, V, targets, S_max, input_lengths, target_lengths, blank,
+                                                   nll, grad_nll, alpha_ws, beta_ws, grad);
   LCASR_LAUNCH_CHECK();
   return 0;
 }

@@ -34,6 +34,7 @@ struct TgEpilogue {
   const float* resid;  // [M,N] fp32 or null
   float alpha;
   int act;
+  bf16* pre_out = nullptr;  // training: the pre-activation acc+bias [M,N] is stored as well (bf16 outputs only)
 };
 
 // Direct epilogue (bf16 outputs, no residual): lane == row, 64 contiguous bytes per lane and chunk.
@@ -56,6 +57,15 @@ __device__ __forceinline__ void tg_store_chunk_direct(const uint32_t (&r)[32], i
         y[8 * g + 0] += b0.x; y[8 * g + 1] += b0.y; y[8 * g + 2] += b0.z; y[8 * g + 3] += b0.w;
         y[8 * g + 4] += b1.x; y[8 * g + 5] += b1.y; y[8 * g + 6] += b1.z; y[8 * g + 7] += b1.w;
       }
+  }
+  if (ep.pre_out) {
+    bf16* pp = ep.pre_out + row * N + col0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < ngroups) Vec8<bf16>::store(pp + 8 * g, *reinterpret_cast<const float(*)[8]>(&y[8 * g]));
+    // the activation below is applied to the ROUNDED pre-activation, i.e. exactly what the backward will see
+#pragma unroll
+    for (int i = 0; i < 32; ++i) y[i] = __bfloat162float(__float2bfloat16_rn(y[i]));
   }
   if (ep.act == LCASR_ACT_GELU_TANH) {
 #pragma unroll
@@ -354,14 +364,16 @@ static int launch_tc(const void* A, const void* W, int64_t M, int N, int K, cons
 }
 
 int gemm_tc_launch(const void* A, const void* W, int64_t M, int N, int K, const float* bias, int act, const float* resid,
-                   float alpha, void* out, int out_dtype, cudaStream_t st) {
+                   float alpha, void* out, int out_dtype, cudaStream_t st, void* pre_out) {
+  LCASR_CHECK_ARG(!pre_out || (out_dtype == LCASR_BF16 && !resid && ((uintptr_t)pre_out & 15) == 0),
+                  "gemm(tcgen05): the pre-activation output needs a bf16, residual-free epilogue");
   LCASR_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "gemm(tcgen05): K=%d and N=%d must be multiples of 8", K, N);
   LCASR_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0,
                   "gemm(tcgen05): A, W and out must be 16-byte aligned");
   LCASR_CHECK_ARG(M < (int64_t)1 << 31, "gemm(tcgen05): M too large");
   LCASR_CHECK_ARG(((uintptr_t)bias & 15) == 0 && ((uintptr_t)resid & 15) == 0, "gemm(tcgen05): bias/resid must be 16-byte aligned");
   LCASR_CHECK_ARG(!resid || out_dtype == LCASR_F32, "gemm: a residual epilogue writes fp32");
-  TgEpilogue ep{bias, resid, alpha, act};
+  TgEpilogue ep{bias, resid, alpha, act, (bf16*)pre_out};
   const bool wide = (N % 256 == 0) || N > 512;
   if (out_dtype == LCASR_BF16)
     return wide ? launch_tc<256, bf16>(A, W, M, N, K, ep, out, st) : launch_tc<128, bf16>(A, W, M, N, K, ep, out, st);

@@ -84,10 +84,20 @@ __device__ __forceinline__ float silu_grad(float x) {
   return s * (1.0f + x * (1.0f - s));
 }
 
+// aux values (bf16, same indexing as the output) of one 32-column chunk of this lane's row: issued one chunk
+// AHEAD of their use, so the strided 16-byte loads (one row per lane) overlap the previous chunk's work
+__device__ __forceinline__ void tx_load_aux(uint4 (&ax)[4], int64_t row, int col0, const TxParams& p, int b1, int b2) {
+  if (row >= p.M) return;
+  const bf16* xp = p.aux + b2 * p.sx2 + b1 * p.sx1 + row * p.ldx + col0;
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    if (col0 + 8 * g < p.Nst) ax[g] = *reinterpret_cast<const uint4*>(xp + 8 * g);
+}
+
 // one 32-column chunk of one accumulator row (lane == row)
 template <typename TOut>
-__device__ __forceinline__ void tx_store_chunk(const uint32_t (&r)[32], int64_t row, int col0, const TxParams& p, int b1,
-                                               int b2, TOut* __restrict__ out) {
+__device__ __forceinline__ void tx_store_chunk(const uint32_t (&r)[32], const uint4 (&ax)[4], float rv, int64_t row, int col0,
+                                               const TxParams& p, int b1, int b2, TOut* __restrict__ out) {
   if (row >= p.M) return;
   const int ngroups = min(4, (p.Nst - col0) >> 3);  // 8 columns per group
   float y[32];
@@ -98,24 +108,21 @@ __device__ __forceinline__ void tx_store_chunk(const uint32_t (&r)[32], int64_t 
 #pragma unroll
     for (int i = 0; i < 32; ++i) y[i] *= a;
   } else if (p.epi == LCASR_EPI_EXP2) {
-    const float rv = p.rowvec[b2 * p.sr2 + b1 * p.sr1 + row];
 #pragma unroll
     for (int i = 0; i < 32; ++i) y[i] = ex2_approx(fmaf(y[i], a, -rv));
   } else {
-    const bf16* xp = p.aux + b2 * p.sx2 + b1 * p.sx1 + row * p.ldx + col0;
-    float rv = 0.f;
-    if (p.epi == LCASR_EPI_DS) rv = p.rowvec[b2 * p.sr2 + b1 * p.sr1 + row];
 #pragma unroll
     for (int g = 0; g < 4; ++g)
       if (g < ngroups) {
-        float x[8];
-        Vec8<bf16>::load(xp + 8 * g, x);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&ax[g]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float& v = y[8 * g + i];
-          if (p.epi == LCASR_EPI_DS) v = x[i] * (v - rv) * a;
-          else if (p.epi == LCASR_EPI_GELU_BWD) v = a * v * gelu_tanh_grad(x[i]);
-          else v = a * v * silu_grad(x[i]);  // LCASR_EPI_SILU_BWD
+        for (int i = 0; i < 4; ++i) {
+          const float2 x = __bfloat1622float2(h[i]);
+          float& v0 = y[8 * g + 2 * i];
+          float& v1 = y[8 * g + 2 * i + 1];
+          if (p.epi == LCASR_EPI_DS) { v0 = x.x * (v0 - rv) * a; v1 = x.y * (v1 - rv) * a; }
+          else if (p.epi == LCASR_EPI_GELU_BWD) { v0 = a * v0 * gelu_tanh_grad(x.x); v1 = a * v1 * gelu_tanh_grad(x.y); }
+          else { v0 = a * v0 * silu_grad(x.x); v1 = a * v1 * silu_grad(x.y); }  // LCASR_EPI_SILU_BWD
         }
       }
   }
@@ -249,6 +256,12 @@ gemm_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TxTile t = tx_decode<BN>(tile, p, tiles_n, tiles_m, num_k);
       const int64_t row = (int64_t)t.m_idx + lane_base + lane;
+      const bool has_aux = p.epi >= LCASR_EPI_DS;
+      // operands of the epilogue are requested BEFORE the accumulator wait: their latency hides behind the main loop
+      float rv = 0.f;
+      if ((p.epi == LCASR_EPI_EXP2 || p.epi == LCASR_EPI_DS) && row < p.M) rv = p.rowvec[t.b2 * p.sr2 + t.b1 * p.sr1 + row];
+      uint4 ax_nxt[4] = {};
+      if (has_aux) tx_load_aux(ax_nxt, row, t.n_idx, p, t.b1, t.b2);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + acc * BN;
@@ -257,8 +270,12 @@ gemm_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (t.n_idx + c * 32 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_addr + c * 32, r);
+        uint4 ax_cur[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) ax_cur[g] = ax_nxt[g];
+        if (has_aux && c + 1 < BN / 32 && t.n_idx + (c + 1) * 32 < p.N) tx_load_aux(ax_nxt, row, t.n_idx + (c + 1) * 32, p, t.b1, t.b2);
         tmem_wait_ld();
-        tx_store_chunk<TOut>(r, row, t.n_idx + c * 32, p, t.b1, t.b2, out);
+        tx_store_chunk<TOut>(r, ax_cur, rv, row, t.n_idx + c * 32, p, t.b1, t.b2, out);
       }
       tc_fence_before();
       __syncwarp();
@@ -271,6 +288,163 @@ gemm_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---- attention backward, first half: P and dS of one (recording, head) in ONE pass --------------------------
+//   S  = Q K^T,  dP = dO V^T          (two accumulators per tile, K = Dh)
+//   P  = exp2(S * scale*log2e - lse2[row])                         -> bf16 [.., N, Np]
+//   dS = P o (dP - D[row]) * scale                                 -> bf16 [.., N, Np]
+// Same pipeline as gemm_tcx_kernel with 128x128 tiles; a stage holds the Q, K, dO and V tiles (64 KB), TMEM holds
+// 2 x (S | dP) = 512 columns.  With K = Dh <= 128 the tile is epilogue-bound: computing both products per tile
+// halves the number of epilogue passes and removes the re-read of P that a separate dS GEMM needs.
+struct PdsParams {
+  int64_t N;   // tokens (rows and keys)
+  int Dh, Nst, H, nbatch;
+  int64_t ldo, so1, so2;      // P / dS pitch and (head, recording) strides
+  const float* lse;           // [nbatch, H, N] log2-domain
+  const float* dvec;          // [nbatch, H, N]
+  float alpha_p, scale;
+  bf16* P;
+  bf16* dS;
+};
+constexpr int PDS_STAGES = 3, PDS_STAGE_BYTES = 4 * 16384, PDS_SMEM = PDS_STAGES * PDS_STAGE_BYTES + 1024;
+
+__global__ void __launch_bounds__(TX_THREADS, 1)
+attn_bwd_pds_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmV, PdsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * PDS_STAGES + 4];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (PDS_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * PDS_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * PDS_STAGES + 2 + a); };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = (p.Dh + TX_BK - 1) / TX_BK;
+  const int tiles_1d = (int)((p.N + 127) / 128);
+  const int64_t total_tiles = (int64_t)tiles_1d * tiles_1d * p.H * p.nbatch;
+  auto decode = [&](int64_t tile, int& m_idx, int& n_idx, int& h, int& b) {
+    n_idx = (int)(tile % tiles_1d) * 128; tile /= tiles_1d;
+    m_idx = (int)(tile % tiles_1d) * 128; tile /= tiles_1d;
+    h = (int)(tile % p.H); b = (int)(tile / p.H);
+  };
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmDO); prefetch_tensormap(&tmV);
+    for (int s = 0; s < PDS_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int m_idx, n_idx, h, b;
+        decode(tile, m_idx, n_idx, h, b);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_arrive_expect_tx(full_bar(stage), PDS_STAGE_BYTES);
+          const uint32_t s0 = smem_base + stage * PDS_STAGE_BYTES;
+          tma_load_4d(s0, &tmQ, full_bar(stage), kb * TX_BK, m_idx, h, b);
+          tma_load_4d(s0 + 16384, &tmK, full_bar(stage), kb * TX_BK, n_idx, h, b);
+          tma_load_4d(s0 + 32768, &tmDO, full_bar(stage), kb * TX_BK, m_idx, h, b);
+          tma_load_4d(s0 + 49152, &tmV, full_bar(stage), kb * TX_BK, n_idx, h, b);
+          if (++stage == PDS_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_mn(128, 128, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_s = tmem_base + acc * 256, d_dp = d_s + 128;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t s0 = smem_base + stage * PDS_STAGE_BYTES;
+          const uint64_t qd = make_smem_desc_kmajor(s0, 1024, kLayoutSW128), kd = make_smem_desc_kmajor(s0 + 16384, 1024, kLayoutSW128);
+          const uint64_t od = make_smem_desc_kmajor(s0 + 32768, 1024, kLayoutSW128), vd = make_smem_desc_kmajor(s0 + 49152, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < TX_BK / 16; ++k) umma_f16_ss(d_s, qd + 2 * k, kd + 2 * k, idesc, (kb | k) != 0);
+#pragma unroll
+          for (int k = 0; k < TX_BK / 16; ++k) umma_f16_ss(d_dp, od + 2 * k, vd + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(empty_bar(stage));
+          if (++stage == PDS_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int lane_base = (warp & 3) * 32;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int m_idx, n_idx, h, b;
+      decode(tile, m_idx, n_idx, h, b);
+      const int64_t row = (int64_t)m_idx + lane_base + lane;
+      const bool row_ok = row < p.N;
+      float lse = 0.f, dv = 0.f;
+      if (row_ok) {
+        lse = p.lse[((int64_t)b * p.H + h) * p.N + row];
+        dv = p.dvec[((int64_t)b * p.H + h) * p.N + row];
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + acc * 256;
+      const int64_t obase = (int64_t)b * p.so2 + (int64_t)h * p.so1 + row * p.ldo;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col0 = n_idx + c * 32;
+        if (col0 >= p.N) break;
+        uint32_t rs[32], rd[32];
+        tmem_ld_32x32b_x32(t_addr + c * 32, rs);
+        tmem_ld_32x32b_x32(t_addr + 128 + c * 32, rd);
+        tmem_wait_ld();
+        if (row_ok) {
+          const int ngroups = min(4, (p.Nst - col0) >> 3);
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if (g < ngroups) {
+              float pv[8], ds[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float pr = ex2_approx(fmaf(__uint_as_float(rs[8 * g + i]), p.alpha_p, -lse));
+                // the backward consumes P as a bf16 operand: dS uses the same rounded value (like the separate kernels)
+                const float prr = __bfloat162float(__float2bfloat16_rn(pr));
+                pv[i] = pr;
+                ds[i] = prr * (__uint_as_float(rd[8 * g + i]) - dv) * p.scale;
+              }
+              Vec8<bf16>::store(p.P + obase + col0 + 8 * g, pv);
+              Vec8<bf16>::store(p.dS + obase + col0 + 8 * g, ds);
+            }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -398,4 +572,37 @@ extern "C" int lcasr_gemm_ex(const lcasr_gemm_ex_args* gp, void* stream) {
   if (g.out_dtype == LCASR_BF16)
     return wide ? dispatch_major<256, bf16>(g, p, st) : dispatch_major<128, bf16>(g, p, st);
   return wide ? dispatch_major<256, float>(g, p, st) : dispatch_major<128, float>(g, p, st);
+}
+
+// P and dS of the attention backward in one pass (see attn_bwd_pds_kernel).  q, k, v, dO: bf16 [nb, N, H, Dh];
+// lse2, dvec: fp32 [nb, H, N]; P, dS: bf16 [nb, H, N, Np] with Np = N rounded up to 8.
+extern "C" int lcasr_attention_bwd_pds(const void* q, const void* k, const void* v, const void* d_out, const float* lse2,
+                                       const float* dvec, int nb, int64_t N, int H, int Dh, void* P, void* dS, void* stream) {
+  LCASR_CHECK_ARG(q && k && v && d_out && lse2 && dvec && P && dS, "attention_bwd_pds: NULL argument");
+  LCASR_CHECK_ARG(nb > 0 && N > 0 && H > 0 && Dh > 0 && Dh % 8 == 0, "attention_bwd_pds: bad shape");
+  LCASR_CHECK_ARG(N < ((int64_t)1 << 30), "attention_bwd_pds: N too large");
+  const int64_t d = (int64_t)H * Dh, Np = (N + 7) / 8 * 8;
+  CUtensorMap tmQ, tmK, tmDO, tmV;
+  LCASR_TRY(make_tmap_4d(&tmQ, q, (uint64_t)N, (uint64_t)Dh, d, H, Dh, nb, N * d, 128, TX_BK));
+  LCASR_TRY(make_tmap_4d(&tmK, k, (uint64_t)N, (uint64_t)Dh, d, H, Dh, nb, N * d, 128, TX_BK));
+  LCASR_TRY(make_tmap_4d(&tmDO, d_out, (uint64_t)N, (uint64_t)Dh, d, H, Dh, nb, N * d, 128, TX_BK));
+  LCASR_TRY(make_tmap_4d(&tmV, v, (uint64_t)N, (uint64_t)Dh, d, H, Dh, nb, N * d, 128, TX_BK));
+  static bool attr_set = false;
+  if (!attr_set) {
+    LCASR_CUDA(cudaFuncSetAttribute(attn_bwd_pds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PDS_SMEM));
+    attr_set = true;
+  }
+  PdsParams p;
+  p.N = N; p.Dh = Dh; p.Nst = (int)Np; p.H = H; p.nbatch = nb;
+  p.ldo = Np; p.so1 = N * Np; p.so2 = (int64_t)H * N * Np;
+  p.lse = lse2; p.dvec = dvec;
+  p.scale = 1.0f / sqrtf((float)Dh);
+  p.alpha_p = p.scale * 1.4426950408889634f;
+  p.P = (bf16*)P; p.dS = (bf16*)dS;
+  const int64_t t1 = ceil_div(N, 128);
+  const int64_t tiles = t1 * t1 * H * nb;
+  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+  attn_bwd_pds_kernel<<<grid, TX_THREADS, PDS_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmDO, tmV, p);
+  LCASR_LAUNCH_CHECK();
+  return 0;
 }

@@ -69,11 +69,13 @@ __global__ void __launch_bounds__(256) subsample_conv0_kernel(const float* __res
 }
 
 // ---- depthwise Conv2d(C,3x3,s2,p1,groups=C), channels-last ------------------------------------
+// One CTA = kDwTB output time rows of one recording; all index arithmetic is 32-bit (the flat 64-bit
+// div/mod chain of a grid-stride loop cost more than the memory traffic: 775 us -> see DESIGN.md).
+constexpr int kDwTB = 4;
 template <typename T>
 __global__ void __launch_bounds__(256) subsample_dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w,
                                                                const float* __restrict__ bias, int64_t Tin, int Fin,
-                                                               int C, int64_t Tout, int Fout, int64_t total_vec,
-                                                               T* __restrict__ out) {
+                                                               int C, int64_t Tout, int Fout, T* __restrict__ out) {
   const int cgroups = C / 8;             // divides blockDim.x, so a thread's channel group is fixed
   const int cg = threadIdx.x % cgroups;
   float wr[8][9], br[8];
@@ -83,31 +85,34 @@ __global__ void __launch_bounds__(256) subsample_dwconv_kernel(const T* __restri
 #pragma unroll
     for (int k = 0; k < 9; ++k) wr[c][k] = w[(cg * 8 + c) * 9 + k];
   }
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total_vec;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t pos = idx / cgroups;
-    int fo = (int)(pos % Fout);
-    int64_t bt = pos / Fout;
-    int64_t to = bt % Tout;
-    int64_t b = bt / Tout;
+  const int64_t b = blockIdx.y;
+  const int64_t t0 = (int64_t)blockIdx.x * kDwTB;
+  const int per_row = Fout * cgroups;
+  const T* inb = in + b * Tin * Fin * C;
+  T* outb = out + b * Tout * Fout * C;
+  for (int i = threadIdx.x; i < kDwTB * per_row; i += blockDim.x) {
+    const int tl = i / per_row;
+    const int fo = (i - tl * per_row) / cgroups;
+    const int64_t to = t0 + tl;
+    if (to >= Tout) break;
     float acc[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = br[c];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      int64_t ti = 2 * to - 1 + i;
+    for (int ii = 0; ii < 3; ++ii) {
+      const int64_t ti = 2 * to - 1 + ii;
       if (ti < 0 || ti >= Tin) continue;
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        int fi = 2 * fo - 1 + j;
+        const int fi = 2 * fo - 1 + j;
         if (fi < 0 || fi >= Fin) continue;
         float v[8];
-        Vec8<T>::load(in + (((b * Tin + ti) * Fin + fi) * C + cg * 8), v);
+        Vec8<T>::load(inb + ((ti * Fin + fi) * C + cg * 8), v);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = fmaf(wr[c][i * 3 + j], v[c], acc[c]);
+        for (int c = 0; c < 8; ++c) acc[c] = fmaf(wr[c][ii * 3 + j], v[c], acc[c]);
       }
     }
-    Vec8<T>::store(out + (pos * C + cg * 8), acc);
+    Vec8<T>::store(outb + ((to * Fout + fo) * C + cg * 8), acc);
   }
 }
 
@@ -235,16 +240,13 @@ extern "C" int lcasr_subsample_dwconv(const void* in, int dtype, const float* w,
   LCASR_CHECK_ARG(C % 8 == 0 && 256 % (C / 8) == 0, "subsample_dwconv: C=%d must be a multiple of 8 with 256 %% (C/8) == 0", C);
   const int64_t Tout = (Tin - 1) / 2 + 1;
   const int Fout = (Fin - 1) / 2 + 1;
-  const int64_t total_vec = (int64_t)B * Tout * Fout * (C / 8);
-  int64_t blocks = ceil_div(total_vec, 256);
-  if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
+  LCASR_CHECK_ARG(B <= 65535 && ceil_div(Tout, kDwTB) <= 0x7fffffff, "subsample_dwconv: grid too large");
+  dim3 grid((unsigned)ceil_div(Tout, kDwTB), (unsigned)B);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == LCASR_BF16)
-    subsample_dwconv_kernel<bf16><<<(unsigned)blocks, 256, 0, st>>>((const bf16*)in, w, b, Tin, Fin, C, Tout, Fout,
-                                                                     total_vec, (bf16*)out);
+    subsample_dwconv_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)in, w, b, Tin, Fin, C, Tout, Fout, (bf16*)out);
   else
-    subsample_dwconv_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)in, w, b, Tin, Fin, C, Tout, Fout,
-                                                                      total_vec, (float*)out);
+    subsample_dwconv_kernel<float><<<grid, 256, 0, st>>>((const float*)in, w, b, Tin, Fin, C, Tout, Fout, (float*)out);
   LCASR_LAUNCH_CHECK();
   return 0;
 }

@@ -15,9 +15,16 @@ __device__ __forceinline__ float silu_grad_sb(float x) {
 }
 
 // din[b,ti,fi,:] = sum_{i,j : ti = 2*to-1+i, fi = 2*fo-1+j} dout[b,to,fo,:] * w[:, i*3+j]
+// Stride 2 makes the tap pattern depend only on the parity of (ti, fi), so a thread produces one 2x2 block of
+// input positions (rows 2a, 2a+1; columns 2e, 2e+1) from the four output gradients G[a..a+1][e..e+1]:
+//   din[2a  ][2e  ] = G00 w11                 din[2a  ][2e+1] = G00 w12 + G01 w10
+//   din[2a+1][2e  ] = G00 w21 + G10 w01       din[2a+1][2e+1] = G00 w22 + G01 w20 + G10 w02 + G11 w00
+// 4 unconditional 16-byte loads and 4 stores per thread (instead of 9 predicated gathers per output), one CTA per
+// kBdTB row pairs of one recording, 32-bit index arithmetic.
+constexpr int kBdTB = 2;
 __global__ void __launch_bounds__(256) subsample_dwconv_bwd_data_kernel(const bf16* __restrict__ dout, const float* __restrict__ w,
                                                                         int64_t Tin, int Fin, int C, int64_t Tout, int Fout,
-                                                                        int64_t total_vec, bf16* __restrict__ din) {
+                                                                        bf16* __restrict__ din) {
   const int cgroups = C / 8;
   const int cg = threadIdx.x % cgroups;
   float wr[8][9];
@@ -25,39 +32,59 @@ __global__ void __launch_bounds__(256) subsample_dwconv_bwd_data_kernel(const bf
   for (int c = 0; c < 8; ++c)
 #pragma unroll
     for (int k = 0; k < 9; ++k) wr[c][k] = w[(cg * 8 + c) * 9 + k];
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total_vec; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t pos = idx / cgroups;
-    const int fi = (int)(pos % Fin);
-    const int64_t bt = pos / Fin;
-    const int64_t ti = bt % Tin, b = bt / Tin;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int64_t b = blockIdx.y;
+  const int64_t a0 = (int64_t)blockIdx.x * kBdTB;
+  const int Fh = (Fin + 1) / 2;            // column pairs
+  const int per_row = Fh * cgroups;
+  const bf16* doutb = dout + b * Tout * Fout * C;
+  bf16* dinb = din + b * Tin * Fin * C;
+  for (int idx = threadIdx.x; idx < kBdTB * per_row; idx += blockDim.x) {
+    const int al = idx / per_row;
+    const int e = (idx - al * per_row) / cgroups;
+    const int64_t a = a0 + al;
+    if (2 * a >= Tin) break;
+    float g00[8], g01[8], g10[8], g11[8];
+    const bool r1 = a + 1 < Tout, c1 = e + 1 < Fout, r0 = a < Tout, c0 = e < Fout;
+    auto ld = [&](float (&g)[8], bool ok, int64_t to, int fo) {
+      if (ok) Vec8<bf16>::load(doutb + ((to * Fout + fo) * C + cg * 8), g);
+      else {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int64_t t2 = ti + 1 - i;
-      if (t2 < 0 || (t2 & 1)) continue;
-      const int64_t to = t2 >> 1;
-      if (to >= Tout) continue;
+        for (int c = 0; c < 8; ++c) g[c] = 0.f;
+      }
+    };
+    ld(g00, r0 && c0, a, e); ld(g01, r0 && c1, a, e + 1); ld(g10, r1 && c0, a + 1, e); ld(g11, r1 && c1, a + 1, e + 1);
+    float o[8];
+    const int64_t ti = 2 * a;
+    const int fi = 2 * e;
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int f2 = fi + 1 - j;
-        if (f2 < 0 || (f2 & 1)) continue;
-        const int fo = f2 >> 1;
-        if (fo >= Fout) continue;
-        float g[8];
-        Vec8<bf16>::load(dout + (((b * Tout + to) * Fout + fo) * C + cg * 8), g);
+    for (int c = 0; c < 8; ++c) o[c] = g00[c] * wr[c][4];
+    Vec8<bf16>::store(dinb + ((ti * Fin + fi) * C + cg * 8), o);
+    if (fi + 1 < Fin) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = fmaf(wr[c][i * 3 + j], g[c], acc[c]);
+      for (int c = 0; c < 8; ++c) o[c] = fmaf(g00[c], wr[c][5], g01[c] * wr[c][3]);
+      Vec8<bf16>::store(dinb + ((ti * Fin + fi + 1) * C + cg * 8), o);
+    }
+    if (ti + 1 < Tin) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o[c] = fmaf(g00[c], wr[c][7], g10[c] * wr[c][1]);
+      Vec8<bf16>::store(dinb + (((ti + 1) * Fin + fi) * C + cg * 8), o);
+      if (fi + 1 < Fin) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          o[c] = fmaf(g00[c], wr[c][8], fmaf(g01[c], wr[c][6], fmaf(g10[c], wr[c][2], g11[c] * wr[c][0])));
+        Vec8<bf16>::store(dinb + (((ti + 1) * Fin + fi + 1) * C + cg * 8), o);
       }
     }
-    Vec8<bf16>::store(din + (pos * C + cg * 8), acc);
   }
 }
 
 // dw[c, i*3+j] += sum dout[b,to,fo,c] * in[b,2to-1+i,2fo-1+j,c] ; db[c] += sum dout
+// CTAs stride over blocks of kBwTB output rows (grid.x of them per recording); register accumulators, one
+// shared-memory reduction and C*10 global atomics per CTA.
+constexpr int kBwTB = 4;
 __global__ void __launch_bounds__(256) subsample_dwconv_bwd_weight_kernel(const bf16* __restrict__ in, const bf16* __restrict__ dout,
                                                                           int64_t Tin, int Fin, int C, int64_t Tout, int Fout,
-                                                                          int64_t total_vec, float* __restrict__ dw,
-                                                                          float* __restrict__ db) {
+                                                                          float* __restrict__ dw, float* __restrict__ db) {
   extern __shared__ float sacc[];  // [C][10]
   for (int i = threadIdx.x; i < C * 10; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
@@ -70,27 +97,35 @@ __global__ void __launch_bounds__(256) subsample_dwconv_bwd_weight_kernel(const 
 #pragma unroll
     for (int k = 0; k < 9; ++k) aw[c][k] = 0.f;
   }
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total_vec; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t pos = idx / cgroups;
-    const int fo = (int)(pos % Fout);
-    const int64_t bt = pos / Fout;
-    const int64_t to = bt % Tout, b = bt / Tout;
-    float g[8];
-    Vec8<bf16>::load(dout + (pos * C + cg * 8), g);
+  const int64_t b = blockIdx.y;
+  const int per_row = Fout * cgroups;
+  const bf16* inb = in + b * Tin * Fin * C;
+  const bf16* doutb = dout + b * Tout * Fout * C;
+  const int64_t nblk = (Tout + kBwTB - 1) / kBwTB;
+  for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const int64_t t0 = blk * kBwTB;
+    for (int idx = threadIdx.x; idx < kBwTB * per_row; idx += blockDim.x) {
+      const int tl = idx / per_row;
+      const int fo = (idx - tl * per_row) / cgroups;
+      const int64_t to = t0 + tl;
+      if (to >= Tout) break;
+      float g[8];
+      Vec8<bf16>::load(doutb + ((to * Fout + fo) * C + cg * 8), g);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) ab[c] += g[c];
+      for (int c = 0; c < 8; ++c) ab[c] += g[c];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int64_t ti = 2 * to - 1 + i;
-      if (ti < 0 || ti >= Tin) continue;
+      for (int i = 0; i < 3; ++i) {
+        const int64_t ti = 2 * to - 1 + i;
+        if (ti < 0 || ti >= Tin) continue;
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int fi = 2 * fo - 1 + j;
-        if (fi < 0 || fi >= Fin) continue;
-        float v[8];
-        Vec8<bf16>::load(in + (((b * Tin + ti) * Fin + fi) * C + cg * 8), v);
+        for (int j = 0; j < 3; ++j) {
+          const int fi = 2 * fo - 1 + j;
+          if (fi < 0 || fi >= Fin) continue;
+          float v[8];
+          Vec8<bf16>::load(inb + ((ti * Fin + fi) * C + cg * 8), v);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) aw[c][i * 3 + j] = fmaf(g[c], v[c], aw[c][i * 3 + j]);
+          for (int c = 0; c < 8; ++c) aw[c][i * 3 + j] = fmaf(g[c], v[c], aw[c][i * 3 + j]);
+        }
       }
     }
   }
@@ -109,8 +144,9 @@ __global__ void __launch_bounds__(256) subsample_dwconv_bwd_weight_kernel(const 
 }
 
 // conv0 (1->C, 3x3, s2, p1) + SiLU: gradients of w0 [C,9] and b0 [C] from ds1 = dL/d(silu output) [B,T1,F1,C].
-// Same tiling as subsample_conv0_kernel: one (batch, 16 output frames) tile per CTA, the input patch in shared
-// memory, each thread owns 8 channels.
+// Same tiling as subsample_conv0_kernel (16 output frames per tile, the input patch in shared memory, each thread
+// owns 8 channels); a CTA walks several tiles and keeps its partial sums in registers, so the reduction costs one
+// shared-memory pass and C*10 global atomics per CTA, not per tile.
 constexpr int kC0bTT = 16;
 __global__ void __launch_bounds__(256) subsample_conv0_bwd_kernel(const float* __restrict__ spec, const float* __restrict__ w,
                                                                   const float* __restrict__ bias, const bf16* __restrict__ ds1,
@@ -122,54 +158,61 @@ __global__ void __launch_bounds__(256) subsample_conv0_bwd_kernel(const float* _
   float* s_in = smem;
   float* sacc = smem + rows * FW;
   const int b = blockIdx.y;
-  const int64_t t1_0 = (int64_t)blockIdx.x * kC0bTT;
-  const int64_t t_in0 = 2 * t1_0 - 1;
-  for (int idx = threadIdx.x; idx < rows * FW; idx += blockDim.x) {
-    const int f = idx / rows - 1;
-    const int r = idx % rows;
-    const int64_t t = t_in0 + r;
-    float v = 0.f;
-    if (f >= 0 && f < F && t >= 0 && t < T) v = spec[((int64_t)b * F + f) * T + t];
-    s_in[r * FW + (f + 1)] = v;
-  }
   for (int i = threadIdx.x; i < C * 10; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
   const int cgroups = C / 8;
   const int pos_stride = blockDim.x / cgroups;
-  if ((int)threadIdx.x < pos_stride * cgroups) {
-    const int cg = threadIdx.x % cgroups;
-    const int pos_lane = threadIdx.x / cgroups;
-    float wr[8][9], br[8], aw[8][9], ab[8];
+  const bool worker = (int)threadIdx.x < pos_stride * cgroups;
+  const int cg = threadIdx.x % cgroups;
+  const int pos_lane = threadIdx.x / cgroups;
+  float wr[8][9], br[8], aw[8][9], ab[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      br[c] = bias[cg * 8 + c];
-      ab[c] = 0.f;
+  for (int c = 0; c < 8; ++c) {
+    br[c] = bias[cg * 8 + c];
+    ab[c] = 0.f;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) { wr[c][k] = w[(cg * 8 + c) * 9 + k]; aw[c][k] = 0.f; }
+    for (int k = 0; k < 9; ++k) { wr[c][k] = w[(cg * 8 + c) * 9 + k]; aw[c][k] = 0.f; }
+  }
+  const int64_t ntiles = (T1 + kC0bTT - 1) / kC0bTT;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t t1_0 = tile * kC0bTT;
+    const int64_t t_in0 = 2 * t1_0 - 1;
+    __syncthreads();  // the previous tile's patch is no longer read
+    for (int idx = threadIdx.x; idx < rows * FW; idx += blockDim.x) {
+      const int f = idx / rows - 1;
+      const int r = idx % rows;
+      const int64_t t = t_in0 + r;
+      float v = 0.f;
+      if (f >= 0 && f < F && t >= 0 && t < T) v = spec[((int64_t)b * F + f) * T + t];
+      s_in[r * FW + (f + 1)] = v;
     }
-    const int npos = kC0bTT * F1;
-    for (int p = pos_lane; p < npos; p += pos_stride) {
-      const int tt = p / F1, f1 = p % F1;
-      const int64_t t1 = t1_0 + tt;
-      if (t1 >= T1) break;
-      float in[9];
+    __syncthreads();
+    if (worker) {
+      const int npos = kC0bTT * F1;
+      for (int p = pos_lane; p < npos; p += pos_stride) {
+        const int tt = p / F1, f1 = p % F1;
+        const int64_t t1 = t1_0 + tt;
+        if (t1 >= T1) break;
+        float in[9];
 #pragma unroll
-      for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) in[i * 3 + j] = s_in[(2 * tt + i) * FW + (2 * f1 + j)];
-      float g[8];
-      Vec8<bf16>::load(ds1 + ((((int64_t)b * T1 + t1) * F1 + f1) * C + cg * 8), g);
+          for (int j = 0; j < 3; ++j) in[i * 3 + j] = s_in[(2 * tt + i) * FW + (2 * f1 + j)];
+        float g[8];
+        Vec8<bf16>::load(ds1 + ((((int64_t)b * T1 + t1) * F1 + f1) * C + cg * 8), g);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float a = br[c];
+        for (int c = 0; c < 8; ++c) {
+          float a = br[c];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) a = fmaf(wr[c][k], in[k], a);
-        const float ga = g[c] * silu_grad_sb(a);
-        ab[c] += ga;
+          for (int k = 0; k < 9; ++k) a = fmaf(wr[c][k], in[k], a);
+          const float ga = g[c] * silu_grad_sb(a);
+          ab[c] += ga;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) aw[c][k] = fmaf(ga, in[k], aw[c][k]);
+          for (int k = 0; k < 9; ++k) aw[c][k] = fmaf(ga, in[k], aw[c][k]);
+        }
       }
     }
+  }
+  if (worker) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
 #pragma unroll
@@ -197,11 +240,10 @@ extern "C" int lcasr_subsample_dwconv_bwd_data(const void* dout, const float* w,
   LCASR_CHECK_ARG(cgroups_ok(C), "subsample_dwconv_bwd_data: C=%d: C/8 must divide 256", C);
   const int64_t Tout = (Tin - 1) / 2 + 1;
   const int Fout = (Fin - 1) / 2 + 1;
-  const int64_t total = (int64_t)B * Tin * Fin * (C / 8);
-  int64_t g = ceil_div(total, 256);
-  if (g > (int64_t)kNumSMs * 32) g = (int64_t)kNumSMs * 32;
-  subsample_dwconv_bwd_data_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>((const bf16*)dout, w, Tin, Fin, C, Tout, Fout,
-                                                                                 total, (bf16*)din);
+  LCASR_CHECK_ARG(B <= 65535 && ceil_div(Tin, 2 * kBdTB) <= 0x7fffffff, "subsample_dwconv_bwd_data: grid too large");
+  dim3 grid((unsigned)ceil_div(ceil_div(Tin, 2), kBdTB), (unsigned)B);
+  subsample_dwconv_bwd_data_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dout, w, Tin, Fin, C, Tout, Fout,
+                                                                          (bf16*)din);
   LCASR_LAUNCH_CHECK();
   return 0;
 }
@@ -212,11 +254,12 @@ extern "C" int lcasr_subsample_dwconv_bwd_weight(const void* in, const void* dou
   LCASR_CHECK_ARG(cgroups_ok(C) && C * 40 <= 48 * 1024, "subsample_dwconv_bwd_weight: C=%d unsupported", C);
   const int64_t Tout = (Tin - 1) / 2 + 1;
   const int Fout = (Fin - 1) / 2 + 1;
-  const int64_t total = (int64_t)B * Tout * Fout * (C / 8);
-  int64_t g = ceil_div(total, 256);
-  if (g > (int64_t)kNumSMs * 4) g = (int64_t)kNumSMs * 4;
-  subsample_dwconv_bwd_weight_kernel<<<(unsigned)g, 256, (size_t)C * 40, (cudaStream_t)stream>>>(
-      (const bf16*)in, (const bf16*)dout, Tin, Fin, C, Tout, Fout, total, dw, db);
+  LCASR_CHECK_ARG(B <= 65535, "subsample_dwconv_bwd_weight: batch too large");
+  int64_t gx = ceil_div((int64_t)kNumSMs * 8, B);  // ~8 CTAs per SM in total
+  if (gx > ceil_div(Tout, kBwTB)) gx = ceil_div(Tout, kBwTB);
+  dim3 grid((unsigned)gx, (unsigned)B);
+  subsample_dwconv_bwd_weight_kernel<<<grid, 256, (size_t)C * 40, (cudaStream_t)stream>>>(
+      (const bf16*)in, (const bf16*)dout, Tin, Fin, C, Tout, Fout, dw, db);
   LCASR_LAUNCH_CHECK();
   return 0;
 }
@@ -229,7 +272,10 @@ extern "C" int lcasr_subsample_conv0_bwd(const float* spec, const float* w, cons
   const int F1 = (F - 1) / 2 + 1;
   const size_t smem = ((size_t)(2 * kC0bTT + 1) * (F + 2) + (size_t)C * 10) * sizeof(float);
   LCASR_CHECK_ARG(smem <= 48 * 1024, "subsample_conv0_bwd: F=%d, C=%d need too much shared memory", F, C);
-  dim3 grid((unsigned)ceil_div(T1, kC0bTT), (unsigned)B);
+  LCASR_CHECK_ARG(B <= 65535, "subsample_conv0_bwd: batch too large");
+  int64_t gx = ceil_div((int64_t)kNumSMs * 4, B);  // ~4 CTAs per SM in total, each walking several tiles
+  if (gx > ceil_div(T1, kC0bTT)) gx = ceil_div(T1, kC0bTT);
+  dim3 grid((unsigned)gx, (unsigned)B);
   subsample_conv0_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(spec, w, b, (const bf16*)ds1, F, T, C, T1, F1, dw, db);
   LCASR_LAUNCH_CHECK();
   return 0;

@@ -314,6 +314,125 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const float* __restrict__
   }
 }
 
+// d == NE*32 (NE a multiple of 4) variant: lane l owns columns {128*j + 4*l .. +3}, j < NE/4, for EVERY row it
+// visits, so the row (x, dy) lives in registers (128-bit loads), and the parameter-gradient partial sums are
+// per-lane register accumulators reduced through shared memory once per CTA (the generic kernel above spends its
+// time in 2*d shared-memory atomics per row).  HBM-bound: reads x (4 B) + dy (e) and reads+writes dx (8 B)
+// per element.
+template <int NE, typename TDy>
+__global__ void __launch_bounds__(256) norm_bwd_reg_kernel(const float* __restrict__ x, const TDy* __restrict__ dy,
+                                                           const float* __restrict__ w, int64_t M, float eps, int kind,
+                                                           int accumulate, float* __restrict__ dx, float* __restrict__ dw,
+                                                           float* __restrict__ db) {
+  constexpr int d = NE * 32, NV = NE / 4;
+  extern __shared__ float sacc[];  // [2][d]
+  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  float4 wv[NV], aw[NV], ab[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    wv[j] = reinterpret_cast<const float4*>(w)[lane + 32 * j];
+    aw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += (int64_t)gridDim.x * wpb) {
+    float4 xv[NV], gv[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      xv[j] = reinterpret_cast<const float4*>(x + row * d)[lane + 32 * j];
+      if constexpr (sizeof(TDy) == 4) {
+        gv[j] = reinterpret_cast<const float4*>(dy + row * d)[lane + 32 * j];
+      } else {
+        const uint2 u = reinterpret_cast<const uint2*>(dy + row * d)[lane + 32 * j];
+        const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+        const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        gv[j] = make_float4(f0.x, f0.y, f1.x, f1.y);
+      }
+    }
+    float4* dxr = reinterpret_cast<float4*>(dx + row * d);
+    if (kind == LCASR_NORM_LAYERNORM) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) s += (xv[j].x + xv[j].y) + (xv[j].z + xv[j].w);
+      const float mean = warp_sum(s) * (1.0f / d);
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        xv[j].x -= mean; xv[j].y -= mean; xv[j].z -= mean; xv[j].w -= mean;
+        q += (xv[j].x * xv[j].x + xv[j].y * xv[j].y) + (xv[j].z * xv[j].z + xv[j].w * xv[j].w);
+      }
+      const float rstd = rsqrtf(warp_sum(q) * (1.0f / d) + eps);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {  // xv becomes xhat
+        xv[j].x *= rstd; xv[j].y *= rstd; xv[j].z *= rstd; xv[j].w *= rstd;
+        const float g0 = gv[j].x * wv[j].x, g1 = gv[j].y * wv[j].y, g2 = gv[j].z * wv[j].z, g3 = gv[j].w * wv[j].w;
+        s1 += (g0 + g1) + (g2 + g3);
+        s2 += (g0 * xv[j].x + g1 * xv[j].y) + (g2 * xv[j].z + g3 * xv[j].w);
+      }
+      s1 = warp_sum(s1) * (1.0f / d);
+      s2 = warp_sum(s2) * (1.0f / d);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        float4 v;
+        v.x = rstd * (gv[j].x * wv[j].x - s1 - xv[j].x * s2);
+        v.y = rstd * (gv[j].y * wv[j].y - s1 - xv[j].y * s2);
+        v.z = rstd * (gv[j].z * wv[j].z - s1 - xv[j].z * s2);
+        v.w = rstd * (gv[j].w * wv[j].w - s1 - xv[j].w * s2);
+        if (accumulate) {
+          const float4 o = dxr[lane + 32 * j];
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        dxr[lane + 32 * j] = v;
+        aw[j].x = fmaf(gv[j].x, xv[j].x, aw[j].x); aw[j].y = fmaf(gv[j].y, xv[j].y, aw[j].y);
+        aw[j].z = fmaf(gv[j].z, xv[j].z, aw[j].z); aw[j].w = fmaf(gv[j].w, xv[j].w, aw[j].w);
+        ab[j].x += gv[j].x; ab[j].y += gv[j].y; ab[j].z += gv[j].z; ab[j].w += gv[j].w;
+      }
+    } else {
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) q += (xv[j].x * xv[j].x + xv[j].y * xv[j].y) + (xv[j].z * xv[j].z + xv[j].w * xv[j].w);
+      const float rms = sqrtf(warp_sum(q)) * rsqrtf((float)d);
+      const float inv = 1.0f / (rms + eps);
+      float s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        s2 += (gv[j].x * wv[j].x * xv[j].x + gv[j].y * wv[j].y * xv[j].y) + (gv[j].z * wv[j].z * xv[j].z + gv[j].w * wv[j].w * xv[j].w);
+      s2 = warp_sum(s2);
+      const float k = rms > 0.f ? s2 * inv * inv / ((float)d * rms) : 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        float4 v;
+        v.x = gv[j].x * wv[j].x * inv - k * xv[j].x;
+        v.y = gv[j].y * wv[j].y * inv - k * xv[j].y;
+        v.z = gv[j].z * wv[j].z * inv - k * xv[j].z;
+        v.w = gv[j].w * wv[j].w * inv - k * xv[j].w;
+        if (accumulate) {
+          const float4 o = dxr[lane + 32 * j];
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        dxr[lane + 32 * j] = v;
+        aw[j].x = fmaf(gv[j].x, xv[j].x * inv, aw[j].x); aw[j].y = fmaf(gv[j].y, xv[j].y * inv, aw[j].y);
+        aw[j].z = fmaf(gv[j].z, xv[j].z * inv, aw[j].z); aw[j].w = fmaf(gv[j].w, xv[j].w * inv, aw[j].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = (lane + 32 * j) * 4;
+    atomicAdd(sacc + c, aw[j].x); atomicAdd(sacc + c + 1, aw[j].y); atomicAdd(sacc + c + 2, aw[j].z); atomicAdd(sacc + c + 3, aw[j].w);
+    atomicAdd(sacc + d + c, ab[j].x); atomicAdd(sacc + d + c + 1, ab[j].y); atomicAdd(sacc + d + c + 2, ab[j].z);
+    atomicAdd(sacc + d + c + 3, ab[j].w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    atomicAdd(dw + i, sacc[i]);
+    if (db) atomicAdd(db + i, sacc[d + i]);
+  }
+}
+
 // ---- depthwise Conv1d over tokens, channels-last [B,N,d] bf16, register sliding window ------------------------
 // MODE 0: out = conv(in, w) + b, and (if sum != NULL) per-channel sum / sum of squares of out (BatchRenorm
 //         training statistics, batchrenorm.py:67-68)
@@ -652,6 +771,22 @@ extern "C" int lcasr_layernorm_bwd(const float* x, const void* dy, int dy_dtype,
   LCASR_CHECK_ARG(smem <= 48 * 1024, "layernorm_bwd: d=%d too wide", d);
   const int64_t want = ceil_div(M, 8);
   const unsigned grid = (unsigned)(want < 2 * kNumSMs ? want : 2 * kNumSMs);
+  const bool al16 = (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)weight) & 15) == 0;
+#define LCASR_NB_CASE(NE)                                                                                                  \
+  case NE * 32:                                                                                                            \
+    if (dy_dtype == LCASR_BF16)                                                                                            \
+      norm_bwd_reg_kernel<NE, bf16><<<grid, 256, smem, ST>>>(x, (const bf16*)dy, weight, M, eps, kind, accumulate, dx, dweight, dbias); \
+    else                                                                                                                   \
+      norm_bwd_reg_kernel<NE, float><<<grid, 256, smem, ST>>>(x, (const float*)dy, weight, M, eps, kind, accumulate, dx, dweight, dbias); \
+    LCASR_LAUNCH_CHECK();                                                                                                  \
+    return 0;
+  if (al16) {
+    switch (d) {
+      LCASR_NB_CASE(4) LCASR_NB_CASE(8) LCASR_NB_CASE(16) LCASR_NB_CASE(24) LCASR_NB_CASE(32)  // wider rows: generic kernel
+      default: break;
+    }
+  }
+#undef LCASR_NB_CASE
   if (dy_dtype == LCASR_BF16)
     norm_bwd_kernel<bf16><<<grid, 256, smem, ST>>>(x, (const bf16*)dy, weight, M, d, eps, kind, accumulate, dx, dweight, dbias);
   else

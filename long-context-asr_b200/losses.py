@@ -12,6 +12,12 @@ class _CTCFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, lp_bnv, targets, input_lengths, target_lengths, blank):
         need_grad = lp_bnv.requires_grad
+        ctx.concurrent = need_grad and 2 * targets.shape[1] + 1 <= 4096
+        if ctx.concurrent:  # alpha and beta in one launch: the backward is only the class scatter
+            nll, alpha, beta = ops.ctc_loss_fwd_ab(lp_bnv, targets, input_lengths, target_lengths, blank)
+            ctx.save_for_backward(lp_bnv, targets, input_lengths, target_lengths, nll, alpha, beta)
+            ctx.blank = blank
+            return nll
         nll, alpha = ops.ctc_loss_fwd(lp_bnv, targets, input_lengths, target_lengths, blank, keep_alpha=need_grad)
         if need_grad:
             ctx.save_for_backward(lp_bnv, targets, input_lengths, target_lengths, nll, alpha)
@@ -20,6 +26,11 @@ class _CTCFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_nll):
+        if ctx.concurrent:
+            lp_bnv, targets, input_lengths, target_lengths, nll, alpha, beta = ctx.saved_tensors
+            grad = ops.ctc_loss_grad(lp_bnv, targets, input_lengths, target_lengths, ctx.blank, nll,
+                                     grad_nll.to(torch.float32).contiguous(), alpha, beta)
+            return grad, None, None, None, None
         lp_bnv, targets, input_lengths, target_lengths, nll, alpha = ctx.saved_tensors
         grad = ops.ctc_loss_bwd(lp_bnv, targets, input_lengths, target_lengths, ctx.blank, nll,
                                 grad_nll.to(torch.float32).contiguous(), alpha)

@@ -79,7 +79,8 @@ def gemm(a, w, bias=None, act=L.ACT_NONE, resid=None, alpha=1.0, out_dtype=None,
     if out is None:
         out = torch.empty(M, N, dtype=out_dtype, device=a.device)
     L.call("lcasr_gemm", L.ptr(a), L.ptr(w), L.dtype_code(a.dtype), M, N, K, L.ptr(bias), act, L.ptr(resid),
-           float(alpha), L.ptr(out), L.dtype_code(out_dtype), impl, _s())
+           float(alpha), L.ptr(out), L.dtype_code(out_dtype), impl, _s(),
+           tag=f"[{M}x{N}x{K} out={'f32' if out_dtype == torch.float32 else 'bf16'}]" if L.TIMING_TAGS else "")
     return out
 
 
@@ -195,5 +196,28 @@ def ctc_loss_bwd(log_probs, targets, input_lengths, target_lengths, blank: int, 
     beta = torch.empty_like(alpha)
     grad = torch.empty_like(log_probs)
     L.call("lcasr_ctc_loss_bwd", L.ptr(log_probs), B, N, V, L.ptr(targets), S, L.ptr(input_lengths), L.ptr(target_lengths),
+           int(blank), L.ptr(nll), L.ptr(grad_nll), L.ptr(alpha), L.ptr(beta), L.ptr(grad), _s())
+    return grad
+
+
+def ctc_loss_fwd_ab(log_probs, targets, input_lengths, target_lengths, blank: int):
+    """alpha and beta recursions concurrently (training): returns (nll [B], alpha, beta [B,N,2S+1])."""
+    _cuda(log_probs, targets, input_lengths, target_lengths)
+    B, N, V = log_probs.shape
+    S = targets.shape[1]
+    nll = torch.empty(B, dtype=torch.float32, device=log_probs.device)
+    alpha = torch.empty(B, N, 2 * S + 1, dtype=torch.float32, device=log_probs.device)
+    beta = torch.empty_like(alpha)
+    L.call("lcasr_ctc_loss_fwd_ab", L.ptr(log_probs), B, N, V, L.ptr(targets), S, L.ptr(input_lengths), L.ptr(target_lengths),
+           int(blank), L.ptr(nll), L.ptr(alpha), L.ptr(beta), _s())
+    return nll, alpha, beta
+
+
+def ctc_loss_grad(log_probs, targets, input_lengths, target_lengths, blank: int, nll, grad_nll, alpha, beta):
+    _cuda(log_probs, targets, input_lengths, target_lengths, nll, grad_nll, alpha, beta)
+    B, N, V = log_probs.shape
+    S = targets.shape[1]
+    grad = torch.empty_like(log_probs)
+    L.call("lcasr_ctc_loss_grad", L.ptr(log_probs), B, N, V, L.ptr(targets), S, L.ptr(input_lengths), L.ptr(target_lengths),
            int(blank), L.ptr(nll), L.ptr(grad_nll), L.ptr(alpha), L.ptr(beta), L.ptr(grad), _s())
     return grad

@@ -24,7 +24,9 @@ def gemm_ex(A, B, out, M, N, K, *, a_mn=False, b_mn=False, lda, ldb, ldo, nb=(1,
         b_mn=int(b_mn), lda=lda, ldb=ldb, ldo=ldo, ldaux=ldaux, nb1=nb[0], nb2=nb[1], sa1=sa[0], sa2=sa[1], sb1=sb[0],
         sb2=sb[1], so1=so[0], so2=so[1], sx1=sx[0], sx2=sx[1], sr1=sr[0], sr2=sr[1], alpha=float(alpha), epi=epi,
         out_dtype=L.dtype_code(out.dtype), ksplit=ksplit)
-    L.call("lcasr_gemm_ex", C.byref(args), _s())
+    L.call("lcasr_gemm_ex", C.byref(args), _s(),
+           tag=f"[{M}x{N}x{K} a_mn={int(a_mn)} b_mn={int(b_mn)} out={'f32' if out.dtype == torch.float32 else 'bf16'} epi={epi} "
+               f"batch={nb[0] * nb[1]}]" if L.TIMING_TAGS else "")
     return out
 
 
@@ -58,7 +60,7 @@ def attention_train(q, k, v):
     return out, lse
 
 
-def attention_bwd(q, k, v, o, do, lse, chunk_b: int = 0):
+def attention_bwd(q, k, v, o, do, lse, chunk_b: int = 0, fused_pds: bool = True):
     """Backward of softmax(q k^T / sqrt(Dh)) v from the saved output and log-sum-exp.
     q,k,v,o,do bf16 [B,N,H,Dh]; returns dq, dk, dv (same layout).  P and dS are materialised per group of
     recordings ([b,H,N,N] bf16 each, sized to stay L2-resident) and every product is one batched tcgen05 GEMM."""
@@ -83,19 +85,54 @@ def attention_bwd(q, k, v, o, do, lse, chunk_b: int = 0):
         x4 = (Dh, N * d)  # (head, recording) strides of a [B,N,H,Dh] tensor
         s4 = (sNN, H * sNN)
         r4 = (N, H * N)
-        # P = exp2(scale*log2e * q k^T - lse2)
-        gemm_ex(qs, ks, P, N, N, Dh, lda=d, ldb=d, ldo=Np, sa=x4, sb=x4, so=s4, rowvec=lse[b0:], sr=r4,
-                alpha=scale * 1.4426950408889634, epi=L.EPI_EXP2, **bat)
-        # dS = P o (do v^T - D) * scale
-        gemm_ex(dos, vs, dS, N, N, Dh, lda=d, ldb=d, ldo=Np, sa=x4, sb=x4, so=s4, aux=P, ldaux=Np, sx=s4,
-                rowvec=Dvec[b0:], sr=r4, alpha=scale, epi=L.EPI_DS, **bat)
+        if fused_pds:  # P = exp2(scale*log2e * q k^T - lse2) and dS = P o (do v^T - D) * scale in one pass
+            L.call("lcasr_attention_bwd_pds", L.ptr(qs), L.ptr(ks), L.ptr(vs), L.ptr(dos), L.ptr(lse[b0:]), L.ptr(Dvec[b0:]),
+                   nb, N, H, Dh, L.ptr(P), L.ptr(dS), _s())
+        else:          # the same as two GEMMs with epilogues (kept as the A/B reference of the fused kernel)
+            gemm_ex(qs, ks, P, N, N, Dh, lda=d, ldb=d, ldo=Np, sa=x4, sb=x4, so=s4, rowvec=lse[b0:], sr=r4,
+                    alpha=scale * 1.4426950408889634, epi=L.EPI_EXP2, **bat)
+            gemm_ex(dos, vs, dS, N, N, Dh, lda=d, ldb=d, ldo=Np, sa=x4, sb=x4, so=s4, aux=P, ldaux=Np, sx=s4,
+                    rowvec=Dvec[b0:], sr=r4, alpha=scale, epi=L.EPI_DS, **bat)
+        # The three products are independent and each fills only H*ceil(N/128) of the 148 SMs: dk and dv run on side
+        # streams next to dq (fork after P/dS are written, join before they are overwritten / the results are used).
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
         # dq = dS k       (B operand k stored [keys, Dh] = [K, N]: MN-major)
         gemm_ex(dS, ks, dq[b0:], N, Dh, N, b_mn=True, lda=Np, ldb=d, ldo=d, sa=s4, sb=x4, so=x4, **bat)
-        # dk = dS^T q     (A stored [q, keys] = [K, M]: MN-major)
-        gemm_ex(dS, qs, dk[b0:], N, Dh, N, a_mn=True, b_mn=True, lda=Np, ldb=d, ldo=d, sa=s4, sb=x4, so=x4, **bat)
-        # dv = P^T do
-        gemm_ex(P, dos, dv[b0:], N, Dh, N, a_mn=True, b_mn=True, lda=Np, ldb=d, ldo=d, sa=s4, sb=x4, so=x4, **bat)
+        for i, side in enumerate(_side_streams(dev)):
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                if i == 0:  # dk = dS^T q     (A stored [q, keys] = [K, M]: MN-major)
+                    gemm_ex(dS, qs, dk[b0:], N, Dh, N, a_mn=True, b_mn=True, lda=Np, ldb=d, ldo=d, sa=s4, sb=x4, so=x4, **bat)
+                else:       # dv = P^T do
+                    gemm_ex(P, dos, dv[b0:], N, Dh, N, a_mn=True, b_mn=True, lda=Np, ldb=d, ldo=d, sa=s4, sb=x4, so=x4, **bat)
+                join = torch.cuda.Event()
+                join.record(side)
+            main.wait_event(join)
     return dq, dk, dv
+
+
+_SIDE = {}
+
+
+def _side_streams(dev):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _SIDE:
+        _SIDE[key] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+    return _SIDE[key]
+
+
+def gemm_act_pre(a, w, bias, act):
+    """(act(pre), pre) with pre = a @ w^T + bias, both bf16: one tcgen05 GEMM with a two-output epilogue."""
+    _cuda(a, w, bias)
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, dtype=BF, device=a.device)
+    pre = torch.empty_like(out)
+    L.call("lcasr_gemm_act_pre", L.ptr(a), L.ptr(w), M, N, K, L.ptr(bias), act, L.ptr(out), L.ptr(pre), _s(),
+           tag=f"[{M}x{N}x{K} out=bf16+pre]" if L.TIMING_TAGS else "")
+    return out, pre
 
 
 def scale_cast(x, scale=1.0):

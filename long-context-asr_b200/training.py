@@ -191,13 +191,12 @@ class TrainEngine:
         # subsampling (unfused kernels: the backward needs every level's input)
         s1 = ops.subsample_conv0(spec, P["conv0_w"], P["conv0_b"], out_dtype=BF)            # [B,T1,F1,C]
         d1 = ops.subsample_dwconv(s1, P["dw1_w"], P["dw1_b"])                                # [B,T2,F2,C]
-        p1 = ops.gemm(d1.view(-1, Cc), P["pw1_w"], bias=P["pw1_b"])
-        a1 = T.act_fwd(p1, SILU).view(d1.shape)
+        a1, p1 = T.gemm_act_pre(d1.view(-1, Cc), P["pw1_w"], P["pw1_b"], SILU)
+        a1 = a1.view(d1.shape)
         d2 = ops.subsample_dwconv(a1, P["dw2_w"], P["dw2_b"])                                # [B,N,F3,C]
         N = d2.shape[1]
         M = B * N
-        p2 = ops.gemm(d2.view(-1, Cc), P["pw2_w"], bias=P["pw2_b"])
-        a2 = T.act_fwd(p2, SILU)
+        a2, p2 = T.gemm_act_pre(d2.view(-1, Cc), P["pw2_w"], P["pw2_b"], SILU)
         x = ops.gemm(a2.view(M, F3 * Cc), P["sub_out_w"], out_dtype=torch.float32)           # [M,d] fp32
         S.update(s1=s1, d1=d1, p1=p1, a1=a1, d2=d2, p2=p2, a2=a2, N=N)
         cos, sin = self.rope(N, dev)
@@ -210,8 +209,7 @@ class TrainEngine:
             for ff in ("ff1", "attn", "conv", "ff2"):
                 if ff in ("ff1", "ff2"):
                     a = ln(x, q + ff + "_norm")
-                    hpre = ops.gemm(a, P[q + ff + "_fc1_w"], bias=P[q + ff + "_fc1_b"])
-                    hact = T.act_fwd(hpre, GELU)
+                    hact, hpre = T.gemm_act_pre(a, P[q + ff + "_fc1_w"], P[q + ff + "_fc1_b"], GELU)
                     xn = ops.gemm(hact, P[q + ff + "_fc2_w"], bias=P[q + ff + "_fc2_b"], resid=x, alpha=0.5)
                     R[ff] = dict(x=x, a=a, hpre=hpre, hact=hact)
                 elif ff == "attn":
@@ -346,13 +344,19 @@ class TrainEngine:
         ds1 = T.subsample_dwconv_bwd_data(dd1, P["dw1_w"], S["s1"].shape[1], S["s1"].shape[2])
         T.subsample_conv0_bwd_(S["spec"], P["conv0_w"], P["conv0_b"], ds1, G["conv0_w"], G["conv0_b"])
 
-        if self.dp_group is not None:  # data-parallel: ONE all-reduce over the flat gradient buffer (NCCL / NVLink)
-            import torch.distributed as dist
-            dist.all_reduce(flat, group=self.dp_group)
-            if self.dp_average:
-                flat.mul_(1.0 / dist.get_world_size(self.dp_group))
+        self.reduce_gradients(flat)
         self.last_flat_grad = flat
         return self.to_param_grads(G)
+
+    def reduce_gradients(self, flat: torch.Tensor) -> None:
+        """data-parallel training: ONE all-reduce over the flat packed gradient buffer (NCCL over NVLink on the GPU
+        box; sum, then divided by the world size like DistributedDataParallel when dp_average)."""
+        if self.dp_group is None:
+            return
+        import torch.distributed as dist
+        dist.all_reduce(flat, group=self.dp_group)
+        if self.dp_average:
+            flat.mul_(1.0 / dist.get_world_size(self.dp_group))
 
 
 class _EncoderFn(torch.autograd.Function):

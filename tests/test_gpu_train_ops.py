@@ -95,6 +95,10 @@ def test_attention_train_and_backward(cuda_device, B, N, H, Dh):
     dq, dk, dv = T.attention_bwd(q, k, v, out.view(B, N, H, Dh), do.view(B, N, H, Dh), lse2)
     for name, got, r in (("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
         _close(got, r.transpose(1, 2), 3e-2, f"attention_bwd {name} {B},{N},{H},{Dh}")
+    # the fused P/dS kernel against the two-GEMM formulation
+    dq3, dk3, dv3 = T.attention_bwd(q, k, v, out.view(B, N, H, Dh), do.view(B, N, H, Dh), lse2, fused_pds=False)
+    for a_, b_ in ((dq, dq3), (dk, dk3), (dv, dv3)):
+        assert (a_.float() - b_.float()).abs().max().item() <= 2 ** -6 * b_.float().abs().max().item()
     if B > 1:  # chunking over recordings gives the same result
         dq2, dk2, dv2 = T.attention_bwd(q, k, v, out.view(B, N, H, Dh), do.view(B, N, H, Dh), lse2, chunk_b=1)
         assert torch.equal(dq, dq2) and torch.equal(dk, dk2) and torch.equal(dv, dv2)

@@ -1,0 +1,53 @@
+"""Data-parallel training check on real GPUs (run under torchrun, one rank per GPU):
+the gradients a rank holds after loss.backward() with the in-backward NCCL all-reduce must equal the mean over
+ranks of the gradients each rank computes alone on its own batch.
+usage: torchrun --nproc-per-node 2 --master-addr 127.0.0.1 tools/dp_check.py"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+import lcasr_b200
+from lcasr_b200.training import TrainEngine
+from oracle import lcasr_oracle as O
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+cfg = O.make_config(n_layers=2, d_model=256, n_heads=2, head_dim=128, subsampling_conv_channels=64, vocab_size=255)
+sd = O.synth_state_dict(cfg, seed=1)
+x = O.synth_input(2, 1024, 80, seed=100 + rank).to(dev)
+tgt, tl = O.synth_targets(2, O.calc_length(1024), vocab=255, seed=7 + rank)
+ctc = lcasr_b200.CTCLoss(blank=255, reduction="sum")
+
+
+def grads(dp):
+    m = lcasr_b200.SCConformerXL(**cfg)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev).train()
+    m._train_engine = TrainEngine(m)
+    if dp:
+        m._train_engine.dp_group = dist.group.WORLD
+    out = m(x)
+    ctc(out["final_posteriors"].transpose(0, 1), tgt, out["length"], tl).backward()
+    return {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+
+
+solo, dp = grads(False), grads(True)
+worst = 0.0
+for n, g in solo.items():
+    mean = g.clone()
+    dist.all_reduce(mean)
+    mean /= world
+    den = max(mean.norm().item(), 1e-6)
+    worst = max(worst, (dp[n] - mean).norm().item() / den)
+t = torch.tensor([worst], device=dev)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print(f"dp_check world={world}: worst relative L2 difference between in-backward all-reduced gradients and the mean of "
+          f"per-rank gradients = {t.item():.3e} (fp32 atomics reorder sums: expected ~1e-6)")
+    assert t.item() < 1e-3
+dist.destroy_process_group()
