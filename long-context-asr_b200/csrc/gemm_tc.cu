@@ -12,21 +12,34 @@
 // transposes are needed anywhere on the path.  Out-of-range rows / K tail are zero-filled by TMA.
 // Tensor-bound: algorithmic FLOPs = 2*M*N*K.
 #include "common.cuh"
+#include <cstdlib>
 #include "sm100_ptx.cuh"
 
 namespace lcasr {
 
 using namespace ptx;
 
-constexpr int TG_BM = 128, TG_BK = 64, TG_THREADS = 192;
+constexpr int TG_BM = 128, TG_BK = 64;
+// four epilogue warps, one per TMEM lane quarter (eight — two per quarter, half of the columns each — measured neutral:
+// the bound of the bf16-output GEMMs was the global store pattern, see tg_stage_chunk64)
+// (CTA pairs + bf16 outputs: eight, two per quarter taking half of the columns each — with the stores gone to TMA the
+// remaining epilogue cost is the per-warp chain TMEM load -> convert -> stage, which two warps per quarter overlap)
+template <typename TOut, int CG> struct TgWarps {
+  static constexpr int EPI = (sizeof(TOut) == 2 && CG == 2) ? 8 : 4, THREADS = 64 + 32 * EPI;
+};
 
-template <int BN> struct TgCfg {
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
+// CG = CTAs per MMA (tcgen05 cta_group): 1, or 2 = a CTA pair computes a 256 x BN tile, each CTA staging its 128 rows
+// of A and HALF of the B tile -> 2/3 of the shared-memory fill traffic per FLOP and a deeper ring
+template <int BN, int CG = 1> struct TgCfg {
+  static constexpr int STAGES = BN == 256 ? (CG == 2 ? 5 : 4) : (CG == 2 ? 8 : 6);
   static constexpr int A_BYTES = TG_BM * TG_BK * 2;
-  static constexpr int B_BYTES = BN * TG_BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * TG_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered fp32 accumulator (power of two: 256 / 512)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/;
+  // bf16 outputs: one 32-row x 64-column (128 B rows) staging box per epilogue warp
+  template <typename TOut> static constexpr int smem_bytes() {
+    return STAGES * STAGE_BYTES + (sizeof(TOut) == 2 ? TgWarps<TOut, CG>::EPI * 4096 : 0) + 1024 /*align slack*/;
+  }
 };
 
 struct TgEpilogue {
@@ -35,6 +48,7 @@ struct TgEpilogue {
   float alpha;
   int act;
   bf16* pre_out = nullptr;  // training: the pre-activation acc+bias [M,N] is stored as well (bf16 outputs only)
+  int debug = 0;            // LCASR_GEMM_DEBUG (profiling only): 1 = skip the global stores, 2 = skip the whole epilogue
 };
 
 // Direct epilogue (bf16 outputs, no residual): lane == row, 64 contiguous bytes per lane and chunk.
@@ -79,6 +93,7 @@ __device__ __forceinline__ void tg_store_chunk_direct(const uint32_t (&r)[32], i
     for (int i = 0; i < 32; ++i) y[i] = silu_fast(y[i]);
   }
   bf16* op = out + row * N + col0;
+  if (ep.debug == 1 && y[0] != 12345.678f) return;  // profiling: everything but the stores (the test keeps y alive)
 #pragma unroll
   for (int g = 0; g < 4; ++g)
     if (g < ngroups) Vec8<bf16>::store(op + 8 * g, *reinterpret_cast<const float(*)[8]>(&y[8 * g]));
@@ -157,15 +172,70 @@ __device__ __forceinline__ void tg_store_chunk(const uint32_t (&r)[32], const fl
   __syncwarp();  // the staging tile is reused by the next chunk
 }
 
-template <int BN, typename TOut>
-__global__ void __launch_bounds__(TG_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int64_t M, int N, int K,
+// bf16 outputs through TMA stores.  Measured on the 768 -> 3072 GELU GEMM: main loop alone 1520 TFLOP/s, + TMEM loads
+// and the activation 1330, + per-lane 16-byte global stores (one row per lane: 32 partial lines per instruction) 944.
+// Here a warp converts 64 columns of its 32 rows into a 128B-swizzled shared-memory box (conflict-free: 8 lanes with
+// distinct row%8 cover 8 distinct 16-byte slots per wavefront) and one lane issues a single cp.async.bulk.tensor
+// store for the box: full lines, no LSU work, rows / columns beyond the tensor clipped by the hardware.
+__device__ __forceinline__ void tg_stage_chunk64(const uint32_t (&r0)[32], const uint32_t (&r1)[32], int lane, uint32_t stage_addr,
+                                                 const TgEpilogue& ep, const float* __restrict__ bias_chunk, bool pre_pass) {
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    float y[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(hh == 0 ? r0[i] : r1[i]);
+    if (ep.bias) {
+      const float4* bp = reinterpret_cast<const float4*>(bias_chunk + 32 * hh);  // shared memory (broadcast reads)
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 b = bp[g];
+        y[4 * g] += b.x; y[4 * g + 1] += b.y; y[4 * g + 2] += b.z; y[4 * g + 3] += b.w;
+      }
+    }
+    if (!pre_pass) {
+      if (ep.pre_out) {  // the activation is applied to the ROUNDED pre-activation, i.e. what the backward will see
+#pragma unroll
+        for (int i = 0; i < 32; ++i) y[i] = __bfloat162float(__float2bfloat16_rn(y[i]));
+      }
+      if (ep.act == LCASR_ACT_GELU_TANH) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x = y[i];
+          const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+          y[i] = 0.5f * x * (1.0f + tanh_approx(u));
+        }
+      } else if (ep.act == LCASR_ACT_SILU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) y[i] = silu_fast(y[i]);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {  // 16-byte slot j = 4*hh + g of this lane's 128-byte row, XOR-swizzled by row % 8
+      uint4 v;
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h2[i] = __floats2bfloat162_rn(y[8 * g + 2 * i], y[8 * g + 2 * i + 1]);
+      const uint32_t addr = stage_addr + lane * 128 + (((4 * hh + g) ^ (lane & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+  }
+}
+
+template <int BN, typename TOut, int CG>
+__global__ void __launch_bounds__(TgWarps<TOut, CG>::THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, int64_t M, int N, int K,
                TgEpilogue ep, TOut* out) {
-  using Cfg = TgCfg<BN>;
+  // tmC / tmC2 (bf16 outputs only): store maps of `out` / `ep.pre_out`, 64-column x 32-row boxes, 128B swizzle
+  using Cfg = TgCfg<BN, CG>;
+  // CG == 2: launched as clusters of 2 CTAs; `rank` 0 is the leader (issues every MMA, owns the full / tempty barriers
+  // that both CTAs signal), tiles are 256 x BN and indexed per cluster
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * Cfg::STAGES + 4];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) float4 epi_stage[4][32 * 8];  // per epilogue warp: 32 rows x 32 fp32, swizzled
+  constexpr int NEW = TgWarps<TOut, CG>::EPI;
+  __shared__ __align__(16) float4 epi_stage[sizeof(TOut) == 4 ? 4 : 1][32 * 8];  // per epilogue warp: 32 rows x 32 fp32, swizzled
   __shared__ __align__(16) float bias_s[2][BN];          // the tile's bias slice, staged while the main loop still runs
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle atoms need 1024B alignment
   const uint32_t bar_base = smem_u32(bars);
@@ -177,46 +247,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = (K + TG_BK - 1) / TG_BK;
   const int tiles_n = (N + BN - 1) / BN;
-  const int64_t tiles_m = (M + TG_BM - 1) / TG_BM;
+  const int64_t tiles_m = (M + CG * TG_BM - 1) / (CG * TG_BM);
   const int64_t total_tiles = tiles_m * tiles_n;
+  const int64_t tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;  // per cluster
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), CG * NEW); }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CG == 2) { tmem_alloc_cg2(smem_u32(&tmem_slot), Cfg::TMEM_COLS); tmem_relinquish_cg2(); }
+    else { tmem_alloc(smem_u32(&tmem_slot), Cfg::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer ----------------
       int stage = 0; uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_idx = (int)(tile / tiles_n) * TG_BM, n_idx = (int)(tile % tiles_n) * BN;
+      const uint32_t full0 = CG == 2 ? mapa_shared(full_bar(0), 0) : full_bar(0);  // the leader's full barriers
+      for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
+        const int m_idx = (int)(tile / tiles_n) * (CG * TG_BM) + (int)rank * TG_BM;
+        const int n_idx = (int)(tile % tiles_n) * BN + (int)rank * (BN / CG);
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-          tma_load_2d(sa, &tmA, full_bar(stage), kb * TG_BK, m_idx);
-          tma_load_2d(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * TG_BK, n_idx);
+          if constexpr (CG == 2) {
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes land here
+            tma_load_2d_cg2(sa, &tmA, full0 + 8u * stage, kb * TG_BK, m_idx);
+            tma_load_2d_cg2(sa + Cfg::A_BYTES, &tmB, full0 + 8u * stage, kb * TG_BK, n_idx);
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+            tma_load_2d(sa, &tmA, full_bar(stage), kb * TG_BK, m_idx);
+            tma_load_2d(sa + Cfg::A_BYTES, &tmB, full_bar(stage), kb * TG_BK, n_idx);
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc = make_idesc_bf16(TG_BM, BN);
+    if (lane == 0 && rank == 0) {  // ---------------- MMA issuer (leader CTA only) ----------------
+      constexpr uint32_t idesc = make_idesc_bf16(CG * TG_BM, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -227,51 +307,75 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t adesc = make_smem_desc_kmajor(sa, 1024, kLayoutSW128);
           const uint64_t bdesc = make_smem_desc_kmajor(sa + Cfg::A_BYTES, 1024, kLayoutSW128);
 #pragma unroll
-          for (int k = 0; k < TG_BK / 16; ++k)  // +32 bytes (= 2 in >>4 units) per K=16 step inside the swizzle row
-            umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(empty_bar(stage));
+          for (int k = 0; k < TG_BK / 16; ++k) {  // +32 bytes (= 2 in >>4 units) per K=16 step inside the swizzle row
+            if constexpr (CG == 2) umma_f16_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          if constexpr (CG == 2) umma_commit_cg2(empty_bar(stage), 3);  // frees the slot in BOTH CTAs
+          else umma_commit(empty_bar(stage));
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar(acc));
+        if constexpr (CG == 2) umma_commit_cg2(tfull_bar(acc), 3);      // each CTA drains its own 128 accumulator rows
+        else umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {  // ---------------- epilogue warps 2..5 ----------------
     const int lane_base = (warp & 3) * 32;  // TMEM lanes this warp may touch
+    const int half = (warp - 2) >> 2;       // NEW == 8: which half of the tile's columns this warp drains
+    constexpr int CPW = (BN / 32) / (NEW / 4);  // 32-column chunks per warp
     int acc = 0; uint32_t acc_phase = 0;
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int64_t m_idx = (tile / tiles_n) * TG_BM;
+    const uint32_t tempty0 = CG == 2 ? mapa_shared(tempty_bar(0), 0) : 0;  // the leader's tempty barriers
+    for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
+      const int64_t m_idx = (tile / tiles_n) * (CG * TG_BM) + rank * TG_BM;
       const int n_idx = (int)(tile % tiles_n) * BN;
       if (ep.bias) {  // stage this tile's bias slice now: its latency hides behind the wait for the accumulator
-        const int e = (warp & 3) * 32 + lane;
-#pragma unroll
-        for (int i = 0; i < BN / 128; ++i) {
-          const int col = n_idx + i * 128 + e;
-          bias_s[acc][i * 128 + e] = col < N ? __ldg(ep.bias + col) : 0.f;
+        const int e = (warp - 2) * 32 + lane;
+        for (int i = e; i < BN; i += 32 * NEW) {
+          const int col = n_idx + i;
+          bias_s[acc][i] = col < N ? __ldg(ep.bias + col) : 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * NEW) : "memory");  // the epilogue warps only
       }
       const int64_t row0 = m_idx + lane_base;
       float4 res_nxt[8];
       if constexpr (sizeof(TOut) == 4) {
-        if (ep.resid) tg_load_resid(res_nxt, lane, row0, n_idx, M, N, ep.resid);  // chunk 0, in flight during the wait
+        if (ep.resid) tg_load_resid(res_nxt, lane, row0, n_idx + half * CPW * 32, M, N, ep.resid);  // first chunk, in flight during the wait
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        if (n_idx + c * 32 >= N) break;  // warp-uniform
+      for (int c = half * CPW; c < (half + 1) * CPW; ++c) {
+        if (n_idx + c * 32 >= N || ep.debug == 2) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_addr + c * 32, r);
         if constexpr (sizeof(TOut) == 2) {
+          if (ep.debug || (c & 1)) {  // profiling variants keep the direct path; odd chunks are drained with their even twin
+            tmem_wait_ld();
+            if (ep.debug) tg_store_chunk_direct(r, row0 + lane, n_idx + c * 32, M, N, ep, &bias_s[acc][c * 32], out);
+            continue;
+          }
+          uint32_t r1[32];
+          tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, r1);  // BN is a multiple of 64: the twin chunk exists
           tmem_wait_ld();
-          tg_store_chunk_direct(r, row0 + lane, n_idx + c * 32, M, N, ep, &bias_s[acc][c * 32], out);
+          const uint32_t stg = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES + (warp - 2) * 4096;
+          for (int pass = ep.pre_out ? 0 : 1; pass < 2; ++pass) {
+            if (lane == 0) tma_store_wait_read();  // the previous box has been read out of the staging tile
+            __syncwarp();
+            tg_stage_chunk64(r, r1, lane, stg, ep, &bias_s[acc][c * 32], pass == 0);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(pass == 0 ? &tmC2 : &tmC, stg, n_idx + c * 32, (int)row0);
+              tma_store_commit();
+            }
+          }
         } else {
           float4 res_cur[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) res_cur[i] = res_nxt[i];
-          if (ep.resid && c + 1 < BN / 32 && n_idx + (c + 1) * 32 < N)
+          if (ep.resid && c + 1 < (half + 1) * CPW && n_idx + (c + 1) * 32 < N)
             tg_load_resid(res_nxt, lane, row0, n_idx + (c + 1) * 32, M, N, ep.resid);  // in flight during this chunk
           tmem_wait_ld();
           tg_store_chunk<TOut>(r, res_cur, epi_stage[warp & 3], lane, row0, n_idx + c * 32, M, N, ep, &bias_s[acc][c * 32], out);
@@ -279,15 +383,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(tempty0 + 8u * acc);
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (sizeof(TOut) == 2 && lane == 0) tma_store_wait_all();  // bulk stores complete before the CTA retires
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the leader's MMAs read the peer's shared memory and write its TMEM
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -344,23 +454,49 @@ int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t d0, uint64_t 
   return 0;
 }
 
-template <int BN, typename TOut>
+template <int BN, typename TOut, int CG>
 static int launch_tc(const void* A, const void* W, int64_t M, int N, int K, const TgEpilogue& ep, void* out,
                      cudaStream_t st) {
-  using Cfg = TgCfg<BN>;
+  using Cfg = TgCfg<BN, CG>;
   CUtensorMap tmA, tmB;
   LCASR_TRY(make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)K * 2, TG_BM, TG_BK, CU_TENSOR_MAP_SWIZZLE_128B));
-  LCASR_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, BN, TG_BK, CU_TENSOR_MAP_SWIZZLE_128B));
+  LCASR_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, BN / CG, TG_BK, CU_TENSOR_MAP_SWIZZLE_128B));
+  CUtensorMap tmC = tmA, tmC2 = tmA;  // placeholders for fp32 outputs (never dereferenced)
+  if (sizeof(TOut) == 2) {
+    LCASR_TRY(make_tmap_2d_bf16(&tmC, out, (uint64_t)M, (uint64_t)N, (uint64_t)N * 2, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
+    if (ep.pre_out)
+      LCASR_TRY(make_tmap_2d_bf16(&tmC2, ep.pre_out, (uint64_t)M, (uint64_t)N, (uint64_t)N * 2, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    LCASR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    LCASR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TOut, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::template smem_bytes<TOut>()));
     attr_set = true;
   }
-  const int64_t tiles = ceil_div(M, TG_BM) * ceil_div(N, BN);
-  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  gemm_tc_kernel<BN, TOut><<<grid, TG_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, ep, (TOut*)out);
+  const int64_t tiles = ceil_div(M, CG * TG_BM) * ceil_div(N, BN);
+  const int64_t units = kNumSMs / CG;  // CTAs (CG == 1) or CTA pairs: one per SM / per TPC, persistent
+  const int grid = (int)(tiles < units ? tiles : units) * CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TgWarps<TOut, CG>::THREADS);
+  cfg.dynamicSmemBytes = Cfg::template smem_bytes<TOut>();
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CG == 2 ? 1 : 0;
+  LCASR_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, TOut, CG>, tmA, tmB, tmC, tmC2, M, N, K, ep, (TOut*)out));
   LCASR_LAUNCH_CHECK();
   return 0;
+}
+
+template <int BN, typename TOut>
+static int launch_tc_cg(const void* A, const void* W, int64_t M, int N, int K, const TgEpilogue& ep, void* out,
+                        cudaStream_t st) {
+  // CTA pairs (256-row tiles) once there is enough work to fill the 74 pairs; LCASR_GEMM_CG=1|2 forces a choice (A/B runs)
+  static const int force = getenv("LCASR_GEMM_CG") ? atoi(getenv("LCASR_GEMM_CG")) : 0;
+  const bool pair = force ? force == 2 : (ceil_div(M, 2 * TG_BM) * ceil_div(N, BN) >= kNumSMs / 2);
+  return pair ? launch_tc<BN, TOut, 2>(A, W, M, N, K, ep, out, st) : launch_tc<BN, TOut, 1>(A, W, M, N, K, ep, out, st);
 }
 
 int gemm_tc_launch(const void* A, const void* W, int64_t M, int N, int K, const float* bias, int act, const float* resid,
@@ -373,11 +509,12 @@ int gemm_tc_launch(const void* A, const void* W, int64_t M, int N, int K, const 
   LCASR_CHECK_ARG(M < (int64_t)1 << 31, "gemm(tcgen05): M too large");
   LCASR_CHECK_ARG(((uintptr_t)bias & 15) == 0 && ((uintptr_t)resid & 15) == 0, "gemm(tcgen05): bias/resid must be 16-byte aligned");
   LCASR_CHECK_ARG(!resid || out_dtype == LCASR_F32, "gemm: a residual epilogue writes fp32");
-  TgEpilogue ep{bias, resid, alpha, act, (bf16*)pre_out};
+  static const int debug = getenv("LCASR_GEMM_DEBUG") ? atoi(getenv("LCASR_GEMM_DEBUG")) : 0;
+  TgEpilogue ep{bias, resid, alpha, act, (bf16*)pre_out, debug};
   const bool wide = (N % 256 == 0) || N > 512;
   if (out_dtype == LCASR_BF16)
-    return wide ? launch_tc<256, bf16>(A, W, M, N, K, ep, out, st) : launch_tc<128, bf16>(A, W, M, N, K, ep, out, st);
-  return wide ? launch_tc<256, float>(A, W, M, N, K, ep, out, st) : launch_tc<128, float>(A, W, M, N, K, ep, out, st);
+    return wide ? launch_tc_cg<256, bf16>(A, W, M, N, K, ep, out, st) : launch_tc_cg<128, bf16>(A, W, M, N, K, ep, out, st);
+  return wide ? launch_tc_cg<256, float>(A, W, M, N, K, ep, out, st) : launch_tc_cg<128, float>(A, W, M, N, K, ep, out, st);
 }
 
 }  // namespace lcasr

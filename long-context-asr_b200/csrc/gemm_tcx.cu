@@ -21,7 +21,9 @@ namespace lcasr {
 
 using namespace ptx;
 
-constexpr int TX_BM = 128, TX_BK = 64, TX_THREADS = 192;
+constexpr int TX_BM = 128, TX_BK = 64;
+constexpr int TX_EPI_WARPS = 8;  // two epilogue warps per TMEM lane quarter, each draining half of the tile's columns
+constexpr int TX_THREADS = 64 + 32 * TX_EPI_WARPS;
 
 template <int BN> struct TxCfg {
   static constexpr int STAGES = BN == 256 ? 4 : 6;
@@ -29,7 +31,8 @@ template <int BN> struct TxCfg {
   static constexpr int B_BYTES = BN * TX_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+  static constexpr int OUT_STAGE_BYTES = TX_EPI_WARPS * 4096;  // bf16 outputs leave through TMA stores (see gemm_tc.cu)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 1024;
 };
 
 struct TxParams {
@@ -94,13 +97,9 @@ __device__ __forceinline__ void tx_load_aux(uint4 (&ax)[4], int64_t row, int col
     if (col0 + 8 * g < p.Nst) ax[g] = *reinterpret_cast<const uint4*>(xp + 8 * g);
 }
 
-// one 32-column chunk of one accumulator row (lane == row)
-template <typename TOut>
-__device__ __forceinline__ void tx_store_chunk(const uint32_t (&r)[32], const uint4 (&ax)[4], float rv, int64_t row, int col0,
-                                               const TxParams& p, int b1, int b2, TOut* __restrict__ out) {
-  if (row >= p.M) return;
-  const int ngroups = min(4, (p.Nst - col0) >> 3);  // 8 columns per group
-  float y[32];
+// epilogue arithmetic of one 32-column chunk of one accumulator row (lane == row); `ngroups` 8-column groups are live
+__device__ __forceinline__ void tx_epi_math(const uint32_t (&r)[32], const uint4 (&ax)[4], float rv, const TxParams& p,
+                                            int ngroups, float (&y)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(r[i]);
   const float a = p.alpha;
@@ -126,18 +125,35 @@ __device__ __forceinline__ void tx_store_chunk(const uint32_t (&r)[32], const ui
         }
       }
   }
-  TOut* op = out + b2 * p.so2 + b1 * p.so1 + row * p.ldo + col0;
+}
+
+// fp32 outputs ACCUMULATE with atomics (split-K partials, gradient accumulation into an existing buffer)
+__device__ __forceinline__ void tx_store_chunk_f32(const uint32_t (&r)[32], const uint4 (&ax)[4], float rv, int64_t row, int col0,
+                                                   const TxParams& p, int b1, int b2, float* __restrict__ out) {
+  if (row >= p.M) return;
+  const int ngroups = min(4, (p.Nst - col0) >> 3);  // 8 columns per group
+  float y[32];
+  tx_epi_math(r, ax, rv, p, ngroups, y);
+  float* op = out + b2 * p.so2 + b1 * p.so1 + row * p.ldo + col0;
 #pragma unroll
   for (int g = 0; g < 4; ++g)
     if (g < ngroups) {
-      if constexpr (sizeof(TOut) == 2) {
-        Vec8<bf16>::store(op + 8 * g, *reinterpret_cast<const float(*)[8]>(&y[8 * g]));
-      } else {  // fp32 outputs ACCUMULATE (split-K partials, gradient accumulation into an existing buffer)
-        atomicAdd(reinterpret_cast<float4*>(op + 8 * g), make_float4(y[8 * g], y[8 * g + 1], y[8 * g + 2], y[8 * g + 3]));
-        atomicAdd(reinterpret_cast<float4*>(op + 8 * g + 4),
-                  make_float4(y[8 * g + 4], y[8 * g + 5], y[8 * g + 6], y[8 * g + 7]));
-      }
+      atomicAdd(reinterpret_cast<float4*>(op + 8 * g), make_float4(y[8 * g], y[8 * g + 1], y[8 * g + 2], y[8 * g + 3]));
+      atomicAdd(reinterpret_cast<float4*>(op + 8 * g + 4), make_float4(y[8 * g + 4], y[8 * g + 5], y[8 * g + 6], y[8 * g + 7]));
     }
+}
+
+// 32 fp32 values of this lane's row -> bf16 -> 16-byte slots [4*hh, 4*hh+4) of its 128-byte row in the 128B-swizzled box
+__device__ __forceinline__ void tx_stage_half(const float (&y)[32], int lane, uint32_t stage_addr, int hh) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4 v;
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h2[i] = __floats2bfloat162_rn(y[8 * g + 2 * i], y[8 * g + 2 * i + 1]);
+    const uint32_t addr = stage_addr + lane * 128 + (((4 * hh + g) ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
 }
 
 struct TxTile {
@@ -162,7 +178,9 @@ __device__ __forceinline__ TxTile tx_decode(int64_t tile, const TxParams& p, int
 
 template <int BN, int A_MN, int B_MN, typename TOut>
 __global__ void __launch_bounds__(TX_THREADS, 1)
-gemm_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TxParams p, TOut* out) {
+gemm_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, TxParams p, TOut* out) {
+  // tmC (bf16 outputs): 4-D store map of `out`, 64-column x 32-row boxes, 128B swizzle
   using Cfg = TxCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * Cfg::STAGES + 4];
@@ -184,7 +202,7 @@ gemm_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TX_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -252,6 +270,8 @@ gemm_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {  // ---------------- epilogue warps 2..5 ----------------
     const int lane_base = (warp & 3) * 32;
+    const int half = (warp - 2) >> 2;
+    constexpr int CPW = (BN / 32) / (TX_EPI_WARPS / 4);  // 32-column chunks per warp
     int acc = 0; uint32_t acc_phase = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TxTile t = tx_decode<BN>(tile, p, tiles_n, tiles_m, num_k);
@@ -260,28 +280,71 @@ gemm_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // operands of the epilogue are requested BEFORE the accumulator wait: their latency hides behind the main loop
       float rv = 0.f;
       if ((p.epi == LCASR_EPI_EXP2 || p.epi == LCASR_EPI_DS) && row < p.M) rv = p.rowvec[t.b2 * p.sr2 + t.b1 * p.sr1 + row];
-      uint4 ax_nxt[4] = {};
-      if (has_aux) tx_load_aux(ax_nxt, row, t.n_idx, p, t.b1, t.b2);
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + acc * BN;
+      const int c_lo = half * CPW, c_hi = (half + 1) * CPW;
+      if constexpr (sizeof(TOut) == 4) {
+        uint4 ax_nxt[4] = {};
+        if (has_aux && t.n_idx + c_lo * 32 < p.N) tx_load_aux(ax_nxt, row, t.n_idx + c_lo * 32, p, t.b1, t.b2);
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        if (t.n_idx + c * 32 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_addr + c * 32, r);
-        uint4 ax_cur[4];
+        for (int c = c_lo; c < c_hi; ++c) {
+          if (t.n_idx + c * 32 >= p.N) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_addr + c * 32, r);
+          uint4 ax_cur[4];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) ax_cur[g] = ax_nxt[g];
-        if (has_aux && c + 1 < BN / 32 && t.n_idx + (c + 1) * 32 < p.N) tx_load_aux(ax_nxt, row, t.n_idx + (c + 1) * 32, p, t.b1, t.b2);
-        tmem_wait_ld();
-        tx_store_chunk<TOut>(r, ax_cur, rv, row, t.n_idx + c * 32, p, t.b1, t.b2, out);
+          for (int g = 0; g < 4; ++g) ax_cur[g] = ax_nxt[g];
+          if (has_aux && c + 1 < c_hi && t.n_idx + (c + 1) * 32 < p.N) tx_load_aux(ax_nxt, row, t.n_idx + (c + 1) * 32, p, t.b1, t.b2);
+          tmem_wait_ld();
+          tx_store_chunk_f32(r, ax_cur, rv, row, t.n_idx + c * 32, p, t.b1, t.b2, reinterpret_cast<float*>(out));
+        }
+      } else {  // bf16: 64 columns at a time through a swizzled shared-memory box and one TMA store per box
+        uint4 ax0[4] = {}, ax1[4] = {};
+        if (has_aux && t.n_idx + c_lo * 32 < p.N) {
+          tx_load_aux(ax0, row, t.n_idx + c_lo * 32, p, t.b1, t.b2);
+          tx_load_aux(ax1, row, t.n_idx + (c_lo + 1) * 32, p, t.b1, t.b2);
+        }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + acc * BN;
+        const uint32_t stg = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES + (warp - 2) * 4096;
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; c += 2) {
+          const int col0 = t.n_idx + c * 32;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(t_addr + c * 32, r0);
+          tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, r1);
+          uint4 a0[4], a1[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) { a0[g] = ax0[g]; a1[g] = ax1[g]; }
+          if (has_aux && c + 2 < c_hi && col0 + 64 < p.N) {  // next pair's aux, in flight during this pair's work
+            tx_load_aux(ax0, row, col0 + 64, p, t.b1, t.b2);
+            tx_load_aux(ax1, row, col0 + 96, p, t.b1, t.b2);
+          }
+          tmem_wait_ld();
+          float y[32];
+          if (lane == 0) tma_store_wait_read();  // the previous box has left the staging tile
+          __syncwarp();
+          tx_epi_math(r0, a0, rv, p, 4, y);
+          tx_stage_half(y, lane, stg, 0);
+          tx_epi_math(r1, a1, rv, p, 4, y);
+          tx_stage_half(y, lane, stg, 1);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmC, stg, col0, t.m_idx + lane_base, t.b1, t.b2);  // rows >= M / columns >= N are clipped
+            tma_store_commit();
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (sizeof(TOut) == 2 && lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -308,11 +371,13 @@ struct PdsParams {
   bf16* P;
   bf16* dS;
 };
-constexpr int PDS_STAGES = 3, PDS_STAGE_BYTES = 4 * 16384, PDS_SMEM = PDS_STAGES * PDS_STAGE_BYTES + 1024;
+constexpr int PDS_STAGES = 3, PDS_STAGE_BYTES = 4 * 16384;
+constexpr int PDS_SMEM = PDS_STAGES * PDS_STAGE_BYTES + TX_EPI_WARPS * 4096 + 1024;  // + one staging box per epilogue warp
 
 __global__ void __launch_bounds__(TX_THREADS, 1)
 attn_bwd_pds_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmV, PdsParams p) {
+                    const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmV,
+                    const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmDS, PdsParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * PDS_STAGES + 4];
   __shared__ uint32_t tmem_slot;
@@ -334,7 +399,7 @@ attn_bwd_pds_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmDO); prefetch_tensormap(&tmV);
     for (int s = 0; s < PDS_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TX_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -392,6 +457,8 @@ attn_bwd_pds_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
   } else {
     const int lane_base = (warp & 3) * 32;
+    const int half = (warp - 2) >> 2;
+    constexpr int CPW = 4 / (TX_EPI_WARPS / 4);
     int acc = 0; uint32_t acc_phase = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int m_idx, n_idx, h, b;
@@ -406,32 +473,44 @@ attn_bwd_pds_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + acc * 256;
-      const int64_t obase = (int64_t)b * p.so2 + (int64_t)h * p.so1 + row * p.ldo;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      const uint32_t stg = smem_base + PDS_STAGES * PDS_STAGE_BYTES + (warp - 2) * 4096;
+      {  // this warp's 64 columns [n_idx + 64*half, +64): P box, then dS box, one TMA store each
+        const int c = half * CPW;
         const int col0 = n_idx + c * 32;
-        if (col0 >= p.N) break;
-        uint32_t rs[32], rd[32];
-        tmem_ld_32x32b_x32(t_addr + c * 32, rs);
-        tmem_ld_32x32b_x32(t_addr + 128 + c * 32, rd);
-        tmem_wait_ld();
-        if (row_ok) {
-          const int ngroups = min(4, (p.Nst - col0) >> 3);
+        if (col0 < p.N) {
+          uint32_t rs0[32], rs1[32], rd0[32], rd1[32];
+          tmem_ld_32x32b_x32(t_addr + c * 32, rs0);
+          tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, rs1);
+          tmem_ld_32x32b_x32(t_addr + 128 + c * 32, rd0);
+          tmem_ld_32x32b_x32(t_addr + 128 + (c + 1) * 32, rd1);
+          tmem_wait_ld();
+          float pv[32];
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            if (g < ngroups) {
-              float pv[8], ds[8];
+          for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float pr = ex2_approx(fmaf(__uint_as_float(rs[8 * g + i]), p.alpha_p, -lse));
-                // the backward consumes P as a bf16 operand: dS uses the same rounded value (like the separate kernels)
-                const float prr = __bfloat162float(__float2bfloat16_rn(pr));
-                pv[i] = pr;
-                ds[i] = prr * (__uint_as_float(rd[8 * g + i]) - dv) * p.scale;
-              }
-              Vec8<bf16>::store(p.P + obase + col0 + 8 * g, pv);
-              Vec8<bf16>::store(p.dS + obase + col0 + 8 * g, ds);
+            for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(hh ? rs1[i] : rs0[i]), p.alpha_p, -lse));
+            tx_stage_half(pv, lane, stg, hh);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) { tma_store_4d(&tmP, stg, col0, m_idx + lane_base, h, b); tma_store_commit(); tma_store_wait_read(); }
+          __syncwarp();
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              // dS uses the bf16-rounded P, the operand the dV product consumes
+              const float pr = ex2_approx(fmaf(__uint_as_float(hh ? rs1[i] : rs0[i]), p.alpha_p, -lse));
+              const float prr = __bfloat162float(__float2bfloat16_rn(pr));
+              pv[i] = prr * (__uint_as_float(hh ? rd1[i] : rd0[i]) - dv) * p.scale;
             }
+            tx_stage_half(pv, lane, stg, hh);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) { tma_store_4d(&tmDS, stg, col0, m_idx + lane_base, h, b); tma_store_commit(); }
         }
       }
       tc_fence_before();
@@ -439,6 +518,7 @@ attn_bwd_pds_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -498,6 +578,9 @@ static int launch_tcx(const lcasr_gemm_ex_args& g, const TxParams& p, cudaStream
   else LCASR_TRY(make_tmap_4d(&tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, g.lda, g.nb1, g.sa1, g.nb2, g.sa2, TX_BM, TX_BK));
   if (B_MN) LCASR_TRY(make_tmap_4d(&tmB, g.B, (uint64_t)g.K, (uint64_t)g.N, g.ldb, g.nb1, g.sb1, g.nb2, g.sb2, TX_BK, 64));
   else LCASR_TRY(make_tmap_4d(&tmB, g.B, (uint64_t)g.N, (uint64_t)g.K, g.ldb, g.nb1, g.sb1, g.nb2, g.sb2, BN, TX_BK));
+  CUtensorMap tmC = tmA;  // placeholder for fp32 outputs (never dereferenced)
+  if (sizeof(TOut) == 2)
+    LCASR_TRY(make_tmap_4d(&tmC, g.out, (uint64_t)g.M, (uint64_t)g.N, g.ldo, g.nb1, g.so1, g.nb2, g.so2, 32, 64));
   static bool attr_set = false;
   if (!attr_set) {
     LCASR_CUDA(cudaFuncSetAttribute(gemm_tcx_kernel<BN, A_MN, B_MN, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -506,7 +589,7 @@ static int launch_tcx(const lcasr_gemm_ex_args& g, const TxParams& p, cudaStream
   }
   const int64_t tiles = ceil_div(g.M, TX_BM) * ceil_div(g.N, BN) * p.ksplit * g.nb1 * g.nb2;
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  gemm_tcx_kernel<BN, A_MN, B_MN, TOut><<<grid, TX_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p, (TOut*)g.out);
+  gemm_tcx_kernel<BN, A_MN, B_MN, TOut><<<grid, TX_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmC, p, (TOut*)g.out);
   LCASR_LAUNCH_CHECK();
   return 0;
 }
@@ -587,6 +670,9 @@ extern "C" int lcasr_attention_bwd_pds(const void* q, const void* k, const void*
   LCASR_TRY(make_tmap_4d(&tmK, k, (uint64_t)N, (uint64_t)Dh, d, H, Dh, nb, N * d, 128, TX_BK));
   LCASR_TRY(make_tmap_4d(&tmDO, d_out, (uint64_t)N, (uint64_t)Dh, d, H, Dh, nb, N * d, 128, TX_BK));
   LCASR_TRY(make_tmap_4d(&tmV, v, (uint64_t)N, (uint64_t)Dh, d, H, Dh, nb, N * d, 128, TX_BK));
+  CUtensorMap tmP, tmDS;
+  LCASR_TRY(make_tmap_4d(&tmP, P, (uint64_t)N, (uint64_t)N, Np, H, N * Np, nb, (int64_t)H * N * Np, 32, 64));
+  LCASR_TRY(make_tmap_4d(&tmDS, dS, (uint64_t)N, (uint64_t)N, Np, H, N * Np, nb, (int64_t)H * N * Np, 32, 64));
   static bool attr_set = false;
   if (!attr_set) {
     LCASR_CUDA(cudaFuncSetAttribute(attn_bwd_pds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PDS_SMEM));
@@ -602,7 +688,7 @@ extern "C" int lcasr_attention_bwd_pds(const void* q, const void* k, const void*
   const int64_t t1 = ceil_div(N, 128);
   const int64_t tiles = t1 * t1 * H * nb;
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  attn_bwd_pds_kernel<<<grid, TX_THREADS, PDS_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmDO, tmV, p);
+  attn_bwd_pds_kernel<<<grid, TX_THREADS, PDS_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmDO, tmV, tmP, tmDS, p);
   LCASR_LAUNCH_CHECK();
   return 0;
 }
