@@ -72,18 +72,21 @@ __global__ void __launch_bounds__(256) subsample_conv0_kernel(const float* __res
 // One CTA = kDwTB output time rows of one recording; all index arithmetic is 32-bit (the flat 64-bit
 // div/mod chain of a grid-stride loop cost more than the memory traffic: 775 us -> see DESIGN.md).
 constexpr int kDwTB = 4;
-template <typename T>
+template <typename T, int V> struct VecT;
+template <> struct VecT<float, 8> : Vec8<float> {};
+template <int V> struct VecT<bf16, V> : VecB<V> {};
+template <typename T, int V>  // V channels per thread (bf16: 4 halves the register footprint -> more loads in flight)
 __global__ void __launch_bounds__(256) subsample_dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w,
                                                                const float* __restrict__ bias, int64_t Tin, int Fin,
                                                                int C, int64_t Tout, int Fout, T* __restrict__ out) {
-  const int cgroups = C / 8;             // divides blockDim.x, so a thread's channel group is fixed
+  const int cgroups = C / V;             // divides blockDim.x, so a thread's channel group is fixed
   const int cg = threadIdx.x % cgroups;
-  float wr[8][9], br[8];
+  float wr[V][9], br[V];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    br[c] = bias[cg * 8 + c];
+  for (int c = 0; c < V; ++c) {
+    br[c] = bias[cg * V + c];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) wr[c][k] = w[(cg * 8 + c) * 9 + k];
+    for (int k = 0; k < 9; ++k) wr[c][k] = w[(cg * V + c) * 9 + k];
   }
   const int64_t b = blockIdx.y;
   const int64_t t0 = (int64_t)blockIdx.x * kDwTB;
@@ -95,9 +98,9 @@ __global__ void __launch_bounds__(256) subsample_dwconv_kernel(const T* __restri
     const int fo = (i - tl * per_row) / cgroups;
     const int64_t to = t0 + tl;
     if (to >= Tout) break;
-    float acc[8];
+    float acc[V];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = br[c];
+    for (int c = 0; c < V; ++c) acc[c] = br[c];
 #pragma unroll
     for (int ii = 0; ii < 3; ++ii) {
       const int64_t ti = 2 * to - 1 + ii;
@@ -106,13 +109,13 @@ __global__ void __launch_bounds__(256) subsample_dwconv_kernel(const T* __restri
       for (int j = 0; j < 3; ++j) {
         const int fi = 2 * fo - 1 + j;
         if (fi < 0 || fi >= Fin) continue;
-        float v[8];
-        Vec8<T>::load(inb + ((ti * Fin + fi) * C + cg * 8), v);
+        float v[V];
+        VecT<T, V>::load(inb + ((ti * Fin + fi) * C + cg * V), v);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = fmaf(wr[c][ii * 3 + j], v[c], acc[c]);
+        for (int c = 0; c < V; ++c) acc[c] = fmaf(wr[c][ii * 3 + j], v[c], acc[c]);
       }
     }
-    Vec8<T>::store(outb + ((to * Fout + fo) * C + cg * 8), acc);
+    VecT<T, V>::store(outb + ((to * Fout + fo) * C + cg * V), acc);
   }
 }
 
@@ -243,10 +246,12 @@ extern "C" int lcasr_subsample_dwconv(const void* in, int dtype, const float* w,
   LCASR_CHECK_ARG(B <= 65535 && ceil_div(Tout, kDwTB) <= 0x7fffffff, "subsample_dwconv: grid too large");
   dim3 grid((unsigned)ceil_div(Tout, kDwTB), (unsigned)B);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == LCASR_BF16)
-    subsample_dwconv_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)in, w, b, Tin, Fin, C, Tout, Fout, (bf16*)out);
+  if (dtype == LCASR_BF16 && C / 4 <= 256 && 256 % (C / 4) == 0)
+    subsample_dwconv_kernel<bf16, 4><<<grid, 256, 0, st>>>((const bf16*)in, w, b, Tin, Fin, C, Tout, Fout, (bf16*)out);
+  else if (dtype == LCASR_BF16)
+    subsample_dwconv_kernel<bf16, 8><<<grid, 256, 0, st>>>((const bf16*)in, w, b, Tin, Fin, C, Tout, Fout, (bf16*)out);
   else
-    subsample_dwconv_kernel<float><<<grid, 256, 0, st>>>((const float*)in, w, b, Tin, Fin, C, Tout, Fout, (float*)out);
+    subsample_dwconv_kernel<float, 8><<<grid, 256, 0, st>>>((const float*)in, w, b, Tin, Fin, C, Tout, Fout, (float*)out);
   LCASR_LAUNCH_CHECK();
   return 0;
 }

@@ -22,16 +22,17 @@ __device__ __forceinline__ float silu_grad_sb(float x) {
 // 4 unconditional 16-byte loads and 4 stores per thread (instead of 9 predicated gathers per output), one CTA per
 // kBdTB row pairs of one recording, 32-bit index arithmetic.
 constexpr int kBdTB = 2;
+template <int V>  // channels per thread (8: 16-byte accesses; 4: half the registers, twice the resident warps)
 __global__ void __launch_bounds__(256) subsample_dwconv_bwd_data_kernel(const bf16* __restrict__ dout, const float* __restrict__ w,
                                                                         int64_t Tin, int Fin, int C, int64_t Tout, int Fout,
                                                                         bf16* __restrict__ din) {
-  const int cgroups = C / 8;
+  const int cgroups = C / V;
   const int cg = threadIdx.x % cgroups;
-  float wr[8][9];
+  float wr[V][9];
 #pragma unroll
-  for (int c = 0; c < 8; ++c)
+  for (int c = 0; c < V; ++c)
 #pragma unroll
-    for (int k = 0; k < 9; ++k) wr[c][k] = w[(cg * 8 + c) * 9 + k];
+    for (int k = 0; k < 9; ++k) wr[c][k] = w[(cg * V + c) * 9 + k];
   const int64_t b = blockIdx.y;
   const int64_t a0 = (int64_t)blockIdx.x * kBdTB;
   const int Fh = (Fin + 1) / 2;            // column pairs
@@ -43,36 +44,36 @@ __global__ void __launch_bounds__(256) subsample_dwconv_bwd_data_kernel(const bf
     const int e = (idx - al * per_row) / cgroups;
     const int64_t a = a0 + al;
     if (2 * a >= Tin) break;
-    float g00[8], g01[8], g10[8], g11[8];
+    float g00[V], g01[V], g10[V], g11[V];
     const bool r1 = a + 1 < Tout, c1 = e + 1 < Fout, r0 = a < Tout, c0 = e < Fout;
-    auto ld = [&](float (&g)[8], bool ok, int64_t to, int fo) {
-      if (ok) Vec8<bf16>::load(doutb + ((to * Fout + fo) * C + cg * 8), g);
+    auto ld = [&](float (&g)[V], bool ok, int64_t to, int fo) {
+      if (ok) VecB<V>::load(doutb + ((to * Fout + fo) * C + cg * V), g);
       else {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) g[c] = 0.f;
+        for (int c = 0; c < V; ++c) g[c] = 0.f;
       }
     };
     ld(g00, r0 && c0, a, e); ld(g01, r0 && c1, a, e + 1); ld(g10, r1 && c0, a + 1, e); ld(g11, r1 && c1, a + 1, e + 1);
-    float o[8];
+    float o[V];
     const int64_t ti = 2 * a;
     const int fi = 2 * e;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) o[c] = g00[c] * wr[c][4];
-    Vec8<bf16>::store(dinb + ((ti * Fin + fi) * C + cg * 8), o);
+    for (int c = 0; c < V; ++c) o[c] = g00[c] * wr[c][4];
+    VecB<V>::store(dinb + ((ti * Fin + fi) * C + cg * V), o);
     if (fi + 1 < Fin) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) o[c] = fmaf(g00[c], wr[c][5], g01[c] * wr[c][3]);
-      Vec8<bf16>::store(dinb + ((ti * Fin + fi + 1) * C + cg * 8), o);
+      for (int c = 0; c < V; ++c) o[c] = fmaf(g00[c], wr[c][5], g01[c] * wr[c][3]);
+      VecB<V>::store(dinb + ((ti * Fin + fi + 1) * C + cg * V), o);
     }
     if (ti + 1 < Tin) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) o[c] = fmaf(g00[c], wr[c][7], g10[c] * wr[c][1]);
-      Vec8<bf16>::store(dinb + (((ti + 1) * Fin + fi) * C + cg * 8), o);
+      for (int c = 0; c < V; ++c) o[c] = fmaf(g00[c], wr[c][7], g10[c] * wr[c][1]);
+      VecB<V>::store(dinb + (((ti + 1) * Fin + fi) * C + cg * V), o);
       if (fi + 1 < Fin) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
+        for (int c = 0; c < V; ++c)
           o[c] = fmaf(g00[c], wr[c][8], fmaf(g01[c], wr[c][6], fmaf(g10[c], wr[c][2], g11[c] * wr[c][0])));
-        Vec8<bf16>::store(dinb + (((ti + 1) * Fin + fi + 1) * C + cg * 8), o);
+        VecB<V>::store(dinb + (((ti + 1) * Fin + fi + 1) * C + cg * V), o);
       }
     }
   }
@@ -82,17 +83,18 @@ __global__ void __launch_bounds__(256) subsample_dwconv_bwd_data_kernel(const bf
 // CTAs stride over blocks of kBwTB output rows (grid.x of them per recording); register accumulators, one
 // shared-memory reduction and C*10 global atomics per CTA.
 constexpr int kBwTB = 4;
+template <int V>
 __global__ void __launch_bounds__(256) subsample_dwconv_bwd_weight_kernel(const bf16* __restrict__ in, const bf16* __restrict__ dout,
                                                                           int64_t Tin, int Fin, int C, int64_t Tout, int Fout,
                                                                           float* __restrict__ dw, float* __restrict__ db) {
   extern __shared__ float sacc[];  // [C][10]
   for (int i = threadIdx.x; i < C * 10; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
-  const int cgroups = C / 8;
+  const int cgroups = C / V;
   const int cg = threadIdx.x % cgroups;
-  float aw[8][9], ab[8];
+  float aw[V][9], ab[V];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < V; ++c) {
     ab[c] = 0.f;
 #pragma unroll
     for (int k = 0; k < 9; ++k) aw[c][k] = 0.f;
@@ -109,10 +111,10 @@ __global__ void __launch_bounds__(256) subsample_dwconv_bwd_weight_kernel(const 
       const int fo = (idx - tl * per_row) / cgroups;
       const int64_t to = t0 + tl;
       if (to >= Tout) break;
-      float g[8];
-      Vec8<bf16>::load(doutb + ((to * Fout + fo) * C + cg * 8), g);
+      float g[V];
+      VecB<V>::load(doutb + ((to * Fout + fo) * C + cg * V), g);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) ab[c] += g[c];
+      for (int c = 0; c < V; ++c) ab[c] += g[c];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         const int64_t ti = 2 * to - 1 + i;
@@ -121,19 +123,19 @@ __global__ void __launch_bounds__(256) subsample_dwconv_bwd_weight_kernel(const 
         for (int j = 0; j < 3; ++j) {
           const int fi = 2 * fo - 1 + j;
           if (fi < 0 || fi >= Fin) continue;
-          float v[8];
-          Vec8<bf16>::load(inb + ((ti * Fin + fi) * C + cg * 8), v);
+          float v[V];
+          VecB<V>::load(inb + ((ti * Fin + fi) * C + cg * V), v);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) aw[c][i * 3 + j] = fmaf(g[c], v[c], aw[c][i * 3 + j]);
+          for (int c = 0; c < V; ++c) aw[c][i * 3 + j] = fmaf(g[c], v[c], aw[c][i * 3 + j]);
         }
       }
     }
   }
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < V; ++c) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) atomicAdd(&sacc[(cg * 8 + c) * 10 + k], aw[c][k]);
-    atomicAdd(&sacc[(cg * 8 + c) * 10 + 9], ab[c]);
+    for (int k = 0; k < 9; ++k) atomicAdd(&sacc[(cg * V + c) * 10 + k], aw[c][k]);
+    atomicAdd(&sacc[(cg * V + c) * 10 + 9], ab[c]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C * 10; i += blockDim.x) {
@@ -242,8 +244,10 @@ extern "C" int lcasr_subsample_dwconv_bwd_data(const void* dout, const float* w,
   const int Fout = (Fin - 1) / 2 + 1;
   LCASR_CHECK_ARG(B <= 65535 && ceil_div(Tin, 2 * kBdTB) <= 0x7fffffff, "subsample_dwconv_bwd_data: grid too large");
   dim3 grid((unsigned)ceil_div(ceil_div(Tin, 2), kBdTB), (unsigned)B);
-  subsample_dwconv_bwd_data_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dout, w, Tin, Fin, C, Tout, Fout,
-                                                                          (bf16*)din);
+  if (C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0)
+    subsample_dwconv_bwd_data_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dout, w, Tin, Fin, C, Tout, Fout, (bf16*)din);
+  else
+    subsample_dwconv_bwd_data_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dout, w, Tin, Fin, C, Tout, Fout, (bf16*)din);
   LCASR_LAUNCH_CHECK();
   return 0;
 }
@@ -258,8 +262,12 @@ extern "C" int lcasr_subsample_dwconv_bwd_weight(const void* in, const void* dou
   int64_t gx = ceil_div((int64_t)kNumSMs * 8, B);  // ~8 CTAs per SM in total
   if (gx > ceil_div(Tout, kBwTB)) gx = ceil_div(Tout, kBwTB);
   dim3 grid((unsigned)gx, (unsigned)B);
-  subsample_dwconv_bwd_weight_kernel<<<grid, 256, (size_t)C * 40, (cudaStream_t)stream>>>(
-      (const bf16*)in, (const bf16*)dout, Tin, Fin, C, Tout, Fout, dw, db);
+  if (C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0)
+    subsample_dwconv_bwd_weight_kernel<4><<<grid, 256, (size_t)C * 40, (cudaStream_t)stream>>>(
+        (const bf16*)in, (const bf16*)dout, Tin, Fin, C, Tout, Fout, dw, db);
+  else
+    subsample_dwconv_bwd_weight_kernel<8><<<grid, 256, (size_t)C * 40, (cudaStream_t)stream>>>(
+        (const bf16*)in, (const bf16*)dout, Tin, Fin, C, Tout, Fout, dw, db);
   LCASR_LAUNCH_CHECK();
   return 0;
 }
