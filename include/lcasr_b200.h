@@ -163,6 +163,14 @@ int lcasr_ctc_loss_bwd(const float* log_probs, int B, int64_t N, int V, const in
                        int blank, const float* nll, const float* grad_nll, const float* alpha_ws,
                        float* beta_ws, float* grad, void* stream);
 
+/* Long-form moving-window merge (lcasr/eval/utils.py:45-111 fetch_logits): window k occupies rows
+ * [win_row0[k], win_row0[k] + win_len[k]) of logp [*, V] (fp32 log-probs) and covers merged frames
+ * [win_pos[k], win_pos[k] + win_len[k]); windows sorted by win_pos, max_len = max win_len.  For every merged frame:
+ * out = log(mean over covering windows of exp(logp)) (optional, [n_total, V]) and argmax (optional, [n_total]). */
+int lcasr_window_merge(const float* logp, int V, int K, const int64_t* win_row0, const int32_t* win_len,
+                       const int32_t* win_pos, int max_len, int64_t n_total, float* out, int32_t* argmax,
+                       void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Training step (cfg 5): the operators behind loss.backward() of exp/train.py:249-262.  The
  * reference gets these from torch.autograd over the modules of SURVEY §8 a3-a11; here each is

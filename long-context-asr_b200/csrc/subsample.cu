@@ -246,7 +246,8 @@ extern "C" int lcasr_subsample_dwconv(const void* in, int dtype, const float* w,
   LCASR_CHECK_ARG(B <= 65535 && ceil_div(Tout, kDwTB) <= 0x7fffffff, "subsample_dwconv: grid too large");
   dim3 grid((unsigned)ceil_div(Tout, kDwTB), (unsigned)B);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == LCASR_BF16 && C / 4 <= 256 && 256 % (C / 4) == 0)
+  static const bool narrow = getenv("LCASR_SUBSAMPLE_V4") != nullptr;  // measured slower (801 vs 685 us): kept for A/B runs
+  if (narrow && dtype == LCASR_BF16 && C / 4 <= 256 && 256 % (C / 4) == 0)
     subsample_dwconv_kernel<bf16, 4><<<grid, 256, 0, st>>>((const bf16*)in, w, b, Tin, Fin, C, Tout, Fout, (bf16*)out);
   else if (dtype == LCASR_BF16)
     subsample_dwconv_kernel<bf16, 8><<<grid, 256, 0, st>>>((const bf16*)in, w, b, Tin, Fin, C, Tout, Fout, (bf16*)out);

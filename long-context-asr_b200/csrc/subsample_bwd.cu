@@ -6,6 +6,7 @@
 //   conv0 weight grad    : reads the spectrogram (x C/64 from L2) and the conv0 output gradient once; the conv0
 //                          pre-activation is recomputed from the spectrogram instead of being stored
 #include "common.cuh"
+#include <cstdlib>
 
 namespace lcasr {
 
@@ -262,7 +263,8 @@ extern "C" int lcasr_subsample_dwconv_bwd_weight(const void* in, const void* dou
   int64_t gx = ceil_div((int64_t)kNumSMs * 8, B);  // ~8 CTAs per SM in total
   if (gx > ceil_div(Tout, kBwTB)) gx = ceil_div(Tout, kBwTB);
   dim3 grid((unsigned)gx, (unsigned)B);
-  if (C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0)
+  static const bool narrow = getenv("LCASR_SUBSAMPLE_V4") != nullptr;  // measured slower (856 vs 766 us): kept for A/B runs
+  if (narrow && C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0)
     subsample_dwconv_bwd_weight_kernel<4><<<grid, 256, (size_t)C * 40, (cudaStream_t)stream>>>(
         (const bf16*)in, (const bf16*)dout, Tin, Fin, C, Tout, Fout, dw, db);
   else

@@ -495,3 +495,46 @@ def training_step(sd: Dict[str, Tensor], cfg: dict, x: Tensor, targets: Tensor, 
     loss.backward()
     grads = {k: v.grad for k, v in leaves.items() if isinstance(v, Tensor) and v.requires_grad and v.grad is not None}
     return float(loss.detach()), grads, new_stats, lp.detach()
+
+
+# --------------------------------------------------------------------------------------------
+# long-form moving-window inference (lcasr/eval/utils.py:45-111, fetch_logits)
+# --------------------------------------------------------------------------------------------
+
+def fetch_logits(sd: Dict[str, Tensor], cfg: dict, spec: Tensor, seq_len: int, overlap: int) -> np.ndarray:
+    """Restatement of the reference's window loop: windows of `seq_len` frames every seq_len - overlap frames, each
+    run through the encoder on its own, exp(log-probs) summed into a position-indexed buffer with per-position
+    counts, mean, log.  The loop stops after the first window shorter than its predecessor (utils.py:75-79).
+    spec [1, feat, T] -> float32 [N, V+1]."""
+    spec_n = spec.shape[-1]
+    ds = cfg["subsampling_factor"]
+    V1 = cfg["vocab_size"] + 1
+    if seq_len > spec_n:
+        seq_len, overlap = spec_n, 0
+    assert overlap / ds == overlap // ds, "Overlap must be a multiple of the downsampling factor"
+    all_logits = torch.zeros((1, spec_n // 4 + seq_len, V1))
+    logit_count = torch.zeros((1, spec_n // 4 + seq_len, V1))
+    logit_position, last_ulen, kill_next = 0, None, False
+    for i in range(0, spec_n, seq_len - overlap):
+        chunk = spec[:, :, i:i + seq_len]
+        u_len = chunk.shape[-1]
+        if kill_next:
+            break
+        if last_ulen is not None and u_len < last_ulen:
+            kill_next = True
+        last_ulen = u_len
+        with torch.no_grad():
+            lp, _ = encoder_forward(sd, cfg, chunk)
+        probs = torch.exp(lp)
+        ds_len = probs.shape[-2]
+        ratio = u_len / ds_len
+        overlap_ds = int(overlap / ratio)
+        if i != 0:
+            logit_position -= overlap_ds
+        logit_count[:, logit_position:logit_position + ds_len, :] += 1
+        all_logits[:, logit_position:logit_position + ds_len, :] += probs
+        logit_position += ds_len
+    keep = logit_count.sum(dim=-1) != 0
+    all_logits = all_logits[keep].reshape(1, -1, V1)
+    logit_count = logit_count[keep].reshape(1, -1, V1)
+    return torch.log(all_logits / logit_count).squeeze(0).numpy()
