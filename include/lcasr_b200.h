@@ -296,6 +296,34 @@ int lcasr_ctc_loss_grad(const float* log_probs, int B, int64_t N, int V, const i
                         const float* beta_ws, float* grad, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Optimizer step of the training loop: exp/train.py:46-61 (clip_grad_norm_ + optimizer.step) with
+ * MADGRAD (lcasr/optim/madgrad.py:81-212, dense fp32 branch), as multi-tensor kernels.
+ * `tensors` is a DEVICE array; work is cut into chunks of lcasr_opt_chunk_elems() elements:
+ * chunk c covers elements [chunk_index[c]*E, +E) of tensor chunk_tensor[c].  g == NULL: skipped.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct lcasr_opt_tensor {
+  float* p;          /* parameter, updated in place */
+  const float* g;    /* gradient (or NULL) */
+  float* gss;        /* state: grad_sum_sq */
+  float* s;          /* state: s */
+  float* x0;         /* state: x0 (momentum != 0) */
+  int64_t n;
+} lcasr_opt_tensor;
+int lcasr_opt_chunk_elems(void);
+/* *sumsq = sum over all gradients of g^2 (the square of clip_grad_norm_'s total norm) */
+int lcasr_grad_sumsq(const lcasr_opt_tensor* tensors, const int32_t* chunk_tensor, const int32_t* chunk_index,
+                     int n_chunks, float* sumsq, void* stream);
+/* g *= min(1, max_norm / (sqrt(*sumsq) + 1e-6)) in place (torch.nn.utils.clip_grad_norm_) */
+int lcasr_grad_scale(const lcasr_opt_tensor* tensors, const int32_t* chunk_tensor, const int32_t* chunk_index,
+                     int n_chunks, const float* sumsq, float max_norm, void* stream);
+/* one MADGRAD step on every tensor; lr = the group's lr (+eps if non-zero, madgrad.py:104), lamb = lr*sqrt(k+1).
+ * sumsq != NULL and max_norm > 0: the clip coefficient is applied to the gradients on the fly (read from device
+ * memory: no host synchronisation); the gradients themselves are left untouched. */
+int lcasr_madgrad_step(const lcasr_opt_tensor* tensors, const int32_t* chunk_tensor, const int32_t* chunk_index,
+                       int n_chunks, const float* sumsq, float max_norm, float lr, float lamb, float eps,
+                       float weight_decay, float momentum, int decouple_decay, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * The model: SCConformerXL.forward (lcasr/models/sconformer_xl.py:162-252), equal-length path
  * ---------------------------------------------------------------------------------------- */
 

@@ -62,6 +62,11 @@ class LcasrGemmExArgs(C.Structure):
                 [("alpha", f32), ("epi", i32), ("out_dtype", i32), ("ksplit", i32)])
 
 
+class LcasrOptTensor(C.Structure):
+    """mirror of lcasr_opt_tensor"""
+    _fields_ = [("p", vp), ("g", vp), ("gss", vp), ("s", vp), ("x0", vp), ("n", i64)]
+
+
 # name -> argtypes; every function returns int status unless listed in _OTHER_RESTYPE
 _SIGNATURES = {
     "lcasr_layernorm": [vp, vp, vp, i64, i32, f32, i32, vp, vp, i32, vp],
@@ -84,6 +89,9 @@ _SIGNATURES = {
     "lcasr_greedy_collapse": [vp, i32, i64, vp, i32, vp, vp, vp],
     "lcasr_ctc_loss_fwd": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp],
     "lcasr_ctc_loss_bwd": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp],
+    "lcasr_grad_sumsq": [vp, vp, vp, i32, vp, vp],
+    "lcasr_grad_scale": [vp, vp, vp, i32, vp, f32, vp],
+    "lcasr_madgrad_step": [vp, vp, vp, i32, vp, f32, f32, f32, f32, f32, f32, i32, vp],
     "lcasr_window_merge": [vp, i32, i32, vp, vp, vp, i32, i64, vp, vp, vp],
     "lcasr_ctc_loss_fwd_ab": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp, vp],
     "lcasr_ctc_loss_grad": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp],
@@ -123,6 +131,7 @@ _SIGNATURES = {
 }
 _OTHER = {
     "lcasr_abi_version": ([], i32),
+    "lcasr_opt_chunk_elems": ([], i32),
     "lcasr_last_error": ([], C.c_char_p),
     "lcasr_launch_count": ([], i64),
     "lcasr_reset_launch_count": ([], None),

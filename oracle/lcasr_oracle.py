@@ -538,3 +538,46 @@ def fetch_logits(sd: Dict[str, Tensor], cfg: dict, spec: Tensor, seq_len: int, o
     all_logits = all_logits[keep].reshape(1, -1, V1)
     logit_count = logit_count[keep].reshape(1, -1, V1)
     return torch.log(all_logits / logit_count).squeeze(0).numpy()
+
+
+# --------------------------------------------------------------------------------------------
+# optimizer step (exp/train.py:46-61: clip_grad_norm_ then MADGRAD, lcasr/optim/madgrad.py:81-212 dense branch)
+# --------------------------------------------------------------------------------------------
+
+def clip_grad_norm(grads, max_norm: float):
+    """torch.nn.utils.clip_grad_norm_: total L2 norm over all gradients, coefficient clamp(max_norm/(norm+1e-6), max=1)."""
+    total = math.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads))
+    coef = min(max_norm / (total + 1e-6), 1.0)
+    return [(g * np.float32(coef)).astype(np.float32) for g in grads], total
+
+
+def madgrad_step(p, g, state, k: int, lr: float, momentum: float = 0.9, weight_decay: float = 0.0, eps: float = 1e-6,
+                 decouple_decay: bool = False):
+    """one MADGRAD step on one fp32 array (in numpy fp32); `state` holds grad_sum_sq, s, x0 and is updated."""
+    f = np.float32
+    if lr != 0.0:
+        lr = lr + eps
+    ck = 1 - momentum
+    lamb = lr * math.pow(k + 1, 0.5)
+    if "grad_sum_sq" not in state:
+        state["grad_sum_sq"], state["s"] = np.zeros_like(p), np.zeros_like(p)
+        if momentum != 0:
+            state["x0"] = p.copy()
+    g = g.astype(f)
+    if weight_decay != 0 and not decouple_decay:
+        g = g + f(weight_decay) * p
+    if momentum == 0:
+        rms = np.power(state["grad_sum_sq"], f(1 / 3)) + f(eps)
+        x0 = p + state["s"] / rms
+    else:
+        x0 = state["x0"]
+    state["grad_sum_sq"] = state["grad_sum_sq"] + f(lamb) * g * g
+    rms = np.power(state["grad_sum_sq"], f(1 / 3)) + f(eps)
+    if eps == 0:
+        rms[rms == 0] = np.inf
+    state["s"] = state["s"] + f(lamb) * g
+    z = x0 - state["s"] / rms
+    p_new = z if momentum == 0 else p * f(1 - ck) + f(ck) * z
+    if weight_decay != 0 and decouple_decay:
+        p_new = p_new - f(lr * weight_decay) * p
+    return p_new.astype(f)
