@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LCASR_ABI_VERSION 1
+#define LCASR_ABI_VERSION 2
 
 enum { LCASR_F32 = 0, LCASR_BF16 = 1 };
 enum { LCASR_OK = 0, LCASR_E_BADARG = -1, LCASR_E_UNSUPPORTED = -2, LCASR_E_CUDA = -3, LCASR_E_NOMEM = -4 };
@@ -120,6 +120,14 @@ int lcasr_attention_cross(const void* q, const void* k, const void* v, int dtype
 int lcasr_attention_masked(const void* q, const void* k, const void* v, int dtype, int B, int64_t Nq,
                            int64_t Nk, const int32_t* kv_len, int H, int Dh, void* out, int impl,
                            void* stream);
+
+/* Local (windowed) self-attention, flash-attn window_size=(win_left, win_right) semantics (attention.py:466,
+ * 527-530; the 'windowed_attention' evaluation mode of eval/run.py:38-43): query i attends to keys
+ * [i - win_left, i + win_right]; -1 = unlimited on that side.  kv_len may be NULL.  Key tiles outside a CTA's band
+ * are skipped, so the cost is O(N * window) instead of O(N^2). */
+int lcasr_attention_window(const void* q, const void* k, const void* v, int dtype, int B, int64_t N,
+                           const int32_t* kv_len, int H, int Dh, int win_left, int win_right, void* out,
+                           int impl, void* stream);
 
 /* GLU that writes zeros for tokens n >= lengths[b] (convolution.py:107-110: glu then masked_fill). */
 int lcasr_glu_masked(const void* in, int dtype, int B, int64_t N, int d, const int32_t* lengths, void* out,
@@ -340,6 +348,8 @@ typedef struct lcasr_config {
   int32_t compute_dtype;      /* LCASR_BF16 (tcgen05 path) or LCASR_F32 (SIMT fp32 parity mode) */
   float   rotary_interp;      /* rotary_interpolation_factor */
   float   norm_eps;           /* 1e-5 (LayerNorm) / 1e-8 (RMSNorm) */
+  int32_t attn_window_left;   /* attention_window_size(_left): keys [i - left, i + right]; -1 = unlimited (ABI 2) */
+  int32_t attn_window_right;
 } lcasr_config;
 
 /* Matrices ("*_w" of rank 2) are in `compute_dtype`; every vector and every depthwise filter is

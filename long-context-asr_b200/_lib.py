@@ -9,14 +9,14 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblcasr_b200.so")
+LIB_PATH = os.environ.get("LCASR_LIB_PATH") or os.path.join(_HERE, "liblcasr_b200.so")  # env: A/B runs of two builds
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_GELU_TANH, ACT_SILU = 0, 1, 2
 NORM_LAYERNORM, NORM_RMSNORM = 0, 1
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
 ATTN_AUTO, ATTN_SIMT, ATTN_TCGEN05 = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -25,7 +25,8 @@ class LcasrConfig(C.Structure):
     _fields_ = [(n, i32) for n in (
         "abi_version", "n_layers", "d_model", "n_heads", "head_dim", "feat_in", "conv_channels",
         "conv_kernel_size", "num_classes", "norm_kind", "decoder_norm", "use_rotary", "self_conditioning",
-        "legasee_double_norm", "bias_in_ff", "compute_dtype")] + [("rotary_interp", f32), ("norm_eps", f32)]
+        "legasee_double_norm", "bias_in_ff", "compute_dtype")] + [("rotary_interp", f32), ("norm_eps", f32),
+                                                                    ("attn_window_left", i32), ("attn_window_right", i32)]
 
 
 LAYER_FIELDS = (
@@ -81,6 +82,7 @@ _SIGNATURES = {
     "lcasr_attention": [vp, vp, vp, i32, i32, i64, i32, i32, i32, i64, vp, i32, vp],
     "lcasr_attention_cross": [vp, vp, vp, i32, i32, i64, i64, i32, i32, vp, i32, vp],
     "lcasr_attention_masked": [vp, vp, vp, i32, i32, i64, i64, vp, i32, i32, vp, i32, vp],
+    "lcasr_attention_window": [vp, vp, vp, i32, i32, i64, vp, i32, i32, i32, i32, vp, i32, vp],
     "lcasr_glu_masked": [vp, i32, i32, i64, i32, vp, vp, vp],
     "lcasr_dwconv_brn_silu": [vp, i32, i32, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp],
     "lcasr_softmax": [vp, i32, i64, i32, vp, i32, vp],

@@ -24,9 +24,9 @@ int gemm_simt_launch(const void* A, const void* W, int ab_dtype, int64_t M, int 
 int gemm_tc_launch(const void* A, const void* W, int64_t M, int N, int K, const float* bias, int act, const float* resid,
                    float alpha, void* out, int out_dtype, cudaStream_t st, void* pre_out = nullptr);
 int attn_simt_launch(const void* q, const void* k, const void* v, int dtype, int B, int64_t N, int64_t Nk, const int32_t* kv_len,
-                     int H, int Dh, int v_transposed, int64_t Npad, void* out, cudaStream_t st);
+                     int H, int Dh, int v_transposed, int64_t Npad, void* out, cudaStream_t st, int wl = -1, int wr = -1);
 int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len, int H,
-                   int Dh, int v_transposed, int64_t Npad, void* out, float* lse, cudaStream_t st);
+                   int Dh, int v_transposed, int64_t Npad, void* out, float* lse, cudaStream_t st, int wl = -1, int wr = -1);
 
 }  // namespace lcasr
 
@@ -64,7 +64,7 @@ extern "C" int lcasr_gemm(const void* A, const void* W, int ab_dtype, int64_t M,
 
 static int attention_dispatch(const void* q, const void* k, const void* v, int dtype, int B, int64_t N, int64_t Nk,
                               const int32_t* kv_len, int H, int Dh, int v_transposed, int64_t Npad, void* out, int impl,
-                              void* stream) {
+                              void* stream, int wl = -1, int wr = -1) {
   LCASR_CHECK_ARG(q && k && v && out, "attention: NULL operand");
   LCASR_CHECK_ARG(B > 0 && N > 0 && Nk > 0 && H > 0 && Dh > 0, "attention: bad shape");
   LCASR_CHECK_ARG(dtype == LCASR_F32 || dtype == LCASR_BF16, "attention: bad dtype %d", dtype);
@@ -73,10 +73,10 @@ static int attention_dispatch(const void* q, const void* k, const void* v, int d
   if (impl == LCASR_ATTN_AUTO) impl = dtype == LCASR_BF16 ? LCASR_ATTN_TCGEN05 : LCASR_ATTN_SIMT;
   if (impl == LCASR_ATTN_TCGEN05) {
     LCASR_CHECK_ARG(dtype == LCASR_BF16, "attention: the tcgen05 kernel takes bf16 operands");
-    return attn_tc_launch(q, k, v, B, N, Nk, kv_len, H, Dh, v_transposed, Npad, out, nullptr, st);
+    return attn_tc_launch(q, k, v, B, N, Nk, kv_len, H, Dh, v_transposed, Npad, out, nullptr, st, wl, wr);
   }
   LCASR_CHECK_ARG(impl == LCASR_ATTN_SIMT, "attention: bad impl %d", impl);
-  return attn_simt_launch(q, k, v, dtype, B, N, Nk, kv_len, H, Dh, v_transposed, Npad, out, st);
+  return attn_simt_launch(q, k, v, dtype, B, N, Nk, kv_len, H, Dh, v_transposed, Npad, out, st, wl, wr);
 }
 
 extern "C" int lcasr_attention(const void* q, const void* k, const void* v, int dtype, int B, int64_t N, int H, int Dh,
@@ -109,4 +109,11 @@ extern "C" int lcasr_gemm_act_pre(const void* A, const void* W, int64_t M, int N
   LCASR_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_act_pre: bad shape");
   LCASR_CHECK_ARG(act == LCASR_ACT_GELU_TANH || act == LCASR_ACT_SILU, "gemm_act_pre: bad activation %d", act);
   return gemm_tc_launch(A, W, M, N, K, bias, act, nullptr, 0.f, out, LCASR_BF16, (cudaStream_t)stream, pre_out);
+}
+
+// local (windowed) self-attention: query i attends to keys [i - win_left, i + win_right] (-1 = unlimited on that side)
+extern "C" int lcasr_attention_window(const void* q, const void* k, const void* v, int dtype, int B, int64_t N, const int32_t* kv_len,
+                                      int H, int Dh, int win_left, int win_right, void* out, int impl, void* stream) {
+  LCASR_CHECK_ARG(win_left >= -1 && win_right >= -1, "attention_window: bad window (%d, %d)", win_left, win_right);
+  return attention_dispatch(q, k, v, dtype, B, N, N, kv_len, H, Dh, 0, 0, out, impl, stream, win_left, win_right);
 }

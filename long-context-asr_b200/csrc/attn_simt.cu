@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(SA_THREADS) attn_simt_kernel(const T* __restri
                                                                const T* __restrict__ v, int64_t N, int64_t Nk,
                                                                const int32_t* __restrict__ kv_len, int H,
                                                                int v_transposed, int64_t Npad, float scale,
-                                                               T* __restrict__ out) {  // N query rows, Nk keys per batch entry
+                                                               T* __restrict__ out, int win_left, int win_right) {  // N query rows, Nk keys per batch entry
   extern __shared__ float smem[];
   constexpr int LD = DH + 1;
   float* Qs = smem;                    // [64][DH+1]
@@ -48,7 +48,11 @@ __global__ void __launch_bounds__(SA_THREADS) attn_simt_kernel(const T* __restri
 #pragma unroll
     for (int j = 0; j < OC; ++j) o_acc[i][j] = 0.f;
 
-  for (int64_t k0 = 0; k0 < Nkv; k0 += SA_BK) {
+  // local attention (win_* >= 0): query i sees keys [i - win_left, i + win_right]; tiles outside the band are skipped
+  const int64_t q_first = (int64_t)blockIdx.x * SA_BQ;
+  const int64_t k_begin = win_left >= 0 ? (max(q_first - win_left, (int64_t)0) / SA_BK) * SA_BK : 0;
+  const int64_t k_end = win_right >= 0 ? min(Nkv, q_first + SA_BQ - 1 + win_right + 1) : Nkv;
+  for (int64_t k0 = k_begin; k0 < k_end; k0 += SA_BK) {
     __syncthreads();
     for (int idx = tid; idx < SA_BK * DH; idx += SA_THREADS) {
       int r = idx / DH, c = idx % DH;
@@ -84,7 +88,9 @@ __global__ void __launch_bounds__(SA_THREADS) attn_simt_kernel(const T* __restri
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         int64_t n = k0 + tx * 4 + j;
-        Ss[(ty * 4 + i) * (SA_BK + 1) + tx * 4 + j] = n < Nkv ? s[i][j] : -INFINITY;
+        const int64_t qi = q_first + ty * 4 + i;
+        const bool in_band = (win_left < 0 || n >= qi - win_left) && (win_right < 0 || n <= qi + win_right);
+        Ss[(ty * 4 + i) * (SA_BK + 1) + tx * 4 + j] = (n < Nkv && in_band) ? s[i][j] : -INFINITY;
       }
     __syncthreads();
     // online softmax: 4 threads per row, 16 columns each
@@ -97,7 +103,7 @@ __global__ void __launch_bounds__(SA_THREADS) attn_simt_kernel(const T* __restri
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
       float m_old = row_m[r];
-      float m_new = fmaxf(m_old, mx);
+      float m_new = fmaxf(fmaxf(m_old, mx), -1e30f);  // stays finite while every key seen so far is masked
       float sum = 0.f;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -150,7 +156,7 @@ __global__ void __launch_bounds__(SA_THREADS) attn_simt_kernel(const T* __restri
 
 template <typename T, int DH>
 static int launch_attn_simt(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len, int H, int vt, int64_t Npad,
-                            void* out, cudaStream_t st) {
+                            void* out, cudaStream_t st, int wl, int wr) {
   size_t smem = sizeof(float) * (2 * SA_BQ * (DH + 1) + SA_BK * DH + SA_BQ * (SA_BK + 1) + 3 * SA_BQ);
   static bool attr_set = false;
   if (!attr_set) {
@@ -160,17 +166,17 @@ static int launch_attn_simt(const void* q, const void* k, const void* v, int B, 
   dim3 grid((unsigned)ceil_div(N, SA_BQ), H, B);
   float scale = 1.0f / sqrtf((float)DH);
   attn_simt_kernel<T, DH><<<grid, SA_THREADS, smem, st>>>((const T*)q, (const T*)k, (const T*)v, N, Nk, kv_len, H, vt, Npad, scale,
-                                                          (T*)out);
+                                                          (T*)out, wl, wr);
   LCASR_LAUNCH_CHECK();
   return 0;
 }
 
 int attn_simt_launch(const void* q, const void* k, const void* v, int dtype, int B, int64_t N, int64_t Nk, const int32_t* kv_len, int H, int Dh,
-                     int v_transposed, int64_t Npad, void* out, cudaStream_t st) {
+                     int v_transposed, int64_t Npad, void* out, cudaStream_t st, int wl, int wr) {
 #define LCASR_SA(DHV)                                                                                     \
   case DHV:                                                                                               \
-    return dtype == LCASR_BF16 ? launch_attn_simt<bf16, DHV>(q, k, v, B, N, Nk, kv_len, H, v_transposed, Npad, out, st) \
-                               : launch_attn_simt<float, DHV>(q, k, v, B, N, Nk, kv_len, H, v_transposed, Npad, out, st);
+    return dtype == LCASR_BF16 ? launch_attn_simt<bf16, DHV>(q, k, v, B, N, Nk, kv_len, H, v_transposed, Npad, out, st, wl, wr) \
+                               : launch_attn_simt<float, DHV>(q, k, v, B, N, Nk, kv_len, H, v_transposed, Npad, out, st, wl, wr);
   switch (Dh) {
     LCASR_SA(32) LCASR_SA(64) LCASR_SA(128)
     default:

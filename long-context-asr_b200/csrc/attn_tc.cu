@@ -333,11 +333,14 @@ template <int DH> struct Fa2Cfg {
   static constexpr int SMEM_TOTAL = SMEM_BYTES + ONES_BYTES;
 };
 
-template <int DH, int POLY>
+template <int DH, int POLY, bool WIN>  // WIN: local-attention instantiation (keeps the band code out of the dense kernel)
 __global__ void __launch_bounds__(FA2_THREADS, 1)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, int64_t N, int64_t Nk, const int32_t* __restrict__ kv_len, int H,
-                float scale_log2, bf16* __restrict__ out, float* __restrict__ lse) {
+                float scale_log2, bf16* __restrict__ out, float* __restrict__ lse, int win_left, int win_right) {
+  // win_left / win_right (-1 = unlimited; self-attention only): local attention, query i sees keys
+  // [i - win_left, i + win_right] (flash-attn window_size, attention.py:466,527-530; eval/run.py:38-43).  Key tiles
+  // outside the band of this CTA's 256 queries are never loaded; tiles crossing a band edge get an element mask.
   // lse (may be NULL; training): [B,H,N] fp32, log2-domain log-sum-exp of the SCALED scores of every query row
   // (lse2 = max*scale*log2e + log2(sum)), so that the backward recomputes P = exp2(s*scale*log2e - lse2)
   // N = query rows per batch entry, Nk = keys per batch entry (row pitch of k/v); kv_len (may be NULL): the
@@ -371,7 +374,15 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int64_t b = blockIdx.z;
   const int64_t q0 = (int64_t)blockIdx.x * (2 * FA_BQ);
   const int64_t Nkv = kv_len ? min((int64_t)kv_len[blockIdx.z], Nk) : Nk;  // valid keys of this batch entry
-  const int n_tiles = (int)((Nkv + FA_BK - 1) / FA_BK);
+  int n_tiles = (int)((Nkv + FA_BK - 1) / FA_BK);
+  int j_lo = 0;  // key tiles [j_lo, j_lo + n_tiles) intersect the band of queries [q0, q0 + 256)
+  if constexpr (WIN) {  // (the dense instantiation keeps exactly the expressions it was tuned with)
+    int j_hi = n_tiles;
+    if (win_left >= 0) j_lo = (int)(max(q0 - win_left, (int64_t)0) / FA_BK);
+    if (win_right >= 0) j_hi = (int)min((int64_t)n_tiles, (min(q0 + 2 * FA_BQ - 1, N - 1) + win_right) / FA_BK + 1);
+    j_lo = min(j_lo, n_tiles - 1);
+    n_tiles = max(j_hi - j_lo, 1);
+  }
 
   if (warp == 8 && lane == 0) {
     prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
@@ -406,7 +417,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int j = 0; j < n_tiles; ++j) {
         mbar_wait(kv_empty(stage), phase ^ 1);
         mbar_arrive_expect_tx(kv_full(stage), Cfg::STAGE_BYTES);
-        const int row_k = (int)(b * Nk + (int64_t)j * FA_BK);
+        const int row_k = (int)(b * Nk + (int64_t)(WIN ? j_lo + j : j) * FA_BK);
 #pragma unroll
         for (int i = 0; i < Cfg::SUB; ++i) {
           tma_load_2d(k_smem(stage) + i * Cfg::KV_SUB_BYTES, &tmK, kv_full(stage), h * DH + i * Cfg::SUB_COLS, row_k);
@@ -590,11 +601,25 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(s_free(t));
       }
-      const int64_t valid = Nkv - (int64_t)j * FA_BK;
+      const int64_t kbase = (int64_t)(WIN ? j_lo + j : j) * FA_BK;  // first key of this tile
+      const int64_t valid = Nkv - kbase;
       if (valid < FA_BK) {
 #pragma unroll
         for (int i = 0; i < FA_BK; ++i)
           if (i >= valid) s[i] = 0xff800000u;  // -inf: key does not exist
+      }
+      if constexpr (WIN) {  // band edges: warp-uniform test on the warp's 32 rows, element mask only in edge tiles
+        const int64_t r_first = q0 + t * FA_BQ + lane_base;
+        const bool edge = (win_left >= 0 && r_first + 31 - win_left > kbase) ||
+                          (win_right >= 0 && r_first + win_right < kbase + FA_BK - 1);
+        if (edge) {
+          const int64_t r = r_first + lane;
+          const int lo_i = win_left >= 0 ? (int)max(r - win_left - kbase, (int64_t)0) : 0;
+          const int hi_i = win_right >= 0 ? (int)min(r + win_right - kbase, (int64_t)FA_BK - 1) : FA_BK - 1;
+#pragma unroll
+          for (int i = 0; i < FA_BK; ++i)
+            if (i < lo_i || i > hi_i) s[i] = 0xff800000u;
+        }
       }
       float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
@@ -603,7 +628,9 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int u = 0; u < 4; ++u)
           asm("max.f32 %0, %0, %1, %2;" : "+f"(mxa[u]) : "f"(__uint_as_float(s[i + 2 * u])), "f"(__uint_as_float(s[i + 2 * u + 1])));
       }
-      const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])) * scale_log2;
+      // (local attention: a row whose keys in this tile are all masked has mx = -inf; keep the running maximum finite)
+      float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])) * scale_log2;
+      if constexpr (WIN) mx = fmaxf(mx, -1e30f);
       if (j == 0) {
         m_run = mx;
       } else {
@@ -713,9 +740,9 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-template <int DH, int POLY>
+template <int DH, int POLY, bool WIN = false>
 static int launch_attn_tc2(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len,
-                           int H, void* out, float* lse, cudaStream_t st) {
+                           int H, void* out, float* lse, int wl, int wr, cudaStream_t st) {
   using Cfg = Fa2Cfg<DH>;
   const uint64_t d = (uint64_t)H * DH;
   const CUtensorMapSwizzle sw = DH >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -725,12 +752,12 @@ static int launch_attn_tc2(const void* q, const void* k, const void* v, int B, i
   LCASR_TRY(make_tmap_2d_bf16(&tmV, v, (uint64_t)B * Nk, d, d * 2, FA_BK, Cfg::SUB_COLS, sw));
   static bool attr_set = false;
   if (!attr_set) {
-    LCASR_CUDA(cudaFuncSetAttribute(attn_tc2_kernel<DH, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
+    LCASR_CUDA(cudaFuncSetAttribute(attn_tc2_kernel<DH, POLY, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div(N, 2 * FA_BQ), (unsigned)H, (unsigned)B);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)DH);
-  attn_tc2_kernel<DH, POLY><<<grid, FA2_THREADS, Cfg::SMEM_TOTAL, st>>>(tmQ, tmK, tmV, N, Nk, kv_len, H, scale_log2, (bf16*)out, lse);
+  attn_tc2_kernel<DH, POLY, WIN><<<grid, FA2_THREADS, Cfg::SMEM_TOTAL, st>>>(tmQ, tmK, tmV, N, Nk, kv_len, H, scale_log2, (bf16*)out, lse, wl, wr);
   LCASR_LAUNCH_CHECK();
   return 0;
 }
@@ -775,7 +802,8 @@ static int launch_attn_tc(const void* q, const void* k, const void* v, int B, in
 }
 
 int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len, int H,
-                   int Dh, int v_transposed, int64_t Npad, void* out, float* lse, cudaStream_t st) {
+                   int Dh, int v_transposed, int64_t Npad, void* out, float* lse, cudaStream_t st, int wl, int wr) {
+  LCASR_CHECK_ARG((wl < 0 && wr < 0) || (!v_transposed && N == Nk), "attention(tcgen05): a window needs self-attention and the natural V layout");
   LCASR_CHECK_ARG(!lse || !v_transposed, "attention(tcgen05): the log-sum-exp output needs the natural V layout");
   LCASR_CHECK_ARG(!kv_len || !v_transposed, "attention(tcgen05): key lengths need the natural V layout");
   LCASR_CHECK_ARG(Nk == N || !v_transposed, "attention(tcgen05): Nq != Nk needs the natural V layout");
@@ -790,14 +818,15 @@ int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N
 #define LCASR_FA(DHV)                                                                                             \
   case DHV:                                                                                                       \
     if (v_transposed) return launch_attn_tc<DHV, true>(q, k, v, B, N, H, Npad, out, st);                          \
+    if (wl >= 0 || wr >= 0) return launch_attn_tc2<DHV, 4, true>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                 \
     if (force_v1 && Nk == N && !kv_len && !lse) return launch_attn_tc<DHV, false>(q, k, v, B, N, H, Npad, out, st);                  \
     switch (poly) {                                                                                               \
-      case 0: return launch_attn_tc2<DHV, 0>(q, k, v, B, N, Nk, kv_len, H, out, lse, st);                                          \
-      case 1: return launch_attn_tc2<DHV, 1>(q, k, v, B, N, Nk, kv_len, H, out, lse, st);                                          \
-      case 2: return launch_attn_tc2<DHV, 2>(q, k, v, B, N, Nk, kv_len, H, out, lse, st);                                          \
-      case 8: return launch_attn_tc2<DHV, 8>(q, k, v, B, N, Nk, kv_len, H, out, lse, st);                                          \
-      case 9: return launch_attn_tc2<DHV, 9>(q, k, v, B, N, Nk, kv_len, H, out, lse, st);                                          \
-      default: return launch_attn_tc2<DHV, 4>(q, k, v, B, N, Nk, kv_len, H, out, lse, st);                                         \
+      case 0: return launch_attn_tc2<DHV, 0>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                                          \
+      case 1: return launch_attn_tc2<DHV, 1>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                                          \
+      case 2: return launch_attn_tc2<DHV, 2>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                                          \
+      case 8: return launch_attn_tc2<DHV, 8>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                                          \
+      case 9: return launch_attn_tc2<DHV, 9>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                                          \
+      default: return launch_attn_tc2<DHV, 4>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                                         \
     }
   switch (Dh) {
     LCASR_FA(32) LCASR_FA(64) LCASR_FA(128)

@@ -241,7 +241,9 @@ extern "C" int lcasr_model_forward_lengths(lcasr_model* m, const float* spec, in
     LCASR_TRY(gemm(a, L.qkv_w, M, 3 * d, d, nullptr, LCASR_ACT_NONE, nullptr, 0.f, wide, cd));
     OP(CAT_ROPE, lcasr_rope_split(wide, cd, B, N, H, Dh, c.use_rotary ? cos_t : nullptr, c.use_rotary ? sin_t : nullptr, q, k,
                                v, vt, p.Npad, stream));
-    if (tok_len) OP(CAT_ATTN, lcasr_attention_masked(q, k, v, cd, B, N, N, tok_len, H, Dh, a, ai, stream));
+    if (c.attn_window_left >= 0 || c.attn_window_right >= 0)
+      OP(CAT_ATTN, lcasr_attention_window(q, k, v, cd, B, N, tok_len, H, Dh, c.attn_window_left, c.attn_window_right, a, ai, stream));
+    else if (tok_len) OP(CAT_ATTN, lcasr_attention_masked(q, k, v, cd, B, N, N, tok_len, H, Dh, a, ai, stream));
     else OP(CAT_ATTN, lcasr_attention(q, k, v, cd, B, N, H, Dh, vt, p.Npad, a, ai, stream));
     LCASR_TRY(gemm(a, L.out_w, M, d, d, nullptr, LCASR_ACT_NONE, x, 1.0f, x, LCASR_F32));
     // convolution module (convolution.py:103-124)

@@ -110,9 +110,11 @@ class Attention(_ParamOnly):
 
     def __init__(self, n_feats, head_dim, n_heads, **kwargs):
         super().__init__()
-        for key in ("attention_window_size", "attention_window_size_left", "attention_window_size_right"):
-            if kwargs.get(key, -1) not in (-1, None):
-                raise NotImplementedError(f"{key}: windowed attention is a 'next' row (SURVEY §8 f4)")
+        # local attention (attention.py:321-328,466): query i sees keys [i - left, i + right]; -1 = unlimited
+        def _win(direction):
+            v = kwargs.get(f"attention_window_size_{direction}", None)
+            return int(v) if v is not None else int(kwargs.get("attention_window_size", -1))
+        self.left_window, self.right_window = _win("left"), _win("right")
         if kwargs.get("causal", False) or kwargs.get("qkv_bias", False) or kwargs.get("bias", False):
             raise NotImplementedError("causal / biased attention is not used by any released config")
         self.layer_idx = kwargs.get("layer_idx", None)
@@ -387,7 +389,8 @@ class SCConformerXL(nn.Module):
             legasee_double_norm=int(self.legasee_double_norm), bias_in_ff=int(self.bias_in_ff),
             compute_dtype=L.dtype_code(cdt),
             rotary_interp=float(sd["rotary_pos_emb.rotary_interpolation_factor"]) if self.use_rotary else 1.0,
-            norm_eps=1e-8 if rms else 1e-5)
+            norm_eps=1e-8 if rms else 1e-5,
+            attn_window_left=self.layers[0].attend.fn.left_window, attn_window_right=self.layers[0].attend.fn.right_window)
         handle = L.vp()
         L.call("lcasr_model_create", C.byref(cfg), C.byref(w), C.byref(handle))
         self._handle = handle.value
@@ -428,6 +431,8 @@ class SCConformerXL(nn.Module):
             raise NotImplementedError("the training path computes in bf16 (the reference trains under bf16 autocast)")
         if return_logits:
             raise NotImplementedError("return_logits=True is an inference option (decoder.py:26-27)")
+        if self.layers[0].attend.fn.left_window >= 0 or self.layers[0].attend.fn.right_window >= 0:
+            raise NotImplementedError("windowed attention is an evaluation mode (eval/run.py:38-43); training uses full attention")
         B, _, T = audio_signal.shape
         if length is not None:
             lens = [int(v) for v in (length.tolist() if torch.is_tensor(length) else length)]

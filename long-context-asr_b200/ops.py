@@ -123,6 +123,16 @@ def attention(q, k, v, v_transposed=False, impl=L.ATTN_AUTO):
     return out
 
 
+def attention_window(q, k, v, left: int, right: int, kv_len=None, impl=L.ATTN_AUTO):
+    """local self-attention: query i attends to keys [i - left, i + right] (-1 = unlimited)"""
+    _cuda(q, k, v, kv_len)
+    B, N, H, Dh = q.shape
+    out = torch.empty(B, N, H * Dh, dtype=q.dtype, device=q.device)
+    L.call("lcasr_attention_window", L.ptr(q), L.ptr(k), L.ptr(v), L.dtype_code(q.dtype), B, N, L.ptr(kv_len), H, Dh, int(left),
+           int(right), L.ptr(out), impl, _s())
+    return out
+
+
 def attention_cross(q, k, v, impl=L.ATTN_AUTO):
     """q [B,Nq,H,Dh] against k,v [B,Nk,H,Dh] (sequence-parallel attention: local queries, gathered K/V)."""
     _cuda(q, k, v)

@@ -249,7 +249,19 @@ def attention_forward(sd, cfg: dict, p: str, a: Tensor, cos, sin, collect=None, 
     B, N, _ = a.shape
     H, Dh = cfg["n_heads"], cfg["head_dim"]
     attn_mask = None
+    wl, wr = cfg.get("attention_window_size_left", None), cfg.get("attention_window_size_right", None)
+    wl = cfg.get("attention_window_size", -1) if wl is None else wl  # attention.py:321-328
+    wr = cfg.get("attention_window_size", -1) if wr is None else wr
+    if wl >= 0 or wr >= 0:  # flash-attn window_size=(wl, wr): key j visible to query i iff i - wl <= j <= i + wr
+        i, j = torch.arange(N)[:, None], torch.arange(N)[None, :]
+        band = torch.ones(N, N, dtype=torch.bool)
+        if wl >= 0:
+            band &= j >= i - wl
+        if wr >= 0:
+            band &= j <= i + wr
+        attn_mask = torch.zeros(N, N, dtype=a.dtype).masked_fill(~band, float("-inf"))[None, None]
     if pad_mask is not None:
+        assert attn_mask is None, "oracle: window + padding not combined"
         a = a.masked_fill(pad_mask.unsqueeze(-1), 0)
         valid = ~pad_mask
         attn_mask = ~(valid[:, None, :, None] * valid[:, None, None, :])

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, f"declared in the header but not exported: {missing}"
     assert set(lcasr_b200._lib.EXPORTED_SYMBOLS) <= declared
-    assert lib.lcasr_abi_version() == 1
+    assert lib.lcasr_abi_version() == 2
 
 
 def test_out_length_host_function():
@@ -58,7 +58,11 @@ def test_constructor_accepts_reference_kwargs_and_rejects_off_path_ones():
     with pytest.raises(NotImplementedError):
         lcasr_b200.SCConformerXL(subsampling="stacking")
     with pytest.raises(NotImplementedError):
-        lcasr_b200.SCConformerXL(attention_window_size=128)
+        lcasr_b200.SCConformerXL(causal=True)
+    # local attention is accepted (eval/run.py:42 sets config.model.attention_window_size), per-direction keys win
+    w = lcasr_b200.SCConformerXL(n_layers=1, d_model=64, n_heads=2, head_dim=32, subsampling_conv_channels=32,
+                                 attention_window_size=128, attention_window_size_right=16)
+    assert (w.layers[0].attend.fn.left_window, w.layers[0].attend.fn.right_window) == (128, 16)
 
 
 def test_no_cpu_fallback():
