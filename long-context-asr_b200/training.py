@@ -331,6 +331,8 @@ class TrainEngine:
                     da = linear_bwd(dqkv, r["a"], q + "qkv_w")
                     ln_bwd(r["x"], da, q + "attn_norm", dx, accumulate=True)
             S["layers"][l] = None  # release this layer's activations
+            if self.dp_group is not None:  # this layer's parameter gradients are final: reduce them behind the rest of the backward
+                handles.append(self._reduce_slice(flat, q))
 
         # subsampling
         dy = T.scale_cast(dx, 1.0)
@@ -344,9 +346,25 @@ class TrainEngine:
         ds1 = T.subsample_dwconv_bwd_data(dd1, P["dw1_w"], S["s1"].shape[1], S["s1"].shape[2])
         T.subsample_conv0_bwd_(S["spec"], P["conv0_w"], P["conv0_b"], ds1, G["conv0_w"], G["conv0_b"])
 
-        self.reduce_gradients(flat)
+        if self.dp_group is not None:
+            handles.append(self._reduce_slice(flat, None))  # subsampling + decoder (accumulated across all layers)
+            for h in handles:
+                h.wait()
+            if self.dp_average:
+                import torch.distributed as dist
+                flat.mul_(1.0 / dist.get_world_size(self.dp_group))
         self.last_flat_grad = flat
         return self.to_param_grads(G)
+
+    def _reduce_slice(self, flat: torch.Tensor, layer_prefix):
+        """asynchronous all-reduce (sum) of the contiguous slice of the flat gradient buffer that belongs to one layer
+        (`layers.<l>.`) or, with None, to everything outside the layer stack.  NCCL orders it after the kernels already
+        enqueued on the current stream and runs it on its own stream, overlapping the remaining backward."""
+        import torch.distributed as dist
+        keys = [k for k in self._layout if (k.startswith(layer_prefix) if layer_prefix else not k.startswith("layers."))]
+        lo = min(self._layout[k][0] for k in keys)
+        hi = max(self._layout[k][0] + _al4(self._layout[k][1]) for k in keys)
+        return dist.all_reduce(flat[lo:hi], group=self.dp_group, async_op=True)
 
     def reduce_gradients(self, flat: torch.Tensor) -> None:
         """data-parallel training: ONE all-reduce over the flat packed gradient buffer (NCCL over NVLink on the GPU
