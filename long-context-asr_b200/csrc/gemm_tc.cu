@@ -24,8 +24,11 @@ constexpr int TG_BM = 128, TG_BK = 64;
 // the bound of the bf16-output GEMMs was the global store pattern, see tg_stage_chunk64)
 // (CTA pairs + bf16 outputs: eight, two per quarter taking half of the columns each — with the stores gone to TMA the
 // remaining epilogue cost is the per-warp chain TMEM load -> convert -> stage, which two warps per quarter overlap)
-template <typename TOut, int CG> struct TgWarps {
-  static constexpr int EPI = (sizeof(TOut) == 2 && CG == 2) ? 8 : 4, THREADS = 64 + 32 * EPI;
+// fp32 outputs with a residual are bound by the memory-level parallelism of the residual loads (4 KB in flight per
+// warp): CTA pairs (5-stage ring, room for 8 transpose tiles) run eight epilogue warps there as well.
+// (W8: chosen for short-K fp32 GEMMs, whose tile time IS the epilogue; long-K ones measured 4 % faster with four)
+template <typename TOut, int CG, bool W8 = true> struct TgWarps {
+  static constexpr int EPI = (CG == 2 && (sizeof(TOut) == 2 || W8)) ? 8 : 4, THREADS = 64 + 32 * EPI;
 };
 
 // CG = CTAs per MMA (tcgen05 cta_group): 1, or 2 = a CTA pair computes a 256 x BN tile, each CTA staging its 128 rows
@@ -221,8 +224,8 @@ __device__ __forceinline__ void tg_stage_chunk64(const uint32_t (&r0)[32], const
   }
 }
 
-template <int BN, typename TOut, int CG>
-__global__ void __launch_bounds__(TgWarps<TOut, CG>::THREADS, 1)
+template <int BN, typename TOut, int CG, bool W8>
+__global__ void __launch_bounds__(TgWarps<TOut, CG, W8>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, int64_t M, int N, int K,
                TgEpilogue ep, TOut* out) {
@@ -234,8 +237,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * Cfg::STAGES + 4];
   __shared__ uint32_t tmem_slot;
-  constexpr int NEW = TgWarps<TOut, CG>::EPI;
-  __shared__ __align__(16) float4 epi_stage[sizeof(TOut) == 4 ? 4 : 1][32 * 8];  // per epilogue warp: 32 rows x 32 fp32, swizzled
+  constexpr int NEW = TgWarps<TOut, CG, W8>::EPI;
+  __shared__ __align__(16) float4 epi_stage[sizeof(TOut) == 4 ? NEW : 1][32 * 8];  // per epilogue warp: 32 rows x 32 fp32, swizzled
   __shared__ __align__(16) float bias_s[2][BN];          // the tile's bias slice, staged while the main loop still runs
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle atoms need 1024B alignment
   const uint32_t bar_base = smem_u32(bars);
@@ -378,7 +381,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (ep.resid && c + 1 < (half + 1) * CPW && n_idx + (c + 1) * 32 < N)
             tg_load_resid(res_nxt, lane, row0, n_idx + (c + 1) * 32, M, N, ep.resid);  // in flight during this chunk
           tmem_wait_ld();
-          tg_store_chunk<TOut>(r, res_cur, epi_stage[warp & 3], lane, row0, n_idx + c * 32, M, N, ep, &bias_s[acc][c * 32], out);
+          tg_store_chunk<TOut>(r, res_cur, epi_stage[sizeof(TOut) == 4 ? warp - 2 : 0], lane, row0, n_idx + c * 32, M, N, ep, &bias_s[acc][c * 32], out);
         }
       }
       tc_fence_before();
@@ -454,7 +457,7 @@ int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t d0, uint64_t 
   return 0;
 }
 
-template <int BN, typename TOut, int CG>
+template <int BN, typename TOut, int CG, bool W8 = true>
 static int launch_tc(const void* A, const void* W, int64_t M, int N, int K, const TgEpilogue& ep, void* out,
                      cudaStream_t st) {
   using Cfg = TgCfg<BN, CG>;
@@ -469,7 +472,7 @@ static int launch_tc(const void* A, const void* W, int64_t M, int N, int K, cons
   }
   static bool attr_set = false;
   if (!attr_set) {
-    LCASR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TOut, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::template smem_bytes<TOut>()));
+    LCASR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TOut, CG, W8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::template smem_bytes<TOut>()));
     attr_set = true;
   }
   const int64_t tiles = ceil_div(M, CG * TG_BM) * ceil_div(N, BN);
@@ -477,7 +480,7 @@ static int launch_tc(const void* A, const void* W, int64_t M, int N, int K, cons
   const int grid = (int)(tiles < units ? tiles : units) * CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(TgWarps<TOut, CG>::THREADS);
+  cfg.blockDim = dim3(TgWarps<TOut, CG, W8>::THREADS);
   cfg.dynamicSmemBytes = Cfg::template smem_bytes<TOut>();
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -485,7 +488,7 @@ static int launch_tc(const void* A, const void* W, int64_t M, int N, int K, cons
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CG == 2 ? 1 : 0;
-  LCASR_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, TOut, CG>, tmA, tmB, tmC, tmC2, M, N, K, ep, (TOut*)out));
+  LCASR_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, TOut, CG, W8>, tmA, tmB, tmC, tmC2, M, N, K, ep, (TOut*)out));
   LCASR_LAUNCH_CHECK();
   return 0;
 }
@@ -496,7 +499,9 @@ static int launch_tc_cg(const void* A, const void* W, int64_t M, int N, int K, c
   // CTA pairs (256-row tiles) once there is enough work to fill the 74 pairs; LCASR_GEMM_CG=1|2 forces a choice (A/B runs)
   static const int force = getenv("LCASR_GEMM_CG") ? atoi(getenv("LCASR_GEMM_CG")) : 0;
   const bool pair = force ? force == 2 : (ceil_div(M, 2 * TG_BM) * ceil_div(N, BN) >= kNumSMs / 2);
-  return pair ? launch_tc<BN, TOut, 2>(A, W, M, N, K, ep, out, st) : launch_tc<BN, TOut, 1>(A, W, M, N, K, ep, out, st);
+  if (!pair) return launch_tc<BN, TOut, 1>(A, W, M, N, K, ep, out, st);
+  if (sizeof(TOut) == 4 && K > 1536) return launch_tc<BN, TOut, 2, false>(A, W, M, N, K, ep, out, st);
+  return launch_tc<BN, TOut, 2, true>(A, W, M, N, K, ep, out, st);
 }
 
 int gemm_tc_launch(const void* A, const void* W, int64_t M, int N, int K, const float* bias, int act, const float* resid,
