@@ -171,6 +171,15 @@ int lcasr_ctc_loss_bwd(const float* log_probs, int B, int64_t N, int V, const in
                        int blank, const float* nll, const float* grad_nll, const float* alpha_ws,
                        float* beta_ws, float* grad, void* stream);
 
+/* Front-end (lcasr/utils/audio_tools.py:44-57 to_spectogram): waveform [B, n_samples] fp32 (16 kHz) -> mel power
+ * spectrogram out [B, n_mels, n_frames], n_frames = lcasr_melspec_frames(n_samples) = 1 + n_samples/160
+ * (torchaudio MelSpectrogram: n_fft 512, Hann(400) centred in the frame, hop 160, center + reflect padding, power 2),
+ * optionally standardised per (recording, mel bin) over time with the unbiased std.  cos_tab / sin_tab [512, 257]: the
+ * DFT twiddles multiplied by the window; fb [257, n_mels]: the mel filterbank; sums: fp64 scratch [B, n_mels, 2]. */
+int64_t lcasr_melspec_frames(int64_t n_samples);
+int lcasr_melspec(const float* wave, int B, int64_t n_samples, const float* cos_tab, const float* sin_tab,
+                  const float* fb, int n_mels, float* out, double* sums, int normalise, void* stream);
+
 /* Long-form moving-window merge (lcasr/eval/utils.py:45-111 fetch_logits): window k occupies rows
  * [win_row0[k], win_row0[k] + win_len[k]) of logp [*, V] (fp32 log-probs) and covers merged frames
  * [win_pos[k], win_pos[k] + win_len[k]); windows sorted by win_pos, max_len = max win_len.  For every merged frame:

@@ -94,6 +94,7 @@ _SIGNATURES = {
     "lcasr_grad_sumsq": [vp, vp, vp, i32, vp, vp],
     "lcasr_grad_scale": [vp, vp, vp, i32, vp, f32, vp],
     "lcasr_madgrad_step": [vp, vp, vp, i32, vp, f32, f32, f32, f32, f32, f32, i32, vp],
+    "lcasr_melspec": [vp, i32, i64, vp, vp, vp, i32, vp, vp, i32, vp],
     "lcasr_window_merge": [vp, i32, i32, vp, vp, vp, i32, i64, vp, vp, vp],
     "lcasr_ctc_loss_fwd_ab": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp, vp],
     "lcasr_ctc_loss_grad": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp],
@@ -138,6 +139,7 @@ _OTHER = {
     "lcasr_launch_count": ([], i64),
     "lcasr_reset_launch_count": ([], None),
     "lcasr_out_length": ([i64], i64),
+    "lcasr_melspec_frames": ([i64], i64),
     "lcasr_model_destroy": ([vp], None),
     "lcasr_model_workspace_bytes": ([vp, i32, i64], i64),
     "lcasr_model_transcribe_workspace_bytes": ([vp, i32, i64], i64),

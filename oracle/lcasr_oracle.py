@@ -593,3 +593,33 @@ def madgrad_step(p, g, state, k: int, lr: float, momentum: float = 0.9, weight_d
     if weight_decay != 0 and decouple_decay:
         p_new = p_new - f(lr * weight_decay) * p
     return p_new.astype(f)
+
+
+# --------------------------------------------------------------------------------------------
+# front-end (lcasr/utils/audio_tools.py:44-57 to_spectogram = torchaudio MelSpectrogram + per-bin standardisation)
+# --------------------------------------------------------------------------------------------
+
+def to_spectogram(waveform: np.ndarray, global_normalisation: bool = True, n_mels: int = 80) -> np.ndarray:
+    """numpy (fp64 internally) restatement: reflect-pad 256, frames of 512 every 160 samples, periodic Hann(400) centred in
+    the frame, |rfft|^2, HTK mel filterbank (no norm), then (x - mean_t) / std_t (unbiased) per bin.  [C, n] -> [C, 80, 1 + n//160]."""
+    n_fft, win_len, hop, sr = 512, 400, 160, 16000
+    w = np.asarray(waveform, dtype=np.float64)
+    if w.ndim == 1:
+        w = w[None]
+    win = np.zeros(n_fft)
+    left = (n_fft - win_len) // 2
+    win[left:left + win_len] = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(win_len) / win_len)
+    x = np.pad(w, ((0, 0), (n_fft // 2, n_fft // 2)), mode="reflect")
+    n_frames = 1 + w.shape[1] // hop
+    idx = np.arange(n_frames)[:, None] * hop + np.arange(n_fft)[None, :]
+    power = np.abs(np.fft.rfft(x[:, idx] * win, axis=-1)) ** 2                        # [C, frames, 257]
+    hz2mel = lambda f: 2595.0 * np.log10(1.0 + f / 700.0)
+    all_freqs = np.linspace(0, sr // 2, n_fft // 2 + 1)
+    f_pts = 700.0 * (10.0 ** (np.linspace(hz2mel(0.0), hz2mel(sr / 2.0), n_mels + 2) / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts[None, :] - all_freqs[:, None]
+    fb = np.maximum(0.0, np.minimum(-slopes[:, :-2] / f_diff[:-1], slopes[:, 2:] / f_diff[1:]))  # [257, n_mels]
+    spec = np.einsum("cfk,km->cmf", power, fb)
+    if global_normalisation:
+        spec = (spec - spec.mean(-1, keepdims=True)) / spec.std(-1, ddof=1, keepdims=True)
+    return spec.astype(np.float32)
