@@ -634,12 +634,19 @@ extern "C" int lcasr_gemm_ex(const lcasr_gemm_ex_args* gp, void* stream) {
   const bool wide = (g.N % 256 == 0) || g.N > 512;
   const int BN = wide ? 256 : 128;
   int ksplit = g.ksplit;
-  if (ksplit <= 0) {  // auto: fill the machine ~2x when the output has few tiles (weight gradients)
+  if (ksplit <= 0) {  // auto (fp32 accumulating outputs: weight gradients have K = all tokens and few output tiles)
     ksplit = 1;
     if (g.out_dtype == LCASR_F32) {
+      // pick the split whose tile count fills whole waves of the 148 persistent CTAs: efficiency = waves / ceil(waves);
+      // a larger split must be 5 % better than a smaller one (fewer atomic passes over the output).  e.g. 72 tiles:
+      // k = 4 -> 288 tiles = 1.95 waves (0.97) instead of k = 5 -> 2.43 waves -> 3 rounds (0.81).
       const int64_t tiles = ceil_div(g.M, TX_BM) * ceil_div(g.N, BN) * g.nb1 * g.nb2;
-      if (tiles < 2 * kNumSMs) ksplit = (int)ceil_div(2 * kNumSMs, tiles);
-      if (ksplit > num_k / 4) ksplit = num_k / 4 > 0 ? num_k / 4 : 1;  // >= 4 K blocks (256 deep) per split
+      double best = 0.0;
+      for (int k = 1; k <= 128 && k * 4 <= num_k; ++k) {
+        const double waves = (double)(tiles * k) / kNumSMs;
+        const double eff = waves / (double)ceil_div(tiles * k, kNumSMs);
+        if (eff > best * 1.05) { best = eff; ksplit = k; }
+      }
     }
   }
   if (ksplit > num_k) ksplit = num_k;
