@@ -266,6 +266,11 @@ int lcasr_colsum(const void* in, int dtype, int64_t M, int d, float scale, float
 int lcasr_layernorm_bwd(const float* x, const void* dy, int dy_dtype, const float* weight, int64_t M, int d,
                         float eps, int kind, int accumulate, float* dx, float* dweight, float* dbias,
                         void* stream);
+/* same, and cast_out (bf16 [M,d], may be NULL) = cast_scale * (the new dx): the dY operand of the next sub-layer's
+ * backward GEMMs, produced here instead of by a separate cast pass */
+int lcasr_layernorm_bwd_cast(const float* x, const void* dy, int dy_dtype, const float* weight, int64_t M, int d,
+                             float eps, int kind, int accumulate, float* dx, float* dweight, float* dbias,
+                             void* cast_out, float cast_scale, void* stream);
 /* depthwise Conv1d(k, pad (k-1)/2, groups=d)+bias, channels-last bf16 [B,N,d] (convolution.py:112), with
  * optional per-channel sum / sum-of-squares of the output (BatchRenorm batch statistics); its data gradient
  * and its weight / bias gradients (dw [d,k], db [d], +=). */

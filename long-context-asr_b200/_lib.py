@@ -113,6 +113,7 @@ _SIGNATURES = {
     "lcasr_log_softmax_bwd": [vp, vp, i64, i32, f32, vp, vp],
     "lcasr_colsum": [vp, i32, i64, i32, f32, vp, vp],
     "lcasr_layernorm_bwd": [vp, vp, i32, vp, i64, i32, f32, i32, i32, vp, vp, vp, vp],
+    "lcasr_layernorm_bwd_cast": [vp, vp, i32, vp, i64, i32, f32, i32, i32, vp, vp, vp, vp, f32, vp],
     "lcasr_dwconv1d_fwd": [vp, i32, i64, i32, i32, vp, vp, vp, vp, vp, vp],
     "lcasr_dwconv1d_bwd_data": [vp, i32, i64, i32, i32, vp, vp, vp],
     "lcasr_dwconv1d_bwd_weight": [vp, vp, i32, i64, i32, i32, vp, vp, vp],

@@ -43,6 +43,7 @@ struct TxParams {
   int ksplit, kper;             // K blocks per split
   int64_t ldo, so1, so2;        // output row pitch / batch strides (elements)
   const bf16* aux;              // bf16, indexed like the output (own pitch / strides)
+  int aux32;                    // aux rows are 32-byte aligned (pointer, pitch, strides): 256-bit loads allowed
   int64_t ldx, sx1, sx2;
   const float* rowvec;          // fp32 per output row: rowvec[b2*sr2 + b1*sr1 + row]
   int64_t sr1, sr2;
@@ -92,6 +93,15 @@ __device__ __forceinline__ float silu_grad(float x) {
 __device__ __forceinline__ void tx_load_aux(uint4 (&ax)[4], int64_t row, int col0, const TxParams& p, int b1, int b2) {
   if (row >= p.M) return;
   const bf16* xp = p.aux + b2 * p.sx2 + b1 * p.sx1 + row * p.ldx + col0;
+  if (p.aux32 && col0 + 32 <= p.Nst) {  // 32-byte aligned rows: two 256-bit loads (LDG.256) instead of four 128-bit ones
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(ax[0].x), "=r"(ax[0].y), "=r"(ax[0].z), "=r"(ax[0].w), "=r"(ax[1].x), "=r"(ax[1].y), "=r"(ax[1].z), "=r"(ax[1].w)
+                 : "l"(xp));
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(ax[2].x), "=r"(ax[2].y), "=r"(ax[2].z), "=r"(ax[2].w), "=r"(ax[3].x), "=r"(ax[3].y), "=r"(ax[3].z), "=r"(ax[3].w)
+                 : "l"(xp + 16));
+    return;
+  }
 #pragma unroll
   for (int g = 0; g < 4; ++g)
     if (col0 + 8 * g < p.Nst) ax[g] = *reinterpret_cast<const uint4*>(xp + 8 * g);
@@ -656,6 +666,7 @@ extern "C" int lcasr_gemm_ex(const lcasr_gemm_ex_args* gp, void* stream) {
   p.M = g.M; p.N = g.N; p.Nst = Nst; p.K = g.K; p.nb1 = g.nb1; p.nb2 = g.nb2; p.ksplit = ksplit; p.kper = kper;
   p.ldo = g.ldo; p.so1 = g.so1; p.so2 = g.so2;
   p.aux = (const bf16*)g.aux; p.ldx = g.ldaux; p.sx1 = g.sx1; p.sx2 = g.sx2;
+  p.aux32 = g.aux && ((uintptr_t)g.aux & 31) == 0 && g.ldaux % 16 == 0 && g.sx1 % 16 == 0 && g.sx2 % 16 == 0;
   p.rowvec = g.rowvec; p.sr1 = g.sr1; p.sr2 = g.sr2;
   p.alpha = g.alpha; p.epi = g.epi;
   cudaStream_t st = (cudaStream_t)stream;

@@ -227,7 +227,17 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, i
   const int64_t r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (cg * 8 < d) {
-    for (int64_t r = r0 + ry; r < r1; r += 8) {
+    int64_t r = r0 + ry;
+    for (; r + 24 < r1; r += 32) {  // four independent 16-byte loads in flight per thread
+      float v0[8], v1[8], v2[8], v3[8];
+      Vec8<T>::load(in + r * d + cg * 8, v0);
+      Vec8<T>::load(in + (r + 8) * d + cg * 8, v1);
+      Vec8<T>::load(in + (r + 16) * d + cg * 8, v2);
+      Vec8<T>::load(in + (r + 24) * d + cg * 8, v3);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += (v0[i] + v1[i]) + (v2[i] + v3[i]);
+    }
+    for (; r < r1; r += 8) {
       float v[8];
       Vec8<T>::load(in + r * d + cg * 8, v);
 #pragma unroll
@@ -255,7 +265,8 @@ template <typename TDy>
 __global__ void __launch_bounds__(256) norm_bwd_kernel(const float* __restrict__ x, const TDy* __restrict__ dy,
                                                        const float* __restrict__ w, int64_t M, int d, float eps, int kind,
                                                        int accumulate, float* __restrict__ dx, float* __restrict__ dw,
-                                                       float* __restrict__ db) {
+                                                       float* __restrict__ db, bf16* __restrict__ cast_out, float cast_scale) {
+  // cast_out (may be NULL): bf16 copy of cast_scale * (the new dx) — the dY operand of the NEXT sub-layer's backward GEMMs
   extern __shared__ float sacc[];  // [2][d]
   float* sdw = sacc;
   float* sdb = sacc + d;
@@ -285,8 +296,10 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const float* __restrict__
       for (int i = lane; i < d; i += 32) {
         const float gy = to_f32<TDy>(gr[i]);
         const float xh = (xr[i] - mean) * rstd;
-        const float v = rstd * (gy * w[i] - s1 - xh * s2);
-        dxr[i] = accumulate ? dxr[i] + v : v;
+        float v = rstd * (gy * w[i] - s1 - xh * s2);
+        if (accumulate) v += dxr[i];
+        dxr[i] = v;
+        if (cast_out) cast_out[row * d + i] = __float2bfloat16_rn(cast_scale * v);
         atomicAdd(sdw + i, gy * xh);
         atomicAdd(sdb + i, gy);
       }
@@ -301,8 +314,10 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const float* __restrict__
       const float k = rms > 0.f ? s2 * inv * inv / ((float)d * rms) : 0.f;
       for (int i = lane; i < d; i += 32) {
         const float gy = to_f32<TDy>(gr[i]);
-        const float v = gy * w[i] * inv - k * xr[i];
-        dxr[i] = accumulate ? dxr[i] + v : v;
+        float v = gy * w[i] * inv - k * xr[i];
+        if (accumulate) v += dxr[i];
+        dxr[i] = v;
+        if (cast_out) cast_out[row * d + i] = __float2bfloat16_rn(cast_scale * v);
         atomicAdd(sdw + i, gy * xr[i] * inv);
       }
     }
@@ -320,37 +335,39 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const float* __restrict__
 // time in 2*d shared-memory atomics per row).  HBM-bound: reads x (4 B) + dy (e) and reads+writes dx (8 B)
 // per element.
 template <int NE, typename TDy>
-__global__ void __launch_bounds__(256) norm_bwd_reg_kernel(const float* __restrict__ x, const TDy* __restrict__ dy,
+__global__ void __launch_bounds__(256, 2) norm_bwd_reg_kernel(const float* __restrict__ x, const TDy* __restrict__ dy,
                                                            const float* __restrict__ w, int64_t M, float eps, int kind,
                                                            int accumulate, float* __restrict__ dx, float* __restrict__ dw,
-                                                           float* __restrict__ db) {
+                                                           float* __restrict__ db, bf16* __restrict__ cast_out, float cast_scale) {
   constexpr int d = NE * 32, NV = NE / 4;
   extern __shared__ float sacc[];  // [2][d]
   for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  float4 wv[NV], aw[NV], ab[NV];
+  // (the weight vector is re-read from L1 where needed instead of living in registers: 2 CTAs per SM need <= 128)
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  float4 aw[NV], ab[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    wv[j] = reinterpret_cast<const float4*>(w)[lane + 32 * j];
     aw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += (int64_t)gridDim.x * wpb) {
-    float4 xv[NV], gv[NV];
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      xv[j] = reinterpret_cast<const float4*>(x + row * d)[lane + 32 * j];
+    // dy is read twice (reduction pass, output pass): the second read hits L1 / L2 and saves NV float4 registers
+    auto load_g = [&](int j) -> float4 {
       if constexpr (sizeof(TDy) == 4) {
-        gv[j] = reinterpret_cast<const float4*>(dy + row * d)[lane + 32 * j];
+        return reinterpret_cast<const float4*>(dy + row * d)[lane + 32 * j];
       } else {
         const uint2 u = reinterpret_cast<const uint2*>(dy + row * d)[lane + 32 * j];
         const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
         const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-        gv[j] = make_float4(f0.x, f0.y, f1.x, f1.y);
+        return make_float4(f0.x, f0.y, f1.x, f1.y);
       }
-    }
+    };
+    float4 xv[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) xv[j] = reinterpret_cast<const float4*>(x + row * d)[lane + 32 * j];
     float4* dxr = reinterpret_cast<float4*>(dx + row * d);
     if (kind == LCASR_NORM_LAYERNORM) {
       float s = 0.f;
@@ -368,7 +385,9 @@ __global__ void __launch_bounds__(256) norm_bwd_reg_kernel(const float* __restri
 #pragma unroll
       for (int j = 0; j < NV; ++j) {  // xv becomes xhat
         xv[j].x *= rstd; xv[j].y *= rstd; xv[j].z *= rstd; xv[j].w *= rstd;
-        const float g0 = gv[j].x * wv[j].x, g1 = gv[j].y * wv[j].y, g2 = gv[j].z * wv[j].z, g3 = gv[j].w * wv[j].w;
+        const float4 wj = __ldg(w4 + lane + 32 * j);
+        const float4 gj = load_g(j);
+        const float g0 = gj.x * wj.x, g1 = gj.y * wj.y, g2 = gj.z * wj.z, g3 = gj.w * wj.w;
         s1 += (g0 + g1) + (g2 + g3);
         s2 += (g0 * xv[j].x + g1 * xv[j].y) + (g2 * xv[j].z + g3 * xv[j].w);
       }
@@ -376,19 +395,27 @@ __global__ void __launch_bounds__(256) norm_bwd_reg_kernel(const float* __restri
       s2 = warp_sum(s2) * (1.0f / d);
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
+        const float4 wj = __ldg(w4 + lane + 32 * j);
+        const float4 gj = load_g(j);
         float4 v;
-        v.x = rstd * (gv[j].x * wv[j].x - s1 - xv[j].x * s2);
-        v.y = rstd * (gv[j].y * wv[j].y - s1 - xv[j].y * s2);
-        v.z = rstd * (gv[j].z * wv[j].z - s1 - xv[j].z * s2);
-        v.w = rstd * (gv[j].w * wv[j].w - s1 - xv[j].w * s2);
+        v.x = rstd * (gj.x * wj.x - s1 - xv[j].x * s2);
+        v.y = rstd * (gj.y * wj.y - s1 - xv[j].y * s2);
+        v.z = rstd * (gj.z * wj.z - s1 - xv[j].z * s2);
+        v.w = rstd * (gj.w * wj.w - s1 - xv[j].w * s2);
         if (accumulate) {
           const float4 o = dxr[lane + 32 * j];
           v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
         }
         dxr[lane + 32 * j] = v;
-        aw[j].x = fmaf(gv[j].x, xv[j].x, aw[j].x); aw[j].y = fmaf(gv[j].y, xv[j].y, aw[j].y);
-        aw[j].z = fmaf(gv[j].z, xv[j].z, aw[j].z); aw[j].w = fmaf(gv[j].w, xv[j].w, aw[j].w);
-        ab[j].x += gv[j].x; ab[j].y += gv[j].y; ab[j].z += gv[j].z; ab[j].w += gv[j].w;
+        if (cast_out) {
+          __nv_bfloat162 c0 = __floats2bfloat162_rn(cast_scale * v.x, cast_scale * v.y), c1 = __floats2bfloat162_rn(cast_scale * v.z, cast_scale * v.w);
+          uint2 u;
+          u.x = *reinterpret_cast<uint32_t*>(&c0); u.y = *reinterpret_cast<uint32_t*>(&c1);
+          reinterpret_cast<uint2*>(cast_out + row * d)[lane + 32 * j] = u;
+        }
+        aw[j].x = fmaf(gj.x, xv[j].x, aw[j].x); aw[j].y = fmaf(gj.y, xv[j].y, aw[j].y);
+        aw[j].z = fmaf(gj.z, xv[j].z, aw[j].z); aw[j].w = fmaf(gj.w, xv[j].w, aw[j].w);
+        ab[j].x += gj.x; ab[j].y += gj.y; ab[j].z += gj.z; ab[j].w += gj.w;
       }
     } else {
       float q = 0.f;
@@ -398,24 +425,35 @@ __global__ void __launch_bounds__(256) norm_bwd_reg_kernel(const float* __restri
       const float inv = 1.0f / (rms + eps);
       float s2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < NV; ++j)
-        s2 += (gv[j].x * wv[j].x * xv[j].x + gv[j].y * wv[j].y * xv[j].y) + (gv[j].z * wv[j].z * xv[j].z + gv[j].w * wv[j].w * xv[j].w);
+      for (int j = 0; j < NV; ++j) {
+        const float4 wj = __ldg(w4 + lane + 32 * j);
+        const float4 gj = load_g(j);
+        s2 += (gj.x * wj.x * xv[j].x + gj.y * wj.y * xv[j].y) + (gj.z * wj.z * xv[j].z + gj.w * wj.w * xv[j].w);
+      }
       s2 = warp_sum(s2);
       const float k = rms > 0.f ? s2 * inv * inv / ((float)d * rms) : 0.f;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
+        const float4 wj = __ldg(w4 + lane + 32 * j);
+        const float4 gj = load_g(j);
         float4 v;
-        v.x = gv[j].x * wv[j].x * inv - k * xv[j].x;
-        v.y = gv[j].y * wv[j].y * inv - k * xv[j].y;
-        v.z = gv[j].z * wv[j].z * inv - k * xv[j].z;
-        v.w = gv[j].w * wv[j].w * inv - k * xv[j].w;
+        v.x = gj.x * wj.x * inv - k * xv[j].x;
+        v.y = gj.y * wj.y * inv - k * xv[j].y;
+        v.z = gj.z * wj.z * inv - k * xv[j].z;
+        v.w = gj.w * wj.w * inv - k * xv[j].w;
         if (accumulate) {
           const float4 o = dxr[lane + 32 * j];
           v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
         }
         dxr[lane + 32 * j] = v;
-        aw[j].x = fmaf(gv[j].x, xv[j].x * inv, aw[j].x); aw[j].y = fmaf(gv[j].y, xv[j].y * inv, aw[j].y);
-        aw[j].z = fmaf(gv[j].z, xv[j].z * inv, aw[j].z); aw[j].w = fmaf(gv[j].w, xv[j].w * inv, aw[j].w);
+        if (cast_out) {
+          __nv_bfloat162 c0 = __floats2bfloat162_rn(cast_scale * v.x, cast_scale * v.y), c1 = __floats2bfloat162_rn(cast_scale * v.z, cast_scale * v.w);
+          uint2 u;
+          u.x = *reinterpret_cast<uint32_t*>(&c0); u.y = *reinterpret_cast<uint32_t*>(&c1);
+          reinterpret_cast<uint2*>(cast_out + row * d)[lane + 32 * j] = u;
+        }
+        aw[j].x = fmaf(gj.x, xv[j].x * inv, aw[j].x); aw[j].y = fmaf(gj.y, xv[j].y * inv, aw[j].y);
+        aw[j].z = fmaf(gj.z, xv[j].z * inv, aw[j].z); aw[j].w = fmaf(gj.w, xv[j].w * inv, aw[j].w);
       }
     }
   }
@@ -752,7 +790,7 @@ extern "C" int lcasr_log_softmax_bwd(const float* lp, const float* dlp, int64_t 
 
 extern "C" int lcasr_colsum(const void* in, int dtype, int64_t M, int d, float scale, float* out, void* stream) {
   LCASR_CHECK_ARG(in && out && M > 0 && d > 0 && d % 8 == 0, "colsum: bad arguments (d %% 8 == 0)");
-  const int rows_per_cta = 128;
+  const int rows_per_cta = 256;
   dim3 grid((unsigned)ceil_div(d / 8, 32), (unsigned)ceil_div(M, rows_per_cta));
   LCASR_CHECK_ARG(grid.y <= 65535, "colsum: too many rows");
   if (dtype == LCASR_BF16) colsum_kernel<bf16><<<grid, 256, 0, ST>>>((const bf16*)in, M, d, rows_per_cta, scale, out);
@@ -761,9 +799,20 @@ extern "C" int lcasr_colsum(const void* in, int dtype, int64_t M, int d, float s
   return 0;
 }
 
+extern "C" int lcasr_layernorm_bwd_cast(const float* x, const void* dy, int dy_dtype, const float* weight, int64_t M, int d,
+                                        float eps, int kind, int accumulate, float* dx, float* dweight, float* dbias,
+                                        void* cast_out_, float cast_scale, void* stream);
+
 extern "C" int lcasr_layernorm_bwd(const float* x, const void* dy, int dy_dtype, const float* weight, int64_t M, int d,
                                    float eps, int kind, int accumulate, float* dx, float* dweight, float* dbias,
                                    void* stream) {
+  return lcasr_layernorm_bwd_cast(x, dy, dy_dtype, weight, M, d, eps, kind, accumulate, dx, dweight, dbias, nullptr, 1.0f, stream);
+}
+
+extern "C" int lcasr_layernorm_bwd_cast(const float* x, const void* dy, int dy_dtype, const float* weight, int64_t M, int d,
+                                        float eps, int kind, int accumulate, float* dx, float* dweight, float* dbias,
+                                        void* cast_out_, float cast_scale, void* stream) {
+  bf16* cast_out = (bf16*)cast_out_;
   LCASR_CHECK_ARG(x && dy && weight && dx && dweight && M > 0 && d > 0, "layernorm_bwd: bad arguments");
   LCASR_CHECK_ARG(kind == LCASR_NORM_LAYERNORM || kind == LCASR_NORM_RMSNORM, "layernorm_bwd: bad kind %d", kind);
   LCASR_CHECK_ARG(kind == LCASR_NORM_RMSNORM || dbias, "layernorm_bwd: LayerNorm needs dbias");
@@ -771,13 +820,13 @@ extern "C" int lcasr_layernorm_bwd(const float* x, const void* dy, int dy_dtype,
   LCASR_CHECK_ARG(smem <= 48 * 1024, "layernorm_bwd: d=%d too wide", d);
   const int64_t want = ceil_div(M, 8);
   const unsigned grid = (unsigned)(want < 2 * kNumSMs ? want : 2 * kNumSMs);
-  const bool al16 = (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)weight) & 15) == 0;
+  const bool al16 = (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)weight | (uintptr_t)cast_out) & 15) == 0;
 #define LCASR_NB_CASE(NE)                                                                                                  \
   case NE * 32:                                                                                                            \
     if (dy_dtype == LCASR_BF16)                                                                                            \
-      norm_bwd_reg_kernel<NE, bf16><<<grid, 256, smem, ST>>>(x, (const bf16*)dy, weight, M, eps, kind, accumulate, dx, dweight, dbias); \
+      norm_bwd_reg_kernel<NE, bf16><<<grid, 256, smem, ST>>>(x, (const bf16*)dy, weight, M, eps, kind, accumulate, dx, dweight, dbias, cast_out, cast_scale); \
     else                                                                                                                   \
-      norm_bwd_reg_kernel<NE, float><<<grid, 256, smem, ST>>>(x, (const float*)dy, weight, M, eps, kind, accumulate, dx, dweight, dbias); \
+      norm_bwd_reg_kernel<NE, float><<<grid, 256, smem, ST>>>(x, (const float*)dy, weight, M, eps, kind, accumulate, dx, dweight, dbias, cast_out, cast_scale); \
     LCASR_LAUNCH_CHECK();                                                                                                  \
     return 0;
   if (al16) {
@@ -788,9 +837,9 @@ extern "C" int lcasr_layernorm_bwd(const float* x, const void* dy, int dy_dtype,
   }
 #undef LCASR_NB_CASE
   if (dy_dtype == LCASR_BF16)
-    norm_bwd_kernel<bf16><<<grid, 256, smem, ST>>>(x, (const bf16*)dy, weight, M, d, eps, kind, accumulate, dx, dweight, dbias);
+    norm_bwd_kernel<bf16><<<grid, 256, smem, ST>>>(x, (const bf16*)dy, weight, M, d, eps, kind, accumulate, dx, dweight, dbias, cast_out, cast_scale);
   else
-    norm_bwd_kernel<float><<<grid, 256, smem, ST>>>(x, (const float*)dy, weight, M, d, eps, kind, accumulate, dx, dweight, dbias);
+    norm_bwd_kernel<float><<<grid, 256, smem, ST>>>(x, (const float*)dy, weight, M, d, eps, kind, accumulate, dx, dweight, dbias, cast_out, cast_scale);
   LCASR_LAUNCH_CHECK();
   return 0;
 }

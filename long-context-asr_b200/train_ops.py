@@ -203,13 +203,15 @@ def colsum_(out, x, scale=1.0):
     return out
 
 
-def layernorm_bwd(x, dy, weight, dx, dweight, dbias=None, eps=1e-5, kind="layer_norm", accumulate=True):
+def layernorm_bwd(x, dy, weight, dx, dweight, dbias=None, eps=1e-5, kind="layer_norm", accumulate=True, cast_scale=None):
+    """returns dx, or (dx, bf16 copy of cast_scale * dx) when cast_scale is given (the next sub-layer's dY operand)"""
     _cuda(x, dy, weight, dx, dweight, dbias)
     M, d = x.shape
-    L.call("lcasr_layernorm_bwd", L.ptr(x), L.ptr(dy), L.dtype_code(dy.dtype), L.ptr(weight), M, d, float(eps),
+    cast = torch.empty(M, d, dtype=BF, device=x.device) if cast_scale is not None else None
+    L.call("lcasr_layernorm_bwd_cast", L.ptr(x), L.ptr(dy), L.dtype_code(dy.dtype), L.ptr(weight), M, d, float(eps),
            L.NORM_RMSNORM if kind == "rms_norm" else L.NORM_LAYERNORM, int(accumulate), L.ptr(dx), L.ptr(dweight),
-           L.ptr(dbias), _s())
-    return dx
+           L.ptr(dbias), L.ptr(cast), float(cast_scale or 1.0), _s())
+    return dx if cast_scale is None else (dx, cast)
 
 
 def dwconv1d_fwd(x, w, b, stats=False):

@@ -270,8 +270,10 @@ class TrainEngine:
         SILU = L.ACT_SILU
         handles = []
 
-        def ln_bwd(x, dy, pk, dx, accumulate):
-            return T.layernorm_bwd(x, dy, P[pk + "_w"], dx, G[pk + "_w"], G.get(pk + "_b"), eps=eps, kind=kind, accumulate=accumulate)
+        def ln_bwd(x, dy, pk, dx, accumulate, cast_scale=None):
+            """cast_scale: also return bf16(cast_scale * dx), the dY operand of the sub-layer processed next"""
+            return T.layernorm_bwd(x, dy, P[pk + "_w"], dx, G[pk + "_w"], G.get(pk + "_b"), eps=eps, kind=kind, accumulate=accumulate,
+                                   cast_scale=cast_scale)
 
         def linear_bwd(dy, x_in, wk, bk=None, need_dx=True, **kw):
             """dy [M,out] bf16, x_in [M,in] bf16: weight (+bias) gradients, returns dx [M,in] bf16"""
@@ -305,16 +307,19 @@ class TrainEngine:
                     ln_bwd(sc["x"], da6, "dec_norm", dx, accumulate=True)
                 else:
                     T.add_bf16_(dx, da6)
-            ln_bwd(R["x_pre_out"], dx, q + "norm_out", dx, accumulate=False)
+            _, dy_next = ln_bwd(R["x_pre_out"], dx, q + "norm_out", dx, accumulate=False, cast_scale=0.5)  # ff2 comes next
+            nxt = {"ff2": 1.0, "conv": 1.0, "attn": 0.5}  # residual scale of the sub-layer that FOLLOWS in the backward order
             for ff in ("ff2", "conv", "attn", "ff1"):
                 r = R[ff]
+                cs = nxt.get(ff)  # None after ff1: the next consumer is the previous layer's self-conditioning / norm_out
                 if ff in ("ff1", "ff2"):
-                    dy = T.scale_cast(dx, 0.5)
+                    dy = dy_next
                     dh = linear_bwd(dy, r["hact"], q + ff + "_fc2_w", q + ff + "_fc2_b", aux=r["hpre"], epi=L.EPI_GELU_BWD)
                     da = linear_bwd(dh, r["a"], q + ff + "_fc1_w", q + ff + "_fc1_b")
-                    ln_bwd(r["x"], da, q + ff + "_norm", dx, accumulate=True)
+                    res = ln_bwd(r["x"], da, q + ff + "_norm", dx, accumulate=True, cast_scale=cs)
+                    dy_next = res[1] if cs is not None else None
                 elif ff == "conv":
-                    dy = T.scale_cast(dx, 1.0)
+                    dy = dy_next
                     dyy = linear_bwd(dy, r["y"].view(M, d), q + "pw2_w", q + "pw2_b")
                     dc = T.brn_silu_bwd(r["c"], dyy.view(B, N, d), r["A"], r["Bc"], r["stats"], P[q + "brn_w"], G[q + "brn_w"],
                                         G[q + "brn_b"])
@@ -322,14 +327,14 @@ class TrainEngine:
                     dg = T.dwconv1d_bwd_data(dc, P[q + "dw_w"])
                     du = T.glu_bwd(r["u"], dg.view(M, d))
                     da = linear_bwd(du, r["a"], q + "pw1_w", q + "pw1_b")
-                    ln_bwd(r["x"], da, q + "conv_norm", dx, accumulate=True)
+                    _, dy_next = ln_bwd(r["x"], da, q + "conv_norm", dx, accumulate=True, cast_scale=cs)
                 else:
-                    dy = T.scale_cast(dx, 1.0)
+                    dy = dy_next
                     do = linear_bwd(dy, r["o"].view(M, d), q + "out_w")
                     dq, dk, dv = T.attention_bwd(r["q"], r["k"], r["v"], r["o"].view(B, N, H, Dh), do.view(B, N, H, Dh), r["lse"])
                     dqkv = T.rope_bwd_merge(dq, dk, dv, S["cos"], S["sin"])
                     da = linear_bwd(dqkv, r["a"], q + "qkv_w")
-                    ln_bwd(r["x"], da, q + "attn_norm", dx, accumulate=True)
+                    _, dy_next = ln_bwd(r["x"], da, q + "attn_norm", dx, accumulate=True, cast_scale=cs)
             S["layers"][l] = None  # release this layer's activations
             if self.dp_group is not None:  # this layer's parameter gradients are final: reduce them behind the rest of the backward
                 handles.append(self._reduce_slice(flat, q))
