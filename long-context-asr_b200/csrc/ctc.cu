@@ -17,10 +17,36 @@ namespace lcasr {
 
 constexpr int kCtcMaxSPT = 32;
 
+// log(e^a + e^b + e^c).  The correction term log(sum of exp(x - max)) lies in [0, log 3]; the state values themselves are
+// O(10^2..10^4) in magnitude, so their fp32 ulp (6e-5 at 1000) is orders above the 2^-22 error of ex2/lg2.approx:
+// the fast intrinsics cost nothing in accuracy and take the recursion from ~70 to ~20 instructions per state
+// (the frame loop is issue-bound on ONE SM per sample: 0.84 -> see DESIGN.md us per frame at 1229 states).
 __device__ __forceinline__ float lse3(float a, float b, float c) {
   float m = fmaxf(fmaxf(a, b), c);
   if (m == -INFINITY) return -INFINITY;
-  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+}
+
+// G[b, t, s] = log_probs[b, t, ext_label(s)] for every frame, into BOTH lattices (fully parallel pre-pass)
+__global__ void __launch_bounds__(256) ctc_gather_kernel(const float* __restrict__ log_probs, int64_t N, int V,
+                                                         const int64_t* __restrict__ targets, int64_t S_max,
+                                                         const int32_t* __restrict__ input_lengths,
+                                                         const int64_t* __restrict__ target_lengths, int blank,
+                                                         float* __restrict__ ga, float* __restrict__ gb) {
+  const int b = blockIdx.y;
+  const int64_t t = blockIdx.x;
+  const int64_t T = input_lengths ? min((int64_t)input_lengths[b], N) : N;
+  if (t >= T) return;
+  const int Lp = (int)(2 * target_lengths[b] + 1), Lp_max = (int)(2 * S_max + 1);
+  const float* row = log_probs + ((int64_t)b * N + t) * V;
+  const int64_t* tgt = targets + (int64_t)b * S_max;
+  const int64_t o = ((int64_t)b * N + t) * Lp_max;
+  const float bl = row[blank];
+  for (int s = threadIdx.x; s < Lp; s += 256) {
+    const float v = (s & 1) ? row[(int)tgt[(s - 1) >> 1]] : bl;
+    ga[o + s] = v;
+    gb[o + s] = v;
+  }
 }
 
 // direction = +1: alpha (forward in time, labels as given); direction = -1: beta (time and label
@@ -33,7 +59,11 @@ __global__ void __launch_bounds__(1024) ctc_recursion_kernel(const float* __rest
                                                              const int64_t* __restrict__ target_lengths, int blank,
                                                              int direction, float* __restrict__ nll,
                                                              float* __restrict__ store, float* __restrict__ store_beta,
-                                                             int batch) {
+                                                             int batch, int pregathered) {
+  // pregathered (direction == 0 only): both lattices were pre-filled with G[t, s] = log_probs[t, ext_label(s)] by
+  // ctc_gather_kernel; the recursion then reads its per-frame inputs as one coalesced row (a few 128-byte lines)
+  // instead of ~(S+1) scattered sectors per frame, which is what bounded the frame time (LSU: ~1 sector per clock),
+  // and overwrites row t with alpha / beta after it has been consumed (reads run kPF frames ahead of the writes).
   // direction == 0: BOTH recursions in one launch (grid = 2*batch CTAs): CTA b < batch runs alpha into `store`,
   // CTA batch+b runs beta into `store_beta` (plain stores: the two are independent and run concurrently)
   extern __shared__ float sm_alpha[];  // [2][Lp_pad]
@@ -82,7 +112,11 @@ __global__ void __launch_bounds__(1024) ctc_recursion_kernel(const float* __rest
   }
   auto frame = [&](int64_t step) -> int64_t { return direction > 0 ? step : (T - 1 - step); };
 
-  float lpv[SPT], lpn[SPT];
+  // log-prob gathers run kPF frames AHEAD of their use (a register ring indexed at compile time by unrolling the
+  // frame loop kPF times): one frame of recursion (~0.2 us) is far shorter than the ~0.6 us global-memory latency of
+  // a gather, which a one-frame look-ahead exposed on every step (0.82 us/frame measured before).
+  constexpr int kPF = SPT <= 4 ? 4 : (SPT <= 8 ? 2 : 1);  // the ring costs kPF*SPT registers (1024-thread CTAs: 64 in all)
+  float lpq[kPF][SPT];
   {
     const float* row = lp + frame(0) * V;
 #pragma unroll
@@ -98,39 +132,69 @@ __global__ void __launch_bounds__(1024) ctc_recursion_kernel(const float* __rest
         *p = (direction > 0 || !beta_adds) ? a : (*p + a);
       }
     }
-    if (T > 1) {
-      const float* row1 = lp + frame(1) * V;
 #pragma unroll
-      for (int j = 0; j < SPT; ++j) lpv[j] = row1[lab[j]];
-    }
-  }
-  __syncthreads();
-  for (int64_t step = 1; step < T; ++step) {
-    if (step + 1 < T) {
-      const float* rown = lp + frame(step + 1) * V;
+    for (int u = 0; u < kPF; ++u) {  // frames 1 .. kPF
+      if (1 + u < T) {
+        const float* rowu = lp + frame(1 + u) * V;
+        const float* gu = st + frame(1 + u) * Lp_max;
 #pragma unroll
-      for (int j = 0; j < SPT; ++j) lpn[j] = rown[lab[j]];
-    }
-    float* strow = st ? st + frame(step) * Lp_max : nullptr;
-#pragma unroll
-    for (int j = 0; j < SPT; ++j) {
-      int s = tid + j * NT;
-      if (s < Lp) {
-        float a0 = cur[s];
-        float a1 = s >= 1 ? cur[s - 1] : -INFINITY;
-        float a2 = skip[j] ? cur[s - 2] : -INFINITY;
-        float a = lse3(a0, a1, a2) + lpv[j];
-        nxt[s] = a;
-        if (strow) {
-          int so = direction > 0 ? s : (Lp - 1 - s);
-          strow[so] = (direction > 0 || !beta_adds) ? a : (strow[so] + a);
+        for (int j = 0; j < SPT; ++j) {
+          const int s = tid + j * NT;
+          if (pregathered) lpq[u][j] = s < Lp ? gu[direction > 0 ? s : (Lp - 1 - s)] : 0.f;
+          else lpq[u][j] = rowu[lab[j]];
         }
       }
     }
-    __syncthreads();
-    float* tmp = cur; cur = nxt; nxt = tmp;
+  }
+  __syncthreads();
+  // The frame loop is issue-bound on one SM (ncu: 64 % issue-active, ~190 warp instructions per frame before this
+  // form): everything that does not depend on the frame is hoisted — per-state validity / output index, and the
+  // row pointers advance by a constant stride instead of being rebuilt from 64-bit products every frame.
+  const int64_t dstride = (int64_t)direction * Lp_max, lstride = (int64_t)direction * V;
+  bool live[SPT];
+  int so_j[SPT];
 #pragma unroll
-    for (int j = 0; j < SPT; ++j) lpv[j] = lpn[j];
+  for (int j = 0; j < SPT; ++j) {
+    const int s = tid + j * NT;
+    live[j] = s < Lp;
+    so_j[j] = direction > 0 ? s : (Lp - 1 - s);
+    if (!live[j]) so_j[j] = 0;
+  }
+  float* strow = st ? st + frame(1) * Lp_max : nullptr;             // row of the frame being computed
+  const float* pf_g = st ? st + frame(1 + kPF) * Lp_max : nullptr;   // rows kPF frames ahead (pre-gathered inputs)
+  const float* pf_l = lp + frame(1 + kPF) * V;                        // (gather form)
+  for (int64_t step0 = 1; step0 < T; step0 += kPF) {
+#pragma unroll
+    for (int u = 0; u < kPF; ++u) {
+      const int64_t step = step0 + u;
+      if (step >= T) break;  // block-uniform
+      float lpv[SPT];
+#pragma unroll
+      for (int j = 0; j < SPT; ++j) lpv[j] = lpq[u][j];
+      if (step + kPF < T) {  // refill this ring slot with the frame kPF steps ahead
+#pragma unroll
+        for (int j = 0; j < SPT; ++j) {
+          if (pregathered) lpq[u][j] = live[j] ? pf_g[so_j[j]] : 0.f;
+          else lpq[u][j] = pf_l[lab[j]];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < SPT; ++j) {
+        const int s = tid + j * NT;
+        if (live[j]) {
+          const float a0 = cur[s];
+          const float a1 = s >= 1 ? cur[s - 1] : -INFINITY;
+          const float a2 = skip[j] ? cur[s - 2] : -INFINITY;
+          const float a = lse3(a0, a1, a2) + lpv[j];
+          nxt[s] = a;
+          if (strow) strow[so_j[j]] = (direction > 0 || !beta_adds) ? a : (strow[so_j[j]] + a);
+        }
+      }
+      __syncthreads();
+      float* tmp = cur; cur = nxt; nxt = tmp;
+      if (strow) { strow += dstride; pf_g += dstride; }
+      pf_l += lstride;
+    }
   }
   if (tid == 0 && nll) {
     float l1 = cur[Lp - 1];
@@ -346,7 +410,7 @@ __global__ void __launch_bounds__(256) ctc_grad_collect_kernel(const float* __re
 template <int SPT>
 static int launch_rec(const float* lp, int B, int64_t N, int V, const int64_t* tg, int64_t S_max, const int32_t* il,
                       const int64_t* tl, int blank, int dir, float* nll, float* store, int nt, cudaStream_t st,
-                      float* store_beta = nullptr) {
+                      float* store_beta = nullptr, int pregathered = 0) {
   size_t smem = (size_t)2 * SPT * nt * sizeof(float);
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
@@ -354,14 +418,14 @@ static int launch_rec(const float* lp, int B, int64_t N, int V, const int64_t* t
     attr = smem;
   }
   ctc_recursion_kernel<SPT><<<dir == 0 ? 2 * B : B, nt, smem, st>>>(lp, N, V, tg, S_max, il, tl, blank, dir, nll, store,
-                                                                    store_beta, B);
+                                                                    store_beta, B, pregathered);
   LCASR_LAUNCH_CHECK();
   return 0;
 }
 
 static int ctc_recursion(const float* lp, int B, int64_t N, int V, const int64_t* tg, int64_t S_max, const int32_t* il,
                          const int64_t* tl, int blank, int dir, float* nll, float* store, cudaStream_t st,
-                         float* store_beta = nullptr) {
+                         float* store_beta = nullptr, int pregathered = 0) {
   const int64_t Lp = 2 * S_max + 1;
   LCASR_CHECK_ARG(dir != 0 || Lp <= 4096, "ctc_loss: the concurrent alpha/beta form covers up to 4096 extended states");
   static const bool no_cluster = getenv("LCASR_CTC_NO_CLUSTER") != nullptr;  // A/B switch for profiling
@@ -389,12 +453,12 @@ static int ctc_recursion(const float* lp, int B, int64_t N, int V, const int64_t
   while ((size_t)2 * spt * nt * 4 > 227 * 1024 && nt > 32) nt -= 32;
   LCASR_CHECK_ARG((int64_t)spt * nt >= Lp, "ctc_loss: internal sizing error");
   switch (spt) {
-    case 1: return launch_rec<1>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st, store_beta);
-    case 2: return launch_rec<2>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st, store_beta);
-    case 4: return launch_rec<4>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st, store_beta);
-    case 8: return launch_rec<8>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st, store_beta);
-    case 16: return launch_rec<16>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st, store_beta);
-    default: return launch_rec<32>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st, store_beta);
+    case 1: return launch_rec<1>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st, store_beta, pregathered);
+    case 2: return launch_rec<2>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st, store_beta, pregathered);
+    case 4: return launch_rec<4>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st, store_beta, pregathered);
+    case 8: return launch_rec<8>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st, store_beta, pregathered);
+    case 16: return launch_rec<16>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st, store_beta, pregathered);
+    default: return launch_rec<32>(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, nt, st, store_beta, pregathered);
   }
 }
 
@@ -445,8 +509,13 @@ extern "C" int lcasr_ctc_loss_fwd_ab(const float* log_probs, int B, int64_t N, i
                                      int blank, float* nll, float* alpha_ws, float* beta_ws, void* stream) {
   LCASR_CHECK_ARG(log_probs && targets && target_lengths && nll && alpha_ws && beta_ws, "ctc_loss_fwd_ab: NULL argument");
   LCASR_CHECK_ARG(B > 0 && N > 0 && V > 1 && S_max >= 0 && blank >= 0 && blank < V, "ctc_loss_fwd_ab: bad shape");
+  LCASR_CHECK_ARG(B <= 65535 && N < ((int64_t)1 << 31), "ctc_loss_fwd_ab: batch / length too large");
+  dim3 grid((unsigned)N, (unsigned)B);
+  ctc_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(log_probs, N, V, targets, S_max, input_lengths, target_lengths, blank,
+                                                            alpha_ws, beta_ws);
+  LCASR_LAUNCH_CHECK();
   return ctc_recursion(log_probs, B, N, V, targets, S_max, input_lengths, target_lengths, blank, 0, nll, alpha_ws,
-                       (cudaStream_t)stream, beta_ws);
+                       (cudaStream_t)stream, beta_ws, 1);
 }
 
 // ... and the gradient from the two state lattices (no recursion left in the backward).
