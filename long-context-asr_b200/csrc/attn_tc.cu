@@ -303,7 +303,8 @@ __device__ int g_attn_trace_on = 0;
 #define TRACE_M1(t, j) do { } while (0)
 #endif
 
-template <int DH> struct Fa2Cfg {
+// PX = packed-exponential variant (POLY == 16, Dh = 32): see the softmax loop
+template <int DH, bool PX = false> struct Fa2Cfg {
   static constexpr int STAGES = DH == 128 ? 2 : (DH == 64 ? 3 : 4);
   static constexpr int ROW_BYTES = DH >= 64 ? 128 : 64;
   static constexpr int SUB = DH >= 64 ? DH / 64 : 1;
@@ -326,7 +327,9 @@ template <int DH> struct Fa2Cfg {
   // ones (a constant all-ones MN-atom in shared memory reached through the descriptor's LBO), so PV
   // produces O[:, 32..47] = sum_k P[:, k] — with the bf16-rounded P that the numerator uses — and the
   // softmax warps drop 128 FADDs per row tile (22% of their instructions; they are issue/latency bound).
-  static constexpr bool MMA_SUM = false;  // implemented and parity-tested for DH == 32, but measured 4% slower: off
+  // (alone it measured 4 % slower; it is what makes the packed bf16x2 exponential possible, whose results never
+  //  exist as fp32 values that could be summed on the CUDA cores)
+  static constexpr bool MMA_SUM = PX && DH == 32;
   static constexpr int PV_N = MMA_SUM ? DH + 16 : DH;
   static constexpr int O_STRIDE = MMA_SUM ? 64 : DH;
   static constexpr int ONES_BYTES = MMA_SUM ? FA_BK * ROW_BYTES : 0;
@@ -345,7 +348,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // (lse2 = max*scale*log2e + log2(sum)), so that the backward recomputes P = exp2(s*scale*log2e - lse2)
   // N = query rows per batch entry, Nk = keys per batch entry (row pitch of k/v); kv_len (may be NULL): the
   // number of VALID keys of each batch entry — the key-padding mask of ragged batches (attention.py:511-547)
-  using Cfg = Fa2Cfg<DH>;
+  using Cfg = Fa2Cfg<DH, POLY == 16>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[1 + 2 * Cfg::STAGES + 9];
   __shared__ uint32_t tmem_slot;
@@ -634,7 +637,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (j == 0) {
         m_run = mx;
       } else {
-        const bool grow = mx > m_run + 8.0f;
+        // packed-exponential variant: the exponent argument is rounded to bf16, so it must stay <= 0 (running max exact)
+        const bool grow = mx > m_run + (POLY == 16 ? 0.0f : 8.0f);
         if (__any_sync(0xffffffffu, grow)) {
           // O_t must be quiescent.  Aliased P: PV_t(j-1) precedes QK_t(j) in the tensor pipe, so it has
           // retired when s_full fired.  Separate P: wait for its commit.
@@ -675,6 +679,22 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int c = 0; c < FA_BK / 64; ++c) {
         uint32_t pk[32];
+        if constexpr (POLY == 16) {
+          // Packed exponential: P is needed as bf16 anyway, so two arguments are rounded to bf16x2 and ONE MUFU
+          // instruction (ex2.approx.ftz.bf16x2) produces two probabilities already in the operand format — half the
+          // MUFU work (the binding unit at Dh = 32: 74 % busy) and 4 instead of 7 issue slots per pair (no fp32 sums:
+          // the row sums come from the tensor core, MMA_SUM; no separate pack).  Arguments are <= 0 (exact running
+          // max), so their bf16 rounding error is <= 2^-9 for the terms that matter (|x| < 1: 0.14 % on p, the size
+          // of P's own bf16 rounding).
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x0 = fmaf(__uint_as_float(s[c * 64 + 2 * i]), scale_log2, neg_m);
+            const float x1 = fmaf(__uint_as_float(s[c * 64 + 2 * i + 1]), scale_log2, neg_m);
+            uint32_t xx;
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(xx) : "f"(x1), "f"(x0));  // {hi, lo} = {x1, x0}
+            asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(pk[i]) : "r"(xx));
+          }
+        } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float x0 = fmaf(__uint_as_float(s[c * 64 + 2 * i]), scale_log2, neg_m);
@@ -686,6 +706,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if constexpr (!Cfg::MMA_SUM) { sums[(2 * i) & 7] += p0; sums[(2 * i + 1) & 7] += p1; }
           __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
           pk[i] = *reinterpret_cast<uint32_t*>(&pp);
+        }
         }
         tmem_st_32x32b_x32(p_addr + c * 32, pk);
         if (c == 0 && j == 0 && t == 0) {
@@ -743,7 +764,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 template <int DH, int POLY, bool WIN = false>
 static int launch_attn_tc2(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len,
                            int H, void* out, float* lse, int wl, int wr, cudaStream_t st) {
-  using Cfg = Fa2Cfg<DH>;
+  using Cfg = Fa2Cfg<DH, POLY == 16>;
   const uint64_t d = (uint64_t)H * DH;
   const CUtensorMapSwizzle sw = DH >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap tmQ, tmK, tmV;
@@ -814,7 +835,8 @@ int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N
   LCASR_CHECK_ARG(H <= 65535 && B <= 65535, "attention(tcgen05): too many heads / batch entries");
   static const bool force_v1 = getenv("LCASR_ATTN_V1") != nullptr;  // debugging aid: one query tile per CTA
   // fraction of exponentials evaluated on the FMA pipes: POLY=p -> every p-th odd key, i.e. 1/(2p) of all
-  static const int poly = getenv("LCASR_ATTN_POLY") ? atoi(getenv("LCASR_ATTN_POLY")) : 0;  // measured: the Dh=32 kernel is latency- not MUFU-bound, offload does not pay yet
+  static const int poly_env = getenv("LCASR_ATTN_POLY") ? atoi(getenv("LCASR_ATTN_POLY")) : 0;  // measured: the Dh=32 kernel is latency- not MUFU-bound, offload does not pay yet
+  const int poly = (poly_env == 16 && Dh != 32) ? 0 : poly_env;  // the packed exponential exists for head dim 32 only
 #define LCASR_FA(DHV)                                                                                             \
   case DHV:                                                                                                       \
     if (v_transposed) return launch_attn_tc<DHV, true>(q, k, v, B, N, H, Npad, out, st);                          \
@@ -826,6 +848,7 @@ int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N
       case 2: return launch_attn_tc2<DHV, 2>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                                          \
       case 8: return launch_attn_tc2<DHV, 8>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                                          \
       case 9: return launch_attn_tc2<DHV, 9>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                                          \
+      case 16: return launch_attn_tc2<DHV, 16>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                                          \
       default: return launch_attn_tc2<DHV, 4>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                                         \
     }
   switch (Dh) {

@@ -53,7 +53,7 @@ class LocalComm:
         self.world = world
         self.local_ranks = list(range(world))
 
-    def all_gather_cat(self, xs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    def all_gather_cat(self, xs: Sequence[torch.Tensor], sizes=None) -> List[torch.Tensor]:
         cat = torch.cat(list(xs), dim=0)
         return [cat for _ in xs]
 
@@ -78,12 +78,17 @@ class DistComm:
         self.rank = dist.get_rank(group)
         self.local_ranks = [self.rank]
 
-    def all_gather_cat(self, xs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    def all_gather_cat(self, xs: Sequence[torch.Tensor], sizes=None) -> List[torch.Tensor]:
+        """concatenation of every rank's rows.  `sizes` (rows per rank) is known to the caller from the static token
+        split; passing it avoids a size exchange and — more importantly — the host synchronisation that reading it
+        back costs on EVERY collective (3 per layer: the host could never run ahead of the GPU)."""
         (x,) = xs
-        n = torch.tensor([x.shape[0]], dtype=torch.int64, device=x.device)
-        sizes = [torch.zeros_like(n) for _ in range(self.world)]
-        self.dist.all_gather(sizes, n, group=self.group)
-        sizes = [int(s.item()) for s in sizes]
+        if sizes is None:
+            n = torch.tensor([x.shape[0]], dtype=torch.int64, device=x.device)
+            szt = [torch.zeros_like(n) for _ in range(self.world)]
+            self.dist.all_gather(szt, n, group=self.group)
+            sizes = [int(s.item()) for s in szt]
+        sizes = [int(v) for v in sizes]
         if len(set(sizes)) == 1:
             out = torch.empty((sizes[0] * self.world,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
             self.dist.all_gather_into_tensor(out, x.contiguous(), group=self.group)
@@ -123,6 +128,7 @@ def forward_sequence_parallel(model, spec: torch.Tensor, comm, return_logits: bo
     eps, kind = (1e-8, "rms_norm") if rms else (1e-5, "layer_norm")
     N = ops.out_length(T)
     blocks = split_tokens(N, comm.world)
+    sizes = [e - b for b, e in blocks]  # rows every rank contributes to a gather: static, no size exchange
     gi, ai = model._impl
     halo = (KS - 1) // 2
 
@@ -151,8 +157,14 @@ def forward_sequence_parallel(model, spec: torch.Tensor, comm, return_logits: bo
         xs.append(x)
         offs.append(s_tok)
 
-    tables = [ops.rope_table(P["inv_freq"], float(model.rotary_pos_emb.rotary_interpolation_factor), x.shape[0], offset=o)
-              if model.use_rotary else (None, None) for x, o in zip(xs, offs)]
+    interp = 1.0
+    if model.use_rotary:  # the buffer lives on the GPU: read it back once per buffer version, not once per forward
+        buf = model.rotary_pos_emb.rotary_interpolation_factor
+        if getattr(model, "_interp_cache", (None, None))[0] != (buf.data_ptr(), buf._version):
+            model._interp_cache = ((buf.data_ptr(), buf._version), float(buf))
+        interp = model._interp_cache[1]
+    tables = [ops.rope_table(P["inv_freq"], interp, x.shape[0], offset=o) if model.use_rotary else (None, None)
+              for x, o in zip(xs, offs)]
 
     def ffn(x, p, name):
         _, a = norm(x, p + name + "_norm")
@@ -170,8 +182,8 @@ def forward_sequence_parallel(model, spec: torch.Tensor, comm, return_logits: bo
             qkv = ops.gemm(a, P[p + "qkv_w"], impl=gi)
             q, k, v = ops.rope_split(qkv, 1, x.shape[0], H, Dh, cos, sin)
             qs.append(q); ks.append(k.view(-1, d)); vs.append(v.view(-1, d))
-        kf = comm.all_gather_cat(ks)
-        vf = comm.all_gather_cat(vs)
+        kf = comm.all_gather_cat(ks, sizes)
+        vf = comm.all_gather_cat(vs, sizes)
         for x, q, kk, vv in zip(xs, qs, kf, vf):
             o = ops.attention_cross(q, kk.view(1, -1, H, Dh), vv.view(1, -1, H, Dh), impl=ai)
             ops.gemm(o.view(-1, d), P[p + "out_w"], resid=x, alpha=1.0, impl=gi, out=x)
@@ -203,5 +215,5 @@ def forward_sequence_parallel(model, spec: torch.Tensor, comm, return_logits: bo
         logits = ops.gemm(a, P["dec_ff_w"], bias=P["dec_ff_b"], out_dtype=torch.float32, impl=gi)
         am = None if return_logits else ops.log_softmax_argmax_(logits)
         outs.append(logits); ams.append(am)
-    am_full = None if return_logits else comm.all_gather_cat(ams)[0]
+    am_full = None if return_logits else comm.all_gather_cat(ams, sizes)[0]
     return [(o, a, blocks[r]) for o, a, r in zip(outs, ams, comm.local_ranks)], am_full
