@@ -405,6 +405,7 @@ def main():
     model = lcasr_b200.SCConformerXL(**cfg, compute_dtype=args.dtype)
     model.load_state_dict(sd, strict=True)
     model = model.to(dev).eval()
+    model.cuda_graphs = args.workload == "cfg1"  # the 10-s config is launch-bound: one graph launch instead of ~135
     x_host = O.synth_input(B, T, cfg["feat_in"], seed=1234 + rank).pin_memory()
     x = x_host.to(dev)
     dec = lcasr_b200.GreedyCTCDecoder(None, blank_id=cfg["vocab_size"])
@@ -420,13 +421,14 @@ def main():
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     L.lib.lcasr_reset_launch_count()
+    model.graph_launches_replayed = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step_device()
     e1.record()
     barrier()
-    launches = int(L.lib.lcasr_launch_count())
+    launches = int(L.lib.lcasr_launch_count()) + model.graph_launches_replayed
     clocks = sampler.stop() if sampler else None
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms = (ctypes.c_float * len(CATS))()

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) subsample_conv0_kernel(const float* __res
 
 // ---- depthwise Conv2d(C,3x3,s2,p1,groups=C), channels-last ------------------------------------
 // One CTA = kDwTB output time rows of one recording; all index arithmetic is 32-bit (the flat 64-bit
-// div/mod chain of a grid-stride loop cost more than the memory traffic: 775 us -> see DESIGN.md).
+// div/mod chain of a grid-stride loop is avoided; measured 775 -> 685 us for the level-1 tensor of cfg 5).
 constexpr int kDwTB = 4;
 template <typename T, int V> struct VecT;
 template <> struct VecT<float, 8> : Vec8<float> {};

@@ -250,6 +250,11 @@ class SCConformerXL(nn.Module):
         self._workspace: Optional[torch.Tensor] = None
         self._impl = (L.GEMM_AUTO, L.ATTN_AUTO)
         self.last_argmax: Optional[torch.Tensor] = None
+        # opt-in: replay the ~135 launches of an equal-length eval forward as ONE CUDA graph per (B, T) — for
+        # launch-bound shapes (10-s contexts: 1.97 ms of launches for ~0.4 ms of kernels)
+        self.cuda_graphs = False
+        self._graphs: Dict = {}
+        self.graph_launches_replayed = 0  # kernels launched through graph replays (they bypass lcasr_launch_count)
 
     # ---- BaseModel API (lcasr/models/base.py) -------------------------------------------------
     def print_total_params(self, only_trainable=False):
@@ -308,6 +313,7 @@ class SCConformerXL(nn.Module):
 
     def _build(self, device):
         self._destroy()
+        self._graphs = {}  # captured graphs hold the old handle / weight pointers
         cdt = self.compute_dtype
         sd = {k: v.detach() for k, v in self.state_dict().items()}
         H, Dh, d, Cc = self.n_heads, self.head_dim, self.d_model, self.subsampling_conv_channels
@@ -475,6 +481,10 @@ class SCConformerXL(nn.Module):
         x = audio_signal.to(torch.float32).contiguous()
         self._ensure_built(device)
         V1 = self.decoder.num_classes
+        if self.cuda_graphs and tok_len is None:
+            out, argmax = self._forward_graph(x, B, T, N, V1, return_logits, device)
+            self.last_argmax = None if return_logits else argmax
+            return {"final_posteriors": out, "length": length_out}
         out = torch.empty(B, N, V1, dtype=torch.float32, device=device)
         argmax = torch.empty(B, N, dtype=torch.int32, device=device)
         nbytes = int(L.lib.lcasr_model_workspace_bytes(self._handle, B, T))
@@ -484,6 +494,35 @@ class SCConformerXL(nn.Module):
                    int(return_logits), L.ptr(ws), ws.numel(), L.current_stream())
         self.last_argmax = None if return_logits else argmax
         return {"final_posteriors": out, "length": length_out}
+
+    def _forward_graph(self, x, B, T, N, V1, return_logits, device):
+        """the C-ABI forward is allocation-free and asynchronous on one stream, so it captures as is: static input /
+        output / workspace buffers per (B, T), one graph launch per call, results cloned out of the static buffers"""
+        key = (B, T, bool(return_logits), str(device))
+        ent = self._graphs.get(key)
+        if ent is None:
+            nbytes = int(L.lib.lcasr_model_workspace_bytes(self._handle, B, T))
+            ent = dict(x=torch.empty_like(x), out=torch.empty(B, N, V1, dtype=torch.float32, device=device),
+                       am=torch.empty(B, N, dtype=torch.int32, device=device), ws=torch.empty(nbytes, dtype=torch.uint8, device=device))
+
+            def run():
+                L.call("lcasr_model_forward_lengths", self._handle, L.ptr(ent["x"]), B, T, None, L.ptr(ent["out"]), L.ptr(ent["am"]),
+                       int(return_logits), L.ptr(ent["ws"]), ent["ws"].numel(), L.current_stream())
+            ent["x"].copy_(x)
+            with torch.cuda.device(device):
+                run()  # un-captured warm-up: function attributes, tensor-map entry point
+                torch.cuda.synchronize(device)
+                g = torch.cuda.CUDAGraph()
+                n0 = int(L.lib.lcasr_launch_count())
+                with torch.cuda.graph(g):
+                    run()
+                ent["launches"] = int(L.lib.lcasr_launch_count()) - n0
+            ent["graph"] = g
+            self._graphs[key] = ent
+        ent["x"].copy_(x)
+        ent["graph"].replay()
+        self.graph_launches_replayed += ent["launches"]
+        return ent["out"].clone(), ent["am"].clone()
 
     @torch.no_grad()
     def transcribe_host(self, spec_host: torch.Tensor):

@@ -135,3 +135,22 @@ def test_oracle_vs_cuda_midsize_fp32(cuda_device):
     report(test="model_fp32_mid", max_abs=err)
     assert err < 1e-4 * max(1.0, ref.abs().max().item() / 8)
     assert [O.greedy_decode(lp[b], 4095) for b in range(2)] == [O.greedy_decode(ref[b], 4095) for b in range(2)]
+
+
+def test_cuda_graph_replay_matches_eager(cuda_device):
+    """opt-in CUDA-graph replay of the eval forward: bit-identical to the eager launches, for several inputs and shapes"""
+    g = load_golden("cfg1_6L256D8H")
+    model, cfg, sd = build_model(g, cuda_device, "bf16")
+    xs = [O.synth_input(g["batch"], g["frames"], cfg["feat_in"], seed=s).to(cuda_device) for s in (1, 2)] + \
+         [O.synth_input(2, 520, cfg["feat_in"], seed=3).to(cuda_device)]
+    eager = [(model(x)["final_posteriors"].clone(), model.last_argmax.clone()) for x in xs]
+    model.cuda_graphs = True
+    for rep in range(2):
+        for x, (lp, am) in zip(xs, eager):
+            out = model(x)
+            assert torch.equal(out["final_posteriors"], lp) and torch.equal(model.last_argmax, am)
+    assert len(model._graphs) == 2
+    model.load_state_dict(O.synth_state_dict(cfg, seed=5), strict=True)  # new weights: graphs are dropped and re-captured
+    lp_new = model(xs[0])["final_posteriors"]
+    model.cuda_graphs = False
+    assert torch.equal(lp_new, model(xs[0])["final_posteriors"])
