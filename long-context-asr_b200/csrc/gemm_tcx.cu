@@ -15,6 +15,7 @@
 //
 // Tensor-bound: algorithmic FLOPs = 2*M*N*K per batch entry.
 #include "common.cuh"
+#include <cstdlib>
 #include "sm100_ptx.cuh"
 
 namespace lcasr {
@@ -25,10 +26,12 @@ constexpr int TX_BM = 128, TX_BK = 64;
 constexpr int TX_EPI_WARPS = 8;  // two epilogue warps per TMEM lane quarter, each draining half of the tile's columns
 constexpr int TX_THREADS = 64 + 32 * TX_EPI_WARPS;
 
-template <int BN> struct TxCfg {
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
+// CG = 2: CTA pairs (tcgen05 cta_group::2, see gemm_tc.cu): 256-row tiles, each CTA stages its 128 rows of A and
+// HALF of the B tile; the leader issues the MMAs, commits are multicast, the peer's epilogue arrives remotely.
+template <int BN, int CG = 1> struct TxCfg {
+  static constexpr int STAGES = BN == 256 ? (CG == 2 ? 5 : 4) : (CG == 2 ? 7 : 6);
   static constexpr int A_BYTES = TX_BM * TX_BK * 2;
-  static constexpr int B_BYTES = BN * TX_BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * TX_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int OUT_STAGE_BYTES = TX_EPI_WARPS * 4096;  // bf16 outputs leave through TMA stores (see gemm_tc.cu)
@@ -56,6 +59,14 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d_cg2(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1,
+                                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 
@@ -170,14 +181,14 @@ struct TxTile {
   int m_idx, n_idx, b1, b2, kb0, kb1;
 };
 
-template <int BN>
+template <int BN, int CG>
 __device__ __forceinline__ TxTile tx_decode(int64_t tile, const TxParams& p, int tiles_n, int64_t tiles_m, int num_k) {
   TxTile t;
   const int ks = (int)(tile % p.ksplit);
   tile /= p.ksplit;
   t.n_idx = (int)(tile % tiles_n) * BN;
   tile /= tiles_n;
-  t.m_idx = (int)(tile % tiles_m) * TX_BM;
+  t.m_idx = (int)(tile % tiles_m) * (CG * TX_BM);
   tile /= tiles_m;
   t.b1 = (int)(tile % p.nb1);
   t.b2 = (int)(tile / p.nb1);
@@ -186,12 +197,13 @@ __device__ __forceinline__ TxTile tx_decode(int64_t tile, const TxParams& p, int
   return t;
 }
 
-template <int BN, int A_MN, int B_MN, typename TOut>
+template <int BN, int A_MN, int B_MN, typename TOut, int CG>
 __global__ void __launch_bounds__(TX_THREADS, 1)
 gemm_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, TxParams p, TOut* out) {
   // tmC (bf16 outputs): 4-D store map of `out`, 64-column x 32-row boxes, 128B swizzle
-  using Cfg = TxCfg<BN>;
+  using Cfg = TxCfg<BN, CG>;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * Cfg::STAGES + 4];
   __shared__ uint32_t tmem_slot;
@@ -205,59 +217,65 @@ gemm_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = (p.K + TX_BK - 1) / TX_BK;
   const int tiles_n = (p.N + BN - 1) / BN;
-  const int64_t tiles_m = (p.M + TX_BM - 1) / TX_BM;
+  const int64_t tiles_m = (p.M + CG * TX_BM - 1) / (CG * TX_BM);
+  const int64_t tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;  // per cluster
   const int64_t total_tiles = tiles_m * tiles_n * p.ksplit * p.nb1 * p.nb2;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TX_EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), CG * TX_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CG == 2) { tmem_alloc_cg2(smem_u32(&tmem_slot), Cfg::TMEM_COLS); tmem_relinquish_cg2(); }
+    else { tmem_alloc(smem_u32(&tmem_slot), Cfg::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer ----------------
       int stage = 0; uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TxTile t = tx_decode<BN>(tile, p, tiles_n, tiles_m, num_k);
+      const uint32_t full0 = CG == 2 ? mapa_shared(full_bar(0), 0) : full_bar(0);  // the leader's full barriers
+      auto load = [&](uint32_t dst, const CUtensorMap* m, int st_, int c0, int c1, int c2, int c3) {
+        if constexpr (CG == 2) tma_load_4d_cg2(dst, m, full0 + 8u * st_, c0, c1, c2, c3);
+        else tma_load_4d(dst, m, full_bar(st_), c0, c1, c2, c3);
+      };
+      for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
+        const TxTile t = tx_decode<BN, CG>(tile, p, tiles_n, tiles_m, num_k);
+        const int m_idx = t.m_idx + (int)rank * TX_BM, n_idx = t.n_idx + (int)rank * (BN / CG);  // this CTA's halves
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), CG * Cfg::STAGE_BYTES);  // both CTAs' bytes land here
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
           if constexpr (A_MN) {
 #pragma unroll
-            for (int i = 0; i < TX_BM / 64; ++i)
-              tma_load_4d(sa + i * 8192, &tmA, full_bar(stage), t.m_idx + i * 64, kb * TX_BK, t.b1, t.b2);
+            for (int i = 0; i < TX_BM / 64; ++i) load(sa + i * 8192, &tmA, stage, m_idx + i * 64, kb * TX_BK, t.b1, t.b2);
           } else {
-            tma_load_4d(sa, &tmA, full_bar(stage), kb * TX_BK, t.m_idx, t.b1, t.b2);
+            load(sa, &tmA, stage, kb * TX_BK, m_idx, t.b1, t.b2);
           }
           if constexpr (B_MN) {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_4d(sb + i * 8192, &tmB, full_bar(stage), t.n_idx + i * 64, kb * TX_BK, t.b1, t.b2);
+            for (int i = 0; i < (BN / CG) / 64; ++i) load(sb + i * 8192, &tmB, stage, n_idx + i * 64, kb * TX_BK, t.b1, t.b2);
           } else {
-            tma_load_4d(sb, &tmB, full_bar(stage), kb * TX_BK, t.n_idx, t.b1, t.b2);
+            load(sb, &tmB, stage, kb * TX_BK, n_idx, t.b1, t.b2);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc = make_idesc_bf16_mn(TX_BM, BN, A_MN, B_MN);
+    if (lane == 0 && rank == 0) {  // ---------------- MMA issuer (leader CTA only) ----------------
+      constexpr uint32_t idesc = make_idesc_bf16_mn(CG * TX_BM, BN, A_MN, B_MN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TxTile t = tx_decode<BN>(tile, p, tiles_n, tiles_m, num_k);
+      for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
+        const TxTile t = tx_decode<BN, CG>(tile, p, tiles_n, tiles_m, num_k);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -268,13 +286,18 @@ gemm_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint64_t adesc = A_MN ? make_smem_desc_mnmajor(sa) : make_smem_desc_kmajor(sa, 1024, kLayoutSW128);
           const uint64_t bdesc = B_MN ? make_smem_desc_mnmajor(sb) : make_smem_desc_kmajor(sb, 1024, kLayoutSW128);
 #pragma unroll
-          for (int k = 0; k < TX_BK / 16; ++k)  // K-major: +32 B per K=16 step; MN-major: +16 rows * 128 B
-            umma_f16_ss(d_tmem, adesc + (A_MN ? 128 : 2) * k, bdesc + (B_MN ? 128 : 2) * k, idesc,
-                        (kb != t.kb0 || k != 0) ? 1u : 0u);
-          umma_commit(empty_bar(stage));
+          for (int k = 0; k < TX_BK / 16; ++k) {  // K-major: +32 B per K=16 step; MN-major: +16 rows * 128 B
+            if constexpr (CG == 2)
+              umma_f16_ss_cg2(d_tmem, adesc + (A_MN ? 128 : 2) * k, bdesc + (B_MN ? 128 : 2) * k, idesc, (kb != t.kb0 || k != 0) ? 1u : 0u);
+            else
+              umma_f16_ss(d_tmem, adesc + (A_MN ? 128 : 2) * k, bdesc + (B_MN ? 128 : 2) * k, idesc, (kb != t.kb0 || k != 0) ? 1u : 0u);
+          }
+          if constexpr (CG == 2) umma_commit_cg2(empty_bar(stage), 3);
+          else umma_commit(empty_bar(stage));
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar(acc));
+        if constexpr (CG == 2) umma_commit_cg2(tfull_bar(acc), 3);
+        else umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -283,9 +306,11 @@ gemm_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int half = (warp - 2) >> 2;
     constexpr int CPW = (BN / 32) / (TX_EPI_WARPS / 4);  // 32-column chunks per warp
     int acc = 0; uint32_t acc_phase = 0;
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TxTile t = tx_decode<BN>(tile, p, tiles_n, tiles_m, num_k);
-      const int64_t row = (int64_t)t.m_idx + lane_base + lane;
+    const uint32_t tempty0 = CG == 2 ? mapa_shared(tempty_bar(0), 0) : 0;  // the leader's tempty barriers
+    for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
+      const TxTile t = tx_decode<BN, CG>(tile, p, tiles_n, tiles_m, num_k);
+      const int m_idx = t.m_idx + (int)rank * TX_BM;  // this CTA's 128 accumulator rows
+      const int64_t row = (int64_t)m_idx + lane_base + lane;
       const bool has_aux = p.epi >= LCASR_EPI_DS;
       // operands of the epilogue are requested BEFORE the accumulator wait: their latency hides behind the main loop
       float rv = 0.f;
@@ -344,23 +369,28 @@ gemm_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_4d(&tmC, stg, col0, t.m_idx + lane_base, t.b1, t.b2);  // rows >= M / columns >= N are clipped
+            tma_store_4d(&tmC, stg, col0, m_idx + lane_base, t.b1, t.b2);  // rows >= M / columns >= N are clipped
             tma_store_commit();
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(tempty0 + 8u * acc);
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (sizeof(TOut) == 2 && lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -579,35 +609,46 @@ static int make_tmap_4d(CUtensorMap* map, const void* base, uint64_t rows, uint6
   return 0;
 }
 
-template <int BN, int A_MN, int B_MN, typename TOut>
+template <int BN, int A_MN, int B_MN, typename TOut, int CG>
 static int launch_tcx(const lcasr_gemm_ex_args& g, const TxParams& p, cudaStream_t st) {
-  using Cfg = TxCfg<BN>;
+  using Cfg = TxCfg<BN, CG>;
   CUtensorMap tmA, tmB;
   // stored matrices: K-major operand = [M or N rows, K cols]; MN-major operand = [K rows, M or N cols]
   if (A_MN) LCASR_TRY(make_tmap_4d(&tmA, g.A, (uint64_t)g.K, (uint64_t)g.M, g.lda, g.nb1, g.sa1, g.nb2, g.sa2, TX_BK, 64));
   else LCASR_TRY(make_tmap_4d(&tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, g.lda, g.nb1, g.sa1, g.nb2, g.sa2, TX_BM, TX_BK));
   if (B_MN) LCASR_TRY(make_tmap_4d(&tmB, g.B, (uint64_t)g.K, (uint64_t)g.N, g.ldb, g.nb1, g.sb1, g.nb2, g.sb2, TX_BK, 64));
-  else LCASR_TRY(make_tmap_4d(&tmB, g.B, (uint64_t)g.N, (uint64_t)g.K, g.ldb, g.nb1, g.sb1, g.nb2, g.sb2, BN, TX_BK));
+  else LCASR_TRY(make_tmap_4d(&tmB, g.B, (uint64_t)g.N, (uint64_t)g.K, g.ldb, g.nb1, g.sb1, g.nb2, g.sb2, BN / CG, TX_BK));
   CUtensorMap tmC = tmA;  // placeholder for fp32 outputs (never dereferenced)
   if (sizeof(TOut) == 2)
     LCASR_TRY(make_tmap_4d(&tmC, g.out, (uint64_t)g.M, (uint64_t)g.N, g.ldo, g.nb1, g.so1, g.nb2, g.so2, 32, 64));
   static bool attr_set = false;
   if (!attr_set) {
-    LCASR_CUDA(cudaFuncSetAttribute(gemm_tcx_kernel<BN, A_MN, B_MN, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LCASR_CUDA(cudaFuncSetAttribute(gemm_tcx_kernel<BN, A_MN, B_MN, TOut, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int64_t tiles = ceil_div(g.M, TX_BM) * ceil_div(g.N, BN) * p.ksplit * g.nb1 * g.nb2;
-  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  gemm_tcx_kernel<BN, A_MN, B_MN, TOut><<<grid, TX_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmC, p, (TOut*)g.out);
+  const int64_t tiles = ceil_div(g.M, CG * TX_BM) * ceil_div(g.N, BN) * p.ksplit * g.nb1 * g.nb2;
+  const int64_t units = kNumSMs / CG;
+  const int grid = (int)(tiles < units ? tiles : units) * CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TX_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CG == 2 ? 1 : 0;
+  LCASR_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcx_kernel<BN, A_MN, B_MN, TOut, CG>, tmA, tmB, tmC, p, (TOut*)g.out));
   LCASR_LAUNCH_CHECK();
   return 0;
 }
 
-template <int BN, typename TOut>
+template <int BN, typename TOut, int CG>
 static int dispatch_major(const lcasr_gemm_ex_args& g, const TxParams& p, cudaStream_t st) {
-  if (g.a_mn) return g.b_mn ? launch_tcx<BN, 1, 1, TOut>(g, p, st) : launch_tcx<BN, 1, 0, TOut>(g, p, st);
-  return g.b_mn ? launch_tcx<BN, 0, 1, TOut>(g, p, st) : launch_tcx<BN, 0, 0, TOut>(g, p, st);
+  if (g.a_mn) return g.b_mn ? launch_tcx<BN, 1, 1, TOut, CG>(g, p, st) : launch_tcx<BN, 1, 0, TOut, CG>(g, p, st);
+  return g.b_mn ? launch_tcx<BN, 0, 1, TOut, CG>(g, p, st) : launch_tcx<BN, 0, 0, TOut, CG>(g, p, st);
 }
 
 }  // namespace lcasr
@@ -643,18 +684,25 @@ extern "C" int lcasr_gemm_ex(const lcasr_gemm_ex_args* gp, void* stream) {
   const int num_k = (int)ceil_div(g.K, TX_BK);
   const bool wide = (g.N % 256 == 0) || g.N > 512;
   const int BN = wide ? 256 : 128;
+  // CTA pairs (256-row tiles) when the un-split problem has at least one 256-row tile per pair-slot worth of work;
+  // LCASR_GEMM_CG=1|2 forces a choice (A/B runs, tests)
+  static const int force_cg = getenv("LCASR_GEMM_CG") ? atoi(getenv("LCASR_GEMM_CG")) : 0;
+  const int64_t tiles2 = ceil_div(g.M, 2 * TX_BM) * ceil_div(g.N, BN) * g.nb1 * g.nb2;
+  const bool pair = force_cg ? force_cg == 2 : (g.M >= 2 * TX_BM && tiles2 * num_k >= (int64_t)(kNumSMs / 2) * 8);
+  const int CGr = pair ? 2 : 1;
   int ksplit = g.ksplit;
   if (ksplit <= 0) {  // auto (fp32 accumulating outputs: weight gradients have K = all tokens and few output tiles)
     ksplit = 1;
     if (g.out_dtype == LCASR_F32) {
-      // pick the split whose tile count fills whole waves of the 148 persistent CTAs: efficiency = waves / ceil(waves);
-      // a larger split must be 5 % better than a smaller one (fewer atomic passes over the output).  e.g. 72 tiles:
-      // k = 4 -> 288 tiles = 1.95 waves (0.97) instead of k = 5 -> 2.43 waves -> 3 rounds (0.81).
-      const int64_t tiles = ceil_div(g.M, TX_BM) * ceil_div(g.N, BN) * g.nb1 * g.nb2;
+      // pick the split whose tile count fills whole waves of the persistent CTAs (CTA pairs): efficiency =
+      // waves / ceil(waves); a larger split must be 5 % better than a smaller one (fewer atomic passes over the output).
+      // e.g. 72 tiles on 148 CTAs: k = 2 -> 144 tiles = 0.97 wave instead of k = 5 -> 2.43 waves -> 3 rounds (0.81).
+      const int64_t tiles = ceil_div(g.M, CGr * TX_BM) * ceil_div(g.N, BN) * g.nb1 * g.nb2;
+      const int64_t units = kNumSMs / CGr;
       double best = 0.0;
       for (int k = 1; k <= 128 && k * 4 <= num_k; ++k) {
-        const double waves = (double)(tiles * k) / kNumSMs;
-        const double eff = waves / (double)ceil_div(tiles * k, kNumSMs);
+        const double waves = (double)(tiles * k) / units;
+        const double eff = waves / (double)ceil_div(tiles * k, units);
         if (eff > best * 1.05) { best = eff; ksplit = k; }
       }
     }
@@ -670,9 +718,14 @@ extern "C" int lcasr_gemm_ex(const lcasr_gemm_ex_args* gp, void* stream) {
   p.rowvec = g.rowvec; p.sr1 = g.sr1; p.sr2 = g.sr2;
   p.alpha = g.alpha; p.epi = g.epi;
   cudaStream_t st = (cudaStream_t)stream;
+  if (pair) {
+    if (g.out_dtype == LCASR_BF16)
+      return wide ? dispatch_major<256, bf16, 2>(g, p, st) : dispatch_major<128, bf16, 2>(g, p, st);
+    return wide ? dispatch_major<256, float, 2>(g, p, st) : dispatch_major<128, float, 2>(g, p, st);
+  }
   if (g.out_dtype == LCASR_BF16)
-    return wide ? dispatch_major<256, bf16>(g, p, st) : dispatch_major<128, bf16>(g, p, st);
-  return wide ? dispatch_major<256, float>(g, p, st) : dispatch_major<128, float>(g, p, st);
+    return wide ? dispatch_major<256, bf16, 1>(g, p, st) : dispatch_major<128, bf16, 1>(g, p, st);
+  return wide ? dispatch_major<256, float, 1>(g, p, st) : dispatch_major<128, float, 1>(g, p, st);
 }
 
 // P and dS of the attention backward in one pass (see attn_bwd_pds_kernel).  q, k, v, dO: bf16 [nb, N, H, Dh];
