@@ -180,6 +180,18 @@ int64_t lcasr_melspec_frames(int64_t n_samples);
 int lcasr_melspec(const float* wave, int B, int64_t n_samples, const float* cos_tab, const float* sin_tab,
                   const float* fb, int n_mels, float* out, double* sums, int normalise, void* stream);
 
+/* SpecAugment (lcasr/utils/augmentation.py:61-104; exp/train.py:227) in one pass over spec [B, F, T] (fp32).
+ * lcasr_specaug_mean leaves {sum, count} of the un-padded region t < lengths[b] (lengths NULL: everything) in acc[2]
+ * (fp64, device) — the reference's fill value when zero_masking is off.  lcasr_specaug_apply rebuilds every mask
+ * interval from its two uniform draws as torchaudio's mask_along_axis(_iid) does (value = u1*param; start =
+ * trunc(u2*(size - value)); end = start + trunc(value)) and writes out = fill where any mask covers (b, f, t), spec
+ * elsewhere.  u_time [n_time, 2, draws_per_mask], u_freq [n_freq, 2, draws_per_mask]: draws_per_mask = B (iid masks) or
+ * 1 (one interval shared by the batch); *_param already limited by max_p; mean_acc NULL = zero masking. */
+int lcasr_specaug_mean(const float* spec, int B, int F, int64_t T, const int32_t* lengths, double* acc, void* stream);
+int lcasr_specaug_apply(const float* spec, int B, int F, int64_t T, int n_time, int time_param, const float* u_time,
+                        int n_freq, int freq_param, const float* u_freq, int draws_per_mask,
+                        const double* mean_acc, float* out, void* stream);
+
 /* Long-form moving-window merge (lcasr/eval/utils.py:45-111 fetch_logits): window k occupies rows
  * [win_row0[k], win_row0[k] + win_len[k]) of logp [*, V] (fp32 log-probs) and covers merged frames
  * [win_pos[k], win_pos[k] + win_len[k]); windows sorted by win_pos, max_len = max win_len.  For every merged frame:
@@ -187,6 +199,13 @@ int lcasr_melspec(const float* wave, int B, int64_t n_samples, const float* cos_
 int lcasr_window_merge(const float* logp, int V, int K, const int64_t* win_row0, const int32_t* win_len,
                        const int32_t* win_pos, int max_len, int64_t n_total, float* out, int32_t* argmax,
                        void* stream);
+
+/* Buffered long-form mode (lcasr/eval/buffered_transcription.py:74-90): same arguments, but the windows' row ranges
+ * (here: the central chunk of every buffer) tile the merged frames without overlap and the log-probabilities are
+ * copied unchanged (bit-exact) together with the per-frame argmax. */
+int lcasr_window_concat(const float* logp, int V, int K, const int64_t* win_row0, const int32_t* win_len,
+                        const int32_t* win_pos, int max_len, int64_t n_total, float* out, int32_t* argmax,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Training step (cfg 5): the operators behind loss.backward() of exp/train.py:249-262.  The

@@ -5,7 +5,7 @@ robflynnyh/long-context-asr: ``SCConformerXL`` (lcasr/models/sconformer_xl.py), 
 Importing this package loads ``liblcasr_b200.so`` (hand-written CUDA behind a C ABI, see
 include/lcasr_b200.h) and fails loudly if it has not been built.  There is no CPU fallback.
 """
-from . import _lib, ops, seqpar, train_ops, training, longform, optim, frontend
+from . import _lib, ops, seqpar, train_ops, training, longform, optim, frontend, augmentation
 from .model import SCConformerXL, ConformerLayer, RMSNorm, BatchRenorm1d
 from .decoding import GreedyCTCDecoder
 from .losses import CTCLoss

@@ -96,6 +96,9 @@ _SIGNATURES = {
     "lcasr_madgrad_step": [vp, vp, vp, i32, vp, f32, f32, f32, f32, f32, f32, i32, vp],
     "lcasr_melspec": [vp, i32, i64, vp, vp, vp, i32, vp, vp, i32, vp],
     "lcasr_window_merge": [vp, i32, i32, vp, vp, vp, i32, i64, vp, vp, vp],
+    "lcasr_window_concat": [vp, i32, i32, vp, vp, vp, i32, i64, vp, vp, vp],
+    "lcasr_specaug_mean": [vp, i32, i32, i64, vp, vp, vp],
+    "lcasr_specaug_apply": [vp, i32, i32, i64, i32, i32, vp, i32, i32, vp, i32, vp, vp, vp],
     "lcasr_ctc_loss_fwd_ab": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp, vp],
     "lcasr_ctc_loss_grad": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp],
     "lcasr_gemm_ex": [C.POINTER(LcasrGemmExArgs), vp],

@@ -12,6 +12,9 @@ namespace lcasr {
 // One CTA per merged output frame p.  Windows are sorted by start position (non-decreasing); the covering set
 // {k : pos_k <= p < pos_k + len_k} is found by a binary search for the last pos_k <= p and a walk to the left.
 // The sum runs over k ascending — the order in which the reference accumulates its windows.
+// MEAN=false is the buffered mode (lcasr/eval/buffered_transcription.py:74-90): every merged frame is covered by exactly
+// one window (its central chunk) and the log-probabilities are copied bit for bit.
+template <bool MEAN>
 __global__ void __launch_bounds__(256) window_merge_kernel(const float* __restrict__ logp, int V, int K,
                                                            const int64_t* __restrict__ win_row0, const int32_t* __restrict__ win_len,
                                                            const int32_t* __restrict__ win_pos, int max_len,
@@ -35,12 +38,20 @@ __global__ void __launch_bounds__(256) window_merge_kernel(const float* __restri
       const int64_t r = p - win_pos[k];
       if (r < 0 || r >= win_len[k]) continue;
       const float4 v = *reinterpret_cast<const float4*>(logp + (win_row0[k] + r) * V + c0);
-      acc.x += expf(v.x); acc.y += expf(v.y); acc.z += expf(v.z); acc.w += expf(v.w);
+      if constexpr (MEAN) {
+        acc.x += expf(v.x); acc.y += expf(v.y); acc.z += expf(v.z); acc.w += expf(v.w);
+      } else {
+        acc = v;
+      }
       ++cnt;
     }
     const float inv = cnt > 0 ? (float)cnt : 1.0f;
     float4 o;
-    o.x = logf(acc.x / inv); o.y = logf(acc.y / inv); o.z = logf(acc.z / inv); o.w = logf(acc.w / inv);
+    if constexpr (MEAN) {
+      o.x = logf(acc.x / inv); o.y = logf(acc.y / inv); o.z = logf(acc.z / inv); o.w = logf(acc.w / inv);
+    } else {
+      o = acc;
+    }
     if (out) *reinterpret_cast<float4*>(out + p * V + c0) = o;
     const float vals[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
@@ -73,8 +84,20 @@ extern "C" int lcasr_window_merge(const float* logp, int V, int K, const int64_t
   LCASR_CHECK_ARG(logp && win_row0 && win_len && win_pos && (out || argmax), "window_merge: NULL argument");
   LCASR_CHECK_ARG(V > 0 && V % 4 == 0 && K > 0 && max_len > 0 && n_total > 0 && n_total < ((int64_t)1 << 31),
                   "window_merge: bad shape (V %% 4 == 0)");
-  window_merge_kernel<<<(unsigned)n_total, 256, 0, (cudaStream_t)stream>>>(logp, V, K, win_row0, win_len, win_pos, max_len, out,
-                                                                          argmax);
+  window_merge_kernel<true><<<(unsigned)n_total, 256, 0, (cudaStream_t)stream>>>(logp, V, K, win_row0, win_len, win_pos, max_len,
+                                                                                out, argmax);
+  LCASR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lcasr_window_concat(const float* logp, int V, int K, const int64_t* win_row0, const int32_t* win_len,
+                                   const int32_t* win_pos, int max_len, int64_t n_total, float* out, int32_t* argmax,
+                                   void* stream) {
+  LCASR_CHECK_ARG(logp && win_row0 && win_len && win_pos && (out || argmax), "window_concat: NULL argument");
+  LCASR_CHECK_ARG(V > 0 && V % 4 == 0 && K > 0 && max_len > 0 && n_total > 0 && n_total < ((int64_t)1 << 31),
+                  "window_concat: bad shape (V %% 4 == 0)");
+  window_merge_kernel<false><<<(unsigned)n_total, 256, 0, (cudaStream_t)stream>>>(logp, V, K, win_row0, win_len, win_pos, max_len,
+                                                                                 out, argmax);
   LCASR_LAUNCH_CHECK();
   return 0;
 }

@@ -92,6 +92,92 @@ def _merged(model, spec: torch.Tensor, seq_len: int, overlap: int, want_logits: 
     return out, am
 
 
+def plan_buffers(spec_n: int, seq_len: int, overlap: int) -> Tuple[List[Tuple[int, int, int, int]], int, int]:
+    """(buffer_start, buffer_end, chunk_start, chunk_end) of every step of the reference's buffered mode
+    (buffered_transcription.py:42-72): chunks of seq_len - overlap frames, each inside a seq_len-frame buffer reaching
+    overlap/2 frames to both sides and shifted inwards at the edges; plus the effective seq_len / overlap."""
+    if seq_len > spec_n:
+        seq_len, overlap = spec_n, 0
+    chunk = seq_len - overlap
+    assert chunk > 0, "overlap must be smaller than seq_len"
+    steps, c0, c1 = [], 0, chunk
+    while True:
+        s0, s1 = c0 - overlap // 2, c1 + overlap // 2
+        if s0 < 0:
+            s0, s1 = 0, seq_len
+        elif s1 > spec_n:
+            s0, s1 = spec_n - seq_len, spec_n
+        steps.append((s0, s1, c0, c1))
+        c0, c1 = c0 + chunk, min(c1 + chunk, spec_n)
+        if c0 >= spec_n:
+            return steps, seq_len, overlap
+
+
+@torch.no_grad()
+def _buffered(model, spec: torch.Tensor, seq_len: int, overlap: int, want_logits: bool, max_batch: int):
+    if spec.dim() == 2:
+        spec = spec.unsqueeze(0)
+    assert spec.dim() == 3 and spec.shape[0] == 1, "fetch_logits takes one recording [1, feat, T]"
+    dev = spec.device if spec.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    spec = spec.to(dev, torch.float32)
+    spec_n = spec.shape[-1]
+    steps, seq_len, overlap = plan_buffers(spec_n, seq_len, overlap)
+    ds = model.subsampling.subsampling_factor
+    assert overlap / ds == overlap // ds, "Overlap must be a multiple of the downsampling factor"
+    V1 = model.decoder.num_classes
+    n_rows = ops.out_length(seq_len)  # every buffer is seq_len frames long
+    ratio = seq_len / n_rows
+    was_training = model.training
+    model.eval()
+    blocks = []
+    starts = torch.tensor([s[0] for s in steps], device=dev)
+    for b0 in range(0, len(steps), max_batch):
+        idx = starts[b0:b0 + max_batch, None] + torch.arange(seq_len, device=dev)[None, :]
+        batch = spec[0][:, idx].permute(1, 0, 2).contiguous()  # [k, feat, seq_len]
+        blocks.append(model(batch)["final_posteriors"].reshape(-1, V1))
+    model.train(was_training)
+    logp = blocks[0] if len(blocks) == 1 else torch.cat(blocks, 0)
+    row0, wlen, wpos, position = [], [], [], 0
+    for k, (s0, s1, c0, c1) in enumerate(steps):  # rows of the central chunk (buffered_transcription.py:84-90)
+        r0, r1 = int((c0 - s0) / ratio), int((c1 - s0) / ratio)
+        row0.append(k * n_rows + r0)
+        wlen.append(r1 - r0)
+        wpos.append(position)
+        position += r1 - r0
+    keep = [k for k in range(len(steps)) if wlen[k] > 0]
+    assert keep, "recording too short for one output frame"
+    row0_t = torch.tensor([row0[k] for k in keep], dtype=torch.int64, device=dev)
+    wlen_t = torch.tensor([wlen[k] for k in keep], dtype=torch.int32, device=dev)
+    wpos_t = torch.tensor([wpos[k] for k in keep], dtype=torch.int32, device=dev)
+    out = torch.empty(position, V1, dtype=torch.float32, device=dev) if want_logits else None
+    am = torch.empty(position, dtype=torch.int32, device=dev)
+    L.call("lcasr_window_concat", L.ptr(logp), V1, len(keep), L.ptr(row0_t), L.ptr(wlen_t), L.ptr(wpos_t), max(wlen), position,
+           L.ptr(out), L.ptr(am), L.current_stream())
+    return out, am
+
+
+def fetch_logits_buffered(args, model, spec: torch.Tensor, seq_len: int, overlap: int, tokenizer=None, use_tqdm: bool = True,
+                          max_batch: int = 16):
+    """Drop-in for ``lcasr/eval/buffered_transcription.py:11-97`` (``fetch_logits`` of the buffered mode): same arguments
+    and result (numpy float32 [N, V+1]: the central-chunk log-probabilities of successive buffers, concatenated).  All
+    buffers run through the encoder in batches of `max_batch`; one kernel gathers the kept rows and their argmax."""
+    if seq_len == -1:
+        seq_len = args.config["audio_chunking"]["size"]
+    if overlap == -1 and seq_len <= spec.shape[-1]:
+        overlap = args.config["audio_chunking"]["overlap"]
+    out, _ = _buffered(model, spec, seq_len, overlap, True, max_batch)
+    return out.cpu().numpy()
+
+
+def transcribe_buffered(model, spec: torch.Tensor, seq_len: int, overlap: int, blank_id: Optional[int] = None,
+                        max_batch: int = 16) -> List[int]:
+    """buffered fetch_logits + GreedyCTCDecoder with only token ids leaving the GPU."""
+    _, am = _buffered(model, spec, seq_len, overlap, False, max_batch)
+    blank = model.decoder.num_classes - 1 if blank_id is None else blank_id
+    toks, n = ops.greedy_collapse(am.view(1, -1), blank)
+    return toks[0, : int(n[0])].tolist()
+
+
 def fetch_logits(args, model, spec: torch.Tensor, seq_len: int, overlap: int, tokenizer=None, use_tqdm: bool = True,
                  max_batch: int = 16):
     """Same arguments and result as the reference (numpy float32 [N, V+1] log-probabilities of the merged windows);

@@ -623,3 +623,100 @@ def to_spectogram(waveform: np.ndarray, global_normalisation: bool = True, n_mel
     if global_normalisation:
         spec = (spec - spec.mean(-1, keepdims=True)) / spec.std(-1, ddof=1, keepdims=True)
     return spec.astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------------
+# buffered long-form inference (lcasr/eval/buffered_transcription.py:11-97, fetch_logits)
+# --------------------------------------------------------------------------------------------
+
+def buffered_positions(spec_n: int, seq_len: int, overlap: int) -> Tuple[List[Tuple[int, int, int, int]], int, int]:
+    """(buffer_start, buffer_end, chunk_start, chunk_end) per step, as buffered_transcription.py:42-72 plans them:
+    consecutive chunks of seq_len - overlap frames, each transcribed inside a buffer of seq_len frames that extends
+    overlap/2 frames to both sides (shifted inwards at the recording's edges)."""
+    if seq_len > spec_n:
+        seq_len, overlap = spec_n, 0
+    chunk_size = seq_len - overlap
+    assert chunk_size > 0
+    c0, c1, out = 0, chunk_size, []
+    while True:
+        s0, s1 = c0 - overlap // 2, c1 + overlap // 2
+        if s0 < 0:
+            s0, s1 = 0, seq_len
+        elif s1 > spec_n:
+            s1 = spec_n
+            s0 = s1 - seq_len
+        out.append((s0, s1, c0, c1))
+        c0 += chunk_size
+        c1 += chunk_size
+        if c1 >= spec_n:
+            c1 = spec_n
+        if c0 >= spec_n:
+            break
+    return out, seq_len, overlap
+
+
+def fetch_logits_buffered(sd: Dict[str, Tensor], cfg: dict, spec: Tensor, seq_len: int, overlap: int) -> np.ndarray:
+    """Restatement of buffered_transcription.py:74-97: every buffer goes through the encoder on its own; only the rows
+    of its central chunk (frame bounds divided by the buffer's frames-per-row ratio, truncated) are kept, and the kept
+    rows of successive buffers are concatenated.  spec [1, feat, T] -> float32 [N, V+1] log-probs."""
+    spec_n = spec.shape[-1]
+    ds = cfg["subsampling_factor"]
+    positions, seq_len, overlap = buffered_positions(spec_n, seq_len, overlap)
+    assert overlap / ds == overlap // ds, "Overlap must be a multiple of the downsampling factor"
+    rows = []
+    for s0, s1, c0, c1 in positions:
+        with torch.no_grad():
+            lp, _ = encoder_forward(sd, cfg, spec[:, :, s0:s1])
+        ratio = (s1 - s0) / lp.shape[-2]
+        r0, r1 = int((c0 - s0) / ratio), int((c1 - s0) / ratio)
+        rows.append(lp[0, r0:r1])
+    return torch.cat(rows, 0).numpy()
+
+
+# --------------------------------------------------------------------------------------------
+# SpecAugment (lcasr/utils/augmentation.py:61-104 over torchaudio.functional.mask_along_axis(_iid))
+# --------------------------------------------------------------------------------------------
+
+def specaug_params(t: int, f: int, n_time_masks: int, n_freq_masks: int, freq_mask_param: int, time_mask_param: int = -1,
+                   min_p: float = -1, max_p: float = 1.0) -> Tuple[int, int]:
+    """effective (time, freq) mask parameters: the width derived from min_p (augmentation.py:79-82), then torchaudio's
+    limit by max_p (_get_mask_param); a parameter < 1 disables that axis WITHOUT consuming random draws."""
+    tw = time_mask_param
+    if min_p != -1:
+        tw = int(int(t * min_p) / n_time_masks) if n_time_masks != 0 else 0
+    lim = (lambda m, n: m if max_p == 1.0 else min(m, int(n * max_p)))
+    return lim(tw, t), lim(freq_mask_param, f)
+
+
+def spec_augment(spec: np.ndarray, lengths, time_param: int, u_time: np.ndarray, freq_param: int, u_freq: np.ndarray,
+                 zero_masking: bool = False) -> np.ndarray:
+    """spec [B, F, T] fp32; u_time [n_time, 2, B or 1], u_freq [n_freq, 2, B or 1]: the uniform draws in the order the
+    reference consumes them (per mask: the width draw, then the position draw).  A last dimension of 1 is the
+    iid_masks=False case (one interval for the whole batch).  Fill value: 0 or the mean over t < lengths[b]."""
+    spec = np.asarray(spec, dtype=np.float32)
+    B, F, T = spec.shape
+    if zero_masking:
+        fill = np.float32(0.0)
+    elif lengths is None:
+        fill = np.float32(spec.astype(np.float64).mean())
+    else:
+        valid = np.arange(T)[None, :] < np.asarray(lengths)[:, None]
+        fill = np.float32(spec.astype(np.float64)[np.broadcast_to(valid[:, None, :], spec.shape)].mean())
+    out = spec.copy()
+
+    def intervals(u, param, size):
+        u = np.asarray(u, dtype=np.float32)
+        value = u[0] * np.float32(param)
+        min_value = u[1] * (np.float32(size) - value)
+        lo = min_value.astype(np.int64)
+        return np.broadcast_to(lo, (B,)), np.broadcast_to(lo + value.astype(np.int64), (B,))
+
+    for u in (u_time if time_param >= 1 else []):
+        lo, hi = intervals(u, time_param, T)
+        m = (np.arange(T)[None, :] >= lo[:, None]) & (np.arange(T)[None, :] < hi[:, None])
+        out[np.broadcast_to(m[:, None, :], out.shape)] = fill
+    for u in (u_freq if freq_param >= 1 else []):
+        lo, hi = intervals(u, freq_param, F)
+        m = (np.arange(F)[None, :] >= lo[:, None]) & (np.arange(F)[None, :] < hi[:, None])
+        out[np.broadcast_to(m[:, :, None], out.shape)] = fill
+    return out

@@ -22,6 +22,10 @@ CFG = dict(n_layers=2, d_model=64, n_heads=2, head_dim=32, subsampling_conv_chan
 CASES = {"longform_overlap875": (1500, 256, 224),     # 87.5 % overlap, ragged tail window
          "longform_overlap50_exact": (1024, 256, 128),  # windows tile the recording exactly
          "longform_single": (300, 512, 64)}             # seq_len > recording: one window, overlap forced to 0
+# buffered mode (lcasr/eval/buffered_transcription.py): name -> (frames, seq_len (buffer), overlap (buffer - chunk))
+BUFFERED_CASES = {"buffered_ragged": (1500, 256, 128),      # last chunk shorter, last buffer shifted inwards
+                  "buffered_exact": (1024, 256, 64),        # chunks of 192 frames: 1024 is not a multiple -> ragged end
+                  "buffered_single": (300, 512, 64)}        # buffer longer than the recording: one step, overlap 0
 
 
 class _Tok:
@@ -53,6 +57,20 @@ def main():
         mine = O.fetch_logits(sd, cfg, spec, seq_len, overlap)
         err = np.abs(mine - ref).max()
         print(f"{name}: frames {frames} seq_len {seq_len} overlap {overlap} -> N={ref.shape[0]}; oracle-vs-reference max-abs {err:.2e}; "
+              f"{len(greedy)} greedy tokens")
+        assert mine.shape == ref.shape and err < 5e-5
+        np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), config=json.dumps(CFG), frames=frames, seq_len=seq_len,
+                            overlap=overlap, weight_seed=12345, peak=2.0, input_seed=4321, logits=ref.astype(np.float32),
+                            greedy=np.array(greedy, dtype=np.int64))
+    from lcasr.eval.buffered_transcription import fetch_logits as fetch_logits_buffered  # the reference's own function
+    for name, (frames, seq_len, overlap) in BUFFERED_CASES.items():
+        spec = O.synth_input(1, frames, cfg["feat_in"], seed=4321)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref = fetch_logits_buffered(None, model, spec, seq_len, overlap, _Tok(V), use_tqdm=False)
+        greedy = GreedyCTCDecoder(tokenizer=None, blank_id=V)(torch.as_tensor(ref))
+        mine = O.fetch_logits_buffered(sd, cfg, spec, seq_len, overlap)
+        err = np.abs(mine - ref).max()
+        print(f"{name}: frames {frames} buffer {seq_len} overlap {overlap} -> N={ref.shape[0]}; oracle-vs-reference max-abs {err:.2e}; "
               f"{len(greedy)} greedy tokens")
         assert mine.shape == ref.shape and err < 5e-5
         np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), config=json.dumps(CFG), frames=frames, seq_len=seq_len,
