@@ -254,6 +254,13 @@ int lcasr_attention_bwd_pds(const void* q, const void* k, const void* v, const v
 int lcasr_attention_train(const void* q, const void* k, const void* v, int B, int64_t N, int H, int Dh,
                           void* out, float* lse, void* stream);
 
+/* Padded training batches (exp/train.py:236-241 passes length=a_lengths): the forward with a key-padding mask, and the
+ * in-place zeroing of the rows of padded tokens (x [B,N,d], rows n >= lengths[b]) that attention.py:511,541 applies to
+ * the attention input / output and that autograd applies to the matching gradients. */
+int lcasr_attention_train_masked(const void* q, const void* k, const void* v, int B, int64_t N, const int32_t* kv_len,
+                                 int H, int Dh, void* out, float* lse, void* stream);
+int lcasr_mask_rows(void* x, int dtype, int B, int64_t N, int d, const int32_t* lengths, void* stream);
+
 /* Training forward of Linear + activation: pre = A.W^T + bias and out = act(pre), both bf16 [M,N] (tcgen05 GEMM
  * with a two-output epilogue; replaces lcasr_gemm + lcasr_act_fwd). */
 int lcasr_gemm_act_pre(const void* A, const void* W, int64_t M, int N, int K, const float* bias, int act,

@@ -96,6 +96,8 @@ _SIGNATURES = {
     "lcasr_madgrad_step": [vp, vp, vp, i32, vp, f32, f32, f32, f32, f32, f32, i32, vp],
     "lcasr_melspec": [vp, i32, i64, vp, vp, vp, i32, vp, vp, i32, vp],
     "lcasr_window_merge": [vp, i32, i32, vp, vp, vp, i32, i64, vp, vp, vp],
+    "lcasr_attention_train_masked": [vp, vp, vp, i32, i64, vp, i32, i32, vp, vp, vp],
+    "lcasr_mask_rows": [vp, i32, i32, i64, i32, vp, vp],
     "lcasr_window_concat": [vp, i32, i32, vp, vp, vp, i32, i64, vp, vp, vp],
     "lcasr_specaug_mean": [vp, i32, i32, i64, vp, vp, vp],
     "lcasr_specaug_apply": [vp, i32, i32, i64, i32, i32, vp, i32, i32, vp, i32, vp, vp, vp],

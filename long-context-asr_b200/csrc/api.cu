@@ -102,6 +102,14 @@ extern "C" int lcasr_attention_train(const void* q, const void* k, const void* v
   return attn_tc_launch(q, k, v, B, N, N, nullptr, H, Dh, 0, 0, out, lse, (cudaStream_t)stream);
 }
 
+// the same for a padded batch: keys at or beyond kv_len[b] are masked (rows of padded queries: see lcasr_attention_masked)
+extern "C" int lcasr_attention_train_masked(const void* q, const void* k, const void* v, int B, int64_t N, const int32_t* kv_len,
+                                            int H, int Dh, void* out, float* lse, void* stream) {
+  LCASR_CHECK_ARG(q && k && v && out && lse, "attention_train_masked: NULL operand");
+  LCASR_CHECK_ARG(B > 0 && N > 0 && H > 0 && Dh > 0, "attention_train_masked: bad shape");
+  return attn_tc_launch(q, k, v, B, N, N, kv_len, H, Dh, 0, 0, out, lse, (cudaStream_t)stream);
+}
+
 // training forward: out = act(pre), pre = A.W^T + bias, both stored as bf16 (the backward needs the pre-activation)
 extern "C" int lcasr_gemm_act_pre(const void* A, const void* W, int64_t M, int N, int K, const float* bias, int act, void* out,
                                   void* pre_out, void* stream) {

@@ -116,9 +116,31 @@ static inline unsigned grid_for(int64_t total, int block) {
   return (unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
+// zero the rows of padded tokens in place: x [B,N,d], rows n >= lengths[b]  (the masked_fill(pad_mask, 0) of
+// attention.py:511,541 and its backward).  One warp per padded row segment; valid rows are not touched.
+__global__ void __launch_bounds__(256) mask_rows_kernel(uint4* __restrict__ x, int64_t M, int64_t N, int vec_per_row,
+                                                        const int32_t* __restrict__ lengths) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  if ((warp % N) < lengths[warp / N]) return;
+  uint4* row = x + warp * vec_per_row;
+  for (int i = lane; i < vec_per_row; i += 32) row[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 }  // namespace lcasr
 
 using namespace lcasr;
+
+extern "C" int lcasr_mask_rows(void* x, int dtype, int B, int64_t N, int d, const int32_t* lengths, void* stream) {
+  LCASR_CHECK_ARG(x && lengths && B > 0 && N > 0 && d > 0, "mask_rows: bad arguments");
+  const size_t row_bytes = (size_t)d * dtype_size(dtype);
+  LCASR_CHECK_ARG(row_bytes % 16 == 0 && (uintptr_t)x % 16 == 0, "mask_rows: rows must be multiples of 16 bytes");
+  const int64_t M = (int64_t)B * N;
+  mask_rows_kernel<<<(unsigned)ceil_div(M * 32, 256), 256, 0, (cudaStream_t)stream>>>((uint4*)x, M, N, (int)(row_bytes / 16), lengths);
+  LCASR_LAUNCH_CHECK();
+  return 0;
+}
 
 static int glu_launch(const void* in, int dtype, int64_t M, int d, void* out, const int32_t* lengths, int64_t N, void* stream) {
   LCASR_CHECK_ARG(in && out && M >= 0 && d > 0 && d % 8 == 0, "glu: bad arguments (d=%d must be a multiple of 8)", d);

@@ -440,14 +440,20 @@ class SCConformerXL(nn.Module):
         if self.layers[0].attend.fn.left_window >= 0 or self.layers[0].attend.fn.right_window >= 0:
             raise NotImplementedError("windowed attention is an evaluation mode (eval/run.py:38-43); training uses full attention")
         B, _, T = audio_signal.shape
-        if length is not None:
-            lens = [int(v) for v in (length.tolist() if torch.is_tensor(length) else length)]
-            if any(v != T for v in lens):
-                raise NotImplementedError("training on padded batches is a 'next' row (SURVEY §8 f4); equal-length chunks only "
-                                          "(what exp/train.py feeds: fixed max_seq_len chunks)")
-        lp = train_forward(self, audio_signal.detach().to(torch.float32).contiguous())
+        tok_lens = None
+        if length is not None:  # padded batch (exp/train.py:236-241): token counts on the host, like the reference's
+            lens = [int(v) for v in (length.tolist() if torch.is_tensor(length) else length)]  # length.max() == length.min()
+            if len(lens) != B or any(v < 1 or v > T for v in lens):
+                raise ValueError(f"length must hold {B} frame counts in [1, {T}], got {lens}")
+            tok_lens = [int(L.lib.lcasr_out_length(v)) for v in lens]
+            if max(tok_lens) != int(L.lib.lcasr_out_length(T)):  # same rule as the evaluation path (shape clash in the reference)
+                raise ValueError("the longest recording must span the padded batch (length.max() == T up to the 8x rounding)")
+        masked = tok_lens if (tok_lens is not None and min(tok_lens) != max(tok_lens)) else None  # sconformer_xl.py:204-205
+        lp = train_forward(self, audio_signal.detach().to(torch.float32).contiguous(), masked)
         N = lp.shape[1]
-        return {"final_posteriors": lp, "length": torch.full((B,), N, dtype=torch.int32, device=audio_signal.device)}
+        out_len = torch.full((B,), N, dtype=torch.int32, device=audio_signal.device) if tok_lens is None else \
+            torch.tensor(tok_lens, dtype=torch.int32, device=audio_signal.device)
+        return {"final_posteriors": lp, "length": out_len}
 
     @torch.no_grad()
     def _forward_eval(self, audio_signal, length=None, cached_kvs=None, cached_kv_lengths=None, return_logits=False):

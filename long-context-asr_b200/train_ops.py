@@ -50,63 +50,96 @@ def wgrad(dy, x, dw, alpha=1.0):
     return gemm_ex(dy, x, dw, No, Ni, M, a_mn=True, b_mn=True, lda=No, ldb=Ni, ldo=Ni, alpha=alpha)
 
 
-def attention_train(q, k, v):
-    """q,k,v bf16 [B,N,H,Dh] -> (out [B,N,H*Dh] bf16, lse2 [B,H,N] fp32 in the log2 domain)."""
+def attention_train(q, k, v, kv_len=None):
+    """q,k,v bf16 [B,N,H,Dh] -> (out [B,N,H*Dh] bf16, lse2 [B,H,N] fp32 in the log2 domain).
+    kv_len int32 [B] (device): keys at or beyond it are masked (padded batch)."""
     _cuda(q, k, v)
     B, N, H, Dh = q.shape
     out = torch.empty(B, N, H * Dh, dtype=BF, device=q.device)
     lse = torch.empty(B, H, N, dtype=torch.float32, device=q.device)
-    L.call("lcasr_attention_train", L.ptr(q), L.ptr(k), L.ptr(v), B, N, H, Dh, L.ptr(out), L.ptr(lse), _s())
+    if kv_len is None:
+        L.call("lcasr_attention_train", L.ptr(q), L.ptr(k), L.ptr(v), B, N, H, Dh, L.ptr(out), L.ptr(lse), _s())
+    else:
+        L.call("lcasr_attention_train_masked", L.ptr(q), L.ptr(k), L.ptr(v), B, N, L.ptr(kv_len), H, Dh, L.ptr(out), L.ptr(lse), _s())
     return out, lse
 
 
-def attention_bwd(q, k, v, o, do, lse, chunk_b: int = 0, fused_pds: bool = True):
+def glu_masked(u, lengths, B: int, N: int):
+    """GLU of u [B*N, 2d] with the rows of padded tokens written as zeros (convolution.py:107-110)"""
+    _cuda(u, lengths)
+    M, d2 = u.shape
+    out = torch.empty(M, d2 // 2, dtype=u.dtype, device=u.device)
+    L.call("lcasr_glu_masked", L.ptr(u), L.dtype_code(u.dtype), B, N, d2 // 2, L.ptr(lengths), L.ptr(out), _s())
+    return out
+
+
+def mask_rows_(x, lengths, B: int, N: int):
+    """in place: zero the rows n >= lengths[b] of x viewed as [B, N, -1] (lengths int32 [B] on the device)"""
+    _cuda(x, lengths)
+    L.call("lcasr_mask_rows", L.ptr(x), L.dtype_code(x.dtype), B, N, x.numel() // (B * N), L.ptr(lengths), _s())
+    return x
+
+
+def attention_bwd(q, k, v, o, do, lse, chunk_b: int = 0, fused_pds: bool = True, lens=None):
     """Backward of softmax(q k^T / sqrt(Dh)) v from the saved output and log-sum-exp.
     q,k,v,o,do bf16 [B,N,H,Dh]; returns dq, dk, dv (same layout).  P and dS are materialised per group of
-    recordings ([b,H,N,N] bf16 each, sized to stay L2-resident) and every product is one batched tcgen05 GEMM."""
+    recordings ([b,H,N,N] bf16 each, sized to stay L2-resident) and every product is one batched tcgen05 GEMM.
+    `lens` (host ints, tokens per recording): padded batch — recording b is differentiated as the n_b x n_b problem of
+    its valid tokens (masked keys have P = 0 and the output rows of padded queries are zeroed by the caller, so their
+    dO is zero: nothing else contributes); gradient rows of padded tokens are zero."""
     _cuda(q, k, v, o, do, lse)
     B, N, H, Dh = q.shape
     d = H * Dh
     dev = q.device
-    dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    ragged = lens is not None and any(int(n) != N for n in lens)
+    alloc = torch.zeros_like if ragged else torch.empty_like
+    dq, dk, dv = alloc(q), alloc(q), alloc(q)
     Dvec = torch.empty(B, H, N, dtype=torch.float32, device=dev)
     L.call("lcasr_rowdot", L.ptr(do), L.ptr(o), B, N, H, Dh, L.ptr(Dvec), _s())
     if chunk_b <= 0:  # P + dS of one chunk ~ 96 MB
         chunk_b = max(1, min(B, (48 << 20) // (H * N * N * 2)))
-    Np = (N + 7) // 8 * 8  # row pitch of the score matrices
-    P = torch.empty(chunk_b, H, N, Np, dtype=BF, device=dev)
+    if ragged:
+        chunk_b = 1
+    Npad = (N + 7) // 8 * 8
+    P = torch.empty(chunk_b * H * N * Npad, dtype=BF, device=dev)
     dS = torch.empty_like(P)
     scale = 1.0 / (Dh ** 0.5)
-    sNN = N * Np
     for b0 in range(0, B, chunk_b):
         nb = min(chunk_b, B - b0)
+        n = int(lens[b0]) if ragged else N   # valid tokens of this chunk's recordings
+        Np = (n + 7) // 8 * 8               # row pitch of the score matrices
+        sNN = n * Np
         qs, ks, vs, dos = q[b0:], k[b0:], v[b0:], do[b0:]
+        lse_c, dvec_c = lse[b0:], Dvec[b0:]
+        r4 = (N, H * N)
+        if n != N:  # the fused kernel derives the row-vector strides from n
+            lse_c, dvec_c = lse[b0, :, :n].contiguous(), Dvec[b0, :, :n].contiguous()
+            r4 = (n, H * n)
         bat = dict(nb=(H, nb))
         x4 = (Dh, N * d)  # (head, recording) strides of a [B,N,H,Dh] tensor
         s4 = (sNN, H * sNN)
-        r4 = (N, H * N)
         if fused_pds:  # P = exp2(scale*log2e * q k^T - lse2) and dS = P o (do v^T - D) * scale in one pass
-            L.call("lcasr_attention_bwd_pds", L.ptr(qs), L.ptr(ks), L.ptr(vs), L.ptr(dos), L.ptr(lse[b0:]), L.ptr(Dvec[b0:]),
-                   nb, N, H, Dh, L.ptr(P), L.ptr(dS), _s())
+            L.call("lcasr_attention_bwd_pds", L.ptr(qs), L.ptr(ks), L.ptr(vs), L.ptr(dos), L.ptr(lse_c), L.ptr(dvec_c),
+                   nb, n, H, Dh, L.ptr(P), L.ptr(dS), _s())
         else:          # the same as two GEMMs with epilogues (kept as the A/B reference of the fused kernel)
-            gemm_ex(qs, ks, P, N, N, Dh, lda=d, ldb=d, ldo=Np, sa=x4, sb=x4, so=s4, rowvec=lse[b0:], sr=r4,
+            gemm_ex(qs, ks, P, n, n, Dh, lda=d, ldb=d, ldo=Np, sa=x4, sb=x4, so=s4, rowvec=lse_c, sr=r4,
                     alpha=scale * 1.4426950408889634, epi=L.EPI_EXP2, **bat)
-            gemm_ex(dos, vs, dS, N, N, Dh, lda=d, ldb=d, ldo=Np, sa=x4, sb=x4, so=s4, aux=P, ldaux=Np, sx=s4,
-                    rowvec=Dvec[b0:], sr=r4, alpha=scale, epi=L.EPI_DS, **bat)
+            gemm_ex(dos, vs, dS, n, n, Dh, lda=d, ldb=d, ldo=Np, sa=x4, sb=x4, so=s4, aux=P, ldaux=Np, sx=s4,
+                    rowvec=dvec_c, sr=r4, alpha=scale, epi=L.EPI_DS, **bat)
         # The three products are independent and each fills only H*ceil(N/128) of the 148 SMs: dk and dv run on side
         # streams next to dq (fork after P/dS are written, join before they are overwritten / the results are used).
         main = torch.cuda.current_stream()
         fork = torch.cuda.Event()
         fork.record(main)
         # dq = dS k       (B operand k stored [keys, Dh] = [K, N]: MN-major)
-        gemm_ex(dS, ks, dq[b0:], N, Dh, N, b_mn=True, lda=Np, ldb=d, ldo=d, sa=s4, sb=x4, so=x4, **bat)
+        gemm_ex(dS, ks, dq[b0:], n, Dh, n, b_mn=True, lda=Np, ldb=d, ldo=d, sa=s4, sb=x4, so=x4, **bat)
         for i, side in enumerate(_side_streams(dev)):
             side.wait_event(fork)
             with torch.cuda.stream(side):
                 if i == 0:  # dk = dS^T q     (A stored [q, keys] = [K, M]: MN-major)
-                    gemm_ex(dS, qs, dk[b0:], N, Dh, N, a_mn=True, b_mn=True, lda=Np, ldb=d, ldo=d, sa=s4, sb=x4, so=x4, **bat)
+                    gemm_ex(dS, qs, dk[b0:], n, Dh, n, a_mn=True, b_mn=True, lda=Np, ldb=d, ldo=d, sa=s4, sb=x4, so=x4, **bat)
                 else:       # dv = P^T do
-                    gemm_ex(P, dos, dv[b0:], N, Dh, N, a_mn=True, b_mn=True, lda=Np, ldb=d, ldo=d, sa=s4, sb=x4, so=x4, **bat)
+                    gemm_ex(P, dos, dv[b0:], n, Dh, n, a_mn=True, b_mn=True, lda=Np, ldb=d, ldo=d, sa=s4, sb=x4, so=x4, **bat)
                 join = torch.cuda.Event()
                 join.record(side)
             main.wait_event(join)

@@ -171,8 +171,11 @@ class TrainEngine:
         bn._nbt_ver = bn.num_batches_tracked._version
 
     # ---- forward -----------------------------------------------------------------------------------------
-    def forward(self, spec: torch.Tensor, save: bool = True):
-        """spec [B,F,T] fp32 -> (log-probs [B,N,V1] fp32, argmax int32 [B,N], ctx for backward or None)"""
+    def forward(self, spec: torch.Tensor, save: bool = True, tok_lens=None):
+        """spec [B,F,T] fp32 -> (log-probs [B,N,V1] fp32, argmax int32 [B,N], ctx for backward or None).
+        tok_lens (host ints, valid tokens per recording, or None): the padded-batch path of sconformer_xl.py:204-215 —
+        key-padding mask and zeroed rows in attention (attention.py:511,541), zeroed GLU output in the conv module
+        (convolution.py:107-110); BatchRenorm statistics still cover every position, as in the reference."""
         m = self.m
         dev = spec.device
         B, Fdim, Tn = spec.shape
@@ -182,6 +185,7 @@ class TrainEngine:
         eps = 1e-8 if kind == "rms_norm" else 1e-5
         P = self.pack(dev)
         S: Dict = {"P": P, "spec": spec, "B": B, "T": Tn}
+        lens_dev = None
         SILU, GELU = L.ACT_SILU, L.ACT_GELU_TANH
 
         def ln(x, pk, f32=False):
@@ -196,6 +200,9 @@ class TrainEngine:
         d2 = ops.subsample_dwconv(a1, P["dw2_w"], P["dw2_b"])                                # [B,N,F3,C]
         N = d2.shape[1]
         M = B * N
+        if tok_lens is not None and any(int(n) != N for n in tok_lens):
+            lens_dev = torch.tensor([int(n) for n in tok_lens], dtype=torch.int32, device=dev)
+        S["tok_lens"], S["lens_dev"] = ([int(n) for n in tok_lens] if lens_dev is not None else None), lens_dev
         a2, p2 = T.gemm_act_pre(d2.view(-1, Cc), P["pw2_w"], P["pw2_b"], SILU)
         x = ops.gemm(a2.view(M, F3 * Cc), P["sub_out_w"], out_dtype=torch.float32)           # [M,d] fp32
         S.update(s1=s1, d1=d1, p1=p1, a1=a1, d2=d2, p2=p2, a2=a2, N=N)
@@ -214,16 +221,20 @@ class TrainEngine:
                     R[ff] = dict(x=x, a=a, hpre=hpre, hact=hact)
                 elif ff == "attn":
                     a = ln(x, q + "attn_norm")
+                    if lens_dev is not None:
+                        T.mask_rows_(a, lens_dev, B, N)
                     qkv = ops.gemm(a, P[q + "qkv_w"])
                     qq, kk, vv = ops.rope_split(qkv, B, N, H, Dh, cos, sin)
-                    o, lse = T.attention_train(qq, kk, vv)
+                    o, lse = T.attention_train(qq, kk, vv, lens_dev)
+                    if lens_dev is not None:
+                        T.mask_rows_(o, lens_dev, B, N)
                     xn = ops.gemm(o.view(M, d), P[q + "out_w"], resid=x, alpha=1.0)
                     R[ff] = dict(x=x, a=a, q=qq, k=kk, v=vv, o=o, lse=lse)
                 else:
                     bn = layer.conv.fn.batch_norm
                     a = ln(x, q + "conv_norm")
                     u = ops.gemm(a, P[q + "pw1_w"], bias=P[q + "pw1_b"])
-                    g = ops.glu(u)
+                    g = ops.glu(u) if lens_dev is None else T.glu_masked(u, lens_dev, B, N)
                     c, sums = T.dwconv1d_fwd(g.view(B, N, d), P[q + "dw_w"], P[q + "dw_b"], stats=True)
                     rmax, dmax = self.brn_clamps(bn)
                     A, Bc, stats = T.brn_train_stats(sums, M, bn.running_mean, bn.running_std, bn.eps, rmax, dmax, bn.momentum,
@@ -325,13 +336,16 @@ class TrainEngine:
                                         G[q + "brn_b"])
                     T.dwconv1d_bwd_weight_(r["g"].view(B, N, d), dc, G[q + "dw_w"], G[q + "dw_b"])
                     dg = T.dwconv1d_bwd_data(dc, P[q + "dw_w"])
+                    if S["lens_dev"] is not None:
+                        T.mask_rows_(dg, S["lens_dev"], B, N)
                     du = T.glu_bwd(r["u"], dg.view(M, d))
                     da = linear_bwd(du, r["a"], q + "pw1_w", q + "pw1_b")
                     _, dy_next = ln_bwd(r["x"], da, q + "conv_norm", dx, accumulate=True, cast_scale=cs)
                 else:
                     dy = dy_next
                     do = linear_bwd(dy, r["o"].view(M, d), q + "out_w")
-                    dq, dk, dv = T.attention_bwd(r["q"], r["k"], r["v"], r["o"].view(B, N, H, Dh), do.view(B, N, H, Dh), r["lse"])
+                    dq, dk, dv = T.attention_bwd(r["q"], r["k"], r["v"], r["o"].view(B, N, H, Dh), do.view(B, N, H, Dh), r["lse"],
+                                                   lens=S["tok_lens"])
                     dqkv = T.rope_bwd_merge(dq, dk, dv, S["cos"], S["sin"])
                     da = linear_bwd(dqkv, r["a"], q + "qkv_w")
                     _, dy_next = ln_bwd(r["x"], da, q + "attn_norm", dx, accumulate=True, cast_scale=cs)
@@ -386,9 +400,9 @@ class _EncoderFn(torch.autograd.Function):
     """log_probs = f(spec; parameters): forward / backward are TrainEngine.forward / backward."""
 
     @staticmethod
-    def forward(ctx, engine: TrainEngine, spec: torch.Tensor, *params):
+    def forward(ctx, engine: TrainEngine, spec: torch.Tensor, tok_lens, *params):
         with torch.no_grad():
-            lp, am, S = engine.forward(spec, save=True)
+            lp, am, S = engine.forward(spec, save=True, tok_lens=tok_lens)
         ctx.engine, ctx.S = engine, S
         ctx.names = [n for n, _ in engine.m.named_parameters()]
         engine.m.last_argmax = am
@@ -401,16 +415,16 @@ class _EncoderFn(torch.autograd.Function):
             raise RuntimeError("lcasr_b200: backward through the encoder a second time (activations were freed)")
         with torch.no_grad():
             grads = ctx.engine.backward(S, dlp)
-        return (None, None) + tuple(grads.get(n) for n in ctx.names)
+        return (None, None, None) + tuple(grads.get(n) for n in ctx.names)
 
 
-def train_forward(model, audio_signal: torch.Tensor) -> torch.Tensor:
+def train_forward(model, audio_signal: torch.Tensor, tok_lens=None) -> torch.Tensor:
     if getattr(model, "_train_engine", None) is None:
         model._train_engine = TrainEngine(model)
     eng = model._train_engine
     params = [p for _, p in model.named_parameters()]
     if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-        return _EncoderFn.apply(eng, audio_signal, *params)
-    lp, am, _ = eng.forward(audio_signal, save=False)
+        return _EncoderFn.apply(eng, audio_signal, tok_lens, *params)
+    lp, am, _ = eng.forward(audio_signal, save=False, tok_lens=tok_lens)
     model.last_argmax = am
     return lp

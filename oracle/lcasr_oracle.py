@@ -495,14 +495,16 @@ def ctc_grad(log_probs, targets, input_lengths, target_lengths, blank: int) -> n
 # training step (exp/train.py:236-262): forward in train mode, CTC loss (sum), backward
 # --------------------------------------------------------------------------------------------
 
-def training_step(sd: Dict[str, Tensor], cfg: dict, x: Tensor, targets: Tensor, target_lengths: Tensor):
+def training_step(sd: Dict[str, Tensor], cfg: dict, x: Tensor, targets: Tensor, target_lengths: Tensor, lengths=None):
     """loss = CTCLoss(blank=V, reduction='sum')(log_probs.transpose(0,1), targets, length, target_lengths)
     (exp/train.py:104,249) of the train-mode forward, and d loss / d parameter for every floating-point
-    parameter of `sd` (buffers excluded).  Returns (loss float, {name: grad}, {buffer name: new running stat})."""
+    parameter of `sd` (buffers excluded).  `lengths` (frames per recording): the padded-batch path of
+    exp/train.py:236-241 (pad masks in attention and the conv module; BatchRenorm statistics still run over every
+    position).  Returns (loss float, {name: grad}, {buffer name: new running stat}, log-probs)."""
     buffers = ("running_mean", "running_std", "num_batches_tracked", "inv_freq", "rotary_interpolation_factor")
     leaves = {k: (v.detach().clone().float().requires_grad_(True) if not k.endswith(buffers) else v) for k, v in sd.items()}
     new_stats: Dict[str, Tensor] = {}
-    lp, length = encoder_forward(leaves, cfg, x, train=True, new_stats=new_stats)
+    lp, length = encoder_forward(leaves, cfg, x, train=True, new_stats=new_stats, lengths=lengths)
     loss = F.ctc_loss(lp.transpose(0, 1), targets, length.long(), target_lengths, blank=cfg["vocab_size"], reduction="sum")
     loss.backward()
     grads = {k: v.grad for k, v in leaves.items() if isinstance(v, Tensor) and v.requires_grad and v.grad is not None}

@@ -34,10 +34,15 @@ CASES = {
     "train_rms_nosc_bias": (dict(n_layers=1, d_model=64, n_heads=2, head_dim=32, subsampling_conv_channels=32,
                                  vocab_size=127, default_norm="rms_norm", self_conditioning=False, bias_in_ff=True,
                                  use_rotary=False), 3, 200, 9000),
+    # padded batch (exp/train.py:236-241 passes length=a_lengths): pad masks in attention and the conv module
+    "train_ragged_dh32": (dict(n_layers=2, d_model=64, n_heads=2, head_dim=32, subsampling_conv_channels=32,
+                               vocab_size=127), 3, 264, 500, [264, 150, 201]),
+    "train_ragged_dh128": (dict(n_layers=1, d_model=128, n_heads=1, head_dim=128, subsampling_conv_channels=64,
+                                vocab_size=255, decoder_norm=True), 2, 1100, 0, [700, 1100]),
 }
 
 
-def run_case(name, overrides, batch, frames, nbt, SCConformerXL):
+def run_case(name, overrides, batch, frames, nbt, SCConformerXL, lengths=None):
     import zlib
     cfg = O.make_config(**overrides)
     sd = O.synth_state_dict(cfg, seed=12345, peak=1.0)
@@ -50,17 +55,19 @@ def run_case(name, overrides, batch, frames, nbt, SCConformerXL):
     model.train()
     x = O.synth_input(batch, frames, cfg["feat_in"], seed=1234)
     V = cfg["vocab_size"]
-    out = model(audio_signal=x, length=None)
+    out = model(audio_signal=x, length=None if lengths is None else torch.tensor(lengths))
     lp, length = out["final_posteriors"], out["length"]
     N = lp.shape[1]
     tgt, tgt_len = O.synth_targets(batch, N, vocab=V, frac=0.3, seed=99)
+    if lengths is not None:  # transcripts no longer than 30 % of each recording's own token count
+        tgt_len = torch.minimum(tgt_len, (0.3 * length.float()).long())
     loss = torch.nn.CTCLoss(blank=V, reduction="sum")(lp.transpose(0, 1), tgt, length, tgt_len).sum()
     loss.backward()
     ref_grads = {k: p.grad.detach() for k, p in model.named_parameters() if p.grad is not None}  # unused parameters
     unused = [k for k, p in model.named_parameters() if p.grad is None]  # (e.g. decoder.reprojection without self-conditioning)
     ref_stats = {k: v.detach().clone() for k, v in model.state_dict().items() if k.endswith(("running_mean", "running_std"))}
 
-    o_loss, o_grads, o_stats, o_lp = O.training_step(sd, cfg, x, tgt, tgt_len)
+    o_loss, o_grads, o_stats, o_lp = O.training_step(sd, cfg, x, tgt, tgt_len, lengths=lengths)
     worst = 0.0
     floor = 1e-4 * max(g.norm().item() for g in ref_grads.values())  # mathematically-zero gradients (a bias in front of
     for k, g in ref_grads.items():                                  # a batch norm) are rounding noise on both sides
@@ -72,7 +79,8 @@ def run_case(name, overrides, batch, frames, nbt, SCConformerXL):
     assert abs(o_loss - loss.item()) <= 1e-5 * abs(loss.item()) and worst < 2e-4 and stat_err < 1e-5
 
     store = dict(config=json.dumps(overrides), batch=batch, frames=frames, nbt=nbt, weight_seed=12345, input_seed=1234,
-                 target_seed=99, loss=np.float64(loss.item()), log_probs=lp.detach().numpy().astype(np.float32),
+                 target_seed=99, loss=np.float64(loss.item()), frame_lengths=np.array(lengths if lengths else [], dtype=np.int64),
+                 target_lengths=tgt_len.numpy().astype(np.int64), log_probs=lp.detach().numpy().astype(np.float32),
                  length=length.numpy().astype(np.int32), names=np.array(list(ref_grads.keys())), unused=np.array(unused + [""]))
     for i, (k, g) in enumerate(ref_grads.items()):
         idx = torch.randint(0, g.numel(), (min(256, g.numel()),), generator=torch.Generator().manual_seed(zlib.crc32(k.encode()) & 0x7FFFFFFF))
@@ -89,10 +97,10 @@ def main():
     SCConformerXL, _ = load_reference()
     torch.set_num_threads(8)
     only = sys.argv[1:]
-    for name, (ov, b, t, nbt) in CASES.items():
+    for name, (ov, b, t, nbt, *rest) in CASES.items():
         if only and name not in only:
             continue
-        run_case(name, ov, b, t, nbt, SCConformerXL)
+        run_case(name, ov, b, t, nbt, SCConformerXL, *rest)
 
 
 if __name__ == "__main__":

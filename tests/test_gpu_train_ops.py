@@ -104,6 +104,33 @@ def test_attention_train_and_backward(cuda_device, B, N, H, Dh):
         assert torch.equal(dq, dq2) and torch.equal(dk, dk2) and torch.equal(dv, dv2)
 
 
+@pytest.mark.parametrize("B,N,H,Dh,lens", [(3, 200, 2, 32, [200, 77, 136]), (2, 300, 1, 128, [129, 300]), (4, 2048, 6, 128, [2048, 1000, 2047, 5])])
+def test_attention_train_padded_batch(cuda_device, B, N, H, Dh, lens):
+    """key-padding mask + zeroed rows of padded tokens (attention.py:511,541 in a padded batch) against SDPA with the same
+    masks; the backward treats every recording as the n_b x n_b problem of its valid tokens"""
+    from lcasr_b200 import train_ops as T
+    lens_dev = torch.tensor(lens, dtype=torch.int32, device=cuda_device)
+    pad = (torch.arange(N)[None, :] >= torch.tensor(lens)[:, None]).to(cuda_device)        # [B,N]
+    q, k, v = (_rand(B, N, H, Dh, seed=s_).to(BF).to(cuda_device) for s_ in (21, 22, 23))
+    for t in (q, k, v):
+        T.mask_rows_(t, lens_dev, B, N)                                                    # qkv of zeroed rows (no bias) is zero
+        assert float(t[pad].abs().max()) == 0 and float(t[~pad].abs().min()) >= 0
+    do = _rand(B, N, H * Dh, seed=24).to(BF).to(cuda_device)
+    out, lse2 = T.attention_train(q, k, v, lens_dev)
+    T.mask_rows_(out, lens_dev, B, N)
+    qf, kf, vf = (t.float().transpose(1, 2).requires_grad_(True) for t in (q, k, v))
+    bias = torch.zeros(B, 1, 1, N, device=cuda_device).masked_fill(pad[:, None, None, :], float("-inf"))
+    ref = F.scaled_dot_product_attention(qf, kf, vf, attn_mask=bias).transpose(1, 2)      # [B,N,H,Dh]
+    ref = ref.masked_fill(pad[:, :, None, None], 0.0)
+    _close(out.view(B, N, H, Dh), ref, 2 ** -6, "masked attention_train out")
+    ref.backward(do.float().view(B, N, H, Dh))
+    for fused in (True, False):
+        dq, dk, dv = T.attention_bwd(q, k, v, out.view(B, N, H, Dh), do.view(B, N, H, Dh), lse2, lens=lens, fused_pds=fused)
+        for name, got, r in (("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
+            _close(got, r.transpose(1, 2), 3e-2, f"padded attention_bwd {name} fused={fused}")
+            assert float(got[pad].abs().max()) == 0, f"{name}: rows of padded tokens must get no gradient"
+
+
 # ---- memory-bound backward kernels ----------------------------------------------------------------------------
 
 def test_elementwise_backward_kernels(cuda_device):

@@ -18,7 +18,8 @@ from gpu_util import report
 from oracle import lcasr_oracle as O
 
 pytestmark = pytest.mark.gpu
-TRAIN_CASES = ["train_tiny_dh32", "train_tiny_dh128_nbt", "train_rms_nosc_bias"]
+TRAIN_CASES = ["train_tiny_dh32", "train_tiny_dh128_nbt", "train_rms_nosc_bias",
+               "train_ragged_dh32", "train_ragged_dh128"]  # the last two: padded batches (length=a_lengths, exp/train.py:236-241)
 
 
 def _load(name):
@@ -48,15 +49,21 @@ def test_training_step_matches_reference_golden(cuda_device, name):
     g = _load(name)
     model, cfg, sd, x = _setup(g, cuda_device)
     V = cfg["vocab_size"]
-    out = model(audio_signal=x.to(cuda_device), length=None)
+    frame_lengths = g["frame_lengths"].tolist() if "frame_lengths" in g else []
+    length = torch.tensor(frame_lengths, device=cuda_device) if frame_lengths else None
+    out = model(audio_signal=x.to(cuda_device), length=length)
     lp = out["final_posteriors"]
     assert lp.requires_grad and lp.grad_fn is not None
+    assert out["length"].cpu().tolist() == g["length"].tolist()
     ref_lp = torch.from_numpy(g["log_probs"])
     scale = max(1.0, ref_lp.abs().max().item() / 8)
-    err = (lp.detach().cpu() - ref_lp).abs().max().item()
+    valid = torch.arange(lp.shape[1])[None, :] < torch.from_numpy(g["length"]).long()[:, None]  # rows of padded tokens never
+    err = (lp.detach().cpu() - ref_lp)[valid].abs().max().item()                               # reach the loss
     assert err < 2e-2 * scale * 2.5, f"train-mode log-probs off by {err}"
     N = lp.shape[1]
     tgt, tl = O.synth_targets(int(g["batch"]), N, vocab=V, frac=0.3, seed=int(g["target_seed"]))
+    if "target_lengths" in g:
+        tl = torch.from_numpy(g["target_lengths"])
     loss = lcasr_b200.CTCLoss(blank=V, reduction="sum")(lp.transpose(0, 1), tgt, out["length"], tl).sum()
     loss.backward()
     rel_loss = abs(loss.item() - float(g["loss"])) / abs(float(g["loss"]))
