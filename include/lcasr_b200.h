@@ -331,6 +331,13 @@ int lcasr_subsample_dwconv_bwd_weight(const void* in, const void* dout, int B, i
                                       float* dw, float* db, void* stream);
 int lcasr_subsample_conv0_bwd(const float* spec, const float* w, const float* b, const void* ds1, int B, int F,
                               int64_t T, int C, float* dw, float* db, void* stream);
+/* Fused backward of conv0 + SiLU + the first depthwise level (C % 64 == 0): from the spectrogram and
+ * dd1 = dL/d(depthwise-1 output) [B,T2,F2,C] (bf16) accumulate (+=) the gradients of conv0 w [C,9] / b [C] and of the
+ * depthwise w [C,9] / b [C].  The conv0 activation and its gradient are recomputed / consumed on chip: together with
+ * lcasr_subsample_conv0_dw in the forward, the 160x-expanded [B,T/2,40,C] tensor never exists in HBM. */
+int lcasr_subsample_l1_bwd(const float* spec, const float* w0, const float* b0, const float* w1, const void* dd1,
+                           int B, int F, int64_t T, int C, float* dw0, float* db0, float* dw1, float* db1,
+                           void* stream);
 
 /* Training form of the CTC loss (up to 4096 extended states): the alpha and beta recursions are independent, so
  * one launch runs both concurrently (2*B CTAs) into alpha_ws / beta_ws [B,N,2*S_max+1]; the backward is then

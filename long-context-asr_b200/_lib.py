@@ -97,6 +97,7 @@ _SIGNATURES = {
     "lcasr_melspec": [vp, i32, i64, vp, vp, vp, i32, vp, vp, i32, vp],
     "lcasr_window_merge": [vp, i32, i32, vp, vp, vp, i32, i64, vp, vp, vp],
     "lcasr_attention_train_masked": [vp, vp, vp, i32, i64, vp, i32, i32, vp, vp, vp],
+    "lcasr_subsample_l1_bwd": [vp, vp, vp, vp, vp, i32, i32, i64, i32, vp, vp, vp, vp, vp],
     "lcasr_mask_rows": [vp, i32, i32, i64, i32, vp, vp],
     "lcasr_window_concat": [vp, i32, i32, vp, vp, vp, i32, i64, vp, vp, vp],
     "lcasr_specaug_mean": [vp, i32, i32, i64, vp, vp, vp],

@@ -7,6 +7,7 @@
 //                          pre-activation is recomputed from the spectrogram instead of being stored
 #include "common.cuh"
 #include <cstdlib>
+#include <algorithm>
 
 namespace lcasr {
 
@@ -231,6 +232,172 @@ __global__ void __launch_bounds__(256) subsample_conv0_bwd_kernel(const float* _
   }
 }
 
+// ---- fused backward of conv0 + SiLU + first depthwise level -------------------------------------------------------
+// The unfused chain writes the 160x-expanded conv0 activation s1 (1.3 GB in bf16 at cfg 5) in the forward, reads it twice
+// (depthwise forward, depthwise weight gradient), writes its gradient ds1 and reads that back for the conv0 weight gradient:
+// 6.7 GB of HBM traffic for 2.7 % of the step's FLOPs.  Nothing of it is needed: s1 = silu(conv0(spec)) is 9 FMAs and one
+// tanh away from the 80-bin spectrogram, and ds1 is consumed where it is produced.  This kernel reads only the
+// spectrogram (L2-resident patch in shared memory) and dd1 = dL/d(depthwise output) [B,T2,F2,C] and accumulates all four
+// parameter gradients (conv0 w/b, depthwise w/b) in registers:
+//   a warp owns one 2x2 block of s1 positions (rows 2a,2a+1; columns 2e,2e+1), a lane two channels.  Stride 2 makes the
+//   tap pattern depend only on the parity of the position, so the block needs the four output gradients
+//   G[a..a+1][e..e+1] and the 5x5 input patch around it — no divergence, no gathers:
+//     ds1[2a  ][2e  ] = G00 w11                 ds1[2a  ][2e+1] = G00 w12 + G01 w10
+//     ds1[2a+1][2e  ] = G00 w21 + G10 w01       ds1[2a+1][2e+1] = G00 w22 + G01 w20 + G10 w02 + G11 w00
+//   and every (G, tap) pair above also feeds the depthwise weight gradient dw1[tap] += G * s1(position).
+// A CTA (one recording, 64 channels) walks tiles of kL1R s1 rows; one shared-memory reduction and 64*20 atomics per CTA.
+constexpr int kL1R = 16;   // s1 rows per tile (even)
+constexpr int kL1CG = 64;  // channels per CTA (2 per lane)
+
+__global__ void __launch_bounds__(256, 2) subsample_l1_bwd_fused_kernel(
+    const float* __restrict__ spec, const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w1,
+    const bf16* __restrict__ dd1, int F, int64_t T, int C, int64_t T1, int F1, int64_t T2, int F2, int FWp,
+    float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dw1, float* __restrict__ db1) {
+  extern __shared__ float l1sm[];  // input patch [2*kL1R+1][FWp] (col 0 = freq -1, zero-filled up to FWp), then accumulators [64][20]
+  constexpr int INR = 2 * kL1R + 1;
+  float* s_in = l1sm;
+  float* sacc = l1sm + INR * FWp;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * kL1CG + 2 * lane;
+  for (int i = threadIdx.x; i < kL1CG * 20; i += blockDim.x) sacc[i] = 0.f;
+  float wa[2][9], ba[2], wd[2][9];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    ba[c] = b0[c0 + c];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { wa[c][k] = w0[(c0 + c) * 9 + k]; wd[c][k] = w1[(c0 + c) * 9 + k]; }
+  }
+  float g0w[2][9], g0b[2], g1w[2][9], g1b[2];  // gradient partial sums: conv0 w/b, depthwise w/b
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    g0b[c] = 0.f; g1b[c] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { g0w[c][k] = 0.f; g1w[c][k] = 0.f; }
+  }
+  const int EB = (F1 + 1) / 2;                 // column blocks
+  const bf16* ddb = dd1 + (int64_t)b * T2 * F2 * C + c0;
+  const int64_t ntiles = (T1 + kL1R - 1) / kL1R;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * kL1R;            // first s1 row of the tile (even)
+    const int64_t t_in0 = 2 * r0 - 1;          // input frame of patch row 0
+    __syncthreads();                           // the previous tile's patch is no longer read
+    for (int idx = threadIdx.x; idx < INR * FWp; idx += blockDim.x) {
+      const int f = idx / INR - 1, r = idx - (f + 1) * INR;
+      const int64_t t = t_in0 + r;
+      float v = 0.f;
+      if (f >= 0 && f < F && t >= 0 && t < T) v = spec[((int64_t)b * F + f) * T + t];
+      s_in[r * FWp + (f + 1)] = v;
+    }
+    __syncthreads();
+    const int a_base = (int)(r0 / 2);          // first block row == first dd1 row touched (T2 < 2^31 rows)
+    const int nal = (int)min((int64_t)(kL1R / 2), (T1 - r0 + 1) / 2);   // block rows of this tile that exist
+    const int T2i = (int)T2, T1rem = (int)min((int64_t)kL1R, T1 - r0); // s1 rows of this tile that exist
+    int al = 0, e = wid;
+    while (e >= EB) { e -= EB; ++al; }
+    // raw bf16x2 output gradients of a block, always from a clamped (valid) address: loads never branch, the
+    // out-of-range ones are zeroed by a select at the point of use.  The next block's four values are requested
+    // before the current block's ~200 FMAs (the kernel was stalled on exactly these loads: long-scoreboard 2.7).
+    auto ldg4 = [&](int al_, int e_, uint32_t (&g)[4]) {
+      const int a_ = a_base + al_;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int ai = min(a_ + i, T2i - 1), ej = min(e_ + j, F2 - 1);
+          g[i * 2 + j] = __ldg(reinterpret_cast<const uint32_t*>(ddb + ((int64_t)ai * F2 + ej) * C));
+        }
+    };
+    uint32_t gcur[4], gnext[4];
+    ldg4(al, e, gcur);
+#pragma unroll 1
+    for (; al < nal;) {
+      const int a = a_base + al;
+      int al2 = al, e2 = e + 8;
+      while (e2 >= EB) { e2 -= EB; ++al2; }
+      ldg4(al2, e2, gnext);
+      float2 G[2][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const bool ok = (a + i < T2i) && (e + j < F2);
+          const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gcur[i * 2 + j]));
+          G[i][j] = make_float2(ok ? g.x : 0.f, ok ? g.y : 0.f);
+        }
+      // bias gradient of the depthwise level: every output gradient is G00 of exactly one block
+      g1b[0] += G[0][0].x; g1b[1] += G[0][0].y;
+      // 5x5 input patch: rows 4*al .. 4*al+4 of the tile patch, columns 4e .. 4e+4 (col 0 = freq -1; FWp >= 4*EB+1)
+      float in[5][5];
+      const float* ip = s_in + (4 * al) * FWp + 4 * e;
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) in[i][j] = ip[i * FWp + j];
+#pragma unroll
+      for (int pi = 0; pi < 2; ++pi) {
+#pragma unroll
+        for (int pj = 0; pj < 2; ++pj) {
+          const bool live = (2 * al + pi < T1rem) && (2 * e + pj < F1);
+          float acc[2] = {ba[0], ba[1]};
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j) acc[c] = fmaf(wa[c][i * 3 + j], in[2 * pi + i][2 * pj + j], acc[c]);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const float sg = sigmoid_fast(acc[c]);
+            // the forward stored s1 as bf16: the depthwise weight gradient sees the same rounded activation
+            const float y = live ? __bfloat162float(__float2bfloat16_rn(acc[c] * sg)) : 0.f;
+            const float dsilu = sg * (1.0f + acc[c] * (1.0f - sg));
+            float ds = 0.f;
+            // (output offset i2, j2; tap) pairs of this parity class — see the table in the header comment
+#define LCASR_L1_PAIR(i2, j2, tap)                                          \
+  {                                                                         \
+    const float g = c == 0 ? G[i2][j2].x : G[i2][j2].y;                     \
+    ds = fmaf(g, wd[c][tap], ds);                                           \
+    g1w[c][tap] = fmaf(g, y, g1w[c][tap]);                                  \
+  }
+            if (pi == 0 && pj == 0) { LCASR_L1_PAIR(0, 0, 4) }
+            if (pi == 0 && pj == 1) { LCASR_L1_PAIR(0, 0, 5) LCASR_L1_PAIR(0, 1, 3) }
+            if (pi == 1 && pj == 0) { LCASR_L1_PAIR(0, 0, 7) LCASR_L1_PAIR(1, 0, 1) }
+            if (pi == 1 && pj == 1) { LCASR_L1_PAIR(0, 0, 8) LCASR_L1_PAIR(0, 1, 6) LCASR_L1_PAIR(1, 0, 2) LCASR_L1_PAIR(1, 1, 0) }
+#undef LCASR_L1_PAIR
+            const float ga = live ? ds * dsilu : 0.f;
+            g0b[c] += ga;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j) g0w[c][i * 3 + j] = fmaf(ga, in[2 * pi + i][2 * pj + j], g0w[c][i * 3 + j]);
+          }
+        }
+      }
+      al = al2; e = e2;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) gcur[i] = gnext[i];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    float* sa = sacc + (2 * lane + c) * 20;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { atomicAdd(sa + k, g0w[c][k]); atomicAdd(sa + 10 + k, g1w[c][k]); }
+    atomicAdd(sa + 9, g0b[c]);
+    atomicAdd(sa + 19, g1b[c]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kL1CG * 20; i += blockDim.x) {
+    const int c = blockIdx.y * kL1CG + i / 20, k = i % 20;
+    const float v = sacc[i];
+    if (k < 9) atomicAdd(dw0 + c * 9 + k, v);
+    else if (k == 9) atomicAdd(db0 + c, v);
+    else if (k < 19) atomicAdd(dw1 + c * 9 + (k - 10), v);
+    else atomicAdd(db1 + c, v);
+  }
+}
+
 }  // namespace lcasr
 
 using namespace lcasr;
@@ -287,6 +454,30 @@ extern "C" int lcasr_subsample_conv0_bwd(const float* spec, const float* w, cons
   if (gx > ceil_div(T1, kC0bTT)) gx = ceil_div(T1, kC0bTT);
   dim3 grid((unsigned)gx, (unsigned)B);
   subsample_conv0_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(spec, w, b, (const bf16*)ds1, F, T, C, T1, F1, dw, db);
+  LCASR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lcasr_subsample_l1_bwd(const float* spec, const float* w0, const float* b0, const float* w1, const void* dd1,
+                                      int B, int F, int64_t T, int C, float* dw0, float* db0, float* dw1, float* db1,
+                                      void* stream) {
+  LCASR_CHECK_ARG(spec && w0 && b0 && w1 && dd1 && dw0 && db0 && dw1 && db1 && B > 0 && F > 0 && T > 0,
+                  "subsample_l1_bwd: bad arguments");
+  LCASR_CHECK_ARG(C % kL1CG == 0, "subsample_l1_bwd: conv_channels=%d must be a multiple of %d (use the unfused kernels)", C, kL1CG);
+  const int64_t T1 = (T - 1) / 2 + 1, T2 = (T1 - 1) / 2 + 1;
+  const int F1 = (F - 1) / 2 + 1, F2 = (F1 - 1) / 2 + 1;
+  const int FWp = std::max(F + 2, 4 * ((F1 + 1) / 2) + 1);  // patch pitch: every 5-wide block read stays inside the row
+  const size_t smem = ((size_t)(2 * kL1R + 1) * FWp + (size_t)kL1CG * 20) * sizeof(float);
+  LCASR_CHECK_ARG(smem <= 48 * 1024, "subsample_l1_bwd: feat_in=%d too large for the staged patch", F);
+  LCASR_CHECK_ARG(T2 < ((int64_t)1 << 30), "subsample_l1_bwd: too many frames");
+  LCASR_CHECK_ARG(B <= 65535, "subsample_l1_bwd: batch too large");
+  const int ncg = C / kL1CG;
+  int64_t gx = ((int64_t)kNumSMs * 2) / ((int64_t)B * ncg);  // one wave of 2 resident CTAs per SM (rounded DOWN: a few extra CTAs
+  if (gx < 1) gx = 1;                                        // would run as a second wave), each walking several tiles
+  if (gx > ceil_div(T1, kL1R)) gx = ceil_div(T1, kL1R);
+  dim3 grid((unsigned)gx, (unsigned)ncg, (unsigned)B);
+  subsample_l1_bwd_fused_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(spec, w0, b0, w1, (const bf16*)dd1, F, T, C, T1, F1, T2, F2,
+                                                                          FWp, dw0, db0, dw1, db1);
   LCASR_LAUNCH_CHECK();
   return 0;
 }

@@ -322,6 +322,15 @@ def subsample_dwconv_bwd_weight_(x, dout, dw, db):
     L.call("lcasr_subsample_dwconv_bwd_weight", L.ptr(x), L.ptr(dout), B, Tin, Fin, C_, L.ptr(dw), L.ptr(db), _s())
 
 
+def subsample_l1_bwd_(spec, w0, b0, w1, dd1, dw0, db0, dw1, db1):
+    """fused backward of conv0 + SiLU + depthwise level 1: parameter gradients (+=) straight from the spectrogram and
+    dd1 [B,T2,F2,C]; the conv0 activation / its gradient are never materialised"""
+    _cuda(spec, w0, b0, w1, dd1, dw0, db0, dw1, db1)
+    B, F, T = spec.shape
+    L.call("lcasr_subsample_l1_bwd", L.ptr(spec), L.ptr(w0), L.ptr(b0), L.ptr(w1), L.ptr(dd1), B, F, T, w0.shape[0],
+           L.ptr(dw0), L.ptr(db0), L.ptr(dw1), L.ptr(db1), _s())
+
+
 def subsample_conv0_bwd_(spec, w, b, ds1, dw, db):
     _cuda(spec, w, b, ds1, dw, db)
     B, F, T = spec.shape

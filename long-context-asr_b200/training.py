@@ -192,9 +192,14 @@ class TrainEngine:
             o32, lo = ops.layernorm(x, P[pk + "_w"], P[pk + "_b"], eps=eps, kind=kind, out_f32=f32, lo_dtype=None if f32 else BF)
             return o32 if f32 else lo
 
-        # subsampling (unfused kernels: the backward needs every level's input)
-        s1 = ops.subsample_conv0(spec, P["conv0_w"], P["conv0_b"], out_dtype=BF)            # [B,T1,F1,C]
-        d1 = ops.subsample_dwconv(s1, P["dw1_w"], P["dw1_b"])                                # [B,T2,F2,C]
+        # subsampling.  Level 1 (conv0 + SiLU + depthwise): the fused kernel keeps the 160x-expanded conv0 activation in
+        # shared memory and the fused backward recomputes it from the spectrogram, so it never exists in HBM.
+        if Cc % 64 == 0:
+            s1 = None
+            d1 = ops.subsample_conv0_dw(spec, P["conv0_w"], P["conv0_b"], P["dw1_w"], P["dw1_b"])   # [B,T2,F2,C]
+        else:
+            s1 = ops.subsample_conv0(spec, P["conv0_w"], P["conv0_b"], out_dtype=BF)        # [B,T1,F1,C]
+            d1 = ops.subsample_dwconv(s1, P["dw1_w"], P["dw1_b"])                            # [B,T2,F2,C]
         a1, p1 = T.gemm_act_pre(d1.view(-1, Cc), P["pw1_w"], P["pw1_b"], SILU)
         a1 = a1.view(d1.shape)
         d2 = ops.subsample_dwconv(a1, P["dw2_w"], P["dw2_b"])                                # [B,N,F3,C]
@@ -361,9 +366,13 @@ class TrainEngine:
         da1 = T.subsample_dwconv_bwd_data(dd2, P["dw2_w"], S["a1"].shape[1], S["a1"].shape[2])
         dp1 = T.act_bwd(S["p1"], da1.view(-1, Cc), SILU)
         dd1 = linear_bwd(dp1, S["d1"].view(-1, Cc), "pw1_w", "pw1_b").view(S["d1"].shape)
-        T.subsample_dwconv_bwd_weight_(S["s1"], dd1, G["dw1_w"], G["dw1_b"])
-        ds1 = T.subsample_dwconv_bwd_data(dd1, P["dw1_w"], S["s1"].shape[1], S["s1"].shape[2])
-        T.subsample_conv0_bwd_(S["spec"], P["conv0_w"], P["conv0_b"], ds1, G["conv0_w"], G["conv0_b"])
+        if S["s1"] is None:
+            T.subsample_l1_bwd_(S["spec"], P["conv0_w"], P["conv0_b"], P["dw1_w"], dd1, G["conv0_w"], G["conv0_b"], G["dw1_w"],
+                                G["dw1_b"])
+        else:
+            T.subsample_dwconv_bwd_weight_(S["s1"], dd1, G["dw1_w"], G["dw1_b"])
+            ds1 = T.subsample_dwconv_bwd_data(dd1, P["dw1_w"], S["s1"].shape[1], S["s1"].shape[2])
+            T.subsample_conv0_bwd_(S["spec"], P["conv0_w"], P["conv0_b"], ds1, G["conv0_w"], G["conv0_b"])
 
         if self.dp_group is not None:
             handles.append(self._reduce_slice(flat, None))  # subsampling + decoder (accumulated across all layers)

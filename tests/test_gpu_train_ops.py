@@ -312,3 +312,42 @@ def test_subsampling_backward_kernels(cuda_device, B, T_, C):
     T.subsample_conv0_bwd_(spec, w0, b0, ds1, dw0, db0)
     _close(dw0, w0r.grad, 5e-3, "conv0 dweight")
     _close(db0, b0r.grad, 5e-3, "conv0 dbias")
+
+
+@pytest.mark.parametrize("B,T_,C,Fdim", [(2, 100, 64, 80), (1, 333, 64, 80), (2, 1024, 256, 80), (1, 130, 128, 37), (3, 61, 64, 18)])
+def test_subsampling_level1_fused_backward(cuda_device, B, T_, C, Fdim):
+    """conv0 + SiLU + depthwise level 1: the fused forward / fused backward pair (the conv0 activation never reaches HBM)
+    against autograd over the same chain in fp32, and against the unfused kernels"""
+    from lcasr_b200 import train_ops as T, ops
+    dev = cuda_device
+    spec = _rand(B, Fdim, T_, seed=70).to(dev)
+    w0 = _rand(C, 9, seed=71, scale=0.3).to(dev)
+    b0 = _rand(C, seed=72, scale=0.1).to(dev)
+    w1 = _rand(C, 9, seed=73, scale=0.3).to(dev)
+    b1 = _rand(C, seed=74, scale=0.1).to(dev)
+    d1 = ops.subsample_conv0_dw(spec, w0, b0, w1, b1)               # fused forward [B,T2,F2,C]
+    dd1 = _rand(*d1.shape, seed=75).to(BF).to(dev)
+    w0r, b0r, w1r, b1r = (t.clone().requires_grad_(True) for t in (w0, b0, w1, b1))
+    img = spec.transpose(1, 2).unsqueeze(1)
+    a1 = F.silu(F.conv2d(img, w0r.view(C, 1, 3, 3), b0r, stride=2, padding=1))
+    a2 = F.conv2d(a1, w1r.view(C, 1, 3, 3), b1r, stride=2, padding=1, groups=C)
+    _close(d1, a2.permute(0, 2, 3, 1), 2 ** -6, "fused level-1 forward")
+    a2.backward(dd1.float().permute(0, 3, 1, 2))
+    dw0, db0, dw1, db1 = (torch.zeros(C, 9, device=dev), torch.zeros(C, device=dev), torch.zeros(C, 9, device=dev),
+                          torch.zeros(C, device=dev))
+    T.subsample_l1_bwd_(spec, w0, b0, w1, dd1, dw0, db0, dw1, db1)
+    _close(dw1, w1r.grad, 4e-3, "fused l1: depthwise dweight")
+    _close(db1, b1r.grad, 2e-3, "fused l1: depthwise dbias")
+    _close(dw0, w0r.grad, 6e-3, "fused l1: conv0 dweight")
+    _close(db0, b0r.grad, 6e-3, "fused l1: conv0 dbias")
+    # accumulation semantics (+=) and agreement with the unfused kernel chain
+    T.subsample_l1_bwd_(spec, w0, b0, w1, dd1, dw0, db0, dw1, db1)
+    _close(dw0, 2 * w0r.grad, 6e-3, "fused l1: accumulates")
+    s1 = ops.subsample_conv0(spec, w0, b0, out_dtype=BF)
+    uw1, ub1, uw0, ub0 = (torch.zeros(C, 9, device=dev), torch.zeros(C, device=dev), torch.zeros(C, 9, device=dev),
+                          torch.zeros(C, device=dev))
+    T.subsample_dwconv_bwd_weight_(s1, dd1, uw1, ub1)
+    ds1 = T.subsample_dwconv_bwd_data(dd1, w1, s1.shape[1], s1.shape[2])
+    T.subsample_conv0_bwd_(spec, w0, b0, ds1, uw0, ub0)
+    _close(dw1, 2 * uw1, 2e-3, "fused vs unfused: depthwise dweight")
+    _close(dw0, 2 * uw0, 6e-3, "fused vs unfused: conv0 dweight (unfused rounds ds1 to bf16)")
