@@ -246,6 +246,14 @@ __global__ void __launch_bounds__(256) subsample_conv0_bwd_kernel(const float* _
 //     ds1[2a+1][2e  ] = G00 w21 + G10 w01       ds1[2a+1][2e+1] = G00 w22 + G01 w20 + G10 w02 + G11 w00
 //   and every (G, tap) pair above also feeds the depthwise weight gradient dw1[tap] += G * s1(position).
 // A CTA (one recording, 64 channels) walks tiles of kL1R s1 rows; one shared-memory reduction and 64*20 atomics per CTA.
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc, bool valid) {  // zero-fills when !valid
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 constexpr int kL1R = 16;   // s1 rows per tile (even)
 constexpr int kL1CG = 64;  // channels per CTA (2 per lane)
 
@@ -253,10 +261,11 @@ __global__ void __launch_bounds__(256, 2) subsample_l1_bwd_fused_kernel(
     const float* __restrict__ spec, const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w1,
     const bf16* __restrict__ dd1, int F, int64_t T, int C, int64_t T1, int F1, int64_t T2, int F2, int FWp,
     float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dw1, float* __restrict__ db1) {
-  extern __shared__ float l1sm[];  // input patch [2*kL1R+1][FWp] (col 0 = freq -1, zero-filled up to FWp), then accumulators [64][20]
+  // two input patches [2*kL1R+1][FWp] (col 0 = freq -1, zero-filled up to FWp; double-buffered: the next tile's patch
+  // arrives by cp.async while this tile is processed — the kernel used to idle on the staging loads), then accumulators [64][20]
+  extern __shared__ float l1sm[];
   constexpr int INR = 2 * kL1R + 1;
-  float* s_in = l1sm;
-  float* sacc = l1sm + INR * FWp;
+  float* sacc = l1sm + 2 * INR * FWp;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * kL1CG + 2 * lane;
@@ -278,18 +287,26 @@ __global__ void __launch_bounds__(256, 2) subsample_l1_bwd_fused_kernel(
   const int EB = (F1 + 1) / 2;                 // column blocks
   const bf16* ddb = dd1 + (int64_t)b * T2 * F2 * C + c0;
   const int64_t ntiles = (T1 + kL1R - 1) / kL1R;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t r0 = tile * kL1R;            // first s1 row of the tile (even)
-    const int64_t t_in0 = 2 * r0 - 1;          // input frame of patch row 0
-    __syncthreads();                           // the previous tile's patch is no longer read
-    for (int idx = threadIdx.x; idx < INR * FWp; idx += blockDim.x) {
-      const int f = idx / INR - 1, r = idx - (f + 1) * INR;
-      const int64_t t = t_in0 + r;
-      float v = 0.f;
-      if (f >= 0 && f < F && t >= 0 && t < T) v = spec[((int64_t)b * F + f) * T + t];
-      s_in[r * FWp + (f + 1)] = v;
+  auto stage = [&](int64_t tile_, float* dst) {
+    if (tile_ < ntiles) {
+      const int64_t t0_ = 2 * tile_ * kL1R - 1;  // input frame of patch row 0
+      for (int idx = threadIdx.x; idx < INR * FWp; idx += blockDim.x) {
+        const int f = idx / INR - 1, r = idx - (f + 1) * INR;
+        const int64_t t = t0_ + r;
+        const bool ok = f >= 0 && f < F && t >= 0 && t < T;
+        cp_async_f32(dst + r * FWp + (f + 1), ok ? spec + ((int64_t)b * F + f) * T + t : spec, ok);
+      }
     }
-    __syncthreads();
+    cp_async_commit();
+  };
+  stage(blockIdx.x, l1sm);
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int64_t r0 = tile * kL1R;            // first s1 row of the tile (even)
+    const float* s_in = l1sm + (it & 1) * INR * FWp;
+    stage(tile + gridDim.x, l1sm + ((it + 1) & 1) * INR * FWp);   // that buffer's readers finished at the barrier below
+    cp_async_wait<1>();
+    __syncthreads();                           // this tile's patch is complete and visible
     const int a_base = (int)(r0 / 2);          // first block row == first dd1 row touched (T2 < 2^31 rows)
     const int nal = (int)min((int64_t)(kL1R / 2), (T1 - r0 + 1) / 2);   // block rows of this tile that exist
     const int T2i = (int)T2, T1rem = (int)min((int64_t)kL1R, T1 - r0); // s1 rows of this tile that exist
@@ -378,6 +395,7 @@ __global__ void __launch_bounds__(256, 2) subsample_l1_bwd_fused_kernel(
 #pragma unroll
       for (int i = 0; i < 4; ++i) gcur[i] = gnext[i];
     }
+    __syncthreads();                           // the patch is no longer read: the stage after next may overwrite it
   }
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
@@ -467,7 +485,7 @@ extern "C" int lcasr_subsample_l1_bwd(const float* spec, const float* w0, const 
   const int64_t T1 = (T - 1) / 2 + 1, T2 = (T1 - 1) / 2 + 1;
   const int F1 = (F - 1) / 2 + 1, F2 = (F1 - 1) / 2 + 1;
   const int FWp = std::max(F + 2, 4 * ((F1 + 1) / 2) + 1);  // patch pitch: every 5-wide block read stays inside the row
-  const size_t smem = ((size_t)(2 * kL1R + 1) * FWp + (size_t)kL1CG * 20) * sizeof(float);
+  const size_t smem = ((size_t)2 * (2 * kL1R + 1) * FWp + (size_t)kL1CG * 20) * sizeof(float);
   LCASR_CHECK_ARG(smem <= 48 * 1024, "subsample_l1_bwd: feat_in=%d too large for the staged patch", F);
   LCASR_CHECK_ARG(T2 < ((int64_t)1 << 30), "subsample_l1_bwd: too many frames");
   LCASR_CHECK_ARG(B <= 65535, "subsample_l1_bwd: batch too large");
