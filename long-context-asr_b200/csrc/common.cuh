@@ -54,6 +54,16 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 inline size_t dtype_size(int dt) { return dt == LCASR_BF16 ? 2 : 4; }
 
+// shared-memory tiled depthwise Conv1d (dwconv_tile.cu): bf16, d % 128 == 0, k in {3,5,7,9,11,15}
+bool dwconv1d_tile_ok(int d, int ks);
+int dwconv1d_tile_fwd(const void* in, int B, int64_t N, int d, int ks, const float* w, const float* b, void* out, float* sum,
+                      float* sumsq, cudaStream_t st);
+int dwconv1d_tile_bwd_data(const void* dout, int B, int64_t N, int d, int ks, const float* w, void* din, cudaStream_t st);
+int dwconv1d_tile_bwd_weight(const void* x, const void* dout, int B, int64_t N, int d, int ks, float* dw, float* db,
+                             cudaStream_t st);
+int dwconv1d_tile_eval(const void* in, int B, int64_t N, int d, int ks, const float* w, const float* b, const float* rm,
+                       const float* rs, const float* bw, const float* bb, void* out, cudaStream_t st);
+
 // ------------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------------

@@ -5,6 +5,7 @@
 // register window over TT consecutive tokens, so every input vector is loaded once per block
 // (+ (k-1)/TT halo re-reads that hit L2).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace lcasr {
 
@@ -105,6 +106,9 @@ extern "C" int lcasr_dwconv_brn_silu(const void* in, int dtype, int B, int64_t N
   LCASR_CHECK_ARG(dtype == out_dtype, "dwconv_brn_silu: in/out dtypes must match");
   LCASR_CHECK_ARG((int64_t)ceil_div(N, kDwTT) <= 65535, "dwconv_brn_silu: N=%lld too long for the grid", (long long)N);
   cudaStream_t st = (cudaStream_t)stream;
+  static const bool legacy = getenv("LCASR_DWCONV_LEGACY") != nullptr;  // A/B switch: the register-window kernel
+  if (dtype == LCASR_BF16 && !legacy && dwconv1d_tile_ok(d, ksize))
+    return dwconv1d_tile_eval(in, B, N, d, ksize, w, b, brn_mean, brn_std, brn_w, brn_b, out, st);
   if (dtype == LCASR_BF16)
     return launch_dwconv<bf16, bf16>(in, B, N, d, ksize, w, b, brn_mean, brn_std, brn_w, brn_b, out, st);
   return launch_dwconv<float, float>(in, B, N, d, ksize, w, b, brn_mean, brn_std, brn_w, brn_b, out, st);

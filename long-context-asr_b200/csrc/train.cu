@@ -5,6 +5,7 @@
 // gradient and every parameter gradient are fp32.  All kernels are HBM-bound; each thread moves 16-byte vectors
 // and rows are contiguous, reductions use warp shuffles + shared-memory atomics + one global atomic per CTA.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace lcasr {
 
@@ -870,18 +871,24 @@ extern "C" int lcasr_dwconv1d_fwd(const void* in, int B, int64_t N, int d, int k
                                   void* out, float* sum, float* sumsq, void* stream) {
   LCASR_CHECK_ARG(in && out && w && b && B > 0 && N > 0 && d > 0 && d % 8 == 0, "dwconv1d_fwd: bad arguments");
   LCASR_CHECK_ARG((sum == nullptr) == (sumsq == nullptr), "dwconv1d_fwd: sum and sumsq come together");
+  static const bool legacy = getenv("LCASR_DWCONV_LEGACY") != nullptr;  // A/B switch: the register-window kernels
+  if (!legacy && dwconv1d_tile_ok(d, ksize)) return dwconv1d_tile_fwd(in, B, N, d, ksize, w, b, out, sum, sumsq, ST);
   return launch_dwconv1d<0>(in, nullptr, B, N, d, ksize, 32, w, b, out, sum, sumsq, ST);
 }
 
 extern "C" int lcasr_dwconv1d_bwd_data(const void* dout, int B, int64_t N, int d, int ksize, const float* w, void* din,
                                        void* stream) {
   LCASR_CHECK_ARG(dout && din && w && B > 0 && N > 0 && d > 0 && d % 8 == 0, "dwconv1d_bwd_data: bad arguments");
+  static const bool legacy = getenv("LCASR_DWCONV_LEGACY") != nullptr;
+  if (!legacy && dwconv1d_tile_ok(d, ksize)) return dwconv1d_tile_bwd_data(dout, B, N, d, ksize, w, din, ST);
   return launch_dwconv1d<1>(dout, nullptr, B, N, d, ksize, 32, w, nullptr, din, nullptr, nullptr, ST);
 }
 
 extern "C" int lcasr_dwconv1d_bwd_weight(const void* x, const void* dout, int B, int64_t N, int d, int ksize, float* dw,
                                          float* db, void* stream) {
   LCASR_CHECK_ARG(x && dout && dw && db && B > 0 && N > 0 && d > 0 && d % 8 == 0, "dwconv1d_bwd_weight: bad arguments");
+  static const bool legacy = getenv("LCASR_DWCONV_LEGACY") != nullptr;
+  if (!legacy && dwconv1d_tile_ok(d, ksize)) return dwconv1d_tile_bwd_weight(x, dout, B, N, d, ksize, dw, db, ST);
   return launch_dwconv1d<2>(x, dout, B, N, d, ksize, 128, nullptr, nullptr, nullptr, dw, db, ST);
 }
 
