@@ -136,8 +136,8 @@ __global__ void __launch_bounds__(256, kMinBlocks) subsample_conv0_dw_fused_kern
   extern __shared__ __align__(16) uint8_t fsm[];
   constexpr int A0R = 2 * kFuTT2 + 1;           // conv0 rows needed: 17
   constexpr int INR = 2 * A0R + 1;              // input frames needed: 35
-  const int FW = F + 2, A0W = F1 + 2;
-  float* s_in = reinterpret_cast<float*>(fsm);                                   // [INR][FW], col 0 = freq -1
+  const int FW = max(F + 2, 4 * ((F1 + 1) / 2) + 1), A0W = F1 + 2;  // patch pitch: every 5-wide block read stays inside its row
+  float* s_in = reinterpret_cast<float*>(fsm);                                   // [INR][FW], col 0 = freq -1, zero beyond F
   __nv_bfloat162* s_a0 = reinterpret_cast<__nv_bfloat162*>(fsm + ((INR * FW * 4 + 15) & ~15));  // [A0R][A0W][32]
   const int cgi = blockIdx.y, b = blockIdx.z;
   const int64_t t2_0 = (int64_t)blockIdx.x * kFuTT2;
@@ -161,30 +161,53 @@ __global__ void __launch_bounds__(256, kMinBlocks) subsample_conv0_dw_fused_kern
   }
   __syncthreads();
   // phase 1: conv0 + SiLU tile (bf16x2 per lane), zero where the depthwise conv sees padding.
-  // Warp w walks tile positions w, w+8, ... with (row, col) advanced incrementally (no div/mod, 32-bit math).
+  // A warp owns one 2x2 block of conv0 positions (global rows 2a, 2a+1; columns 2e, 2e+1): the four positions share a
+  // 5x5 input patch (25 shared-memory reads instead of 36) and one round of index arithmetic; blocks advance
+  // incrementally (no div/mod).  Tile row 0 is a global ODD row: it is the lower half of block row 0, whose upper half
+  // lies above the tile and is skipped (warp-uniform).
   {
     const int r_lo = (int)max((int64_t)0, -a0_row0);                       // tile rows below are conv0 row < 0
     const int r_hi = (int)min((int64_t)A0R, T1 - a0_row0);                 // tile rows from here on are >= T1
-    int r = 0, c = wid;                                                    // A0W > 8, so one wrap per step at most
-#pragma unroll 2
-    for (int p = wid; p < A0R * A0W; p += 8) {
-      float y0 = 0.f, y1 = 0.f;
-      if (r >= r_lo && r < r_hi && c >= 1 && c <= F1) {
-        const float* in0 = s_in + (2 * r) * FW + 2 * (c - 1);
-        float a = ba[0], bq = ba[1];
+    const int EB = (F1 + 1) / 2;                                           // column blocks
+    constexpr int NBR = kFuTT2 + 1;                                        // block rows: tile rows (2bi-1, 2bi)
+    for (int i = threadIdx.x; i < A0R * 2 * 32; i += blockDim.x) {        // the two zero-padding columns of the tile
+      const int r = i / 64, side = (i >> 5) & 1;
+      s_a0[(r * A0W + (side ? A0W - 1 : 0)) * 32 + (i & 31)] = __floats2bfloat162_rn(0.f, 0.f);
+    }
+    int bi = 0, e = wid;
+    while (e >= EB) { e -= EB; ++bi; }
+#pragma unroll 1
+    while (bi < NBR) {
+      float in[5][5];
+      const int prow0 = 4 * bi - 2;                                        // patch row of in[0] (>= 0 except for bi == 0)
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+      for (int i = 0; i < 5; ++i)
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const float v = in0[i * FW + j];
-            a = fmaf(wa[0][i * 3 + j], v, a);
-            bq = fmaf(wa[1][i * 3 + j], v, bq);
-          }
-        y0 = silu_fast(a); y1 = silu_fast(bq);
+        for (int j = 0; j < 5; ++j) in[i][j] = s_in[max(prow0 + i, 0) * FW + 4 * e + j];
+#pragma unroll
+      for (int pi = 0; pi < 2; ++pi) {
+        const int r = 2 * bi - 1 + pi;                                     // tile row
+        if (r < 0) continue;                                               // warp-uniform: upper half of block row 0
+        const bool row_live = r >= r_lo && r < r_hi;
+#pragma unroll
+        for (int pj = 0; pj < 2; ++pj) {
+          const int c = 2 * e + 1 + pj;                                    // tile column (conv0 column c - 1)
+          float a = ba[0], bq = ba[1];
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const float v = in[2 * pi + i][2 * pj + j];
+              a = fmaf(wa[0][i * 3 + j], v, a);
+              bq = fmaf(wa[1][i * 3 + j], v, bq);
+            }
+          const bool live = row_live && c <= F1;
+          const float y0 = live ? silu_fast(a) : 0.f, y1 = live ? silu_fast(bq) : 0.f;
+          if (c < A0W) s_a0[(r * A0W + c) * 32 + lane] = __floats2bfloat162_rn(y0, y1);
+        }
       }
-      s_a0[p * 32 + lane] = __floats2bfloat162_rn(y0, y1);
-      c += 8;
-      if (c >= A0W) { c -= A0W; ++r; }
+      e += 8;
+      while (e >= EB) { e -= EB; ++bi; }
     }
   }
   __syncthreads();
@@ -262,7 +285,8 @@ static int launch_fused(const float* spec, const float* w0, const float* b0, con
                         int64_t T, int C, void* out, cudaStream_t st) {
   const int64_t T1 = (T - 1) / 2 + 1, T2 = (T1 - 1) / 2 + 1;
   const int F1 = (F - 1) / 2 + 1, F2 = (F1 - 1) / 2 + 1;
-  const size_t smem = (((size_t)(2 * (2 * TT2 + 1) + 1) * (F + 2) * 4 + 15) & ~(size_t)15) + (size_t)(2 * TT2 + 1) * (F1 + 2) * 32 * 4;
+  const int FWp = std::max(F + 2, 4 * ((F1 + 1) / 2) + 1);
+  const size_t smem = (((size_t)(2 * (2 * TT2 + 1) + 1) * FWp * 4 + 15) & ~(size_t)15) + (size_t)(2 * TT2 + 1) * (F1 + 2) * 32 * 4;
   LCASR_CHECK_ARG(smem <= 110 * 1024, "subsample_conv0_dw: feat_in=%d too large for the fused tile", F);
   LCASR_CHECK_ARG(ceil_div(T2, TT2) <= 0x7fffffff && B <= 65535, "subsample_conv0_dw: grid too large");
   static bool attr_set = false;
@@ -281,6 +305,6 @@ extern "C" int lcasr_subsample_conv0_dw(const float* spec, const float* w0, cons
   LCASR_CHECK_ARG(spec && w0 && b0 && w1 && b1 && out && B > 0 && F > 0 && T > 0, "subsample_conv0_dw: bad arguments");
   LCASR_CHECK_ARG(C % kFuCG == 0, "subsample_conv0_dw: conv_channels=%d must be a multiple of %d (use the unfused kernels)", C, kFuCG);
   static const int tt2 = getenv("LCASR_SUB_TT2") ? atoi(getenv("LCASR_SUB_TT2")) : 4;  // tuning knob: depthwise rows per CTA (4: 1.48 ms, 8: 1.63 ms at cfg3)
-  if (tt2 == 4) return launch_fused<4, 4>(spec, w0, b0, w1, b1, B, F, T, C, out, (cudaStream_t)stream);
+  if (tt2 == 4) return launch_fused<4, 3>(spec, w0, b0, w1, b1, B, F, T, C, out, (cudaStream_t)stream);
   return launch_fused<8, 2>(spec, w0, b0, w1, b1, B, F, T, C, out, (cudaStream_t)stream);
 }

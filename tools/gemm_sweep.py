@@ -10,7 +10,7 @@ from lcasr_b200 import ops, _lib as L
 
 dev = torch.device("cuda", 0)
 SHAPES = [(16384, 3072, 768, "bf16"), (16384, 2304, 768, "bf16"), (16384, 4096, 768, "bf16"), (16384, 768, 3072, "f32r"),
-          (16384, 768, 768, "f32r"), (32768, 3072, 768, "bf16"), (45056, 8192, 2048, "bf16"), (45056, 2048, 8192, "f32r")]
+          (16384, 768, 768, "f32r"), (32768, 768, 768, "f32r"), (32768, 768, 3072, "f32r"), (16384, 768, 4096, "f32r"), (32768, 3072, 768, "bf16"), (45056, 8192, 2048, "bf16"), (45056, 2048, 8192, "f32r")]
 tag = f"CG={os.environ.get('LCASR_GEMM_CG', 'auto')} DEBUG={os.environ.get('LCASR_GEMM_DEBUG', '0')}"
 for M, N, K, kind in SHAPES:
     a = torch.randn(M, K, device=dev).bfloat16()
