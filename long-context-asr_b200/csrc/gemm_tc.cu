@@ -33,17 +33,22 @@ template <typename TOut, int CG, bool W8 = true> struct TgWarps {
 
 // CG = CTAs per MMA (tcgen05 cta_group): 1, or 2 = a CTA pair computes a 256 x BN tile, each CTA staging its 128 rows
 // of A and HALF of the B tile -> 2/3 of the shared-memory fill traffic per FLOP and a deeper ring
-template <int BN, int CG = 1> struct TgCfg {
-  static constexpr int STAGES = BN == 256 ? (CG == 2 ? 5 : 4) : (CG == 2 ? 8 : 6);
+// EPI_BYTES: epilogue staging behind the operand ring — bf16 outputs: one 4 KB TMA-store box (32 rows x 64 columns) per
+// epilogue warp; fp32 outputs: two 4 KB boxes (32 x 32 fp32) per warp, which alternate as TMA-load target of the residual
+// chunk and, after the in-place add, TMA-store source.  The ring gives up stages where both do not fit.
+template <int BN, int CG, int EPI_BYTES> struct TgCfgE {
   static constexpr int A_BYTES = TG_BM * TG_BK * 2;
   static constexpr int B_BYTES = (BN / CG) * TG_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int DEF_STAGES = BN == 256 ? (CG == 2 ? 5 : 4) : (CG == 2 ? 8 : 6);
+  static constexpr int FIT_STAGES = (232448 - 1024 /*align slack*/ - (2 * BN * 4 + 512) /*static: bias, barriers*/ - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = DEF_STAGES < FIT_STAGES ? DEF_STAGES : FIT_STAGES;
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered fp32 accumulator (power of two: 256 / 512)
-  // bf16 outputs: one 32-row x 64-column (128 B rows) staging box per epilogue warp
-  template <typename TOut> static constexpr int smem_bytes() {
-    return STAGES * STAGE_BYTES + (sizeof(TOut) == 2 ? TgWarps<TOut, CG>::EPI * 4096 : 0) + 1024 /*align slack*/;
-  }
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;
+  static_assert(STAGES >= 3, "gemm_tc: operand ring too shallow");
 };
+template <int BN, typename TOut, int CG, bool W8> using TgCfgFor =
+    TgCfgE<BN, CG, TgWarps<TOut, CG, W8>::EPI * (sizeof(TOut) == 4 ? 8192 : 4096)>;
 
 struct TgEpilogue {
   const float* bias;   // [N] or null
@@ -118,6 +123,47 @@ __device__ __forceinline__ void tg_load_resid(float4 (&res)[8], int lane, int64_
   for (int it = 0; it < 8; ++it) {
     const int64_t row = row0 + it * 4 + rsub;
     if (row < M && col < N) res[it] = *reinterpret_cast<const float4*>(resid + row * N + col);
+  }
+}
+
+// fp32 outputs: residual in and result out through TMA (run 83: the epilogue of these GEMMs cost 12.2 us per 256x256 pair
+// tile whatever K — its coalesced residual loads (+14 us over the launch) and its stores (+10 us) each occupied the eight
+// epilogue warps in turn; TMA stores alone brought the residual-free case to the main-loop bound, register loads of the
+// residual in the accumulator's row layout made the other case worse).
+// box: this warp's 32 x 32 fp32 shared-memory box (128-byte rows, 16-byte slots XOR-swizzled by row % 8 — the
+// SWIZZLE_128B layout both TMA directions use).  With a residual the box holds its chunk (TMA-loaded) and is updated in
+// place; lane == row, 8 lanes with distinct row % 8 cover 8 distinct slots per wavefront: conflict-free both ways.
+__device__ __forceinline__ void tg_stage_chunk_f32(const uint32_t (&r)[32], int lane, uint32_t box, const TgEpilogue& ep,
+                                                   const float* __restrict__ bias_chunk) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                           __uint_as_float(r[4 * q + 3]));
+    if (ep.bias) {
+      const float4 b = *reinterpret_cast<const float4*>(bias_chunk + 4 * q);  // shared memory (broadcast reads)
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    if (ep.act == LCASR_ACT_GELU_TANH) {
+      float* pv = reinterpret_cast<float*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float x = pv[i];
+        const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+        pv[i] = 0.5f * x * (1.0f + tanh_approx(u));
+      }
+    } else if (ep.act == LCASR_ACT_SILU) {
+      float* pv = reinterpret_cast<float*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pv[i] = __fdividef(pv[i], 1.0f + __expf(-pv[i]));
+    }
+    const uint32_t addr = box + lane * 128 + ((q ^ (lane & 7)) << 4);
+    if (ep.resid) {
+      float4 res;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(res.x), "=f"(res.y), "=f"(res.z), "=f"(res.w) : "r"(addr) : "memory");
+      v.x = fmaf(ep.alpha, v.x, res.x); v.y = fmaf(ep.alpha, v.y, res.y);
+      v.z = fmaf(ep.alpha, v.z, res.z); v.w = fmaf(ep.alpha, v.w, res.w);
+    }
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
   }
 }
 
@@ -230,7 +276,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, int64_t M, int N, int K,
                TgEpilogue ep, TOut* out) {
   // tmC / tmC2 (bf16 outputs only): store maps of `out` / `ep.pre_out`, 64-column x 32-row boxes, 128B swizzle
-  using Cfg = TgCfg<BN, CG>;
+  using Cfg = TgCfgFor<BN, TOut, CG, W8>;
   // CG == 2: launched as clusters of 2 CTAs; `rank` 0 is the leader (issues every MMA, owns the full / tempty barriers
   // that both CTAs signal), tiles are 256 x BN and indexed per cluster
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
@@ -238,7 +284,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t bars[2 * Cfg::STAGES + 4];
   __shared__ uint32_t tmem_slot;
   constexpr int NEW = TgWarps<TOut, CG, W8>::EPI;
-  __shared__ __align__(16) float4 epi_stage[sizeof(TOut) == 4 ? NEW : 1][32 * 8];  // per epilogue warp: 32 rows x 32 fp32, swizzled
+  __shared__ __align__(8) uint64_t rbars[sizeof(TOut) == 4 ? 2 * NEW : 1];  // fp32: residual-box "landed" barriers, two per epilogue warp
   __shared__ __align__(16) float bias_s[2][BN];          // the tile's bias slice, staged while the main loop still runs
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle atoms need 1024B alignment
   const uint32_t bar_base = smem_u32(bars);
@@ -259,6 +305,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tensormap(&tmB);
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), CG * NEW); }
+    if (sizeof(TOut) == 4)
+      for (int i = 0; i < 2 * NEW; ++i) mbar_init(smem_u32(&rbars[i]), 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -328,6 +376,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = (warp - 2) >> 2;       // NEW == 8: which half of the tile's columns this warp drains
     constexpr int CPW = (BN / 32) / (NEW / 4);  // 32-column chunks per warp
     int acc = 0; uint32_t acc_phase = 0;
+    uint32_t rsel = 0, rphase = 0;  // fp32: box in use, parity bits of the two residual barriers
     const uint32_t tempty0 = CG == 2 ? mapa_shared(tempty_bar(0), 0) : 0;  // the leader's tempty barriers
     for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
       const int64_t m_idx = (tile / tiles_n) * (CG * TG_BM) + rank * TG_BM;
@@ -342,9 +391,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       const int64_t row0 = m_idx + lane_base;
       // (a two-chunk-deep prefetch ring was measured neutral — 43.4 vs 43.2 us on 16384x768x768 — and spills at 168 registers)
-      float4 res_nxt[8];
+      // fp32: this warp's two boxes alternate per chunk.  Chunk c's residual is requested one chunk ahead (at tile start for
+      // the first one), as soon as the box's previous bulk store has been read out.
+      const uint32_t box0 = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES + (warp - 2) * 8192;
+      const uint32_t rbar0 = smem_u32(&rbars[sizeof(TOut) == 4 ? 2 * (warp - 2) : 0]);
+      const int c_begin = half * CPW;
       if constexpr (sizeof(TOut) == 4) {
-        if (ep.resid) tg_load_resid(res_nxt, lane, row0, n_idx + half * CPW * 32, M, N, ep.resid);  // first chunk, in flight during the wait
+        // (the boxes bound the bytes in flight — one 4 KB chunk ahead per warp; L2 prefetches of the next tile's residual
+        // boxes, cp.async.bulk.prefetch.tensor, were measured: no gain at K = 768, 6-12 % slower for long K)
+        if (ep.resid && lane == 0 && n_idx + c_begin * 32 < N) {
+          tma_store_wait_read();
+          mbar_arrive_expect_tx(rbar0 + 8u * rsel, 4096);
+          tma_load_2d(box0 + 4096u * rsel, &tmC2, rbar0 + 8u * rsel, n_idx + c_begin * 32, (int)row0);
+        }
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -376,13 +435,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         } else {
-          float4 res_cur[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) res_cur[i] = res_nxt[i];
-          if (ep.resid && c + 1 < (half + 1) * CPW && n_idx + (c + 1) * 32 < N)
-            tg_load_resid(res_nxt, lane, row0, n_idx + (c + 1) * 32, M, N, ep.resid);  // in flight during this chunk
+          const uint32_t box = box0 + 4096u * rsel, other = box0 + 4096u * (rsel ^ 1);
+          if (lane == 0) {
+            tma_store_wait_read();  // the other box (stored from in the previous chunk) has been read out
+            if (ep.resid && c + 1 < (half + 1) * CPW && n_idx + (c + 1) * 32 < N) {  // next chunk's residual, in flight during this one
+              mbar_arrive_expect_tx(rbar0 + 8u * (rsel ^ 1), 4096);
+              tma_load_2d(other, &tmC2, rbar0 + 8u * (rsel ^ 1), n_idx + (c + 1) * 32, (int)row0);
+            }
+          }
+          if (ep.resid) {
+            mbar_wait(rbar0 + 8u * rsel, (rphase >> rsel) & 1u);
+            rphase ^= 1u << rsel;
+          }
           tmem_wait_ld();
-          tg_store_chunk<TOut>(r, res_cur, epi_stage[sizeof(TOut) == 4 ? warp - 2 : 0], lane, row0, n_idx + c * 32, M, N, ep, &bias_s[acc][c * 32], out);
+          __syncwarp();
+          tg_stage_chunk_f32(r, lane, box, ep, &bias_s[acc][c * 32]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && ep.debug != 3) {
+            tma_store_2d(&tmC, box, n_idx + c * 32, (int)row0);
+            tma_store_commit();
+          }
+          rsel ^= 1;
         }
       }
       tc_fence_before();
@@ -393,7 +467,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (sizeof(TOut) == 2 && lane == 0) tma_store_wait_all();  // bulk stores complete before the CTA retires
+    if (lane == 0) tma_store_wait_all();  // bulk stores complete before the CTA retires
   }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all();  // the leader's MMAs read the peer's shared memory and write its TMEM
@@ -423,15 +497,23 @@ static PFN_tmapEncodeTiled get_encode_fn() {
   return fn;
 }
 
+static int make_tmap_2d_any(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t rows, uint64_t cols,
+                            uint64_t row_pitch_bytes, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swizzle);
+
 int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes,
                       uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swizzle) {
+  return make_tmap_2d_any(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rows, cols, row_pitch_bytes, box_rows, box_cols, swizzle);
+}
+
+static int make_tmap_2d_any(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t rows, uint64_t cols,
+                            uint64_t row_pitch_bytes, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swizzle) {
   PFN_tmapEncodeTiled fn = get_encode_fn();
   if (!fn) return set_error(LCASR_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {row_pitch_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -461,19 +543,25 @@ int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t d0, uint64_t 
 template <int BN, typename TOut, int CG, bool W8 = true>
 static int launch_tc(const void* A, const void* W, int64_t M, int N, int K, const TgEpilogue& ep, void* out,
                      cudaStream_t st) {
-  using Cfg = TgCfg<BN, CG>;
+  using Cfg = TgCfgFor<BN, TOut, CG, W8>;
   CUtensorMap tmA, tmB;
   LCASR_TRY(make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)K * 2, TG_BM, TG_BK, CU_TENSOR_MAP_SWIZZLE_128B));
   LCASR_TRY(make_tmap_2d_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, BN / CG, TG_BK, CU_TENSOR_MAP_SWIZZLE_128B));
-  CUtensorMap tmC = tmA, tmC2 = tmA;  // placeholders for fp32 outputs (never dereferenced)
-  if (sizeof(TOut) == 2) {
+  CUtensorMap tmC = tmA, tmC2 = tmA;
+  if (sizeof(TOut) == 4) {  // 32 x 32 fp32 boxes (128-byte rows)
+    LCASR_TRY(make_tmap_2d_any(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, out, (uint64_t)M, (uint64_t)N, (uint64_t)N * 4, 32, 32,
+                               CU_TENSOR_MAP_SWIZZLE_128B));
+    if (ep.resid)
+      LCASR_TRY(make_tmap_2d_any(&tmC2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, ep.resid, (uint64_t)M, (uint64_t)N, (uint64_t)N * 4, 32, 32,
+                                 CU_TENSOR_MAP_SWIZZLE_128B));
+  } else {
     LCASR_TRY(make_tmap_2d_bf16(&tmC, out, (uint64_t)M, (uint64_t)N, (uint64_t)N * 2, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
     if (ep.pre_out)
       LCASR_TRY(make_tmap_2d_bf16(&tmC2, ep.pre_out, (uint64_t)M, (uint64_t)N, (uint64_t)N * 2, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
   }
   static bool attr_set = false;
   if (!attr_set) {
-    LCASR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TOut, CG, W8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::template smem_bytes<TOut>()));
+    LCASR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TOut, CG, W8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int64_t tiles = ceil_div(M, CG * TG_BM) * ceil_div(N, BN);
@@ -482,7 +570,7 @@ static int launch_tc(const void* A, const void* W, int64_t M, int N, int K, cons
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(TgWarps<TOut, CG, W8>::THREADS);
-  cfg.dynamicSmemBytes = Cfg::template smem_bytes<TOut>();
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
