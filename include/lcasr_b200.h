@@ -301,7 +301,7 @@ int lcasr_layernorm_bwd_cast(const float* x, const void* dy, int dy_dtype, const
  * optional per-channel sum / sum-of-squares of the output (BatchRenorm batch statistics); its data gradient
  * and its weight / bias gradients (dw [d,k], db [d], +=). */
 int lcasr_dwconv1d_fwd(const void* in, int B, int64_t N, int d, int ksize, const float* w, const float* b,
-                       void* out, float* sum, float* sumsq, void* stream);
+                       void* out, double* sum, double* sumsq, void* stream);
 int lcasr_dwconv1d_bwd_data(const void* dout, int B, int64_t N, int d, int ksize, const float* w, void* din,
                             void* stream);
 int lcasr_dwconv1d_bwd_weight(const void* x, const void* dout, int B, int64_t N, int d, int ksize, float* dw,
@@ -309,17 +309,19 @@ int lcasr_dwconv1d_bwd_weight(const void* x, const void* dout, int B, int64_t N,
 /* BatchRenorm1d training forward (batchrenorm.py:52-84) from the channel sums over `count` tokens:
  * writes the affine z = c*A + Bc, saves stats [5,d] = (mu, sigma, r, d, std) and updates running_mean /
  * running_std in place with `momentum`.  rmax, dmax: the module's current clamps (:41-50). */
-int lcasr_brn_train_stats(const float* sum, const float* sumsq, int64_t count, int d, float* running_mean,
+int lcasr_brn_train_stats(const double* sum, const double* sumsq, int64_t count, int d, float* running_mean,
                           float* running_std, float eps, float rmax, float dmax, float momentum,
                           const float* weight, const float* bias, float* A, float* Bc, float* stats,
                           void* stream);
 /* y = silu(c*A + Bc) */
 int lcasr_affine_silu(const void* c, int64_t M, int d, const float* A, const float* Bc, void* out, void* stream);
-/* dz = dy * silu'(c*A+Bc) (bf16) and S1 += sum dz, S2 += sum dz*xhat per channel */
+/* dz = dy * silu'(c*A+Bc) (bf16) and S1 += sum dz, S2 += sum dz*xhat per channel.  The per-channel sums of the
+ * BatchRenorm forward (lcasr_dwconv1d_fwd) and backward are accumulated across CTAs in fp64 so that the fp32 statistics
+ * and everything downstream of them are reproducible run to run. */
 int lcasr_affine_silu_bwd(const void* c, const void* dy, int64_t M, int d, const float* A, const float* Bc,
-                          const float* stats, void* dz, float* S1, float* S2, void* stream);
+                          const float* stats, void* dz, double* S1, double* S2, void* stream);
 /* BatchRenorm backward, per channel: dweight +=, dbias +=, and coef [3,d] of dc = k1*dz + k2*c + k3 */
-int lcasr_brn_bwd_finalize(const float* S1, const float* S2, int64_t count, int d, const float* weight,
+int lcasr_brn_bwd_finalize(const double* S1, const double* S2, int64_t count, int d, const float* weight,
                            const float* stats, float* dweight, float* dbias, float* coef, void* stream);
 /* out = coef[0]*a + coef[1]*b + coef[2] per channel, bf16 [M,d] */
 int lcasr_affine3(const void* a, const void* b, int64_t M, int d, const float* coef, void* out, void* stream);

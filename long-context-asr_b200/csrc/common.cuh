@@ -56,8 +56,8 @@ inline size_t dtype_size(int dt) { return dt == LCASR_BF16 ? 2 : 4; }
 
 // shared-memory tiled depthwise Conv1d (dwconv_tile.cu): bf16, d % 128 == 0, k in {3,5,7,9,11,15}
 bool dwconv1d_tile_ok(int d, int ks);
-int dwconv1d_tile_fwd(const void* in, int B, int64_t N, int d, int ks, const float* w, const float* b, void* out, float* sum,
-                      float* sumsq, cudaStream_t st);
+int dwconv1d_tile_fwd(const void* in, int B, int64_t N, int d, int ks, const float* w, const float* b, void* out, double* sum,
+                      double* sumsq, cudaStream_t st);
 int dwconv1d_tile_bwd_data(const void* dout, int B, int64_t N, int d, int ks, const float* w, void* din, cudaStream_t st);
 int dwconv1d_tile_bwd_weight(const void* x, const void* dout, int B, int64_t N, int d, int ks, float* dw, float* db,
                              cudaStream_t st);

@@ -361,8 +361,12 @@ __global__ void __launch_bounds__(256) ctc_grad_collect_kernel(const float* __re
                                                                const float* __restrict__ ab, const float* __restrict__ ab2,
                                                                float* __restrict__ grad) {
   // ab2 == NULL: `ab` holds alpha+beta; else ab = alpha, ab2 = beta (kept apart by the concurrent recursion)
-  extern __shared__ float acc[];  // [V] linear-domain sums relative to the frame max
+  // [V] linear-domain sums relative to the frame max, as 64-bit FIXED-POINT numbers (2^-40 steps): integer atomics are
+  // associative, so the sum over the lattice states of a repeated label does not depend on the order in which the
+  // threads' atomics land — the CTC gradient feeds every other gradient of the step and is now reproducible.
+  extern __shared__ unsigned long long acc[];
   __shared__ float red[8];
+  constexpr float kFix = 1099511627776.0f;  // 2^40; every term is exp(v - max) <= 1, at most 2S+1 < 2^23 of them
   const int64_t t = blockIdx.x;
   const int b = blockIdx.y;
   const int64_t T = input_lengths ? min((int64_t)input_lengths[b], N) : N;
@@ -377,7 +381,7 @@ __global__ void __launch_bounds__(256) ctc_grad_collect_kernel(const float* __re
   const float* abr2 = ab2 ? ab2 + ((int64_t)b * N + t) * Lp_max : nullptr;
   const int64_t* tgt = targets + (int64_t)b * S_max;
   const float* lp = log_probs + ((int64_t)b * N + t) * V;
-  for (int c = threadIdx.x; c < V; c += blockDim.x) acc[c] = 0.f;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) acc[c] = 0ull;
   float mx = -INFINITY;
   for (int s = threadIdx.x; s < Lp; s += blockDim.x) mx = fmaxf(mx, abr2 ? abr[s] + abr2[s] : abr[s]);
   mx = warp_max(mx);
@@ -387,23 +391,26 @@ __global__ void __launch_bounds__(256) ctc_grad_collect_kernel(const float* __re
   for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
   __syncthreads();
   if (mx != -INFINITY) {
-    float blank_sum = 0.f;  // the S+1 blank states would serialise on one shared-memory atomic
+    unsigned long long blank_sum = 0ull;  // the S+1 blank states would serialise on one shared-memory atomic
     for (int s = threadIdx.x; s < Lp; s += blockDim.x) {
       float v = abr2 ? abr[s] + abr2[s] : abr[s];
       if (v == -INFINITY) continue;
       float e = expf(v - mx);
-      if (s & 1) atomicAdd(&acc[(int)tgt[(s - 1) >> 1]], e);
-      else blank_sum += e;
+      const unsigned long long q = (unsigned long long)(e * kFix);
+      if (s & 1) atomicAdd(&acc[(int)tgt[(s - 1) >> 1]], q);
+      else blank_sum += q;
     }
-    blank_sum = warp_sum(blank_sum);
-    if ((threadIdx.x & 31) == 0 && blank_sum != 0.f) atomicAdd(&acc[blank], blank_sum);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) blank_sum += __shfl_xor_sync(0xffffffffu, blank_sum, o);
+    if ((threadIdx.x & 31) == 0 && blank_sum != 0ull) atomicAdd(&acc[blank], blank_sum);
   }
   __syncthreads();
   const float nl = nll[b], gn = grad_nll ? grad_nll[b] : 1.f;
   const bool bad = isinf(nl);  // zero_infinity=False: grads of an inf loss are NaN in ATen; we emit 0*gn
   for (int c = threadIdx.x; c < V; c += blockDim.x) {
     float l = lp[c];
-    float occ = acc[c] > 0.f ? expf(logf(acc[c]) + mx + nl - l) : 0.f;
+    const float a = (float)acc[c] * (1.0f / kFix);
+    float occ = a > 0.f ? expf(logf(a) + mx + nl - l) : 0.f;
     g[c] = bad ? 0.f : (expf(l) - occ) * gn;
   }
 }
@@ -490,7 +497,7 @@ extern "C" int lcasr_ctc_loss_bwd(const float* log_probs, int B, int64_t N, int 
   LCASR_CUDA(cudaMemcpyAsync(beta_ws, alpha_ws, (size_t)B * N * Lp_max * sizeof(float), cudaMemcpyDeviceToDevice, st));
   LCASR_TRY(ctc_recursion(log_probs, B, N, V, targets, S_max, input_lengths, target_lengths, blank, -1, nullptr,
                           beta_ws, st));
-  size_t smem = (size_t)V * sizeof(float);
+  size_t smem = (size_t)V * sizeof(unsigned long long);
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
     LCASR_CUDA(cudaFuncSetAttribute(ctc_grad_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -528,7 +535,7 @@ extern "C" int lcasr_ctc_loss_grad(const float* log_probs, int B, int64_t N, int
   LCASR_CHECK_ARG(B > 0 && B <= 65535 && N > 0 && V > 1 && S_max >= 0 && blank >= 0 && blank < V, "ctc_loss_grad: bad shape");
   LCASR_CHECK_ARG((size_t)V * 4 <= 200 * 1024, "ctc_loss_grad: V=%d too large", V);
   cudaStream_t st = (cudaStream_t)stream;
-  size_t smem = (size_t)V * sizeof(float);
+  size_t smem = (size_t)V * sizeof(unsigned long long);
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
     LCASR_CUDA(cudaFuncSetAttribute(ctc_grad_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -37,7 +37,7 @@ struct DtParams {
   const float* w;        // [d, KS]
   const float* b;        // conv bias (FWD, EVAL)
   const float *rm, *rs, *bw, *bb;  // EVAL: BatchRenorm running mean / std, weight, bias
-  float* acc0;           // FWD: sum [d] (may be NULL); BWD_WEIGHT: dw [d, KS]
+  float* acc0;           // FWD: sum [d] (fp64 behind the pointer; may be NULL); BWD_WEIGHT: dw [d, KS]
   float* acc1;           // FWD: sum of squares [d];    BWD_WEIGHT: db [d]
   int64_t N;
   int d;
@@ -216,9 +216,9 @@ __global__ void __launch_bounds__(256, 2) dwconv1d_tile_kernel(const DtParams p)
         const int c = idx / (KS + 1), k = idx - c * (KS + 1);
         if (k < KS) atomicAdd(p.acc0 + (int64_t)(cbase + c) * KS + k, v);
         else atomicAdd(p.acc1 + cbase + c, v);
-      } else {
-        if (idx < 4) atomicAdd(p.acc0 + cbase + idx, v);
-        else atomicAdd(p.acc1 + cbase + idx - 4, v);
+      } else {  // BatchRenorm batch statistics: fp64 across CTAs, so the fp32 mean / variance do not depend on the order
+        if (idx < 4) atomicAdd(reinterpret_cast<double*>(p.acc0) + cbase + idx, (double)v);
+        else atomicAdd(reinterpret_cast<double*>(p.acc1) + cbase + idx - 4, (double)v);
       }
     }
   }
@@ -267,9 +267,10 @@ bool dwconv1d_tile_ok(int d, int ks) {
   return d % kDtCS == 0 && (ks == 3 || ks == 5 || ks == 7 || ks == 9 || ks == 11 || ks == 15);
 }
 
-int dwconv1d_tile_fwd(const void* in, int B, int64_t N, int d, int ks, const float* w, const float* b, void* out, float* sum,
-                      float* sumsq, cudaStream_t st) {
-  DtParams p{(const bf16*)in, nullptr, (bf16*)out, w, b, nullptr, nullptr, nullptr, nullptr, sum, sumsq, N, d};
+int dwconv1d_tile_fwd(const void* in, int B, int64_t N, int d, int ks, const float* w, const float* b, void* out, double* sum,
+                      double* sumsq, cudaStream_t st) {
+  DtParams p{(const bf16*)in, nullptr, (bf16*)out, w, b, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<float*>(sum),
+             reinterpret_cast<float*>(sumsq), N, d};
   return dwconv1d_tile_launch<DT_FWD>(p, B, ks, st);
 }
 int dwconv1d_tile_bwd_data(const void* dout, int B, int64_t N, int d, int ks, const float* w, void* din, cudaStream_t st) {

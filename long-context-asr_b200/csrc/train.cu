@@ -554,9 +554,11 @@ __global__ void __launch_bounds__(128) dwconv1d_kernel(const bf16* __restrict__ 
       }
     }
   }
-  if (MODE == 0 && acc0) {
+  if (MODE == 0 && acc0) {  // cross-CTA sums in fp64: the order in which the atomics land no longer reaches the fp32 result
+    double* q0 = reinterpret_cast<double*>(acc0);
+    double* q1 = reinterpret_cast<double*>(acc1);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) { atomicAdd(acc0 + c0 + c, s1[c]); atomicAdd(acc1 + c0 + c, s2[c]); }
+    for (int c = 0; c < 8; ++c) { atomicAdd(q0 + c0 + c, (double)s1[c]); atomicAdd(q1 + c0 + c, (double)s2[c]); }
   }
   if (MODE == 2) {
 #pragma unroll
@@ -575,15 +577,15 @@ __global__ void __launch_bounds__(128) dwconv1d_kernel(const bf16* __restrict__ 
 //   z = weight * ((c - mu) / sigma * r + dd) + bias = c * A + Bc
 // and the running statistics are updated in place (momentum), exactly like the reference module.
 // stats[5][d] receives mu, sigma, r, dd, s (= sigma - eps) for the backward.
-__global__ void brn_train_stats_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, float count, int d,
+__global__ void brn_train_stats_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, float count, int d,
                                        float* __restrict__ running_mean, float* __restrict__ running_std, float eps,
                                        float rmax, float dmax, float momentum, const float* __restrict__ weight,
                                        const float* __restrict__ bias, float* __restrict__ A, float* __restrict__ Bc,
                                        float* __restrict__ stats) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= d) return;
-  const float mu = sum[c] / count;
-  const float var = fmaxf(sumsq[c] / count - mu * mu, 0.f);
+  const float mu = (float)sum[c] / count;
+  const float var = fmaxf((float)sumsq[c] / count - mu * mu, 0.f);
   const float s = sqrtf(var);
   const float sigma = s + eps;
   const float rs = running_std[c], rm = running_mean[c];
@@ -618,8 +620,8 @@ __global__ void __launch_bounds__(256) affine_silu_kernel(const bf16* __restrict
 __global__ void __launch_bounds__(256) affine_silu_bwd_kernel(const bf16* __restrict__ cin, const bf16* __restrict__ dy,
                                                               int64_t M, int d, int rows_per_cta, const float* __restrict__ A,
                                                               const float* __restrict__ Bc, const float* __restrict__ stats,
-                                                              bf16* __restrict__ dz, float* __restrict__ S1,
-                                                              float* __restrict__ S2) {
+                                                              bf16* __restrict__ dz, double* __restrict__ S1,
+                                                              double* __restrict__ S2) {
   __shared__ float red[8][32][16];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int cg = blockIdx.x * 32 + cx;
@@ -660,8 +662,8 @@ __global__ void __launch_bounds__(256) affine_silu_bwd_kernel(const bf16* __rest
       float s = 0.f, t = 0.f;
 #pragma unroll
       for (int y = 0; y < 8; ++y) { s += red[y][cx][i]; t += red[y][cx][8 + i]; }
-      atomicAdd(S1 + cg * 8 + i, s);
-      atomicAdd(S2 + cg * 8 + i, t);
+      atomicAdd(S1 + cg * 8 + i, (double)s);  // fp64 across CTAs: deterministic fp32 coefficients downstream
+      atomicAdd(S2 + cg * 8 + i, (double)t);
     }
   }
 }
@@ -669,13 +671,13 @@ __global__ void __launch_bounds__(256) affine_silu_bwd_kernel(const bf16* __rest
 // backward finalize (per channel): gradients of the BatchRenorm affine parameters and the three coefficient
 // vectors of  dc = k1*dz + k2*c + k3 :
 //   dxhat = dz*w*r ; dc = (1/sigma) [dxhat - mean(dxhat) - xhat * (sigma/s) * mean(dxhat*xhat)]
-__global__ void brn_bwd_finalize_kernel(const float* __restrict__ S1, const float* __restrict__ S2, float count, int d,
+__global__ void brn_bwd_finalize_kernel(const double* __restrict__ S1, const double* __restrict__ S2, float count, int d,
                                         const float* __restrict__ weight, const float* __restrict__ stats,
                                         float* __restrict__ dweight, float* __restrict__ dbias, float* __restrict__ coef) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= d) return;
   const float mu = stats[c], sigma = stats[d + c], r = stats[2 * d + c], dd = stats[3 * d + c], s = stats[4 * d + c];
-  const float s1 = S1[c], s2 = S2[c];
+  const float s1 = (float)S1[c], s2 = (float)S2[c];
   atomicAdd(dweight + c, r * s2 + dd * s1);  // sum dz * (r*xhat + dd)
   atomicAdd(dbias + c, s1);
   const float k = weight[c] * r / sigma;
@@ -868,12 +870,12 @@ static int launch_dwconv1d(const void* in, const void* in2, int B, int64_t N, in
 }
 
 extern "C" int lcasr_dwconv1d_fwd(const void* in, int B, int64_t N, int d, int ksize, const float* w, const float* b,
-                                  void* out, float* sum, float* sumsq, void* stream) {
+                                  void* out, double* sum, double* sumsq, void* stream) {
   LCASR_CHECK_ARG(in && out && w && b && B > 0 && N > 0 && d > 0 && d % 8 == 0, "dwconv1d_fwd: bad arguments");
   LCASR_CHECK_ARG((sum == nullptr) == (sumsq == nullptr), "dwconv1d_fwd: sum and sumsq come together");
   static const bool legacy = getenv("LCASR_DWCONV_LEGACY") != nullptr;  // A/B switch: the register-window kernels
   if (!legacy && dwconv1d_tile_ok(d, ksize)) return dwconv1d_tile_fwd(in, B, N, d, ksize, w, b, out, sum, sumsq, ST);
-  return launch_dwconv1d<0>(in, nullptr, B, N, d, ksize, 32, w, b, out, sum, sumsq, ST);
+  return launch_dwconv1d<0>(in, nullptr, B, N, d, ksize, 32, w, b, out, reinterpret_cast<float*>(sum), reinterpret_cast<float*>(sumsq), ST);
 }
 
 extern "C" int lcasr_dwconv1d_bwd_data(const void* dout, int B, int64_t N, int d, int ksize, const float* w, void* din,
@@ -892,7 +894,7 @@ extern "C" int lcasr_dwconv1d_bwd_weight(const void* x, const void* dout, int B,
   return launch_dwconv1d<2>(x, dout, B, N, d, ksize, 128, nullptr, nullptr, nullptr, dw, db, ST);
 }
 
-extern "C" int lcasr_brn_train_stats(const float* sum, const float* sumsq, int64_t count, int d, float* running_mean,
+extern "C" int lcasr_brn_train_stats(const double* sum, const double* sumsq, int64_t count, int d, float* running_mean,
                                      float* running_std, float eps, float rmax, float dmax, float momentum,
                                      const float* weight, const float* bias, float* A, float* Bc, float* stats,
                                      void* stream) {
@@ -912,7 +914,7 @@ extern "C" int lcasr_affine_silu(const void* c, int64_t M, int d, const float* A
 }
 
 extern "C" int lcasr_affine_silu_bwd(const void* c, const void* dy, int64_t M, int d, const float* A, const float* Bc,
-                                     const float* stats, void* dz, float* S1, float* S2, void* stream) {
+                                     const float* stats, void* dz, double* S1, double* S2, void* stream) {
   LCASR_CHECK_ARG(c && dy && A && Bc && stats && dz && S1 && S2 && M > 0 && d > 0 && d % 8 == 0, "affine_silu_bwd: bad arguments");
   const int rows_per_cta = 128;
   dim3 grid((unsigned)ceil_div(d / 8, 32), (unsigned)ceil_div(M, rows_per_cta));
@@ -923,7 +925,7 @@ extern "C" int lcasr_affine_silu_bwd(const void* c, const void* dy, int64_t M, i
   return 0;
 }
 
-extern "C" int lcasr_brn_bwd_finalize(const float* S1, const float* S2, int64_t count, int d, const float* weight,
+extern "C" int lcasr_brn_bwd_finalize(const double* S1, const double* S2, int64_t count, int d, const float* weight,
                                       const float* stats, float* dweight, float* dbias, float* coef, void* stream) {
   LCASR_CHECK_ARG(S1 && S2 && weight && stats && dweight && dbias && coef && count > 0 && d > 0, "brn_bwd_finalize: bad arguments");
   brn_bwd_finalize_kernel<<<(unsigned)ceil_div(d, 128), 128, 0, ST>>>(S1, S2, (float)count, d, weight, stats, dweight, dbias, coef);

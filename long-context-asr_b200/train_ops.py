@@ -251,7 +251,7 @@ def dwconv1d_fwd(x, w, b, stats=False):
     _cuda(x, w, b)
     B, N, d = x.shape
     out = torch.empty_like(x)
-    s = torch.zeros(2, d, dtype=torch.float32, device=x.device) if stats else None
+    s = torch.zeros(2, d, dtype=torch.float64, device=x.device) if stats else None  # fp64 cross-CTA sums (reproducible)
     L.call("lcasr_dwconv1d_fwd", L.ptr(x), B, N, d, w.shape[-1], L.ptr(w), L.ptr(b), L.ptr(out),
            L.ptr(s[0]) if stats else None, L.ptr(s[1]) if stats else None, _s())
     return out, s
@@ -297,7 +297,7 @@ def brn_silu_bwd(c, dy, A, Bc, stats, weight, dweight, dbias):
     d = c.shape[-1]
     M = c.numel() // d
     dz = torch.empty_like(c)
-    S = torch.zeros(2, d, dtype=torch.float32, device=c.device)
+    S = torch.zeros(2, d, dtype=torch.float64, device=c.device)  # fp64 cross-CTA sums (reproducible)
     L.call("lcasr_affine_silu_bwd", L.ptr(c), L.ptr(dy), M, d, L.ptr(A), L.ptr(Bc), L.ptr(stats), L.ptr(dz), L.ptr(S[0]),
            L.ptr(S[1]), _s())
     coef = torch.empty(3, d, dtype=torch.float32, device=c.device)

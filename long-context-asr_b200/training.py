@@ -42,6 +42,8 @@ class TrainEngine:
         self._layout: Optional[Dict[str, tuple]] = None
         self.dp_group = None      # torch.distributed process group: all-reduce gradients inside backward
         self.dp_average = True    # divide by the world size (DistributedDataParallel semantics)
+        self.dp_overlap = True    # per-layer all-reduces behind the rest of the backward (False: one all-reduce at the end)
+        self.trace = None
         self.last_flat_grad: Optional[torch.Tensor] = None
 
     # ---- parameters -------------------------------------------------------------------------------------
@@ -285,6 +287,7 @@ class TrainEngine:
         flat, G = self.grad_buffers(P, dev)
         SILU = L.ACT_SILU
         handles = []
+        trace = self.trace  # debugging aid (tools/bwd_trace_check.py): list receiving (stage, clone) pairs, or None
 
         def ln_bwd(x, dy, pk, dx, accumulate, cast_scale=None):
             """cast_scale: also return bf16(cast_scale * dx), the dY operand of the sub-layer processed next"""
@@ -300,6 +303,8 @@ class TrainEngine:
 
         dlp = dlp.contiguous().view(M, V1).to(torch.float32)
         dl = T.log_softmax_bwd(S["lp"], dlp)                          # [M,V1] bf16
+        if trace is not None:
+            trace += [("dlp (CTC gradient)", dlp.clone()), ("dl (log-softmax backward, bf16)", dl.clone())]
         da = linear_bwd(dl, S["a_dec"], "dec_ff_w", "dec_ff_b")
         dx = torch.empty(M, d, dtype=torch.float32, device=dev)       # gradient of the residual stream
         if m.decoder_norm:
@@ -324,6 +329,8 @@ class TrainEngine:
                 else:
                     T.add_bf16_(dx, da6)
             _, dy_next = ln_bwd(R["x_pre_out"], dx, q + "norm_out", dx, accumulate=False, cast_scale=0.5)  # ff2 comes next
+            if trace is not None:
+                trace += [(f"{q}dx after norm_out (fp32)", dx.clone()), (f"{q}dy into ff2 (bf16)", dy_next.clone())]
             nxt = {"ff2": 1.0, "conv": 1.0, "attn": 0.5}  # residual scale of the sub-layer that FOLLOWS in the backward order
             for ff in ("ff2", "conv", "attn", "ff1"):
                 r = R[ff]
@@ -339,6 +346,8 @@ class TrainEngine:
                     dyy = linear_bwd(dy, r["y"].view(M, d), q + "pw2_w", q + "pw2_b")
                     dc = T.brn_silu_bwd(r["c"], dyy.view(B, N, d), r["A"], r["Bc"], r["stats"], P[q + "brn_w"], G[q + "brn_w"],
                                         G[q + "brn_b"])
+                    if trace is not None:
+                        trace += [(f"{q}conv dy (bf16)", dy.clone()), (f"{q}conv dyy (bf16)", dyy.clone()), (f"{q}conv dc (bf16)", dc.clone())]
                     T.dwconv1d_bwd_weight_(r["g"].view(B, N, d), dc, G[q + "dw_w"], G[q + "dw_b"])
                     dg = T.dwconv1d_bwd_data(dc, P[q + "dw_w"])
                     if S["lens_dev"] is not None:
@@ -355,8 +364,8 @@ class TrainEngine:
                     da = linear_bwd(dqkv, r["a"], q + "qkv_w")
                     _, dy_next = ln_bwd(r["x"], da, q + "attn_norm", dx, accumulate=True, cast_scale=cs)
             S["layers"][l] = None  # release this layer's activations
-            if self.dp_group is not None:  # this layer's parameter gradients are final: reduce them behind the rest of the backward
-                handles.append(self._reduce_slice(flat, q))
+            if self.dp_group is not None and self.dp_overlap:  # this layer's parameter gradients are final: reduce them behind
+                handles.append(self._reduce_slice(flat, q))                # the rest of the backward
 
         # subsampling
         dy = T.scale_cast(dx, 1.0)
@@ -374,7 +383,9 @@ class TrainEngine:
             ds1 = T.subsample_dwconv_bwd_data(dd1, P["dw1_w"], S["s1"].shape[1], S["s1"].shape[2])
             T.subsample_conv0_bwd_(S["spec"], P["conv0_w"], P["conv0_b"], ds1, G["conv0_w"], G["conv0_b"])
 
-        if self.dp_group is not None:
+        if self.dp_group is not None and not self.dp_overlap:
+            self.reduce_gradients(flat)
+        elif self.dp_group is not None:
             handles.append(self._reduce_slice(flat, None))  # subsampling + decoder (accumulated across all layers)
             for h in handles:
                 h.wait()
