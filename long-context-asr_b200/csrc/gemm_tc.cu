@@ -107,25 +107,6 @@ __device__ __forceinline__ void tg_store_chunk_direct(const uint32_t (&r)[32], i
     if (g < ngroups) Vec8<bf16>::store(op + 8 * g, *reinterpret_cast<const float(*)[8]>(&y[8 * g]));
 }
 
-// Epilogue for one 32-column chunk of a warp's 32 accumulator rows.
-// tcgen05.ld hands every lane one ROW (32 consecutive fp32 columns); writing that straight to global
-// memory makes each warp store touch 32 different 128-byte lines.  The chunk is therefore transposed
-// through a 4 KB per-warp shared-memory tile (16-byte XOR swizzle, conflict-free both ways) so that
-// 8 consecutive lanes cover one row's 128 contiguous bytes: every global load / store instruction of the
-// warp then covers 4 full lines.  All loads of the chunk (residual) are issued before any store
-// (`out` may alias `resid`: in-place residual update).
-// residual values of one chunk for this lane's 8 (row, 4-column) slots; issued one chunk AHEAD of their use so
-// the L2/HBM latency overlaps the previous chunk's work (4 epilogue warps cannot hide it by occupancy)
-__device__ __forceinline__ void tg_load_resid(float4 (&res)[8], int lane, int64_t row0, int col0, int64_t M, int N,
-                                              const float* resid) {
-  const int col = col0 + 4 * (lane & 7), rsub = lane >> 3;
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int64_t row = row0 + it * 4 + rsub;
-    if (row < M && col < N) res[it] = *reinterpret_cast<const float4*>(resid + row * N + col);
-  }
-}
-
 // fp32 outputs: residual in and result out through TMA (run 83: the epilogue of these GEMMs cost 12.2 us per 256x256 pair
 // tile whatever K — its coalesced residual loads (+14 us over the launch) and its stores (+10 us) each occupied the eight
 // epilogue warps in turn; TMA stores alone brought the residual-free case to the main-loop bound, register loads of the
@@ -165,60 +146,6 @@ __device__ __forceinline__ void tg_stage_chunk_f32(const uint32_t (&r)[32], int 
     }
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
   }
-}
-
-template <typename TOut>
-__device__ __forceinline__ void tg_store_chunk(const uint32_t (&r)[32], const float4 (&res)[8], float4* __restrict__ stage,
-                                               int lane, int64_t row0, int col0, int64_t M, int N, const TgEpilogue& ep,
-                                               const float* __restrict__ bias_chunk, TOut* out) {
-  // 1) lane == row: write 8 float4 (columns 4q..4q+3) at swizzled slot q ^ (row & 7)
-#pragma unroll
-  for (int q = 0; q < 8; ++q)
-    stage[lane * 8 + (q ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                                     __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-  __syncwarp();
-  // 2) lane -> (row = it*4 + lane/8, columns 4*(lane%8)..+3)
-  const int qq = lane & 7, rsub = lane >> 3;
-  const int col = col0 + 4 * qq;
-  const bool col_ok = col < N;
-  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ep.bias) bias4 = *reinterpret_cast<const float4*>(bias_chunk + 4 * qq);  // shared memory
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int rr = it * 4 + rsub;
-    const int64_t row = row0 + rr;
-    float4 v = stage[rr * 8 + (qq ^ (rr & 7))];
-    v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-    if (ep.act == LCASR_ACT_GELU_TANH) {
-      float* pv = reinterpret_cast<float*>(&v);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float x = pv[i];
-        const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-        pv[i] = 0.5f * x * (1.0f + tanh_approx(u));
-      }
-    } else if (ep.act == LCASR_ACT_SILU) {
-      float* pv = reinterpret_cast<float*>(&v);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) pv[i] = __fdividef(pv[i], 1.0f + __expf(-pv[i]));
-    }
-    if (ep.resid) {
-      v.x = fmaf(ep.alpha, v.x, res[it].x); v.y = fmaf(ep.alpha, v.y, res[it].y);
-      v.z = fmaf(ep.alpha, v.z, res[it].z); v.w = fmaf(ep.alpha, v.w, res[it].w);
-    }
-    if (row < M && col_ok && ep.debug != 3) {  // (3: profiling — everything but the fp32 stores)
-      if constexpr (sizeof(TOut) == 4) {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row * N + col) = v;
-      } else {
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
-        uint2 u;
-        u.x = *reinterpret_cast<uint32_t*>(&p0);
-        u.y = *reinterpret_cast<uint32_t*>(&p1);
-        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(out) + row * N + col) = u;
-      }
-    }
-  }
-  __syncwarp();  // the staging tile is reused by the next chunk
 }
 
 // bf16 outputs through TMA stores.  Measured on the 768 -> 3072 GELU GEMM: main loop alone 1520 TFLOP/s, + TMEM loads
@@ -390,7 +317,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("bar.sync 1, %0;" ::"n"(32 * NEW) : "memory");  // the epilogue warps only
       }
       const int64_t row0 = m_idx + lane_base;
-      // (a two-chunk-deep prefetch ring was measured neutral — 43.4 vs 43.2 us on 16384x768x768 — and spills at 168 registers)
       // fp32: this warp's two boxes alternate per chunk.  Chunk c's residual is requested one chunk ahead (at tile start for
       // the first one), as soon as the box's previous bulk store has been read out.
       const uint32_t box0 = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES + (warp - 2) * 8192;

@@ -169,3 +169,47 @@ def test_train_mode_host_contract(cuda_device):
     with torch.no_grad():
         model.train()
         assert not model(x)["final_posteriors"].requires_grad
+
+
+def test_training_step_is_reproducible(cuda_device):
+    """Two executions of the same step — the second while unrelated kernels share the GPU, as NCCL all-reduces do in a
+    data-parallel run — give bit-identical intermediates of the backward (CTC gradient, residual-stream gradients,
+    conv-module gradients) and parameter gradients that agree to 1e-6 (split-K / column-sum atomics are leaves).
+    Guards the fixed-point CTC accumulation and the fp64 cross-CTA BatchRenorm sums."""
+    import lcasr_b200
+    from lcasr_b200.training import TrainEngine
+    cfg = O.make_config(n_layers=2, d_model=256, n_heads=2, head_dim=128, subsampling_conv_channels=64, vocab_size=255)
+    sd = O.synth_state_dict(cfg, seed=1)
+    x = O.synth_input(2, 1024, 80, seed=100).to(cuda_device)
+    tgt, tl = O.synth_targets(2, O.calc_length(1024), vocab=255, seed=7)
+    ctc = lcasr_b200.CTCLoss(blank=255, reduction="sum")
+    junk = torch.randn(16 << 20, device=cuda_device)
+    side = torch.cuda.Stream(device=cuda_device)
+
+    def run(perturb):
+        m = lcasr_b200.SCConformerXL(**cfg)
+        m.load_state_dict(sd, strict=True)
+        m = m.to(cuda_device).train()
+        m._train_engine = TrainEngine(m)
+        m._train_engine.trace = []
+        out = m(x)
+        loss = ctc(out["final_posteriors"].transpose(0, 1), tgt, out["length"], tl)
+        if perturb:
+            with torch.cuda.stream(side):
+                for _ in range(100):
+                    junk.mul_(1.0000001)
+        loss.backward()
+        torch.cuda.synchronize()
+        grads = torch.cat([p.grad.reshape(-1) for p in m.parameters() if p.grad is not None])
+        return out["final_posteriors"].detach().clone(), m._train_engine.trace, grads
+
+    lp0, tr0, g0 = run(False)
+    for perturb in (False, True, True):
+        lp1, tr1, g1 = run(perturb)
+        assert torch.equal(lp0, lp1), "train-mode forward must be bit-reproducible"
+        assert len(tr0) == len(tr1) and len(tr0) >= 8
+        for (name, a), (_, b) in zip(tr0, tr1):
+            assert torch.equal(a, b), f"backward intermediate '{name}' differs between two runs of the same step"
+        rel = (g0 - g1).norm().item() / g0.norm().item()
+        report(test="train_step_reproducible", perturbed=perturb, param_grad_rel=rel)
+        assert rel < 1e-6
