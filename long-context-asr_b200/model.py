@@ -253,6 +253,9 @@ class SCConformerXL(nn.Module):
         # opt-in: replay the ~135 launches of an equal-length eval forward as ONE CUDA graph per (B, T) — for
         # launch-bound shapes (10-s contexts: 1.97 ms of launches for ~0.4 ms of kernels)
         self.cuda_graphs = False
+        # eval() mode WITH gradients (test-time adaptation, lcasr/eval/dynamic_eval.py:47-100): opt-in, because a plain
+        # model(x) in eval mode outside torch.no_grad() should keep taking the fused inference call
+        self.grad_in_eval = False
         self._graphs: Dict = {}
         self.graph_launches_replayed = 0  # kernels launched through graph replays (they bypass lcasr_launch_count)
 
@@ -420,8 +423,10 @@ class SCConformerXL(nn.Module):
         """Same signature and result as the reference (sconformer_xl.py:162-252).  ``model.eval()``: one fused
         inference call (no autograd graph).  ``model.train()``: the training path (training.py) — BatchRenorm uses
         batch statistics and updates its running buffers, and ``final_posteriors`` carries a grad_fn whose
-        backward is the hand-written backward pass, so ``loss.backward()`` fills ``.grad`` of every parameter."""
-        if self.training:
+        backward is the hand-written backward pass, so ``loss.backward()`` fills ``.grad`` of every parameter.
+        ``model.eval()`` with ``model.grad_in_eval = True`` and gradients enabled: the same autograd node with
+        BatchRenorm in its eval form (running statistics, buffers untouched) — dynamic_eval.py's adaptation step."""
+        if self.training or (self.grad_in_eval and torch.is_grad_enabled()):
             return self._forward_train(audio_signal, length, cached_kvs, cached_kv_lengths, return_logits)
         return self._forward_eval(audio_signal, length, cached_kvs, cached_kv_lengths, return_logits)
 
@@ -435,8 +440,6 @@ class SCConformerXL(nn.Module):
             raise ValueError(f"audio_signal must be [B, {self.feat_in}, T], got {tuple(audio_signal.shape)}")
         if self.compute_dtype != torch.bfloat16:
             raise NotImplementedError("the training path computes in bf16 (the reference trains under bf16 autocast)")
-        if return_logits:
-            raise NotImplementedError("return_logits=True is an inference option (decoder.py:26-27)")
         if self.layers[0].attend.fn.left_window >= 0 or self.layers[0].attend.fn.right_window >= 0:
             raise NotImplementedError("windowed attention is an evaluation mode (eval/run.py:38-43); training uses full attention")
         B, _, T = audio_signal.shape
@@ -449,7 +452,8 @@ class SCConformerXL(nn.Module):
             if max(tok_lens) != int(L.lib.lcasr_out_length(T)):  # same rule as the evaluation path (shape clash in the reference)
                 raise ValueError("the longest recording must span the padded batch (length.max() == T up to the 8x rounding)")
         masked = tok_lens if (tok_lens is not None and min(tok_lens) != max(tok_lens)) else None  # sconformer_xl.py:204-205
-        lp = train_forward(self, audio_signal.detach().to(torch.float32).contiguous(), masked)
+        lp = train_forward(self, audio_signal.detach().to(torch.float32).contiguous(), masked, brn_eval=not self.training,
+                           return_logits=bool(return_logits))
         N = lp.shape[1]
         out_len = torch.full((B,), N, dtype=torch.int32, device=audio_signal.device) if tok_lens is None else \
             torch.tensor(tok_lens, dtype=torch.int32, device=audio_signal.device)

@@ -291,8 +291,10 @@ def affine_silu(c, A, Bc):
     return out
 
 
-def brn_silu_bwd(c, dy, A, Bc, stats, weight, dweight, dbias):
-    """backward of y = silu(BatchRenorm_train(c)): returns dc (bf16); dweight, dbias (fp32) accumulate."""
+def brn_silu_bwd(c, dy, A, Bc, stats, weight, dweight, dbias, eval_mode: bool = False):
+    """backward of y = silu(BatchRenorm(c)): returns dc (bf16); dweight, dbias (fp32) accumulate.
+    eval_mode: the statistics are the running buffers (constants): dc = dz * weight / running_std, without the
+    mean / variance terms of the batch-statistics form."""
     _cuda(c, dy, A, Bc, stats, weight, dweight, dbias)
     d = c.shape[-1]
     M = c.numel() // d
@@ -303,6 +305,8 @@ def brn_silu_bwd(c, dy, A, Bc, stats, weight, dweight, dbias):
     coef = torch.empty(3, d, dtype=torch.float32, device=c.device)
     L.call("lcasr_brn_bwd_finalize", L.ptr(S[0]), L.ptr(S[1]), M, d, L.ptr(weight), L.ptr(stats), L.ptr(dweight),
            L.ptr(dbias), L.ptr(coef), _s())
+    if eval_mode:
+        coef[1:].zero_()
     dc = torch.empty_like(c)
     L.call("lcasr_affine3", L.ptr(dz), L.ptr(c), M, d, L.ptr(coef), L.ptr(dc), _s())
     return dc

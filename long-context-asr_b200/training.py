@@ -173,11 +173,13 @@ class TrainEngine:
         bn._nbt_ver = bn.num_batches_tracked._version
 
     # ---- forward -----------------------------------------------------------------------------------------
-    def forward(self, spec: torch.Tensor, save: bool = True, tok_lens=None):
+    def forward(self, spec: torch.Tensor, save: bool = True, tok_lens=None, brn_eval: bool = False, return_logits: bool = False):
         """spec [B,F,T] fp32 -> (log-probs [B,N,V1] fp32, argmax int32 [B,N], ctx for backward or None).
         tok_lens (host ints, valid tokens per recording, or None): the padded-batch path of sconformer_xl.py:204-215 —
         key-padding mask and zeroed rows in attention (attention.py:511,541), zeroed GLU output in the conv module
-        (convolution.py:107-110); BatchRenorm statistics still cover every position, as in the reference."""
+        (convolution.py:107-110); BatchRenorm statistics still cover every position, as in the reference.
+        brn_eval: eval()-mode BatchRenorm (running statistics, batchrenorm.py:86-91; nothing is updated) with the graph kept
+        for the backward (dynamic_eval.py).  return_logits: stop before the log-softmax (decoder.py:26-27)."""
         m = self.m
         dev = spec.device
         B, Fdim, Tn = spec.shape
@@ -242,14 +244,20 @@ class TrainEngine:
                     a = ln(x, q + "conv_norm")
                     u = ops.gemm(a, P[q + "pw1_w"], bias=P[q + "pw1_b"])
                     g = ops.glu(u) if lens_dev is None else T.glu_masked(u, lens_dev, B, N)
-                    c, sums = T.dwconv1d_fwd(g.view(B, N, d), P[q + "dw_w"], P[q + "dw_b"], stats=True)
-                    rmax, dmax = self.brn_clamps(bn)
-                    A, Bc, stats = T.brn_train_stats(sums, M, bn.running_mean, bn.running_std, bn.eps, rmax, dmax, bn.momentum,
-                                                     P[q + "brn_w"], P[q + "brn_b"])
-                    self.brn_tick(bn)
+                    c, sums = T.dwconv1d_fwd(g.view(B, N, d), P[q + "dw_w"], P[q + "dw_b"], stats=not brn_eval)
+                    if brn_eval:  # (c - running_mean) / running_std * weight + bias as the affine c*A + Bc; the backward reads
+                        rm, rs = bn.running_mean.float(), bn.running_std.float()   # stats = mu, sigma, r = 1, d = 0, s = 0
+                        A = (P[q + "brn_w"] / rs).contiguous()
+                        Bc = (P[q + "brn_b"] - rm * A).contiguous()
+                        stats = torch.stack([rm, rs, torch.ones_like(rm), torch.zeros_like(rm), torch.zeros_like(rm)]).contiguous()
+                    else:
+                        rmax, dmax = self.brn_clamps(bn)
+                        A, Bc, stats = T.brn_train_stats(sums, M, bn.running_mean, bn.running_std, bn.eps, rmax, dmax, bn.momentum,
+                                                         P[q + "brn_w"], P[q + "brn_b"])
+                        self.brn_tick(bn)
                     y = T.affine_silu(c, A, Bc)
                     xn = ops.gemm(y.view(M, d), P[q + "pw2_w"], bias=P[q + "pw2_b"], resid=x, alpha=1.0)
-                    R[ff] = dict(x=x, a=a, u=u, g=g, c=c, A=A, Bc=Bc, stats=stats, y=y)
+                    R[ff] = dict(x=x, a=a, u=u, g=g, c=c, A=A, Bc=Bc, stats=stats, y=y, brn_eval=brn_eval)
                 x = xn
             R["x_pre_out"] = x
             x = ln(x, q + "norm_out", f32=True)
@@ -269,6 +277,9 @@ class TrainEngine:
         a = ln(x, "dec_norm") if m.decoder_norm else T.scale_cast(x, 1.0)
         S["a_dec"] = a
         lp = ops.gemm(a, P["dec_ff_w"], bias=P["dec_ff_b"], out_dtype=torch.float32)
+        S["logits_out"] = return_logits
+        if return_logits:
+            return lp.view(B, N, V1), None, (S if save else None)
         am = ops.log_softmax_argmax_(lp)  # in place: logits -> log-probs
         S["lp"] = lp
         return lp.view(B, N, V1), am.view(B, N), (S if save else None)
@@ -302,7 +313,7 @@ class TrainEngine:
             return T.dgrad(dy, P[wk], **kw) if need_dx else None
 
         dlp = dlp.contiguous().view(M, V1).to(torch.float32)
-        dl = T.log_softmax_bwd(S["lp"], dlp)                          # [M,V1] bf16
+        dl = T.scale_cast(dlp, 1.0) if S.get("logits_out") else T.log_softmax_bwd(S["lp"], dlp)   # [M,V1] bf16
         if trace is not None:
             trace += [("dlp (CTC gradient)", dlp.clone()), ("dl (log-softmax backward, bf16)", dl.clone())]
         da = linear_bwd(dl, S["a_dec"], "dec_ff_w", "dec_ff_b")
@@ -345,7 +356,7 @@ class TrainEngine:
                     dy = dy_next
                     dyy = linear_bwd(dy, r["y"].view(M, d), q + "pw2_w", q + "pw2_b")
                     dc = T.brn_silu_bwd(r["c"], dyy.view(B, N, d), r["A"], r["Bc"], r["stats"], P[q + "brn_w"], G[q + "brn_w"],
-                                        G[q + "brn_b"])
+                                        G[q + "brn_b"], eval_mode=r["brn_eval"])
                     if trace is not None:
                         trace += [(f"{q}conv dy (bf16)", dy.clone()), (f"{q}conv dyy (bf16)", dyy.clone()), (f"{q}conv dc (bf16)", dc.clone())]
                     T.dwconv1d_bwd_weight_(r["g"].view(B, N, d), dc, G[q + "dw_w"], G[q + "dw_b"])
@@ -420,9 +431,9 @@ class _EncoderFn(torch.autograd.Function):
     """log_probs = f(spec; parameters): forward / backward are TrainEngine.forward / backward."""
 
     @staticmethod
-    def forward(ctx, engine: TrainEngine, spec: torch.Tensor, tok_lens, *params):
+    def forward(ctx, engine: TrainEngine, spec: torch.Tensor, tok_lens, brn_eval, return_logits, *params):
         with torch.no_grad():
-            lp, am, S = engine.forward(spec, save=True, tok_lens=tok_lens)
+            lp, am, S = engine.forward(spec, save=True, tok_lens=tok_lens, brn_eval=brn_eval, return_logits=return_logits)
         ctx.engine, ctx.S = engine, S
         ctx.names = [n for n, _ in engine.m.named_parameters()]
         engine.m.last_argmax = am
@@ -435,16 +446,16 @@ class _EncoderFn(torch.autograd.Function):
             raise RuntimeError("lcasr_b200: backward through the encoder a second time (activations were freed)")
         with torch.no_grad():
             grads = ctx.engine.backward(S, dlp)
-        return (None, None, None) + tuple(grads.get(n) for n in ctx.names)
+        return (None, None, None, None, None) + tuple(grads.get(n) for n in ctx.names)
 
 
-def train_forward(model, audio_signal: torch.Tensor, tok_lens=None) -> torch.Tensor:
+def train_forward(model, audio_signal: torch.Tensor, tok_lens=None, brn_eval: bool = False, return_logits: bool = False) -> torch.Tensor:
     if getattr(model, "_train_engine", None) is None:
         model._train_engine = TrainEngine(model)
     eng = model._train_engine
     params = [p for _, p in model.named_parameters()]
     if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-        return _EncoderFn.apply(eng, audio_signal, tok_lens, *params)
-    lp, am, _ = eng.forward(audio_signal, save=False, tok_lens=tok_lens)
+        return _EncoderFn.apply(eng, audio_signal, tok_lens, brn_eval, return_logits, *params)
+    lp, am, _ = eng.forward(audio_signal, save=False, tok_lens=tok_lens, brn_eval=brn_eval, return_logits=return_logits)
     model.last_argmax = am
     return lp

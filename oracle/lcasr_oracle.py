@@ -176,6 +176,17 @@ def synth_state_dict(cfg: dict, seed: int = 12345, peak: float = 1.0) -> Dict[st
     return out
 
 
+def perturb_running_stats(sd: Dict[str, Tensor], seed: int = 5) -> Dict[str, Tensor]:
+    """BatchRenorm running statistics away from their initial (0, 1), in place, so that eval-mode tests depend on them"""
+    g = torch.Generator().manual_seed(seed)
+    for k in list(sd):
+        if k.endswith("running_mean"):
+            sd[k] = 0.2 * torch.randn(sd[k].shape, generator=g)
+        if k.endswith("running_std"):
+            sd[k] = 0.6 + 0.8 * torch.rand(sd[k].shape, generator=g)
+    return sd
+
+
 def synth_input(batch: int, frames: int, feat_in: int = 80, seed: int = 1234, rho: float = 0.9) -> Tensor:
     """Standardised synthetic spectrogram [B, feat_in, T] (audio_tools.py:56 normalises per bin):
     unit-variance Gaussian noise, AR(1)-smoothed along time (coefficient rho) like real features."""
@@ -495,17 +506,22 @@ def ctc_grad(log_probs, targets, input_lengths, target_lengths, blank: int) -> n
 # training step (exp/train.py:236-262): forward in train mode, CTC loss (sum), backward
 # --------------------------------------------------------------------------------------------
 
-def training_step(sd: Dict[str, Tensor], cfg: dict, x: Tensor, targets: Tensor, target_lengths: Tensor, lengths=None):
+def training_step(sd: Dict[str, Tensor], cfg: dict, x: Tensor, targets: Tensor, target_lengths: Tensor, lengths=None,
+                  train: bool = True, return_logits: bool = False):
     """loss = CTCLoss(blank=V, reduction='sum')(log_probs.transpose(0,1), targets, length, target_lengths)
     (exp/train.py:104,249) of the train-mode forward, and d loss / d parameter for every floating-point
     parameter of `sd` (buffers excluded).  `lengths` (frames per recording): the padded-batch path of
     exp/train.py:236-241 (pad masks in attention and the conv module; BatchRenorm statistics still run over every
-    position).  Returns (loss float, {name: grad}, {buffer name: new running stat}, log-probs)."""
+    position).  train=False: the model stays in eval() mode while gradients flow — test-time adaptation,
+    lcasr/eval/dynamic_eval.py:47-100 (BatchRenorm uses its running statistics, no buffer changes); return_logits=True
+    (dynamic_eval.py:217): the network returns logits and the loss is taken on their log-softmax.
+    Returns (loss float, {name: grad}, {buffer name: new running stat}, log-probs or logits)."""
     buffers = ("running_mean", "running_std", "num_batches_tracked", "inv_freq", "rotary_interpolation_factor")
     leaves = {k: (v.detach().clone().float().requires_grad_(True) if not k.endswith(buffers) else v) for k, v in sd.items()}
     new_stats: Dict[str, Tensor] = {}
-    lp, length = encoder_forward(leaves, cfg, x, train=True, new_stats=new_stats, lengths=lengths)
-    loss = F.ctc_loss(lp.transpose(0, 1), targets, length.long(), target_lengths, blank=cfg["vocab_size"], reduction="sum")
+    lp, length = encoder_forward(leaves, cfg, x, return_logits=return_logits, train=train, new_stats=new_stats, lengths=lengths)
+    lsm = F.log_softmax(lp, dim=-1) if return_logits else lp
+    loss = F.ctc_loss(lsm.transpose(0, 1), targets, length.long(), target_lengths, blank=cfg["vocab_size"], reduction="sum")
     loss.backward()
     grads = {k: v.grad for k, v in leaves.items() if isinstance(v, Tensor) and v.requires_grad and v.grad is not None}
     return float(loss.detach()), grads, new_stats, lp.detach()

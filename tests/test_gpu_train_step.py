@@ -19,7 +19,8 @@ from oracle import lcasr_oracle as O
 
 pytestmark = pytest.mark.gpu
 TRAIN_CASES = ["train_tiny_dh32", "train_tiny_dh128_nbt", "train_rms_nosc_bias",
-               "train_ragged_dh32", "train_ragged_dh128"]  # the last two: padded batches (length=a_lengths, exp/train.py:236-241)
+               "train_ragged_dh32", "train_ragged_dh128",  # padded batches (length=a_lengths, exp/train.py:236-241)
+               "train_evalmode_dh32", "train_evalmode_logits_dh128"]  # eval() mode with gradients (dynamic_eval.py:47-100, :217)
 
 
 def _load(name):
@@ -36,9 +37,13 @@ def _setup(g, device):
     for k in sd:
         if k.endswith("num_batches_tracked"):
             sd[k] = torch.tensor(int(g["nbt"]), dtype=torch.long)
+    eval_mode = bool(g["eval_mode"]) if "eval_mode" in g else False
+    if eval_mode:
+        O.perturb_running_stats(sd, seed=5)
     model = lcasr_b200.SCConformerXL(**cfg, compute_dtype="bf16")
     model.load_state_dict(sd, strict=True)
-    model = model.to(device).train()
+    model = model.to(device).train(not eval_mode)
+    model.grad_in_eval = eval_mode  # opt-in: eval-mode forward that keeps the graph (test-time adaptation)
     x = O.synth_input(int(g["batch"]), int(g["frames"]), cfg["feat_in"], seed=int(g["input_seed"]))
     return model, cfg, sd, x
 
@@ -51,7 +56,9 @@ def test_training_step_matches_reference_golden(cuda_device, name):
     V = cfg["vocab_size"]
     frame_lengths = g["frame_lengths"].tolist() if "frame_lengths" in g else []
     length = torch.tensor(frame_lengths, device=cuda_device) if frame_lengths else None
-    out = model(audio_signal=x.to(cuda_device), length=length)
+    eval_mode = bool(g["eval_mode"]) if "eval_mode" in g else False
+    ret_logits = bool(g["return_logits"]) if "return_logits" in g else False
+    out = model(audio_signal=x.to(cuda_device), length=length, return_logits=ret_logits)
     lp = out["final_posteriors"]
     assert lp.requires_grad and lp.grad_fn is not None
     assert out["length"].cpu().tolist() == g["length"].tolist()
@@ -64,7 +71,8 @@ def test_training_step_matches_reference_golden(cuda_device, name):
     tgt, tl = O.synth_targets(int(g["batch"]), N, vocab=V, frac=0.3, seed=int(g["target_seed"]))
     if "target_lengths" in g:
         tl = torch.from_numpy(g["target_lengths"])
-    loss = lcasr_b200.CTCLoss(blank=V, reduction="sum")(lp.transpose(0, 1), tgt, out["length"], tl).sum()
+    lsm = torch.log_softmax(lp, dim=-1) if ret_logits else lp  # dynamic_eval.py:218 applies its own softmax to the logits
+    loss = lcasr_b200.CTCLoss(blank=V, reduction="sum")(lsm.transpose(0, 1), tgt, out["length"], tl).sum()
     loss.backward()
     rel_loss = abs(loss.item() - float(g["loss"])) / abs(float(g["loss"]))
     report(test="train_step_loss", case=name, rel=rel_loss, logp_max_abs=err)
@@ -105,7 +113,7 @@ def test_training_step_matches_reference_golden(cuda_device, name):
         assert (sd_after[n].cpu() - ref).abs().max().item() < 2e-3, n
     for k, v in sd_after.items():
         if k.endswith("num_batches_tracked"):
-            assert int(v) == int(g["nbt"]) + 1
+            assert int(v) == int(g["nbt"]) + (0 if eval_mode else 1)  # eval mode leaves the buffers alone
 
 
 def test_training_step_midsize_against_oracle(cuda_device):
