@@ -25,18 +25,14 @@ class SpecAugment(torch.nn.Module):
     def __init__(self, n_time_masks: int, n_freq_masks: int, freq_mask_param: int, iid_masks: bool = True,
                  time_mask_param: int = -1, min_p: float = -1, max_p: float = 1.0, zero_masking: bool = False, **kwargs) -> None:
         super().__init__()
-        if n_time_masks != 0:
-            assert (min_p != -1 or time_mask_param != -1), "Either min_p or n_time_masks must be set o:"
-        assert min_p == -1 or (min_p >= 0 and min_p <= 1), "min_p must be within range [0.0, 1.0]"
-        assert max_p >= 0 and max_p <= 1, "max_p must be within range [0.0, 1.0]"
-        self.n_time_masks = n_time_masks
-        self.time_mask_param = time_mask_param
-        self.n_freq_masks = n_freq_masks
-        self.freq_mask_param = freq_mask_param
-        self.iid_masks = iid_masks
-        self.max_p = max_p
-        self.zero_masking = zero_masking
-        self.min_p = min_p
+        # the same argument checks as the reference constructor (augmentation.py:49-51)
+        assert n_time_masks == 0 or min_p != -1 or time_mask_param != -1, "time masks need a width: give time_mask_param or min_p"
+        assert min_p == -1 or 0 <= min_p <= 1, f"min_p={min_p} is not a proportion in [0, 1]"
+        assert 0 <= max_p <= 1, f"max_p={max_p} is not a proportion in [0, 1]"
+        self.n_time_masks, self.n_freq_masks = n_time_masks, n_freq_masks
+        self.time_mask_param, self.freq_mask_param = time_mask_param, freq_mask_param
+        self.min_p, self.max_p = min_p, max_p
+        self.iid_masks, self.zero_masking = iid_masks, zero_masking
 
     def mask_params(self, f: int, t: int):
         """effective (time, freq) mask parameters for a [.., f, t] input (augmentation.py:79-82 + torchaudio's max_p limit)"""
