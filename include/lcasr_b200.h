@@ -333,7 +333,8 @@ int lcasr_subsample_dwconv_bwd_weight(const void* in, const void* dout, int B, i
                                       float* dw, float* db, void* stream);
 int lcasr_subsample_conv0_bwd(const float* spec, const float* w, const float* b, const void* ds1, int B, int F,
                               int64_t T, int C, float* dw, float* db, void* stream);
-/* Fused backward of conv0 + SiLU + the first depthwise level (C % 64 == 0): from the spectrogram and
+/* Fused backward of conv0 + SiLU + the first depthwise level (subsampling.py:277-296: Conv2d(1->C,3x3,s2), SiLU,
+ * depthwise Conv2d(3x3,s2); autograd in the reference), C % 64 == 0: from the spectrogram and
  * dd1 = dL/d(depthwise-1 output) [B,T2,F2,C] (bf16) accumulate (+=) the gradients of conv0 w [C,9] / b [C] and of the
  * depthwise w [C,9] / b [C].  The conv0 activation and its gradient are recomputed / consumed on chip: together with
  * lcasr_subsample_conv0_dw in the forward, the 160x-expanded [B,T/2,40,C] tensor never exists in HBM. */

@@ -76,6 +76,20 @@ def test_no_cpu_fallback():
         lcasr_b200.CTCLoss(blank=127)(torch.randn(5, 1, 128), torch.zeros(1, 2, dtype=torch.long), torch.tensor([5]), torch.tensor([2]))
 
 
+def test_eval_mode_with_gradients_is_opt_in_and_cuda_only():
+    """dynamic_eval.py-style adaptation: model.grad_in_eval routes an eval()-mode call to the autograd path; like every other
+    path it refuses CPU tensors instead of falling back"""
+    import lcasr_b200
+    m = lcasr_b200.SCConformerXL(vocab_size=127, n_layers=1, d_model=64, n_heads=2, head_dim=32, subsampling_conv_channels=32).eval()
+    assert m.grad_in_eval is False
+    m.grad_in_eval = True
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(1, 80, 64), return_logits=True)
+    with torch.no_grad():  # without gradients the fused inference call is taken (and refuses CPU tensors the same way)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            m(torch.randn(1, 80, 64))
+
+
 def test_param_groups_follow_reference_rule():
     import lcasr_b200
     m = lcasr_b200.SCConformerXL(vocab_size=127, n_layers=1, d_model=64, n_heads=2, head_dim=32, subsampling_conv_channels=32,
