@@ -184,6 +184,17 @@ def check(status: int, what: str = "") -> None:
         raise LcasrError(f"lcasr_b200 {what} failed (status {status}): {msg}")
 
 
+# Parameters can change behind PyTorch's version counters: the MADGRAD / BatchRenorm kernels write through raw pointers and
+# `p.data.mul_()` (the reference's optimizer) does not bump `p._version` either.  Everything that may have changed weights
+# (a training-mode forward, an optimizer step of this package) bumps this epoch; SCConformerXL re-packs its eval weights
+# when it moved.  Callers that edit `.data` by hand (an EMA swap) call `model.invalidate_packed_weights()`.
+WEIGHT_EPOCH = [0]
+
+
+def bump_weight_epoch() -> None:
+    WEIGHT_EPOCH[0] += 1
+
+
 # Optional per-entry-point device timing (bench.py's kernel breakdown of the Python-orchestrated training step):
 # set TIMING = {} to collect {name: [(start_event, end_event), ...]} on the current stream; None = off.
 TIMING = None

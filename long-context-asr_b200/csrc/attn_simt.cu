@@ -158,10 +158,11 @@ template <typename T, int DH>
 static int launch_attn_simt(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len, int H, int vt, int64_t Npad,
                             void* out, cudaStream_t st, int wl, int wr) {
   size_t smem = sizeof(float) * (2 * SA_BQ * (DH + 1) + SA_BK * DH + SA_BQ * (SA_BK + 1) + 3 * SA_BQ);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  int attr_dev = 0;
+  if (attr_set.needs_set(&attr_dev)) {
     LCASR_CUDA(cudaFuncSetAttribute(attn_simt_kernel<T, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set.mark(attr_dev);
   }
   dim3 grid((unsigned)ceil_div(N, SA_BQ), H, B);
   float scale = 1.0f / sqrtf((float)DH);

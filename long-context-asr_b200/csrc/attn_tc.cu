@@ -771,10 +771,11 @@ static int launch_attn_tc2(const void* q, const void* k, const void* v, int B, i
   LCASR_TRY(make_tmap_2d_bf16(&tmQ, q, (uint64_t)B * N, d, d * 2, 2 * FA_BQ, Cfg::SUB_COLS, sw));
   LCASR_TRY(make_tmap_2d_bf16(&tmK, k, (uint64_t)B * Nk, d, d * 2, FA_BK, Cfg::SUB_COLS, sw));
   LCASR_TRY(make_tmap_2d_bf16(&tmV, v, (uint64_t)B * Nk, d, d * 2, FA_BK, Cfg::SUB_COLS, sw));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  int attr_dev = 0;
+  if (attr_set.needs_set(&attr_dev)) {
     LCASR_CUDA(cudaFuncSetAttribute(attn_tc2_kernel<DH, POLY, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
-    attr_set = true;
+    attr_set.mark(attr_dev);
   }
   dim3 grid((unsigned)ceil_div(N, 2 * FA_BQ), (unsigned)H, (unsigned)B);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)DH);
@@ -810,10 +811,11 @@ static int launch_attn_tc(const void* q, const void* k, const void* v, int B, in
   LCASR_TRY(make_tmap_2d_bf16(&tmK, k, (uint64_t)B * N, d, d * 2, FA_BK, Cfg::SUB_COLS, sw));
   if (VT) LCASR_TRY(make_tmap_2d_bf16(&tmV, v, (uint64_t)B * H * DH, (uint64_t)Npad, (uint64_t)Npad * 2, DH, 64, CU_TENSOR_MAP_SWIZZLE_128B));
   else LCASR_TRY(make_tmap_2d_bf16(&tmV, v, (uint64_t)B * N, d, d * 2, FA_BK, Cfg::SUB_COLS, sw));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  int attr_dev = 0;
+  if (attr_set.needs_set(&attr_dev)) {
     LCASR_CUDA(cudaFuncSetAttribute(attn_tc_kernel<DH, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_set.mark(attr_dev);
   }
   dim3 grid((unsigned)ceil_div(N, FA_BQ), (unsigned)H, (unsigned)B);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)DH);

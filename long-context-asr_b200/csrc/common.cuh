@@ -48,6 +48,18 @@ inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_or
 
 using bf16 = __nv_bfloat16;
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember it per (call site, device), not per process
+struct PerDeviceFlag {
+  std::atomic<bool> done[64] = {};
+  bool needs_set(int* dev_out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    *dev_out = dev;
+    return dev < 0 || dev >= 64 || !done[dev].load(std::memory_order_acquire);
+  }
+  void mark(int dev) { if (dev >= 0 && dev < 64) done[dev].store(true, std::memory_order_release); }
+};
+
 constexpr int kNumSMs = 148;
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -420,10 +420,8 @@ static int launch_rec(const float* lp, int B, int64_t N, int V, const int64_t* t
                       const int64_t* tl, int blank, int dir, float* nll, float* store, int nt, cudaStream_t st,
                       float* store_beta = nullptr, int pregathered = 0) {
   size_t smem = (size_t)2 * SPT * nt * sizeof(float);
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
+    if (smem > 48 * 1024) {  // per device and size-dependent: set on every call (cheap)
     LCASR_CUDA(cudaFuncSetAttribute(ctc_recursion_kernel<SPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
   }
   ctc_recursion_kernel<SPT><<<dir == 0 ? 2 * B : B, nt, smem, st>>>(lp, N, V, tg, S_max, il, tl, blank, dir, nll, store,
                                                                     store_beta, B, pregathered);
@@ -498,10 +496,8 @@ extern "C" int lcasr_ctc_loss_bwd(const float* log_probs, int B, int64_t N, int 
   LCASR_TRY(ctc_recursion(log_probs, B, N, V, targets, S_max, input_lengths, target_lengths, blank, -1, nullptr,
                           beta_ws, st));
   size_t smem = (size_t)V * sizeof(unsigned long long);
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
+    if (smem > 48 * 1024) {  // per device and size-dependent: set on every call (cheap)
     LCASR_CUDA(cudaFuncSetAttribute(ctc_grad_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
   }
   LCASR_CHECK_ARG(B <= 65535, "ctc_loss_bwd: batch too large");
   dim3 grid((unsigned)N, (unsigned)B);
@@ -536,10 +532,8 @@ extern "C" int lcasr_ctc_loss_grad(const float* log_probs, int B, int64_t N, int
   LCASR_CHECK_ARG((size_t)V * 4 <= 200 * 1024, "ctc_loss_grad: V=%d too large", V);
   cudaStream_t st = (cudaStream_t)stream;
   size_t smem = (size_t)V * sizeof(unsigned long long);
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
+    if (smem > 48 * 1024) {  // per device and size-dependent: set on every call (cheap)
     LCASR_CUDA(cudaFuncSetAttribute(ctc_grad_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
   }
   dim3 grid((unsigned)N, (unsigned)B);
   ctc_grad_collect_kernel<<<grid, 256, smem, st>>>(log_probs, N, V, targets, S_max, input_lengths, target_lengths, blank,

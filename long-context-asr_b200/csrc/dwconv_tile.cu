@@ -231,10 +231,11 @@ static int dt_launch_ks(const DtParams& p, int B, cudaStream_t st) {
   constexpr size_t red_bytes = MODE == DT_BWD_WEIGHT ? (size_t)8 * 4 * (KS + 1) * 32 * 4 : (MODE == DT_FWD ? 8 * 8 * 32 * 4 : 0);
   constexpr size_t smem = tile_bytes > red_bytes ? tile_bytes : red_bytes;
   static_assert(smem <= 100 * 1024, "dwconv1d tile: shared memory");
-  static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) {
+  static PerDeviceFlag attr_set;
+  int attr_dev = 0;
+  if (attr_set.needs_set(&attr_dev) && smem > 48 * 1024) {
     LCASR_CUDA(cudaFuncSetAttribute(dwconv1d_tile_kernel<KS, MODE, TPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set.mark(attr_dev);
   }
   const int64_t ntiles = ceil_div(p.N, TT);
   const int slabs = p.d / kDtCS;

@@ -485,10 +485,11 @@ static int launch_tc(const void* A, const void* W, int64_t M, int N, int K, cons
     if (ep.pre_out)
       LCASR_TRY(make_tmap_2d_bf16(&tmC2, ep.pre_out, (uint64_t)M, (uint64_t)N, (uint64_t)N * 2, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  int attr_dev = 0;
+  if (attr_set.needs_set(&attr_dev)) {
     LCASR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TOut, CG, W8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_set.mark(attr_dev);
   }
   const int64_t tiles = ceil_div(M, CG * TG_BM) * ceil_div(N, BN);
   const int64_t units = kNumSMs / CG;  // CTAs (CG == 1) or CTA pairs: one per SM / per TPC, persistent

@@ -621,11 +621,12 @@ static int launch_tcx(const lcasr_gemm_ex_args& g, const TxParams& p, cudaStream
   CUtensorMap tmC = tmA;  // placeholder for fp32 outputs (never dereferenced)
   if (sizeof(TOut) == 2)
     LCASR_TRY(make_tmap_4d(&tmC, g.out, (uint64_t)g.M, (uint64_t)g.N, g.ldo, g.nb1, g.so1, g.nb2, g.so2, 32, 64));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  int attr_dev = 0;
+  if (attr_set.needs_set(&attr_dev)) {
     LCASR_CUDA(cudaFuncSetAttribute(gemm_tcx_kernel<BN, A_MN, B_MN, TOut, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_set.mark(attr_dev);
   }
   const int64_t tiles = ceil_div(g.M, CG * TX_BM) * ceil_div(g.N, BN) * p.ksplit * g.nb1 * g.nb2;
   const int64_t units = kNumSMs / CG;
@@ -744,10 +745,11 @@ extern "C" int lcasr_attention_bwd_pds(const void* q, const void* k, const void*
   CUtensorMap tmP, tmDS;
   LCASR_TRY(make_tmap_4d(&tmP, P, (uint64_t)N, (uint64_t)N, Np, H, N * Np, nb, (int64_t)H * N * Np, 32, 64));
   LCASR_TRY(make_tmap_4d(&tmDS, dS, (uint64_t)N, (uint64_t)N, Np, H, N * Np, nb, (int64_t)H * N * Np, 32, 64));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  int attr_dev = 0;
+  if (attr_set.needs_set(&attr_dev)) {
     LCASR_CUDA(cudaFuncSetAttribute(attn_bwd_pds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PDS_SMEM));
-    attr_set = true;
+    attr_set.mark(attr_dev);
   }
   PdsParams p;
   p.N = N; p.Dh = Dh; p.Nst = (int)Np; p.H = H; p.nbatch = nb;

@@ -289,10 +289,11 @@ static int launch_fused(const float* spec, const float* w0, const float* b0, con
   const size_t smem = (((size_t)(2 * (2 * TT2 + 1) + 1) * FWp * 4 + 15) & ~(size_t)15) + (size_t)(2 * TT2 + 1) * (F1 + 2) * 32 * 4;
   LCASR_CHECK_ARG(smem <= 110 * 1024, "subsample_conv0_dw: feat_in=%d too large for the fused tile", F);
   LCASR_CHECK_ARG(ceil_div(T2, TT2) <= 0x7fffffff && B <= 65535, "subsample_conv0_dw: grid too large");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  int attr_dev = 0;
+  if (attr_set.needs_set(&attr_dev)) {
     LCASR_CUDA(cudaFuncSetAttribute(subsample_conv0_dw_fused_kernel<TT2, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-    attr_set = true;
+    attr_set.mark(attr_dev);
   }
   dim3 grid((unsigned)ceil_div(T2, TT2), (unsigned)(C / kFuCG), (unsigned)B);
   subsample_conv0_dw_fused_kernel<TT2, MINB><<<grid, 256, smem, st>>>(spec, w0, b0, w1, b1, F, T, C, T1, F1, T2, F2, (bf16*)out);

@@ -301,7 +301,12 @@ class SCConformerXL(nn.Module):
             L.call("lcasr_model_set_impl", self._handle, gemm, attn)
 
     def _state_key(self):
-        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers())) + (self.compute_dtype,)
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers())) + \
+            (self.compute_dtype, L.WEIGHT_EPOCH[0])
+
+    def invalidate_packed_weights(self):
+        """call after editing parameters through `.data` / raw pointers outside this package (version counters do not move)"""
+        self._pack_key = None
 
     def _destroy(self):
         if self._handle is not None:
@@ -452,6 +457,7 @@ class SCConformerXL(nn.Module):
             if max(tok_lens) != int(L.lib.lcasr_out_length(T)):  # same rule as the evaluation path (shape clash in the reference)
                 raise ValueError("the longest recording must span the padded batch (length.max() == T up to the 8x rounding)")
         masked = tok_lens if (tok_lens is not None and min(tok_lens) != max(tok_lens)) else None  # sconformer_xl.py:204-205
+        L.bump_weight_epoch()  # a training / adaptation step follows: the packed eval weights are stale from here on
         lp = train_forward(self, audio_signal.detach().to(torch.float32).contiguous(), masked, brn_eval=not self.training,
                            return_logits=bool(return_logits))
         N = lp.shape[1]

@@ -33,8 +33,11 @@ class _Table:
         self.chunk_index = torch.tensor(ci, dtype=torch.int32, device=device)
         self.host = torch.zeros(len(params), 6, dtype=torch.int64).pin_memory()
         self.dev = torch.zeros(len(params), 6, dtype=torch.int64, device=device)
+        self._copied = None  # event after the last H2D copy of the pinned table
 
     def fill(self, state=None):
+        if self._copied is not None:  # the previous step's copy may still be reading the pinned table
+            self._copied.synchronize()
         a = self.host.numpy()
         for t, p in enumerate(self.params):
             g = p.grad
@@ -48,6 +51,9 @@ class _Table:
                 a[t, 4] = st["x0"].data_ptr() if "x0" in st else 0
             a[t, 5] = p.numel()
         self.dev.copy_(self.host, non_blocking=True)
+        if self._copied is None:
+            self._copied = torch.cuda.Event()
+        self._copied.record()
         return self.dev
 
 
@@ -161,6 +167,7 @@ class MADGRAD(torch.optim.Optimizer):
                    int(bool(group.get("decouple_decay", False))), st)
         self.state["k"] += 1
         self._k_host += 1
+        L.bump_weight_epoch()  # parameters were written through raw pointers: packed eval copies are stale
         return loss
 
     def load_state_dict(self, state_dict):

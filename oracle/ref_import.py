@@ -17,7 +17,11 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("LCASR_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# search order: explicit env, the read-only checkout of the build container, then the pip-installed UNMODIFIED copy under
+# baseline/_ref (git-ignored, shipped to the GPU box by gpurun: `pip install --no-deps --target baseline/_ref /root/reference`)
+_CANDIDATES = [os.environ.get("LCASR_REFERENCE_ROOT"), "/root/reference", os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+REFERENCE_ROOT = next((c for c in _CANDIDATES if c and os.path.isdir(os.path.join(c, "lcasr"))), "/root/reference")
 
 _STUB_ROOTS = {"librosa", "omegaconf", "causal_conv1d", "mamba_ssm", "lming", "jiwer",
                "pyctcdecode", "whisper", "wandb", "flashfftconv_stub_never"}

@@ -23,10 +23,13 @@ def load_golden(name):
     g = {k: z[k] for k in z.files}
     g["config"] = json.loads(str(g["config"]))
     g["greedy"] = [json.loads(s) for s in g["greedy"].tolist()]
-    g["state_dict_shapes"] = json.loads(str(g["state_dict_shapes"]))
-    for k in ("batch", "frames", "weight_seed", "input_seed", "target_seed"):
-        g[k] = int(g[k])
-    g["peak"] = float(g["peak"])
+    if "state_dict_shapes" in g:
+        g["state_dict_shapes"] = json.loads(str(g["state_dict_shapes"]))
+    for k in ("batch", "frames", "weight_seed", "input_seed", "target_seed", "init_seed"):
+        if k in g:
+            g[k] = int(g[k])
+    if "peak" in g:
+        g["peak"] = float(g["peak"])
     g["frame_lengths"] = g["frame_lengths"].tolist() if "frame_lengths" in g else [g["frames"]] * g["batch"]
     return g
 

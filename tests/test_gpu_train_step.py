@@ -221,3 +221,40 @@ def test_training_step_is_reproducible(cuda_device):
         rel = (g0 - g1).norm().item() / g0.norm().item()
         report(test="train_step_reproducible", perturbed=perturb, param_grad_rel=rel)
         assert rel < 1e-6
+
+
+@pytest.mark.parametrize("which_opt", ["lcasr", "data_edit"])
+def test_eval_after_parameter_update_uses_the_new_weights(cuda_device, which_opt):
+    """The packed eval weights must follow parameter updates that bypass PyTorch's version counters: the device MADGRAD
+    step (raw pointers) and `.data` edits + `invalidate_packed_weights()`.  eval -> adapt (grad_in_eval) -> eval."""
+    import lcasr_b200
+    cfg = O.make_config(n_layers=2, d_model=128, n_heads=1, head_dim=128, subsampling_conv_channels=64, vocab_size=255)
+    sd = O.synth_state_dict(cfg, seed=3)
+    model = lcasr_b200.SCConformerXL(**cfg, compute_dtype="bf16")
+    model.load_state_dict(sd, strict=True)
+    model = model.to(cuda_device).eval()
+    x = O.synth_input(1, 520, seed=4).to(cuda_device)
+    with torch.no_grad():
+        before = model(x)["final_posteriors"].clone()
+    if which_opt == "lcasr":
+        model.grad_in_eval = True
+        opt = lcasr_b200.optim.MADGRAD(model.parameters(), lr=1e-2)
+        out = model(x)
+        tgt, tl = O.synth_targets(1, out["final_posteriors"].shape[1], vocab=255)
+        loss = lcasr_b200.CTCLoss(blank=255, reduction="sum")(out["final_posteriors"].transpose(0, 1), tgt, out["length"], tl).sum()
+        loss.backward()
+        opt.step()
+    else:
+        with torch.no_grad():
+            for p in model.parameters():
+                p.data.mul_(1.05)  # leaves p._version untouched
+        model.invalidate_packed_weights()
+    with torch.no_grad():
+        after = model(x)["final_posteriors"].clone()
+    assert (after - before).abs().max().item() > 1e-3, "eval forward still runs the stale packed weights"
+    fresh = lcasr_b200.SCConformerXL(**cfg, compute_dtype="bf16")
+    fresh.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()}, strict=True)
+    fresh = fresh.to(cuda_device).eval()
+    with torch.no_grad():
+        want = fresh(x)["final_posteriors"]
+    assert torch.equal(after, want), "eval after the update differs from a freshly built model with the same state_dict"
