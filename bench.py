@@ -263,6 +263,117 @@ def cpu_reference_train(cfg, B, T, budget_s):
     return Bs * T / 100.0 / per, per, Bs, cores, kind
 
 
+def seqpar_bench(mkey, T, dtype, steps, dev, rank, world, comm, dist):
+    """ONE recording across `world` ranks (BASELINE configs 3 / 4: sequence-parallel ring attention): the native driver
+    (lcasr_model_forward_seqpar: K/V blocks as NCCL P2P transfers in ring order overlapped with attention, neighbour halo
+    exchange) against the single-GPU forward of the same recording on the same rank.  Device-timed, max over ranks."""
+    import torch
+    import lcasr_b200
+    from lcasr_b200 import seqpar
+    from oracle import lcasr_oracle as O
+    cfg = O.make_config(**O.BASELINE_MODELS[mkey])
+    sd = default_init_state_dict(cfg)
+    model = lcasr_b200.SCConformerXL(**cfg, compute_dtype=dtype)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+    x = O.synth_input(1, T, cfg["feat_in"], seed=1234).to(dev)  # every rank holds the recording, reads only its slice
+    V = cfg["vocab_size"]
+
+    def timed(fn, k):
+        for _ in range(3):
+            fn()
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / k], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sp_step():
+        lp, am, blk = seqpar.forward_sequence_parallel_native(model, x, comm)
+        return lp, am, blk, lcasr_b200.ops.greedy_collapse(am.view(1, -1), V)
+
+    def single_step():
+        out = model(x)
+        return out, lcasr_b200.ops.greedy_collapse(model.last_argmax, V)
+
+    ms_sp = timed(sp_step, steps)
+    ms_1 = timed(single_step, steps)
+    lp, am, (s0, e0_), _ = sp_step()
+    out1, _ = single_step()
+    err = (lp - out1["final_posteriors"][0, s0:e0_]).abs().max()
+    agree = (am == model.last_argmax[0]).float().mean()
+    stats = torch.stack([err.double(), (1.0 - agree).double()])
+    dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    audio_s = T / 100.0
+    del model
+    torch.cuda.empty_cache()
+    return {"model": mkey, "frames": T, "tokens": T // 8, "ranks": world, "ms_per_step": ms_sp, "ms_single_gpu": ms_1,
+            "speedup_vs_single_gpu": ms_1 / ms_sp, "efficiency": ms_1 / ms_sp / world, "audio_s_per_s": audio_s / (ms_sp / 1e3),
+            "max_abs_vs_single_gpu": float(stats[0].item()), "argmax_disagree_frac_vs_single_gpu": float(stats[1].item()),
+            "what": "forward + log-softmax + greedy decode of ONE recording; tokens split into contiguous blocks; per layer the K/V "
+                    "blocks move as ncclSend/ncclRecv pairs in ring order on a side stream while the tcgen05 attention kernel runs "
+                    "on the blocks already present (exact fp32 merge of the per-block partials); conv-module halo rows to/from the "
+                    "two neighbours; one C-ABI call per rank and step"}
+
+
+def dp_train_bench(steps, dev, rank, world, dist):
+    """BASELINE config 5 under data parallelism: batch 8 per GPU, gradients all-reduced (averaged) per layer inside backward over
+    NCCL; weak-scaling efficiency = the same rank's step WITHOUT the all-reduce / the data-parallel step."""
+    import torch
+    import lcasr_b200
+    from lcasr_b200.training import TrainEngine
+    from oracle import lcasr_oracle as O
+    mkey, T, B = WORKLOADS["cfg5"]
+    cfg = O.make_config(**O.BASELINE_MODELS[mkey])
+    N, V = O.calc_length(T), cfg["vocab_size"]
+    model = lcasr_b200.SCConformerXL(**cfg, compute_dtype="bf16")
+    model.load_state_dict(default_init_state_dict(cfg), strict=True)
+    model = model.to(dev).train()
+    model._train_engine = TrainEngine(model)
+    ctc = lcasr_b200.CTCLoss(blank=V, reduction="sum")
+    x = O.synth_input(B, T, cfg["feat_in"], seed=1234 + rank).to(dev)
+    tgt, tl = O.synth_targets(B, N, vocab=V, frac=0.3, seed=99 + rank)
+    tgt, tl = tgt.to(dev), tl.to(dev)
+
+    def step():
+        out = model(audio_signal=x, length=None)
+        loss = ctc(out["final_posteriors"].transpose(0, 1), tgt, out["length"], tl).sum()
+        for p_ in model.parameters():
+            p_.grad = None
+        loss.backward()
+
+    def timed(k):
+        for _ in range(3):
+            step()
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            step()
+        e1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / k], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    model._train_engine.dp_group = None
+    ms_local = timed(steps)
+    model._train_engine.dp_group = dist.group.WORLD
+    ms_dp = timed(steps)
+    del model
+    torch.cuda.empty_cache()
+    audio_s = B * T / 100.0
+    return {"model": mkey, "frames": T, "batch_per_gpu": B, "ranks": world, "ms_per_step": ms_dp, "ms_per_step_without_allreduce": ms_local,
+            "weak_scaling_efficiency": ms_local / ms_dp, "audio_s_per_s": world * audio_s / (ms_dp / 1e3),
+            "what": "training step (train-mode forward + CTC loss + hand-written backward) with the per-layer asynchronous NCCL "
+                    "all-reduce of the flat gradient buffer inside backward"}
+
+
 def train_bench(args, cfg, mkey, T, B, rank, world, local):
     """cfg 5: the training step through the drop-in classes exactly as exp/train.py:236-262 drives them."""
     import torch
@@ -420,6 +531,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="override context length in 10 ms frames")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-multi-gpu-extras", action="store_true", help="N > 1: skip the sequence-parallel and data-parallel-training objects")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
     args = ap.parse_args()
 
@@ -560,6 +672,19 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
     e2e_value = world * audio_s / e2e_s
 
+    # ---- N > 1: the two paths that actually communicate (the headline above is N independent recordings) ----
+    multi = {}
+    if world > 1 and not args.no_multi_gpu_extras:
+        from lcasr_b200 import seqpar as _sp
+        del model
+        torch.cuda.empty_cache()
+        comm = _sp.NativeComm()
+        k = max(2, min(args.steps, 5))
+        multi["seqpar"] = {"cfg3": seqpar_bench("cfg3_6L768D24H", 131072, args.dtype, k, dev, rank, world, comm, dist),
+                           "cfg4": seqpar_bench("cfg4_3L2048D16H", 360000, args.dtype, max(2, k // 2), dev, rank, world, comm, dist)}
+        comm.close()
+        multi["dp_train"] = dp_train_bench(k, dev, rank, world, dist)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -595,6 +720,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
                     "d2h_bytes_per_step": int(B * N * 4 + B * 4 + (4 if with_ctc else 0)), "ms_per_step": e2e_s * 1e3},
             "gpu_launches": launches, "roofline": roofline, "kernels": kern}
+    line.update(multi)
 
     if not args.no_cpu_baseline and world == 1:
         r = cpu_reference_run(cfg, sd, B, T, 1, 0, args.cpu_budget_s)

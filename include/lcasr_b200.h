@@ -476,6 +476,51 @@ int lcasr_model_transcribe_host(lcasr_model* m, const float* spec_host, int B, i
 /* workspace bytes lcasr_model_transcribe_host needs (forward workspace + input/token staging) */
 int64_t lcasr_model_transcribe_workspace_bytes(const lcasr_model* m, int B, int64_t T);
 
+/* ------------------------------------------------------------------------------------------
+ * Sequence-parallel forward (BASELINE configs 3 and 4): ONE recording, its tokens split into
+ * `world` contiguous blocks, one per rank (one process per GPU).  The reference has no multi-GPU path
+ * (single GPU, exp/gn.sh:5); what these replace is SCConformerXL.forward (sconformer_xl.py:162-252) for
+ * contexts whose attention (attention.py:509-551) is worth spreading over an NVLink domain.
+ * ---------------------------------------------------------------------------------------- */
+
+/* One (query block x key block) term of attention: out32 [B,Nq,H*Dh] fp32 = softmax over THIS key block only,
+ * lse [B,H,Nq] fp32 = log2-domain log-sum-exp of its scaled scores (bf16 operands, tcgen05 kernel). */
+int lcasr_attention_partial(const void* q, const void* k, const void* v, int B, int64_t Nq, int64_t Nk, int H, int Dh,
+                            float* out32, float* lse, void* stream);
+/* Exact combination of P such terms (parts [P][rows,H*Dh], lses [P][H,rows], rows = B*Nq with B == 1):
+ * out = sum_s 2^(lse_s - L) parts_s, L = log2 sum_s 2^lse_s — softmax over the union of the key blocks. */
+int lcasr_attention_merge(const float* parts, const float* lses, int P, int64_t rows, int H, int Dh, void* out,
+                          int out_dtype, void* stream);
+
+/* NCCL communicator owned by this library (NCCL is bound at run time: dlopen of the libnccl.so.2 already mapped
+ * by the host process, or `nccl_path`).  Rank 0 calls lcasr_comm_unique_id (128 bytes, host) and distributes the
+ * id by its own means (torch.distributed broadcast in the Python host); every rank then calls lcasr_comm_create
+ * (collective).  The communicator also owns the side streams of the sequence-parallel forward. */
+typedef struct lcasr_comm lcasr_comm;
+int lcasr_comm_unique_id(char* id_out_host, const char* nccl_path_or_null);
+int lcasr_comm_create(const char* id_host, int rank, int world, const char* nccl_path_or_null, lcasr_comm** out);
+void lcasr_comm_destroy(lcasr_comm* c);
+
+/* token block [start, start+n) of `rank` for a T-frame recording (T % 8 == 0), and the per-rank workspace */
+int lcasr_model_seqpar_block(const lcasr_model* m, int world, int rank, int64_t T, int64_t* start_tok, int64_t* n_tok);
+int64_t lcasr_model_seqpar_workspace_bytes(const lcasr_model* m, int world, int rank, int64_t T);
+
+/* One rank of the forward.  spec_full [1,feat_in,T] fp32 (only this rank's slice + 8 frames of left context are
+ * read); out_local [n_rank, num_classes] fp32; argmax_full [T/8] int32 or NULL (ids of the WHOLE recording on
+ * every rank, for the greedy collapse).  K/V blocks move as ncclSend/ncclRecv pairs in ring order on a side
+ * stream while attention runs on the blocks already present; the conv module exchanges (k-1)/2 halo rows with
+ * the two neighbours.  Asynchronous on `stream`. */
+int lcasr_model_forward_seqpar(lcasr_model* m, lcasr_comm* comm, const float* spec_full, int64_t T, float* out_local,
+                               int32_t* argmax_full, int return_logits, void* workspace, int64_t workspace_bytes,
+                               void* stream);
+
+/* The same per-rank phases for all `world` ranks in ONE process on one GPU (device-to-device copies instead of
+ * NCCL transfers): the parity check that needs no second GPU.  out_full [T/8, num_classes]. */
+int64_t lcasr_model_seqpar_emulated_workspace_bytes(const lcasr_model* m, int world, int64_t T);
+int lcasr_model_forward_seqpar_emulated(lcasr_model* m, int world, const float* spec_full, int64_t T, float* out_full,
+                                        int32_t* argmax_full, int return_logits, void* workspace,
+                                        int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -138,6 +138,13 @@ _SIGNATURES = {
     "lcasr_model_forward": [vp, vp, i32, i64, vp, vp, i32, vp, i64, vp],
     "lcasr_model_forward_lengths": [vp, vp, i32, i64, vp, vp, vp, i32, vp, i64, vp],
     "lcasr_model_transcribe_host": [vp, vp, i32, i64, vp, vp, vp, vp, i64, vp],
+    "lcasr_attention_partial": [vp, vp, vp, i32, i64, i64, i32, i32, vp, vp, vp],
+    "lcasr_attention_merge": [vp, vp, i32, i64, i32, i32, vp, i32, vp],
+    "lcasr_comm_unique_id": [C.c_char_p, C.c_char_p],
+    "lcasr_comm_create": [C.c_char_p, i32, i32, C.c_char_p, C.POINTER(vp)],
+    "lcasr_model_seqpar_block": [vp, i32, i32, i64, C.POINTER(i64), C.POINTER(i64)],
+    "lcasr_model_forward_seqpar": [vp, vp, vp, i64, vp, vp, i32, vp, i64, vp],
+    "lcasr_model_forward_seqpar_emulated": [vp, i32, vp, i64, vp, vp, i32, vp, i64, vp],
 }
 _OTHER = {
     "lcasr_abi_version": ([], i32),
@@ -150,6 +157,9 @@ _OTHER = {
     "lcasr_model_destroy": ([vp], None),
     "lcasr_model_workspace_bytes": ([vp, i32, i64], i64),
     "lcasr_model_transcribe_workspace_bytes": ([vp, i32, i64], i64),
+    "lcasr_comm_destroy": ([vp], None),
+    "lcasr_model_seqpar_workspace_bytes": ([vp, i32, i32, i64], i64),
+    "lcasr_model_seqpar_emulated_workspace_bytes": ([vp, i32, i64], i64),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES) + tuple(_OTHER)
 

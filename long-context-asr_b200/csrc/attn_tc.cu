@@ -340,7 +340,10 @@ template <int DH, int POLY, bool WIN>  // WIN: local-attention instantiation (ke
 __global__ void __launch_bounds__(FA2_THREADS, 1)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, int64_t N, int64_t Nk, const int32_t* __restrict__ kv_len, int H,
-                float scale_log2, bf16* __restrict__ out, float* __restrict__ lse, int win_left, int win_right) {
+                float scale_log2, bf16* __restrict__ out, float* __restrict__ lse, int win_left, int win_right,
+                float* __restrict__ out32) {
+  // out32 (may be NULL; sequence-parallel partial results): the normalised output O / l is written as fp32 [B,N,H,Dh] there
+  // INSTEAD of bf16 to `out`; together with lse it is one term of the exact merge over key blocks (attn_merge_kernel)
   // win_left / win_right (-1 = unlimited; self-attention only): local attention, query i sees keys
   // [i - win_left, i + win_right] (flash-attn window_size, attention.py:466,527-530; eval/run.py:38-43).  Key tiles
   // outside the band of this CTA's 256 queries are never loaded; tiles crossing a band edge get an element mask.
@@ -735,7 +738,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     const float inv_l = 1.0f / l_run;
     const int64_t n = q0 + t * FA_BQ + row;
-    bf16* orow = out + ((b * N + n) * H + h) * DH;
+    const int64_t o_off = ((b * N + n) * H + h) * DH;
     if (lse && n < N) lse[(b * H + h) * N + n] = m_run + log2f(l_run);
 #pragma unroll
     for (int c = 0; c < DH / 32; ++c) {
@@ -748,7 +751,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           float y[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(o[g * 8 + i]) * inv_l;
-          Vec8<bf16>::store(orow + c * 32 + g * 8, y);
+          if (out32) Vec8<float>::store(out32 + o_off + c * 32 + g * 8, y);
+          else Vec8<bf16>::store(out + o_off + c * 32 + g * 8, y);
         }
       }
     }
@@ -763,14 +767,15 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 template <int DH, int POLY, bool WIN = false>
 static int launch_attn_tc2(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len,
-                           int H, void* out, float* lse, int wl, int wr, cudaStream_t st) {
+                           int H, void* out, float* lse, int wl, int wr, cudaStream_t st, float* out32, int64_t ldq, int64_t ldkv) {
   using Cfg = Fa2Cfg<DH, POLY == 16>;
   const uint64_t d = (uint64_t)H * DH;
   const CUtensorMapSwizzle sw = DH >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap tmQ, tmK, tmV;
-  LCASR_TRY(make_tmap_2d_bf16(&tmQ, q, (uint64_t)B * N, d, d * 2, 2 * FA_BQ, Cfg::SUB_COLS, sw));
-  LCASR_TRY(make_tmap_2d_bf16(&tmK, k, (uint64_t)B * Nk, d, d * 2, FA_BK, Cfg::SUB_COLS, sw));
-  LCASR_TRY(make_tmap_2d_bf16(&tmV, v, (uint64_t)B * Nk, d, d * 2, FA_BK, Cfg::SUB_COLS, sw));
+  // ldq / ldkv: row pitch in elements (>= H*DH): q, k, v may be column blocks of a wider row-major matrix (the qkv projection)
+  LCASR_TRY(make_tmap_2d_bf16(&tmQ, q, (uint64_t)B * N, d, (uint64_t)ldq * 2, 2 * FA_BQ, Cfg::SUB_COLS, sw));
+  LCASR_TRY(make_tmap_2d_bf16(&tmK, k, (uint64_t)B * Nk, d, (uint64_t)ldkv * 2, FA_BK, Cfg::SUB_COLS, sw));
+  LCASR_TRY(make_tmap_2d_bf16(&tmV, v, (uint64_t)B * Nk, d, (uint64_t)ldkv * 2, FA_BK, Cfg::SUB_COLS, sw));
   static PerDeviceFlag attr_set;
   int attr_dev = 0;
   if (attr_set.needs_set(&attr_dev)) {
@@ -779,7 +784,7 @@ static int launch_attn_tc2(const void* q, const void* k, const void* v, int B, i
   }
   dim3 grid((unsigned)ceil_div(N, 2 * FA_BQ), (unsigned)H, (unsigned)B);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)DH);
-  attn_tc2_kernel<DH, POLY, WIN><<<grid, FA2_THREADS, Cfg::SMEM_TOTAL, st>>>(tmQ, tmK, tmV, N, Nk, kv_len, H, scale_log2, (bf16*)out, lse, wl, wr);
+  attn_tc2_kernel<DH, POLY, WIN><<<grid, FA2_THREADS, Cfg::SMEM_TOTAL, st>>>(tmQ, tmK, tmV, N, Nk, kv_len, H, scale_log2, (bf16*)out, lse, wl, wr, out32);
   LCASR_LAUNCH_CHECK();
   return 0;
 }
@@ -825,7 +830,14 @@ static int launch_attn_tc(const void* q, const void* k, const void* v, int B, in
 }
 
 int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len, int H,
-                   int Dh, int v_transposed, int64_t Npad, void* out, float* lse, cudaStream_t st, int wl, int wr) {
+                   int Dh, int v_transposed, int64_t Npad, void* out, float* lse, cudaStream_t st, int wl, int wr, float* out32,
+                   int64_t ldq, int64_t ldkv) {
+  if (ldq <= 0) ldq = (int64_t)H * Dh;
+  if (ldkv <= 0) ldkv = (int64_t)H * Dh;
+  LCASR_CHECK_ARG(ldq % 8 == 0 && ldkv % 8 == 0 && ldq >= (int64_t)H * Dh && ldkv >= (int64_t)H * Dh, "attention(tcgen05): bad row pitch");
+  LCASR_CHECK_ARG((!out32 && ldq == (int64_t)H * Dh && ldkv == (int64_t)H * Dh) || (!v_transposed && wl < 0 && wr < 0),
+                  "attention(tcgen05): fp32 partial outputs / row pitches need the dense natural-layout kernel");
+  LCASR_CHECK_ARG(!out32 || lse, "attention(tcgen05): a partial result needs its log-sum-exp output");
   LCASR_CHECK_ARG((wl < 0 && wr < 0) || (!v_transposed && N == Nk), "attention(tcgen05): a window needs self-attention and the natural V layout");
   LCASR_CHECK_ARG(!lse || !v_transposed, "attention(tcgen05): the log-sum-exp output needs the natural V layout");
   LCASR_CHECK_ARG(!kv_len || !v_transposed, "attention(tcgen05): key lengths need the natural V layout");
@@ -842,16 +854,16 @@ int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N
 #define LCASR_FA(DHV)                                                                                             \
   case DHV:                                                                                                       \
     if (v_transposed) return launch_attn_tc<DHV, true>(q, k, v, B, N, H, Npad, out, st);                          \
-    if (wl >= 0 || wr >= 0) return launch_attn_tc2<DHV, 4, true>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                 \
-    if (force_v1 && Nk == N && !kv_len && !lse) return launch_attn_tc<DHV, false>(q, k, v, B, N, H, Npad, out, st);                  \
+    if (wl >= 0 || wr >= 0) return launch_attn_tc2<DHV, 4, true>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st, nullptr, ldq, ldkv);                 \
+    if (force_v1 && Nk == N && !kv_len && !lse && !out32 && ldq == (int64_t)H * Dh && ldkv == ldq) return launch_attn_tc<DHV, false>(q, k, v, B, N, H, Npad, out, st);                  \
     switch (poly) {                                                                                               \
-      case 0: return launch_attn_tc2<DHV, 0>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                                          \
-      case 1: return launch_attn_tc2<DHV, 1>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                                          \
-      case 2: return launch_attn_tc2<DHV, 2>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                                          \
-      case 8: return launch_attn_tc2<DHV, 8>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                                          \
-      case 9: return launch_attn_tc2<DHV, 9>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                                          \
-      case 16: return launch_attn_tc2<DHV, 16>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                                          \
-      default: return launch_attn_tc2<DHV, 4>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st);                                         \
+      case 0: return launch_attn_tc2<DHV, 0>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st, out32, ldq, ldkv);                                          \
+      case 1: return launch_attn_tc2<DHV, 1>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st, out32, ldq, ldkv);                                          \
+      case 2: return launch_attn_tc2<DHV, 2>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st, out32, ldq, ldkv);                                          \
+      case 8: return launch_attn_tc2<DHV, 8>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st, out32, ldq, ldkv);                                          \
+      case 9: return launch_attn_tc2<DHV, 9>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st, out32, ldq, ldkv);                                          \
+      case 16: return launch_attn_tc2<DHV, 16>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st, out32, ldq, ldkv);                                          \
+      default: return launch_attn_tc2<DHV, 4>(q, k, v, B, N, Nk, kv_len, H, out, lse, wl, wr, st, out32, ldq, ldkv);                                         \
     }
   switch (Dh) {
     LCASR_FA(32) LCASR_FA(64) LCASR_FA(128)

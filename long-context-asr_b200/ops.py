@@ -231,3 +231,22 @@ def ctc_loss_grad(log_probs, targets, input_lengths, target_lengths, blank: int,
     L.call("lcasr_ctc_loss_grad", L.ptr(log_probs), B, N, V, L.ptr(targets), S, L.ptr(input_lengths), L.ptr(target_lengths),
            int(blank), L.ptr(nll), L.ptr(grad_nll), L.ptr(alpha), L.ptr(beta), L.ptr(grad), _s())
     return grad
+
+
+def attention_partial(q, k, v):
+    """one (query block x key block) term: (normalised fp32 output [B,Nq,H*Dh], log2-domain log-sum-exp [B,H,Nq])"""
+    _cuda(q, k, v)
+    B, Nq, H, Dh = q.shape
+    out = torch.empty(B, Nq, H * Dh, dtype=torch.float32, device=q.device)
+    lse = torch.empty(B, H, Nq, dtype=torch.float32, device=q.device)
+    L.call("lcasr_attention_partial", L.ptr(q), L.ptr(k), L.ptr(v), B, Nq, k.shape[1], H, Dh, L.ptr(out), L.ptr(lse), _s())
+    return out, lse
+
+
+def attention_merge(parts, lses, H: int, Dh: int, out_dtype=torch.bfloat16):
+    """parts [P, rows, H*Dh] fp32, lses [P, H, rows] fp32 -> softmax over the union of the key blocks, [rows, H*Dh]"""
+    _cuda(parts, lses)
+    P, rows, d = parts.shape
+    out = torch.empty(rows, d, dtype=out_dtype, device=parts.device)
+    L.call("lcasr_attention_merge", L.ptr(parts), L.ptr(lses), P, rows, H, Dh, L.ptr(out), L.dtype_code(out_dtype), _s())
+    return out

@@ -217,3 +217,102 @@ def forward_sequence_parallel(model, spec: torch.Tensor, comm, return_logits: bo
         outs.append(logits); ams.append(am)
     am_full = None if return_logits else comm.all_gather_cat(ams, sizes)[0]
     return [(o, a, blocks[r]) for o, a, r in zip(outs, ams, comm.local_ranks)], am_full
+
+
+# ------------------------------------------------------------------------------------------------------
+# Native driver (csrc/seqpar.cu): the whole per-rank forward is ONE C-ABI call; K/V blocks travel as NCCL
+# point-to-point transfers in ring order on a side stream while attention runs on the blocks already present
+# (exact merge of per-block partial results), neighbour-only halo exchange, argmax ids exchanged at the end.
+# The Python driver above stays as the readable statement of the algorithm (and runs under gloo on CPU-only hosts).
+# ------------------------------------------------------------------------------------------------------
+import ctypes as _C
+import os as _os
+
+
+def _nccl_path() -> bytes:
+    cand = _os.path.join(_os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so.2")
+    return _os.path.abspath(cand).encode() if _os.path.exists(cand) else b""
+
+
+class NativeComm:
+    """NCCL communicator owned by liblcasr_b200.so, bootstrapped over an existing torch.distributed group
+    (rank 0 creates the NCCL unique id, a broadcast distributes it; one process per GPU)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        buf = _C.create_string_buffer(128)
+        if self.rank == 0:
+            L.call("lcasr_comm_unique_id", buf, _nccl_path())
+        backend = dist.get_backend(group)
+        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        t = t.to(dev) if backend == "nccl" else t
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        idb = bytes(t.cpu().numpy().tobytes())
+        h = L.vp()
+        torch.cuda.synchronize()
+        L.call("lcasr_comm_create", idb, self.rank, self.world, _nccl_path(), _C.byref(h))
+        self._h = h.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.lib.lcasr_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _sp_buffers(model, key, nbytes, device):
+    cache = model.__dict__.setdefault("_sp_ws", {})
+    ws = cache.get(key)
+    if ws is None or ws.numel() < nbytes or ws.device != device:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        cache[key] = ws
+    return ws
+
+
+@torch.no_grad()
+def forward_sequence_parallel_native(model, spec: torch.Tensor, comm: NativeComm, return_logits: bool = False):
+    """This rank's share of SCConformerXL.forward for ONE recording.  spec [1, feat_in, T] fp32 CUDA (the whole recording
+    on every rank; only the rank's slice is read), T % 8 == 0.  Returns (log-probs [n_rank, V1] fp32, argmax ids of the
+    WHOLE recording [N] int32 (None with return_logits), (start_tok, end_tok))."""
+    assert spec.dim() == 3 and spec.shape[0] == 1 and spec.is_cuda and spec.dtype == torch.float32 and spec.is_contiguous()
+    T = spec.shape[-1]
+    device = spec.device
+    model._ensure_built(device)
+    s, n = L.i64(), L.i64()
+    L.call("lcasr_model_seqpar_block", model._handle, comm.world, comm.rank, T, _C.byref(s), _C.byref(n))
+    V1 = model.decoder.num_classes
+    out = torch.empty(n.value, V1, dtype=torch.float32, device=device)
+    am = None if return_logits else torch.empty(T // 8, dtype=torch.int32, device=device)
+    nbytes = int(L.lib.lcasr_model_seqpar_workspace_bytes(model._handle, comm.world, comm.rank, T))
+    ws = _sp_buffers(model, ("native", comm.world, comm.rank, T), nbytes, device)
+    L.call("lcasr_model_forward_seqpar", model._handle, comm._h, L.ptr(spec), T, L.ptr(out), L.ptr(am), int(return_logits),
+           L.ptr(ws), ws.numel(), L.current_stream())
+    return out, am, (s.value, s.value + n.value)
+
+
+@torch.no_grad()
+def forward_sequence_parallel_emulated(model, spec: torch.Tensor, world: int, return_logits: bool = False):
+    """All `world` ranks of the native driver in this process on one GPU (copies instead of NCCL): (log-probs [N, V1],
+    argmax [N])."""
+    assert spec.dim() == 3 and spec.shape[0] == 1 and spec.is_cuda and spec.dtype == torch.float32 and spec.is_contiguous()
+    T = spec.shape[-1]
+    device = spec.device
+    model._ensure_built(device)
+    V1 = model.decoder.num_classes
+    out = torch.empty(T // 8, V1, dtype=torch.float32, device=device)
+    am = None if return_logits else torch.empty(T // 8, dtype=torch.int32, device=device)
+    nbytes = int(L.lib.lcasr_model_seqpar_emulated_workspace_bytes(model._handle, world, T))
+    if nbytes < 0:
+        raise L.LcasrError(f"sequence-parallel plan rejected: {L.lib.lcasr_last_error().decode()}")
+    ws = _sp_buffers(model, ("emulated", world, T), nbytes, device)
+    L.call("lcasr_model_forward_seqpar_emulated", model._handle, world, L.ptr(spec), T, L.ptr(out), L.ptr(am), int(return_logits),
+           L.ptr(ws), ws.numel(), L.current_stream())
+    return out, am

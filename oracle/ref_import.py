@@ -1,9 +1,10 @@
 """TEST INFRASTRUCTURE ONLY — loads the *unmodified* reference (robflynnyh/long-context-asr)
 from /root/reference so the oracle restatement can be pinned against it.
 
-This only works inside the build container (``/root/reference`` does not exist on the GPU box);
-it is used by ``oracle/make_golden.py`` to generate ``tests/golden/*.npz`` and by CPU tests that
-skip when the reference tree is absent.  Nothing under ``long-context-asr_b200/`` may import this.
+Search order: ``$LCASR_REFERENCE_ROOT``, ``/root/reference`` (build container only), ``baseline/_ref`` (the pip-installed
+unmodified copy that travels to the GPU box; ``bench.py --impl reference`` and its ``cpu_baseline`` leg time it there).
+It is used by ``oracle/make_golden*.py`` to generate ``tests/golden/*.npz`` and by CPU tests that skip when no reference
+tree is found.  Nothing under ``long-context-asr_b200/`` may import this.
 
 ``lcasr/__init__.py:1-6`` eagerly imports every sub-package, which drags in packages that are not in
 this image (librosa, omegaconf, causal_conv1d, mamba_ssm, lming, ...).  We register empty stub
@@ -76,8 +77,10 @@ def load_reference():
         sys.meta_path.append(_Finder())
         sys.path.insert(0, REFERENCE_ROOT)
         _installed = True
+    import contextlib
     import warnings
-    with warnings.catch_warnings():
+    # the reference print()s install hints on import (fused_dense.py:16-30): keep them off stdout (bench.py prints ONE line)
+    with warnings.catch_warnings(), contextlib.redirect_stdout(sys.stderr):
         warnings.simplefilter("ignore")
         from lcasr.models.sconformer_xl import SCConformerXL  # noqa: E402
         from lcasr.decoding.greedy import GreedyCTCDecoder  # noqa: E402
