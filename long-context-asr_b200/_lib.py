@@ -138,6 +138,9 @@ _SIGNATURES = {
     "lcasr_model_forward": [vp, vp, i32, i64, vp, vp, i32, vp, i64, vp],
     "lcasr_model_forward_lengths": [vp, vp, i32, i64, vp, vp, vp, i32, vp, i64, vp],
     "lcasr_model_transcribe_host": [vp, vp, i32, i64, vp, vp, vp, vp, i64, vp],
+    "lcasr_ctc_loss_fwd_ws": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp, i64, vp],
+    "lcasr_ctc_loss_bwd_ws": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, vp],
+    "lcasr_ctc_loss_fwd_ab_ws": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp, vp, i64, vp],
     "lcasr_attention_partial": [vp, vp, vp, i32, i64, i64, i32, i32, vp, vp, vp],
     "lcasr_attention_merge": [vp, vp, i32, i64, i32, i32, vp, i32, vp],
     "lcasr_comm_unique_id": [C.c_char_p, C.c_char_p],
@@ -158,6 +161,7 @@ _OTHER = {
     "lcasr_model_workspace_bytes": ([vp, i32, i64], i64),
     "lcasr_model_transcribe_workspace_bytes": ([vp, i32, i64], i64),
     "lcasr_comm_destroy": ([vp], None),
+    "lcasr_ctc_workspace_bytes": ([i32, i64, i64, i32], i64),
     "lcasr_model_seqpar_workspace_bytes": ([vp, i32, i32, i64], i64),
     "lcasr_model_seqpar_emulated_workspace_bytes": ([vp, i32, i64], i64),
 }

@@ -540,7 +540,7 @@ static int wf_chunks(int units, int64_t Lp_max) {
 
 int64_t ctc_wavefront_workspace_bytes(int units, int64_t N, int64_t Lp_max) {
   const int G = wf_chunks(units, Lp_max);
-  if (!G) return 0;
+  if (G < 2) return 0;  // one chunk per lattice: the plain one-CTA recursion is the same thing
   return (int64_t)units * G * N * 2 * 4 + 256 + (int64_t)units * G * 4;
 }
 
@@ -650,8 +650,15 @@ static int launch_rec(const float* lp, int B, int64_t N, int V, const int64_t* t
 
 static int ctc_recursion(const float* lp, int B, int64_t N, int V, const int64_t* tg, int64_t S_max, const int32_t* il,
                          const int64_t* tl, int blank, int dir, float* nll, float* store, cudaStream_t st,
-                         float* store_beta = nullptr, int pregathered = 0) {
+                         float* store_beta = nullptr, int pregathered = 0, void* workspace = nullptr, int64_t workspace_bytes = 0) {
   const int64_t Lp = 2 * S_max + 1;
+  static const bool no_wavefront = getenv("LCASR_CTC_NO_WAVEFRONT") != nullptr;  // A/B switch
+  if (workspace && !no_wavefront) {  // time-skewed wavefront over the whole GPU whenever a lattice can be cut into >= 2 chunks
+    const int units = dir == 0 ? 2 * B : B;
+    if (wf_chunks(units, Lp) >= 2)
+      return launch_wavefront(lp, B, N, V, tg, S_max, il, tl, blank, dir, nll, store, store_beta, pregathered, workspace,
+                              workspace_bytes, st);
+  }
   LCASR_CHECK_ARG(dir != 0 || Lp <= 4096, "ctc_loss: the concurrent alpha/beta form covers up to 4096 extended states");
   static const bool no_cluster = getenv("LCASR_CTC_NO_CLUSTER") != nullptr;  // A/B switch for profiling
   if (Lp > 4096 && !no_cluster) {  // spread the states over a cluster of up to 8 SMs (below that the cluster
@@ -691,19 +698,45 @@ static int ctc_recursion(const float* lp, int B, int64_t N, int V, const int64_t
 
 using namespace lcasr;
 
-extern "C" int lcasr_ctc_loss_fwd(const float* log_probs, int B, int64_t N, int V, const int64_t* targets,
-                                  int64_t S_max, const int32_t* input_lengths, const int64_t* target_lengths,
-                                  int blank, float* nll, float* alpha_ws, void* stream) {
+extern "C" int64_t lcasr_ctc_workspace_bytes(int B, int64_t N, int64_t S_max, int both_directions) {
+  if (B <= 0 || N <= 0 || S_max < 0) return -1;
+  return ctc_wavefront_workspace_bytes(both_directions ? 2 * B : B, N, 2 * S_max + 1);
+}
+
+extern "C" int lcasr_ctc_loss_fwd_ws(const float* log_probs, int B, int64_t N, int V, const int64_t* targets,
+                                     int64_t S_max, const int32_t* input_lengths, const int64_t* target_lengths,
+                                     int blank, float* nll, float* alpha_ws, void* workspace, int64_t workspace_bytes,
+                                     void* stream) {
   LCASR_CHECK_ARG(log_probs && targets && target_lengths && nll, "ctc_loss_fwd: NULL argument");
   LCASR_CHECK_ARG(B > 0 && N > 0 && V > 1 && S_max >= 0 && blank >= 0 && blank < V, "ctc_loss_fwd: bad shape");
   return ctc_recursion(log_probs, B, N, V, targets, S_max, input_lengths, target_lengths, blank, +1, nll, alpha_ws,
-                       (cudaStream_t)stream);
+                       (cudaStream_t)stream, nullptr, 0, workspace, workspace_bytes);
 }
+
+extern "C" int lcasr_ctc_loss_fwd(const float* log_probs, int B, int64_t N, int V, const int64_t* targets,
+                                  int64_t S_max, const int32_t* input_lengths, const int64_t* target_lengths,
+                                  int blank, float* nll, float* alpha_ws, void* stream) {
+  return lcasr_ctc_loss_fwd_ws(log_probs, B, N, V, targets, S_max, input_lengths, target_lengths, blank, nll, alpha_ws, nullptr, 0,
+                               stream);
+}
+
+extern "C" int lcasr_ctc_loss_bwd_ws(const float* log_probs, int B, int64_t N, int V, const int64_t* targets,
+                                     int64_t S_max, const int32_t* input_lengths, const int64_t* target_lengths,
+                                     int blank, const float* nll, const float* grad_nll, const float* alpha_ws,
+                                     float* beta_ws, float* grad, void* workspace, int64_t workspace_bytes, void* stream);
 
 extern "C" int lcasr_ctc_loss_bwd(const float* log_probs, int B, int64_t N, int V, const int64_t* targets,
                                   int64_t S_max, const int32_t* input_lengths, const int64_t* target_lengths,
                                   int blank, const float* nll, const float* grad_nll, const float* alpha_ws,
                                   float* beta_ws, float* grad, void* stream) {
+  return lcasr_ctc_loss_bwd_ws(log_probs, B, N, V, targets, S_max, input_lengths, target_lengths, blank, nll, grad_nll, alpha_ws,
+                               beta_ws, grad, nullptr, 0, stream);
+}
+
+extern "C" int lcasr_ctc_loss_bwd_ws(const float* log_probs, int B, int64_t N, int V, const int64_t* targets,
+                                     int64_t S_max, const int32_t* input_lengths, const int64_t* target_lengths,
+                                     int blank, const float* nll, const float* grad_nll, const float* alpha_ws,
+                                     float* beta_ws, float* grad, void* workspace, int64_t workspace_bytes, void* stream) {
   LCASR_CHECK_ARG(log_probs && targets && target_lengths && nll && alpha_ws && beta_ws && grad,
                   "ctc_loss_bwd: NULL argument");
   LCASR_CHECK_ARG(B > 0 && N > 0 && V > 1 && S_max >= 0 && blank >= 0 && blank < V, "ctc_loss_bwd: bad shape");
@@ -713,7 +746,7 @@ extern "C" int lcasr_ctc_loss_bwd(const float* log_probs, int B, int64_t N, int 
   // beta_ws <- alpha, then the reversed recursion adds beta - lp[t, ext[s]] ... we store alpha+beta
   LCASR_CUDA(cudaMemcpyAsync(beta_ws, alpha_ws, (size_t)B * N * Lp_max * sizeof(float), cudaMemcpyDeviceToDevice, st));
   LCASR_TRY(ctc_recursion(log_probs, B, N, V, targets, S_max, input_lengths, target_lengths, blank, -1, nullptr,
-                          beta_ws, st));
+                          beta_ws, st, nullptr, 0, workspace, workspace_bytes));
   size_t smem = (size_t)V * sizeof(unsigned long long);
     if (smem > 48 * 1024) {  // per device and size-dependent: set on every call (cheap)
     LCASR_CUDA(cudaFuncSetAttribute(ctc_grad_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -727,9 +760,22 @@ extern "C" int lcasr_ctc_loss_bwd(const float* log_probs, int B, int64_t N, int 
 }
 
 // Training form: alpha and beta recursions in ONE launch (2*B CTAs, independent, concurrent) ...
+extern "C" int lcasr_ctc_loss_fwd_ab_ws(const float* log_probs, int B, int64_t N, int V, const int64_t* targets,
+                                        int64_t S_max, const int32_t* input_lengths, const int64_t* target_lengths,
+                                        int blank, float* nll, float* alpha_ws, float* beta_ws, void* workspace,
+                                        int64_t workspace_bytes, void* stream);
+
 extern "C" int lcasr_ctc_loss_fwd_ab(const float* log_probs, int B, int64_t N, int V, const int64_t* targets,
                                      int64_t S_max, const int32_t* input_lengths, const int64_t* target_lengths,
                                      int blank, float* nll, float* alpha_ws, float* beta_ws, void* stream) {
+  return lcasr_ctc_loss_fwd_ab_ws(log_probs, B, N, V, targets, S_max, input_lengths, target_lengths, blank, nll, alpha_ws, beta_ws,
+                                  nullptr, 0, stream);
+}
+
+extern "C" int lcasr_ctc_loss_fwd_ab_ws(const float* log_probs, int B, int64_t N, int V, const int64_t* targets,
+                                        int64_t S_max, const int32_t* input_lengths, const int64_t* target_lengths,
+                                        int blank, float* nll, float* alpha_ws, float* beta_ws, void* workspace,
+                                        int64_t workspace_bytes, void* stream) {
   LCASR_CHECK_ARG(log_probs && targets && target_lengths && nll && alpha_ws && beta_ws, "ctc_loss_fwd_ab: NULL argument");
   LCASR_CHECK_ARG(B > 0 && N > 0 && V > 1 && S_max >= 0 && blank >= 0 && blank < V, "ctc_loss_fwd_ab: bad shape");
   LCASR_CHECK_ARG(B <= 65535 && N < ((int64_t)1 << 31), "ctc_loss_fwd_ab: batch / length too large");
@@ -738,7 +784,7 @@ extern "C" int lcasr_ctc_loss_fwd_ab(const float* log_probs, int B, int64_t N, i
                                                             alpha_ws, beta_ws);
   LCASR_LAUNCH_CHECK();
   return ctc_recursion(log_probs, B, N, V, targets, S_max, input_lengths, target_lengths, blank, 0, nll, alpha_ws,
-                       (cudaStream_t)stream, beta_ws, 1);
+                       (cudaStream_t)stream, beta_ws, 1, workspace, workspace_bytes);
 }
 
 // ... and the gradient from the two state lattices (no recursion left in the backward).

@@ -12,7 +12,9 @@ class _CTCFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, lp_bnv, targets, input_lengths, target_lengths, blank):
         need_grad = lp_bnv.requires_grad
-        ctx.concurrent = need_grad and 2 * targets.shape[1] + 1 <= 4096
+        B_, N_ = lp_bnv.shape[0], lp_bnv.shape[1]
+        # alpha and beta in one launch: up to 4096 extended states on one SM each, or any length as two wavefronts
+        ctx.concurrent = need_grad and (2 * targets.shape[1] + 1 <= 4096 or ops.ctc_wavefront_applies(B_, N_, targets.shape[1], True))
         if ctx.concurrent:  # alpha and beta in one launch: the backward is only the class scatter
             nll, alpha, beta = ops.ctc_loss_fwd_ab(lp_bnv, targets, input_lengths, target_lengths, blank)
             ctx.save_for_backward(lp_bnv, targets, input_lengths, target_lengths, nll, alpha, beta)

@@ -187,6 +187,25 @@ def greedy_collapse(argmax, blank: int, lengths=None) -> Tuple[torch.Tensor, tor
     return tokens, n
 
 
+_CTC_WS = {}
+
+
+def ctc_workspace(B: int, N: int, S: int, both: bool, device):
+    """hand-off buffers of the wavefront CTC recursion (cached per device; None when the wavefront form does not apply)"""
+    nbytes = int(L.lib.lcasr_ctc_workspace_bytes(B, N, S, int(both)))
+    if nbytes <= 0:
+        return None
+    ws = _CTC_WS.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _CTC_WS[device] = ws
+    return ws
+
+
+def ctc_wavefront_applies(B: int, N: int, S: int, both: bool) -> bool:
+    return int(L.lib.lcasr_ctc_workspace_bytes(B, N, S, int(both))) > 0
+
+
 def ctc_loss_fwd(log_probs, targets, input_lengths, target_lengths, blank: int, keep_alpha: bool = False):
     """log_probs fp32 [B,N,V] (batch-major); returns (nll fp32 [B], alpha or None)."""
     _cuda(log_probs, targets, input_lengths, target_lengths)
@@ -194,8 +213,9 @@ def ctc_loss_fwd(log_probs, targets, input_lengths, target_lengths, blank: int, 
     S = targets.shape[1]
     nll = torch.empty(B, dtype=torch.float32, device=log_probs.device)
     alpha = torch.empty(B, N, 2 * S + 1, dtype=torch.float32, device=log_probs.device) if keep_alpha else None
-    L.call("lcasr_ctc_loss_fwd", L.ptr(log_probs), B, N, V, L.ptr(targets), S, L.ptr(input_lengths), L.ptr(target_lengths),
-           int(blank), L.ptr(nll), L.ptr(alpha), _s())
+    ws = ctc_workspace(B, N, S, False, log_probs.device)
+    L.call("lcasr_ctc_loss_fwd_ws", L.ptr(log_probs), B, N, V, L.ptr(targets), S, L.ptr(input_lengths), L.ptr(target_lengths),
+           int(blank), L.ptr(nll), L.ptr(alpha), L.ptr(ws), 0 if ws is None else ws.numel(), _s())
     return nll, alpha
 
 
@@ -205,8 +225,10 @@ def ctc_loss_bwd(log_probs, targets, input_lengths, target_lengths, blank: int, 
     S = targets.shape[1]
     beta = torch.empty_like(alpha)
     grad = torch.empty_like(log_probs)
-    L.call("lcasr_ctc_loss_bwd", L.ptr(log_probs), B, N, V, L.ptr(targets), S, L.ptr(input_lengths), L.ptr(target_lengths),
-           int(blank), L.ptr(nll), L.ptr(grad_nll), L.ptr(alpha), L.ptr(beta), L.ptr(grad), _s())
+    ws = ctc_workspace(B, N, S, False, log_probs.device)
+    L.call("lcasr_ctc_loss_bwd_ws", L.ptr(log_probs), B, N, V, L.ptr(targets), S, L.ptr(input_lengths), L.ptr(target_lengths),
+           int(blank), L.ptr(nll), L.ptr(grad_nll), L.ptr(alpha), L.ptr(beta), L.ptr(grad), L.ptr(ws), 0 if ws is None else ws.numel(),
+           _s())
     return grad
 
 
@@ -218,8 +240,9 @@ def ctc_loss_fwd_ab(log_probs, targets, input_lengths, target_lengths, blank: in
     nll = torch.empty(B, dtype=torch.float32, device=log_probs.device)
     alpha = torch.empty(B, N, 2 * S + 1, dtype=torch.float32, device=log_probs.device)
     beta = torch.empty_like(alpha)
-    L.call("lcasr_ctc_loss_fwd_ab", L.ptr(log_probs), B, N, V, L.ptr(targets), S, L.ptr(input_lengths), L.ptr(target_lengths),
-           int(blank), L.ptr(nll), L.ptr(alpha), L.ptr(beta), _s())
+    ws = ctc_workspace(B, N, S, True, log_probs.device)
+    L.call("lcasr_ctc_loss_fwd_ab_ws", L.ptr(log_probs), B, N, V, L.ptr(targets), S, L.ptr(input_lengths), L.ptr(target_lengths),
+           int(blank), L.ptr(nll), L.ptr(alpha), L.ptr(beta), L.ptr(ws), 0 if ws is None else ws.numel(), _s())
     return nll, alpha, beta
 
 

@@ -271,3 +271,39 @@ def test_subsampling_fused_conv0_dw(cuda_device, C, T, B):
     assert (got.float().cpu() - ref).abs().max() < 2 ** -6 * max(1.0, ref.abs().max())
     two = ops.subsample_dwconv(ops.subsample_conv0(args[0], args[1], args[2], torch.bfloat16), args[3], args[4])
     assert (got.float() - two.float()).abs().max().item() <= 2 ** -7 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,N,V,S", [(1, 3000, 512, 1400), (3, 900, 128, 400), (8, 512, 64, 150), (1, 45, 32, 40), (2, 4000, 4096, 2100)])
+def test_ctc_wavefront_is_bit_identical_to_plain_recursion(cuda_device, B, N, V, S):
+    """The time-skewed wavefront form (state chunks on persistent CTAs, boundary hand-off through global memory) performs the
+    same arithmetic per state as the one-CTA / cluster recursions: losses and both lattices must be bit-identical."""
+    from lcasr_b200 import ops, _lib as L
+    blank = V - 1
+    g = torch.Generator().manual_seed(5)
+    lp = torch.randn(B, N, V, generator=g).log_softmax(-1).to(cuda_device)
+    tgt = torch.randint(0, V - 1, (B, S), generator=g)
+    tgt[:, 3] = tgt[:, 2]
+    tgt = tgt.to(cuda_device)
+    tl = torch.tensor([S - 5 * b for b in range(B)], dtype=torch.long, device=cuda_device)
+    il = torch.tensor([N - 7 * b for b in range(B)], dtype=torch.int32, device=cuda_device)
+    assert ops.ctc_wavefront_applies(B, N, S, False)
+    nll_w, alpha_w = ops.ctc_loss_fwd(lp, tgt, il, tl, blank, keep_alpha=True)
+    nll_p = torch.empty_like(nll_w)
+    alpha_p = torch.full_like(alpha_w, float("nan"))
+    L.call("lcasr_ctc_loss_fwd", L.ptr(lp), B, N, V, L.ptr(tgt), S, L.ptr(il), L.ptr(tl), blank, L.ptr(nll_p), L.ptr(alpha_p),
+           L.current_stream())
+    torch.cuda.synchronize()
+    assert torch.equal(nll_w, nll_p)
+    for b in range(B):  # rows / states beyond a sample's lengths are unspecified
+        t, lpb = int(il[b]), 2 * int(tl[b]) + 1
+        assert torch.equal(alpha_w[b, :t, :lpb], alpha_p[b, :t, :lpb])
+    if 2 * S + 1 <= 4096 and ops.ctc_wavefront_applies(B, N, S, True):  # concurrent alpha / beta (training form)
+        nll2, a2, b2 = ops.ctc_loss_fwd_ab(lp, tgt, il, tl, blank)
+        nll3, a3, b3 = torch.empty_like(nll2), torch.empty_like(a2), torch.empty_like(b2)
+        L.call("lcasr_ctc_loss_fwd_ab", L.ptr(lp), B, N, V, L.ptr(tgt), S, L.ptr(il), L.ptr(tl), blank, L.ptr(nll3), L.ptr(a3),
+               L.ptr(b3), L.current_stream())
+        torch.cuda.synchronize()
+        assert torch.equal(nll2, nll3) and torch.equal(nll2, nll_p)
+        for b in range(B):
+            t, lpb = int(il[b]), 2 * int(tl[b]) + 1
+            assert torch.equal(a2[b, :t, :lpb], a3[b, :t, :lpb]) and torch.equal(b2[b, :t, :lpb], b3[b, :t, :lpb])

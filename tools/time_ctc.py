@@ -25,6 +25,13 @@ def t(fn, n=3):
 nll, _ = ops.ctc_loss_fwd(lp, tgt, il, tl, a.V - 1)
 ref = torch.nn.functional.ctc_loss(lp.transpose(0, 1), tgt, il.long(), tl, blank=a.V - 1, reduction="none")
 print(f"N={a.N} S={S} B={a.B}: ours nll {nll.tolist()} torch {ref.tolist()}")
+from lcasr_b200 import _lib as L
+nll_p = torch.empty_like(nll)
+def plain():
+    L.call("lcasr_ctc_loss_fwd", L.ptr(lp), a.B, a.N, a.V, L.ptr(tgt), S, L.ptr(il), L.ptr(tl), a.V - 1, L.ptr(nll_p), None, L.current_stream())
+plain(); torch.cuda.synchronize()
+print(f"  wavefront applies: {ops.ctc_wavefront_applies(a.B, a.N, S, False)}; bit-identical to the plain recursion: {torch.equal(nll, nll_p)}")
+print(f"  plain (one CTA / cluster) fwd {t(plain):.2f} ms")
 print(f"  ours fwd {t(lambda: ops.ctc_loss_fwd(lp, tgt, il, tl, a.V - 1)):.2f} ms ; torch(ATen CUDA) fwd {t(lambda: torch.nn.functional.ctc_loss(lp.transpose(0, 1), tgt, il.long(), tl, blank=a.V - 1, reduction='none')):.2f} ms")
 if a.bwd:
     def ours_bwd():
