@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LCASR_ABI_VERSION 2
+#define LCASR_ABI_VERSION 3
 
 enum { LCASR_F32 = 0, LCASR_BF16 = 1 };
 enum { LCASR_OK = 0, LCASR_E_BADARG = -1, LCASR_E_UNSUPPORTED = -2, LCASR_E_CUDA = -3, LCASR_E_NOMEM = -4 };
@@ -80,6 +80,22 @@ int lcasr_subsample_conv0_dw(const float* spec, const float* w0, const float* b0
 int lcasr_gemm(const void* A, const void* W, int ab_dtype, int64_t M, int N, int K,
                const float* bias, int act, const float* resid, float alpha, void* out,
                int out_dtype, int impl, void* stream);
+
+/* The qkv projection with the rotary embedding applied in the GEMM epilogue (attention.py:483 + :499-507 in one kernel;
+ * bf16, tcgen05): W = qkv weights with interleaved q / k head rows (see lcasr_layer_weights.qkv_w_il); out [M, N] bf16 =
+ * [q | k | v] with columns < rope_cols rotated by cos/sin [rope_n, Dh/2] (position = row % rope_n) in fp32 before the store.
+ * q.k^T is invariant under the common permutation of the head dimension, so lcasr_attention_qkv on this output equals
+ * lcasr_rope_split + lcasr_attention on the plain projection. */
+int lcasr_gemm_rope(const void* A, const void* W, int64_t M, int N, int K, const float* cos_t, const float* sin_t,
+                    int64_t rope_n, int rope_cols, int Dh, void* out, void* stream);
+
+/* pointwise_conv1 + GLU in one kernel (convolution.py:105-107; bf16, tcgen05): W [2d, K] / bias [2d] packed in 64-row blocks
+ * (32 value channels, then their 32 gate channels); out [M, d] bf16 = value * sigmoid(gate). */
+int lcasr_gemm_glu(const void* A, const void* W, int64_t M, int N, int K, const float* bias, void* out, void* stream);
+
+/* Attention reading q, k, v as the three column blocks of ONE row-major [B*N, 3*H*Dh] bf16 matrix (the qkv projection):
+ * no split / copy pass.  kv_len may be NULL. out [B,N,H*Dh] bf16. */
+int lcasr_attention_qkv(const void* qkv, int B, int64_t N, const int32_t* kv_len, int H, int Dh, void* out, void* stream);
 
 /* fp32 -> compute-dtype copy of n elements (the implicit autocast cast in front of a Linear when
  * decoder_norm=False, decoder.py:23-24). */
@@ -431,6 +447,12 @@ typedef struct lcasr_layer_weights {
   const float *dw_w, *dw_b, *brn_mean, *brn_std, *brn_w, *brn_b; const void *pw2_w; const float *pw2_b;
   const float *ff2_norm_w, *ff2_norm_b; const void *ff2_fc1_w; const float *ff2_fc1_b; const void *ff2_fc2_w; const float *ff2_fc2_b;
   const float *norm_out_w, *norm_out_b;
+  /* ABI 3 — optional (NULL = use the unfused kernels), compute dtype, for the fused epilogues of the bf16 path:
+   * qkv_w_il : qkv_w with the rows of every q and k head interleaved (new row 2i <- old i, 2i+1 <- old i + Dh/2) so that a
+   *            rotary pair is two adjacent output columns (rotary_emb.py:61-73 rotate_half pairs (i, i + Dh/2));
+   * pw1_w_glu / pw1_b_glu : pointwise_conv1 rows / bias in 64-row blocks [32 value channels | their 32 gate channels]
+   *            (convolution.py:105-107: glu pairs channel c with channel d + c). */
+  const void *qkv_w_il; const void *pw1_w_glu; const float *pw1_b_glu;
 } lcasr_layer_weights;
 
 typedef struct lcasr_weights {

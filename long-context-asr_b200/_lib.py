@@ -16,7 +16,7 @@ ACT_NONE, ACT_GELU_TANH, ACT_SILU = 0, 1, 2
 NORM_LAYERNORM, NORM_RMSNORM = 0, 1
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
 ATTN_AUTO, ATTN_SIMT, ATTN_TCGEN05 = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -35,7 +35,7 @@ LAYER_FIELDS = (
     "conv_norm_w", "conv_norm_b", "pw1_w", "pw1_b",
     "dw_w", "dw_b", "brn_mean", "brn_std", "brn_w", "brn_b", "pw2_w", "pw2_b",
     "ff2_norm_w", "ff2_norm_b", "ff2_fc1_w", "ff2_fc1_b", "ff2_fc2_w", "ff2_fc2_b",
-    "norm_out_w", "norm_out_b")
+    "norm_out_w", "norm_out_b", "qkv_w_il", "pw1_w_glu", "pw1_b_glu")
 
 
 class LcasrLayerWeights(C.Structure):
@@ -76,6 +76,9 @@ _SIGNATURES = {
     "lcasr_subsample_conv0_dw": [vp, vp, vp, vp, vp, i32, i32, i64, i32, vp, vp],
     "lcasr_gemm": [vp, vp, i32, i64, i32, i32, vp, i32, vp, f32, vp, i32, i32, vp],
     "lcasr_cast_f32": [vp, i64, vp, i32, vp],
+    "lcasr_gemm_rope": [vp, vp, i64, i32, i32, vp, vp, i64, i32, i32, vp, vp],
+    "lcasr_gemm_glu": [vp, vp, i64, i32, i32, vp, vp, vp],
+    "lcasr_attention_qkv": [vp, i32, i64, vp, i32, i32, vp, vp],
     "lcasr_glu": [vp, i32, i64, i32, vp, vp],
     "lcasr_rope_table": [vp, f32, i64, i64, i32, vp, vp, vp],
     "lcasr_rope_split": [vp, i32, i32, i64, i32, i32, vp, vp, vp, vp, vp, i32, i64, vp],

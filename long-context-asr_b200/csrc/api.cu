@@ -23,6 +23,9 @@ int gemm_simt_launch(const void* A, const void* W, int ab_dtype, int64_t M, int 
                      const float* resid, float alpha, void* out, int out_dtype, cudaStream_t st);
 int gemm_tc_launch(const void* A, const void* W, int64_t M, int N, int K, const float* bias, int act, const float* resid,
                    float alpha, void* out, int out_dtype, cudaStream_t st, void* pre_out = nullptr);
+int gemm_tc_launch_rope(const void* A, const void* W, int64_t M, int N, int K, const float* cos_t, const float* sin_t,
+                        int64_t rope_n, int rope_cols, int dh, void* out, cudaStream_t st);
+int gemm_tc_launch_glu(const void* A, const void* W, int64_t M, int N, int K, const float* bias, void* out, cudaStream_t st);
 int attn_simt_launch(const void* q, const void* k, const void* v, int dtype, int B, int64_t N, int64_t Nk, const int32_t* kv_len,
                      int H, int Dh, int v_transposed, int64_t Npad, void* out, cudaStream_t st, int wl = -1, int wr = -1);
 int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len, int H,
@@ -93,6 +96,29 @@ extern "C" int lcasr_attention_cross(const void* q, const void* k, const void* v
 extern "C" int lcasr_attention_masked(const void* q, const void* k, const void* v, int dtype, int B, int64_t Nq, int64_t Nk,
                                       const int32_t* kv_len, int H, int Dh, void* out, int impl, void* stream) {
   return attention_dispatch(q, k, v, dtype, B, Nq, Nk, kv_len, H, Dh, 0, 0, out, impl, stream);
+}
+
+extern "C" int lcasr_gemm_rope(const void* A, const void* W, int64_t M, int N, int K, const float* cos_t, const float* sin_t,
+                               int64_t rope_n, int rope_cols, int Dh, void* out, void* stream) {
+  LCASR_CHECK_ARG(A && W && out, "gemm_rope: NULL operand");
+  LCASR_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm_rope: bad shape");
+  if (M == 0) return 0;
+  return gemm_tc_launch_rope(A, W, M, N, K, cos_t, sin_t, rope_n, rope_cols, Dh, out, (cudaStream_t)stream);
+}
+
+extern "C" int lcasr_gemm_glu(const void* A, const void* W, int64_t M, int N, int K, const float* bias, void* out, void* stream) {
+  LCASR_CHECK_ARG(A && W && out, "gemm_glu: NULL operand");
+  LCASR_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm_glu: bad shape");
+  if (M == 0) return 0;
+  return gemm_tc_launch_glu(A, W, M, N, K, bias, out, (cudaStream_t)stream);
+}
+
+extern "C" int lcasr_attention_qkv(const void* qkv, int B, int64_t N, const int32_t* kv_len, int H, int Dh, void* out, void* stream) {
+  LCASR_CHECK_ARG(qkv && out && B > 0 && N > 0 && H > 0 && Dh > 0, "attention_qkv: bad arguments");
+  const int64_t d = (int64_t)H * Dh;
+  const char* base = (const char*)qkv;
+  return attn_tc_launch(base, base + d * 2, base + 2 * d * 2, B, N, N, kv_len, H, Dh, 0, 0, out, nullptr, (cudaStream_t)stream, -1, -1,
+                        nullptr, 3 * d, 3 * d);
 }
 
 // training forward: bf16 tcgen05 attention that also returns the per-row log-sum-exp the backward needs

@@ -359,7 +359,7 @@ static int launch_cluster(const float* lp, int B, int64_t N, int V, const int64_
 // <= 1024 threads — ~0.1 us) instead of 2.1 us for a barrier across 8 SMs, and the 45000-frame lattice of a
 // 1-hour recording is finished (45000 + G*kWfTB) * 0.1 us after it starts.  Log-prob gathers run one batch of frames
 // ahead in registers.  Same arithmetic per state as the kernels above (bit-identical results).
-constexpr int kWfTB = 16;
+constexpr int kWfTBDefault = 16;
 
 __device__ __forceinline__ unsigned wf_ld_acquire(const unsigned* p) {
   unsigned v;
@@ -370,7 +370,8 @@ __device__ __forceinline__ void wf_st_release(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(1024, 1)
+template <int kWfTB, int DBG, int MAXT>  // DBG (profiling only): 1 = no log-prob gathers, 2 = no waiting for the left neighbour
+__global__ void __launch_bounds__(MAXT, 1)
 ctc_wavefront_kernel(const float* __restrict__ log_probs, int64_t N, int V, const int64_t* __restrict__ targets, int64_t S_max,
                      const int32_t* __restrict__ input_lengths, const int64_t* __restrict__ target_lengths, int blank,
                      int direction, int G, int batch, float* __restrict__ nll, float* __restrict__ store,
@@ -417,6 +418,7 @@ ctc_wavefront_kernel(const float* __restrict__ log_probs, int64_t N, int V, cons
   auto frame = [&](int64_t step) -> int64_t { return direction > 0 ? step : (T - 1 - step); };
   auto fetch = [&](int64_t step) -> float {  // the log-prob this state consumes at `step`
     if (!live || step >= T) return 0.f;
+    if (DBG == 1) return -1.0f;
     if (pregathered) return __ldcg(st + frame(step) * Lp_max + so);
     return __ldg(lp + frame(step) * V + lab);
   };
@@ -427,7 +429,7 @@ ctc_wavefront_kernel(const float* __restrict__ log_probs, int64_t N, int V, cons
   const bool pub0 = tid == CH - 2, pub1 = tid == CH - 1;
 
   auto wait_left = [&](unsigned need) {  // thread 0: until the left chunk has published `need` steps
-    if (tid == 0 && left_flag) {
+    if (tid == 0 && left_flag && DBG != 2) {
       unsigned spins = 0;
       uint64_t t_first = 0;
       while (wf_ld_acquire(left_flag) < need) {
@@ -528,6 +530,11 @@ ctc_wavefront_kernel(const float* __restrict__ log_probs, int64_t N, int V, cons
 }
 
 // chunks per lattice for `units` lattices of Lp_max states on this GPU (0 = the wavefront form does not apply)
+static int wf_tb() {
+  static const int tb = getenv("LCASR_CTC_WF_TB") ? atoi(getenv("LCASR_CTC_WF_TB")) : kWfTBDefault;
+  return tb == 8 || tb == 32 || tb == 64 ? tb : 16;
+}
+
 static int wf_chunks(int units, int64_t Lp_max) {
   if (units < 1 || units > kNumSMs) return 0;
   int G = kNumSMs / units;
@@ -557,14 +564,26 @@ static int launch_wavefront(const float* lp, int B, int64_t N, int V, const int6
   float* bnd = (float*)workspace;
   unsigned* flags = (unsigned*)((char*)workspace + (((size_t)units * G * N * 2 * 4 + 255) & ~(size_t)255));
   LCASR_CUDA(cudaMemsetAsync(flags, 0, (size_t)units * G * 4, st));
-  const size_t smem = (size_t)(2 * (nt + 2) + 2 * kWfTB) * sizeof(float);
+  const int tb = wf_tb();
+  static const int dbg = getenv("LCASR_CTC_WF_DBG") ? atoi(getenv("LCASR_CTC_WF_DBG")) : 0;
+  const size_t smem = (size_t)(2 * (nt + 2) + 2 * tb) * sizeof(float);
   int batch = B;
   void* args[] = {(void*)&lp, (void*)&N, (void*)&V, (void*)&tg, (void*)&S_max, (void*)&il, (void*)&tl, (void*)&blank, (void*)&dir,
                   (void*)&G, (void*)&batch, (void*)&nll, (void*)&store, (void*)&store_beta, (void*)&pregathered, (void*)&bnd,
                   (void*)&flags};
   // cooperative launch: every CTA is resident, so the spin on a neighbour's flag always makes progress
-  LCASR_CUDA(cudaLaunchCooperativeKernel((const void*)ctc_wavefront_kernel, dim3((unsigned)(units * G)), dim3((unsigned)nt), args,
-                                         smem, st));
+  const void* fn = nullptr;
+  const bool small = nt <= 256;  // chunks of <= 256 states: up to 255 registers per thread for the look-ahead ring
+#define LCASR_WF(TB)                                                                                                        \
+  fn = dbg == 1 ? (small ? (const void*)ctc_wavefront_kernel<TB, 1, 256> : (const void*)ctc_wavefront_kernel<TB, 1, 1024>)   \
+       : dbg == 2 ? (small ? (const void*)ctc_wavefront_kernel<TB, 2, 256> : (const void*)ctc_wavefront_kernel<TB, 2, 1024>) \
+                  : (small ? (const void*)ctc_wavefront_kernel<TB, 0, 256> : (const void*)ctc_wavefront_kernel<TB, 0, 1024>)
+  if (tb == 8) { LCASR_WF(8); } else if (tb == 32 && small) { LCASR_WF(32); } else if (tb == 64 && small) { LCASR_WF(64); } else { LCASR_WF(16); }
+#undef LCASR_WF
+  const int tb_used = (tb == 8) ? 8 : ((tb == 32 && small) ? 32 : ((tb == 64 && small) ? 64 : 16));
+  const size_t smem_used = (size_t)(2 * (nt + 2) + 2 * tb_used) * sizeof(float);
+  (void)smem;
+  LCASR_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)(units * G)), dim3((unsigned)nt), args, smem_used, st));
   count_launch();
   return 0;
 }

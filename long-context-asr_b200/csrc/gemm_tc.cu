@@ -57,7 +57,18 @@ struct TgEpilogue {
   int act;
   bf16* pre_out = nullptr;  // training: the pre-activation acc+bias [M,N] is stored as well (bf16 outputs only)
   int debug = 0;            // LCASR_GEMM_DEBUG (profiling only): 1 = skip the global stores, 2 = skip the whole epilogue, 3 / 4 = fp32: no stores / no residual
+  // EPI == TG_EPI_ROPE (fused rotary, attention.py:499-507 / rotary_emb.py:61-73): output columns < rope_cols are rotated in
+  // fp32 before the bf16 store.  The weight rows of every q / k head were interleaved on the host (new 2i <- old i,
+  // new 2i+1 <- old i + Dh/2), so a rotation pair is two ADJACENT columns: y[2i] = x[2i] c_i - x[2i+1] s_i,
+  // y[2i+1] = x[2i+1] c_i + x[2i] s_i with c/s = tables[pos, i], pos = row % rope_n.  (q.k is invariant under a common
+  // permutation of the head dimension, so attention sees exactly the reference's scores.)
+  const float* rope_cos = nullptr;
+  const float* rope_sin = nullptr;
+  int rope_cols = 0, rope_dh = 0;
+  int64_t rope_n = 1;
 };
+
+enum { TG_EPI_STD = 0, TG_EPI_ROPE = 1, TG_EPI_GLU = 2 };
 
 // Direct epilogue (bf16 outputs, no residual): lane == row, 64 contiguous bytes per lane and chunk.
 // Measured faster than the transposed variant below for 2-byte outputs (923 vs 654 TFLOP/s on the
@@ -153,8 +164,12 @@ __device__ __forceinline__ void tg_stage_chunk_f32(const uint32_t (&r)[32], int 
 // Here a warp converts 64 columns of its 32 rows into a 128B-swizzled shared-memory box (conflict-free: 8 lanes with
 // distinct row%8 cover 8 distinct 16-byte slots per wavefront) and one lane issues a single cp.async.bulk.tensor
 // store for the box: full lines, no LSU work, rows / columns beyond the tensor clipped by the hardware.
+template <int EPI>
 __device__ __forceinline__ void tg_stage_chunk64(const uint32_t (&r0)[32], const uint32_t (&r1)[32], int lane, uint32_t stage_addr,
-                                                 const TgEpilogue& ep, const float* __restrict__ bias_chunk, bool pre_pass) {
+                                                 const TgEpilogue& ep, const float* __restrict__ bias_chunk, bool pre_pass,
+                                                 int col0 = 0, const float* __restrict__ cos_row = nullptr,
+                                                 const float* __restrict__ sin_row = nullptr) {
+  // col0 (EPI == ROPE): global column of r0[0]; cos_row / sin_row: this lane's table rows (position of its token)
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
     float y[32];
@@ -166,6 +181,25 @@ __device__ __forceinline__ void tg_stage_chunk64(const uint32_t (&r0)[32], const
       for (int g = 0; g < 8; ++g) {
         const float4 b = bp[g];
         y[4 * g] += b.x; y[4 * g + 1] += b.y; y[4 * g + 2] += b.z; y[4 * g + 3] += b.w;
+      }
+    }
+    if constexpr (EPI == TG_EPI_ROPE) {
+      const int colh = col0 + 32 * hh;
+      if (colh < ep.rope_cols) {  // warp-uniform: a q / k column block (v passes through)
+        const int j0 = (colh % ep.rope_dh) >> 1;  // first rotation pair of this 32-column block inside its head
+        const float4* cp = reinterpret_cast<const float4*>(cos_row + j0);
+        const float4* sp = reinterpret_cast<const float4*>(sin_row + j0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {  // 4 pairs = 8 columns per step
+          const float4 cc = __ldg(cp + g), ss = __ldg(sp + g);
+          const float cv[4] = {cc.x, cc.y, cc.z, cc.w}, sv[4] = {ss.x, ss.y, ss.z, ss.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float a = y[8 * g + 2 * i], b = y[8 * g + 2 * i + 1];
+            y[8 * g + 2 * i] = fmaf(a, cv[i], -b * sv[i]);
+            y[8 * g + 2 * i + 1] = fmaf(b, cv[i], a * sv[i]);
+          }
+        }
       }
     }
     if (!pre_pass) {
@@ -197,7 +231,30 @@ __device__ __forceinline__ void tg_stage_chunk64(const uint32_t (&r0)[32], const
   }
 }
 
-template <int BN, typename TOut, int CG, bool W8>
+// EPI == TG_EPI_GLU (torch.nn.functional.glu fused into pointwise_conv1, convolution.py:105-107): the weight rows were
+// packed on the host so that every 64-column block of the tile holds 32 value channels followed by THEIR 32 gate channels;
+// out[:, ch] = (acc_v + b_v) * sigmoid(acc_g + b_g) — 32 bf16 outputs per block, two blocks fill one 64-column store box.
+__device__ __forceinline__ void tg_stage_glu32(const uint32_t (&rv)[32], const uint32_t (&rg)[32], int lane, uint32_t stage_addr,
+                                               int half_sel, const TgEpilogue& ep, const float* __restrict__ bias_chunk) {
+  float y[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float v = __uint_as_float(rv[i]), g = __uint_as_float(rg[i]);
+    if (ep.bias) { v += bias_chunk[i]; g += bias_chunk[32 + i]; }
+    y[i] = v * sigmoid_fast(g);
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {  // 16-byte slot 4*half_sel + g of this lane's 128-byte row, XOR-swizzled by row % 8
+    uint4 v;
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h2[i] = __floats2bfloat162_rn(y[8 * g + 2 * i], y[8 * g + 2 * i + 1]);
+    const uint32_t addr = stage_addr + lane * 128 + (((4 * half_sel + g) ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+}
+
+template <int BN, typename TOut, int CG, bool W8, int EPI = TG_EPI_STD>
 __global__ void __launch_bounds__(TgWarps<TOut, CG, W8>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, int64_t M, int N, int K,
@@ -339,7 +396,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (n_idx + c * 32 >= N || ep.debug == 2) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_addr + c * 32, r);
-        if constexpr (sizeof(TOut) == 2) {
+        if constexpr (sizeof(TOut) == 2 && EPI == TG_EPI_GLU) {
+          // chunks come in groups of four: (value, gate) (value, gate) -> one 64-column store box of the [M, N/2] output
+          const uint32_t stg = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES + (warp - 2) * 4096;
+          uint32_t r1[32];
+          tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, r1);
+          tmem_wait_ld();
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+          tg_stage_glu32(r, r1, lane, stg, 0, ep, &bias_s[acc][c * 32]);
+          if (n_idx + (c + 2) * 32 < N) {  // warp-uniform (N % 64 == 0: a block is complete or absent)
+            tmem_ld_32x32b_x32(t_addr + (c + 2) * 32, r);
+            tmem_ld_32x32b_x32(t_addr + (c + 3) * 32, r1);
+            tmem_wait_ld();
+            tg_stage_glu32(r, r1, lane, stg, 1, ep, &bias_s[acc][(c + 2) * 32]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {  // columns beyond N/2 are clipped by the tensor map
+            tma_store_2d(&tmC, stg, (n_idx + c * 32) >> 1, (int)row0);
+            tma_store_commit();
+          }
+          c += 3;  // four chunks per iteration (CPW and the warp's first chunk are multiples of 4)
+        } else if constexpr (sizeof(TOut) == 2) {
           if (ep.debug || (c & 1)) {  // profiling variants keep the direct path; odd chunks are drained with their even twin
             tmem_wait_ld();
             if (ep.debug) tg_store_chunk_direct(r, row0 + lane, n_idx + c * 32, M, N, ep, &bias_s[acc][c * 32], out);
@@ -347,12 +426,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           uint32_t r1[32];
           tmem_ld_32x32b_x32(t_addr + (c + 1) * 32, r1);  // BN is a multiple of 64: the twin chunk exists
+          const float* cos_row = nullptr;
+          const float* sin_row = nullptr;
+          if constexpr (EPI == TG_EPI_ROPE) {  // this lane's token position -> its table rows (clamped for rows beyond M)
+            const int64_t rr = row0 + lane < M ? row0 + lane : M - 1;
+            const int64_t pos = rr % ep.rope_n;
+            cos_row = ep.rope_cos + pos * (ep.rope_dh >> 1);
+            sin_row = ep.rope_sin + pos * (ep.rope_dh >> 1);
+          }
           tmem_wait_ld();
           const uint32_t stg = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES + (warp - 2) * 4096;
           for (int pass = ep.pre_out ? 0 : 1; pass < 2; ++pass) {
             if (lane == 0) tma_store_wait_read();  // the previous box has been read out of the staging tile
             __syncwarp();
-            tg_stage_chunk64(r, r1, lane, stg, ep, &bias_s[acc][c * 32], pass == 0);
+            tg_stage_chunk64<EPI>(r, r1, lane, stg, ep, &bias_s[acc][c * 32], pass == 0, n_idx + c * 32, cos_row, sin_row);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
@@ -466,7 +553,7 @@ int make_tmap_3d_bf16(CUtensorMap* map, const void* base, uint64_t d0, uint64_t 
   return 0;
 }
 
-template <int BN, typename TOut, int CG, bool W8 = true>
+template <int BN, typename TOut, int CG, bool W8 = true, int EPI = TG_EPI_STD>
 static int launch_tc(const void* A, const void* W, int64_t M, int N, int K, const TgEpilogue& ep, void* out,
                      cudaStream_t st) {
   using Cfg = TgCfgFor<BN, TOut, CG, W8>;
@@ -481,14 +568,15 @@ static int launch_tc(const void* A, const void* W, int64_t M, int N, int K, cons
       LCASR_TRY(make_tmap_2d_any(&tmC2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, ep.resid, (uint64_t)M, (uint64_t)N, (uint64_t)N * 4, 32, 32,
                                  CU_TENSOR_MAP_SWIZZLE_128B));
   } else {
-    LCASR_TRY(make_tmap_2d_bf16(&tmC, out, (uint64_t)M, (uint64_t)N, (uint64_t)N * 2, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
+    const uint64_t No = EPI == TG_EPI_GLU ? (uint64_t)N / 2 : (uint64_t)N;  // GLU halves the output width
+    LCASR_TRY(make_tmap_2d_bf16(&tmC, out, (uint64_t)M, No, No * 2, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
     if (ep.pre_out)
       LCASR_TRY(make_tmap_2d_bf16(&tmC2, ep.pre_out, (uint64_t)M, (uint64_t)N, (uint64_t)N * 2, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B));
   }
   static PerDeviceFlag attr_set;
   int attr_dev = 0;
   if (attr_set.needs_set(&attr_dev)) {
-    LCASR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TOut, CG, W8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    LCASR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, TOut, CG, W8, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set.mark(attr_dev);
   }
   const int64_t tiles = ceil_div(M, CG * TG_BM) * ceil_div(N, BN);
@@ -504,31 +592,37 @@ static int launch_tc(const void* A, const void* W, int64_t M, int N, int K, cons
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CG == 2 ? 1 : 0;
-  LCASR_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, TOut, CG, W8>, tmA, tmB, tmC, tmC2, M, N, K, ep, (TOut*)out));
+  LCASR_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, TOut, CG, W8, EPI>, tmA, tmB, tmC, tmC2, M, N, K, ep, (TOut*)out));
   LCASR_LAUNCH_CHECK();
   return 0;
 }
 
-template <int BN, typename TOut>
+template <int BN, typename TOut, int EPI = TG_EPI_STD>
 static int launch_tc_cg(const void* A, const void* W, int64_t M, int N, int K, const TgEpilogue& ep, void* out,
                         cudaStream_t st) {
   // CTA pairs (256-row tiles) once there is enough work to fill the 74 pairs; LCASR_GEMM_CG=1|2 forces a choice (A/B runs)
   static const int force = getenv("LCASR_GEMM_CG") ? atoi(getenv("LCASR_GEMM_CG")) : 0;
   const bool pair = force ? force == 2 : (ceil_div(M, 2 * TG_BM) * ceil_div(N, BN) >= kNumSMs / 2);
-  if (!pair) return launch_tc<BN, TOut, 1>(A, W, M, N, K, ep, out, st);
-  if (sizeof(TOut) == 4 && K > 1536) return launch_tc<BN, TOut, 2, false>(A, W, M, N, K, ep, out, st);
-  return launch_tc<BN, TOut, 2, true>(A, W, M, N, K, ep, out, st);
+  if (!pair) return launch_tc<BN, TOut, 1, true, EPI>(A, W, M, N, K, ep, out, st);
+  if (sizeof(TOut) == 4 && K > 1536) return launch_tc<BN, TOut, 2, false, EPI>(A, W, M, N, K, ep, out, st);
+  return launch_tc<BN, TOut, 2, true, EPI>(A, W, M, N, K, ep, out, st);
+}
+
+static int gemm_tc_check_common(const void* A, const void* W, int64_t M, int N, int K, const float* bias, const void* out) {
+  LCASR_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "gemm(tcgen05): K=%d and N=%d must be multiples of 8", K, N);
+  LCASR_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0,
+                  "gemm(tcgen05): A, W and out must be 16-byte aligned");
+  LCASR_CHECK_ARG(M < (int64_t)1 << 31, "gemm(tcgen05): M too large");
+  LCASR_CHECK_ARG(((uintptr_t)bias & 15) == 0, "gemm(tcgen05): bias must be 16-byte aligned");
+  return 0;
 }
 
 int gemm_tc_launch(const void* A, const void* W, int64_t M, int N, int K, const float* bias, int act, const float* resid,
                    float alpha, void* out, int out_dtype, cudaStream_t st, void* pre_out) {
   LCASR_CHECK_ARG(!pre_out || (out_dtype == LCASR_BF16 && !resid && ((uintptr_t)pre_out & 15) == 0),
                   "gemm(tcgen05): the pre-activation output needs a bf16, residual-free epilogue");
-  LCASR_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "gemm(tcgen05): K=%d and N=%d must be multiples of 8", K, N);
-  LCASR_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0,
-                  "gemm(tcgen05): A, W and out must be 16-byte aligned");
-  LCASR_CHECK_ARG(M < (int64_t)1 << 31, "gemm(tcgen05): M too large");
-  LCASR_CHECK_ARG(((uintptr_t)bias & 15) == 0 && ((uintptr_t)resid & 15) == 0, "gemm(tcgen05): bias/resid must be 16-byte aligned");
+  LCASR_TRY(gemm_tc_check_common(A, W, M, N, K, bias, out));
+  LCASR_CHECK_ARG(((uintptr_t)resid & 15) == 0, "gemm(tcgen05): resid must be 16-byte aligned");
   LCASR_CHECK_ARG(!resid || out_dtype == LCASR_F32, "gemm: a residual epilogue writes fp32");
   static const int debug = getenv("LCASR_GEMM_DEBUG") ? atoi(getenv("LCASR_GEMM_DEBUG")) : 0;
   TgEpilogue ep{bias, debug == 4 ? nullptr : resid, alpha, act, (bf16*)pre_out, debug};  // (4: profiling — no residual loads)
@@ -536,6 +630,31 @@ int gemm_tc_launch(const void* A, const void* W, int64_t M, int N, int K, const 
   if (out_dtype == LCASR_BF16)
     return wide ? launch_tc_cg<256, bf16>(A, W, M, N, K, ep, out, st) : launch_tc_cg<128, bf16>(A, W, M, N, K, ep, out, st);
   return wide ? launch_tc_cg<256, float>(A, W, M, N, K, ep, out, st) : launch_tc_cg<128, float>(A, W, M, N, K, ep, out, st);
+}
+
+// qkv projection with the rotary embedding applied in the epilogue (see TgEpilogue): out [M, N] bf16, columns
+// [0, rope_cols) rotated with tables cos/sin [rope_n, dh/2] (position = row % rope_n), the rest (v) stored as is.
+int gemm_tc_launch_rope(const void* A, const void* W, int64_t M, int N, int K, const float* cos_t, const float* sin_t,
+                        int64_t rope_n, int rope_cols, int dh, void* out, cudaStream_t st) {
+  LCASR_TRY(gemm_tc_check_common(A, W, M, N, K, nullptr, out));
+  LCASR_CHECK_ARG(cos_t && sin_t && rope_n > 0, "gemm_rope: NULL tables");
+  LCASR_CHECK_ARG(dh >= 32 && dh % 32 == 0 && rope_cols % 64 == 0 && rope_cols <= N && N % 64 == 0,
+                  "gemm_rope: head_dim %d / rotated columns %d / N %d not supported", dh, rope_cols, N);
+  LCASR_CHECK_ARG(((uintptr_t)cos_t & 15) == 0 && ((uintptr_t)sin_t & 15) == 0 && (dh / 2) % 4 == 0, "gemm_rope: tables must be 16-byte aligned");
+  TgEpilogue ep{nullptr, nullptr, 0.f, LCASR_ACT_NONE, nullptr, 0};
+  ep.rope_cos = cos_t; ep.rope_sin = sin_t; ep.rope_cols = rope_cols; ep.rope_dh = dh; ep.rope_n = rope_n;
+  const bool wide = (N % 256 == 0) || N > 512;
+  return wide ? launch_tc_cg<256, bf16, TG_EPI_ROPE>(A, W, M, N, K, ep, out, st)
+              : launch_tc_cg<128, bf16, TG_EPI_ROPE>(A, W, M, N, K, ep, out, st);
+}
+
+// pointwise_conv1 + GLU: W [N = 2d, K] with rows packed in 64-row blocks (32 value channels, then their 32 gate channels),
+// bias packed the same way; out [M, d] bf16.
+int gemm_tc_launch_glu(const void* A, const void* W, int64_t M, int N, int K, const float* bias, void* out, cudaStream_t st) {
+  LCASR_TRY(gemm_tc_check_common(A, W, M, N, K, bias, out));
+  LCASR_CHECK_ARG(N % 64 == 0 && ((N % 256 == 0) || N > 512), "gemm_glu: N=%d needs the 256-column tile form (N %% 64 == 0, N > 512 or N %% 256 == 0)", N);
+  TgEpilogue ep{bias, nullptr, 0.f, LCASR_ACT_NONE, nullptr, 0};
+  return launch_tc_cg<256, bf16, TG_EPI_GLU>(A, W, M, N, K, ep, out, st);
 }
 
 }  // namespace lcasr

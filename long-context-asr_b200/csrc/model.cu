@@ -12,9 +12,13 @@
 #include "common.cuh"
 #include <vector>
 #include <new>
+#include <cstdlib>
 
 namespace lcasr {
 int attn_tc_available();
+int gemm_tc_launch_rope(const void* A, const void* W, int64_t M, int N, int K, const float* cos_t, const float* sin_t,
+                        int64_t rope_n, int rope_cols, int dh, void* out, cudaStream_t st);
+int gemm_tc_launch_glu(const void* A, const void* W, int64_t M, int N, int K, const float* bias, void* out, cudaStream_t st);
 }
 
 using namespace lcasr;
@@ -144,6 +148,8 @@ extern "C" int lcasr_model_forward_lengths(lcasr_model* m, const float* spec, in
   const int gi = m->gemm_impl;
   int ai = m->attn_impl;
   if (ai == LCASR_ATTN_AUTO) ai = (cd == LCASR_BF16 && attn_tc_available()) ? LCASR_ATTN_TCGEN05 : LCASR_ATTN_SIMT;
+  void* const a2 = a;  // attention output (the LayerNorm output in `a` is dead once the qkv GEMM has run)
+  static const bool no_fuse = getenv("LCASR_NO_FUSED_EPILOGUES") != nullptr;  // A/B switch: separate rope_split / glu passes
   const int vt = 0;  // natural [B,N,H,Dh] V: the tcgen05 kernel consumes it as an MN-major B operand (no transpose pass)
 
   cudaStream_t cst = (cudaStream_t)stream;
@@ -212,19 +218,40 @@ extern "C" int lcasr_model_forward_lengths(lcasr_model* m, const float* spec, in
     LCASR_TRY(ffn(L.ff1_norm_w, L.ff1_norm_b, L.ff1_fc1_w, L.ff1_fc1_b, L.ff1_fc2_w, L.ff1_fc2_b));
     // attention (attention.py:509-551)
     LCASR_TRY(norm(L.attn_norm_w, L.attn_norm_b, nullptr, a));
+    // bf16 tensor-core path: rotary in the epilogue of the qkv GEMM (q / k rotated in fp32 before the bf16 store) and
+    // attention reading q, k, v as column blocks of the projection — the split / rotate pass (3 reads + 3 writes of M*d) is gone
+    const bool fused_qkv = !no_fuse && cd == LCASR_BF16 && gi != LCASR_GEMM_SIMT && ai == LCASR_ATTN_TCGEN05 && d % 32 == 0 &&
+                           c.attn_window_left < 0 && c.attn_window_right < 0 && (!c.use_rotary || L.qkv_w_il);
+    if (fused_qkv) {
+      if (c.use_rotary) {
+        begin(CAT_GEMM);
+        LCASR_TRY(timed(CAT_GEMM, gemm_tc_launch_rope(a, L.qkv_w_il, M, 3 * d, d, cos_t, sin_t, N, 2 * d, Dh, wide, cst)));
+      } else {
+        LCASR_TRY(gemm(a, L.qkv_w, M, 3 * d, d, nullptr, LCASR_ACT_NONE, nullptr, 0.f, wide, cd));
+      }
+      OP(CAT_ATTN, lcasr_attention_qkv(wide, B, N, tok_len, H, Dh, a2, stream));
+    } else {
     LCASR_TRY(gemm(a, L.qkv_w, M, 3 * d, d, nullptr, LCASR_ACT_NONE, nullptr, 0.f, wide, cd));
     OP(CAT_ROPE, lcasr_rope_split(wide, cd, B, N, H, Dh, c.use_rotary ? cos_t : nullptr, c.use_rotary ? sin_t : nullptr, q, k,
                                v, vt, p.Npad, stream));
     if (c.attn_window_left >= 0 || c.attn_window_right >= 0)
-      OP(CAT_ATTN, lcasr_attention_window(q, k, v, cd, B, N, tok_len, H, Dh, c.attn_window_left, c.attn_window_right, a, ai, stream));
-    else if (tok_len) OP(CAT_ATTN, lcasr_attention_masked(q, k, v, cd, B, N, N, tok_len, H, Dh, a, ai, stream));
-    else OP(CAT_ATTN, lcasr_attention(q, k, v, cd, B, N, H, Dh, vt, p.Npad, a, ai, stream));
-    LCASR_TRY(gemm(a, L.out_w, M, d, d, nullptr, LCASR_ACT_NONE, x, 1.0f, x, LCASR_F32));
+      OP(CAT_ATTN, lcasr_attention_window(q, k, v, cd, B, N, tok_len, H, Dh, c.attn_window_left, c.attn_window_right, a2, ai, stream));
+    else if (tok_len) OP(CAT_ATTN, lcasr_attention_masked(q, k, v, cd, B, N, N, tok_len, H, Dh, a2, ai, stream));
+    else OP(CAT_ATTN, lcasr_attention(q, k, v, cd, B, N, H, Dh, vt, p.Npad, a2, ai, stream));
+    }
+    LCASR_TRY(gemm(a2, L.out_w, M, d, d, nullptr, LCASR_ACT_NONE, x, 1.0f, x, LCASR_F32));
     // convolution module (convolution.py:103-124)
     LCASR_TRY(norm(L.conv_norm_w, L.conv_norm_b, nullptr, a));
-    LCASR_TRY(gemm(a, L.pw1_w, M, 2 * d, d, L.pw1_b, LCASR_ACT_NONE, nullptr, 0.f, wide, cd));
-    if (tok_len) OP(CAT_CONVMOD, lcasr_glu_masked(wide, cd, B, N, d, tok_len, q, stream));
-    else OP(CAT_CONVMOD, lcasr_glu(wide, cd, M, d, q, stream));
+    const bool fused_glu = !no_fuse && cd == LCASR_BF16 && gi != LCASR_GEMM_SIMT && !tok_len && L.pw1_w_glu && L.pw1_b_glu &&
+                           (2 * d) % 64 == 0 && ((2 * d) % 256 == 0 || 2 * d > 512);
+    if (fused_glu) {  // GLU in the epilogue of pointwise_conv1: the [M, 2d] pre-activation never reaches HBM
+      begin(CAT_GEMM);
+      LCASR_TRY(timed(CAT_GEMM, gemm_tc_launch_glu(a, L.pw1_w_glu, M, 2 * d, d, L.pw1_b_glu, q, cst)));
+    } else {
+      LCASR_TRY(gemm(a, L.pw1_w, M, 2 * d, d, L.pw1_b, LCASR_ACT_NONE, nullptr, 0.f, wide, cd));
+      if (tok_len) OP(CAT_CONVMOD, lcasr_glu_masked(wide, cd, B, N, d, tok_len, q, stream));
+      else OP(CAT_CONVMOD, lcasr_glu(wide, cd, M, d, q, stream));
+    }
     OP(CAT_CONVMOD, lcasr_dwconv_brn_silu(q, cd, B, N, d, c.conv_kernel_size, L.dw_w, L.dw_b, L.brn_mean, L.brn_std, L.brn_w,
                                     L.brn_b, k, cd, stream));
     LCASR_TRY(gemm(k, L.pw2_w, M, d, d, L.pw2_b, LCASR_ACT_NONE, x, 1.0f, x, LCASR_F32));

@@ -383,9 +383,22 @@ class SCConformerXL(nn.Module):
             # attention.py:485: rows ordered (h, dh, qkv) -> de-interleave once to [q | k | v]
             qkv = sd[p + "attend.fn.qkv_proj.weight"].reshape(H, Dh, 3, d).permute(2, 0, 1, 3).reshape(3 * H * Dh, d)
             put(lw, "qkv_w", mat(qkv)); put(lw, "out_w", mat(sd[p + "attend.fn.out_proj.weight"]))
+            # fused-rotary form: inside every q / k head interleave the two rotate_half halves (rotary_emb.py:61-66 pairs
+            # (i, i + Dh/2)) so that a rotation pair is two adjacent output columns of the qkv GEMM
+            qk = qkv[: 2 * H * Dh].reshape(2 * H, Dh, d)
+            qk_il = torch.stack([qk[:, : Dh // 2], qk[:, Dh // 2:]], dim=2).reshape(2 * H * Dh, d)
+            put(lw, "qkv_w_il", mat(torch.cat([qk_il, qkv[2 * H * Dh:]], 0)) if cdt == torch.bfloat16 and self.use_rotary else None)
             nw, nb = norm_wb(p + "conv.norm")
             put(lw, "conv_norm_w", nw); put(lw, "conv_norm_b", nb)
             put(lw, "pw1_w", mat(sd[p + "conv.fn.pointwise_conv1.weight"].reshape(2 * d, d))); put(lw, "pw1_b", vec(p + "conv.fn.pointwise_conv1.bias"))
+            if cdt == torch.bfloat16 and d % 32 == 0:  # fused-GLU form: 64-row blocks [32 value channels | their 32 gate channels]
+                w1 = sd[p + "conv.fn.pointwise_conv1.weight"].reshape(2 * d, d)
+                b1 = sd[p + "conv.fn.pointwise_conv1.bias"]
+                put(lw, "pw1_w_glu", mat(torch.stack([w1[:d].reshape(d // 32, 32, d), w1[d:].reshape(d // 32, 32, d)], 1).reshape(2 * d, d)))
+                put(lw, "pw1_b_glu", torch.stack([b1[:d].reshape(d // 32, 32), b1[d:].reshape(d // 32, 32)], 1).reshape(2 * d)
+                    .to(device=device, dtype=torch.float32).contiguous())
+            else:
+                put(lw, "pw1_w_glu", None); put(lw, "pw1_b_glu", None)
             put(lw, "dw_w", vec(p + "conv.fn.depthwise_conv.weight").reshape(d, self.conv_kernel_size).contiguous())
             put(lw, "dw_b", vec(p + "conv.fn.depthwise_conv.bias"))
             put(lw, "brn_mean", vec(p + "conv.fn.batch_norm.running_mean")); put(lw, "brn_std", vec(p + "conv.fn.batch_norm.running_std"))

@@ -273,3 +273,31 @@ def attention_merge(parts, lses, H: int, Dh: int, out_dtype=torch.bfloat16):
     out = torch.empty(rows, d, dtype=out_dtype, device=parts.device)
     L.call("lcasr_attention_merge", L.ptr(parts), L.ptr(lses), P, rows, H, Dh, L.ptr(out), L.dtype_code(out_dtype), _s())
     return out
+
+
+def gemm_rope(a, w_il, cos, sin, rope_n: int, rope_cols: int, Dh: int):
+    """qkv projection with the rotary embedding in the GEMM epilogue (w_il: interleaved q / k head rows); bf16 [M, N]"""
+    _cuda(a, w_il, cos, sin)
+    M, K = a.shape
+    N = w_il.shape[0]
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    L.call("lcasr_gemm_rope", L.ptr(a), L.ptr(w_il), M, N, K, L.ptr(cos), L.ptr(sin), int(rope_n), int(rope_cols), int(Dh), L.ptr(out), _s())
+    return out
+
+
+def gemm_glu(a, w_glu, b_glu):
+    """pointwise_conv1 + GLU in one kernel (w_glu / b_glu: 64-row blocks [32 value | 32 gate channels]); bf16 [M, N/2]"""
+    _cuda(a, w_glu, b_glu)
+    M, K = a.shape
+    N = w_glu.shape[0]
+    out = torch.empty(M, N // 2, dtype=torch.bfloat16, device=a.device)
+    L.call("lcasr_gemm_glu", L.ptr(a), L.ptr(w_glu), M, N, K, L.ptr(b_glu), L.ptr(out), _s())
+    return out
+
+
+def attention_qkv(qkv, B: int, N: int, H: int, Dh: int, kv_len=None):
+    """attention reading q, k, v as the column blocks of the [B*N, 3*H*Dh] projection (no split pass); bf16 [B, N, H*Dh]"""
+    _cuda(qkv, kv_len)
+    out = torch.empty(B, N, H * Dh, dtype=torch.bfloat16, device=qkv.device)
+    L.call("lcasr_attention_qkv", L.ptr(qkv), B, N, L.ptr(kv_len), H, Dh, L.ptr(out), _s())
+    return out

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, f"declared in the header but not exported: {missing}"
     assert set(lcasr_b200._lib.EXPORTED_SYMBOLS) <= declared
-    assert lib.lcasr_abi_version() == 2
+    assert lib.lcasr_abi_version() == lcasr_b200._lib.ABI_VERSION == 3
 
 
 def test_out_length_host_function():

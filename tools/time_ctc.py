@@ -9,7 +9,7 @@ from lcasr_b200 import ops
 ap = argparse.ArgumentParser()
 ap.add_argument("--N", type=int, default=45000); ap.add_argument("--B", type=int, default=1)
 ap.add_argument("--V", type=int, default=4096); ap.add_argument("--frac", type=float, default=0.3)
-ap.add_argument("--bwd", action="store_true")
+ap.add_argument("--bwd", action="store_true"); ap.add_argument("--quick", action="store_true", help="only the wavefront forward (kernel experiments)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 S = int(a.frac * a.N)
@@ -23,6 +23,10 @@ def t(fn, n=3):
     for _ in range(n): fn()
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e3
 nll, _ = ops.ctc_loss_fwd(lp, tgt, il, tl, a.V - 1)
+if a.quick:
+    print(f"N={a.N} S={S} B={a.B} TB={os.environ.get('LCASR_CTC_WF_TB', '16')} DBG={os.environ.get('LCASR_CTC_WF_DBG', '0')}: "
+          f"wavefront fwd {t(lambda: ops.ctc_loss_fwd(lp, tgt, il, tl, a.V - 1), 5):.2f} ms, nll {nll.tolist()[:2]}")
+    sys.exit(0)
 ref = torch.nn.functional.ctc_loss(lp.transpose(0, 1), tgt, il.long(), tl, blank=a.V - 1, reduction="none")
 print(f"N={a.N} S={S} B={a.B}: ours nll {nll.tolist()} torch {ref.tolist()}")
 from lcasr_b200 import _lib as L
