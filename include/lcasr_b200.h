@@ -83,7 +83,8 @@ int lcasr_gemm(const void* A, const void* W, int ab_dtype, int64_t M, int N, int
 
 /* The qkv projection with the rotary embedding applied in the GEMM epilogue (attention.py:483 + :499-507 in one kernel;
  * bf16, tcgen05): W = qkv weights with interleaved q / k head rows (see lcasr_layer_weights.qkv_w_il); out [M, N] bf16 =
- * [q | k | v] with columns < rope_cols rotated by cos/sin [rope_n, Dh/2] (position = row % rope_n) in fp32 before the store.
+ * [q | k | v] with columns < rope_cols rotated by the PAIR-MAJOR tables cos/sin [Dh/2, rope_n] of lcasr_rope_table_t
+ * (position = row % rope_n) in fp32 before the store.
  * q.k^T is invariant under the common permutation of the head dimension, so lcasr_attention_qkv on this output equals
  * lcasr_rope_split + lcasr_attention on the plain projection. */
 int lcasr_gemm_rope(const void* A, const void* W, int64_t M, int N, int K, const float* cos_t, const float* sin_t,
@@ -109,6 +110,11 @@ int lcasr_glu(const void* in, int dtype, int64_t M, int d, void* out, void* stre
  * angle = fp32(pos_offset + n) / interp * inv_freq[j]. */
 int lcasr_rope_table(const float* inv_freq, float interp, int64_t pos_offset, int64_t N, int half,
                      float* cos_out, float* sin_out, void* stream);
+
+/* The same tables written pair-major, cos/sin [Dh/2, N] — the layout lcasr_gemm_rope reads (one pair index of 32
+ * consecutive token positions is one coalesced 128-byte line for the epilogue warp that owns those 32 rows). */
+int lcasr_rope_table_t(const float* inv_freq, float interp, int64_t pos_offset, int64_t N, int half,
+                       float* cos_out, float* sin_out, void* stream);
 
 /* The qkv split + rotary of Attention.forward (attention.py:485 "b n (h d qkv)", :499-506,
  * rotary_emb.py:61-73).  qkv [B*N, 3*H*Dh] holds the projection computed with DE-INTERLEAVED

@@ -81,6 +81,7 @@ _SIGNATURES = {
     "lcasr_attention_qkv": [vp, i32, i64, vp, i32, i32, vp, vp],
     "lcasr_glu": [vp, i32, i64, i32, vp, vp],
     "lcasr_rope_table": [vp, f32, i64, i64, i32, vp, vp, vp],
+    "lcasr_rope_table_t": [vp, f32, i64, i64, i32, vp, vp, vp],
     "lcasr_rope_split": [vp, i32, i32, i64, i32, i32, vp, vp, vp, vp, vp, i32, i64, vp],
     "lcasr_attention": [vp, vp, vp, i32, i32, i64, i32, i32, i32, i64, vp, i32, vp],
     "lcasr_attention_cross": [vp, vp, vp, i32, i32, i64, i64, i32, i32, vp, i32, vp],

@@ -791,6 +791,8 @@ static int launch_attn_tc2(const void* q, const void* k, const void* v, int B, i
 
 
 int attn_tc_available() { return 1; }
+int attn_tc4_launch(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len, int H,
+                    void* out, float* lse, cudaStream_t st, float* out32, int64_t ldq, int64_t ldkv);
 
 }  // namespace lcasr
 // debug hooks (not part of the public header): phase trace of the v2 attention kernel
@@ -847,6 +849,10 @@ int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N
   LCASR_CHECK_ARG((int64_t)B * N < ((int64_t)1 << 31) && (int64_t)B * Nk < ((int64_t)1 << 31), "attention(tcgen05): B*N too large");
   LCASR_CHECK_ARG(!v_transposed || Npad % 8 == 0, "attention(tcgen05): Npad must be a multiple of 8");
   LCASR_CHECK_ARG(H <= 65535 && B <= 65535, "attention(tcgen05): too many heads / batch entries");
+  // head dim 32: the four-stream kernel (attn_tc4.cu; two independent 64-key softmax streams per query tile)
+  static const int v4 = getenv("LCASR_ATTN_V4") ? atoi(getenv("LCASR_ATTN_V4")) : 0;
+  if (v4 && Dh == 32 && !v_transposed && wl < 0 && wr < 0)
+    return attn_tc4_launch(q, k, v, B, N, Nk, kv_len, H, out, lse, st, out32, ldq, ldkv);
   static const bool force_v1 = getenv("LCASR_ATTN_V1") != nullptr;  // debugging aid: one query tile per CTA
   // fraction of exponentials evaluated on the FMA pipes: POLY=p -> every p-th odd key, i.e. 1/(2p) of all
   static const int poly_env = getenv("LCASR_ATTN_POLY") ? atoi(getenv("LCASR_ATTN_POLY")) : 0;  // measured: the Dh=32 kernel is latency- not MUFU-bound, offload does not pay yet

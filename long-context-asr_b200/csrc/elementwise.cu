@@ -26,12 +26,15 @@ __global__ void __launch_bounds__(256) glu_kernel(const T* __restrict__ in, int6
 }
 
 // ---- rotary tables (rotary_emb.py:52-56): fp32 t = pos / interp ; ang = t * inv_freq ----------
+// TRANSPOSED: tables are written pair-major [half, N] (the layout the fused-rotary GEMM epilogue reads: a warp's 32 lanes
+// are 32 consecutive token positions, so one pair index is one coalesced 128-byte line)
+template <bool TRANSPOSED>
 __global__ void rope_table_kernel(const float* __restrict__ inv_freq, float interp, int64_t pos_offset, int64_t N,
                                   int half, float* __restrict__ cos_out, float* __restrict__ sin_out) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * half) return;
-  int64_t n = idx / half;
-  int j = (int)(idx % half);
+  const int64_t n = TRANSPOSED ? idx % N : idx / half;
+  const int j = (int)(TRANSPOSED ? idx / N : idx % half);
   float t = (float)(pos_offset + n) / interp;
   float ang = t * inv_freq[j];
   float s, c;
@@ -169,8 +172,18 @@ extern "C" int lcasr_rope_table(const float* inv_freq, float interp, int64_t pos
                                 float* cos_out, float* sin_out, void* stream) {
   LCASR_CHECK_ARG(inv_freq && cos_out && sin_out && N > 0 && half > 0 && interp > 0.f, "rope_table: bad arguments");
   int64_t total = N * half;
-  rope_table_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(inv_freq, interp, pos_offset, N,
-                                                                                       half, cos_out, sin_out);
+  rope_table_kernel<false><<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(inv_freq, interp, pos_offset, N,
+                                                                                              half, cos_out, sin_out);
+  LCASR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lcasr_rope_table_t(const float* inv_freq, float interp, int64_t pos_offset, int64_t N, int half,
+                                  float* cos_out, float* sin_out, void* stream) {
+  LCASR_CHECK_ARG(inv_freq && cos_out && sin_out && N > 0 && half > 0 && interp > 0.f, "rope_table_t: bad arguments");
+  int64_t total = N * half;
+  rope_table_kernel<true><<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(inv_freq, interp, pos_offset, N,
+                                                                                             half, cos_out, sin_out);
   LCASR_LAUNCH_CHECK();
   return 0;
 }

@@ -60,7 +60,7 @@ struct TgEpilogue {
   // EPI == TG_EPI_ROPE (fused rotary, attention.py:499-507 / rotary_emb.py:61-73): output columns < rope_cols are rotated in
   // fp32 before the bf16 store.  The weight rows of every q / k head were interleaved on the host (new 2i <- old i,
   // new 2i+1 <- old i + Dh/2), so a rotation pair is two ADJACENT columns: y[2i] = x[2i] c_i - x[2i+1] s_i,
-  // y[2i+1] = x[2i+1] c_i + x[2i] s_i with c/s = tables[pos, i], pos = row % rope_n.  (q.k is invariant under a common
+  // y[2i+1] = x[2i+1] c_i + x[2i] s_i with c/s = tables[i, pos] (pair-major, lcasr_rope_table_t), pos = row % rope_n.  (q.k is invariant under a common
   // permutation of the head dimension, so attention sees exactly the reference's scores.)
   const float* rope_cos = nullptr;
   const float* rope_sin = nullptr;
@@ -186,19 +186,20 @@ __device__ __forceinline__ void tg_stage_chunk64(const uint32_t (&r0)[32], const
     if constexpr (EPI == TG_EPI_ROPE) {
       const int colh = col0 + 32 * hh;
       if (colh < ep.rope_cols) {  // warp-uniform: a q / k column block (v passes through)
-        const int j0 = (colh % ep.rope_dh) >> 1;  // first rotation pair of this 32-column block inside its head
-        const float4* cp = reinterpret_cast<const float4*>(cos_row + j0);
-        const float4* sp = reinterpret_cast<const float4*>(sin_row + j0);
+        // tables are pair-major [Dh/2][rope_n]: the warp's lanes are consecutive token positions, so each of the 16 pair
+        // indices of this block is ONE coalesced line (position-major tables cost 32 lines per load: measured +60 us per GEMM)
+        const int64_t j0 = (int64_t)((colh % ep.rope_dh) >> 1) * ep.rope_n;
+        float cv[16], sv[16];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {  // 4 pairs = 8 columns per step
-          const float4 cc = __ldg(cp + g), ss = __ldg(sp + g);
-          const float cv[4] = {cc.x, cc.y, cc.z, cc.w}, sv[4] = {ss.x, ss.y, ss.z, ss.w};
+        for (int i = 0; i < 16; ++i) {
+          cv[i] = __ldg(cos_row + j0 + i * ep.rope_n);
+          sv[i] = __ldg(sin_row + j0 + i * ep.rope_n);
+        }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float a = y[8 * g + 2 * i], b = y[8 * g + 2 * i + 1];
-            y[8 * g + 2 * i] = fmaf(a, cv[i], -b * sv[i]);
-            y[8 * g + 2 * i + 1] = fmaf(b, cv[i], a * sv[i]);
-          }
+        for (int i = 0; i < 16; ++i) {
+          const float a = y[2 * i], b = y[2 * i + 1];
+          y[2 * i] = fmaf(a, cv[i], -b * sv[i]);
+          y[2 * i + 1] = fmaf(b, cv[i], a * sv[i]);
         }
       }
     }
@@ -431,8 +432,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if constexpr (EPI == TG_EPI_ROPE) {  // this lane's token position -> its table rows (clamped for rows beyond M)
             const int64_t rr = row0 + lane < M ? row0 + lane : M - 1;
             const int64_t pos = rr % ep.rope_n;
-            cos_row = ep.rope_cos + pos * (ep.rope_dh >> 1);
-            sin_row = ep.rope_sin + pos * (ep.rope_dh >> 1);
+            cos_row = ep.rope_cos + pos;  // pair-major tables: element (j, pos) at j * rope_n + pos
+            sin_row = ep.rope_sin + pos;
           }
           tmem_wait_ld();
           const uint32_t stg = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES + (warp - 2) * 4096;
@@ -640,7 +641,6 @@ int gemm_tc_launch_rope(const void* A, const void* W, int64_t M, int N, int K, c
   LCASR_CHECK_ARG(cos_t && sin_t && rope_n > 0, "gemm_rope: NULL tables");
   LCASR_CHECK_ARG(dh >= 32 && dh % 32 == 0 && rope_cols % 64 == 0 && rope_cols <= N && N % 64 == 0,
                   "gemm_rope: head_dim %d / rotated columns %d / N %d not supported", dh, rope_cols, N);
-  LCASR_CHECK_ARG(((uintptr_t)cos_t & 15) == 0 && ((uintptr_t)sin_t & 15) == 0 && (dh / 2) % 4 == 0, "gemm_rope: tables must be 16-byte aligned");
   TgEpilogue ep{nullptr, nullptr, 0.f, LCASR_ACT_NONE, nullptr, 0};
   ep.rope_cos = cos_t; ep.rope_sin = sin_t; ep.rope_cols = rope_cols; ep.rope_dh = dh; ep.rope_n = rope_n;
   const bool wide = (N % 256 == 0) || N > 512;

@@ -200,8 +200,13 @@ extern "C" int lcasr_model_forward_lengths(lcasr_model* m, const float* spec, in
     LCASR_TRY(gemm(s3a, w.pw2_w, (int64_t)B * N * p.F3, C, C, w.pw2_b, LCASR_ACT_SILU, nullptr, 0.f, s3b, cd));
     LCASR_TRY(gemm(s3b, w.sub_out_w, M, d, p.F3 * C, nullptr, LCASR_ACT_NONE, nullptr, 0.f, x, LCASR_F32));
   }
-  if (c.use_rotary)
-    OP(CAT_ROPE, lcasr_rope_table(w.inv_freq, c.rotary_interp, 0, N, Dh / 2, cos_t, sin_t, stream));
+  // fused rotary (bf16 tensor-core path) reads pair-major tables; the split / rotate kernel position-major ones
+  const bool fused_rope_tables = !no_fuse && cd == LCASR_BF16 && gi != LCASR_GEMM_SIMT && ai == LCASR_ATTN_TCGEN05 && d % 32 == 0 &&
+                                 c.attn_window_left < 0 && c.attn_window_right < 0 && m->layers[0].qkv_w_il;
+  if (c.use_rotary) {
+    if (fused_rope_tables) OP(CAT_ROPE, lcasr_rope_table_t(w.inv_freq, c.rotary_interp, 0, N, Dh / 2, cos_t, sin_t, stream));
+    else OP(CAT_ROPE, lcasr_rope_table(w.inv_freq, c.rotary_interp, 0, N, Dh / 2, cos_t, sin_t, stream));
+  }
 
   auto ffn = [&](const float* nw, const float* nb, const void* fc1, const float* b1, const void* fc2, const float* b2) {
     LCASR_TRY(norm(nw, nb, nullptr, a));
@@ -221,7 +226,7 @@ extern "C" int lcasr_model_forward_lengths(lcasr_model* m, const float* spec, in
     // bf16 tensor-core path: rotary in the epilogue of the qkv GEMM (q / k rotated in fp32 before the bf16 store) and
     // attention reading q, k, v as column blocks of the projection — the split / rotate pass (3 reads + 3 writes of M*d) is gone
     const bool fused_qkv = !no_fuse && cd == LCASR_BF16 && gi != LCASR_GEMM_SIMT && ai == LCASR_ATTN_TCGEN05 && d % 32 == 0 &&
-                           c.attn_window_left < 0 && c.attn_window_right < 0 && (!c.use_rotary || L.qkv_w_il);
+                           c.attn_window_left < 0 && c.attn_window_right < 0 && (!c.use_rotary || (L.qkv_w_il && fused_rope_tables));
     if (fused_qkv) {
       if (c.use_rotary) {
         begin(CAT_GEMM);

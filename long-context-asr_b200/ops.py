@@ -92,12 +92,14 @@ def glu(x):
     return out
 
 
-def rope_table(inv_freq, interp: float, N: int, offset: int = 0):
+def rope_table(inv_freq, interp: float, N: int, offset: int = 0, transposed: bool = False):
+    """cos / sin [N, Dh/2]; transposed=True: pair-major [Dh/2, N] (the layout gemm_rope reads)"""
     _cuda(inv_freq)
     half = inv_freq.numel()
-    cos = torch.empty(N, half, dtype=torch.float32, device=inv_freq.device)
+    cos = torch.empty((half, N) if transposed else (N, half), dtype=torch.float32, device=inv_freq.device)
     sin = torch.empty_like(cos)
-    L.call("lcasr_rope_table", L.ptr(inv_freq), float(interp), offset, N, half, L.ptr(cos), L.ptr(sin), _s())
+    L.call("lcasr_rope_table_t" if transposed else "lcasr_rope_table", L.ptr(inv_freq), float(interp), offset, N, half,
+           L.ptr(cos), L.ptr(sin), _s())
     return cos, sin
 
 
@@ -276,7 +278,8 @@ def attention_merge(parts, lses, H: int, Dh: int, out_dtype=torch.bfloat16):
 
 
 def gemm_rope(a, w_il, cos, sin, rope_n: int, rope_cols: int, Dh: int):
-    """qkv projection with the rotary embedding in the GEMM epilogue (w_il: interleaved q / k head rows); bf16 [M, N]"""
+    """qkv projection with the rotary embedding in the GEMM epilogue (w_il: interleaved q / k head rows; cos / sin:
+    pair-major tables from rope_table(..., transposed=True)); bf16 [M, N]"""
     _cuda(a, w_il, cos, sin)
     M, K = a.shape
     N = w_il.shape[0]

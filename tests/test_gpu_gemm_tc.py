@@ -69,7 +69,9 @@ def test_fused_rotary_epilogue_and_strided_attention(cuda_device, Dh, H, N, B):
     w = w.to(cuda_device)
     inv_freq = (1.0 / (1500000 ** (torch.arange(0, Dh, 2).float() / Dh))).to(cuda_device)
     cos, sin = ops.rope_table(inv_freq, 1.0, N)
-    fused = ops.attention_qkv(ops.gemm_rope(a, w_il, cos, sin, N, 2 * d, Dh), B, N, H, Dh)
+    cos_t, sin_t = ops.rope_table(inv_freq, 1.0, N, transposed=True)
+    assert torch.equal(cos_t.t().contiguous(), cos) and torch.equal(sin_t.t().contiguous(), sin)
+    fused = ops.attention_qkv(ops.gemm_rope(a, w_il, cos_t, sin_t, N, 2 * d, Dh), B, N, H, Dh)
     q, k, v = ops.rope_split(ops.gemm(a, w), B, N, H, Dh, cos, sin)
     unfused = ops.attention(q, k, v)
     err = (fused.float() - unfused.float()).abs().max().item()
