@@ -737,6 +737,19 @@ def main():
         ctc_cuda = float(ctc(out["final_posteriors"].transpose(0, 1), tgt, in_len, tl).item())
         line["parity"] = parity_report(cfg, lp_cuda, r["lp"].float(), greedy_cuda, r["greedy"], ctc_cuda, args.dtype)
         line["parity"]["against"] = r["kind"]
+        if args.dtype == "bf16":  # north_star's fp32-mode criteria on the same weights and input (1e-4, identical greedy tokens)
+            del out, lp_cuda
+            m32 = lcasr_b200.SCConformerXL(**cfg, compute_dtype="fp32")
+            m32.load_state_dict(sd, strict=True)
+            m32 = m32.to(dev).eval()
+            o32 = m32(x)
+            t32, c32 = lcasr_b200.ops.greedy_collapse(m32.last_argmax, V)
+            t32, c32 = t32.cpu(), c32.cpu()
+            g32 = [t32[b, : int(c32[b])].tolist() for b in range(B)]
+            ctc32 = float(ctc(o32["final_posteriors"].transpose(0, 1), tgt, in_len, tl).item())
+            p32 = parity_report(cfg, o32["final_posteriors"].cpu(), r["lp"].float(), g32, r["greedy"], ctc32, "fp32")
+            line["parity"]["fp32_mode"] = {k: p32[k] for k in ("max_abs", "bar", "within_bar", "greedy_equal", "argmax_agree", "ctc_rel")}
+            del m32, o32
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line))

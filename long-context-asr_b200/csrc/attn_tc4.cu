@@ -13,7 +13,7 @@
 // 16 softmax warps = 4 per SM sub-partition, each handling 32 rows x 64 columns per key tile.
 //
 //   warps 0-15  softmax: warp w -> TMEM lane quarter w % 4, stream w / 4 (t = stream / 2, h = stream % 2)
-//   warp 16     TMA producer (Q once, K/V tiles into a 4-deep ring)         warp 17  MMA issuer        (18, 19 idle)
+//   warp 16     TMA producer (Q once, K/V tiles into a 4-deep ring)         warp 17  MMA issuer
 // TMEM (512 columns): S_A [0,128) | S_B [128,256) | P[t][h] 4 x 32 at 256 | O[t][h] 4 x 32 at 384.
 // Per key tile the issuer emits QK_t (M128 N128 K32) when S_t has been read by all 8 warps of tile t, and
 // PV_{t,h} (M128 N32 K64, A = P from tensor memory, B = V rows [64h, 64h+64) MN-major) when stream (t, h) published P.
@@ -29,7 +29,9 @@ using namespace ptx;
 namespace {
 
 constexpr int F4_DH = 32, F4_BQ = 128, F4_BK = 128, F4_HK = 64;  // HK: keys per stream and tile
-constexpr int F4_THREADS = 640, F4_STAGES = 4;
+constexpr int F4_THREADS = 576, F4_STAGES = 4;  // 16 softmax warps + TMA producer + MMA issuer: 112 registers each, no setmaxnreg
+// (setmaxnreg can only redistribute what the CTA was launched with: 640 x 96 would leave the softmax warps 112 as well,
+//  and an issuer squeezed into 24 registers spills its whole state)
 constexpr int F4_ROW_BYTES = 64;                       // one 32-element bf16 row; SWIZZLE_64B
 constexpr int F4_Q_BYTES = 2 * F4_BQ * F4_ROW_BYTES;   // both query tiles
 constexpr int F4_K_BYTES = F4_BK * F4_ROW_BYTES;
@@ -39,7 +41,7 @@ constexpr int F4_EX_BYTES = 2 * F4_BQ * (F4_EXO_STRIDE + 2) * 4;
 constexpr int F4_SMEM_BYTES = F4_Q_BYTES + F4_STAGES * F4_STAGE_BYTES + F4_EX_BYTES + 1024;
 constexpr int F4_P_COL = 256, F4_O_COL = 384;
 
-__global__ void __launch_bounds__(F4_THREADS, 1)
+__global__ void __maxnreg__(112)  // 576 threads x 112 registers = 63 of the SM's 64 K (ptxas sizes __launch_bounds__(576) like 640 threads: 96)
 attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, int64_t N, int64_t Nk, const int32_t* __restrict__ kv_len, int H,
                 float scale_log2, bf16* __restrict__ out, float* __restrict__ lse, float* __restrict__ out32) {
@@ -86,7 +88,6 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
 
   if (warp >= 16) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if (warp == 16) {
       if (lane == 0) {  // ------------------------- TMA producer -------------------------
         const int row_q = (int)(b * N + q0);
@@ -192,15 +193,14 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (idle_t0 == 0) idle_t0 = now;
           else if (now - idle_t0 > 4000000000ull) {
             if (lane == 0)
-              printf("lcasr_b200: attention(4-stream) MMA issuer stalled (block %d,%d,%d pv %d %d %d %d of %d)\n", blockIdx.x,
-                     blockIdx.y, blockIdx.z, pv_n[0], pv_n[1], pv_n[2], pv_n[3], n_tiles);
+              printf("lcasr_b200: attention(4-stream) MMA issuer stalled (block %d,%d,%d qk %d %d pv %d %d %d %d of %d)\n", blockIdx.x,
+                     blockIdx.y, blockIdx.z, qk_n[0], qk_n[1], pv_n[0], pv_n[1], pv_n[2], pv_n[3], n_tiles);
             asm volatile("trap;");
           }
         }
       }
     }
   } else {  // ------------------------- softmax warps -------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
     const int st = warp >> 2;                // stream
     const int t = st >> 1, hh = st & 1;      // query tile, key half
     const int lane_base = (warp & 3) * 32;   // TMEM lane quarter == warp_id % 4
