@@ -29,9 +29,9 @@ using namespace ptx;
 namespace {
 
 constexpr int F4_DH = 32, F4_BQ = 128, F4_BK = 128, F4_HK = 64;  // HK: keys per stream and tile
-constexpr int F4_THREADS = 576, F4_STAGES = 4;  // 16 softmax warps + TMA producer + MMA issuer: 112 registers each, no setmaxnreg
-// (setmaxnreg can only redistribute what the CTA was launched with: 640 x 96 would leave the softmax warps 112 as well,
-//  and an issuer squeezed into 24 registers spills its whole state)
+constexpr int F4_THREADS = 640, F4_STAGES = 4;  // 16 softmax warps + one warpgroup for the TMA producer and the MMA issuer
+// Registers: the SM allocates them per 4 warps, so 20 warps launch with 96 each (61440 in all) and setmaxnreg can only
+// REDISTRIBUTE that total: producer / issuer warpgroup down to 40, softmax warps up to 104 (128*40 + 512*104 = 58368).
 constexpr int F4_ROW_BYTES = 64;                       // one 32-element bf16 row; SWIZZLE_64B
 constexpr int F4_Q_BYTES = 2 * F4_BQ * F4_ROW_BYTES;   // both query tiles
 constexpr int F4_K_BYTES = F4_BK * F4_ROW_BYTES;
@@ -41,7 +41,7 @@ constexpr int F4_EX_BYTES = 2 * F4_BQ * (F4_EXO_STRIDE + 2) * 4;
 constexpr int F4_SMEM_BYTES = F4_Q_BYTES + F4_STAGES * F4_STAGE_BYTES + F4_EX_BYTES + 1024;
 constexpr int F4_P_COL = 256, F4_O_COL = 384;
 
-__global__ void __maxnreg__(112)  // 576 threads x 112 registers = 63 of the SM's 64 K (ptxas sizes __launch_bounds__(576) like 640 threads: 96)
+__global__ void __launch_bounds__(F4_THREADS, 1)
 attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, int64_t N, int64_t Nk, const int32_t* __restrict__ kv_len, int H,
                 float scale_log2, bf16* __restrict__ out, float* __restrict__ lse, float* __restrict__ out32) {
@@ -88,6 +88,7 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
 
   if (warp >= 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 16) {
       if (lane == 0) {  // ------------------------- TMA producer -------------------------
         const int row_q = (int)(b * N + q0);
@@ -201,6 +202,7 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else {  // ------------------------- softmax warps -------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int st = warp >> 2;                // stream
     const int t = st >> 1, hh = st & 1;      // query tile, key half
     const int lane_base = (warp & 3) * 32;   // TMEM lane quarter == warp_id % 4
