@@ -353,32 +353,35 @@ static int launch_cluster(const float* lp, int B, int64_t N, int V, const int64_
 // ---- time-skewed wavefront over the whole GPU ---------------------------------------------------
 // The recursion is serial in time, but state s at frame t only needs states s, s-1, s-2 at frame t-1.  The extended
 // states of one lattice are cut into G contiguous chunks, one persistent CTA each (cooperative launch: all resident);
-// chunk g runs kWfTB frames BEHIND chunk g-1 and receives the alpha values of its left neighbour's last two states
-// through a global hand-off buffer (one release/acquire flag per kWfTB frames).  No grid- or cluster-wide barrier
-// remains: the per-frame cost is one CTA's dependent chain (shared-memory neighbours, one lse3, __syncthreads over
-// <= 1024 threads — ~0.1 us) instead of 2.1 us for a barrier across 8 SMs, and the 45000-frame lattice of a
-// 1-hour recording is finished (45000 + G*kWfTB) * 0.1 us after it starts.  Log-prob gathers run one batch of frames
-// ahead in registers.  Same arithmetic per state as the kernels above (bit-identical results).
+// chunk g runs about two batches of kWfTB frames BEHIND chunk g-1 and receives the alpha values of its left neighbour's
+// last two states through a global hand-off buffer.  No grid- or cluster-wide barrier remains: the per-frame cost is one
+// CTA's dependent chain (shared-memory neighbours, one branch-free lse3, __syncthreads over <= 1024 threads) instead of
+// 2.1 us for a barrier across 8 SMs.
+// Hand-off without flags or fences: the record of (chunk, step) is ONE aligned 16-byte store
+//   {alpha[last-1], alpha[last], step + 1, launch epoch}
+// written by the thread that owns the chunk's last state (it reads its left neighbour's previous value anyway), and the
+// consumer checks the tag of every record it loads (L2 loads, 16 records = one 256-byte request by half a warp); stale
+// data of an earlier launch carries another epoch.  Records of the NEXT batch are fetched while the current one is being
+// computed, so in steady state nobody waits.  Log-prob gathers run one batch ahead in registers.
+// Same arithmetic per state as the kernels above (bit-identical results).
 constexpr int kWfTBDefault = 16;
 
-__device__ __forceinline__ unsigned wf_ld_acquire(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void wf_st_release(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// branch-free lse3: an all -inf input gives exp(-inf) = 0 -> log(0) = -inf, as the branchy form returns
+__device__ __forceinline__ float lse3_nb(float a, float b, float c) {
+  const float m = fmaxf(fmaxf(fmaxf(a, b), c), -1e30f);
+  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
 }
 
-template <int kWfTB, int DBG, int MAXT>  // DBG (profiling only): 1 = no log-prob gathers, 2 = no waiting for the left neighbour
+template <int kWfTB, bool STORE, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 ctc_wavefront_kernel(const float* __restrict__ log_probs, int64_t N, int V, const int64_t* __restrict__ targets, int64_t S_max,
                      const int32_t* __restrict__ input_lengths, const int64_t* __restrict__ target_lengths, int blank,
                      int direction, int G, int batch, float* __restrict__ nll, float* __restrict__ store,
-                     float* __restrict__ store_beta, int pregathered, float* __restrict__ bnd, unsigned* __restrict__ flags) {
+                     float* __restrict__ store_beta, int pregathered, float4* __restrict__ bnd, unsigned epoch) {
   // grid = units * G CTAs, unit = (sample) for direction +-1, (sample, direction) for direction 0 (alpha units first).
-  // bnd [units*G][N][2]: alpha of a chunk's last two states per step; flags [units*G]: steps published so far.
-  extern __shared__ float wf_sm[];  // [2][2 + CH] state vectors with a 2-slot left halo, then bl [kWfTB][2]
+  // bnd [units*G][N]: one record per (chunk, step).
+  static_assert(kWfTB <= 32, "one lane per record of a batch");
+  extern __shared__ float wf_sm[];  // [2][2 + CH] state vectors with a 2-slot left halo, then bl [2][kWfTB][2]
   const int NT = blockDim.x, tid = threadIdx.x, CH = NT;
   const int unit = (int)blockIdx.x / G, g = (int)blockIdx.x % G;
   const bool both = direction == 0;
@@ -400,10 +403,10 @@ ctc_wavefront_kernel(const float* __restrict__ log_probs, int64_t N, int V, cons
   if (s0 >= Lp) return;  // dead chunk: everything to its right is dead as well
   float* cur = wf_sm + 2;              // cur[-2], cur[-1] = left neighbour's last two states
   float* nxt = wf_sm + 2 + (CH + 2);
-  float* bl = wf_sm + 2 * (CH + 2);    // [kWfTB][2]
+  float* bl = wf_sm + 2 * (CH + 2);    // [2][kWfTB][2]
   const float* lp = log_probs + (int64_t)b * N * V;
   const int64_t* tgt = targets + (int64_t)b * S_max;
-  float* st = store ? store + (int64_t)b * N * Lp_max : nullptr;
+  float* st = (STORE && store) ? store + (int64_t)b * N * Lp_max : nullptr;
   const int s = s0 + tid;
   const bool live = s < Lp;
   int lab = blank;
@@ -418,30 +421,39 @@ ctc_wavefront_kernel(const float* __restrict__ log_probs, int64_t N, int V, cons
   auto frame = [&](int64_t step) -> int64_t { return direction > 0 ? step : (T - 1 - step); };
   auto fetch = [&](int64_t step) -> float {  // the log-prob this state consumes at `step`
     if (!live || step >= T) return 0.f;
-    if (DBG == 1) return -1.0f;
-    if (pregathered) return __ldcg(st + frame(step) * Lp_max + so);
+    if (STORE && pregathered) return __ldcg(st + frame(step) * Lp_max + so);
     return __ldg(lp + frame(step) * V + lab);
   };
-  float* my_bnd = bnd + (int64_t)blockIdx.x * N * 2;
-  const float* left_bnd = g > 0 ? bnd + (int64_t)(blockIdx.x - 1) * N * 2 : nullptr;
-  unsigned* my_flag = flags + blockIdx.x;
-  const unsigned* left_flag = g > 0 ? flags + blockIdx.x - 1 : nullptr;
-  const bool pub0 = tid == CH - 2, pub1 = tid == CH - 1;
+  float4* my_bnd = bnd + (int64_t)blockIdx.x * N;
+  const float4* left_bnd = g > 0 ? bnd + (int64_t)(blockIdx.x - 1) * N : nullptr;
+  const bool pub = tid == CH - 1;  // owner of the chunk's last state: publishes one record per step
+  const float epoch_f = __uint_as_float(epoch);
 
-  auto wait_left = [&](unsigned need) {  // thread 0: until the left chunk has published `need` steps
-    if (tid == 0 && left_flag && DBG != 2) {
-      unsigned spins = 0;
-      uint64_t t_first = 0;
-      while (wf_ld_acquire(left_flag) < need) {
-        __nanosleep(32);
-        if ((++spins & 0x3FFF) == 0) {  // deadlock guard: trap instead of hanging the GPU
-          uint64_t now;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-          if (t_first == 0) t_first = now;
-          else if (now - t_first > 4000000000ull) {
-            printf("lcasr_b200: ctc wavefront stalled (cta %d waits for %u steps)\n", (int)blockIdx.x, need);
-            asm volatile("trap;");
-          }
+  // warp 0, lanes < cnt: records of steps [first, first + cnt) of the left chunk -> bl[slot]; true once all tags match
+  auto try_fetch = [&](int64_t first, int cnt, int slot) -> bool {
+    bool ok = true;
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < cnt) {
+      r = __ldcg(left_bnd + first + tid);
+      ok = __float_as_uint(r.z) == (unsigned)(first + tid + 1) && __float_as_uint(r.w) == epoch;
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (ok && tid < cnt) { bl[(slot * kWfTB + tid) * 2] = r.x; bl[(slot * kWfTB + tid) * 2 + 1] = r.y; }
+    __syncwarp();
+    return ok;
+  };
+  auto fetch_blocking = [&](int64_t first, int cnt, int slot) {  // warp 0 only; deadlock guard: trap instead of hanging the GPU
+    unsigned spins = 0;
+    uint64_t t_first = 0;
+    while (!try_fetch(first, cnt, slot)) {
+      __nanosleep(64);
+      if ((++spins & 0x3FFF) == 0) {
+        uint64_t now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t_first == 0) t_first = now;
+        else if (now - t_first > 4000000000ull) {
+          if (tid == 0) printf("lcasr_b200: ctc wavefront stalled (cta %d waits for steps %lld..)\n", (int)blockIdx.x, (long long)first);
+          asm volatile("trap;");
         }
       }
     }
@@ -462,61 +474,69 @@ ctc_wavefront_kernel(const float* __restrict__ log_probs, int64_t N, int V, cons
       float* p = st + frame(0) * Lp_max + so;
       *p = (direction > 0 || !beta_adds) ? a : (*p + a);
     }
-    if (pub0) my_bnd[0] = a;
-    if (pub1) my_bnd[1] = a;
 #pragma unroll
     for (int u = 0; u < kWfTB; ++u) lpa[u] = fetch(1 + u);
   }
   __syncthreads();
-  if (tid == 0) { __threadfence(); wf_st_release(my_flag, 1u); }
+  // records of steps t0-1 .. t1-2 serve batch [t0, t1); batch 0 = [1, ..): fetched before anything else
+  int slot = 0;
+  bool next_ready = false;
+  if (g > 0 && tid < 32 && T > 1) fetch_blocking(0, (int)min((int64_t)kWfTB, T - 1), 0);
 
   // one batch of up to kWfTB steps [t0, t1): inputs from `lq`, next batch's inputs prefetched into `lnext`
   auto run_batch = [&](int64_t t0, float (&lq)[kWfTB], float (&lnext)[kWfTB]) {
     const int64_t t1 = min(T, t0 + kWfTB);
+    const int64_t n1 = min(T, t1 + kWfTB);  // next batch = [t1, n1)
 #pragma unroll
     for (int u = 0; u < kWfTB; ++u) lnext[u] = fetch(t0 + kWfTB + u);
-    if (g > 0) {  // left boundary values of steps t0-1 .. t1-2
-      wait_left((unsigned)(t1 - 1));
-      __syncthreads();
-      const int cnt = (int)(t1 - t0) * 2;
-      if (tid < cnt) bl[tid] = __ldcg(left_bnd + (t0 - 1) * 2 + tid);
-      __syncthreads();
-      if (tid < 2) cur[tid - 2] = bl[tid];
-      __syncthreads();
+    if (g > 0 && tid < 32) {
+      __syncwarp();
+      if (tid < 2) cur[tid - 2] = bl[(slot * kWfTB) * 2 + tid];  // boundary of step t0-1 (same warp wrote bl: no CTA barrier)
+      next_ready = n1 > t1 ? try_fetch(t1 - 1, (int)(n1 - t1), slot ^ 1) : true;  // usually already there: the left chunk is ahead
     }
+    // (no CTA barrier: the halo slots are written and read by lanes 0 / 1 of warp 0 only)
 #pragma unroll
     for (int u = 0; u < kWfTB; ++u) {
       const int64_t step = t0 + u;
       if (step < t1) {  // block-uniform
         const float a0 = cur[tid], a1 = cur[tid - 1], a2 = skip ? cur[tid - 2] : -INFINITY;
-        float a = -INFINITY;
-        if (live) a = lse3(a0, a1, a2) + lq[u];
+        if (pub) {  // a0 / a1 are the chunk's last two states at step-1: their record (one 16-byte store)
+          float4 rec = make_float4(a1, a0, __uint_as_float((unsigned)step), epoch_f);
+          __stcg(my_bnd + (step - 1), rec);
+        }
+        const float a = lse3_nb(a0, a1, a2) + lq[u];
         nxt[tid] = a;
-        if (g > 0 && tid < 2 && step + 1 < t1) nxt[tid - 2] = bl[(u + 1) * 2 + tid];
-        if (st && live) {
+        if (g > 0 && tid < 2 && step + 1 < t1) nxt[tid - 2] = bl[(slot * kWfTB + u + 1) * 2 + tid];
+        if (STORE && st && live) {
           float* p = st + frame(step) * Lp_max + so;
           *p = (direction > 0 || !beta_adds) ? a : (*p + a);
         }
-        if (pub0) my_bnd[step * 2] = a;
-        if (pub1) my_bnd[step * 2 + 1] = a;
         __syncthreads();
         float* tmp = cur; cur = nxt; nxt = tmp;
       }
     }
-    if (tid == 0) { __threadfence(); wf_st_release(my_flag, (unsigned)t1); }
+    if (g > 0 && tid < 32) {
+      if (!next_ready && n1 > t1) fetch_blocking(t1 - 1, (int)(n1 - t1), slot ^ 1);
+    }
+    slot ^= 1;
   };
   for (int64_t t0 = 1; t0 < T; t0 += 2 * kWfTB) {
     run_batch(t0, lpa, lpb);
     if (t0 + kWfTB < T) run_batch(t0 + kWfTB, lpb, lpa);
+  }
+  if (pub) {  // record of the final step
+    float4 rec = make_float4(cur[tid - 1], cur[tid], __uint_as_float((unsigned)T), epoch_f);
+    __stcg(my_bnd + (T - 1), rec);
   }
   if (nll) {  // the chunk that owns state Lp-1 finishes the sample
     const int sl = Lp - 1;
     if (sl >= s0 && sl < s0 + CH) {
       const int loc = sl - s0;
       if (loc == 0 && g > 0) {  // alpha_{T-1}[Lp-2] lives in the left chunk
-        wait_left((unsigned)T);
-        __syncthreads();
-        if (tid == 0) cur[-1] = __ldcg(left_bnd + (T - 1) * 2 + 1);
+        if (tid < 32) {
+          fetch_blocking(T - 1, 1, 0);
+          if (tid == 0) cur[-1] = bl[1];
+        }
         __syncthreads();
       }
       if (tid == loc) {
@@ -529,10 +549,9 @@ ctc_wavefront_kernel(const float* __restrict__ log_probs, int64_t N, int V, cons
   }
 }
 
-// chunks per lattice for `units` lattices of Lp_max states on this GPU (0 = the wavefront form does not apply)
 static int wf_tb() {
   static const int tb = getenv("LCASR_CTC_WF_TB") ? atoi(getenv("LCASR_CTC_WF_TB")) : kWfTBDefault;
-  return tb == 8 || tb == 32 || tb == 64 ? tb : 16;
+  return tb == 8 || tb == 32 ? tb : 16;
 }
 
 static int wf_chunks(int units, int64_t Lp_max) {
@@ -548,7 +567,7 @@ static int wf_chunks(int units, int64_t Lp_max) {
 int64_t ctc_wavefront_workspace_bytes(int units, int64_t N, int64_t Lp_max) {
   const int G = wf_chunks(units, Lp_max);
   if (G < 2) return 0;  // one chunk per lattice: the plain one-CTA recursion is the same thing
-  return (int64_t)units * G * N * 2 * 4 + 256 + (int64_t)units * G * 4;
+  return (int64_t)units * G * N * 16;
 }
 
 static int launch_wavefront(const float* lp, int B, int64_t N, int V, const int64_t* tg, int64_t S_max, const int32_t* il,
@@ -560,30 +579,29 @@ static int launch_wavefront(const float* lp, int B, int64_t N, int V, const int6
   LCASR_CHECK_ARG(G > 0, "ctc wavefront: %d lattices of %lld states do not fit this GPU", units, (long long)Lp_max);
   LCASR_CHECK_ARG(workspace && workspace_bytes >= ctc_wavefront_workspace_bytes(units, N, Lp_max) && ((uintptr_t)workspace & 15) == 0,
                   "ctc wavefront: workspace too small or misaligned");
+  LCASR_CHECK_ARG(N < ((int64_t)1 << 31), "ctc wavefront: too many frames");
   int nt = (int)round_up(ceil_div(Lp_max, (int64_t)G), 32);
-  float* bnd = (float*)workspace;
-  unsigned* flags = (unsigned*)((char*)workspace + (((size_t)units * G * N * 2 * 4 + 255) & ~(size_t)255));
-  LCASR_CUDA(cudaMemsetAsync(flags, 0, (size_t)units * G * 4, st));
+  float4* bnd = (float4*)workspace;
+  // every launch tags its records with a fresh epoch: records left in the workspace by earlier launches never match
+  static std::atomic<unsigned> g_epoch{0x5eed0000u};
+  unsigned epoch = g_epoch.fetch_add(1, std::memory_order_relaxed) + 1;
   const int tb = wf_tb();
-  static const int dbg = getenv("LCASR_CTC_WF_DBG") ? atoi(getenv("LCASR_CTC_WF_DBG")) : 0;
-  const size_t smem = (size_t)(2 * (nt + 2) + 2 * tb) * sizeof(float);
   int batch = B;
   void* args[] = {(void*)&lp, (void*)&N, (void*)&V, (void*)&tg, (void*)&S_max, (void*)&il, (void*)&tl, (void*)&blank, (void*)&dir,
                   (void*)&G, (void*)&batch, (void*)&nll, (void*)&store, (void*)&store_beta, (void*)&pregathered, (void*)&bnd,
-                  (void*)&flags};
-  // cooperative launch: every CTA is resident, so the spin on a neighbour's flag always makes progress
+                  (void*)&epoch};
+  // cooperative launch: every CTA is resident, so waiting for a neighbour's records always makes progress
   const void* fn = nullptr;
   const bool small = nt <= 256;  // chunks of <= 256 states: up to 255 registers per thread for the look-ahead ring
-#define LCASR_WF(TB)                                                                                                        \
-  fn = dbg == 1 ? (small ? (const void*)ctc_wavefront_kernel<TB, 1, 256> : (const void*)ctc_wavefront_kernel<TB, 1, 1024>)   \
-       : dbg == 2 ? (small ? (const void*)ctc_wavefront_kernel<TB, 2, 256> : (const void*)ctc_wavefront_kernel<TB, 2, 1024>) \
-                  : (small ? (const void*)ctc_wavefront_kernel<TB, 0, 256> : (const void*)ctc_wavefront_kernel<TB, 0, 1024>)
-  if (tb == 8) { LCASR_WF(8); } else if (tb == 32 && small) { LCASR_WF(32); } else if (tb == 64 && small) { LCASR_WF(64); } else { LCASR_WF(16); }
+  const bool has_store = store != nullptr || store_beta != nullptr;
+#define LCASR_WF(TB)                                                                                                          \
+  fn = has_store ? (small ? (const void*)ctc_wavefront_kernel<TB, true, 256> : (const void*)ctc_wavefront_kernel<TB, true, 1024>)   \
+                 : (small ? (const void*)ctc_wavefront_kernel<TB, false, 256> : (const void*)ctc_wavefront_kernel<TB, false, 1024>)
+  int tb_used = 16;
+  if (tb == 8) { LCASR_WF(8); tb_used = 8; } else if (tb == 32 && small) { LCASR_WF(32); tb_used = 32; } else { LCASR_WF(16); }
 #undef LCASR_WF
-  const int tb_used = (tb == 8) ? 8 : ((tb == 32 && small) ? 32 : ((tb == 64 && small) ? 64 : 16));
-  const size_t smem_used = (size_t)(2 * (nt + 2) + 2 * tb_used) * sizeof(float);
-  (void)smem;
-  LCASR_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)(units * G)), dim3((unsigned)nt), args, smem_used, st));
+  const size_t smem = (size_t)(2 * (nt + 2) + 2 * 2 * tb_used) * sizeof(float);
+  LCASR_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)(units * G)), dim3((unsigned)nt), args, smem, st));
   count_launch();
   return 0;
 }
