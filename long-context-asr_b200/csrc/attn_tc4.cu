@@ -40,13 +40,17 @@ constexpr int F4_EXO_STRIDE = 33;                      // fp32 words per exchang
 constexpr int F4_EX_BYTES = 2 * F4_BQ * (F4_EXO_STRIDE + 2) * 4;
 constexpr int F4_SMEM_BYTES = F4_Q_BYTES + F4_STAGES * F4_STAGE_BYTES + F4_EX_BYTES + 1024;
 constexpr int F4_P_COL = 256, F4_O_COL = 384;
+constexpr int kF4DefaultPoly = 0;
 
+// POLY = p > 0: every p-th odd key's exponential is evaluated on the FMA / ALU pipes (ex2_poly: Cody-Waite split + cubic,
+// relative error 1.6e-4, far below the bf16 rounding of P) instead of the MUFU pipe — 1/(2p) of all exponentials.
+template <int POLY>
 __global__ void __launch_bounds__(F4_THREADS, 1)
 attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, int64_t N, int64_t Nk, const int32_t* __restrict__ kv_len, int H,
                 float scale_log2, bf16* __restrict__ out, float* __restrict__ lse, float* __restrict__ out32) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[1 + 2 * F4_STAGES + 2 + 2 + 4 + 4 + 3];
+  __shared__ __align__(8) uint64_t bars[1 + 2 * F4_STAGES + 2 + 2 + 4 + 4];
   __shared__ uint32_t tmem_slot;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t q_smem = smem_base;
@@ -62,7 +66,6 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   auto s_free = [&](int t) { return bar0 + 8u * (BB + 2 + t); };          // S_t(j) is in the registers of all 8 warps of tile t
   auto p_full = [&](int st) { return bar0 + 8u * (BB + 4 + st); };        // P of stream st published
   auto pv_done = [&](int st) { return bar0 + 8u * (BB + 8 + st); };       // PV of stream st retired
-  auto stagger = [&](int st) { return bar0 + 8u * (BB + 12 + st - 1); };  // stream st-1 is half-way through its first exp phase
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h_idx = blockIdx.y;
@@ -77,7 +80,6 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int s = 0; s < F4_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     for (int t = 0; t < 2; ++t) { mbar_init(s_full(t), 1); mbar_init(s_free(t), 8); }
     for (int st = 0; st < 4; ++st) { mbar_init(p_full(st), 4); mbar_init(pv_done(st), 1); }
-    for (int st = 1; st < 4; ++st) mbar_init(stagger(st), 4);
     fence_barrier_init();
   }
   if (warp == 17) {
@@ -214,11 +216,8 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t p_addr = t_lane + F4_P_COL + st * (F4_HK / 2);
     const uint32_t o_addr = t_lane + F4_O_COL + st * F4_DH;
     float m_run = -1e30f, l_run = 0.f;
-    // De-synchronise the four streams of a sub-partition: all S tiles of the first key tile arrive together, and streams
-    // that start together stay in lockstep — every warp in its MUFU phase at the same time, then every warp in its load /
-    // max / store phase with the MUFU pipe idle (measured: 3100 instead of 2048 cycles per pair of score tiles).  Stream k
-    // starts once stream k-1 is half-way through the exponentials of its first tile.
-    if (st > 0) mbar_wait(stagger(st), 0);
+    // (Starting stream k only when stream k-1 is half-way through its first exp phase — the de-phasing that helps the
+    //  two-stream kernel — measured SLOWER here: 2.21 vs 2.11 ms at N = 16384, H = 24.)
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full(t), j & 1);
       tc_fence_after();
@@ -276,17 +275,14 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float p0 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + 2 * i]), scale_log2, neg_m));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + 2 * i + 1]), scale_log2, neg_m));
+          const float x1 = fmaf(__uint_as_float(s[c * 32 + 2 * i + 1]), scale_log2, neg_m);
+          const float p1 = (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == 0) ? ex2_poly(x1) : ex2_approx(x1);
           sums[(2 * i) & 3] += p0;
           sums[(2 * i + 1) & 3] += p1;
           __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
           pk[i] = *reinterpret_cast<uint32_t*>(&pp);
         }
         tmem_st_32x32b_x16(p_addr + c * 16, pk);
-        if (c == 0 && j == 0 && st < 3) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(stagger(st + 1));
-        }
       }
       l_run += (sums[0] + sums[1]) + (sums[2] + sums[3]);
       tmem_wait_st();
@@ -348,15 +344,27 @@ int attn_tc4_launch(const void* q, const void* k, const void* v, int B, int64_t 
   LCASR_TRY(make_tmap_2d_bf16(&tmQ, q, (uint64_t)B * N, d, (uint64_t)ldq * 2, 2 * F4_BQ, F4_DH, CU_TENSOR_MAP_SWIZZLE_64B));
   LCASR_TRY(make_tmap_2d_bf16(&tmK, k, (uint64_t)B * Nk, d, (uint64_t)ldkv * 2, F4_BK, F4_DH, CU_TENSOR_MAP_SWIZZLE_64B));
   LCASR_TRY(make_tmap_2d_bf16(&tmV, v, (uint64_t)B * Nk, d, (uint64_t)ldkv * 2, F4_BK, F4_DH, CU_TENSOR_MAP_SWIZZLE_64B));
-  static PerDeviceFlag attr_set;
-  int attr_dev = 0;
-  if (attr_set.needs_set(&attr_dev)) {
-    LCASR_CUDA(cudaFuncSetAttribute(attn_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));
-    attr_set.mark(attr_dev);
-  }
+  static const int poly = getenv("LCASR_ATTN_POLY") ? atoi(getenv("LCASR_ATTN_POLY")) : kF4DefaultPoly;
   dim3 grid((unsigned)ceil_div(N, 2 * F4_BQ), (unsigned)H, (unsigned)B);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)F4_DH);
-  attn_tc4_kernel<<<grid, F4_THREADS, F4_SMEM_BYTES, st>>>(tmQ, tmK, tmV, N, Nk, kv_len, H, scale_log2, (bf16*)out, lse, out32);
+#define LCASR_F4(P)                                                                                                            \
+  {                                                                                                                            \
+    static PerDeviceFlag attr_set;                                                                                             \
+    int attr_dev = 0;                                                                                                          \
+    if (attr_set.needs_set(&attr_dev)) {                                                                                       \
+      LCASR_CUDA(cudaFuncSetAttribute(attn_tc4_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));        \
+      attr_set.mark(attr_dev);                                                                                                 \
+    }                                                                                                                          \
+    attn_tc4_kernel<P><<<grid, F4_THREADS, F4_SMEM_BYTES, st>>>(tmQ, tmK, tmV, N, Nk, kv_len, H, scale_log2, (bf16*)out, lse, out32); \
+  }
+  switch (poly) {
+    case 1: LCASR_F4(1) break;
+    case 2: LCASR_F4(2) break;
+    case 4: LCASR_F4(4) break;
+    case 8: LCASR_F4(8) break;
+    default: LCASR_F4(0) break;
+  }
+#undef LCASR_F4
   LCASR_LAUNCH_CHECK();
   return 0;
 }
