@@ -31,7 +31,7 @@ namespace {
 constexpr int F4_DH = 32, F4_BQ = 128, F4_BK = 128, F4_HK = 64;  // HK: keys per stream and tile
 constexpr int F4_THREADS = 640, F4_STAGES = 4;  // 16 softmax warps + one warpgroup for the TMA producer and the MMA issuer
 // Registers: the SM allocates them per 4 warps, so 20 warps launch with 96 each (61440 in all) and setmaxnreg can only
-// REDISTRIBUTE that total: producer / issuer warpgroup down to 40, softmax warps up to 104 (128*40 + 512*104 = 58368).
+// REDISTRIBUTE that total: producer / issuer warpgroup down to 32, softmax warps up to 112 (128*32 + 512*112 = 61440).
 constexpr int F4_ROW_BYTES = 64;                       // one 32-element bf16 row; SWIZZLE_64B
 constexpr int F4_Q_BYTES = 2 * F4_BQ * F4_ROW_BYTES;   // both query tiles
 constexpr int F4_K_BYTES = F4_BK * F4_ROW_BYTES;
@@ -92,7 +92,7 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
 
   if (warp >= 16) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == 16) {
       if (lane == 0) {  // ------------------------- TMA producer -------------------------
         const int row_q = (int)(b * N + q0);
@@ -206,7 +206,7 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else {  // ------------------------- softmax warps -------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const int st = warp >> 2;                // stream
     const int t = st >> 1, hh = st & 1;      // query tile, key half
     const int lane_base = (warp & 3) * 32;   // TMEM lane quarter == warp_id % 4
@@ -274,11 +274,15 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + 2 * i]), scale_log2, neg_m));
-          const float x1 = fmaf(__uint_as_float(s[c * 32 + 2 * i + 1]), scale_log2, neg_m);
+          // packed fp32 pairs: one FFMA2 (scale and subtract the running maximum) and one FADD2 (row sums) per TWO scores —
+          // 5 instead of 7 issue slots per pair; the kernel is issue-bound, not MUFU-bound (moving exponentials to the FMA
+          // pipes made it slower at every fraction)
+          float x0, x1;
+          ffma2(x0, x1, __uint_as_float(s[c * 32 + 2 * i]), __uint_as_float(s[c * 32 + 2 * i + 1]), scale_log2, neg_m);
+          const float p0 = ex2_approx(x0);
           const float p1 = (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == 0) ? ex2_poly(x1) : ex2_approx(x1);
-          sums[(2 * i) & 3] += p0;
-          sums[(2 * i + 1) & 3] += p1;
+          if (i & 1) fadd2(sums[2], sums[3], p0, p1);
+          else fadd2(sums[0], sums[1], p0, p1);
           __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
           pk[i] = *reinterpret_cast<uint32_t*>(&pp);
         }

@@ -275,6 +275,17 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// packed fp32 pairs (FFMA2 / FADD2, sm_100): two independent fp32 operations per issue slot, same rounding as the scalar forms
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {  // d = a * b + c (b, c broadcast)
+  asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %4}; mov.b64 rc, {%5, %5};"
+      " fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd;}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) {  // d += a
+  asm("{.reg .b64 ra, rd; mov.b64 ra, {%2, %3}; mov.b64 rd, {%0, %1}; add.rn.f32x2 rd, rd, ra; mov.b64 {%0, %1}, rd;}"
+      : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
+}
+
 // 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = i + f, f in [-0.5, 0.5], degree-3
 // minimax polynomial for 2^f (max relative error 1.6e-4 — far below the bf16 rounding of P) and an
 // integer add into the exponent field.  Used for a fraction of the softmax exponentials so the
