@@ -13,7 +13,8 @@
 // 16 softmax warps = 4 per SM sub-partition, each handling 32 rows x 64 columns per key tile.
 //
 //   warps 0-15  softmax: warp w -> TMEM lane quarter w % 4, stream w / 4 (t = stream / 2, h = stream % 2)
-//   warp 16     TMA producer (Q once, K/V tiles into a 4-deep ring)         warp 17  MMA issuer
+//   warp 16     TMA producer (Q once, K/V tiles into a 4-deep ring)
+//   warp 17     QK^T issuer (both query tiles)       warps 18, 19   PV issuers (query tile A / B)
 // TMEM (512 columns): S_A [0,128) | S_B [128,256) | P[t][h] 4 x 32 at 256 | O[t][h] 4 x 32 at 384.
 // Per key tile the issuer emits QK_t (M128 N128 K32) when S_t has been read by all 8 warps of tile t, and
 // PV_{t,h} (M128 N32 K64, A = P from tensor memory, B = V rows [64h, 64h+64) MN-major) when stream (t, h) published P.
@@ -77,7 +78,7 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 16 && lane == 0) {
     prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < F4_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    for (int s = 0; s < F4_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 2); }  // kv_empty: one commit per PV warp
     for (int t = 0; t < 2; ++t) { mbar_init(s_full(t), 1); mbar_init(s_free(t), 8); }
     for (int st = 0; st < 4; ++st) { mbar_init(p_full(st), 4); mbar_init(pv_done(st), 1); }
     fence_barrier_init();
@@ -108,8 +109,11 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (++stage == F4_STAGES) { stage = 0; phase ^= 1; }
         }
       }
-    } else if (warp == 17) {
-      // ------------------------- MMA issuer (whole warp converged, one elected lane issues) -------------------------
+    } else {
+      // ------------------------- MMA issuers: warp 17 issues QK^T of both query tiles, warps 18 / 19 issue the PV products
+      // of query tile A / B (two streams each).  Three small polling loops instead of one that watches six barriers: the
+      // reaction time from "P published" to "PV retired" is on the softmax warps' critical path, and one loop with all the
+      // state did not fit the 32 registers these warps keep.  Whole warp converged, one elected lane issues. ---------------
       constexpr uint32_t idesc_qk = make_idesc_bf16(F4_BQ, F4_BK, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(F4_BQ, F4_DH, 1);  // B (= V) is MN-major
       constexpr uint32_t SBO = 8 * F4_ROW_BYTES;
@@ -117,91 +121,96 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t LBO_K = 1u << 16;                                 // unused for swizzled K-major operands
       constexpr uint32_t LBO_V = ((F4_K_BYTES >> 4) & 0x3FFF) << 16;      // MN-major V: next 64-dh sub-tile (there is one)
       auto mk = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; };
-      const uint32_t q_lo0 = (q_smem >> 4) | LBO_K;
-      const uint32_t k_lo0 = (k_smem(0) >> 4) | LBO_K;
-      const uint32_t v_lo0 = (v_smem(0) >> 4) | LBO_V;
-      auto issue_qk = [&](int stage, int t) {
-        const uint32_t d_tmem = tmem_base + t * F4_BK;
-        const uint32_t a_lo = q_lo0 + t * ((F4_BQ * F4_ROW_BYTES) >> 4);
-        const uint32_t b_lo = k_lo0 + stage * (F4_STAGE_BYTES >> 4);
-#pragma unroll
-        for (int kk = 0; kk < F4_DH / 16; ++kk)
-          umma_f16_ss(d_tmem, mk(a_lo + ((kk * 32) >> 4)), mk(b_lo + ((kk * 32) >> 4)), idesc_qk, kk != 0);
-      };
-      auto issue_pv = [&](int stage, int st, bool accumulate) {
-        const uint32_t d_tmem = tmem_base + F4_O_COL + st * F4_DH;
-        const uint32_t a_tmem = tmem_base + F4_P_COL + st * (F4_HK / 2);
-        const uint32_t b_lo = v_lo0 + stage * (F4_STAGE_BYTES >> 4) + (((st & 1) * F4_HK * F4_ROW_BYTES) >> 4);
-#pragma unroll
-        for (int kk = 0; kk < F4_HK / 16; ++kk)  // 16 key rows per step
-          umma_f16_ts(d_tmem, a_tmem + kk * 8, mk(b_lo + ((kk * 16 * F4_ROW_BYTES) >> 4)), idesc_pv, (accumulate || kk != 0) ? 1u : 0u);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(kv_full(0), 0);
-      tc_fence_after();
-      if (elect_one()) {
-        issue_qk(0, 0); umma_commit(s_full(0));
-        issue_qk(0, 1); umma_commit(s_full(1));
-      }
-      __syncwarp();
-      int qk_n[2] = {1, 1};       // QK tiles issued per query tile
-      int pv_n[4] = {0, 0, 0, 0}; // PV tiles issued per stream
-      int full_upto = 0;
       uint32_t idle = 0;
       uint64_t idle_t0 = 0;
-      auto kv_landed = [&](int jj) {
-        if (jj <= full_upto) return true;
-        if (!mbar_test_wait(kv_full(jj % F4_STAGES), (jj / F4_STAGES) & 1)) return false;
-        full_upto = jj;
-        return true;
+      auto guard = [&](bool progressed) {  // deadlock guard: trap instead of hanging the GPU (no printf: 32 registers)
+        if (progressed) { idle = 0; idle_t0 = 0; return; }
+        if ((++idle & 0xFFFF) != 0) return;
+        uint64_t now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (idle_t0 == 0) idle_t0 = now;
+        else if (now - idle_t0 > 4000000000ull) asm volatile("trap;");
       };
-      auto all_done = [&]() { return pv_n[0] >= n_tiles && pv_n[1] >= n_tiles && pv_n[2] >= n_tiles && pv_n[3] >= n_tiles; };
-      while (!all_done()) {
-        bool progressed = false;
+      if (warp == 17) {
+        const uint32_t q_lo0 = (q_smem >> 4) | LBO_K;
+        const uint32_t k_lo0 = (k_smem(0) >> 4) | LBO_K;
+        auto issue_qk = [&](int stage, int t) {
+          const uint32_t d_tmem = tmem_base + t * F4_BK;
+          const uint32_t a_lo = q_lo0 + t * ((F4_BQ * F4_ROW_BYTES) >> 4);
+          const uint32_t b_lo = k_lo0 + stage * (F4_STAGE_BYTES >> 4);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int jq = qk_n[t];
-          if (jq < n_tiles && mbar_test_wait(s_free(t), (jq - 1) & 1) && kv_landed(jq)) {
-            tc_fence_after();
-            if (elect_one()) {
-              issue_qk(jq % F4_STAGES, t);
-              umma_commit(s_full(t));
-            }
-            __syncwarp();
-            qk_n[t] = jq + 1;
-            progressed = true;
-          }
+          for (int kk = 0; kk < F4_DH / 16; ++kk)
+            umma_f16_ss(d_tmem, mk(a_lo + ((kk * 32) >> 4)), mk(b_lo + ((kk * 32) >> 4)), idesc_qk, kk != 0);
+        };
+        mbar_wait(q_full, 0);
+        mbar_wait(kv_full(0), 0);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_qk(0, 0); umma_commit(s_full(0));
+          issue_qk(0, 1); umma_commit(s_full(1));
         }
+        __syncwarp();
+        int qk0 = 1, qk1 = 1;  // QK tiles issued per query tile
+        int full_upto = 0;
+        auto kv_landed = [&](int jj) {
+          if (jj <= full_upto) return true;
+          if (!mbar_test_wait(kv_full(jj % F4_STAGES), (jj / F4_STAGES) & 1)) return false;
+          full_upto = jj;
+          return true;
+        };
+        while (qk0 < n_tiles || qk1 < n_tiles) {
+          bool progressed = false;
 #pragma unroll
-        for (int st = 0; st < 4; ++st) {
-          const int j = pv_n[st];
-          if (j < n_tiles && mbar_test_wait(p_full(st), j & 1)) {
-            tc_fence_after();
-            const int stage = j % F4_STAGES;
-            // the K/V slot of tile j is free once the last of the four PV(j) has been issued (QK_t(j) precede them)
-            const bool release = pv_n[st ^ 1] > j && pv_n[st ^ 2] > j && pv_n[st ^ 3] > j;
-            if (elect_one()) {
-              issue_pv(stage, st, j > 0);
-              if (release) umma_commit(kv_empty(stage));
-              umma_commit(pv_done(st));
+          for (int t = 0; t < 2; ++t) {
+            const int jq = t == 0 ? qk0 : qk1;
+            if (jq < n_tiles && mbar_test_wait(s_free(t), (jq - 1) & 1) && kv_landed(jq)) {
+              tc_fence_after();
+              if (elect_one()) {
+                issue_qk(jq % F4_STAGES, t);
+                umma_commit(s_full(t));
+              }
+              __syncwarp();
+              if (t == 0) qk0 = jq + 1; else qk1 = jq + 1;
+              progressed = true;
             }
-            __syncwarp();
-            pv_n[st] = j + 1;
-            progressed = true;
           }
+          guard(progressed);
         }
-        if (progressed) {
-          idle = 0; idle_t0 = 0;
-        } else if ((++idle & 0xFFFF) == 0) {  // deadlock guard: trap instead of hanging the GPU
-          uint64_t now;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-          if (idle_t0 == 0) idle_t0 = now;
-          else if (now - idle_t0 > 4000000000ull) {
-            if (lane == 0)
-              printf("lcasr_b200: attention(4-stream) MMA issuer stalled (block %d,%d,%d qk %d %d pv %d %d %d %d of %d)\n", blockIdx.x,
-                     blockIdx.y, blockIdx.z, qk_n[0], qk_n[1], pv_n[0], pv_n[1], pv_n[2], pv_n[3], n_tiles);
-            asm volatile("trap;");
+      } else {
+        const int t = warp - 18;  // query tile whose two streams this warp serves
+        const uint32_t v_lo0 = (v_smem(0) >> 4) | LBO_V;
+        auto issue_pv = [&](int stage, int st, bool accumulate) {
+          const uint32_t d_tmem = tmem_base + F4_O_COL + st * F4_DH;
+          const uint32_t a_tmem = tmem_base + F4_P_COL + st * (F4_HK / 2);
+          const uint32_t b_lo = v_lo0 + stage * (F4_STAGE_BYTES >> 4) + (((st & 1) * F4_HK * F4_ROW_BYTES) >> 4);
+#pragma unroll
+          for (int kk = 0; kk < F4_HK / 16; ++kk)  // 16 key rows per step
+            umma_f16_ts(d_tmem, a_tmem + kk * 8, mk(b_lo + ((kk * 16 * F4_ROW_BYTES) >> 4)), idesc_pv, (accumulate || kk != 0) ? 1u : 0u);
+        };
+        int pv0 = 0, pv1 = 0;  // PV tiles issued for key half 0 / 1
+        while (pv0 < n_tiles || pv1 < n_tiles) {
+          bool progressed = false;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int j = hh == 0 ? pv0 : pv1;
+            const int st = 2 * t + hh;
+            if (j < n_tiles && mbar_test_wait(p_full(st), j & 1)) {
+              tc_fence_after();
+              const int stage = j % F4_STAGES;
+              // this warp's share of K/V tile j is consumed once BOTH of its PV(j) have been issued (kv_empty counts the
+              // commits of the two PV warps; QK_t(j) retired before P_t(j) could exist)
+              const bool release = (hh == 0 ? pv1 : pv0) > j;
+              if (elect_one()) {
+                issue_pv(stage, st, j > 0);
+                if (release) umma_commit(kv_empty(stage));
+                umma_commit(pv_done(st));
+              }
+              __syncwarp();
+              if (hh == 0) pv0 = j + 1; else pv1 = j + 1;
+              progressed = true;
+            }
           }
+          guard(progressed);
         }
       }
     }
@@ -267,8 +276,6 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       float sums[4] = {0.f, 0.f, 0.f, 0.f};
       const float neg_m = -m_run;
-      if (!pv_ok) mbar_wait(pv_done(st), (j - 1) & 1);  // PV(j-1) has consumed P(j-1): the buffer may be rewritten
-      tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t pk[16];
@@ -285,6 +292,13 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           else fadd2(sums[0], sums[1], p0, p1);
           __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
           pk[i] = *reinterpret_cast<uint32_t*>(&pp);
+        }
+        if (c == 0) {
+          // PV(j-1) must have consumed P(j-1) before the buffer is rewritten.  Waiting HERE — after the first half of the
+          // exponentials, not before them — hides the issuer's reaction time (p_full -> PV -> commit took longer than this
+          // warp's load / max phase: 8 % of all stall samples sat on this barrier)
+          if (!pv_ok) mbar_wait(pv_done(st), (j - 1) & 1);
+          tc_fence_after();
         }
         tmem_st_32x32b_x16(p_addr + c * 16, pk);
       }
