@@ -627,7 +627,14 @@ int gemm_tc_launch(const void* A, const void* W, int64_t M, int N, int K, const 
   LCASR_CHECK_ARG(!resid || out_dtype == LCASR_F32, "gemm: a residual epilogue writes fp32");
   static const int debug = getenv("LCASR_GEMM_DEBUG") ? atoi(getenv("LCASR_GEMM_DEBUG")) : 0;
   TgEpilogue ep{bias, debug == 4 ? nullptr : resid, alpha, act, (bf16*)pre_out, debug};  // (4: profiling — no residual loads)
-  const bool wide = (N % 256 == 0) || N > 512;
+  bool wide = (N % 256 == 0) || N > 512;
+  if (wide && N % 128 == 0) {
+    // few rows (a sequence-parallel rank's block, short recordings): 256-column tiles leave most SMs idle — e.g. 2048 x 768
+    // is 48 tiles for 148 SMs; 128-column tiles double the CTAs in flight
+    const int64_t t256 = ceil_div(M, TG_BM) * ceil_div(N, 256), t128 = ceil_div(M, TG_BM) * ceil_div(N, 128);
+    auto fill = [](int64_t t) { return (double)t / (double)(ceil_div(t, kNumSMs) * kNumSMs); };
+    if (t256 < kNumSMs && fill(t128) > 1.15 * fill(t256)) wide = false;
+  }
   if (out_dtype == LCASR_BF16)
     return wide ? launch_tc_cg<256, bf16>(A, W, M, N, K, ep, out, st) : launch_tc_cg<128, bf16>(A, W, M, N, K, ep, out, st);
   return wide ? launch_tc_cg<256, float>(A, W, M, N, K, ep, out, st) : launch_tc_cg<128, float>(A, W, M, N, K, ep, out, st);

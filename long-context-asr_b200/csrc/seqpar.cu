@@ -2,12 +2,13 @@
 // into P contiguous blocks, one block per rank (one process per GPU), driven entirely from C++ (no Python per op).
 //
 // What crosses ranks — everything else is token-local:
-//   attention   K/V blocks travel over NVLink as NCCL point-to-point transfers on a side stream, in ring order
-//               (step s: send the own block to rank r+s, receive the block of rank r-s), while the attention kernel
-//               already works on the blocks that have landed.  Each (query block, key block) launch produces an exact
-//               partial result (O_s / l_s in fp32 + log2-domain log-sum-exp) and attn_merge_kernel combines the P
-//               partials: softmax over the union of the key blocks, no approximation, independent launches (so
-//               consecutive blocks overlap on two streams and the 1.3-wave grids of a 2048-token block fill each other's tails);
+//   attention   K/V blocks travel over NVLink through NCCL on a side stream (one in-place all-gather pair per layer, or
+//               ncclSend/ncclRecv pairs in ring order: step s sends the own block to rank r+s and receives the block of
+//               rank r-s — see LCASR_SP_KV_MODE below) while the attention kernel already works on the own block.  Each
+//               (query block, key block) launch produces an exact partial result (O_s / l_s in fp32 + log2-domain
+//               log-sum-exp) and attn_merge_kernel combines the P partials: softmax over the union of the key blocks, no
+//               approximation, independent launches (so consecutive blocks overlap on two streams and the 1.3-wave grids
+//               of a 2048-token block fill each other's tails);
 //   conv module the k=9 depthwise conv needs (k-1)/2 rows of the post-GLU tensor from each NEIGHBOUR: two small
 //               ncclSend/ncclRecv pairs per layer (zeros at the true sequence ends);
 //   decode      per-frame argmax ids are exchanged so that the greedy collapse sees the seams.
@@ -23,6 +24,7 @@
 #include <nccl.h>
 #include <new>
 #include <string>
+#include <cstdlib>
 
 namespace lcasr {
 int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len, int H,
@@ -109,6 +111,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -132,6 +135,7 @@ struct NcclApi {
     LCASR_NCCL_SYM(CommDestroy, "ncclCommDestroy");
     LCASR_NCCL_SYM(Send, "ncclSend");
     LCASR_NCCL_SYM(Recv, "ncclRecv");
+    LCASR_NCCL_SYM(AllGather, "ncclAllGather");
     LCASR_NCCL_SYM(GroupStart, "ncclGroupStart");
     LCASR_NCCL_SYM(GroupEnd, "ncclGroupEnd");
     LCASR_NCCL_SYM(GetErrorString, "ncclGetErrorString");
@@ -473,23 +477,56 @@ extern "C" int lcasr_model_forward_seqpar(lcasr_model* m, lcasr_comm* comm, cons
       LCASR_CUDA(cudaEventRecord(ev_kv, st));
       LCASR_CUDA(cudaStreamWaitEvent(cs, ev_kv, 0));
       LCASR_CUDA(cudaStreamWaitEvent(aux, ev_kv, 0));
+      // How the other ranks' K/V blocks arrive (LCASR_SP_KV_MODE):
+      //   2 (default when the blocks are equal): ONE in-place ncclAllGather pair per layer — NVSwitch-optimised, 2 NCCL
+      //     kernels; the own block's attention overlaps it, the other blocks follow its completion;
+      //   1: ONE group of all P-1 ncclSend/ncclRecv pairs (ring-ordered peers; NCCL runs them concurrently over its
+      //     channels) — the form for unequal blocks;
+      //   0: P-1 separate groups, one event each, so that attention on block r-s can start as soon as that block landed.
+      //     Finest overlap on paper, but every group is a separate NCCL kernel over the one or two channels NCCL gives a peer
+      //     pair: measured 136 us per step at 8 ranks (6 MB per step) — 2.2x instead of 5x+ for the 20-minute context.
+      static const int kv_mode_env = getenv("LCASR_SP_KV_MODE") ? atoi(getenv("LCASR_SP_KV_MODE")) : -1;
+      bool equal_blocks = true;
+      for (int j = 1; j < P; ++j) equal_blocks = equal_blocks && p.cnt[j] == p.cnt[0];
+      int kv_mode = kv_mode_env >= 0 ? kv_mode_env : 2;
+      if (kv_mode == 2 && !equal_blocks) kv_mode = 1;
       std::vector<cudaEvent_t> ev_blk(P, nullptr);
-      for (int s = 1; s < P; ++s) {  // ring order: step s sends to r+s and receives the block of r-s
-        const int to = (r + s) % P, from = (r - s + P) % P;
+      if (kv_mode == 0) {
+        for (int s = 1; s < P; ++s) {  // ring order: step s sends to r+s and receives the block of r-s
+          const int to = (r + s) % P, from = (r - s + P) % P;
+          LCASR_NCCL(g_nccl.GroupStart());
+          LCASR_NCCL(g_nccl.Send(R.K(p.s0), R.block_bytes(r), ncclChar, to, comm->comm, cs));
+          LCASR_NCCL(g_nccl.Send(R.V(p.s0), R.block_bytes(r), ncclChar, to, comm->comm, cs));
+          LCASR_NCCL(g_nccl.Recv(R.K(p.start[from]), R.block_bytes(from), ncclChar, from, comm->comm, cs));
+          LCASR_NCCL(g_nccl.Recv(R.V(p.start[from]), R.block_bytes(from), ncclChar, from, comm->comm, cs));
+          LCASR_NCCL(g_nccl.GroupEnd());
+          ev_blk[s] = comm->next_event();
+          LCASR_CUDA(cudaEventRecord(ev_blk[s], cs));
+        }
+      } else {
         LCASR_NCCL(g_nccl.GroupStart());
-        LCASR_NCCL(g_nccl.Send(R.K(p.s0), R.block_bytes(r), ncclChar, to, comm->comm, cs));
-        LCASR_NCCL(g_nccl.Send(R.V(p.s0), R.block_bytes(r), ncclChar, to, comm->comm, cs));
-        LCASR_NCCL(g_nccl.Recv(R.K(p.start[from]), R.block_bytes(from), ncclChar, from, comm->comm, cs));
-        LCASR_NCCL(g_nccl.Recv(R.V(p.start[from]), R.block_bytes(from), ncclChar, from, comm->comm, cs));
+        if (kv_mode == 2) {  // in place: this rank's block already sits at its slot of the gathered tensors
+          LCASR_NCCL(g_nccl.AllGather(R.K(p.s0), R.K(0), R.block_bytes(r), ncclChar, comm->comm, cs));
+          LCASR_NCCL(g_nccl.AllGather(R.V(p.s0), R.V(0), R.block_bytes(r), ncclChar, comm->comm, cs));
+        } else {
+          for (int s = 1; s < P; ++s) {
+            const int to = (r + s) % P, from = (r - s + P) % P;
+            LCASR_NCCL(g_nccl.Send(R.K(p.s0), R.block_bytes(r), ncclChar, to, comm->comm, cs));
+            LCASR_NCCL(g_nccl.Send(R.V(p.s0), R.block_bytes(r), ncclChar, to, comm->comm, cs));
+            LCASR_NCCL(g_nccl.Recv(R.K(p.start[from]), R.block_bytes(from), ncclChar, from, comm->comm, cs));
+            LCASR_NCCL(g_nccl.Recv(R.V(p.start[from]), R.block_bytes(from), ncclChar, from, comm->comm, cs));
+          }
+        }
         LCASR_NCCL(g_nccl.GroupEnd());
-        ev_blk[s] = comm->next_event();
-        LCASR_CUDA(cudaEventRecord(ev_blk[s], cs));
+        cudaEvent_t ev_all = comm->next_event();
+        LCASR_CUDA(cudaEventRecord(ev_all, cs));
+        for (int s = 1; s < P; ++s) ev_blk[s] = ev_all;
       }
       if (partial) {
-        LCASR_TRY(R.attn_block(0, r, st));  // the own block needs no transfer
+        LCASR_TRY(R.attn_block(0, r, st));  // the own block needs no transfer: it overlaps the exchange
         for (int s = 1; s < P; ++s) {
           cudaStream_t as = (s & 1) ? aux : st;  // independent partials: alternate streams so that tails overlap
-          LCASR_CUDA(cudaStreamWaitEvent(as, ev_blk[s], 0));
+          if (kv_mode == 0 || s <= 2) LCASR_CUDA(cudaStreamWaitEvent(as, ev_blk[s], 0));
           LCASR_TRY(R.attn_block(s, (r - s + P) % P, as));
         }
         cudaEvent_t ev_aux = comm->next_event();
