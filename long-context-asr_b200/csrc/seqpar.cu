@@ -358,13 +358,25 @@ struct SpRank {
 
   bool partial_mode() const { return c().compute_dtype == LCASR_BF16 && m->attn_impl != LCASR_ATTN_SIMT; }
 
-  // bf16: own queries x key block j -> partial slot `slot` (may run on another stream)
-  int attn_block(int slot, int j, cudaStream_t stream) {
+  int n_parts = 1;  // partial results the merge of this layer combines
+
+  // bf16: own queries x keys [tok0, tok0 + ntok) -> partial slot `slot` (may run on another stream)
+  int attn_range(int slot, int64_t tok0, int64_t ntok, cudaStream_t stream) {
     const int d = c().d_model, H = c().n_heads, Dh = c().head_dim;
     float* part = (float*)(ws + p.off_parts) + (size_t)slot * p.n * d;
     float* lse = (float*)(ws + p.off_lse) + (size_t)slot * H * p.n;
-    return attn_tc_launch(ws + p.off_q, K(p.start[j]), V(p.start[j]), 1, p.n, p.cnt[j], nullptr, H, Dh, 0, 0, nullptr, lse, stream,
-                          -1, -1, part);
+    return attn_tc_launch(ws + p.off_q, K(tok0), V(tok0), 1, p.n, ntok, nullptr, H, Dh, 0, 0, nullptr, lse, stream, -1, -1, part);
+  }
+  int attn_block(int slot, int j, cudaStream_t stream) { return attn_range(slot, p.start[j], p.cnt[j], stream); }
+  // everything that is not the own block, as at most two launches over the contiguous key ranges in front of / behind it
+  // (slots 1 and 2; a 2048-key launch is 1.3 waves of 16-iteration CTAs: 221 instead of 425 TFLOP/s — few long launches
+  //  whose CTAs fill each other's tails are what the gathered layout allows)
+  int attn_others(cudaStream_t s_before, cudaStream_t s_after) {
+    int slot = 1;
+    if (p.s0 > 0) LCASR_TRY(attn_range(slot++, 0, p.s0, s_before));
+    if (p.s0 + p.n < p.N) LCASR_TRY(attn_range(slot++, p.s0 + p.n, p.N - p.s0 - p.n, s_after));
+    n_parts = slot;
+    return 0;
   }
 
   // merge (bf16) or the single fp32 launch over the gathered K/V, out-projection, conv-module front: norm, pw1, GLU
@@ -373,7 +385,7 @@ struct SpRank {
     const int d = c().d_model, H = c().n_heads, Dh = c().head_dim, cd = c().compute_dtype;
     void* a = ws + p.off_a; void* wide = ws + p.off_wide;
     if (partial_mode()) {
-      LCASR_TRY(merge_launch((float*)(ws + p.off_parts), (float*)(ws + p.off_lse), p.P, p.n, H, Dh, (int64_t)p.n * d,
+      LCASR_TRY(merge_launch((float*)(ws + p.off_parts), (float*)(ws + p.off_lse), n_parts, p.n, H, Dh, (int64_t)p.n * d,
                              (int64_t)H * p.n, a, cd, st));
     } else {  // fp32 parity mode: one launch over all keys in global order — bit-identical to the single-GPU forward
       if (cd == LCASR_BF16) LCASR_TRY(attn_tc_launch(ws + p.off_q, K(0), V(0), 1, p.n, p.N, nullptr, H, Dh, 0, 0, a, nullptr, st));
@@ -524,10 +536,17 @@ extern "C" int lcasr_model_forward_seqpar(lcasr_model* m, lcasr_comm* comm, cons
       }
       if (partial) {
         LCASR_TRY(R.attn_block(0, r, st));  // the own block needs no transfer: it overlaps the exchange
-        for (int s = 1; s < P; ++s) {
-          cudaStream_t as = (s & 1) ? aux : st;  // independent partials: alternate streams so that tails overlap
-          if (kv_mode == 0 || s <= 2) LCASR_CUDA(cudaStreamWaitEvent(as, ev_blk[s], 0));
-          LCASR_TRY(R.attn_block(s, (r - s + P) % P, as));
+        if (kv_mode == 0) {
+          for (int s = 1; s < P; ++s) {
+            cudaStream_t as = (s & 1) ? aux : st;  // independent partials: alternate streams so that tails overlap
+            LCASR_CUDA(cudaStreamWaitEvent(as, ev_blk[s], 0));
+            LCASR_TRY(R.attn_block(s, (r - s + P) % P, as));
+          }
+          R.n_parts = P;
+        } else {  // everything arrives at once: two long launches (keys in front of / behind the own block) on two streams
+          LCASR_CUDA(cudaStreamWaitEvent(aux, ev_blk[1], 0));
+          LCASR_CUDA(cudaStreamWaitEvent(st, ev_blk[1], 0));
+          LCASR_TRY(R.attn_others(aux, st));
         }
         cudaEvent_t ev_aux = comm->next_event();
         LCASR_CUDA(cudaEventRecord(ev_aux, aux));
@@ -537,6 +556,7 @@ extern "C" int lcasr_model_forward_seqpar(lcasr_model* m, lcasr_comm* comm, cons
       }
     } else if (partial) {
       LCASR_TRY(R.attn_block(0, 0, st));
+      R.n_parts = 1;
     }
     LCASR_TRY(R.layer_b(l));
     if (P > 1) {  // halo rows of the post-GLU tensor to / from the two neighbours
@@ -607,8 +627,10 @@ extern "C" int lcasr_model_forward_seqpar_emulated(lcasr_model* m, int world, co
         LCASR_CUDA(cudaMemcpyAsync(R[r].V(p.start[j]), R[j].V(p.start[j]), R[r].block_bytes(j), cudaMemcpyDeviceToDevice, st));
       }
     if (partial)
-      for (int r = 0; r < world; ++r)
-        for (int s = 0; s < world; ++s) LCASR_TRY(R[r].attn_block(s, (r - s + world) % world, st));
+      for (int r = 0; r < world; ++r) {  // the same launches as the real driver's default exchange mode
+        LCASR_TRY(R[r].attn_block(0, r, st));
+        LCASR_TRY(R[r].attn_others(st, st));
+      }
     for (int r = 0; r < world; ++r) LCASR_TRY(R[r].layer_b(l));
     for (int r = 0; r < world; ++r) {
       const SpPlan& p = R[r].p;
