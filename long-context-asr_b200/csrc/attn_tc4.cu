@@ -41,11 +41,13 @@ constexpr int F4_EXO_STRIDE = 33;                      // fp32 words per exchang
 constexpr int F4_EX_BYTES = 2 * F4_BQ * (F4_EXO_STRIDE + 2) * 4;
 constexpr int F4_SMEM_BYTES = F4_Q_BYTES + F4_STAGES * F4_STAGE_BYTES + F4_EX_BYTES + 1024;
 constexpr int F4_P_COL = 256, F4_O_COL = 384;
-constexpr int kF4DefaultPoly = 0;
+constexpr int kF4DefaultPoly = 0, kF4DefaultIpack = 0;
 
 // POLY = p > 0: every p-th odd key's exponential is evaluated on the FMA / ALU pipes (ex2_poly: Cody-Waite split + cubic,
 // relative error 1.6e-4, far below the bf16 rounding of P) instead of the MUFU pipe — 1/(2p) of all exponentials.
-template <int POLY>
+// IPACK: P is packed to bf16 with integer arithmetic (+0x8000 on the fp32 bits = round half up, then one byte permute per
+// pair) instead of F2FP: ncu shows the conversion on the XU pipe next to MUFU.EX2 (81 % busy, 14 points of it not ex2).
+template <int POLY, bool IPACK>
 __global__ void __launch_bounds__(F4_THREADS, 1)
 attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, int64_t N, int64_t Nk, const int32_t* __restrict__ kv_len, int H,
@@ -290,8 +292,12 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const float p1 = (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == 0) ? ex2_poly(x1) : ex2_approx(x1);
           if (i & 1) fadd2(sums[2], sums[3], p0, p1);
           else fadd2(sums[0], sums[1], p0, p1);
-          __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
-          pk[i] = *reinterpret_cast<uint32_t*>(&pp);
+          if constexpr (IPACK) {  // p >= 0 and finite: no carry into the sign, ties (exact .5 ulp) round up instead of to even
+            pk[i] = __byte_perm(__float_as_uint(p0) + 0x8000u, __float_as_uint(p1) + 0x8000u, 0x7632);
+          } else {
+            __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
+            pk[i] = *reinterpret_cast<uint32_t*>(&pp);
+          }
         }
         if (c == 0) {
           // PV(j-1) must have consumed P(j-1) before the buffer is rewritten.  Waiting HERE — after the first half of the
@@ -363,24 +369,27 @@ int attn_tc4_launch(const void* q, const void* k, const void* v, int B, int64_t 
   LCASR_TRY(make_tmap_2d_bf16(&tmK, k, (uint64_t)B * Nk, d, (uint64_t)ldkv * 2, F4_BK, F4_DH, CU_TENSOR_MAP_SWIZZLE_64B));
   LCASR_TRY(make_tmap_2d_bf16(&tmV, v, (uint64_t)B * Nk, d, (uint64_t)ldkv * 2, F4_BK, F4_DH, CU_TENSOR_MAP_SWIZZLE_64B));
   static const int poly = getenv("LCASR_ATTN_POLY") ? atoi(getenv("LCASR_ATTN_POLY")) : kF4DefaultPoly;
+  static const int ipack = getenv("LCASR_ATTN_IPACK") ? atoi(getenv("LCASR_ATTN_IPACK")) : kF4DefaultIpack;
   dim3 grid((unsigned)ceil_div(N, 2 * F4_BQ), (unsigned)H, (unsigned)B);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)F4_DH);
-#define LCASR_F4(P)                                                                                                            \
+#define LCASR_F4(P, I)                                                                                                          \
   {                                                                                                                            \
     static PerDeviceFlag attr_set;                                                                                             \
     int attr_dev = 0;                                                                                                          \
     if (attr_set.needs_set(&attr_dev)) {                                                                                       \
-      LCASR_CUDA(cudaFuncSetAttribute(attn_tc4_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));        \
+      LCASR_CUDA(cudaFuncSetAttribute(attn_tc4_kernel<P, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM_BYTES));     \
       attr_set.mark(attr_dev);                                                                                                 \
     }                                                                                                                          \
-    attn_tc4_kernel<P><<<grid, F4_THREADS, F4_SMEM_BYTES, st>>>(tmQ, tmK, tmV, N, Nk, kv_len, H, scale_log2, (bf16*)out, lse, out32); \
+    attn_tc4_kernel<P, I><<<grid, F4_THREADS, F4_SMEM_BYTES, st>>>(tmQ, tmK, tmV, N, Nk, kv_len, H, scale_log2, (bf16*)out, lse, out32); \
   }
-  switch (poly) {
-    case 1: LCASR_F4(1) break;
-    case 2: LCASR_F4(2) break;
-    case 4: LCASR_F4(4) break;
-    case 8: LCASR_F4(8) break;
-    default: LCASR_F4(0) break;
+  if (ipack) {
+    LCASR_F4(0, true)
+  } else {
+    switch (poly) {
+      case 2: LCASR_F4(2, false) break;
+      case 4: LCASR_F4(4, false) break;
+      default: LCASR_F4(0, false) break;
+    }
   }
 #undef LCASR_F4
   LCASR_LAUNCH_CHECK();
