@@ -25,6 +25,7 @@
 #include <new>
 #include <string>
 #include <cstdlib>
+#include <climits>
 
 namespace lcasr {
 int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len, int H,
@@ -215,6 +216,8 @@ extern "C" void lcasr_comm_destroy(lcasr_comm* c) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+constexpr int kMaxOtherPieces = 8;  // partial-attention launches over the keys of the other ranks (+ 1 for the own block)
+
 inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct SpPlan {
@@ -257,8 +260,9 @@ int make_sp_plan(const lcasr_config& c, int P, int r, int64_t T, SpPlan* out) {
   p.off_sin = o; o += al256((size_t)p.n * (c.head_dim / 2) * 4);
   p.off_K = o; o += al256((size_t)p.N * d * e);
   p.off_V = o; o += al256((size_t)p.N * d * e);
-  p.off_parts = o; o += al256((size_t)P * p.n * d * 4);
-  p.off_lse = o; o += al256((size_t)P * c.n_heads * p.n * 4);
+  const int slots = P > kMaxOtherPieces + 1 ? P : kMaxOtherPieces + 1;  // per-step mode: P partials; gathered mode: own + pieces
+  p.off_parts = o; o += al256((size_t)slots * p.n * d * 4);
+  p.off_lse = o; o += al256((size_t)slots * c.n_heads * p.n * 4);
   p.off_ext = o; o += al256((size_t)(p.n + 2 * p.halo) * d * e);
   p.off_cb = o; o += al256((size_t)(p.n + 2 * p.halo) * d * e);
   p.off_am = o; o += al256((size_t)p.N * 4);
@@ -368,13 +372,31 @@ struct SpRank {
     return attn_tc_launch(ws + p.off_q, K(tok0), V(tok0), 1, p.n, ntok, nullptr, H, Dh, 0, 0, nullptr, lse, stream, -1, -1, part);
   }
   int attn_block(int slot, int j, cudaStream_t stream) { return attn_range(slot, p.start[j], p.cnt[j], stream); }
-  // everything that is not the own block, as at most two launches over the contiguous key ranges in front of / behind it
-  // (slots 1 and 2; a 2048-key launch is 1.3 waves of 16-iteration CTAs: 221 instead of 425 TFLOP/s — few long launches
-  //  whose CTAs fill each other's tails are what the gathered layout allows)
-  int attn_others(cudaStream_t s_before, cudaStream_t s_after) {
+  // Everything that is not the own block: the keys in front of and behind it, cut into pieces of equal length so that the
+  // CTAs of all pieces (launched on two streams, they fill each other's tails) tile the 148 SMs with little left over.
+  // One launch per side is 192 CTAs of up to 112 key tiles at 8 ranks of the 20-minute context: 2 waves for 1.3 waves of
+  // work; three pieces are 576 CTAs of 38 tiles: 4 waves x 38 = 152 tile-times against an ideal of 145.
+  int attn_others(cudaStream_t s_a, cudaStream_t s_b) {
+    const int64_t ranges[2][2] = {{0, p.s0}, {p.s0 + p.n, p.N}};
+    const int64_t tiles_total = ceil_div(ranges[0][1] - ranges[0][0], 128) + ceil_div(ranges[1][1] - ranges[1][0], 128);
     int slot = 1;
-    if (p.s0 > 0) LCASR_TRY(attn_range(slot++, 0, p.s0, s_before));
-    if (p.s0 + p.n < p.N) LCASR_TRY(attn_range(slot++, p.s0 + p.n, p.N - p.s0 - p.n, s_after));
+    if (tiles_total > 0) {
+      const int64_t ctas = ceil_div(p.n, 256) * c().n_heads;  // CTAs per launch (two 128-row query tiles each)
+      int64_t best_c = tiles_total, best_cost = INT64_MAX;
+      for (int pieces = 1; pieces <= kMaxOtherPieces - 1; ++pieces) {
+        const int64_t cc = ceil_div(tiles_total, pieces);  // tiles per piece
+        const int64_t np = ceil_div(ceil_div(ranges[0][1] - ranges[0][0], 128), cc) + ceil_div(ceil_div(ranges[1][1] - ranges[1][0], 128), cc);
+        if (np > kMaxOtherPieces) continue;
+        const int64_t cost = ceil_div(ctas * np, kNumSMs) * (cc + 2);  // waves x (tiles per CTA + fixed cost of a CTA)
+        if (cost < best_cost) { best_cost = cost; best_c = cc; }
+      }
+      int k = 0;
+      for (int side = 0; side < 2; ++side)
+        for (int64_t t0 = ranges[side][0]; t0 < ranges[side][1]; t0 += best_c * 128) {
+          const int64_t cnt = ranges[side][1] - t0 < best_c * 128 ? ranges[side][1] - t0 : best_c * 128;
+          LCASR_TRY(attn_range(slot++, t0, cnt, (k++ & 1) ? s_b : s_a));
+        }
+    }
     n_parts = slot;
     return 0;
   }
