@@ -161,6 +161,7 @@ struct lcasr_comm {
   int rank = 0, world = 1;
   cudaStream_t cs = nullptr;   // communication stream (K/V blocks, halos)
   cudaStream_t aux = nullptr;  // second attention stream
+  cudaStream_t aux2 = nullptr, aux3 = nullptr;  // further attention streams: the pieces of one layer run concurrently
   std::vector<cudaEvent_t> ev;
   size_t ev_used = 0;
   cudaEvent_t next_event() {
@@ -197,6 +198,8 @@ extern "C" int lcasr_comm_create(const char* id_host, int rank, int world, const
   }
   LCASR_CUDA(cudaStreamCreateWithFlags(&c->cs, cudaStreamNonBlocking));
   LCASR_CUDA(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+  LCASR_CUDA(cudaStreamCreateWithFlags(&c->aux2, cudaStreamNonBlocking));
+  LCASR_CUDA(cudaStreamCreateWithFlags(&c->aux3, cudaStreamNonBlocking));
   *out = c;
   return 0;
 }
@@ -207,6 +210,8 @@ extern "C" void lcasr_comm_destroy(lcasr_comm* c) {
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   if (c->cs) cudaStreamDestroy(c->cs);
   if (c->aux) cudaStreamDestroy(c->aux);
+  if (c->aux2) cudaStreamDestroy(c->aux2);
+  if (c->aux3) cudaStreamDestroy(c->aux3);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   delete c;
 }
@@ -376,17 +381,20 @@ struct SpRank {
   // CTAs of all pieces (launched on two streams, they fill each other's tails) tile the 148 SMs with little left over.
   // One launch per side is 192 CTAs of up to 112 key tiles at 8 ranks of the 20-minute context: 2 waves for 1.3 waves of
   // work; three pieces are 576 CTAs of 38 tiles: 4 waves x 38 = 152 tile-times against an ideal of 145.
-  int attn_others(cudaStream_t s_a, cudaStream_t s_b) {
+  int attn_others(cudaStream_t s_a, cudaStream_t s_b, cudaStream_t s_c = nullptr, cudaStream_t s_d = nullptr) {
+    static const int max_pieces_env = getenv("LCASR_SP_MAX_PIECES") ? atoi(getenv("LCASR_SP_MAX_PIECES")) : kMaxOtherPieces;
+    const int max_pieces = max_pieces_env < 2 ? 2 : (max_pieces_env > kMaxOtherPieces ? kMaxOtherPieces : max_pieces_env);
+    cudaStream_t streams[4] = {s_a, s_b, s_c ? s_c : s_a, s_d ? s_d : s_b};
     const int64_t ranges[2][2] = {{0, p.s0}, {p.s0 + p.n, p.N}};
     const int64_t tiles_total = ceil_div(ranges[0][1] - ranges[0][0], 128) + ceil_div(ranges[1][1] - ranges[1][0], 128);
     int slot = 1;
     if (tiles_total > 0) {
       const int64_t ctas = ceil_div(p.n, 256) * c().n_heads;  // CTAs per launch (two 128-row query tiles each)
       int64_t best_c = tiles_total, best_cost = INT64_MAX;
-      for (int pieces = 1; pieces <= kMaxOtherPieces - 1; ++pieces) {
+      for (int pieces = 1; pieces <= max_pieces - 1; ++pieces) {
         const int64_t cc = ceil_div(tiles_total, pieces);  // tiles per piece
         const int64_t np = ceil_div(ceil_div(ranges[0][1] - ranges[0][0], 128), cc) + ceil_div(ceil_div(ranges[1][1] - ranges[1][0], 128), cc);
-        if (np > kMaxOtherPieces) continue;
+        if (np > max_pieces) continue;
         const int64_t cost = ceil_div(ctas * np, kNumSMs) * (cc + 2);  // waves x (tiles per CTA + fixed cost of a CTA)
         if (cost < best_cost) { best_cost = cost; best_c = cc; }
       }
@@ -394,7 +402,7 @@ struct SpRank {
       for (int side = 0; side < 2; ++side)
         for (int64_t t0 = ranges[side][0]; t0 < ranges[side][1]; t0 += best_c * 128) {
           const int64_t cnt = ranges[side][1] - t0 < best_c * 128 ? ranges[side][1] - t0 : best_c * 128;
-          LCASR_TRY(attn_range(slot++, t0, cnt, (k++ & 1) ? s_b : s_a));
+          LCASR_TRY(attn_range(slot++, t0, cnt, streams[k++ & 3]));
         }
     }
     n_parts = slot;
@@ -566,9 +574,18 @@ extern "C" int lcasr_model_forward_seqpar(lcasr_model* m, lcasr_comm* comm, cons
           }
           R.n_parts = P;
         } else {  // everything arrives at once: two long launches (keys in front of / behind the own block) on two streams
-          LCASR_CUDA(cudaStreamWaitEvent(aux, ev_blk[1], 0));
+          cudaStream_t side[3] = {aux, comm->aux2, comm->aux3};
           LCASR_CUDA(cudaStreamWaitEvent(st, ev_blk[1], 0));
-          LCASR_TRY(R.attn_others(aux, st));
+          for (cudaStream_t ss : side) {
+            LCASR_CUDA(cudaStreamWaitEvent(ss, ev_kv, 0));
+            LCASR_CUDA(cudaStreamWaitEvent(ss, ev_blk[1], 0));
+          }
+          LCASR_TRY(R.attn_others(aux, comm->aux2, comm->aux3, st));
+          for (int i = 1; i < 3; ++i) {  // join the extra streams
+            cudaEvent_t ev_j = comm->next_event();
+            LCASR_CUDA(cudaEventRecord(ev_j, side[i]));
+            LCASR_CUDA(cudaStreamWaitEvent(st, ev_j, 0));
+          }
         }
         cudaEvent_t ev_aux = comm->next_event();
         LCASR_CUDA(cudaEventRecord(ev_aux, aux));
