@@ -600,10 +600,10 @@ static int launch_tc(const void* A, const void* W, int64_t M, int N, int K, cons
 
 template <int BN, typename TOut, int EPI = TG_EPI_STD>
 static int launch_tc_cg(const void* A, const void* W, int64_t M, int N, int K, const TgEpilogue& ep, void* out,
-                        cudaStream_t st) {
+                        cudaStream_t st, int prefer_single = 0) {
   // CTA pairs (256-row tiles) once there is enough work to fill the 74 pairs; LCASR_GEMM_CG=1|2 forces a choice (A/B runs)
   static const int force = getenv("LCASR_GEMM_CG") ? atoi(getenv("LCASR_GEMM_CG")) : 0;
-  const bool pair = force ? force == 2 : (ceil_div(M, 2 * TG_BM) * ceil_div(N, BN) >= kNumSMs / 2);
+  const bool pair = force ? force == 2 : (!prefer_single && ceil_div(M, 2 * TG_BM) * ceil_div(N, BN) >= kNumSMs / 2);
   if (!pair) return launch_tc<BN, TOut, 1, true, EPI>(A, W, M, N, K, ep, out, st);
   if (sizeof(TOut) == 4 && K > 1536) return launch_tc<BN, TOut, 2, false, EPI>(A, W, M, N, K, ep, out, st);
   return launch_tc<BN, TOut, 2, true, EPI>(A, W, M, N, K, ep, out, st);
@@ -628,16 +628,23 @@ int gemm_tc_launch(const void* A, const void* W, int64_t M, int N, int K, const 
   static const int debug = getenv("LCASR_GEMM_DEBUG") ? atoi(getenv("LCASR_GEMM_DEBUG")) : 0;
   TgEpilogue ep{bias, debug == 4 ? nullptr : resid, alpha, act, (bf16*)pre_out, debug};  // (4: profiling — no residual loads)
   bool wide = (N % 256 == 0) || N > 512;
+  int single = 0;
   if (wide && N % 128 == 0) {
-    // few rows (a sequence-parallel rank's block, short recordings): 256-column tiles leave most SMs idle — e.g. 2048 x 768
-    // is 48 tiles for 148 SMs; 128-column tiles double the CTAs in flight
-    const int64_t t256 = ceil_div(M, TG_BM) * ceil_div(N, 256), t128 = ceil_div(M, TG_BM) * ceil_div(N, 128);
-    auto fill = [](int64_t t) { return (double)t / (double)(ceil_div(t, kNumSMs) * kNumSMs); };
-    if (t256 < kNumSMs && fill(t128) > 1.15 * fill(t256)) wide = false;
+    // Few rows (a sequence-parallel rank's block, short recordings): pick the tile form that fills the SMs best.  E.g.
+    // 2048 x 768 is 48 tiles of 128 x 256 for 148 SMs; 2048 x 3072 is 96 CTA-pair tiles for 74 pairs (two waves, the second
+    // 30 % full) but 384 single-CTA tiles of 128 x 128 (2.6 waves).  Large problems keep the tuned choice (all forms > 0.9).
+    auto fill = [](int64_t t, int64_t units) { return (double)t / (double)(ceil_div(t, units) * units); };
+    const int64_t mt = ceil_div(M, TG_BM), mt2 = ceil_div(M, 2 * TG_BM), nt256 = ceil_div(N, 256), nt128 = ceil_div(N, 128);
+    const bool pair_ok = mt2 * nt256 >= kNumSMs / 2;
+    const double cur = pair_ok ? fill(mt2 * nt256, kNumSMs / 2) : fill(mt * nt256, kNumSMs);
+    const double narrow = 0.9 * fill(mt * nt128, kNumSMs);  // 128-column tiles re-read A twice as often
+    const double single256 = 0.97 * fill(mt * nt256, kNumSMs);
+    if (narrow > 1.12 * cur && narrow >= single256) { wide = false; single = 1; }
+    else if (pair_ok && single256 > 1.12 * cur) single = 1;
   }
   if (out_dtype == LCASR_BF16)
-    return wide ? launch_tc_cg<256, bf16>(A, W, M, N, K, ep, out, st) : launch_tc_cg<128, bf16>(A, W, M, N, K, ep, out, st);
-  return wide ? launch_tc_cg<256, float>(A, W, M, N, K, ep, out, st) : launch_tc_cg<128, float>(A, W, M, N, K, ep, out, st);
+    return wide ? launch_tc_cg<256, bf16>(A, W, M, N, K, ep, out, st, single) : launch_tc_cg<128, bf16>(A, W, M, N, K, ep, out, st, single);
+  return wide ? launch_tc_cg<256, float>(A, W, M, N, K, ep, out, st, single) : launch_tc_cg<128, float>(A, W, M, N, K, ep, out, st, single);
 }
 
 // qkv projection with the rotary embedding applied in the epilogue (see TgEpilogue): out [M, N] bf16, columns

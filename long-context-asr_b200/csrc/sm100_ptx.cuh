@@ -286,6 +286,20 @@ __device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) 
       : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
 }
 
+// acc (packed pair, 64-bit register) += w (packed pair) * v (scalar broadcast) — the two channels a lane owns in one issue slot
+__device__ __forceinline__ uint64_t pack2f(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2f(uint64_t p, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p)); }
+__device__ __forceinline__ void ffma2_acc_bcast(uint64_t& acc, uint64_t w, float v) {
+  asm("{.reg .b64 rv; mov.b64 rv, {%2, %2}; fma.rn.f32x2 %0, %1, rv, %0;}" : "+l"(acc) : "l"(w), "f"(v));
+}
+__device__ __forceinline__ void ffma2_acc(uint64_t& acc, uint64_t w, uint64_t v) {  // acc += w * v, all packed pairs
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(w), "l"(v));
+}
+
 // 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = i + f, f in [-0.5, 0.5], degree-3
 // minimax polynomial for 2^f (max relative error 1.6e-4 — far below the bf16 rounding of P) and an
 // integer add into the exponent field.  Used for a fraction of the softmax exponentials so the

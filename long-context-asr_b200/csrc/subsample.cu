@@ -4,6 +4,7 @@
 //   conv0 : reads B*F*T*4 bytes, writes B*T1*F1*C*e bytes  (the activation is 160x the input)
 //   dwconv: reads B*Tin*Fin*C*e, writes B*Tout*Fout*C*e
 #include "common.cuh"
+#include "sm100_ptx.cuh"
 #include <cstdlib>
 
 namespace lcasr {
@@ -152,12 +153,13 @@ __global__ void __launch_bounds__(256, kMinBlocks) subsample_conv0_dw_fused_kern
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;   // lane -> channel pair, warp -> positions
   const int c0 = cgi * kFuCG + 2 * lane;
-  float wa[2][9], ba[2], wd[2][9], bd[2];
+  // the lane's two channels as packed fp32 pairs: one FFMA2 per tap for both (the kernel is issue-bound on FFMA)
+  uint64_t wa2[9], wd2[9];
+  const uint64_t ba2 = ptx::pack2f(b0[c0], b0[c0 + 1]), bd2 = ptx::pack2f(b1[c0], b1[c0 + 1]);
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    ba[c] = b0[c0 + c]; bd[c] = b1[c0 + c];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) { wa[c][k] = w0[(c0 + c) * 9 + k]; wd[c][k] = w1[(c0 + c) * 9 + k]; }
+  for (int k = 0; k < 9; ++k) {
+    wa2[k] = ptx::pack2f(w0[c0 * 9 + k], w0[(c0 + 1) * 9 + k]);
+    wd2[k] = ptx::pack2f(w1[c0 * 9 + k], w1[(c0 + 1) * 9 + k]);
   }
   __syncthreads();
   // phase 1: conv0 + SiLU tile (bf16x2 per lane), zero where the depthwise conv sees padding.
@@ -192,15 +194,13 @@ __global__ void __launch_bounds__(256, kMinBlocks) subsample_conv0_dw_fused_kern
 #pragma unroll
         for (int pj = 0; pj < 2; ++pj) {
           const int c = 2 * e + 1 + pj;                                    // tile column (conv0 column c - 1)
-          float a = ba[0], bq = ba[1];
+          uint64_t acc2 = ba2;
 #pragma unroll
           for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const float v = in[2 * pi + i][2 * pj + j];
-              a = fmaf(wa[0][i * 3 + j], v, a);
-              bq = fmaf(wa[1][i * 3 + j], v, bq);
-            }
+            for (int j = 0; j < 3; ++j) ptx::ffma2_acc_bcast(acc2, wa2[i * 3 + j], in[2 * pi + i][2 * pj + j]);
+          float a, bq;
+          ptx::unpack2f(acc2, a, bq);
           const bool live = row_live && c <= F1;
           const float y0 = live ? silu_fast(a) : 0.f, y1 = live ? silu_fast(bq) : 0.f;
           if (c < A0W) s_a0[(r * A0W + c) * 32 + lane] = __floats2bfloat162_rn(y0, y1);
@@ -221,15 +221,16 @@ __global__ void __launch_bounds__(256, kMinBlocks) subsample_conv0_dw_fused_kern
     for (int q = wid; q < kFuTT2 * F2; q += 8) {
       if (tl >= tl_hi) break;
       const __nv_bfloat162* a0p = s_a0 + ((2 * tl) * A0W + 2 * f2) * 32 + lane;
-      float a = bd[0], bq = bd[1];
+      uint64_t acc2 = bd2;
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           const float2 v = __bfloat1622float2(a0p[(i * A0W + j) * 32]);
-          a = fmaf(wd[0][i * 3 + j], v.x, a);
-          bq = fmaf(wd[1][i * 3 + j], v.y, bq);
+          ptx::ffma2_acc(acc2, wd2[i * 3 + j], ptx::pack2f(v.x, v.y));
         }
+      float a, bq;
+      ptx::unpack2f(acc2, a, bq);
       *reinterpret_cast<__nv_bfloat162*>(obase + (size_t)q * C) = __floats2bfloat162_rn(a, bq);
       f2 += 8;
       while (f2 >= F2) { f2 -= F2; ++tl; }
