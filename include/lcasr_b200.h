@@ -52,6 +52,15 @@ void lcasr_reset_launch_count(void);
 int lcasr_layernorm(const float* x, const float* weight, const float* bias, int64_t M, int d,
                     float eps, int kind, float* out_f32, void* out_lo, int lo_dtype, void* stream);
 
+/* Up to three of those norms back to back on a row that stays in registers (d a multiple of 128, <= 2048):
+ * ConformerLayer.norm_out followed by decoder.norm for the self-conditioning branch (sconformer_xl.py:371 + decoder.py:23),
+ * and norm_out -> decoder.norm -> decoder.norm at the end with legasee_double_norm (:245-247).  weights / biases: HOST
+ * arrays of n_stages device pointers (biases or its entries may be NULL).  out_f32 (may be NULL) receives the result of
+ * stage f32_stage, out_lo (may be NULL) the result of the last stage.  In-place (out_f32 == x) is allowed. */
+int lcasr_layernorm_chain(const float* x, int n_stages, const float* const* weights, const float* const* biases,
+                          int64_t M, int d, float eps, int kind, int f32_stage, float* out_f32, void* out_lo,
+                          int lo_dtype, void* stream);
+
 /* ConvSubsampling.conv[0] + SiLU: Conv2d(1->C, 3x3, stride 2, pad 1) on the [B,1,T,F] image
  * (lcasr/components/subsampling.py:277-290, run at :418).  spec is the model input [B,F,T] fp32
  * (sconformer_xl.py:185 transposes it); w [C,9] (= weight[C,1,3,3], taps (time,freq) row-major),

@@ -71,6 +71,7 @@ class LcasrOptTensor(C.Structure):
 # name -> argtypes; every function returns int status unless listed in _OTHER_RESTYPE
 _SIGNATURES = {
     "lcasr_layernorm": [vp, vp, vp, i64, i32, f32, i32, vp, vp, i32, vp],
+    "lcasr_layernorm_chain": [vp, i32, vp, vp, i64, i32, f32, i32, i32, vp, vp, i32, vp],
     "lcasr_subsample_conv0": [vp, vp, vp, i32, i32, i64, i32, vp, i32, vp],
     "lcasr_subsample_dwconv": [vp, i32, vp, vp, i32, i64, i32, i32, vp, vp],
     "lcasr_subsample_conv0_dw": [vp, vp, vp, vp, vp, i32, i32, i64, i32, vp, vp],

@@ -15,6 +15,7 @@
 #include <cstdlib>
 
 namespace lcasr {
+bool norm_chain_ok(int d);
 int attn_tc_available();
 int gemm_tc_launch_rope(const void* A, const void* W, int64_t M, int N, int K, const float* cos_t, const float* sin_t,
                         int64_t rope_n, int rope_cols, int dh, void* out, cudaStream_t st);
@@ -218,6 +219,7 @@ extern "C" int lcasr_model_forward_lengths(lcasr_model* m, const float* spec, in
   // transposed-V layout: the key padding columns [N, Npad) are read by TMA (times P == 0): keep them finite
   if (vt) LCASR_CUDA(cudaMemsetAsync(v, 0, (size_t)B * H * Dh * p.Npad * dtype_size(cd), cst));
 
+  bool final_operand_ready = false;
   for (int l = 0; l < c.n_layers; ++l) {
     const lcasr_layer_weights& L = m->layers[l];
     LCASR_TRY(ffn(L.ff1_norm_w, L.ff1_norm_b, L.ff1_fc1_w, L.ff1_fc1_b, L.ff1_fc2_w, L.ff1_fc2_b));
@@ -261,18 +263,37 @@ extern "C" int lcasr_model_forward_lengths(lcasr_model* m, const float* spec, in
                                     L.brn_b, k, cd, stream));
     LCASR_TRY(gemm(k, L.pw2_w, M, d, d, L.pw2_b, LCASR_ACT_NONE, x, 1.0f, x, LCASR_F32));
     LCASR_TRY(ffn(L.ff2_norm_w, L.ff2_norm_b, L.ff2_fc1_w, L.ff2_fc1_b, L.ff2_fc2_w, L.ff2_fc2_b));
-    LCASR_TRY(norm(L.norm_out_w, L.norm_out_b, x, nullptr));
+    const bool last = l == c.n_layers - 1;
+    const bool chain = !no_fuse && c.decoder_norm && norm_chain_ok(d);
+    if (chain && !last && c.self_conditioning) {
+      // norm_out (-> residual stream, fp32) and decoder.norm (-> GEMM operand) in one pass over the row
+      const float* cw[2] = {L.norm_out_w, w.dec_norm_w};
+      const float* cb[2] = {L.norm_out_b, w.dec_norm_b};
+      OP(CAT_NORM, lcasr_layernorm_chain(x, 2, cw, cb, M, d, c.norm_eps, c.norm_kind, 0, x, a, cd, stream));
+    } else if (chain && last) {
+      // end of the encoder: norm_out -> [decoder.norm (legasee double norm)] -> decoder.norm, only the operand is kept
+      const float* cw[3] = {L.norm_out_w, w.dec_norm_w, w.dec_norm_w};
+      const float* cb[3] = {L.norm_out_b, w.dec_norm_b, w.dec_norm_b};
+      OP(CAT_NORM, lcasr_layernorm_chain(x, c.legasee_double_norm ? 3 : 2, cw, cb, M, d, c.norm_eps, c.norm_kind, 0, nullptr, a,
+                                         cd, stream));
+      final_operand_ready = true;
+    } else {
+      LCASR_TRY(norm(L.norm_out_w, L.norm_out_b, x, nullptr));
+    }
     if (l != c.n_layers - 1 && c.self_conditioning) {  // sconformer_xl.py:241-243
-      if (c.decoder_norm) LCASR_TRY(norm(w.dec_norm_w, w.dec_norm_b, nullptr, a));
+      if (chain) { /* operand produced by the chained norm above */ }
+      else if (c.decoder_norm) LCASR_TRY(norm(w.dec_norm_w, w.dec_norm_b, nullptr, a));
       else OP(CAT_NORM, lcasr_cast_f32(x, M * d, a, cd, stream));
       LCASR_TRY(gemm(a, w.dec_ff_w, M, V1, d, w.dec_ff_b, LCASR_ACT_NONE, nullptr, 0.f, wide, cd));
       OP(CAT_SOFTMAX, lcasr_softmax(wide, cd, M, V1, wide, cd, stream));
       LCASR_TRY(gemm(wide, w.dec_rep_w, M, d, V1, w.dec_rep_b, LCASR_ACT_NONE, x, 1.0f, x, LCASR_F32));
     }
   }
-  if (c.legasee_double_norm && c.decoder_norm) LCASR_TRY(norm(w.dec_norm_w, w.dec_norm_b, x, nullptr));
-  if (c.decoder_norm) LCASR_TRY(norm(w.dec_norm_w, w.dec_norm_b, nullptr, a));
-  else OP(CAT_NORM, lcasr_cast_f32(x, M * d, a, cd, stream));
+  if (!final_operand_ready) {
+    if (c.legasee_double_norm && c.decoder_norm) LCASR_TRY(norm(w.dec_norm_w, w.dec_norm_b, x, nullptr));
+    if (c.decoder_norm) LCASR_TRY(norm(w.dec_norm_w, w.dec_norm_b, nullptr, a));
+    else OP(CAT_NORM, lcasr_cast_f32(x, M * d, a, cd, stream));
+  }
   LCASR_TRY(gemm(a, w.dec_ff_w, M, V1, d, w.dec_ff_b, LCASR_ACT_NONE, nullptr, 0.f, out, LCASR_F32));
   if (!return_logits) OP(CAT_SOFTMAX, lcasr_log_softmax_argmax(out, M, V1, argmax, stream));
 #undef OP

@@ -304,3 +304,20 @@ def attention_qkv(qkv, B: int, N: int, H: int, Dh: int, kv_len=None):
     out = torch.empty(B, N, H * Dh, dtype=torch.bfloat16, device=qkv.device)
     L.call("lcasr_attention_qkv", L.ptr(qkv), B, N, L.ptr(kv_len), H, Dh, L.ptr(out), _s())
     return out
+
+
+def layernorm_chain(x, weights, biases, eps=1e-5, kind="layer_norm", f32_stage=None, lo_dtype=None):
+    """up to three norms back to back on rows kept in registers: (fp32 result of stage `f32_stage` or None, low-precision
+    result of the last stage or None)"""
+    import ctypes as C
+    _cuda(x, *weights, *[b for b in biases if b is not None])
+    M, d = x.shape
+    n = len(weights)
+    o32 = torch.empty_like(x) if f32_stage is not None else None
+    olo = torch.empty(M, d, dtype=lo_dtype, device=x.device) if lo_dtype is not None else None
+    wp = (C.c_void_p * n)(*[w.data_ptr() for w in weights])
+    bp = (C.c_void_p * n)(*[(b.data_ptr() if b is not None else None) for b in biases])
+    L.call("lcasr_layernorm_chain", L.ptr(x), n, wp, bp, M, d, float(eps),
+           L.NORM_RMSNORM if kind == "rms_norm" else L.NORM_LAYERNORM, 0 if f32_stage is None else int(f32_stage), L.ptr(o32),
+           L.ptr(olo), L.dtype_code(lo_dtype) if lo_dtype is not None else L.F32, _s())
+    return o32, olo

@@ -307,3 +307,23 @@ def test_ctc_wavefront_is_bit_identical_to_plain_recursion(cuda_device, B, N, V,
         for b in range(B):
             t, lpb = int(il[b]), 2 * int(tl[b]) + 1
             assert torch.equal(a2[b, :t, :lpb], a3[b, :t, :lpb]) and torch.equal(b2[b, :t, :lpb], b3[b, :t, :lpb])
+
+
+@pytest.mark.parametrize("kind", ["layer_norm", "rms_norm"])
+@pytest.mark.parametrize("M,d,n", [(300, 768, 2), (129, 256, 3), (64, 2048, 2), (7, 128, 3)])
+def test_layernorm_chain_equals_sequential_norms(cuda_device, M, d, n, kind):
+    """norm_out -> decoder.norm (-> decoder.norm) on rows kept in registers == the same norms applied one kernel at a time"""
+    from lcasr_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    x = (torch.randn(M, d, generator=g) * 3 + 0.5).to(cuda_device)
+    ws = [(1 + 0.2 * torch.randn(d, generator=g)).to(cuda_device) for _ in range(n)]
+    bs = [(0.1 * torch.randn(d, generator=g)).to(cuda_device) if kind == "layer_norm" else None for _ in range(n)]
+    eps = 1e-5 if kind == "layer_norm" else 1e-8
+    cur, first = x, None
+    for i in range(n):
+        cur, lo = ops.layernorm(cur, ws[i], bs[i], eps, kind, out_f32=True, lo_dtype=torch.bfloat16)
+        if i == 0:
+            first = cur
+    o32, olo = ops.layernorm_chain(x, ws, bs, eps, kind, f32_stage=0, lo_dtype=torch.bfloat16)
+    assert torch.equal(o32, first)
+    assert torch.equal(olo, lo)
