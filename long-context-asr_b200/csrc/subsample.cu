@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(256) subsample_dwconv_kernel(const T* __restri
 // (zeros where the depthwise conv pads), and reduces it to the 8 x F2 x 64 depthwise outputs.
 // HBM traffic drops to: input (re-read by the 4-8 channel groups, L2-resident) + the depthwise output.
 constexpr int kFuCG = 64;
+constexpr int kSubTcDefault = 0;
 
 template <int kFuTT2, int kMinBlocks>
 __global__ void __launch_bounds__(256, kMinBlocks) subsample_conv0_dw_fused_kernel(
@@ -302,10 +303,22 @@ static int launch_fused(const float* spec, const float* w0, const float* b0, con
   return 0;
 }
 
+namespace lcasr {
+int subsample_conv0_dw_tc_launch(const float* spec, const float* w0, const float* b0, const float* w1, const float* b1, int B, int F,
+                                 int64_t T, int C, void* out, cudaStream_t st);
+}
+
 extern "C" int lcasr_subsample_conv0_dw(const float* spec, const float* w0, const float* b0, const float* w1,
                                         const float* b1, int B, int F, int64_t T, int C, void* out, void* stream) {
   LCASR_CHECK_ARG(spec && w0 && b0 && w1 && b1 && out && B > 0 && F > 0 && T > 0, "subsample_conv0_dw: bad arguments");
   LCASR_CHECK_ARG(C % kFuCG == 0, "subsample_conv0_dw: conv_channels=%d must be a multiple of %d (use the unfused kernels)", C, kFuCG);
+  // conv0 on the tensor cores (subsample_tc.cu); LCASR_SUB_TC=0 selects the SIMT kernel below (A/B runs), which also serves
+  // feature axes too wide for the tensor-core tile
+  static const int use_tc = getenv("LCASR_SUB_TC") ? atoi(getenv("LCASR_SUB_TC")) : kSubTcDefault;
+  if (use_tc) {
+    const int st_tc = subsample_conv0_dw_tc_launch(spec, w0, b0, w1, b1, B, F, T, C, out, (cudaStream_t)stream);
+    if (st_tc != LCASR_E_UNSUPPORTED) return st_tc;
+  }
   static const int tt2 = getenv("LCASR_SUB_TT2") ? atoi(getenv("LCASR_SUB_TT2")) : 4;  // tuning knob: depthwise rows per CTA (4: 1.48 ms, 8: 1.63 ms at cfg3)
   if (tt2 == 4) return launch_fused<4, 3>(spec, w0, b0, w1, b1, B, F, T, C, out, (cudaStream_t)stream);
   return launch_fused<8, 2>(spec, w0, b0, w1, b1, B, F, T, C, out, (cudaStream_t)stream);
