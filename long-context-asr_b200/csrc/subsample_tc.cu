@@ -31,6 +31,8 @@ constexpr int kTcINR = 2 * kTcA0R + 1;     // input frames per CTA (19)
 constexpr int kTcCG = 64;                  // channels per CTA
 constexpr int kTcK = 32;                   // padded contraction length
 constexpr int kTcThreads = 256;
+constexpr int kTcRowB = 144;                // bytes per position of the stencil tile: 32 bf16 pairs + 16 bytes of padding, so that the
+                                           // epilogue's 16-byte stores of consecutive positions fall into different banks
 
 // canonical K-major no-swizzle operand: core matrix = 8 rows x 16 bytes (8 bf16), stored as 128 contiguous bytes;
 // core matrices adjacent in K are 128 bytes apart (LBO), 8-row groups are kTcK/8 * 128 = 512 bytes apart (SBO)
@@ -84,7 +86,7 @@ subsample_conv0_dw_tc_kernel(const float* __restrict__ spec, const float* __rest
   uint8_t* sA = sm;                                            // [MT*128][32] bf16, canonical layout
   uint8_t* sB = sA + (size_t)MT * 128 * kTcK * 2;              // [64][32] bf16
   float* s_in = reinterpret_cast<float*>(sB + kTcCG * kTcK * 2);   // [INR][FW]
-  uint32_t* s_a0 = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s_in) + ((kTcINR * FW * 4 + 127) & ~127));  // [A0R][A0W][32] bf16x2, 16-byte chunks XOR-swizzled by position
+  uint32_t* s_a0 = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s_in) + ((kTcINR * FW * 4 + 127) & ~127));  // [A0R][A0W] rows of kTcRowB bytes: 32 bf16 pairs + padding
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cgi = blockIdx.y, b = blockIdx.z;
   const int64_t t2_0 = (int64_t)blockIdx.x * kTcTT2;
@@ -124,7 +126,7 @@ subsample_conv0_dw_tc_kernel(const float* __restrict__ spec, const float* __rest
   // zero padding columns of the conv0 tile (the depthwise conv's left / right padding)
   for (int i = tid; i < kTcA0R * 2 * 32; i += kTcThreads) {
     const int r = i / 64, side = (i >> 5) & 1;
-    s_a0[(r * A0W + (side ? A0W - 1 : 0)) * 32 + (i & 31)] = 0u;
+    *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s_a0) + (size_t)(r * A0W + (side ? A0W - 1 : 0)) * kTcRowB + (i & 31) * 4) = 0u;
   }
   __syncthreads();
   // im2col rows: [x_hi | x_lo | x_hi]
@@ -169,6 +171,9 @@ subsample_conv0_dw_tc_kernel(const float* __restrict__ spec, const float* __rest
   {
     const int quarter = warp & 3, half = warp >> 2;   // TMEM lane quarter; which 32 of the 64 channels
     const int r_lo = (int)max((int64_t)0, -a0_row0), r_hi = (int)min((int64_t)kTcA0R, T1 - a0_row0);
+    float bias[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bias[j] = s_bias[half * 32 + j];
     for (int mt = 0; mt < MT; ++mt) {
       const int p = mt * 128 + quarter * 32 + lane;
       uint32_t acc[32];
@@ -181,19 +186,16 @@ subsample_conv0_dw_tc_kernel(const float* __restrict__ spec, const float* __rest
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float y0 = live ? silu_fast(__uint_as_float(acc[2 * j]) + s_bias[half * 32 + 2 * j]) : 0.f;
-          const float y1 = live ? silu_fast(__uint_as_float(acc[2 * j + 1]) + s_bias[half * 32 + 2 * j + 1]) : 0.f;
+          const float y0 = live ? silu_fast(__uint_as_float(acc[2 * j]) + bias[2 * j]) : 0.f;
+          const float y1 = live ? silu_fast(__uint_as_float(acc[2 * j + 1]) + bias[2 * j + 1]) : 0.f;
           pk[j] = bf16x2_bits(y0, y1);
         }
-        // the position's 128-byte row holds 32 channel pairs; 16-byte chunk ch is stored at ch ^ (pos & 7): lanes of a warp
-        // are consecutive positions, so the 8 lanes of a store phase hit 8 different chunk slots (conflict-free), and the
-        // stencil's reads (all lanes in one row) stay conflict-free as well
-        uint8_t* rowp = reinterpret_cast<uint8_t*>(s_a0) + (size_t)pos * 128;
+        // the position's row holds 32 channel pairs in 144 bytes: lanes of a warp are consecutive positions, so the 8 lanes
+        // of a 16-byte store phase fall into 8 different bank groups; the stencil's reads (all lanes in one row) are contiguous
+        uint8_t* rowp = reinterpret_cast<uint8_t*>(s_a0) + (size_t)pos * kTcRowB + half * 64;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int ch = half * 4 + q;
-          *reinterpret_cast<uint4*>(rowp + ((ch ^ (pos & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        }
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(rowp + q * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       }
     }
   }
@@ -214,18 +216,16 @@ subsample_conv0_dw_tc_kernel(const float* __restrict__ spec, const float* __rest
     int tl = 0, f2 = warp;
     while (f2 >= F2) { f2 -= F2; ++tl; }
     bf16* obase = out + (((int64_t)b * T2 + t2_0) * F2) * C + c0;
-    const int chunk = lane >> 2, within = (lane & 3) * 4;
 #pragma unroll 2
     for (int q = warp; q < kTcTT2 * F2; q += 8) {
       if (tl >= tl_hi) break;
       uint64_t acc2 = bd2;
+      const uint8_t* a0p = reinterpret_cast<const uint8_t*>(s_a0) + (size_t)((2 * tl) * A0W + 2 * f2) * kTcRowB + lane * 4;
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          const int pos = (2 * tl + i) * A0W + 2 * f2 + j;
-          const uint32_t bits = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(s_a0) + (size_t)pos * 128 +
-                                                                  ((chunk ^ (pos & 7)) << 4) + within);
+          const uint32_t bits = *reinterpret_cast<const uint32_t*>(a0p + (size_t)(i * A0W + j) * kTcRowB);
           const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bits));
           ffma2_acc(acc2, wd2[i * 3 + j], pack2f(v.x, v.y));
         }
@@ -250,7 +250,7 @@ int subsample_conv0_dw_tc_launch(const float* spec, const float* w0, const float
   const int FW = ((2 * F1 + 2) + 3) & ~3;  // patch columns 0 .. 2*F1 (col 0 = frequency -1)
   if (MT * kTcCG > 256 || C % kTcCG != 0) return set_error(LCASR_E_UNSUPPORTED, "subsample(tc): feat_in=%d / C=%d not supported", F, C);
   const size_t smem = 128 + (size_t)MT * 128 * kTcK * 2 + kTcCG * kTcK * 2 + (((size_t)kTcINR * FW * 4 + 127) & ~(size_t)127) +
-                      (size_t)kTcA0R * (F1 + 2) * 128;
+                      (size_t)kTcA0R * (F1 + 2) * kTcRowB;
   if (smem > 100 * 1024) return set_error(LCASR_E_UNSUPPORTED, "subsample(tc): tile needs %zu bytes of shared memory", smem);
   LCASR_CHECK_ARG(ceil_div(T2, kTcTT2) <= 0x7fffffff && B <= 65535, "subsample(tc): grid too large");
   static PerDeviceFlag attr_set;
