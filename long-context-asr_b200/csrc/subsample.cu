@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) subsample_dwconv_kernel(const T* __restri
 // (zeros where the depthwise conv pads), and reduces it to the 8 x F2 x 64 depthwise outputs.
 // HBM traffic drops to: input (re-read by the 4-8 channel groups, L2-resident) + the depthwise output.
 constexpr int kFuCG = 64;
-constexpr int kSubTcDefault = 0;
+constexpr int kSubTcDefault = 1;  // conv0 on the tensor cores: 0.985 vs 1.020 ms (cfg 3), 1.87 vs 1.97 (cfg 2), 5.33 vs 5.54 (cfg 4)
 
 template <int kFuTT2, int kMinBlocks>
 __global__ void __launch_bounds__(256, kMinBlocks) subsample_conv0_dw_fused_kernel(
