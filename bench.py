@@ -316,9 +316,10 @@ def seqpar_bench(mkey, T, dtype, steps, dev, rank, world, comm, dist):
             "speedup_vs_single_gpu": ms_1 / ms_sp, "efficiency": ms_1 / ms_sp / world, "audio_s_per_s": audio_s / (ms_sp / 1e3),
             "max_abs_vs_single_gpu": float(stats[0].item()), "argmax_disagree_frac_vs_single_gpu": float(stats[1].item()),
             "what": "forward + log-softmax + greedy decode of ONE recording; tokens split into contiguous blocks; per layer the K/V "
-                    "blocks move as ncclSend/ncclRecv pairs in ring order on a side stream while the tcgen05 attention kernel runs "
-                    "on the blocks already present (exact fp32 merge of the per-block partials); conv-module halo rows to/from the "
-                    "two neighbours; one C-ABI call per rank and step"}
+                    "blocks of the other ranks arrive by one in-place NCCL all-gather on a side stream (LCASR_SP_KV_MODE=2; 0 = "
+                    "ring-ordered ncclSend/ncclRecv steps) while the tcgen05 attention kernel already runs on the rank's own block, "
+                    "then on the keys in front of and behind it in planned pieces on four streams (exact fp32 merge of the partial "
+                    "results); conv-module halo rows to/from the two neighbours; one C-ABI call per rank and step"}
 
 
 def dp_train_bench(steps, dev, rank, world, dist):

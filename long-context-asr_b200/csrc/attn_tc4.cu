@@ -42,12 +42,14 @@ constexpr int F4_EX_BYTES = 2 * F4_BQ * (F4_EXO_STRIDE + 2) * 4;
 constexpr int F4_SMEM_BYTES = F4_Q_BYTES + F4_STAGES * F4_STAGE_BYTES + F4_EX_BYTES + 1024;
 constexpr int F4_P_COL = 256, F4_O_COL = 384;
 constexpr int kF4DefaultPoly = 0, kF4DefaultIpack = 0;
+constexpr float kF4TruncBias = 0.7213475f / 256.f;            // mean relative loss of truncating fp32 -> bf16
+constexpr float kF4TruncBiasLog2 = 1.4426950f * kF4TruncBias;  // log2(1 + b) ~ b / ln 2 (b = 2.8e-3: error 4e-6)
 
 // POLY = p > 0: every p-th odd key's exponential is evaluated on the FMA / ALU pipes (ex2_poly: Cody-Waite split + cubic,
 // relative error 1.6e-4, far below the bf16 rounding of P) instead of the MUFU pipe — 1/(2p) of all exponentials.
 // IPACK: P is packed to bf16 with integer arithmetic (+0x8000 on the fp32 bits = round half up, then one byte permute per
 // pair) instead of F2FP: ncu shows the conversion on the XU pipe next to MUFU.EX2 (81 % busy, 14 points of it not ex2).
-template <int POLY, bool IPACK>
+template <int POLY, int IPACK>
 __global__ void __launch_bounds__(F4_THREADS, 1)
 attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, int64_t N, int64_t Nk, const int32_t* __restrict__ kv_len, int H,
@@ -277,7 +279,10 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       float sums[4] = {0.f, 0.f, 0.f, 0.f};
-      const float neg_m = -m_run;
+      // IPACK == 2: P is TRUNCATED to bf16 by one byte permute (ALU pipe; F2FP shares the XU pipe with MUFU.EX2).  Truncation
+      // loses on average 0.7213 * 2^-8 of a value (log-uniform mantissa), so the exponent is offset by log2(1 + that): the
+      // row sum then carries the same factor as the mean of the truncated P, and O / l is unbiased; lse is corrected below.
+      const float neg_m = IPACK == 2 ? kF4TruncBiasLog2 - m_run : -m_run;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t pk[16];
@@ -292,7 +297,9 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const float p1 = (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == 0) ? ex2_poly(x1) : ex2_approx(x1);
           if (i & 1) fadd2(sums[2], sums[3], p0, p1);
           else fadd2(sums[0], sums[1], p0, p1);
-          if constexpr (IPACK) {  // p >= 0 and finite: no carry into the sign, ties (exact .5 ulp) round up instead of to even
+          if constexpr (IPACK == 2) {
+            pk[i] = __byte_perm(__float_as_uint(p0), __float_as_uint(p1), 0x7632);
+          } else if constexpr (IPACK == 1) {  // p >= 0 and finite: no carry into the sign, ties (exact .5 ulp) round up instead of to even
             pk[i] = __byte_perm(__float_as_uint(p0) + 0x8000u, __float_as_uint(p1) + 0x8000u, 0x7632);
           } else {
             __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
@@ -338,7 +345,7 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int64_t n = q0 + t * F4_BQ + row;
       if (n < N) {
         const int64_t o_off = ((b * N + n) * H + h_idx) * F4_DH;
-        if (lse) lse[(b * H + h_idx) * N + n] = M + log2f(l);
+        if (lse) lse[(b * H + h_idx) * N + n] = M + log2f(l) - (IPACK == 2 ? kF4TruncBiasLog2 : 0.f);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float y[8];
@@ -382,13 +389,15 @@ int attn_tc4_launch(const void* q, const void* k, const void* v, int B, int64_t 
     }                                                                                                                          \
     attn_tc4_kernel<P, I><<<grid, F4_THREADS, F4_SMEM_BYTES, st>>>(tmQ, tmK, tmV, N, Nk, kv_len, H, scale_log2, (bf16*)out, lse, out32); \
   }
-  if (ipack) {
-    LCASR_F4(0, true)
+  if (ipack == 2) {
+    LCASR_F4(0, 2)
+  } else if (ipack) {
+    LCASR_F4(0, 1)
   } else {
     switch (poly) {
-      case 2: LCASR_F4(2, false) break;
-      case 4: LCASR_F4(4, false) break;
-      default: LCASR_F4(0, false) break;
+      case 2: LCASR_F4(2, 0) break;
+      case 4: LCASR_F4(4, 0) break;
+      default: LCASR_F4(0, 0) break;
     }
   }
 #undef LCASR_F4

@@ -27,11 +27,27 @@ def main():
     ap.add_argument("--resid", action="store_true")
     ap.add_argument("--out", default="bf16")
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--check", action="store_true", help="attn: error against chunked fp32 softmax(QK^T)V")
+    ap.add_argument("--qscale", type=float, default=1.0, help="attn: scale of q (larger = more peaked rows)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     g = torch.Generator(device="cpu").manual_seed(0)
     if a.op == "attn":
         q, k, v = (torch.randn(a.B, a.N, a.H, a.Dh, generator=g).bfloat16().to(dev) for _ in range(3))
+        q = (q.float() * a.qscale).bfloat16()
+        if a.check:
+            o = ops.attention(q, k, v, impl=L.ATTN_TCGEN05).float()
+            kf, vf = k.float().transpose(1, 2), v.float().transpose(1, 2)
+            worst, bias, sq, cnt = 0.0, 0.0, 0.0, 0
+            for i in range(0, a.N, 2048):
+                qf = q[:, i:i + 2048].float().transpose(1, 2)
+                ref = torch.softmax(qf @ kf.transpose(-1, -2) / a.Dh ** 0.5, dim=-1) @ vf
+                d = o[:, i:i + 2048].transpose(1, 2) - ref
+                worst = max(worst, d.abs().max().item())
+                bias += (d * ref.sign()).sum().item()
+                sq += (d * d).sum().item()
+                cnt += d.numel()
+            print(f"attn check qscale {a.qscale}: max-abs {worst:.3e}  rms {(sq / cnt) ** 0.5:.3e}  mean signed (towards |ref|) {bias / cnt:.3e}")
         fn = lambda: ops.attention(q, k, v, impl=L.ATTN_TCGEN05)
         flops = 4.0 * a.B * a.H * a.N * a.N * a.Dh
     else:
