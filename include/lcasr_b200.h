@@ -492,6 +492,13 @@ void lcasr_model_destroy(lcasr_model* m);
 /* test / profiling hook: force the GEMM (LCASR_GEMM_*) and attention (LCASR_ATTN_*) kernels */
 int lcasr_model_set_impl(lcasr_model* m, int gemm_impl, int attn_impl);
 
+/* Tuning hook of the dense attention launch (bf16 tensor-core path).  A CTA owns 256 queries of one head and walks all
+ * keys, one CTA per SM, so a launch takes ceil(units / SMs) unit-times; by default (tail_pairs < 0) the forward computes
+ * the last `tail_pairs` query-tile pairs of the last recording as `key_pieces` key-range partial results on side streams
+ * (merged exactly) whenever a list-schedule model says the last wave would otherwise be mostly idle.  tail_pairs = 0
+ * turns that off; tail_pairs > 0 forces a split (key_pieces in 2..4). */
+int lcasr_model_set_attention_tail(lcasr_model* m, int tail_pairs, int key_pieces);
+
 /* In-step kernel timing for the roofline report: when enabled, lcasr_model_forward brackets every
  * kernel launch with CUDA events on the launch stream; lcasr_model_get_timing synchronises, returns
  * the summed milliseconds / launch counts per category and clears the recorder.

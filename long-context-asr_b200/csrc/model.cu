@@ -20,11 +20,17 @@ int attn_tc_available();
 int gemm_tc_launch_rope(const void* A, const void* W, int64_t M, int N, int K, const float* cos_t, const float* sin_t,
                         int64_t rope_n, int rope_cols, int dh, void* out, cudaStream_t st);
 int gemm_tc_launch_glu(const void* A, const void* W, int64_t M, int N, int K, const float* bias, void* out, cudaStream_t st);
+int attn_tc_launch(const void* q, const void* k, const void* v, int B, int64_t N, int64_t Nk, const int32_t* kv_len, int H,
+                   int Dh, int v_transposed, int64_t Npad, void* out, float* lse, cudaStream_t st, int wl = -1, int wr = -1,
+                   float* out32 = nullptr, int64_t ldq = 0, int64_t ldkv = 0);
+int attn_merge_launch(const float* parts, const float* lses, int P, int64_t n, int H, int Dh, int64_t part_stride,
+                      int64_t lse_stride, void* out, int out_dtype, cudaStream_t st);
 }
 
 using namespace lcasr;
 
 #include "model_internal.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -72,6 +78,47 @@ Plan make_plan(const lcasr_config& c, int B, int64_t T) {
   return p;
 }
 
+// ---- wave quantisation of the attention launch ----
+// One CTA of the flash kernels owns 256 queries of one head and walks ALL keys, one CTA per SM: the launch is U = B*H*ceil(N/256)
+// equal units on W SMs and takes ceil(U / W) unit-times — 1536 units on 148 SMs are 10.38 waves of work in 11 (cfg 3), 2816
+// units 19.03 in 20 (cfg 4), 768 units 5.19 in 6 (cfg 2).  The last t query-tile pairs of the last recording are therefore
+// computed as P key-range pieces (exact partial results + the merge kernel of the sequence-parallel path) on side streams:
+// the short CTAs fill the SMs the last wave leaves idle.  Greedy list-schedule model, all candidates (t, P) tried.
+double attention_makespan(int W, int64_t full, double full_cost, int64_t pieces, double piece_cost) {
+  std::vector<double> sm((size_t)W, 0.0);  // a heap of SM-free times
+  auto cmp = [](double a, double b) { return a > b; };
+  auto run = [&](int64_t n, double cost) {
+    for (int64_t i = 0; i < n; ++i) {
+      std::pop_heap(sm.begin(), sm.end(), cmp);
+      sm.back() += cost;
+      std::push_heap(sm.begin(), sm.end(), cmp);
+    }
+  };
+  run(full, full_cost);
+  run(pieces, piece_cost);
+  return *std::max_element(sm.begin(), sm.end());
+}
+
+lcasr_model::TailPlan plan_attention_tail(int B, int64_t N, int H, int W) {
+  lcasr_model::TailPlan best;
+  best.B = B; best.N = N;
+  static const bool off = getenv("LCASR_ATTN_TAIL") && atoi(getenv("LCASR_ATTN_TAIL")) == 0;
+  const int64_t nq = ceil_div(N, (int64_t)256), nkt = ceil_div(N, (int64_t)128);
+  const int64_t U = (int64_t)B * H * nq;
+  if (off || U <= W || nkt < 16) return best;
+  const double ovh = 1.5 / (double)nkt;  // prologue + epilogue of a CTA in unit-times
+  const double base = attention_makespan(W, U, 1.0 + ovh, 0, 0.0);
+  double best_ms = base * 0.985;  // worth two more launches and a merge only beyond 1.5 %
+  for (int t = 1; t <= 8 && t <= nq; ++t)
+    for (int P = 2; P <= 4; ++P) {
+      if (nkt / P < 4) continue;
+      const double piece = (double)ceil_div(nkt, (int64_t)P) / (double)nkt + ovh;
+      const double ms = attention_makespan(W, U - (int64_t)t * H, 1.0 + ovh, (int64_t)t * H * P, piece);
+      if (ms < best_ms) { best_ms = ms; best.t = t; best.P = P; }
+    }
+  return best;
+}
+
 }  // namespace
 
 extern "C" int lcasr_model_create(const lcasr_config* cfg, const lcasr_weights* w, lcasr_model** out) {
@@ -95,6 +142,17 @@ extern "C" int lcasr_model_create(const lcasr_config* cfg, const lcasr_weights* 
   m->w = *w;
   m->layers.assign(w->layers_host, w->layers_host + cfg->n_layers);
   m->w.layers_host = m->layers.data();
+  for (int i = 0; i < lcasr_model::kTailStreams; ++i) {
+    if (cudaStreamCreateWithFlags(&m->tail_streams[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->tail_done[i], cudaEventDisableTiming) != cudaSuccess) {
+      delete m;
+      return set_error(LCASR_E_CUDA, "model_create: cannot create the side streams of the attention tail split");
+    }
+  }
+  if (cudaEventCreateWithFlags(&m->tail_fork, cudaEventDisableTiming) != cudaSuccess) {
+    delete m;
+    return set_error(LCASR_E_CUDA, "model_create: cannot create an event");
+  }
   *out = m;
   return 0;
 }
@@ -105,6 +163,16 @@ extern "C" int lcasr_model_set_impl(lcasr_model* m, int gemm_impl, int attn_impl
   LCASR_CHECK_ARG(m, "model_set_impl: NULL model");
   m->gemm_impl = gemm_impl;
   m->attn_impl = attn_impl;
+  return 0;
+}
+
+extern "C" int lcasr_model_set_attention_tail(lcasr_model* m, int tail_pairs, int key_pieces) {
+  LCASR_CHECK_ARG(m, "model_set_attention_tail: NULL model");
+  LCASR_CHECK_ARG(tail_pairs <= 0 || (key_pieces >= 2 && key_pieces <= 4), "model_set_attention_tail: key_pieces %d not in 2..4",
+                  key_pieces);
+  m->tail_force_t = tail_pairs;
+  m->tail_force_p = key_pieces;
+  m->tail_plan = lcasr_model::TailPlan();
   return 0;
 }
 
@@ -219,6 +287,73 @@ extern "C" int lcasr_model_forward_lengths(lcasr_model* m, const float* spec, in
   // transposed-V layout: the key padding columns [N, Npad) are read by TMA (times P == 0): keep them finite
   if (vt) LCASR_CUDA(cudaMemsetAsync(v, 0, (size_t)B * H * Dh * p.Npad * dtype_size(cd), cst));
 
+  // attention of the fused path with the last wave filled (plan_attention_tail); the partial results live in the q / k / v
+  // buffers, which the fused path does not use
+  if (m->tail_plan.B != B || m->tail_plan.N != N) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    m->tail_plan = plan_attention_tail(B, N, H, sms);
+    if (m->tail_force_t >= 0) {
+      m->tail_plan.t = (int)std::min<int64_t>(m->tail_force_t, ceil_div(N, (int64_t)256));
+      m->tail_plan.P = m->tail_force_p;
+      if (m->tail_plan.P > ceil_div(N, (int64_t)128)) m->tail_plan.t = 0;
+    }
+  }
+  lcasr_model::TailPlan tail = m->tail_plan;
+  {
+    const int64_t rows_tail = N - std::max<int64_t>(0, ceil_div(N, (int64_t)256) - tail.t) * 256;
+    const size_t need = (size_t)tail.P * rows_tail * (d + H) * 4;
+    if (cd != LCASR_BF16 || need > (size_t)(p.off_v - p.off_q) + (size_t)M * d * 2) tail.t = 0;
+  }
+  auto attention_qkv_tail_split = [&]() -> int {
+    const int64_t ld = 3 * (int64_t)d;
+    const int64_t n_main = (ceil_div(N, (int64_t)256) - tail.t) * 256, rows_tail = N - n_main;
+    const char* qb = (const char*)wide + (size_t)(B - 1) * N * ld * 2;  // the last recording
+    const char* kb = qb + (size_t)d * 2;
+    const char* vb = qb + (size_t)2 * d * 2;
+    char* ob = (char*)a2 + (size_t)(B - 1) * N * d * 2;
+    float* parts = (float*)q;
+    float* lses = parts + (size_t)tail.P * rows_tail * d;
+    cudaStream_t* ss = m->tail_streams;
+    LCASR_CUDA(cudaEventRecord(m->tail_fork, cst));
+    const int n_side = tail.P + 1;
+    for (int i = (B > 1 ? 0 : 1); i < n_side; ++i) LCASR_CUDA(cudaStreamWaitEvent(ss[i], m->tail_fork, 0));
+    // full-length CTAs first (launch order = dispatch order): the other recordings, then the last recording's leading rows —
+    // on their own stream when both exist, so that neither waits for the other's last wave
+    if (B > 1) {
+      const char* w0 = (const char*)wide;
+      LCASR_TRY(attn_tc_launch(w0, w0 + (size_t)d * 2, w0 + (size_t)2 * d * 2, B - 1, N, N, nullptr, H, Dh, 0, 0, a2, nullptr, cst, -1,
+                               -1, nullptr, ld, ld));
+    }
+    if (n_main > 0)
+      LCASR_TRY(attn_tc_launch(qb, kb, vb, 1, n_main, N, nullptr, H, Dh, 0, 0, ob, nullptr, B > 1 ? ss[0] : cst, -1, -1, nullptr, ld,
+                               ld));
+    const int64_t nkt = ceil_div(N, (int64_t)128), tiles = ceil_div(nkt, (int64_t)tail.P);
+    int n_parts = 0;
+    for (int s = 0; s < tail.P; ++s) {
+      const int64_t k0 = s * tiles * 128, k1 = std::min<int64_t>(N, k0 + tiles * 128);
+      if (k1 <= k0) break;
+      LCASR_TRY(attn_tc_launch(qb + (size_t)n_main * ld * 2, kb + (size_t)k0 * ld * 2, vb + (size_t)k0 * ld * 2, 1, rows_tail, k1 - k0,
+                               nullptr, H, Dh, 0, 0, nullptr, lses + (size_t)s * H * rows_tail, ss[1 + s], -1, -1,
+                               parts + (size_t)s * rows_tail * d, ld, ld));
+      ++n_parts;
+    }
+    for (int s = 1; s < n_parts; ++s) {
+      LCASR_CUDA(cudaEventRecord(m->tail_done[1 + s], ss[1 + s]));
+      LCASR_CUDA(cudaStreamWaitEvent(ss[1], m->tail_done[1 + s], 0));
+    }
+    LCASR_TRY(attn_merge_launch(parts, lses, n_parts, rows_tail, H, Dh, rows_tail * d, (int64_t)H * rows_tail,
+                                ob + (size_t)n_main * d * 2, LCASR_BF16, ss[1]));
+    LCASR_CUDA(cudaEventRecord(m->tail_done[1], ss[1]));
+    LCASR_CUDA(cudaStreamWaitEvent(cst, m->tail_done[1], 0));
+    if (B > 1 && n_main > 0) {
+      LCASR_CUDA(cudaEventRecord(m->tail_done[0], ss[0]));
+      LCASR_CUDA(cudaStreamWaitEvent(cst, m->tail_done[0], 0));
+    }
+    return 0;
+  };
+
   bool final_operand_ready = false;
   for (int l = 0; l < c.n_layers; ++l) {
     const lcasr_layer_weights& L = m->layers[l];
@@ -236,7 +371,8 @@ extern "C" int lcasr_model_forward_lengths(lcasr_model* m, const float* spec, in
       } else {
         LCASR_TRY(gemm(a, L.qkv_w, M, 3 * d, d, nullptr, LCASR_ACT_NONE, nullptr, 0.f, wide, cd));
       }
-      OP(CAT_ATTN, lcasr_attention_qkv(wide, B, N, tok_len, H, Dh, a2, stream));
+      if (tail.t > 0 && !tok_len) OP(CAT_ATTN, attention_qkv_tail_split());
+      else OP(CAT_ATTN, lcasr_attention_qkv(wide, B, N, tok_len, H, Dh, a2, stream));
     } else {
     LCASR_TRY(gemm(a, L.qkv_w, M, 3 * d, d, nullptr, LCASR_ACT_NONE, nullptr, 0.f, wide, cd));
     OP(CAT_ROPE, lcasr_rope_split(wide, cd, B, N, H, Dh, c.use_rotary ? cos_t : nullptr, c.use_rotary ? sin_t : nullptr, q, k,

@@ -26,8 +26,18 @@ struct lcasr_model {
     }
     return ev_pool[ev_used++];
   }
+  // wave-quantisation fix of the attention launch (model.cu: attention_tail_split): side streams + fork / join events
+  static constexpr int kTailStreams = 5;
+  cudaStream_t tail_streams[kTailStreams] = {};
+  cudaEvent_t tail_fork = nullptr, tail_done[kTailStreams] = {};
+  struct TailPlan { int B = -1; int64_t N = -1; int t = 0, P = 0; };  // last t query-tile pairs of the last recording in P key pieces
+  TailPlan tail_plan;
+  int tail_force_t = -1, tail_force_p = 0;  // lcasr_model_set_attention_tail
   ~lcasr_model() {
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+    for (cudaStream_t s : tail_streams) if (s) cudaStreamDestroy(s);
+    for (cudaEvent_t e : tail_done) if (e) cudaEventDestroy(e);
+    if (tail_fork) cudaEventDestroy(tail_fork);
   }
 };
 

@@ -86,6 +86,13 @@ int merge_launch(const float* parts, const float* lses, int P, int64_t n, int H,
 
 }  // namespace
 
+namespace lcasr {
+int attn_merge_launch(const float* parts, const float* lses, int P, int64_t n, int H, int Dh, int64_t part_stride,
+                      int64_t lse_stride, void* out, int out_dtype, cudaStream_t st) {
+  return merge_launch(parts, lses, P, n, H, Dh, part_stride, lse_stride, out, out_dtype, st);
+}
+}  // namespace lcasr
+
 extern "C" int lcasr_attention_partial(const void* q, const void* k, const void* v, int B, int64_t Nq, int64_t Nk, int H, int Dh,
                                        float* out32, float* lse, void* stream) {
   LCASR_CHECK_ARG(q && k && v && out32 && lse, "attention_partial: NULL operand");

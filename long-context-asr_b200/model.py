@@ -300,6 +300,12 @@ class SCConformerXL(nn.Module):
         if self._handle is not None:
             L.call("lcasr_model_set_impl", self._handle, gemm, attn)
 
+    def set_attention_tail(self, tail_pairs: int = -1, key_pieces: int = 0):
+        """tuning hook (lcasr_model_set_attention_tail): -1 = planned automatically, 0 = off, > 0 = forced split."""
+        self._attn_tail = (int(tail_pairs), int(key_pieces))
+        if self._handle is not None:
+            L.call("lcasr_model_set_attention_tail", self._handle, *self._attn_tail)
+
     def _state_key(self):
         return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers())) + \
             (self.compute_dtype, L.WEIGHT_EPOCH[0])
@@ -424,6 +430,7 @@ class SCConformerXL(nn.Module):
         self._keepalive = (keep, layers, w)
         self._packed = packed
         L.call("lcasr_model_set_impl", self._handle, *self._impl)
+        L.call("lcasr_model_set_attention_tail", self._handle, *getattr(self, "_attn_tail", (-1, 0)))
 
     def _ensure_built(self, device):
         key = (self._state_key(), str(device))

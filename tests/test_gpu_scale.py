@@ -106,3 +106,28 @@ def test_cfg2_shape_synthetic_weights_vs_oracle(cuda_device):
     report(test="model_cfg2_shape_fp32", max_abs=err32)
     assert err32 < 1e-4 * scale
     assert [O.greedy_decode(lp32[b], 4095) for b in range(2)] == [O.greedy_decode(ref[b], 4095) for b in range(2)]
+
+
+@pytest.mark.parametrize("B,T,t,P", [(1, 32768, 2, 3), (1, 36000, 3, 2), (3, 24576, 1, 4), (1, 16384, 4, 2)])
+def test_attention_tail_split_equals_one_launch(cuda_device, B, T, t, P):
+    """The wave-quantisation fix of the dense attention launch (lcasr_model_set_attention_tail): the last query-tile pairs of the
+    last recording computed as key-range partial results on side streams + exact merge must give the single-launch result
+    up to the bf16 rounding of the attention output (the partial results are merged in fp32)."""
+    cfg = O.make_config(**O.BASELINE_MODELS["cfg1_6L256D8H"])
+    x = O.synth_input(B, T, cfg["feat_in"], seed=77).to(cuda_device)
+    model, _ = _default_init_model(cfg, cuda_device, "bf16")
+    with torch.no_grad():
+        model.set_attention_tail(0, 0)
+        ref = model(x)["final_posteriors"].float()
+        model.set_attention_tail(t, P)
+        got = model(x)["final_posteriors"].float()
+        got2 = model(x)["final_posteriors"].float()
+    err = (got - ref).abs().max().item()
+    report(test="attention_tail_split", B=B, T=T, t=t, P=P, max_abs=err)
+    assert torch.isfinite(got).all()
+    assert torch.equal(got, got2), "tail split is not repeatable (missing stream dependency?)"
+    assert err < 8e-3, f"tail split differs from the single launch by {err}"
+    # rows far from the tail see the same attention launch arithmetic: most of the output is bit-identical in layer 1 only,
+    # so the check here is the bound above plus agreement of the confident argmaxes
+    mask = margin_mask(ref, 4e-2)
+    assert (got.argmax(-1)[mask] == ref.argmax(-1)[mask]).all()

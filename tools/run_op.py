@@ -36,7 +36,7 @@ def main():
         q, k, v = (torch.randn(a.B, a.N, a.H, a.Dh, generator=g).bfloat16().to(dev) for _ in range(3))
         q = (q.float() * a.qscale).bfloat16()
         if a.check:
-            o = ops.attention(q, k, v, impl=L.ATTN_TCGEN05).float()
+            o = ops.attention(q, k, v, impl=L.ATTN_TCGEN05).float().reshape(a.B, a.N, a.H, a.Dh)
             kf, vf = k.float().transpose(1, 2), v.float().transpose(1, 2)
             worst, bias, sq, cnt = 0.0, 0.0, 0.0, 0
             for i in range(0, a.N, 2048):
