@@ -280,6 +280,18 @@ int lcasr_gemm_ex(const lcasr_gemm_ex_args* args, void* stream);
 int lcasr_attention_bwd_pds(const void* q, const void* k, const void* v, const void* d_out, const float* lse2,
                             const float* dvec, int nb, int64_t N, int H, int Dh, void* P, void* dS, void* stream);
 
+/* The whole attention backward, flash style (head_dim 64 or 128): dq, dk, dv from q, k, v, the saved output o, its
+ * gradient d_out and the forward's lse2, WITHOUT materialising P or dS — O(N) memory, so a 20-minute context trains
+ * (replaces flash-attn's backward behind attention.py:509-551 / F.scaled_dot_product_attention autograd).  One launch
+ * computes dk, dv (a CTA owns 128 keys and streams the queries), a second dq (a CTA owns 128 queries and streams the
+ * keys); the score tiles are recomputed on the tensor cores in both.  All tensors bf16 [nb, n_pitch, H, Dh], the first
+ * N tokens of every recording valid (gradient rows beyond N are not written); lse2 fp32 [nb, H, lse_pitch];
+ * workspace: lcasr_attention_bwd_flash_workspace_bytes(nb, N, H) bytes, 16-byte aligned. */
+int64_t lcasr_attention_bwd_flash_workspace_bytes(int nb, int64_t N, int H);
+int lcasr_attention_bwd_flash(const void* q, const void* k, const void* v, const void* o, const void* d_out,
+                              const float* lse2, int nb, int64_t N, int64_t n_pitch, int64_t lse_pitch, int H, int Dh,
+                              void* dq, void* dk, void* dv, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Attention forward that also returns lse [B,H,N] fp32 = log2-domain log-sum-exp of the scaled scores
  * (bf16, natural-layout V, tcgen05 kernel). */
 int lcasr_attention_train(const void* q, const void* k, const void* v, int B, int64_t N, int H, int Dh,

@@ -111,6 +111,7 @@ _SIGNATURES = {
     "lcasr_ctc_loss_grad": [vp, i32, i64, i32, vp, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp],
     "lcasr_gemm_ex": [C.POINTER(LcasrGemmExArgs), vp],
     "lcasr_attention_bwd_pds": [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, vp, vp, vp],
+    "lcasr_attention_bwd_flash": [vp, vp, vp, vp, vp, vp, i32, i64, i64, i64, i32, i32, vp, vp, vp, vp, i64, vp],
     "lcasr_attention_train": [vp, vp, vp, i32, i64, i32, i32, vp, vp, vp],
     "lcasr_gemm_act_pre": [vp, vp, i64, i32, i32, vp, i32, vp, vp, vp],
     "lcasr_scale_cast": [vp, i64, f32, vp, vp],
@@ -168,6 +169,7 @@ _OTHER = {
     "lcasr_model_transcribe_workspace_bytes": ([vp, i32, i64], i64),
     "lcasr_comm_destroy": ([vp], None),
     "lcasr_ctc_workspace_bytes": ([i32, i64, i64, i32], i64),
+    "lcasr_attention_bwd_flash_workspace_bytes": ([i32, i64, i32], i64),
     "lcasr_model_seqpar_workspace_bytes": ([vp, i32, i32, i64], i64),
     "lcasr_model_seqpar_emulated_workspace_bytes": ([vp, i32, i64], i64),
 }

@@ -568,6 +568,274 @@ attn_bwd_pds_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
+
+// ---- attention backward, flash style: no N x N tensor ever reaches memory -------------------------------------
+// Two launches of one kernel template (7 tile products instead of the 5 of the materialised form, but no atomics and
+// O(N) memory):
+//   MODE 0 (dK, dV): a CTA owns 128 KEYS (K_j, V_j resident in shared memory) and streams 64-query chunks (Q_i, dO_i):
+//       S^T = K_j Q_i^T, dP^T = V_j dO_i^T            (SS products, 128 x 64 fp32 accumulators, double-buffered)
+//       P^T = exp2(S^T c - lse_i), dS^T = P^T o (dP^T - D_i) scale   -> bf16, written over the accumulators they came from
+//       dV_j += P^T dO_i, dK_j += dS^T Q_i            (TS products: A from tensor memory, B = the same chunk tiles read
+//                                                      as MN-major operands — no transposed copies)
+//   MODE 1 (dQ):     a CTA owns 128 QUERIES (Q_i, dO_i resident) and streams 64-key chunks (K_j, V_j):
+//       S = Q_i K_j^T, dP = dO_i V_j^T, dS as above (lane = query: lse / D are per-thread scalars), dQ_i += dS K_j.
+// The transposed formulation of MODE 0 is what lets P^T / dS^T be TS operands: tensor memory lanes must be the M
+// dimension (keys) of the dV / dK products.  TMEM: accumulators [0, 2 Dh) (MODE 1: [0, Dh)), then 2 x 64 columns of
+// S and 2 x 64 of dP.  Per-row statistics come packed as float2 {lse2, D * scale} per (recording, head, token), padded
+// to a multiple of 128 tokens with {+inf, 0} (P = dS = 0 for tokens that do not exist) by attn_bwd_prep_kernel.
+// Warps 0-7: softmax (two per TMEM lane quarter, 32 columns each), warp 8: TMA producer, warp 9: MMA issuer.
+constexpr int FB_THREADS = 320, FB_STAGES = 3, FB_CH = 64;
+template <int DH> struct FbCfg {
+  static constexpr int SUB = DH / 64;
+  static constexpr int X_BYTES = SUB * 128 * 128;          // one resident tile: [128 rows][DH] as SUB swizzled boxes
+  static constexpr int Y_BYTES = SUB * FB_CH * 128;        // one streamed tile: [64 rows][DH]
+  static constexpr int STAGE_BYTES = 2 * Y_BYTES;
+  static constexpr int VEC_BYTES = FB_CH * 8;
+  static constexpr int SMEM = 2 * X_BYTES + FB_STAGES * STAGE_BYTES + FB_STAGES * VEC_BYTES + 1024;
+};
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct FbParams {
+  int64_t N, Npad;        // valid tokens; padded length of the statistics rows
+  int64_t tok_stride;     // elements between consecutive tokens of an output tensor (H * Dh)
+  int64_t rec_stride;     // elements between recordings of an output tensor
+  int H;
+  float c_log2, scale;    // scale * log2(e), scale
+  const float2* stats;    // [nb, H, Npad]
+  bf16* out1;             // MODE 0: dV, MODE 1: dQ
+  bf16* out2;             // MODE 0: dK
+};
+
+template <int DH, int MODE>
+__global__ void __launch_bounds__(FB_THREADS, 1)
+attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
+                      const __grid_constant__ CUtensorMap tmY1, const __grid_constant__ CUtensorMap tmY2, FbParams p) {
+  using Cfg = FbCfg<DH>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[1 + 2 * FB_STAGES + 2 + 2 + 1];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t x1_smem = smem_base, x2_smem = smem_base + Cfg::X_BYTES;
+  auto y1_smem = [&](int s) { return smem_base + 2 * Cfg::X_BYTES + s * Cfg::STAGE_BYTES; };
+  auto y2_smem = [&](int s) { return y1_smem(s) + Cfg::Y_BYTES; };
+  const uint32_t vec0 = smem_base + 2 * Cfg::X_BYTES + FB_STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t x_full = bar0;
+  auto full_bar = [&](int s) { return bar0 + 8u * (1 + s); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (1 + FB_STAGES + s); };
+  auto s_full = [&](int u) { return bar0 + 8u * (1 + 2 * FB_STAGES + u); };      // S, dP of a chunk retired
+  auto p_full = [&](int u) { return bar0 + 8u * (1 + 2 * FB_STAGES + 2 + u); };  // P / dS written (8 warps)
+  const uint32_t done_bar = bar0 + 8u * (1 + 2 * FB_STAGES + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int x_row0 = blockIdx.x * 128;
+  const int n_chunks = (int)((p.N + FB_CH - 1) / FB_CH);
+  constexpr int ACC_COLS = MODE == 0 ? 2 * DH : DH;
+  constexpr int S_COL = ACC_COLS, DP_COL = ACC_COLS + 128;
+
+  if (warp == 8 && lane == 0) {
+    prefetch_tensormap(&tmX1); prefetch_tensormap(&tmX2); prefetch_tensormap(&tmY1); prefetch_tensormap(&tmY2);
+    mbar_init(x_full, 1);
+    for (int s = 0; s < FB_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int u = 0; u < 2; ++u) { mbar_init(s_full(u), 1); mbar_init(p_full(u), 8); }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(smem_u32(&tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+  const float2* stats_row = p.stats + ((int64_t)b * p.H + h) * p.Npad;
+
+  if (warp == 8) {
+    if (lane == 0) {  // ------------------------- TMA producer -------------------------
+      mbar_arrive_expect_tx(x_full, 2 * Cfg::X_BYTES);
+#pragma unroll
+      for (int i = 0; i < Cfg::SUB; ++i) {
+        tma_load_4d(x1_smem + i * 16384, &tmX1, x_full, i * 64, x_row0, h, b);
+        tma_load_4d(x2_smem + i * 16384, &tmX2, x_full, i * 64, x_row0, h, b);
+      }
+      int stage = 0; uint32_t phase = 0;
+      for (int c = 0; c < n_chunks; ++c) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES + (MODE == 0 ? Cfg::VEC_BYTES : 0));
+#pragma unroll
+        for (int i = 0; i < Cfg::SUB; ++i) {
+          tma_load_4d(y1_smem(stage) + i * 8192, &tmY1, full_bar(stage), i * 64, c * FB_CH, h, b);
+          tma_load_4d(y2_smem(stage) + i * 8192, &tmY2, full_bar(stage), i * 64, c * FB_CH, h, b);
+        }
+        if (MODE == 0) bulk_load_1d(vec0 + stage * Cfg::VEC_BYTES, stats_row + (int64_t)c * FB_CH, Cfg::VEC_BYTES, full_bar(stage));
+        if (++stage == FB_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------- MMA issuer (converged warp, one elected lane issues) -------------------------
+    constexpr uint32_t idesc_s = make_idesc_bf16_mn(128, FB_CH, 0, 0);
+    constexpr uint32_t idesc_acc = make_idesc_bf16_mn(128, DH, 0, 1);  // A from tensor memory, B MN-major
+    auto issue_s = [&](int stage, int u) {
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        const int sub = kk / 4, within = kk % 4;
+        umma_f16_ss(tmem_base + S_COL + u * FB_CH, make_smem_desc_kmajor(x1_smem + sub * 16384, 1024, kLayoutSW128) + 2 * within,
+                    make_smem_desc_kmajor(y1_smem(stage) + sub * 8192, 1024, kLayoutSW128) + 2 * within, idesc_s, kk != 0);
+      }
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        const int sub = kk / 4, within = kk % 4;
+        umma_f16_ss(tmem_base + DP_COL + u * FB_CH, make_smem_desc_kmajor(x2_smem + sub * 16384, 1024, kLayoutSW128) + 2 * within,
+                    make_smem_desc_kmajor(y2_smem(stage) + sub * 8192, 1024, kLayoutSW128) + 2 * within, idesc_s, kk != 0);
+      }
+    };
+    // bf16 operand columns of a chunk: the softmax warp of column half hc writes its 32 values as 16 packed columns at the
+    // START of its own fp32 range (never over columns another warp may still have to read): k-step kk -> (kk/2)*32 + (kk%2)*8
+    auto issue_acc = [&](int stage, int u, bool accumulate) {
+      if (MODE == 0) {
+#pragma unroll
+        for (int kk = 0; kk < FB_CH / 16; ++kk)  // dV += P^T dO
+          umma_f16_ts(tmem_base, tmem_base + S_COL + u * FB_CH + (kk >> 1) * 32 + (kk & 1) * 8,
+                      make_smem_desc_mnmajor(y2_smem(stage)) + kk * (2048 >> 4), idesc_acc, (accumulate || kk != 0) ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < FB_CH / 16; ++kk)  // dK += dS^T Q
+          umma_f16_ts(tmem_base + DH, tmem_base + DP_COL + u * FB_CH + (kk >> 1) * 32 + (kk & 1) * 8,
+                      make_smem_desc_mnmajor(y1_smem(stage)) + kk * (2048 >> 4), idesc_acc, (accumulate || kk != 0) ? 1u : 0u);
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < FB_CH / 16; ++kk)  // dQ += dS K
+          umma_f16_ts(tmem_base, tmem_base + DP_COL + u * FB_CH + (kk >> 1) * 32 + (kk & 1) * 8,
+                      make_smem_desc_mnmajor(y1_smem(stage)) + kk * (2048 >> 4), idesc_acc, (accumulate || kk != 0) ? 1u : 0u);
+      }
+    };
+    mbar_wait(x_full, 0);
+    for (int c = 0; c < 2 && c < n_chunks; ++c) {
+      mbar_wait(full_bar(c), 0);
+      tc_fence_after();
+      if (elect_one()) { issue_s(c, c); umma_commit(s_full(c)); }
+      __syncwarp();
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+      const int u = c & 1, stage = c % FB_STAGES;
+      mbar_wait(p_full(u), (c >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) { issue_acc(stage, u, c > 0); umma_commit(empty_bar(stage)); }
+      __syncwarp();
+      if (c + 2 < n_chunks) {
+        // S / dP of chunk c+2 reuse buffer u: the in-order tensor pipe runs them after the products that read P / dS(c)
+        const int st2 = (c + 2) % FB_STAGES;
+        mbar_wait(full_bar(st2), ((c + 2) / FB_STAGES) & 1);
+        tc_fence_after();
+        if (elect_one()) { issue_s(st2, u); umma_commit(s_full(u)); }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) umma_commit(done_bar);
+    __syncwarp();
+  } else {
+    // ------------------------- softmax warps -------------------------
+    const int lq = warp & 3, hc = warp >> 2;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(lq * 32) << 16);
+    float lse_r = 0.f, dsc_r = 0.f;  // MODE 1: this lane's query row
+    if (MODE == 1) {
+      const float2 st = stats_row[x_row0 + lq * 32 + lane];  // padded to a multiple of 128 rows
+      lse_r = st.x; dsc_r = st.y;
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+      const int u = c & 1, stage = c % FB_STAGES;
+      if (MODE == 0) mbar_wait(full_bar(stage), (c / FB_STAGES) & 1);  // the statistics of this chunk (already complete)
+      mbar_wait(s_full(u), (c >> 1) & 1);
+      tc_fence_after();
+      uint32_t s[32], dp[32];
+      tmem_ld_32x32b_x32(t_lane + S_COL + u * FB_CH + hc * 32, s);
+      tmem_ld_32x32b_x32(t_lane + DP_COL + u * FB_CH + hc * 32, dp);
+      tmem_wait_ld();
+      uint32_t pk[16], dk[16];
+      const float2* vec = reinterpret_cast<const float2*>(smem_raw + (vec0 - smem_u32(smem_raw)) + stage * Cfg::VEC_BYTES) + hc * 32;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float l0 = lse_r, l1 = lse_r, d0 = dsc_r, d1 = dsc_r;
+        if (MODE == 0) {
+          const float4 v2 = *reinterpret_cast<const float4*>(vec + 2 * i);  // two queries' {lse, D scale}: broadcast read
+          l0 = v2.x; d0 = v2.y; l1 = v2.z; d1 = v2.w;
+        }
+        const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * i]), p.c_log2, -l0));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), p.c_log2, -l1));
+        const float g0 = p0 * fmaf(__uint_as_float(dp[2 * i]), p.scale, -d0);
+        const float g1 = p1 * fmaf(__uint_as_float(dp[2 * i + 1]), p.scale, -d1);
+        __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1), gg = __floats2bfloat162_rn(g0, g1);
+        pk[i] = *reinterpret_cast<uint32_t*>(&pp);
+        dk[i] = *reinterpret_cast<uint32_t*>(&gg);
+      }
+      if (MODE == 0) tmem_st_32x32b_x16(t_lane + S_COL + u * FB_CH + hc * 32, pk);
+      tmem_st_32x32b_x16(t_lane + DP_COL + u * FB_CH + hc * 32, dk);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(u));
+    }
+    // ---- epilogue: this warp's lane quarter, column half hc of every accumulator ----
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const int64_t row = (int64_t)x_row0 + lq * 32 + lane;
+#pragma unroll
+    for (int a = 0; a < (MODE == 0 ? 2 : 1); ++a) {
+      bf16* outp = (a == 0 ? p.out1 : p.out2) + (int64_t)b * p.rec_stride + row * p.tok_stride + (int64_t)h * DH;
+#pragma unroll
+      for (int cc = 0; cc < DH / 64; ++cc) {
+        const int col = hc * (DH / 2) + cc * 32;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_lane + a * DH + col, r);
+        tmem_wait_ld();
+        if (row < p.N) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float y[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(r[8 * g + i]);
+            Vec8<bf16>::store(outp + col + 8 * g, y);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// D = rowsum(dO o O) and the packed per-row statistics {lse2, D * scale} of the flash backward
+__global__ void attn_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_out, const float* __restrict__ lse2,
+                                     int nb, int64_t N, int64_t Npad, int64_t n_pitch, int64_t lse_pitch, int H, int Dh,
+                                     float scale, float2* __restrict__ stats) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (b, n in [0, Npad), h), h fastest
+  if (idx >= (int64_t)nb * Npad * H) return;
+  const int h = (int)(idx % H);
+  const int64_t n = (idx / H) % Npad, b = idx / ((int64_t)H * Npad);
+  float2 st = make_float2(INFINITY, 0.f);
+  if (n < N) {
+    const int64_t off = ((b * n_pitch + n) * H + h) * Dh;
+    float acc = 0.f;
+    for (int i = 0; i < Dh; i += 8) {
+      float a[8], g[8];
+      Vec8<bf16>::load(o + off + i, a);
+      Vec8<bf16>::load(d_out + off + i, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(a[j], g[j], acc);
+    }
+    st = make_float2(lse2[(b * H + h) * lse_pitch + n], acc * scale);
+  }
+  stats[(b * H + h) * Npad + n] = st;
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 
 typedef CUresult (*PFN_tmapEncodeTiledX)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -764,4 +1032,69 @@ extern "C" int lcasr_attention_bwd_pds(const void* q, const void* k, const void*
   attn_bwd_pds_kernel<<<grid, TX_THREADS, PDS_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmDO, tmV, tmP, tmDS, p);
   LCASR_LAUNCH_CHECK();
   return 0;
+}
+
+// Flash-style attention backward (attn_bwd_flash_kernel): q, k, v, o, dO, dq, dk, dv bf16 [nb, n_pitch, H, Dh] of which
+// the first N tokens of every recording are valid; lse2 fp32 [nb, H, lse_pitch] (log2-domain, from the training forward);
+// workspace: lcasr_attention_bwd_flash_workspace_bytes.  Gradient rows of tokens >= N are left untouched.
+extern "C" int64_t lcasr_attention_bwd_flash_workspace_bytes(int nb, int64_t N, int H) {
+  if (nb <= 0 || N <= 0 || H <= 0) return -1;
+  return (int64_t)nb * H * round_up(N, (int64_t)128) * 8;
+}
+
+template <int DH>
+static int launch_attn_bwd_flash(const void* q, const void* k, const void* v, const void* d_out, int nb, int64_t N, int64_t n_pitch,
+                                 int H, const float2* stats, int64_t Npad, void* dq, void* dk, void* dv, cudaStream_t st) {
+  using Cfg = FbCfg<DH>;
+  const int64_t d = (int64_t)H * DH;
+  CUtensorMap kX, vX, qY, oY, qX, oX, kY, vY;
+  LCASR_TRY(make_tmap_4d(&kX, k, (uint64_t)N, DH, d, H, DH, nb, n_pitch * d, 128, 64));
+  LCASR_TRY(make_tmap_4d(&vX, v, (uint64_t)N, DH, d, H, DH, nb, n_pitch * d, 128, 64));
+  LCASR_TRY(make_tmap_4d(&qY, q, (uint64_t)N, DH, d, H, DH, nb, n_pitch * d, FB_CH, 64));
+  LCASR_TRY(make_tmap_4d(&oY, d_out, (uint64_t)N, DH, d, H, DH, nb, n_pitch * d, FB_CH, 64));
+  LCASR_TRY(make_tmap_4d(&qX, q, (uint64_t)N, DH, d, H, DH, nb, n_pitch * d, 128, 64));
+  LCASR_TRY(make_tmap_4d(&oX, d_out, (uint64_t)N, DH, d, H, DH, nb, n_pitch * d, 128, 64));
+  LCASR_TRY(make_tmap_4d(&kY, k, (uint64_t)N, DH, d, H, DH, nb, n_pitch * d, FB_CH, 64));
+  LCASR_TRY(make_tmap_4d(&vY, v, (uint64_t)N, DH, d, H, DH, nb, n_pitch * d, FB_CH, 64));
+  static PerDeviceFlag attr_set;
+  int attr_dev = 0;
+  if (attr_set.needs_set(&attr_dev)) {
+    LCASR_CUDA(cudaFuncSetAttribute(attn_bwd_flash_kernel<DH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    LCASR_CUDA(cudaFuncSetAttribute(attn_bwd_flash_kernel<DH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set.mark(attr_dev);
+  }
+  FbParams p;
+  p.N = N; p.Npad = Npad; p.tok_stride = d; p.rec_stride = n_pitch * d; p.H = H;
+  p.scale = 1.0f / sqrtf((float)DH);
+  p.c_log2 = p.scale * 1.4426950408889634f;
+  p.stats = stats;
+  const dim3 grid((unsigned)ceil_div(N, (int64_t)128), (unsigned)H, (unsigned)nb);
+  p.out1 = (bf16*)dv; p.out2 = (bf16*)dk;
+  attn_bwd_flash_kernel<DH, 0><<<grid, FB_THREADS, Cfg::SMEM, st>>>(kX, vX, qY, oY, p);
+  LCASR_LAUNCH_CHECK();
+  p.out1 = (bf16*)dq; p.out2 = nullptr;
+  attn_bwd_flash_kernel<DH, 1><<<grid, FB_THREADS, Cfg::SMEM, st>>>(qX, oX, kY, vY, p);
+  LCASR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lcasr_attention_bwd_flash(const void* q, const void* k, const void* v, const void* o, const void* d_out,
+                                         const float* lse2, int nb, int64_t N, int64_t n_pitch, int64_t lse_pitch, int H, int Dh,
+                                         void* dq, void* dk, void* dv, void* workspace, int64_t workspace_bytes, void* stream) {
+  LCASR_CHECK_ARG(q && k && v && o && d_out && lse2 && dq && dk && dv && workspace, "attention_bwd_flash: NULL argument");
+  LCASR_CHECK_ARG(nb > 0 && N > 0 && H > 0 && n_pitch >= N && lse_pitch >= N, "attention_bwd_flash: bad shape");
+  LCASR_CHECK_ARG(Dh == 64 || Dh == 128, "attention_bwd_flash: head_dim %d not in {64, 128} (use the materialised form)", Dh);
+  LCASR_CHECK_ARG(N < ((int64_t)1 << 30), "attention_bwd_flash: N too large");
+  LCASR_CHECK_ARG(workspace_bytes >= lcasr_attention_bwd_flash_workspace_bytes(nb, N, H), "attention_bwd_flash: workspace too small");
+  LCASR_CHECK_ARG(((uintptr_t)workspace & 15) == 0, "attention_bwd_flash: workspace must be 16-byte aligned");
+  const int64_t Npad = round_up(N, (int64_t)128);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = (int64_t)nb * Npad * H;
+  attn_bwd_prep_kernel<<<(unsigned)ceil_div(total, (int64_t)256), 256, 0, st>>>((const bf16*)o, (const bf16*)d_out, lse2, nb, N, Npad,
+                                                                              n_pitch, lse_pitch, H, Dh, 1.0f / sqrtf((float)Dh),
+                                                                              (float2*)workspace);
+  LCASR_LAUNCH_CHECK();
+  if (Dh == 128)
+    return launch_attn_bwd_flash<128>(q, k, v, d_out, nb, N, n_pitch, H, (const float2*)workspace, Npad, dq, dk, dv, st);
+  return launch_attn_bwd_flash<64>(q, k, v, d_out, nb, N, n_pitch, H, (const float2*)workspace, Npad, dq, dk, dv, st);
 }

@@ -6,6 +6,8 @@ parameters and of the residual stream.  No CPU fallback.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 
 import torch
@@ -80,9 +82,15 @@ def mask_rows_(x, lengths, B: int, N: int):
     return x
 
 
-def attention_bwd(q, k, v, o, do, lse, chunk_b: int = 0, fused_pds: bool = True, lens=None):
+def flash_applies(Dh: int) -> bool:
+    """the flash-style backward kernel exists for head dims 64 and 128; LCASR_ATTN_BWD_FLASH=0 selects the materialised form"""
+    return Dh in (64, 128) and os.environ.get("LCASR_ATTN_BWD_FLASH", "1") != "0"
+
+
+def attention_bwd(q, k, v, o, do, lse, chunk_b: int = 0, fused_pds: bool = True, lens=None, flash=None):
     """Backward of softmax(q k^T / sqrt(Dh)) v from the saved output and log-sum-exp.
-    q,k,v,o,do bf16 [B,N,H,Dh]; returns dq, dk, dv (same layout).  P and dS are materialised per group of
+    q,k,v,o,do bf16 [B,N,H,Dh]; returns dq, dk, dv (same layout).  Head dims 64 / 128 (flash=None: automatic): the
+    flash-style kernels (lcasr_attention_bwd_flash: O(N) memory).  Otherwise P and dS are materialised per group of
     recordings ([b,H,N,N] bf16 each, sized to stay L2-resident) and every product is one batched tcgen05 GEMM.
     `lens` (host ints, tokens per recording): padded batch — recording b is differentiated as the n_b x n_b problem of
     its valid tokens (masked keys have P = 0 and the output rows of padded queries are zeroed by the caller, so their
@@ -94,6 +102,17 @@ def attention_bwd(q, k, v, o, do, lse, chunk_b: int = 0, fused_pds: bool = True,
     ragged = lens is not None and any(int(n) != N for n in lens)
     alloc = torch.zeros_like if ragged else torch.empty_like
     dq, dk, dv = alloc(q), alloc(q), alloc(q)
+    if flash_applies(Dh) if flash is None else flash:
+        # flash-style backward: no [N, N] tensor reaches memory (two launches: dk / dv, then dq)
+        groups = [(b, 1, int(lens[b])) for b in range(B)] if ragged else [(0, B, N)]
+        for b0, nb, n in groups:
+            if n <= 0:
+                continue
+            ws_bytes = int(L.lib.lcasr_attention_bwd_flash_workspace_bytes(nb, n, H))
+            ws = torch.empty(ws_bytes // 8, 2, dtype=torch.float32, device=dev)
+            L.call("lcasr_attention_bwd_flash", L.ptr(q[b0:]), L.ptr(k[b0:]), L.ptr(v[b0:]), L.ptr(o[b0:]), L.ptr(do[b0:]),
+                   L.ptr(lse[b0:]), nb, n, N, N, H, Dh, L.ptr(dq[b0:]), L.ptr(dk[b0:]), L.ptr(dv[b0:]), L.ptr(ws), ws_bytes, _s())
+        return dq, dk, dv
     Dvec = torch.empty(B, H, N, dtype=torch.float32, device=dev)
     L.call("lcasr_rowdot", L.ptr(do), L.ptr(o), B, N, H, Dh, L.ptr(Dvec), _s())
     if chunk_b <= 0:  # P + dS of one chunk ~ 96 MB
