@@ -16,6 +16,7 @@
 // Tensor-bound: algorithmic FLOPs = 2*M*N*K per batch entry.
 #include "common.cuh"
 #include <cstdlib>
+#include <mutex>
 #include "sm100_ptx.cuh"
 
 namespace lcasr {
@@ -577,18 +578,24 @@ attn_bwd_pds_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 //       P^T = exp2(S^T c - lse_i), dS^T = P^T o (dP^T - D_i) scale   -> bf16, written over the accumulators they came from
 //       dV_j += P^T dO_i, dK_j += dS^T Q_i            (TS products: A from tensor memory, B = the same chunk tiles read
 //                                                      as MN-major operands — no transposed copies)
-//   MODE 1 (dQ):     a CTA owns 128 QUERIES (Q_i, dO_i resident) and streams 64-key chunks (K_j, V_j):
+//   MODE 1 (dQ):     a CTA owns 128 QUERIES and streams 64-key chunks (K_j, V_j):
 //       S = Q_i K_j^T, dP = dO_i V_j^T, dS as above (lane = query: lse / D are per-thread scalars), dQ_i += dS K_j.
+//       Q_i and dO_i live in TENSOR memory (copied there once by the softmax warps), so every product of this mode is a TS
+//       product: an SS product with a 64-wide N re-reads the 128-row A tile from shared memory for every K = 16 step
+//       (6 KB per 32 tensor cycles: shared-memory-bound, MODE 0 pays that for S^T / dP^T).
 // The transposed formulation of MODE 0 is what lets P^T / dS^T be TS operands: tensor memory lanes must be the M
 // dimension (keys) of the dV / dK products.  TMEM: accumulators [0, 2 Dh) (MODE 1: [0, Dh)), then 2 x 64 columns of
-// S and 2 x 64 of dP.  Per-row statistics come packed as float2 {lse2, D * scale} per (recording, head, token), padded
-// to a multiple of 128 tokens with {+inf, 0} (P = dS = 0 for tokens that do not exist) by attn_bwd_prep_kernel.
-// Warps 0-7: softmax (two per TMEM lane quarter, 32 columns each), warp 8: TMA producer, warp 9: MMA issuer.
-constexpr int FB_THREADS = 320, FB_STAGES = 3, FB_CH = 64;
-template <int DH> struct FbCfg {
+// S and 2 x 64 of dP (MODE 1: then Q_i and dO_i, Dh / 2 columns each).  Per-row statistics come packed as float2
+// {lse2, D * scale} per (recording, head, token), padded to a multiple of 128 tokens with {+inf, 0} (P = dS = 0 for tokens
+// that do not exist) by attn_bwd_prep_kernel.
+// Warps 0-15: softmax (four per TMEM lane quarter, 16 columns each — the first version had 8 and its tensor pipe idled half
+// the time: ncu showed 270 instructions per warp and chunk taking ~1300 cycles, pure latency), warp 16: TMA producer,
+// warp 17: MMA issuer.
+constexpr int FB_SOFT_WARPS = 16, FB_THREADS = 32 * FB_SOFT_WARPS + 64, FB_STAGES = 3, FB_CH = 64;
+template <int DH, int MODE> struct FbCfg {
   static constexpr int SUB = DH / 64;
-  static constexpr int X_BYTES = SUB * 128 * 128;          // one resident tile: [128 rows][DH] as SUB swizzled boxes
-  static constexpr int Y_BYTES = SUB * FB_CH * 128;        // one streamed tile: [64 rows][DH]
+  static constexpr int X_BYTES = MODE == 0 ? SUB * 128 * 128 : 0;  // one resident tile: [128 rows][DH] as SUB swizzled boxes
+  static constexpr int Y_BYTES = SUB * FB_CH * 128;                // one streamed tile: [64 rows][DH]
   static constexpr int STAGE_BYTES = 2 * Y_BYTES;
   static constexpr int VEC_BYTES = FB_CH * 8;
   static constexpr int SMEM = 2 * X_BYTES + FB_STAGES * STAGE_BYTES + FB_STAGES * VEC_BYTES + 1024;
@@ -601,11 +608,13 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src,
 
 struct FbParams {
   int64_t N, Npad;        // valid tokens; padded length of the statistics rows
-  int64_t tok_stride;     // elements between consecutive tokens of an output tensor (H * Dh)
-  int64_t rec_stride;     // elements between recordings of an output tensor
+  int64_t tok_stride;     // elements between consecutive tokens of a [.., N, H, Dh] tensor (H * Dh)
+  int64_t rec_stride;     // elements between recordings
   int H;
   float c_log2, scale;    // scale * log2(e), scale
   const float2* stats;    // [nb, H, Npad]
+  const bf16* x1;         // MODE 1: q and dO (copied to tensor memory by the softmax warps)
+  const bf16* x2;
   bf16* out1;             // MODE 0: dV, MODE 1: dQ
   bf16* out2;             // MODE 0: dK
 };
@@ -614,7 +623,7 @@ template <int DH, int MODE>
 __global__ void __launch_bounds__(FB_THREADS, 1)
 attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
                       const __grid_constant__ CUtensorMap tmY1, const __grid_constant__ CUtensorMap tmY2, FbParams p) {
-  using Cfg = FbCfg<DH>;
+  using Cfg = FbCfg<DH, MODE>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[1 + 2 * FB_STAGES + 2 + 2 + 1];
   __shared__ uint32_t tmem_slot;
@@ -628,7 +637,7 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_con
   auto full_bar = [&](int s) { return bar0 + 8u * (1 + s); };
   auto empty_bar = [&](int s) { return bar0 + 8u * (1 + FB_STAGES + s); };
   auto s_full = [&](int u) { return bar0 + 8u * (1 + 2 * FB_STAGES + u); };      // S, dP of a chunk retired
-  auto p_full = [&](int u) { return bar0 + 8u * (1 + 2 * FB_STAGES + 2 + u); };  // P / dS written (8 warps)
+  auto p_full = [&](int u) { return bar0 + 8u * (1 + 2 * FB_STAGES + 2 + u); };  // P / dS written (all softmax warps)
   const uint32_t done_bar = bar0 + 8u * (1 + 2 * FB_STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -636,16 +645,19 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_con
   const int n_chunks = (int)((p.N + FB_CH - 1) / FB_CH);
   constexpr int ACC_COLS = MODE == 0 ? 2 * DH : DH;
   constexpr int S_COL = ACC_COLS, DP_COL = ACC_COLS + 128;
+  constexpr int X1_COL = ACC_COLS + 256, X2_COL = X1_COL + DH / 2;  // MODE 1: bf16 Q_i, dO_i
+  static_assert(MODE == 0 ? ACC_COLS + 256 <= 512 : X2_COL + DH / 2 <= 512, "tensor memory budget");
 
-  if (warp == 8 && lane == 0) {
-    prefetch_tensormap(&tmX1); prefetch_tensormap(&tmX2); prefetch_tensormap(&tmY1); prefetch_tensormap(&tmY2);
-    mbar_init(x_full, 1);
+  if (warp == FB_SOFT_WARPS && lane == 0) {
+    if (MODE == 0) { prefetch_tensormap(&tmX1); prefetch_tensormap(&tmX2); }
+    prefetch_tensormap(&tmY1); prefetch_tensormap(&tmY2);
+    mbar_init(x_full, MODE == 0 ? 1 : FB_SOFT_WARPS);
     for (int s = 0; s < FB_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int u = 0; u < 2; ++u) { mbar_init(s_full(u), 1); mbar_init(p_full(u), 8); }
+    for (int u = 0; u < 2; ++u) { mbar_init(s_full(u), 1); mbar_init(p_full(u), FB_SOFT_WARPS); }
     mbar_init(done_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 9) {
+  if (warp == FB_SOFT_WARPS + 1) {
     tmem_alloc(smem_u32(&tmem_slot), 512);
     tmem_relinquish();
   }
@@ -655,13 +667,15 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_con
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
   const float2* stats_row = p.stats + ((int64_t)b * p.H + h) * p.Npad;
 
-  if (warp == 8) {
+  if (warp == FB_SOFT_WARPS) {
     if (lane == 0) {  // ------------------------- TMA producer -------------------------
-      mbar_arrive_expect_tx(x_full, 2 * Cfg::X_BYTES);
+      if (MODE == 0) {
+        mbar_arrive_expect_tx(x_full, 2 * Cfg::X_BYTES);
 #pragma unroll
-      for (int i = 0; i < Cfg::SUB; ++i) {
-        tma_load_4d(x1_smem + i * 16384, &tmX1, x_full, i * 64, x_row0, h, b);
-        tma_load_4d(x2_smem + i * 16384, &tmX2, x_full, i * 64, x_row0, h, b);
+        for (int i = 0; i < Cfg::SUB; ++i) {
+          tma_load_4d(x1_smem + i * 16384, &tmX1, x_full, i * 64, x_row0, h, b);
+          tma_load_4d(x2_smem + i * 16384, &tmX2, x_full, i * 64, x_row0, h, b);
+        }
       }
       int stage = 0; uint32_t phase = 0;
       for (int c = 0; c < n_chunks; ++c) {
@@ -676,7 +690,7 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_con
         if (++stage == FB_STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == FB_SOFT_WARPS + 1) {
     // ------------------------- MMA issuer (converged warp, one elected lane issues) -------------------------
     constexpr uint32_t idesc_s = make_idesc_bf16_mn(128, FB_CH, 0, 0);
     constexpr uint32_t idesc_acc = make_idesc_bf16_mn(128, DH, 0, 1);  // A from tensor memory, B MN-major
@@ -684,33 +698,39 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_con
 #pragma unroll
       for (int kk = 0; kk < DH / 16; ++kk) {
         const int sub = kk / 4, within = kk % 4;
-        umma_f16_ss(tmem_base + S_COL + u * FB_CH, make_smem_desc_kmajor(x1_smem + sub * 16384, 1024, kLayoutSW128) + 2 * within,
-                    make_smem_desc_kmajor(y1_smem(stage) + sub * 8192, 1024, kLayoutSW128) + 2 * within, idesc_s, kk != 0);
+        const uint64_t bd = make_smem_desc_kmajor(y1_smem(stage) + sub * 8192, 1024, kLayoutSW128) + 2 * within;
+        if (MODE == 0)
+          umma_f16_ss(tmem_base + S_COL + u * FB_CH, make_smem_desc_kmajor(x1_smem + sub * 16384, 1024, kLayoutSW128) + 2 * within, bd,
+                      idesc_s, kk != 0);
+        else umma_f16_ts(tmem_base + S_COL + u * FB_CH, tmem_base + X1_COL + kk * 8, bd, idesc_s, kk != 0);
       }
 #pragma unroll
       for (int kk = 0; kk < DH / 16; ++kk) {
         const int sub = kk / 4, within = kk % 4;
-        umma_f16_ss(tmem_base + DP_COL + u * FB_CH, make_smem_desc_kmajor(x2_smem + sub * 16384, 1024, kLayoutSW128) + 2 * within,
-                    make_smem_desc_kmajor(y2_smem(stage) + sub * 8192, 1024, kLayoutSW128) + 2 * within, idesc_s, kk != 0);
+        const uint64_t bd = make_smem_desc_kmajor(y2_smem(stage) + sub * 8192, 1024, kLayoutSW128) + 2 * within;
+        if (MODE == 0)
+          umma_f16_ss(tmem_base + DP_COL + u * FB_CH, make_smem_desc_kmajor(x2_smem + sub * 16384, 1024, kLayoutSW128) + 2 * within, bd,
+                      idesc_s, kk != 0);
+        else umma_f16_ts(tmem_base + DP_COL + u * FB_CH, tmem_base + X2_COL + kk * 8, bd, idesc_s, kk != 0);
       }
     };
-    // bf16 operand columns of a chunk: the softmax warp of column half hc writes its 32 values as 16 packed columns at the
-    // START of its own fp32 range (never over columns another warp may still have to read): k-step kk -> (kk/2)*32 + (kk%2)*8
+    // bf16 operand columns of a chunk: the softmax warp of column quarter cq writes its 16 values as 8 packed columns at the
+    // START of its own fp32 range (never over columns another warp may still have to read): k-step kk -> column kk * 16
     auto issue_acc = [&](int stage, int u, bool accumulate) {
       if (MODE == 0) {
 #pragma unroll
         for (int kk = 0; kk < FB_CH / 16; ++kk)  // dV += P^T dO
-          umma_f16_ts(tmem_base, tmem_base + S_COL + u * FB_CH + (kk >> 1) * 32 + (kk & 1) * 8,
-                      make_smem_desc_mnmajor(y2_smem(stage)) + kk * (2048 >> 4), idesc_acc, (accumulate || kk != 0) ? 1u : 0u);
+          umma_f16_ts(tmem_base, tmem_base + S_COL + u * FB_CH + kk * 16, make_smem_desc_mnmajor(y2_smem(stage)) + kk * (2048 >> 4),
+                      idesc_acc, (accumulate || kk != 0) ? 1u : 0u);
 #pragma unroll
         for (int kk = 0; kk < FB_CH / 16; ++kk)  // dK += dS^T Q
-          umma_f16_ts(tmem_base + DH, tmem_base + DP_COL + u * FB_CH + (kk >> 1) * 32 + (kk & 1) * 8,
-                      make_smem_desc_mnmajor(y1_smem(stage)) + kk * (2048 >> 4), idesc_acc, (accumulate || kk != 0) ? 1u : 0u);
+          umma_f16_ts(tmem_base + DH, tmem_base + DP_COL + u * FB_CH + kk * 16, make_smem_desc_mnmajor(y1_smem(stage)) + kk * (2048 >> 4),
+                      idesc_acc, (accumulate || kk != 0) ? 1u : 0u);
       } else {
 #pragma unroll
         for (int kk = 0; kk < FB_CH / 16; ++kk)  // dQ += dS K
-          umma_f16_ts(tmem_base, tmem_base + DP_COL + u * FB_CH + (kk >> 1) * 32 + (kk & 1) * 8,
-                      make_smem_desc_mnmajor(y1_smem(stage)) + kk * (2048 >> 4), idesc_acc, (accumulate || kk != 0) ? 1u : 0u);
+          umma_f16_ts(tmem_base, tmem_base + DP_COL + u * FB_CH + kk * 16, make_smem_desc_mnmajor(y1_smem(stage)) + kk * (2048 >> 4),
+                      idesc_acc, (accumulate || kk != 0) ? 1u : 0u);
       }
     };
     mbar_wait(x_full, 0);
@@ -739,26 +759,48 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_con
     __syncwarp();
   } else {
     // ------------------------- softmax warps -------------------------
-    const int lq = warp & 3, hc = warp >> 2;
+    const int lq = warp & 3, cq = warp >> 2;  // TMEM lane quarter (== warp_id % 4), column quarter of a chunk
     const uint32_t t_lane = tmem_base + ((uint32_t)(lq * 32) << 16);
+    const int64_t row = (int64_t)x_row0 + lq * 32 + lane;
     float lse_r = 0.f, dsc_r = 0.f;  // MODE 1: this lane's query row
     if (MODE == 1) {
-      const float2 st = stats_row[x_row0 + lq * 32 + lane];  // padded to a multiple of 128 rows
+      const float2 st = stats_row[row];  // padded to a multiple of 128 rows
       lse_r = st.x; dsc_r = st.y;
+      // Q_i and dO_i of this lane's row -> tensor memory (bf16 pairs): this warp's quarter of the head dim
+      constexpr int CW = DH / 4;  // elements per warp
+      const int64_t off = (int64_t)b * p.rec_stride + row * p.tok_stride + (int64_t)h * DH + cq * CW;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const bf16* src = (t == 0 ? p.x1 : p.x2) + off;
+        uint32_t w[CW / 2];
+#pragma unroll
+        for (int g = 0; g < CW / 8; ++g) {
+          uint4 v4 = make_uint4(0u, 0u, 0u, 0u);
+          if (row < p.N) v4 = *reinterpret_cast<const uint4*>(src + 8 * g);
+          w[4 * g] = v4.x; w[4 * g + 1] = v4.y; w[4 * g + 2] = v4.z; w[4 * g + 3] = v4.w;
+        }
+        const uint32_t dst = t_lane + (t == 0 ? X1_COL : X2_COL) + cq * (CW / 2);
+        if constexpr (CW / 2 == 16) tmem_st_32x32b_x16(dst, *reinterpret_cast<uint32_t(*)[16]>(&w[0]));
+        else tmem_st_32x32b_x8(dst, *reinterpret_cast<uint32_t(*)[8]>(&w[0]));
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(x_full);
     }
     for (int c = 0; c < n_chunks; ++c) {
       const int u = c & 1, stage = c % FB_STAGES;
       if (MODE == 0) mbar_wait(full_bar(stage), (c / FB_STAGES) & 1);  // the statistics of this chunk (already complete)
       mbar_wait(s_full(u), (c >> 1) & 1);
       tc_fence_after();
-      uint32_t s[32], dp[32];
-      tmem_ld_32x32b_x32(t_lane + S_COL + u * FB_CH + hc * 32, s);
-      tmem_ld_32x32b_x32(t_lane + DP_COL + u * FB_CH + hc * 32, dp);
+      uint32_t s[16], dp[16];
+      tmem_ld_32x32b_x16(t_lane + S_COL + u * FB_CH + cq * 16, s);
+      tmem_ld_32x32b_x16(t_lane + DP_COL + u * FB_CH + cq * 16, dp);
       tmem_wait_ld();
-      uint32_t pk[16], dk[16];
-      const float2* vec = reinterpret_cast<const float2*>(smem_raw + (vec0 - smem_u32(smem_raw)) + stage * Cfg::VEC_BYTES) + hc * 32;
+      uint32_t pk[8], dk[8];
+      const float2* vec = reinterpret_cast<const float2*>(smem_raw + (vec0 - smem_u32(smem_raw)) + stage * Cfg::VEC_BYTES) + cq * 16;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < 8; ++i) {
         float l0 = lse_r, l1 = lse_r, d0 = dsc_r, d1 = dsc_r;
         if (MODE == 0) {
           const float4 v2 = *reinterpret_cast<const float4*>(vec + 2 * i);  // two queries' {lse, D scale}: broadcast read
@@ -772,29 +814,28 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_con
         pk[i] = *reinterpret_cast<uint32_t*>(&pp);
         dk[i] = *reinterpret_cast<uint32_t*>(&gg);
       }
-      if (MODE == 0) tmem_st_32x32b_x16(t_lane + S_COL + u * FB_CH + hc * 32, pk);
-      tmem_st_32x32b_x16(t_lane + DP_COL + u * FB_CH + hc * 32, dk);
+      if (MODE == 0) tmem_st_32x32b_x8(t_lane + S_COL + u * FB_CH + cq * 16, pk);
+      tmem_st_32x32b_x8(t_lane + DP_COL + u * FB_CH + cq * 16, dk);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(u));
     }
-    // ---- epilogue: this warp's lane quarter, column half hc of every accumulator ----
+    // ---- epilogue: this warp's lane quarter, column quarter cq of every accumulator ----
     mbar_wait(done_bar, 0);
     tc_fence_after();
-    const int64_t row = (int64_t)x_row0 + lq * 32 + lane;
 #pragma unroll
     for (int a = 0; a < (MODE == 0 ? 2 : 1); ++a) {
       bf16* outp = (a == 0 ? p.out1 : p.out2) + (int64_t)b * p.rec_stride + row * p.tok_stride + (int64_t)h * DH;
 #pragma unroll
       for (int cc = 0; cc < DH / 64; ++cc) {
-        const int col = hc * (DH / 2) + cc * 32;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_lane + a * DH + col, r);
+        const int col = cq * (DH / 4) + cc * 16;
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_lane + a * DH + col, r);
         tmem_wait_ld();
         if (row < p.N) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < 2; ++g) {
             float y[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(r[8 * g + i]);
@@ -806,7 +847,7 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == FB_SOFT_WARPS + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -1042,10 +1083,31 @@ extern "C" int64_t lcasr_attention_bwd_flash_workspace_bytes(int nb, int64_t N, 
   return (int64_t)nb * H * round_up(N, (int64_t)128) * 8;
 }
 
+// one side stream + fork / join events per device (created on first use; LCASR_ATTN_BWD_ONE_STREAM=1: both launches in order)
+struct FbSide { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static FbSide* fb_side() {
+  static const bool off = getenv("LCASR_ATTN_BWD_ONE_STREAM") != nullptr;
+  if (off) return nullptr;
+  static FbSide sides[64];
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  FbSide& s = sides[dev];
+  if (!s.stream) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+      s = FbSide();
+      return nullptr;
+    }
+  }
+  return &s;
+}
+
 template <int DH>
 static int launch_attn_bwd_flash(const void* q, const void* k, const void* v, const void* d_out, int nb, int64_t N, int64_t n_pitch,
                                  int H, const float2* stats, int64_t Npad, void* dq, void* dk, void* dv, cudaStream_t st) {
-  using Cfg = FbCfg<DH>;
   const int64_t d = (int64_t)H * DH;
   CUtensorMap kX, vX, qY, oY, qX, oX, kY, vY;
   LCASR_TRY(make_tmap_4d(&kX, k, (uint64_t)N, DH, d, H, DH, nb, n_pitch * d, 128, 64));
@@ -1059,8 +1121,8 @@ static int launch_attn_bwd_flash(const void* q, const void* k, const void* v, co
   static PerDeviceFlag attr_set;
   int attr_dev = 0;
   if (attr_set.needs_set(&attr_dev)) {
-    LCASR_CUDA(cudaFuncSetAttribute(attn_bwd_flash_kernel<DH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    LCASR_CUDA(cudaFuncSetAttribute(attn_bwd_flash_kernel<DH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    LCASR_CUDA(cudaFuncSetAttribute(attn_bwd_flash_kernel<DH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FbCfg<DH, 0>::SMEM));
+    LCASR_CUDA(cudaFuncSetAttribute(attn_bwd_flash_kernel<DH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FbCfg<DH, 1>::SMEM));
     attr_set.mark(attr_dev);
   }
   FbParams p;
@@ -1068,13 +1130,27 @@ static int launch_attn_bwd_flash(const void* q, const void* k, const void* v, co
   p.scale = 1.0f / sqrtf((float)DH);
   p.c_log2 = p.scale * 1.4426950408889634f;
   p.stats = stats;
+  p.x1 = (const bf16*)q; p.x2 = (const bf16*)d_out;
   const dim3 grid((unsigned)ceil_div(N, (int64_t)128), (unsigned)H, (unsigned)nb);
+  // the two launches are independent: the dQ kernel goes to a side stream so that its CTAs fill the last wave of the dK / dV
+  // kernel (768 CTAs on 148 SMs at the training config: 5.19 waves each, 10.4 together instead of 6 + 6)
+  FbSide* side = fb_side();
+  cudaStream_t st_b = st;
+  if (side) {
+    LCASR_CUDA(cudaEventRecord(side->fork, st));
+    LCASR_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    st_b = side->stream;
+  }
   p.out1 = (bf16*)dv; p.out2 = (bf16*)dk;
-  attn_bwd_flash_kernel<DH, 0><<<grid, FB_THREADS, Cfg::SMEM, st>>>(kX, vX, qY, oY, p);
+  attn_bwd_flash_kernel<DH, 0><<<grid, FB_THREADS, FbCfg<DH, 0>::SMEM, st>>>(kX, vX, qY, oY, p);
   LCASR_LAUNCH_CHECK();
   p.out1 = (bf16*)dq; p.out2 = nullptr;
-  attn_bwd_flash_kernel<DH, 1><<<grid, FB_THREADS, Cfg::SMEM, st>>>(qX, oX, kY, vY, p);
+  attn_bwd_flash_kernel<DH, 1><<<grid, FB_THREADS, FbCfg<DH, 1>::SMEM, st_b>>>(qX, oX, kY, vY, p);
   LCASR_LAUNCH_CHECK();
+  if (side) {
+    LCASR_CUDA(cudaEventRecord(side->join, side->stream));
+    LCASR_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+  }
   return 0;
 }
 
