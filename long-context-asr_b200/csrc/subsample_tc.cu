@@ -52,13 +52,15 @@ __device__ __forceinline__ uint32_t bf16x2_bits(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
-// 27 values [a(9) | b(9) | c(9)] + 5 zeros as four 16-byte chunks of bf16
-__device__ __forceinline__ void tc_store_row(uint8_t* base, int row, const float (&a)[9], const float (&b)[9], const float (&c)[9]) {
+// 27 values [a(9) | b(9) | c(9)] + the two bias columns (e0, e1) + 3 zeros as four 16-byte chunks of bf16
+__device__ __forceinline__ void tc_store_row(uint8_t* base, int row, const float (&a)[9], const float (&b)[9], const float (&c)[9],
+                                             float e0, float e1) {
   float k[32];
 #pragma unroll
   for (int i = 0; i < 9; ++i) { k[i] = a[i]; k[9 + i] = b[i]; k[18 + i] = c[i]; }
+  k[27] = e0; k[28] = e1;
 #pragma unroll
-  for (int i = 27; i < 32; ++i) k[i] = 0.f;
+  for (int i = 29; i < 32; ++i) k[i] = 0.f;
 #pragma unroll
   for (int ch = 0; ch < 4; ++ch) {
     uint4 v;
@@ -70,16 +72,22 @@ __device__ __forceinline__ void tc_store_row(uint8_t* base, int row, const float
   }
 }
 
+// F1C > 0: the conv0 frequency width as a compile-time constant (80 mel bins -> 40): the stencil offsets become immediates and
+// the position -> (row, column) divisions constant divisions (ncu of the first version: 48 % of the 571 M warp instructions at
+// cfg 3 were integer / address arithmetic).  The bias and the 1/2 of SiLU's tanh form ride in the product: A gets two columns
+// of ones (zero for positions outside the conv0 range, whose accumulator is then exactly 0 = SiLU(0): no select), B holds
+// w/2 and b/2 (hi, lo) — the epilogue is h = acc, y = h + h tanh(h): MUFU + FFMA per value.
+template <int F1C>
 __global__ void __launch_bounds__(kTcThreads, 2)
 subsample_conv0_dw_tc_kernel(const float* __restrict__ spec, const float* __restrict__ w0, const float* __restrict__ b0,
                              const float* __restrict__ w1, const float* __restrict__ b1, int F, int64_t T, int C, int64_t T1,
-                             int F1, int64_t T2, int F2, int FW, int MT, bf16* __restrict__ out) {
+                             int F1_rt, int64_t T2, int F2, int FW, int MT, bf16* __restrict__ out) {
+  const int F1 = F1C > 0 ? F1C : F1_rt;
   // MT = M tiles of 128 positions (ceil(9 * F1 / 128)); FW = pitch of the input patch
   extern __shared__ __align__(16) uint8_t tsm[];
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_bias[kTcCG];
-  const int A0W = F1 + 2;
+    const int A0W = F1 + 2;
   const uint32_t raw = smem_u32(tsm);
   const uint32_t base = (raw + 127u) & ~127u;
   uint8_t* sm = tsm + (base - raw);
@@ -116,12 +124,13 @@ subsample_conv0_dw_tc_kernel(const float* __restrict__ spec, const float* __rest
     float wh[9], wl[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      const float w = w0[c * 9 + k];
+      const float w = 0.5f * w0[c * 9 + k];  // exact: the split of w/2 is half the split of w
       wh[k] = __bfloat162float(__float2bfloat16_rn(w));
       wl[k] = w - wh[k];
     }
-    tc_store_row(sB, tid, wh, wh, wl);
-    s_bias[tid] = b0[c];
+    const float bh = 0.5f * b0[c];
+    const float bhh = __bfloat162float(__float2bfloat16_rn(bh));
+    tc_store_row(sB, tid, wh, wh, wl, bhh, bh - bhh);
   }
   // zero padding columns of the conv0 tile (the depthwise conv's left / right padding)
   for (int i = tid; i < kTcA0R * 2 * 32; i += kTcThreads) {
@@ -130,10 +139,12 @@ subsample_conv0_dw_tc_kernel(const float* __restrict__ spec, const float* __rest
   }
   __syncthreads();
   // im2col rows: [x_hi | x_lo | x_hi]
+  const int r_lo = (int)max((int64_t)0, -a0_row0), r_hi = (int)min((int64_t)kTcA0R, T1 - a0_row0);  // conv0 rows that exist
   for (int p = tid; p < MT * 128; p += kTcThreads) {
     float xh[9], xl[9];
-    if (p < npos) {
-      const int r = p / F1, col = p - r * F1;
+    const int r = p / F1, col = p - r * F1;
+    const bool live = p < npos && r >= r_lo && r < r_hi;
+    if (live) {
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -146,7 +157,7 @@ subsample_conv0_dw_tc_kernel(const float* __restrict__ spec, const float* __rest
 #pragma unroll
       for (int k = 0; k < 9; ++k) { xh[k] = 0.f; xl[k] = 0.f; }
     }
-    tc_store_row(sA, p, xh, xl, xh);
+    tc_store_row(sA, p, xh, xl, xh, live ? 1.f : 0.f, live ? 1.f : 0.f);
   }
   fence_proxy_async();   // generic-proxy writes of A / B -> visible to the tensor core's async proxy
   tc_fence_before();
@@ -170,10 +181,6 @@ subsample_conv0_dw_tc_kernel(const float* __restrict__ spec, const float* __rest
   // epilogue: TMEM (lane = position) -> + bias, SiLU, zero outside the conv0 range -> bf16 pairs into the stencil tile
   {
     const int quarter = warp & 3, half = warp >> 2;   // TMEM lane quarter; which 32 of the 64 channels
-    const int r_lo = (int)max((int64_t)0, -a0_row0), r_hi = (int)min((int64_t)kTcA0R, T1 - a0_row0);
-    float bias[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) bias[j] = s_bias[half * 32 + j];
     for (int mt = 0; mt < MT; ++mt) {
       const int p = mt * 128 + quarter * 32 + lane;
       uint32_t acc[32];
@@ -181,14 +188,12 @@ subsample_conv0_dw_tc_kernel(const float* __restrict__ spec, const float* __rest
       tmem_wait_ld();
       if (p < npos) {
         const int r = p / F1, col = p - r * F1;
-        const bool live = r >= r_lo && r < r_hi;
         const int pos = r * A0W + col + 1;
         uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float y0 = live ? silu_fast(__uint_as_float(acc[2 * j]) + bias[2 * j]) : 0.f;
-          const float y1 = live ? silu_fast(__uint_as_float(acc[2 * j + 1]) + bias[2 * j + 1]) : 0.f;
-          pk[j] = bf16x2_bits(y0, y1);
+        for (int j = 0; j < 16; ++j) {  // acc = (conv0 + bias) / 2 =: h; SiLU = h + h tanh(h)
+          const float h0 = __uint_as_float(acc[2 * j]), h1 = __uint_as_float(acc[2 * j + 1]);
+          pk[j] = bf16x2_bits(fmaf(h0, tanh_approx_f(h0), h0), fmaf(h1, tanh_approx_f(h1), h1));
         }
         // the position's row holds 32 channel pairs in 144 bytes: lanes of a warp are consecutive positions, so the 8 lanes
         // of a 16-byte store phase fall into 8 different bank groups; the stencil's reads (all lanes in one row) are contiguous
@@ -256,11 +261,15 @@ int subsample_conv0_dw_tc_launch(const float* spec, const float* w0, const float
   static PerDeviceFlag attr_set;
   int attr_dev = 0;
   if (attr_set.needs_set(&attr_dev)) {
-    LCASR_CUDA(cudaFuncSetAttribute(subsample_conv0_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    LCASR_CUDA(cudaFuncSetAttribute(subsample_conv0_dw_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    LCASR_CUDA(cudaFuncSetAttribute(subsample_conv0_dw_tc_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set.mark(attr_dev);
   }
   dim3 grid((unsigned)ceil_div(T2, kTcTT2), (unsigned)(C / kTcCG), (unsigned)B);
-  subsample_conv0_dw_tc_kernel<<<grid, kTcThreads, smem, st>>>(spec, w0, b0, w1, b1, F, T, C, T1, F1, T2, F2, FW, MT, (bf16*)out);
+  if (F1 == 40)
+    subsample_conv0_dw_tc_kernel<40><<<grid, kTcThreads, smem, st>>>(spec, w0, b0, w1, b1, F, T, C, T1, F1, T2, F2, FW, MT, (bf16*)out);
+  else
+    subsample_conv0_dw_tc_kernel<0><<<grid, kTcThreads, smem, st>>>(spec, w0, b0, w1, b1, F, T, C, T1, F1, T2, F2, FW, MT, (bf16*)out);
   LCASR_LAUNCH_CHECK();
   return 0;
 }
