@@ -717,6 +717,14 @@ def main():
                 "share_of_step": (ms[3] / args.steps) / ms_per_step,
                 "gemm_tflops": gemm_flops / ((ms[2] / args.steps) / 1e3) / 1e12 if ms[2] > 0 else None,
                 "model_tflops_per_step": flops_forward(cfg, T, N) * B / 1e12}
+    dh = d // cfg["n_heads"]
+    if dh <= 64:
+        # one MUFU.EX2 per score (16 per clock and SM; packed f16x2 / bf16x2 exponentials are two scalar MUFU ops on sm_100a):
+        # at small head dims the exponentials, not the tensor cores, bound the kernel
+        mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+        ceil_tf = 4.0 * dh * 16 * 148 * mhz * 1e6 / 1e12
+        roofline["mufu_ceiling"] = {"tflops": ceil_tf, "frac": achieved / ceil_tf if ceil_tf > 0 else None,
+                                    "what": f"4*Dh FLOPs per exponential, 16 ex2/clk/SM x 148 SMs at {mhz:.0f} MHz"}
 
     line = {"metric": "audio-sec/sec encoder+CTC", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
