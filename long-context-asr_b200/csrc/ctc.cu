@@ -10,6 +10,7 @@
 // Backward: beta recursion run the same way backwards in time writing log(alpha*beta) in place,
 // then a collect kernel (one CTA per frame) scatters into the class axis.
 #include "common.cuh"
+#include "sm100_ptx.cuh"
 #include <cooperative_groups.h>
 #include <cstdlib>
 
@@ -367,9 +368,18 @@ static int launch_cluster(const float* lp, int B, int64_t N, int V, const int64_
 constexpr int kWfTBDefault = 16;
 
 // branch-free lse3: an all -inf input gives exp(-inf) = 0 -> log(0) = -inf, as the branchy form returns
+// ex2 / lg2 in their .ftz forms: __expf / __logf wrap every MUFU in a compare and two predicated multiplies for denormal
+// results / arguments (a third of the recursion's instructions, all on its dependent chain).  Here they cannot matter: the
+// largest term is exp(0) = 1, a denormal term added to >= 1 does not change the fp32 sum, and lg2's argument lies in [1, 3]
+// (or is exactly 0) — the results stay bit-identical to lse3 above (tests/test_gpu_ops.py checks exactly that).
 __device__ __forceinline__ float lse3_nb(float a, float b, float c) {
   const float m = fmaxf(fmaxf(fmaxf(a, b), c), -1e30f);
-  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+  constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+  auto e2 = [](float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
+  const float sum = e2((a - m) * kLog2e) + e2((b - m) * kLog2e) + e2((c - m) * kLog2e);
+  float l;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(sum));
+  return m + l * kLn2;
 }
 
 template <int kWfTB, bool STORE, int MAXT>
@@ -549,6 +559,246 @@ ctc_wavefront_kernel(const float* __restrict__ log_probs, int64_t N, int V, cons
   }
 }
 
+
+// ---- wavefront, third form: ONE warp runs a chunk's recursion out of registers ----------------------------------------
+// ctc_wavefront_kernel above keeps one state per thread: per frame three shared-memory loads, a store and a __syncthreads
+// over six warps — ~520 cycles per frame at 183 states per chunk (12.3 ms for the 1-hour lattice), of which the arithmetic
+// is a fraction.  Here lane l of the compute warp owns SPL consecutive states in registers: the neighbours s-1 / s-2 are
+// registers of the same lane or two warp shuffles from lane l-1; no shared-memory round trip and no CTA barrier remain in
+// the frame loop.  Seven helper warps gather the log-probs of the next batch of frames into a shared-memory ring
+// (lane-major layout: conflict-free) behind a pair of mbarriers, so the compute warp never waits for a global load either.
+// Hand-off between chunks: the same tagged 16-byte records, same arithmetic per state: bit-identical results.
+constexpr int kWwHelpers = 7, kWwThreads = 32 * (1 + kWwHelpers);
+
+template <int kTB, bool STORE, int SPL>
+__global__ void __launch_bounds__(kWwThreads, 1)
+ctc_wavefront_warp_kernel(const float* __restrict__ log_probs, int64_t N, int V, const int64_t* __restrict__ targets, int64_t S_max,
+                          const int32_t* __restrict__ input_lengths, const int64_t* __restrict__ target_lengths, int blank,
+                          int direction, int G, int batch, float* __restrict__ nll, float* __restrict__ store,
+                          float* __restrict__ store_beta, int pregathered, float4* __restrict__ bnd, unsigned epoch) {
+  using namespace ptx;
+  static_assert(kTB <= 32, "one lane per record of a batch");
+  constexpr int CH = 32 * SPL;
+  __shared__ float lps[2][kTB][CH];        // log-prob ring: [slot][frame of the batch][j * 32 + lane]
+  __shared__ float bl[2][kTB][2];          // records of the left chunk
+  __shared__ float fin[CH + 2];            // final state vector (for the loss)
+  __shared__ int labs[CH];
+  __shared__ __align__(8) uint64_t bars[4];  // full[2], empty[2]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int unit = (int)blockIdx.x / G, g = (int)blockIdx.x % G;
+  const bool both = direction == 0;
+  int b = unit;
+  if (both) {
+    direction = unit < batch ? +1 : -1;
+    b = unit % batch;
+    if (direction < 0) { store = store_beta; nll = nullptr; }
+  }
+  const bool beta_adds = !both;
+  const int64_t T = input_lengths ? min((int64_t)input_lengths[b], N) : N;
+  const int64_t S = target_lengths[b];
+  const int Lp = (int)(2 * S + 1), Lp_max = (int)(2 * S_max + 1);
+  if (T <= 0 || T < S) {
+    if (g == 0 && tid == 0 && nll) nll[b] = INFINITY;
+    return;
+  }
+  const int s0 = g * CH;
+  if (s0 >= Lp) return;  // dead chunk
+  const float* lp = log_probs + (int64_t)b * N * V;
+  const int64_t* tgt = targets + (int64_t)b * S_max;
+  float* st = (STORE && store) ? store + (int64_t)b * N * Lp_max : nullptr;
+  auto frame = [&](int64_t step) -> int64_t { return direction > 0 ? step : (T - 1 - step); };
+  auto label_of = [&](int s_) -> int {  // extended label of state s_ (odd states carry targets, in recursion order)
+    if (!(s_ & 1) || s_ >= Lp) return blank;
+    const int64_t li = (s_ - 1) >> 1;
+    return (int)tgt[direction > 0 ? li : (S - 1 - li)];
+  };
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int sl) { return bar0 + 8u * sl; };
+  auto empty_bar = [&](int sl) { return bar0 + 8u * (2 + sl); };
+  for (int i = tid; i < CH; i += kWwThreads) labs[i] = label_of(s0 + i);
+  if (tid == 0) {
+    mbar_init(full_bar(0), kWwHelpers); mbar_init(full_bar(1), kWwHelpers);
+    mbar_init(empty_bar(0), 1); mbar_init(empty_bar(1), 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int64_t n_batches = (T - 1 + kTB - 1) / kTB;  // steps 1 .. T-1
+
+  if (warp > 0) {
+    // ------------------------- helper warps: gather the log-probs of batch k into slot k & 1 -------------------------
+    const int ht = tid - 32;
+    for (int64_t k = 0; k < n_batches; ++k) {
+      const int slot = (int)(k & 1);
+      mbar_wait(empty_bar(slot), (uint32_t)(((k >> 1) & 1) ^ 1));
+      const int64_t t0 = 1 + k * kTB;
+      // all loads of this thread first (independent: their latencies overlap), then the shared-memory stores
+      constexpr int NIT = (kTB * CH + 32 * kWwHelpers - 1) / (32 * kWwHelpers);
+      float v[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int idx = ht + it * 32 * kWwHelpers;
+        const int u = idx / CH, sl = idx - u * CH;
+        const int64_t step = t0 + u;
+        const int s_ = s0 + sl;
+        v[it] = 0.f;
+        if (idx < kTB * CH && s_ < Lp && step < T) {
+          if (STORE && pregathered) v[it] = __ldcg(st + frame(step) * Lp_max + (direction > 0 ? s_ : (Lp - 1 - s_)));
+          else v[it] = __ldg(lp + frame(step) * V + labs[sl]);
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int idx = ht + it * 32 * kWwHelpers;
+        const int u = idx / CH, sl = idx - u * CH;
+        if (idx < kTB * CH) lps[slot][u][(sl % SPL) * 32 + sl / SPL] = v[it];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(slot));
+    }
+    return;
+  }
+
+  // ------------------------- compute warp -------------------------
+  float4* my_bnd = bnd + (int64_t)blockIdx.x * N;
+  const float4* left_bnd = g > 0 ? bnd + (int64_t)(blockIdx.x - 1) * N : nullptr;
+  const float epoch_f = __uint_as_float(epoch);
+  auto try_fetch = [&](int64_t first, int cnt, int slot) -> bool {
+    bool ok = true;
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < cnt) {
+      r = __ldcg(left_bnd + first + lane);
+      ok = __float_as_uint(r.z) == (unsigned)(first + lane + 1) && __float_as_uint(r.w) == epoch;
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (ok && lane < cnt) { bl[slot][lane][0] = r.x; bl[slot][lane][1] = r.y; }
+    __syncwarp();
+    return ok;
+  };
+  auto fetch_blocking = [&](int64_t first, int cnt, int slot) {
+    unsigned spins = 0;
+    uint64_t t_first = 0;
+    while (!try_fetch(first, cnt, slot)) {
+      __nanosleep(64);
+      if ((++spins & 0x3FFF) == 0) {
+        uint64_t now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t_first == 0) t_first = now;
+        else if (now - t_first > 4000000000ull) {
+          if (lane == 0) printf("lcasr_b200: ctc wavefront (warp form) stalled (cta %d waits for steps %lld..)\n", (int)blockIdx.x, (long long)first);
+          asm volatile("trap;");
+        }
+      }
+    }
+  };
+
+  float a[SPL];
+  bool skip[SPL], live[SPL];
+  int so[SPL];
+#pragma unroll
+  for (int j = 0; j < SPL; ++j) {
+    const int s_ = s0 + lane * SPL + j;
+    live[j] = s_ < Lp;
+    skip[j] = false;
+    if (live[j] && (s_ & 1)) {
+      const int64_t li = (s_ - 1) >> 1;
+      const int64_t oi = direction > 0 ? li : (S - 1 - li);
+      if (li >= 1) skip[j] = tgt[direction > 0 ? oi - 1 : oi + 1] != tgt[oi];
+    }
+    so[j] = live[j] ? (direction > 0 ? s_ : (Lp - 1 - s_)) : 0;
+    // ---- step 0 ----
+    float v = -INFINITY;
+    if (live[j]) {
+      const float* row = lp + frame(0) * V;
+      if (s_ == 0) v = row[blank];
+      else if (s_ == 1) v = row[labs[lane * SPL + j]];
+    }
+    a[j] = v;
+    if (STORE && st && live[j]) {
+      float* p = st + frame(0) * Lp_max + so[j];
+      *p = (direction > 0 || !beta_adds) ? v : (*p + v);
+    }
+  }
+  int rslot = 0;
+  if (g > 0 && T > 1) fetch_blocking(0, (int)min((int64_t)kTB, T - 1), 0);
+  for (int64_t k = 0; k < n_batches; ++k) {
+    const int slot = (int)(k & 1);
+    const int64_t t0 = 1 + k * kTB, t1 = min(T, t0 + kTB), n1 = min(T, t1 + kTB);
+    bool next_ready = true;
+    if (g > 0 && n1 > t1) next_ready = try_fetch(t1 - 1, (int)(n1 - t1), rslot ^ 1);  // usually there: the left chunk is ahead
+    mbar_wait(full_bar(slot), (uint32_t)((k >> 1) & 1));
+#pragma unroll
+    for (int u = 0; u < kTB; ++u) {
+      const int64_t step = t0 + u;
+      if (step < t1) {  // warp-uniform
+        float lq[SPL];
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) lq[j] = lps[slot][u][j * 32 + lane];
+        // the left neighbour's last two states at step-1: lane-1's registers, or the left chunk's record for lane 0
+        float p1 = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1), p2 = __shfl_up_sync(0xffffffffu, a[SPL - 2], 1);
+        if (lane == 0) {
+          p1 = g > 0 ? bl[rslot][u][1] : -INFINITY;
+          p2 = g > 0 ? bl[rslot][u][0] : -INFINITY;
+        }
+        if (lane == 31) __stcg(my_bnd + (step - 1), make_float4(a[SPL - 2], a[SPL - 1], __uint_as_float((unsigned)step), epoch_f));
+        float nw[SPL];
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+          const float x1 = j >= 1 ? a[j - 1] : p1;
+          const float x2 = j >= 2 ? a[j - 2] : (j == 1 ? p1 : p2);
+          nw[j] = lse3_nb(a[j], x1, skip[j] ? x2 : -INFINITY) + lq[j];
+        }
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+          a[j] = nw[j];
+          if (STORE && st && live[j]) {
+            float* p = st + frame(step) * Lp_max + so[j];
+            *p = (direction > 0 || !beta_adds) ? nw[j] : (*p + nw[j]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar(slot));
+    if (g > 0 && !next_ready && n1 > t1) fetch_blocking(t1 - 1, (int)(n1 - t1), rslot ^ 1);
+    rslot ^= 1;
+  }
+  if (lane == 31) __stcg(my_bnd + (T - 1), make_float4(a[SPL - 2], a[SPL - 1], __uint_as_float((unsigned)T), epoch_f));
+  if (nll) {  // the chunk that owns state Lp-1 finishes the sample
+    const int sl = Lp - 1;
+    if (sl >= s0 && sl < s0 + CH) {
+      const int loc = sl - s0;
+#pragma unroll
+      for (int j = 0; j < SPL; ++j) fin[2 + lane * SPL + j] = a[j];
+      if (loc == 0 && g > 0) {  // alpha_{T-1}[Lp-2] lives in the left chunk
+        fetch_blocking(T - 1, 1, 0);
+        if (lane == 0) fin[1] = bl[0][0][1];
+      }
+      __syncwarp();
+      if (lane == 0) {
+        const float l1 = fin[2 + loc];
+        const float l2 = Lp > 1 ? fin[2 + loc - 1] : -INFINITY;
+        const float m = fmaxf(l1, l2);
+        nll[b] = m == -INFINITY ? INFINITY : -(m + logf(expf(l1 - m) + expf(l2 - m)));
+      }
+    }
+  }
+}
+
+// states per lane and chunks of the warp form (0: does not apply — the thread-per-state kernel takes the lattice)
+static int ww_plan(int units, int64_t Lp_max, int* G_out) {
+  // MEASURED SLOWER than the thread-per-state form (1-hour lattice 15.7 vs 10.6 ms, N = 16384: 4.9 vs 3.5, cfg 5: 0.62 vs
+  // 0.45): one warp issues ~250 instructions per frame for its six states at an IPC of 0.38 — the six dependent chains do
+  // not overlap as well as six warps do.  Kept behind LCASR_CTC_WF_WARP=1 as the record of the experiment.
+  static const bool on = getenv("LCASR_CTC_WF_WARP") && atoi(getenv("LCASR_CTC_WF_WARP")) == 1;
+  if (!on || units < 1 || units > kNumSMs) return 0;
+  const int G_max = kNumSMs / units;
+  for (int spl : {2, 4, 6, 8}) {
+    const int64_t G = ceil_div(Lp_max, (int64_t)32 * spl);
+    if (G <= G_max && G >= 2) { *G_out = (int)G; return spl; }
+  }
+  return 0;
+}
+
 static int wf_tb() {
   static const int tb = getenv("LCASR_CTC_WF_TB") ? atoi(getenv("LCASR_CTC_WF_TB")) : kWfTBDefault;
   return tb == 8 || tb == 32 ? tb : 16;
@@ -590,6 +840,24 @@ static int launch_wavefront(const float* lp, int B, int64_t N, int V, const int6
   void* args[] = {(void*)&lp, (void*)&N, (void*)&V, (void*)&tg, (void*)&S_max, (void*)&il, (void*)&tl, (void*)&blank, (void*)&dir,
                   (void*)&G, (void*)&batch, (void*)&nll, (void*)&store, (void*)&store_beta, (void*)&pregathered, (void*)&bnd,
                   (void*)&epoch};
+  const bool has_store_w = store != nullptr || store_beta != nullptr;
+  int Gw = 0;
+  const int spl = ww_plan(units, Lp_max, &Gw);
+  if (spl > 0 && Gw <= G) {  // the records fit the workspace sized for G chunks
+    void* wargs[] = {(void*)&lp, (void*)&N, (void*)&V, (void*)&tg, (void*)&S_max, (void*)&il, (void*)&tl, (void*)&blank, (void*)&dir,
+                     (void*)&Gw, (void*)&batch, (void*)&nll, (void*)&store, (void*)&store_beta, (void*)&pregathered, (void*)&bnd,
+                     (void*)&epoch};
+    const void* wfn = nullptr;
+#define LCASR_WW(S_)                                                                                                     \
+  case S_:                                                                                                               \
+    wfn = has_store_w ? (const void*)ctc_wavefront_warp_kernel<16, true, S_> : (const void*)ctc_wavefront_warp_kernel<16, false, S_>; \
+    break;
+    switch (spl) { LCASR_WW(2) LCASR_WW(4) LCASR_WW(6) LCASR_WW(8) default: break; }
+#undef LCASR_WW
+    LCASR_CUDA(cudaLaunchCooperativeKernel(wfn, dim3((unsigned)(units * Gw)), dim3((unsigned)kWwThreads), wargs, 0, st));
+    count_launch();
+    return 0;
+  }
   // cooperative launch: every CTA is resident, so waiting for a neighbour's records always makes progress
   const void* fn = nullptr;
   const bool small = nt <= 256;  // chunks of <= 256 states: up to 255 registers per thread for the look-ahead ring
