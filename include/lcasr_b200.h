@@ -510,6 +510,9 @@ int lcasr_model_set_impl(lcasr_model* m, int gemm_impl, int attn_impl);
  * (merged exactly) whenever a list-schedule model says the last wave would otherwise be mostly idle.  tail_pairs = 0
  * turns that off; tail_pairs > 0 forces a split (key_pieces in 2..4). */
 int lcasr_model_set_attention_tail(lcasr_model* m, int tail_pairs, int key_pieces);
+/* host-only (no GPU needed): the split the automatic mode chooses for B recordings of N tokens, H heads, `sms` SMs
+ * (tail_pairs = 0: none). */
+int lcasr_attention_tail_plan(int B, int64_t N, int H, int sms, int* tail_pairs, int* key_pieces);
 
 /* In-step kernel timing for the roofline report: when enabled, lcasr_model_forward brackets every
  * kernel launch with CUDA events on the launch stream; lcasr_model_get_timing synchronises, returns

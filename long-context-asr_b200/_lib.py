@@ -140,6 +140,7 @@ _SIGNATURES = {
     "lcasr_model_create": [C.POINTER(LcasrConfig), C.POINTER(LcasrWeights), C.POINTER(vp)],
     "lcasr_model_set_impl": [vp, i32, i32],
     "lcasr_model_set_attention_tail": [vp, i32, i32],
+    "lcasr_attention_tail_plan": [i32, i64, i32, i32, vp, vp],
     "lcasr_model_set_timing": [vp, i32],
     "lcasr_model_get_timing": [vp, vp, vp, i32],
     "lcasr_model_forward": [vp, vp, i32, i64, vp, vp, i32, vp, i64, vp],

@@ -166,6 +166,15 @@ extern "C" int lcasr_model_set_impl(lcasr_model* m, int gemm_impl, int attn_impl
   return 0;
 }
 
+// host-only: the plan lcasr_model_forward would choose for (B recordings, N tokens, H heads) on a GPU with `sms` SMs
+extern "C" int lcasr_attention_tail_plan(int B, int64_t N, int H, int sms, int* tail_pairs, int* key_pieces) {
+  LCASR_CHECK_ARG(B > 0 && N > 0 && H > 0 && sms > 0 && tail_pairs && key_pieces, "attention_tail_plan: bad arguments");
+  const lcasr_model::TailPlan tp = plan_attention_tail(B, N, H, sms);
+  *tail_pairs = tp.t;
+  *key_pieces = tp.P;
+  return 0;
+}
+
 extern "C" int lcasr_model_set_attention_tail(lcasr_model* m, int tail_pairs, int key_pieces) {
   LCASR_CHECK_ARG(m, "model_set_attention_tail: NULL model");
   LCASR_CHECK_ARG(tail_pairs <= 0 || (key_pieces >= 2 && key_pieces <= 4), "model_set_attention_tail: key_pieces %d not in 2..4",

@@ -108,3 +108,42 @@ def test_bad_arguments_return_errors_not_crashes():
     assert b"NULL" in L.lib.lcasr_last_error()
     assert L.lib.lcasr_layernorm(None, None, None, 1, 8, 1e-5, 0, None, None, 0, None) == -1
     assert L.lib.lcasr_model_workspace_bytes(None, 1, 100) == -1
+
+
+def test_attention_tail_plan_host_logic():
+    """the wave-quantisation planner of the dense attention launch is pure host code: a split is chosen only
+    where the list-schedule model gains > 1.5 %, never for launches of at most one wave or short key ranges, and the
+    chosen pieces always shorten the modelled makespan"""
+    import ctypes as C
+    import heapq
+    from lcasr_b200 import _lib as L
+
+    def plan(B, N, H, sms=148):
+        t, p = C.c_int(-1), C.c_int(-1)
+        L.call("lcasr_attention_tail_plan", B, N, H, sms, C.byref(t), C.byref(p))
+        return t.value, p.value
+
+    def makespan(W, full, pieces, piece_cost):
+        h = [0.0] * W
+        for _ in range(full):
+            heapq.heapreplace(h, h[0] + 1.0)
+        for _ in range(pieces):
+            heapq.heapreplace(h, h[0] + piece_cost)
+        return max(h)
+
+    assert plan(1, 16384, 24) == (3, 2)      # BASELINE cfg 3: 1536 units = 10.38 waves
+    assert plan(1, 45000, 16) == (1, 4)      # cfg 4: 2816 units = 19.03 waves
+    assert plan(16, 2048, 6) == (5, 4)       # cfg 2
+    assert plan(1, 128, 8) == (0, 0)         # cfg 1: fewer units than SMs
+    assert plan(1, 1024, 24) == (0, 0)       # 8 key tiles: too short to cut
+    assert plan(1, 37888, 1, sms=148) == (0, 0)  # exactly one full wave
+    for B, N, H in ((1, 16384, 24), (1, 45000, 16), (16, 2048, 6), (2, 8192, 12), (3, 6000, 8)):
+        t, P = plan(B, N, H)
+        nq, nkt = -(-N // 256), -(-N // 128)
+        U = B * H * nq
+        if t:
+            assert 1 <= t <= min(8, nq) and 2 <= P <= 4
+            piece = (-(-nkt // P)) / nkt
+            assert makespan(148, U - t * H, t * H * P, piece) < makespan(148, U, 0, 0.0)
+    with pytest.raises(L.LcasrError):
+        plan(0, 16384, 24)
