@@ -147,3 +147,16 @@ def test_attention_tail_plan_host_logic():
             assert makespan(148, U - t * H, t * H * P, piece) < makespan(148, U, 0, 0.0)
     with pytest.raises(L.LcasrError):
         plan(0, 16384, 24)
+
+
+def test_workspace_size_host_functions():
+    """sizes of the caller-owned workspaces are pure host arithmetic"""
+    from lcasr_b200 import _lib as L
+    f = L.lib.lcasr_attention_bwd_flash_workspace_bytes
+    assert f(8, 2048, 6) == 8 * 6 * 2048 * 8          # float2 {lse2, D*scale} per (recording, head, token)
+    assert f(1, 100, 2) == 1 * 2 * 128 * 8            # tokens padded to a multiple of 128
+    assert f(0, 100, 2) == -1
+    g = L.lib.lcasr_ctc_workspace_bytes
+    assert g(1, 45000, 13500, 0) == 148 * 45000 * 16  # 1-hour lattice: one record per (chunk, frame), 148 chunks
+    assert g(8, 2048, 614, 1) == 16 * 9 * 2048 * 16   # cfg 5, alpha and beta concurrently: 16 lattices x 9 chunks
+    assert g(8, 100, 10, 1) == 0                      # 21 states: one chunk, the plain recursion is the same thing
