@@ -355,6 +355,20 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_reg_kernel(const float* __res
     ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += (int64_t)gridDim.x * wpb) {
+    // The row's three phases (statistics of x, the two dy reductions, the output pass) each wait for their own loads and the
+    // registers are full (128, spilling): 16 warps per SM keep too few bytes in flight for HBM (0.58 of the copy rate).
+    // The NEXT row of this warp is therefore pulled into L2 now — a hint, no registers: its loads then cost L2 latency.
+    {
+      const int64_t nrow = row + (int64_t)gridDim.x * wpb;
+      if (nrow < M) {
+        if (lane < NE) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(x + nrow * d) + lane * 128));
+          if (accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(dx + nrow * d) + lane * 128));
+        }
+        if (lane < (NE * (int)sizeof(TDy) + 3) / 4)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(dy + nrow * d) + lane * 128));
+      }
+    }
     // dy is read twice (reduction pass, output pass): the second read hits L1 / L2 and saves NV float4 registers
     auto load_g = [&](int j) -> float4 {
       if constexpr (sizeof(TDy) == 4) {
