@@ -142,16 +142,24 @@ extern "C" int lcasr_model_create(const lcasr_config* cfg, const lcasr_weights* 
   m->w = *w;
   m->layers.assign(w->layers_host, w->layers_host + cfg->n_layers);
   m->w.layers_host = m->layers.data();
-  for (int i = 0; i < lcasr_model::kTailStreams; ++i) {
-    if (cudaStreamCreateWithFlags(&m->tail_streams[i], cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&m->tail_done[i], cudaEventDisableTiming) != cudaSuccess) {
-      delete m;
-      return set_error(LCASR_E_CUDA, "model_create: cannot create the side streams of the attention tail split");
-    }
-  }
-  if (cudaEventCreateWithFlags(&m->tail_fork, cudaEventDisableTiming) != cudaSuccess) {
+  // side streams / events of the attention tail split, on the device that holds the weights (not necessarily the caller's
+  // current device)
+  int prev_dev = 0, w_dev = 0;
+  cudaGetDevice(&prev_dev);
+  w_dev = prev_dev;
+  cudaPointerAttributes pa;
+  if (w->conv0_w && cudaPointerGetAttributes(&pa, w->conv0_w) == cudaSuccess && pa.type == cudaMemoryTypeDevice) w_dev = pa.device;
+  else cudaGetLastError();
+  if (w_dev != prev_dev) cudaSetDevice(w_dev);
+  bool ok = cudaEventCreateWithFlags(&m->tail_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < lcasr_model::kTailStreams; ++i)
+    ok = cudaStreamCreateWithFlags(&m->tail_streams[i], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&m->tail_done[i], cudaEventDisableTiming) == cudaSuccess;
+  if (w_dev != prev_dev) cudaSetDevice(prev_dev);
+  if (!ok) {
+    cudaGetLastError();
     delete m;
-    return set_error(LCASR_E_CUDA, "model_create: cannot create an event");
+    return set_error(LCASR_E_CUDA, "model_create: cannot create the side streams of the attention tail split");
   }
   *out = m;
   return 0;

@@ -425,7 +425,8 @@ class SCConformerXL(nn.Module):
             norm_eps=1e-8 if rms else 1e-5,
             attn_window_left=self.layers[0].attend.fn.left_window, attn_window_right=self.layers[0].attend.fn.right_window)
         handle = L.vp()
-        L.call("lcasr_model_create", C.byref(cfg), C.byref(w), C.byref(handle))
+        with torch.cuda.device(device):  # the handle owns side streams: they must live on the model's device
+            L.call("lcasr_model_create", C.byref(cfg), C.byref(w), C.byref(handle))
         self._handle = handle.value
         self._keepalive = (keep, layers, w)
         self._packed = packed
