@@ -185,6 +185,28 @@ class ASRLinearSCDecoder(_ParamOnly):
 _COMPUTE_DTYPES = {"bf16": torch.bfloat16, "bfloat16": torch.bfloat16, "fp32": torch.float32, "float32": torch.float32}
 
 
+def pack_qkv_rotary_interleaved(qkv: torch.Tensor, H: int, Dh: int) -> torch.Tensor:
+    """Weight rows for the qkv GEMM with the rotary embedding in its epilogue (csrc/gemm_tc.cu, TG_EPI_ROPE).
+    qkv: [3*H*Dh, d] with rows already in [q | k | v] order.  Inside every q / k head the rows are interleaved —
+    new row 2i <- old row i, new row 2i+1 <- old row i + Dh/2 — so that a ``rotate_half`` pair (rotary_emb.py:61-66) is two
+    ADJACENT output columns of one epilogue thread.  q.k is invariant under the common permutation of the head dimension,
+    so attention needs no un-permute; v is left alone."""
+    d = qkv.shape[1]
+    qk = qkv[: 2 * H * Dh].reshape(2 * H, Dh, d)
+    qk_il = torch.stack([qk[:, : Dh // 2], qk[:, Dh // 2:]], dim=2).reshape(2 * H * Dh, d)
+    return torch.cat([qk_il, qkv[2 * H * Dh:]], 0)
+
+
+def pack_glu_blocks(w1: torch.Tensor, b1: torch.Tensor):
+    """pointwise_conv1 rows for the GEMM with ``F.glu`` in its epilogue (TG_EPI_GLU): w1 [2d, d] = [value rows | gate rows]
+    (convolution.py:107-108) becomes 64-row blocks of 32 value channels followed by THEIR 32 gate channels, so that one
+    epilogue warp holds a (value, gate) chunk pair; the bias likewise."""
+    d = w1.shape[0] // 2
+    w = torch.stack([w1[:d].reshape(d // 32, 32, -1), w1[d:].reshape(d // 32, 32, -1)], 1).reshape(2 * d, -1)
+    b = torch.stack([b1[:d].reshape(d // 32, 32), b1[d:].reshape(d // 32, 32)], 1).reshape(2 * d)
+    return w, b
+
+
 class SCConformerXL(nn.Module):
     """Same signature as the reference (sconformer_xl.py:32-64).  One extra, optional kwarg:
     ``compute_dtype`` ('bf16' default: tcgen05 tensor-core path; 'fp32': SIMT fp32 parity mode)."""
@@ -391,18 +413,16 @@ class SCConformerXL(nn.Module):
             put(lw, "qkv_w", mat(qkv)); put(lw, "out_w", mat(sd[p + "attend.fn.out_proj.weight"]))
             # fused-rotary form: inside every q / k head interleave the two rotate_half halves (rotary_emb.py:61-66 pairs
             # (i, i + Dh/2)) so that a rotation pair is two adjacent output columns of the qkv GEMM
-            qk = qkv[: 2 * H * Dh].reshape(2 * H, Dh, d)
-            qk_il = torch.stack([qk[:, : Dh // 2], qk[:, Dh // 2:]], dim=2).reshape(2 * H * Dh, d)
-            put(lw, "qkv_w_il", mat(torch.cat([qk_il, qkv[2 * H * Dh:]], 0)) if cdt == torch.bfloat16 and self.use_rotary else None)
+            put(lw, "qkv_w_il", mat(pack_qkv_rotary_interleaved(qkv, H, Dh)) if cdt == torch.bfloat16 and self.use_rotary else None)
             nw, nb = norm_wb(p + "conv.norm")
             put(lw, "conv_norm_w", nw); put(lw, "conv_norm_b", nb)
             put(lw, "pw1_w", mat(sd[p + "conv.fn.pointwise_conv1.weight"].reshape(2 * d, d))); put(lw, "pw1_b", vec(p + "conv.fn.pointwise_conv1.bias"))
             if cdt == torch.bfloat16 and d % 32 == 0:  # fused-GLU form: 64-row blocks [32 value channels | their 32 gate channels]
                 w1 = sd[p + "conv.fn.pointwise_conv1.weight"].reshape(2 * d, d)
                 b1 = sd[p + "conv.fn.pointwise_conv1.bias"]
-                put(lw, "pw1_w_glu", mat(torch.stack([w1[:d].reshape(d // 32, 32, d), w1[d:].reshape(d // 32, 32, d)], 1).reshape(2 * d, d)))
-                put(lw, "pw1_b_glu", torch.stack([b1[:d].reshape(d // 32, 32), b1[d:].reshape(d // 32, 32)], 1).reshape(2 * d)
-                    .to(device=device, dtype=torch.float32).contiguous())
+                w1g, b1g = pack_glu_blocks(w1, b1)
+                put(lw, "pw1_w_glu", mat(w1g))
+                put(lw, "pw1_b_glu", b1g.to(device=device, dtype=torch.float32).contiguous())
             else:
                 put(lw, "pw1_w_glu", None); put(lw, "pw1_b_glu", None)
             put(lw, "dw_w", vec(p + "conv.fn.depthwise_conv.weight").reshape(d, self.conv_kernel_size).contiguous())
