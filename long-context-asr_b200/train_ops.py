@@ -120,6 +120,13 @@ def attention_bwd(q, k, v, o, do, lse, chunk_b: int = 0, fused_pds: bool = True,
     if ragged:
         chunk_b = 1
     Npad = (N + 7) // 8 * 8
+    need = 2 * chunk_b * H * N * Npad * 2  # P and dS, bf16
+    free, _ = torch.cuda.mem_get_info(dev)
+    if need > free:
+        raise RuntimeError(
+            f"attention backward (materialised form, head_dim {Dh}): P and dS of one recording need {need / 2**30:.1f} GiB "
+            f"([{H}, {N}, {N}] bf16 each) but {free / 2**30:.1f} GiB are free; the flash-style backward (O(N) memory) covers "
+            "head dims 64 and 128 only")
     P = torch.empty(chunk_b * H * N * Npad, dtype=BF, device=dev)
     dS = torch.empty_like(P)
     scale = 1.0 / (Dh ** 0.5)
