@@ -122,6 +122,7 @@ def attention_bwd(q, k, v, o, do, lse, chunk_b: int = 0, fused_pds: bool = True,
     Npad = (N + 7) // 8 * 8
     need = 2 * chunk_b * H * N * Npad * 2  # P and dS, bf16
     free, _ = torch.cuda.mem_get_info(dev)
+    free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)  # blocks the caching allocator can reuse
     if need > free:
         raise RuntimeError(
             f"attention backward (materialised form, head_dim {Dh}): P and dS of one recording need {need / 2**30:.1f} GiB "
