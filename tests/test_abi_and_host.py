@@ -147,6 +147,20 @@ def test_attention_tail_plan_host_logic():
             assert makespan(148, U - t * H, t * H * P, piece) < makespan(148, U, 0, 0.0)
     with pytest.raises(L.LcasrError):
         plan(0, 16384, 24)
+    # random shapes: whatever is chosen stays inside the stated ranges and never lengthens the modelled launch
+    import random
+    rnd = random.Random(5)
+    for _ in range(200):
+        B, H = rnd.randint(1, 16), rnd.choice([1, 2, 6, 8, 12, 16, 24])
+        N, sms = rnd.randint(1, 60000), rnd.choice([74, 132, 148])
+        t, P = plan(B, N, H, sms)
+        nq, nkt = -(-N // 256), -(-N // 128)
+        U = B * H * nq
+        if t == 0:
+            assert P == 0
+            continue
+        assert U > sms and nkt >= 16 and 1 <= t <= min(8, nq) and 2 <= P <= 4 and nkt // P >= 4
+        assert makespan(sms, U - t * H, t * H * P, (-(-nkt // P)) / nkt) < makespan(sms, U, 0, 0.0)
 
 
 def test_workspace_size_host_functions():
