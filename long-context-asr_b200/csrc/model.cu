@@ -85,17 +85,19 @@ Plan make_plan(const lcasr_config& c, int B, int64_t T) {
 // computed as P key-range pieces (exact partial results + the merge kernel of the sequence-parallel path) on side streams:
 // the short CTAs fill the SMs the last wave leaves idle.  Greedy list-schedule model, all candidates (t, P) tried.
 double attention_makespan(int W, int64_t full, double full_cost, int64_t pieces, double piece_cost) {
-  std::vector<double> sm((size_t)W, 0.0);  // a heap of SM-free times
+  // the full-length units are equal, so their greedy assignment is known in closed form (full / W each, the first full % W
+  // SMs one more); only the few pieces are list-scheduled on the heap of SM-free times — planning stays O(pieces log W)
+  // however large the batch is
+  std::vector<double> sm((size_t)W);
+  const int64_t base = full / W, extra = full % W;
+  for (int i = 0; i < W; ++i) sm[(size_t)i] = (double)(base + (i < extra ? 1 : 0)) * full_cost;
   auto cmp = [](double a, double b) { return a > b; };
-  auto run = [&](int64_t n, double cost) {
-    for (int64_t i = 0; i < n; ++i) {
-      std::pop_heap(sm.begin(), sm.end(), cmp);
-      sm.back() += cost;
-      std::push_heap(sm.begin(), sm.end(), cmp);
-    }
-  };
-  run(full, full_cost);
-  run(pieces, piece_cost);
+  std::make_heap(sm.begin(), sm.end(), cmp);
+  for (int64_t i = 0; i < pieces; ++i) {
+    std::pop_heap(sm.begin(), sm.end(), cmp);
+    sm.back() += piece_cost;
+    std::push_heap(sm.begin(), sm.end(), cmp);
+  }
   return *std::max_element(sm.begin(), sm.end());
 }
 
